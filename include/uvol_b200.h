@@ -1,0 +1,99 @@
+/*
+ * uvol_b200.h -- C ABI of libuvol_b200.so, the B200-native UVOL decode path.
+ *
+ * The reference has no single FFI for its V2 path (JS -> WASM inside Web Workers); its contract is
+ * the manifest plus the worker message payloads.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference repo).  Plain pointers and sizes only.
+ *
+ * Ownership: all output arrays are LIBRARY-owned (mirrors the transfer-of-ownership the workers
+ * do with transferable ArrayBuffers, src/lib/DRACOLoader.js:152,449; src/lib/KTX2Loader.js:335,431).
+ * Buffers returned by a *_batch call stay valid until the next *_batch call of the same kind on
+ * the same ctx, or uvol_destroy.  With UVOL_MEM_DEVICE they are device pointers on the ctx's GPU,
+ * with UVOL_MEM_HOST pinned host pointers (the device->host copy is part of the call).
+ *
+ * Errors: functions return 0 or a negative uvol_status; per-item failures are reported in
+ * item.status and never abort the batch (mirrors "a failed frame is simply absent from meshMap",
+ * src/V2/player.ts:429-444, and the worker's {type:'error'} reply, DRACOLoader.js:451-455).
+ * Threading: one ctx per GPU; calls on one ctx must be serialised by the caller; distinct ctxs are
+ * independent (mirrors one decoder instance per worker, DRACOLoader.js:439).
+ * There is no CPU decode path: without a usable CUDA device every call fails with UVOL_ERR_CUDA.
+ */
+#ifndef UVOL_B200_H
+#define UVOL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct uvol_ctx uvol_ctx;
+
+enum uvol_status { UVOL_STATUS_OK = 0, UVOL_STATUS_TRUNCATED = -1, UVOL_STATUS_CORRUPT = -2, UVOL_STATUS_UNSUPPORTED = -3,
+                   UVOL_STATUS_CUDA = -4, UVOL_STATUS_ARG = -5, UVOL_STATUS_IO = -6 };
+enum uvol_memory { UVOL_MEM_DEVICE = 0, UVOL_MEM_HOST = 1 };
+/* Target texture format.  RGBA32 is the parity target (and the reference's own fallback,
+ * src/lib/KTX2Loader.js:682-687). */
+enum uvol_texture_format { UVOL_TEX_RGBA32 = 0 };
+
+/* Result of one geometry frame.  Replaces the Draco worker reply
+ *   {type:'decode', geometry:{index:{array:Uint32Array(F*3)}, attributes:[{name, array:Float32Array(P*itemSize), itemSize}]}}
+ * (src/lib/DRACOLoader.js:449,502,567,584-588); attribute presence follows the semantic lookup at
+ * :523-525 (POSITION, NORMAL, COLOR, TEX_COORD; GENERIC ignored).  All arrays are in Draco point order. */
+typedef struct uvol_geometry {
+    int32_t status;
+    uint32_t num_points;
+    uint32_t num_faces;
+    uint32_t color_components;
+    uint32_t *index;       /* u32[num_faces*3] */
+    float *position;       /* f32[num_points*3] */
+    float *normal;         /* f32[num_points*3] or NULL */
+    float *uv;             /* f32[num_points*2] or NULL */
+    float *color;          /* f32[num_points*color_components] or NULL */
+} uvol_geometry;
+
+/* Result of one KTX2 segment.  Replaces the Basis worker reply
+ *   {type:'transcode', faces:[{mipmaps:[{data, width, height}], ...}], width, height, hasAlpha, format, dfdTransferFn, dfdFlags}
+ * (src/lib/KTX2Loader.js:431,565-578): `data` holds all layers back to back (concat, :565). */
+typedef struct uvol_texture {
+    int32_t status;
+    uint32_t width, height, layers;
+    uint32_t format;       /* uvol_texture_format */
+    uint32_t has_alpha, dfd_transfer, dfd_flags;
+    uint8_t *data;         /* u8[layers * width * height * 4] for RGBA32 */
+    uint64_t bytes;
+} uvol_texture;
+
+/* Timing / traffic of the last batch call on a ctx (CUDA events on the ctx's stream). */
+typedef struct uvol_stats {
+    double host_parse_ms, h2d_ms, device_ms, d2h_ms, total_ms;
+    float stage_ms[16];            /* per-kernel-stage device time; names via uvol_stage_name() */
+    uint32_t num_stages, kernel_launches;
+    uint64_t bytes_in, bytes_out;  /* compressed bytes consumed / final output bytes produced */
+    uint64_t scratch_bytes;
+} uvol_stats;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int uvol_create(int device, uvol_ctx **out);
+void uvol_destroy(uvol_ctx *ctx);
+const char *uvol_last_error(const uvol_ctx *ctx);
+int uvol_get_stats(const uvol_ctx *ctx, uvol_stats *out);
+const char *uvol_stage_name(int kind /*0 geometry, 1 texture, 2 corto*/, int stage);
+int uvol_set_profiling(uvol_ctx *ctx, int enable);   /* per-stage CUDA events on/off (default off) */
+
+/* ---- V2 geometry: replaces DRACOLoader.decodeGeometry -> DRACOWorker 'decode'
+ * (src/lib/DRACOLoader.js:104-187,433-457,470-554) for n files at once; V2Player.decodeDraco
+ * (src/V2/player.ts:325-331) maps frame numbers to files.  data[i]/size[i] = the bytes of one .drc. */
+int uvol_decode_draco_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n,
+                            int memory, uvol_geometry *out);
+
+/* ---- V2 texture: replaces KTX2Loader._createTexture -> BasisWorker.transcode
+ * (src/lib/KTX2Loader.js:297-337,469-580) for n .ktx2 segments at once; V2Player.decodeKTX2
+ * (src/V2/player.ts:359-366) maps segment numbers to files. */
+int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n,
+                              int target_format, int memory, uvol_texture *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

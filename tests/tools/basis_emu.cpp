@@ -1,0 +1,54 @@
+// basis_emu.cpp -- HOST EMULATION of the texture pipeline's per-unit logic (basis_core.h) for
+// logic checks without a GPU.  Test tool only; never part of libuvol_b200.so, never a fallback.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../universal-volumetric_b200/csrc/uvol_internal.h"
+#include "../../universal-volumetric_b200/csrc/basis_core.h"
+
+int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
+
+extern "C" int basis_emu_decode(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers) {
+    std::vector<uint8_t> padded(len + 64, 0); memcpy(padded.data(), data, len);   // the launcher pads the blob the same way
+    const uint8_t *file = padded.data();
+    Ktx2File f; memset(&f, 0, sizeof f); std::vector<Ktx2Slice> slices;
+    int rc = uvol_ktx2_parse(file, len, 0, f, slices); if (rc) return rc;
+    if (f.is_uastc) return UVOL_ERR_UNSUPPORTED;
+    const uint32_t pool_cap = f.endpoint_count + f.selector_count + 8192 + 1024, nblk = f.bx * f.by;
+    std::vector<uint32_t> eps(f.endpoint_count), sels(f.selector_count); std::vector<HuffTable> tabs(10);
+    std::vector<uint16_t> pool(pool_cap + 16384 + 64);
+    BasisGlobalsMem m{eps.data(), sels.data(), tabs.data(), pool.data(), (uint8_t *)(pool.data() + pool_cap), pool_cap};
+    uint32_t hs = 0;
+    rc = basis_build_globals(f, file, m, &hs); if (rc) return rc;
+    const size_t ns = slices.size();
+    std::vector<std::vector<uint8_t>> pred(ns); std::vector<std::vector<uint16_t>> delta(ns), sel(ns), ep(ns);
+    std::vector<uint8_t> rowp(4096); std::vector<uint16_t> hist(1024);
+    for (size_t k = 0; k < ns; k++) {
+        pred[k].resize(nblk); delta[k].resize(nblk); sel[k].resize(nblk); ep[k].resize(nblk);
+        BitRd b; br_init(b, file + slices[k].data_off);
+        SliceTables T{&tabs[0], &tabs[1], &tabs[2], &tabs[3], pool.data()};
+        rc = etc1s_slice_symbols(b, T, f.bx, f.by, f.selector_count, hs, (int)f.is_video, rowp.data(), hist.data(), pred[k].data(), delta[k].data(), sel[k].data());
+        if (rc) return rc;
+        if ((b.consumed + 7) / 8 != slices[k].data_len) return UVOL_ERR_TRUNCATED;
+    }
+    // serial resolve (the kernel does the same with a warp segmented scan)
+    for (uint32_t plane = 0; plane < (f.has_alpha ? 2u : 1u); plane++) for (uint32_t L = 0; L < f.layers; L++) {
+        const size_t k = plane * f.layers + L; uint32_t prev = 0;
+        for (uint32_t y = 0; y < f.by; y++) for (uint32_t x = 0; x < f.bx; x++) {
+            const uint32_t bi = y * f.bx + x, p = pred[k][bi]; uint32_t e;
+            if (p == 0) e = prev; else if (p == 1) e = ep[k][bi - f.bx];
+            else if (p == 2) { if (f.is_video) { if (!L) return UVOL_ERR_CORRUPT; e = ep[k - 1][bi]; sel[k][bi] = sel[k - 1][bi]; } else e = ep[k][bi - f.bx - 1]; }
+            else { e = delta[k][bi] + prev; if (e >= f.endpoint_count) e -= f.endpoint_count; }
+            ep[k][bi] = (uint16_t)e; prev = e;
+        }
+    }
+    *w = f.width; *h = f.height; *layers = f.layers;
+    *rgba = (uint8_t *)malloc((size_t)f.layers * f.width * f.height * 4);
+    for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
+        uint32_t rows[4][4]; etc1s_block_rows(eps[ep[L][bi]], sels[sel[L][bi]], rows);
+        const uint32_t xb = bi % f.bx, yb = bi / f.bx;
+        for (uint32_t y = 0; y < 4 && yb * 4 + y < f.height; y++) for (uint32_t x = 0; x < 4 && xb * 4 + x < f.width; x++)
+            memcpy(*rgba + ((size_t)L * f.width * f.height + (size_t)(yb * 4 + y) * f.width + xb * 4 + x) * 4, &rows[y][x], 4);
+    }
+    return 0;
+}

@@ -1,0 +1,143 @@
+// draco_emu.cpp -- HOST EMULATION of the geometry pipeline's per-unit logic (draco_core.h), used
+// only by tests to validate the algorithms without a GPU.  It runs the same __host__ __device__
+// functions the kernels call, in the same stage order as the launcher in draco_decode.cu, with
+// serial loops standing in for grids.  It is NOT part of libuvol_b200.so and is never a fallback.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../universal-volumetric_b200/csrc/uvol_internal.h"
+#include "../../universal-volumetric_b200/csrc/draco_core.h"
+#include "../../universal-volumetric_b200/csrc/draco_plan.h"
+
+int uvol_draco_parse(const uint8_t *data, size_t len, DracoFrame &f, std::vector<uint32_t> &aux);
+
+extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_points, uint32_t *num_faces,
+                                uint32_t **index, float **position, float **normal, float **uv) {
+    std::vector<DracoFrame> frames(1); std::vector<uint32_t> aux;
+    DracoFrame &f = frames[0]; memset(&f, 0, sizeof f);
+    f.file_off = 0; f.file_len = (uint32_t)len;
+    f.status = uvol_draco_parse(data, len, f, aux);
+    if (f.status) return f.status;
+    DracoPlan pl; draco_plan_phase1(frames, pl);
+    std::vector<uint8_t> scratch(pl.scratch + 256), zs(pl.zscratch + 256, 0);
+    uint8_t *S = scratch.data(), *Z = zs.data();
+    const uint8_t *file = data; aux.push_back(0);
+    const int F = (int)f.nf, nad = (int)f.nad;
+    DracoCounts cnt; memset(&cnt, 0, sizeof cnt);
+    // stage: context symbol runs
+    for (int i = 0; i < 6; i++) {
+        const RansStream &s = f.ctx[i]; if (!s.count) continue;
+        std::vector<uint32_t> cum(s.alphabet + 1, 0); std::vector<uint16_t> bucket(257);
+        for (uint32_t k = 0; k < s.alphabet; k++) cum[k + 1] = cum[k] + aux[s.prob_off + k];
+        if (cum[s.alphabet] != (1u << s.pb)) return UVOL_ERR_CORRUPT;
+        for (uint32_t b = 0; b < 256; b++) bucket[b] = (uint16_t)rans_bucket_symbol(cum.data(), s.alphabet, b << (s.pb - 8));
+        RansTables t{cum.data(), bucket.data(), s.alphabet, s.pb};
+        int rc = rans_decode_run(file + s.data_off, s.data_len, t, s.count, 0, S + f.o_ctxsym[i]); if (rc) return rc;
+    }
+    // stage: seam bits
+    for (int i = 0; i < nad; i++) {
+        Rabs r; if (!rabs_init(r, file, f.seams[i])) return UVOL_ERR_CORRUPT;
+        uint8_t *o = S + f.o_seambits[i]; for (int k = 0; k < 3 * F / 2 + 1; k++) o[k] = (uint8_t)rabs_bit(r);
+    }
+    // stage: edgebreaker
+    EbMem m; m.opp = (int *)(S + f.o_opp); m.c2v = (int *)(S + f.o_c2v); m.lmc = (int *)(S + f.o_lmc); m.val = (int *)(S + f.o_val);
+    m.hole = S + f.o_hole; m.stack = (int *)(S + f.o_stack); m.skey = m.stack + f.nsym + 8; m.sval = m.skey + f.nts + 1; m.invalid = (int *)(S + f.o_invalid);
+    for (int i = 0; i < 6; i++) m.ctxsym[i] = S + f.o_ctxsym[i];
+    int rc = eb_decode_frame(f, file, aux.data(), m, &cnt.num_vertex_slots); if (rc) return rc;
+    const int V = (int)cnt.num_vertex_slots;
+    // stage: seams
+    { int idx = 0;
+      for (int c = 0; c < 3 * F; c++) {
+        int o = m.opp[c];
+        if (o < 0) { for (int i = 0; i < nad; i++) seam_mark(c, m.opp, m.c2v, Z + f.o_eos[i], Z + f.o_vos[i]); continue; }
+        if (o / 3 < c / 3) continue;
+        for (int i = 0; i < nad; i++) if ((S + f.o_seambits[i])[idx]) seam_mark(c, m.opp, m.c2v, Z + f.o_eos[i], Z + f.o_vos[i]);
+        idx++;
+      } }
+    // stage: attribute vertex tables (count, scan, assign)
+    int err = 0;
+    for (int i = 0; i < nad; i++) {
+        int *acnt = (int *)(S + f.o_acnt[i]), *afirst = (int *)(S + f.o_afirst[i]), *ac2v = (int *)(S + f.o_ac2v[i]);
+        for (int v = 0; v < V; v++) acnt[v] = attr_vertex_fan(v, m.opp, m.lmc, Z + f.o_eos[i], Z + f.o_vos[i], afirst, ac2v, 0, 0, F, &err);
+        int run = 0; for (int v = 0; v < V; v++) { int c = acnt[v]; acnt[v] = run; run += c; }
+        cnt.attr_vertices[i] = (uint32_t)run;
+        for (int v = 0; v < V; v++) attr_vertex_fan(v, m.opp, m.lmc, Z + f.o_eos[i], Z + f.o_vos[i], afirst, ac2v, acnt[v], 1, F, &err);
+    }
+    const uint8_t *vos[UVOL_MAX_ATTR_DATA]; const int *ac2v[UVOL_MAX_ATTR_DATA];
+    for (int i = 0; i < nad; i++) { vos[i] = Z + f.o_vos[i]; ac2v[i] = (int *)(S + f.o_ac2v[i]); }
+    int *pcnt = (int *)(S + f.o_pcnt), *pfirst = (int *)(S + f.o_pfirst);
+    for (int v = 0; v < V; v++) pcnt[v] = point_fan(v, m.opp, m.c2v, m.lmc, m.hole, nad, vos, ac2v, pfirst, nullptr, nullptr, 0, 0, F, &err);
+    { int run = 0; for (int v = 0; v < V; v++) { int c = pcnt[v]; pcnt[v] = run; run += c; } cnt.num_points = (uint32_t)run; }
+    if (err) return UVOL_ERR_CORRUPT;
+    // ---- phase 2
+    draco_plan_phase2(frames, &cnt, pl);
+    std::vector<uint8_t> scratch2(pl.scratch2 + 256), zs2(pl.zscratch2 + 256, 0), outb(pl.out + 256);
+    uint8_t *S2 = scratch2.data(), *Z2 = zs2.data(), *O = outb.data();
+    const int P = (int)cnt.num_points;
+    uint32_t *c2p = (uint32_t *)(O + f.out_index); int *p2c = (int *)(S2 + f.o_p2c);
+    for (int v = 0; v < V; v++) point_fan(v, m.opp, m.c2v, m.lmc, m.hole, nad, vos, ac2v, pfirst, c2p, p2c, pcnt[v], 1, F, &err);
+    // traversals
+    TableView tv[UVOL_MAX_ATTR_DATA + 1];
+    for (int t = 0; t <= nad; t++) {
+        if (f.o_d2c[t] == UVOL_NONE) continue;
+        tv[t] = (t == 0) ? TableView{m.opp, m.c2v, nullptr, nullptr, nullptr} : TableView{m.opp, m.c2v, Z + f.o_eos[t - 1], ac2v[t - 1], vos[t - 1]};
+        const int maxe = (int)(t == 0 ? cnt.num_vertex_slots : cnt.attr_vertices[t - 1]);
+        rc = traverse_table(tv[t], m.lmc, F, Z2 + f.o_fvis[t], (int *)(Z2 + f.o_v2d[t]), (int *)(S2 + f.o_d2c[t]), (int *)(S2 + f.o_tstack[t]), maxe, &cnt.entries[t]);
+        if (rc) return rc;
+    }
+    // attribute symbol runs + aux bits
+    for (int j = 0; j < f.nattr; j++) {
+        const DracoAttr &a = f.attr[j]; if (f.o_corr[j] == UVOL_NONE) continue;
+        const RansStream &s = a.sym; const uint32_t n = cnt.entries[a.table + 1];
+        std::vector<uint32_t> cum(s.alphabet + 1, 0); std::vector<uint16_t> bucket(257);
+        for (uint32_t k = 0; k < s.alphabet; k++) cum[k + 1] = cum[k] + aux[s.prob_off + k];
+        if (cum[s.alphabet] != (1u << s.pb)) return UVOL_ERR_CORRUPT;
+        for (uint32_t b = 0; b < 256; b++) bucket[b] = (uint16_t)rans_bucket_symbol(cum.data(), s.alphabet, b << (s.pb - 8));
+        RansTables t{cum.data(), bucket.data(), s.alphabet, s.pb};
+        const int positive = a.pred != -2 && (a.xform == 2 || a.xform == 3);
+        rc = rans_decode_run(file + s.data_off, s.data_len, t, n * a.vnc, positive ? 2 : 1, S2 + f.o_corr[j]); if (rc) return rc;
+        if (a.pred == 5 || a.pred == 6) {
+            Rabs r; if (!rabs_init(r, file, a.aux_bits)) return UVOL_ERR_CORRUPT;
+            uint8_t *o = S2 + f.o_auxbits[j];
+            if (a.pred == 5) { if ((uint32_t)a.num_orient > n) return UVOL_ERR_CORRUPT; int last = 1; for (int k = 0; k < a.num_orient; k++) { if (!rabs_bit(r)) last = !last; o[k] = (uint8_t)last; } }
+            else for (uint32_t k = 0; k < n; k++) o[k] = (uint8_t)rabs_bit(r);
+        }
+    }
+    // prediction reversal: position-like first, then uv / normal
+    const DracoAttr &pa = f.attr[f.pos_attr];
+    const int *pos_v2d1 = (int *)(Z2 + f.o_v2d[0]); const int32_t *posq = (int32_t *)(S2 + f.o_val_attr[f.pos_attr]);
+    for (int pass = 0; pass < 2; pass++) for (int j = 0; j < f.nattr; j++) {
+        const DracoAttr &a = f.attr[j]; if (f.o_corr[j] == UVOL_NONE) continue;
+        const int t = a.table + 1, n = (int)cnt.entries[t];
+        const int32_t *corr = (int32_t *)(S2 + f.o_corr[j]); int32_t *val = (int32_t *)(S2 + f.o_val_attr[j]);
+        const int *d2c = (int *)(S2 + f.o_d2c[t]), *v2d1 = (int *)(Z2 + f.o_v2d[t]);
+        if (pass == 0 && (a.pred == 0 || a.pred == 1 || a.pred == -2)) {
+            if (a.pred == -2) { memcpy(val, corr, (size_t)n * a.vnc * 4); continue; }
+            int *par = (int *)(S2 + f.o_par[j]);
+            if (a.pred == 1) for (int p = 0; p < n; p++) parallelogram_parents(p, tv[t], d2c, v2d1, par + 4 * p);
+            for (int k = 0; k < a.vnc; k++) predict_wrap_component(k, a.vnc, n, a.pred == 1, par, corr, val, a.wmin, a.wmax);
+        } else if (pass == 1 && a.pred == 5) {
+            UvPrep *prep = (UvPrep *)(S2 + f.o_par[j]);
+            for (int p = 0; p < n; p++) uv_prepare(p, tv[t], d2c, v2d1, pos_v2d1, posq, prep[p]);
+            rc = predict_uv_chain(n, prep, corr, val, S2 + f.o_auxbits[j], a.num_orient, a.wmin, a.wmax); if (rc) return rc;
+        } else if (pass == 1 && a.pred == 6) {
+            for (int p = 0; p < n; p++) normal_entry(p, tv[t], d2c, pos_v2d1, posq, corr, S2 + f.o_auxbits[j], a.wmin, val);
+        }
+    }
+    (void)pa;
+    // expansion
+    *num_points = (uint32_t)P; *num_faces = (uint32_t)F;
+    *index = (uint32_t *)malloc((size_t)F * 12); memcpy(*index, c2p, (size_t)F * 12);
+    float **dst[4] = {position, normal, uv, nullptr}; *position = *normal = *uv = nullptr;
+    for (int j = 0; j < f.nattr; j++) {
+        const DracoAttr &a = f.attr[j]; if (a.out_slot < 0 || a.out_slot > 2) continue;
+        const int t = a.table + 1;
+        float *o = (float *)(O + f.out_attr[a.out_slot]);
+        const int *voc = t == 0 ? m.c2v : ac2v[t - 1];
+        for (int p = 0; p < P; p++) expand_point(p, p2c, voc, (int *)(Z2 + f.o_v2d[t]), a, (int32_t *)(S2 + f.o_val_attr[j]), o);
+        *dst[a.out_slot] = (float *)malloc((size_t)P * a.nc * 4); memcpy(*dst[a.out_slot], o, (size_t)P * a.nc * 4);
+    }
+    return err ? UVOL_ERR_CORRUPT : UVOL_OK;
+}
+extern "C" void draco_emu_free(void *p) { free(p); }

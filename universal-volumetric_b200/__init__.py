@@ -1,0 +1,11 @@
+"""universal-volumetric_b200 -- B200-native UVOL decode hot path (V2 Draco + KTX2/Basis, V1 Corto).
+
+The product is ``libuvol_b200.so`` (hand-written sm_100a CUDA behind the C ABI in
+``include/uvol_b200.h``); this package is the thin host-side mirror of the reference's loader
+interface.  Import it with ``importlib.import_module("universal-volumetric_b200")``.
+"""
+from . import _native
+from ._native import UvolError, MEM_DEVICE, MEM_HOST
+from .loaders import Context, DRACOLoader, KTX2Loader
+
+__all__ = ["Context", "DRACOLoader", "KTX2Loader", "UvolError", "MEM_DEVICE", "MEM_HOST", "_native"]

@@ -1,0 +1,70 @@
+"""ctypes binding of libuvol_b200.so (the C ABI declared in include/uvol_b200.h).
+
+The shared library is the product; this module only marshals pointers.  It fails loudly when the
+library is missing or when no CUDA device is usable -- there is no CPU decode path.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libuvol_b200.so")
+
+MEM_DEVICE, MEM_HOST = 0, 1
+TEX_RGBA32 = 0
+
+
+class UvolError(RuntimeError):
+    pass
+
+
+class Geometry(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_int32), ("num_points", ctypes.c_uint32), ("num_faces", ctypes.c_uint32),
+                ("color_components", ctypes.c_uint32),
+                ("index", ctypes.POINTER(ctypes.c_uint32)), ("position", ctypes.POINTER(ctypes.c_float)),
+                ("normal", ctypes.POINTER(ctypes.c_float)), ("uv", ctypes.POINTER(ctypes.c_float)),
+                ("color", ctypes.POINTER(ctypes.c_float))]
+
+
+class Texture(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_int32), ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("layers", ctypes.c_uint32),
+                ("format", ctypes.c_uint32), ("has_alpha", ctypes.c_uint32), ("dfd_transfer", ctypes.c_uint32), ("dfd_flags", ctypes.c_uint32),
+                ("data", ctypes.POINTER(ctypes.c_uint8)), ("bytes", ctypes.c_uint64)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("host_parse_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("device_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
+                ("total_ms", ctypes.c_double), ("stage_ms", ctypes.c_float * 16), ("num_stages", ctypes.c_uint32),
+                ("kernel_launches", ctypes.c_uint32), ("bytes_in", ctypes.c_uint64), ("bytes_out", ctypes.c_uint64),
+                ("scratch_bytes", ctypes.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libuvol_b200.so once.  Raises UvolError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UvolError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(the CUDA extension is mandatory; there is no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    L.uvol_create.argtypes = [i, ctypes.POINTER(vp)]; L.uvol_create.restype = i
+    L.uvol_destroy.argtypes = [vp]; L.uvol_destroy.restype = None
+    L.uvol_last_error.argtypes = [vp]; L.uvol_last_error.restype = ctypes.c_char_p
+    L.uvol_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]; L.uvol_get_stats.restype = i
+    L.uvol_stage_name.argtypes = [i, i]; L.uvol_stage_name.restype = ctypes.c_char_p
+    L.uvol_set_profiling.argtypes = [vp, i]; L.uvol_set_profiling.restype = i
+    L.uvol_decode_draco_batch.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz), i, i, ctypes.POINTER(Geometry)]
+    L.uvol_decode_draco_batch.restype = i
+    if hasattr(L, "uvol_transcode_ktx2_batch"):
+        L.uvol_transcode_ktx2_batch.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz), i, i, i, ctypes.POINTER(Texture)]
+        L.uvol_transcode_ktx2_batch.restype = i
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = ["uvol_create", "uvol_destroy", "uvol_last_error", "uvol_get_stats", "uvol_stage_name", "uvol_set_profiling",
+                    "uvol_decode_draco_batch", "uvol_transcode_ktx2_batch"]

@@ -1,0 +1,241 @@
+// basis_core.h -- per-unit device logic of the KTX2 / BasisLZ (ETC1S) transcode to RGBA32.
+// __host__ __device__ so tests/tools/basis_emu.cpp can check the logic on the host (debug harness
+// only; libuvol_b200.so has no host transcode).  Format: SURVEY.md Appendix B; reference call
+// site src/lib/KTX2Loader.js:469-580 (startTranscoding :506, transcodeImage :551-552).
+#pragma once
+#include "uvol_internal.h"
+
+#if defined(__CUDACC__)
+#define UVOL_HD __host__ __device__ __forceinline__
+#else
+#define UVOL_HD static inline
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// LSB-first bit reader over 32-bit aligned words (the batch blob is padded so that reading one
+// word past a section is always in bounds).
+struct BitRd { const uint32_t *w; uint32_t wi; uint64_t buf; int nbits; uint64_t consumed; };
+UVOL_HD void br_init(BitRd &b, const uint8_t *p) {
+    const uintptr_t a = (uintptr_t)p; const unsigned mis = (unsigned)(a & 3);
+    b.w = (const uint32_t *)(a - mis); b.buf = (uint64_t)b.w[0] >> (8 * mis); b.nbits = 32 - 8 * (int)mis; b.wi = 1; b.consumed = 0;
+}
+UVOL_HD void br_refill(BitRd &b) { if (b.nbits <= 32) { b.buf |= (uint64_t)b.w[b.wi++] << b.nbits; b.nbits += 32; } }
+UVOL_HD uint32_t br_peek(BitRd &b) { br_refill(b); return (uint32_t)b.buf; }
+UVOL_HD void br_skip(BitRd &b, int n) { b.buf >>= n; b.nbits -= n; b.consumed += (uint64_t)n; }
+UVOL_HD uint32_t br_get(BitRd &b, int n) { if (n == 0) return 0; br_refill(b); uint32_t v = (uint32_t)b.buf & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u)); br_skip(b, n); return v; }
+UVOL_HD uint32_t br_vlc(BitRd &b, int cb) {
+    uint32_t v = 0; int ofs = 0;
+    for (;;) { uint32_t ch = br_get(b, cb + 1); v |= (ch & ((1u << cb) - 1u)) << ofs; ofs += cb; if (!(ch & (1u << cb)) || ofs >= 32) return v; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Canonical Huffman (B.2).  Codes are stored MSB-first canonical, read LSB-first from the stream.
+UVOL_HD int huff_decode(const HuffTable &T, const uint16_t *sorted_pool, BitRd &b) {
+    if (T.used == 0) return 0;
+    const uint32_t v = br_peek(b);
+    const uint32_t e = T.fast[v & ((1u << UVOL_HUFF_FAST_BITS) - 1u)];
+    if (e & 0xff) { br_skip(b, (int)(e & 0xff)); return (int)(e >> 8); }
+    uint32_t code = 0;
+    for (uint32_t l = 1; l <= T.maxl; l++) {
+        code = (code << 1) | ((v >> (l - 1)) & 1u);
+        if (T.count[l] && code >= T.first_code[l] && code - T.first_code[l] < T.count[l]) { br_skip(b, (int)l); return sorted_pool[T.sorted_off + T.first_idx[l] + (code - T.first_code[l])]; }
+    }
+    br_skip(b, 16);
+    return -1;
+}
+
+// Builds T from code sizes (serial part; the fast-table fill is split over `nlanes` callers).
+UVOL_HD int huff_build_serial(HuffTable &T, const uint8_t *sizes, uint32_t total, uint16_t *sorted_pool, uint32_t sorted_off) {
+    T.total = total; T.used = 0; T.maxl = 0; T.sorted_off = sorted_off;
+    for (int l = 0; l < 17; l++) T.count[l] = 0;
+    for (uint32_t i = 0; i < total; i++) { const uint32_t s = sizes[i]; if (s > 16) return UVOL_ERR_CORRUPT; if (s) { T.count[s]++; T.used++; if (s > T.maxl) T.maxl = s; } }
+    uint32_t code = 0, idx = 0, fill[17];
+    T.first_code[0] = 0; T.first_idx[0] = 0; fill[0] = 0;
+    for (int l = 1; l <= 16; l++) { code = (code + (l > 1 ? T.count[l - 1] : 0)) << 1; T.first_code[l] = code; T.first_idx[l] = idx; fill[l] = idx; idx += T.count[l]; }
+    for (uint32_t s = 0; s < total; s++) if (sizes[s]) sorted_pool[sorted_off + fill[sizes[s]]++] = (uint16_t)s;
+    return UVOL_OK;
+}
+UVOL_HD void huff_fill_fast(HuffTable &T, const uint16_t *sorted_pool, uint32_t lane, uint32_t nlanes) {
+    for (uint32_t i = lane; i < (1u << UVOL_HUFF_FAST_BITS); i += nlanes) T.fast[i] = 0;
+}
+UVOL_HD void huff_fill_fast2(HuffTable &T, const uint16_t *sorted_pool, uint32_t lane, uint32_t nlanes) {
+    for (uint32_t l = 1; l <= UVOL_HUFF_FAST_BITS && l <= T.maxl; l++) {
+        for (uint32_t k = lane; k < T.count[l]; k += nlanes) {
+            const uint32_t c = T.first_code[l] + k; uint32_t rev = 0;
+            for (uint32_t i = 0; i < l; i++) rev |= ((c >> i) & 1u) << (l - 1 - i);
+            const uint32_t sym = sorted_pool[T.sorted_off + T.first_idx[l] + k];
+            for (uint32_t hi = 0; hi < (1u << (UVOL_HUFF_FAST_BITS - l)); hi++) T.fast[rev | (hi << l)] = (sym << 8) | l;
+        }
+    }
+}
+
+// Reads one Huffman table header (code-length code + RLE'd lengths) into sizes[]; serial.
+// `tmp` is a scratch HuffTable + 32-entry pool for the code-length code.
+UVOL_HD int huff_read_sizes(BitRd &b, uint8_t *sizes, uint32_t max_total, uint32_t *out_total, HuffTable &tmp, uint16_t *tmp_pool) {
+    const uint32_t total = br_get(b, 14);
+    *out_total = total;
+    if (total == 0) return UVOL_OK;
+    if (total > max_total) return UVOL_ERR_CORRUPT;
+    const uint32_t ncl = br_get(b, 5);
+    if (ncl < 1 || ncl > 21) return UVOL_ERR_CORRUPT;
+    const uint8_t order[21] = {17, 18, 19, 20, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15, 16};
+    uint8_t cls[21];
+    for (int i = 0; i < 21; i++) cls[i] = 0;
+    for (uint32_t i = 0; i < ncl; i++) cls[order[i]] = (uint8_t)br_get(b, 3);
+    int rc = huff_build_serial(tmp, cls, 21, tmp_pool, 0); if (rc) return rc;
+    huff_fill_fast(tmp, tmp_pool, 0, 1); huff_fill_fast2(tmp, tmp_pool, 0, 1);
+    uint32_t n = 0;
+    while (n < total) {
+        const int c = huff_decode(tmp, tmp_pool, b);
+        if (c < 0) return UVOL_ERR_CORRUPT;
+        if (c <= 16) sizes[n++] = (uint8_t)c;
+        else if (c == 17 || c == 18) { uint32_t rep = c == 17 ? br_get(b, 3) + 3 : br_get(b, 7) + 11; if (n + rep > total) return UVOL_ERR_CORRUPT; for (uint32_t k = 0; k < rep; k++) sizes[n++] = 0; }
+        else { uint32_t rep = c == 19 ? br_get(b, 2) + 3 : br_get(b, 7) + 7; if (n == 0 || n + rep > total) return UVOL_ERR_CORRUPT; const uint8_t pv = sizes[n - 1]; for (uint32_t k = 0; k < rep; k++) sizes[n++] = pv; }
+    }
+    return UVOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slice symbol decode (B.3), serial per slice.  Emits per block: pred (2 bits), the delta-endpoint
+// symbol (pred==3) and the selector index (non-CR blocks).  Endpoint indices are resolved later.
+struct SliceTables { const HuffTable *epm, *dem, *sm, *rle; const uint16_t *pool; };
+UVOL_HD int etc1s_slice_symbols(BitRd &b, const SliceTables &T, uint32_t bx, uint32_t by, uint32_t sel_count, uint32_t hist_size, int is_video,
+                                uint8_t *rowp /*[bx]*/, uint16_t *hist /*[hist_size]*/, uint8_t *pred_out, uint16_t *delta_out, uint16_t *sel_out) {
+    for (uint32_t i = 0; i < hist_size; i++) hist[i] = 0;
+    uint32_t rover = hist_size / 2, rle_cnt = 0, prev_sym = 0, rep = 0, bits = 0;
+    for (uint32_t y = 0; y < by; y++) {
+        for (uint32_t x = 0; x < bx; x++) {
+            if ((x & 1) == 0) {
+                if ((y & 1) == 0) {
+                    if (rep) { rep--; bits = prev_sym; }
+                    else {
+                        const int sy = huff_decode(*T.epm, T.pool, b); if (sy < 0) return UVOL_ERR_CORRUPT;
+                        bits = (uint32_t)sy;
+                        if (bits == 256) { rep = br_vlc(b, 4) + 3 - 1; bits = prev_sym; } else prev_sym = bits;
+                    }
+                    rowp[x] = (uint8_t)(bits >> 4);
+                } else bits = rowp[x];
+            }
+            const uint32_t pred = bits & 3; bits >>= 2;
+            const uint32_t bi = y * bx + x;
+            pred_out[bi] = (uint8_t)pred;
+            if (pred == 0 && x == 0) return UVOL_ERR_CORRUPT;
+            if (pred == 1 && y == 0) return UVOL_ERR_CORRUPT;
+            if (pred == 2 && !is_video && (x == 0 || y == 0)) return UVOL_ERR_CORRUPT;
+            if (pred == 3) { const int d = huff_decode(*T.dem, T.pool, b); if (d < 0) return UVOL_ERR_CORRUPT; delta_out[bi] = (uint16_t)d; }
+            if (!(is_video && pred == 2)) {
+                uint32_t s;
+                if (rle_cnt > 0) { rle_cnt--; s = hist[0]; }
+                else {
+                    const int sy = huff_decode(*T.sm, T.pool, b); if (sy < 0) return UVOL_ERR_CORRUPT;
+                    s = (uint32_t)sy;
+                    if (s == sel_count + hist_size) {
+                        const int rr = huff_decode(*T.rle, T.pool, b); if (rr < 0) return UVOL_ERR_CORRUPT;
+                        rle_cnt = (rr == 63) ? br_vlc(b, 7) + 3 : (uint32_t)rr + 3;
+                        s = hist[0]; rle_cnt--;
+                    } else if (s >= sel_count) {
+                        const uint32_t i = s - sel_count; if (i >= hist_size) return UVOL_ERR_CORRUPT;
+                        s = hist[i];
+                        if (i) { const uint16_t t = hist[i / 2]; hist[i / 2] = hist[i]; hist[i] = t; }
+                    } else { hist[rover++] = (uint16_t)s; if (rover == hist_size) rover = hist_size / 2; }
+                }
+                if (s >= sel_count) return UVOL_ERR_CORRUPT;
+                sel_out[bi] = (uint16_t)s;
+            }
+        }
+    }
+    return UVOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ETC1S block -> 16 RGBA texels (B.5).  ep = {r5,g5,b5,inten}, sel = 4 row bytes (2 bits/pixel).
+UVOL_HD uint32_t etc1s_color(uint32_t ep, int k) {
+    const int tab[8][4] = {{-8, -2, 2, 8}, {-17, -5, 5, 17}, {-29, -9, 9, 29}, {-42, -13, 13, 42}, {-60, -18, 18, 60}, {-80, -24, 24, 80}, {-106, -33, 33, 106}, {-183, -47, 47, 183}};
+    const int d = tab[(ep >> 24) & 7][k];
+    uint32_t out = 0;
+    for (int c = 0; c < 3; c++) { const int c5 = (int)((ep >> (8 * c)) & 31); int v = ((c5 << 3) | (c5 >> 2)) + d; v = v < 0 ? 0 : (v > 255 ? 255 : v); out |= (uint32_t)v << (8 * c); }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-file global data (B.2): endpoint / selector codebooks and the four slice Huffman tables.
+// Serial (a few thousand symbols per file); runs once per KTX2 file.
+struct BasisGlobalsMem {
+    uint32_t *endpoints;      // [ec]  r5 | g5<<8 | b5<<16 | inten<<24
+    uint32_t *selectors;      // [sc]  4 row bytes, 2 bits per pixel
+    HuffTable *tables;        // [0..3] endpoint_pred, delta_endpoint, selector, selector_rle ; [4..9] temporaries
+    uint16_t *pool;           // sorted-symbol pool
+    uint8_t *sizes;           // [32768] temporary code sizes
+    uint32_t pool_cap;
+};
+UVOL_HD int basis_read_table(BitRd &b, HuffTable &T, BasisGlobalsMem &m, uint32_t &pool_used, uint32_t max_total) {
+    uint32_t total = 0;
+    HuffTable &tmp = m.tables[9]; uint16_t *tmp_pool = m.pool + m.pool_cap - 32;
+    int rc = huff_read_sizes(b, m.sizes, max_total, &total, tmp, tmp_pool); if (rc) return rc;
+    if (pool_used + total > m.pool_cap - 32) return UVOL_ERR_CORRUPT;
+    rc = huff_build_serial(T, m.sizes, total, m.pool, pool_used); if (rc) return rc;
+    huff_fill_fast(T, m.pool, 0, 1); huff_fill_fast2(T, m.pool, 0, 1);
+    pool_used += T.used;
+    return UVOL_OK;
+}
+UVOL_HD int basis_build_globals(const Ktx2File &f, const uint8_t *file, BasisGlobalsMem &m, uint32_t *out_hist_size) {
+    uint32_t pool_used = 0; int rc;
+    // slice tables first (they persist at the front of the pool)
+    {
+        BitRd b; br_init(b, file + f.tab_off);
+        if ((rc = basis_read_table(b, m.tables[0], m, pool_used, 32768))) return rc;
+        if ((rc = basis_read_table(b, m.tables[1], m, pool_used, 32768))) return rc;
+        if ((rc = basis_read_table(b, m.tables[2], m, pool_used, 32768))) return rc;
+        if ((rc = basis_read_table(b, m.tables[3], m, pool_used, 32768))) return rc;
+        const uint32_t hs = br_get(b, 13);
+        if (hs == 0 || hs > 1024) return UVOL_ERR_UNSUPPORTED;
+        *out_hist_size = hs;
+        if ((b.consumed + 7) / 8 > f.tab_len) return UVOL_ERR_CORRUPT;
+    }
+    {   // endpoints
+        BitRd b; br_init(b, file + f.ep_off);
+        for (int k = 0; k < 4; k++) if ((rc = basis_read_table(b, m.tables[4 + k], m, pool_used, 256))) return rc;
+        const uint32_t gray = br_get(b, 1);
+        uint32_t prev[3] = {16, 16, 16}, pint = 0;
+        for (uint32_t i = 0; i < f.endpoint_count; i++) {
+            int d = huff_decode(m.tables[7], m.pool, b); if (d < 0) return UVOL_ERR_CORRUPT;
+            pint = (pint + (uint32_t)d) & 7;
+            for (uint32_t c = 0; c < (gray ? 1u : 3u); c++) {
+                const HuffTable &mt = prev[c] <= 9 ? m.tables[4] : (prev[c] <= 21 ? m.tables[5] : m.tables[6]);
+                d = huff_decode(mt, m.pool, b); if (d < 0) return UVOL_ERR_CORRUPT;
+                prev[c] = (prev[c] + (uint32_t)d) & 31;
+            }
+            if (gray) prev[1] = prev[2] = prev[0];
+            m.endpoints[i] = prev[0] | (prev[1] << 8) | (prev[2] << 16) | (pint << 24);
+        }
+        if ((b.consumed + 7) / 8 > f.ep_len) return UVOL_ERR_CORRUPT;
+    }
+    {   // selectors
+        BitRd b; br_init(b, file + f.sel_off);
+        const uint32_t glob = br_get(b, 1), hyb = br_get(b, 1), raw = br_get(b, 1);
+        if (glob || hyb) return UVOL_ERR_UNSUPPORTED;
+        if (raw) { for (uint32_t i = 0; i < f.selector_count; i++) { uint32_t v = 0; for (int j = 0; j < 4; j++) v |= br_get(b, 8) << (8 * j); m.selectors[i] = v; } }
+        else {
+            if ((rc = basis_read_table(b, m.tables[8], m, pool_used, 256))) return rc;
+            uint32_t pb[4] = {0, 0, 0, 0};
+            for (uint32_t i = 0; i < f.selector_count; i++) {
+                uint32_t v = 0;
+                for (int j = 0; j < 4; j++) {
+                    if (i == 0) pb[j] = br_get(b, 8);
+                    else { const int d = huff_decode(m.tables[8], m.pool, b); if (d < 0) return UVOL_ERR_CORRUPT; pb[j] ^= (uint32_t)d; }
+                    v |= (pb[j] & 255u) << (8 * j);
+                }
+                m.selectors[i] = v;
+            }
+        }
+        if ((b.consumed + 7) / 8 > f.sel_len) return UVOL_ERR_CORRUPT;
+    }
+    return UVOL_OK;
+}
+
+// One ETC1S block -> RGBA32 rows.  rows[r] receives 4 packed RGBA texels of pixel row r.
+UVOL_HD void etc1s_block_rows(uint32_t ep, uint32_t sel, uint32_t rows[4][4]) {
+    uint32_t col[4];
+    for (int k = 0; k < 4; k++) col[k] = etc1s_color(ep, k) | 0xff000000u;
+    for (int y = 0; y < 4; y++) { const uint32_t rb = (sel >> (8 * y)) & 255u; for (int x = 0; x < 4; x++) rows[y][x] = col[(rb >> (2 * x)) & 3u]; }
+}

@@ -1,0 +1,251 @@
+// basis_transcode.cu -- sm_100a kernels + batch launcher for the V2 texture path (KTX2 -> RGBA32).
+//
+// Replaces KTX2Loader._createTexture -> BasisWorker.transcode (src/lib/KTX2Loader.js:297-337,
+// 469-580) for a batch of .ktx2 segments.  Stages (DESIGN.md "Texture pipeline"):
+//   globals   one warp per file : Huffman tables + endpoint/selector codebooks (startTranscoding, :506)
+//   slices    one warp per slice: VLC decode -> per-block {pred, delta symbol, selector}   (transcodeImage, :551)
+//   resolve   one warp per (file, plane): layer-ordered, row-ordered endpoint prediction reversal
+//             (left / up / CR / delta) as a warp segmented scan; CR selectors copied from the previous layer
+//   blocks    one thread per 4x4 block: codebook lookup -> 64 B of RGBA32, coalesced row stores
+// UASTC files skip the first three stages (no entropy coding) and run the block kernel in uastc_transcode.cu.
+#include <chrono>
+#include <string.h>
+#include "uvol_ctx.h"
+#include "basis_core.h"
+
+int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
+void uvol_uastc_launch(const Ktx2File *dF, const int32_t *dStatus, const uint8_t *dBlob, uint8_t *dOut, const uint32_t *dLayerList, int nlayers,
+                       uint32_t max_blocks, cudaStream_t st);
+
+namespace {
+
+struct TexState { int32_t status; uint32_t hist_size; };
+
+__global__ void __launch_bounds__(32) k_basis_globals(const Ktx2File *files, TexState *state, const uint8_t *blob, uint8_t *S, int nfiles) {
+    const uint32_t fi = blockIdx.x;
+    if ((int)fi >= nfiles || threadIdx.x != 0) return;
+    const Ktx2File &f = files[fi];
+    if (f.status) { state[fi].status = f.status; return; }
+    if (f.is_uastc) return;
+    BasisGlobalsMem m;
+    m.endpoints = (uint32_t *)(S + f.o_endpoints); m.selectors = (uint32_t *)(S + f.o_selectors); m.tables = (HuffTable *)(S + f.o_huff);
+    m.pool = (uint16_t *)(S + f.o_sorted); m.pool_cap = f.endpoint_count + f.selector_count + 8192 + 1024;
+    m.sizes = (uint8_t *)(m.pool + m.pool_cap);
+    uint32_t hs = 0;
+    const int rc = basis_build_globals(f, blob + f.file_off, m, &hs);
+    state[fi].hist_size = hs;
+    if (rc) state[fi].status = rc;
+}
+
+__global__ void __launch_bounds__(32) k_etc1s_slices(const Ktx2File *files, TexState *state, const Ktx2Slice *slices, const uint8_t *blob, uint8_t *S, int nslices) {
+    __shared__ HuffTable tabs[4];
+    __shared__ uint8_t rowp[4096];
+    __shared__ uint16_t hist[1024];
+    const uint32_t si = blockIdx.x;
+    if ((int)si >= nslices) return;
+    const Ktx2Slice &sl = slices[si]; const Ktx2File &f = files[sl.file];
+    if (f.status || state[sl.file].status) return;
+    const HuffTable *gt = (const HuffTable *)(S + f.o_huff);
+    {   // stage the four slice tables in shared memory (word copy by the whole warp)
+        const uint32_t *src = (const uint32_t *)gt; uint32_t *dst = (uint32_t *)tabs;
+        for (uint32_t i = threadIdx.x; i < 4 * sizeof(HuffTable) / 4; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    BitRd b; br_init(b, blob + f.file_off + sl.data_off);
+    SliceTables T{&tabs[0], &tabs[1], &tabs[2], &tabs[3], (const uint16_t *)(S + f.o_sorted)};
+    const int rc = etc1s_slice_symbols(b, T, f.bx, f.by, f.selector_count, state[sl.file].hist_size, (int)f.is_video, rowp, hist,
+                                       S + sl.o_pred, (uint16_t *)(S + sl.o_delta), (uint16_t *)(S + sl.o_sel));
+    if (rc) state[sl.file].status = rc;
+    else if ((b.consumed + 7) / 8 > sl.data_len) state[sl.file].status = UVOL_ERR_TRUNCATED;
+}
+
+// Endpoint prediction reversal.  One warp per (file, plane); layers and rows in order, 32 blocks per step.
+__global__ void __launch_bounds__(32) k_etc1s_resolve(const Ktx2File *files, TexState *state, const Ktx2Slice *slices, uint8_t *S, int nfiles) {
+    const uint32_t fi = blockIdx.x, plane = blockIdx.y, lane = threadIdx.x;
+    if ((int)fi >= nfiles) return;
+    const Ktx2File &f = files[fi];
+    if (f.status || state[fi].status || f.is_uastc) return;
+    if (plane && !f.has_alpha) return;
+    const uint32_t bx = f.bx, by = f.by, ec = f.endpoint_count; const int video = (int)f.is_video;
+    int bad = 0;
+    for (uint32_t L = 0; L < f.layers; L++) {
+        const Ktx2Slice &sl = slices[f.first_slice + plane * f.layers + L];
+        const uint8_t *pred = S + sl.o_pred; const uint16_t *delta = (const uint16_t *)(S + sl.o_delta);
+        uint16_t *E = (uint16_t *)(S + sl.o_ep), *Ssel = (uint16_t *)(S + sl.o_sel);
+        const uint16_t *PE = nullptr, *PS = nullptr;
+        if (L) { const Ktx2Slice &pl = slices[f.first_slice + plane * f.layers + L - 1]; PE = (const uint16_t *)(S + pl.o_ep); PS = (const uint16_t *)(S + pl.o_sel); }
+        uint32_t carry = 0;
+        for (uint32_t y = 0; y < by; y++) {
+            for (uint32_t base = 0; base < bx; base += 32) {
+                const uint32_t x = base + lane; const bool in = x < bx; const uint32_t bi = y * bx + x;
+                uint32_t p = 0, d = 0, bv = 0; bool head = false;
+                if (in) {
+                    p = pred[bi];
+                    if (p == 3) d = delta[bi];
+                    else if (p == 1) { head = true; bv = E[bi - bx]; }
+                    else if (p == 2) {
+                        head = true;
+                        if (video) { if (PE) { bv = PE[bi]; Ssel[bi] = PS[bi]; } else bad = 1; }
+                        else bv = E[bi - bx - 1];
+                    }
+                }
+                uint32_t sc = d;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, sc, o); if ((int)lane >= o) sc += t; }
+                const unsigned hm = __ballot_sync(0xffffffffu, head);
+                const unsigned below = hm & (0xffffffffu >> (31 - lane));
+                const int h = below ? 31 - __clz(below) : 0;
+                const uint32_t bh = __shfl_sync(0xffffffffu, bv, h), sh = __shfl_sync(0xffffffffu, sc, h);
+                uint32_t e = below ? bh + sc - sh : carry + sc;
+                e %= ec;
+                if (in) E[bi] = (uint16_t)e;
+                const int lastl = (bx - base) >= 32 ? 31 : (int)(bx - base) - 1;
+                carry = __shfl_sync(0xffffffffu, e, lastl);
+            }
+            __syncwarp();
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) state[fi].status = UVOL_ERR_CORRUPT;
+}
+
+// Block -> RGBA32.  grid = (ceil(nblk/256), layer list); one thread per 4x4 block, each pixel row of
+// a block is one 16-byte store, a warp covers 32 adjacent blocks = 512 contiguous bytes per row.
+__global__ void __launch_bounds__(256) k_etc1s_blocks(const Ktx2File *files, const TexState *state, const Ktx2Slice *slices, const uint32_t *layer_list,
+                                                      const uint8_t *S, uint8_t *O) {
+    const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
+    const Ktx2File &f = files[fi];
+    if (f.status || state[fi].status || f.is_uastc) return;
+    const uint32_t nblk = f.bx * f.by, bi = blockIdx.x * 256 + threadIdx.x;
+    if (bi >= nblk) return;
+    const Ktx2Slice &sl = slices[f.first_slice + L];
+    const uint32_t *eps = (const uint32_t *)(S + f.o_endpoints), *sels = (const uint32_t *)(S + f.o_selectors);
+    const uint32_t ep = eps[((const uint16_t *)(S + sl.o_ep))[bi]], se = sels[((const uint16_t *)(S + sl.o_sel))[bi]];
+    uint32_t rows[4][4];
+    etc1s_block_rows(ep, se, rows);
+    if (f.has_alpha) {
+        const Ktx2Slice &al = slices[f.first_slice + f.layers + L];
+        const uint32_t aep = eps[((const uint16_t *)(S + al.o_ep))[bi]], ase = sels[((const uint16_t *)(S + al.o_sel))[bi]];
+        uint32_t acol[4];
+        for (int k = 0; k < 4; k++) acol[k] = (etc1s_color(aep, k) >> 8) & 255u;      // alpha = G of the alpha slice
+        for (int y = 0; y < 4; y++) { const uint32_t rb = (ase >> (8 * y)) & 255u; for (int x = 0; x < 4; x++) rows[y][x] = (rows[y][x] & 0x00ffffffu) | (acol[(rb >> (2 * x)) & 3u] << 24); }
+    }
+    const uint32_t xb = bi % f.bx, yb = bi / f.bx, W = f.width, H = f.height;
+    uint8_t *dst = O + f.o_rgba + (size_t)L * W * H * 4;
+    if (xb * 4 + 4 <= W && (W & 3) == 0) {
+        for (uint32_t y = 0; y < 4 && yb * 4 + y < H; y++)
+            *(uint4 *)(dst + ((size_t)(yb * 4 + y) * W + xb * 4) * 4) = make_uint4(rows[y][0], rows[y][1], rows[y][2], rows[y][3]);
+    } else {
+        for (uint32_t y = 0; y < 4 && yb * 4 + y < H; y++) for (uint32_t x = 0; x < 4 && xb * 4 + x < W; x++)
+            *(uint32_t *)(dst + ((size_t)(yb * 4 + y) * W + xb * 4 + x) * 4) = rows[y][x];
+    }
+}
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+uint64_t take(uint64_t &cur, uint64_t bytes) { uint64_t o = cur; cur = (cur + bytes + 127) / 128 * 128; return o; }
+
+}  // namespace
+
+static const char *kTexStages[] = {"h2d", "globals", "slices", "resolve", "blocks", "d2h"};
+extern "C" const char *uvol_tex_stage_name(int i) { return (i >= 0 && i < 6) ? kTexStages[i] : ""; }
+
+extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target_format, int memory, uvol_texture *out) {
+    if (!ctx || !out || n < 0 || (n > 0 && (!data || !size)) || n >= (1 << 19)) return UVOL_ERR_ARG;
+    if (target_format != UVOL_TEX_RGBA32) { ctx->err = "only UVOL_TEX_RGBA32 is implemented"; return UVOL_ERR_UNSUPPORTED; }
+    UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    for (int i = 0; i < n; i++) memset(&out[i], 0, sizeof out[i]);
+    if (n == 0) return UVOL_OK;
+    const double t_begin = now_ms();
+    cudaStream_t st = ctx->s0;
+    std::vector<Ktx2File> files((size_t)n); std::vector<Ktx2Slice> slices; std::vector<uint32_t> layer_list, uastc_layers;
+    uint64_t blob_bytes = 0, s = 0, o = 0; uint32_t max_blocks = 1; bool any_alpha = false;
+    for (int i = 0; i < n; i++) {
+        Ktx2File &f = files[i]; memset(&f, 0, sizeof f);
+        f.file_off = blob_bytes; f.file_len = (uint32_t)size[i];
+        blob_bytes = align_up(blob_bytes + size[i] + 8, 16);
+        f.status = (data[i] && size[i] < (1ull << 31)) ? uvol_ktx2_parse(data[i], size[i], (uint32_t)i, f, slices) : UVOL_ERR_ARG;
+        if (f.status) { slices.resize(f.first_slice); continue; }
+        if (f.layers > 4095) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(f.first_slice); continue; }
+        const uint64_t nblk = (uint64_t)f.bx * f.by;
+        if (nblk > max_blocks) max_blocks = (uint32_t)nblk;
+        if (f.bx > 4096) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(f.first_slice); continue; }
+        f.o_rgba = take(o, (uint64_t)f.layers * f.width * f.height * 4);
+        if (f.is_uastc) { f.status = UVOL_ERR_UNSUPPORTED; continue; }
+        any_alpha |= f.has_alpha != 0;
+        const uint64_t pool = (uint64_t)f.endpoint_count + f.selector_count + 8192 + 1024;
+        f.o_endpoints = take(s, (uint64_t)f.endpoint_count * 4); f.o_selectors = take(s, (uint64_t)f.selector_count * 4);
+        f.o_huff = take(s, sizeof(HuffTable) * 10); f.o_sorted = take(s, pool * 2 + 32768 + 64);
+        for (size_t k = f.first_slice; k < slices.size(); k++) {
+            Ktx2Slice &sl = slices[k];
+            sl.o_pred = take(s, nblk); sl.o_delta = take(s, nblk * 2); sl.o_sel = take(s, nblk * 2); sl.o_ep = take(s, nblk * 2);
+        }
+        for (uint32_t L = 0; L < f.layers; L++) layer_list.push_back(((uint32_t)i << 12) | L);
+    }
+    const double t_parsed = now_ms();
+    const size_t nsl = slices.size(), nll = layer_list.size(), nul = uastc_layers.size();
+    UVOL_CUDA(ctx, ctx->h_tblob.reserve(blob_bytes + 64));
+    for (int i = 0; i < n; i++) if (data[i]) memcpy((uint8_t *)ctx->h_tblob.p + files[i].file_off, data[i], size[i]);
+    const size_t desc_bytes = sizeof(Ktx2File) * (size_t)n + sizeof(Ktx2Slice) * (nsl + 1) + 4 * (nll + nul + 2);
+    UVOL_CUDA(ctx, ctx->h_tdesc.reserve(desc_bytes));
+    UVOL_CUDA(ctx, ctx->d_tdesc.reserve(desc_bytes));
+    UVOL_CUDA(ctx, ctx->d_tblob.reserve(blob_bytes + 64));
+    UVOL_CUDA(ctx, ctx->d_tslices.reserve(sizeof(TexState) * (size_t)n));
+    UVOL_CUDA(ctx, ctx->d_tscratch.reserve(s + 256));
+    UVOL_CUDA(ctx, ctx->d_out_tex.reserve(o + 256));
+    uint8_t *hd = (uint8_t *)ctx->h_tdesc.p;
+    memcpy(hd, files.data(), sizeof(Ktx2File) * (size_t)n);
+    const size_t off_sl = sizeof(Ktx2File) * (size_t)n, off_ll = off_sl + sizeof(Ktx2Slice) * (nsl + 1), off_ul = off_ll + 4 * (nll + 1);
+    if (nsl) memcpy(hd + off_sl, slices.data(), sizeof(Ktx2Slice) * nsl);
+    if (nll) memcpy(hd + off_ll, layer_list.data(), 4 * nll);
+    if (nul) memcpy(hd + off_ul, uastc_layers.data(), 4 * nul);
+    int ev = 0;
+    auto stamp = [&]() { if (ctx->profile && ev < 20) cudaEventRecord(ctx->ev[ev++], st); };
+    stamp();
+    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_tblob.p, ctx->h_tblob.p, blob_bytes, cudaMemcpyHostToDevice, st));
+    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc.p, hd, desc_bytes, cudaMemcpyHostToDevice, st));
+    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_tslices.p, 0, sizeof(TexState) * (size_t)n, st));
+    stamp();
+    const uint8_t *dD = (const uint8_t *)ctx->d_tdesc.p;
+    const Ktx2File *dF = (const Ktx2File *)dD; const Ktx2Slice *dSl = (const Ktx2Slice *)(dD + off_sl);
+    const uint32_t *dLL = (const uint32_t *)(dD + off_ll), *dUL = (const uint32_t *)(dD + off_ul);
+    TexState *dSt = (TexState *)ctx->d_tslices.p; const uint8_t *dBlob = (const uint8_t *)ctx->d_tblob.p;
+    uint8_t *dS = (uint8_t *)ctx->d_tscratch.p, *dO = (uint8_t *)ctx->d_out_tex.p;
+    uint32_t launches = 0;
+    k_basis_globals<<<n, 32, 0, st>>>(dF, dSt, dBlob, dS, n); launches++;
+    stamp();
+    if (nsl) { k_etc1s_slices<<<(unsigned)nsl, 32, 0, st>>>(dF, dSt, dSl, dBlob, dS, (int)nsl); launches++; }
+    stamp();
+    if (nsl) { k_etc1s_resolve<<<dim3(n, any_alpha ? 2 : 1), 32, 0, st>>>(dF, dSt, dSl, dS, n); launches++; }
+    stamp();
+    if (nll) { k_etc1s_blocks<<<dim3((max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO); launches++; }
+    if (nul) { uvol_uastc_launch(dF, (const int32_t *)dSt, dBlob, dO, dUL, (int)nul, max_blocks, st); launches++; }
+    stamp();
+    const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
+    UVOL_CUDA(ctx, ctx->h_tout.reserve(st_bytes + (memory == UVOL_MEM_HOST ? o + 256 : 0)));
+    TexState *hSt = (TexState *)ctx->h_tout.p; uint8_t *hO = (uint8_t *)ctx->h_tout.p + st_bytes;
+    UVOL_CUDA(ctx, cudaMemcpyAsync(hSt, dSt, sizeof(TexState) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(hO, dO, o, cudaMemcpyDeviceToHost, st));
+    stamp();
+    UVOL_CUDA(ctx, cudaStreamSynchronize(st));
+    UVOL_CUDA(ctx, cudaGetLastError());
+    uint8_t *base = memory == UVOL_MEM_HOST ? hO : dO; uint64_t bytes_out = 0;
+    for (int i = 0; i < n; i++) {
+        const Ktx2File &f = files[i]; uvol_texture &t = out[i];
+        t.status = f.status ? f.status : hSt[i].status;
+        if (t.status) continue;
+        t.width = f.width; t.height = f.height; t.layers = f.layers; t.format = UVOL_TEX_RGBA32; t.has_alpha = f.has_alpha;
+        t.dfd_transfer = f.dfd_transfer; t.dfd_flags = f.dfd_flags;
+        t.bytes = (uint64_t)f.layers * f.width * f.height * 4; t.data = base + f.o_rgba; bytes_out += t.bytes;
+    }
+    uvol_stats &sx = ctx->stats;
+    sx.host_parse_ms = t_parsed - t_begin; sx.total_ms = now_ms() - t_begin; sx.kernel_launches = launches;
+    for (int i = 0; i < n; i++) sx.bytes_in += size[i];
+    sx.bytes_out = bytes_out; sx.scratch_bytes = s;
+    if (ctx->profile) {
+        sx.num_stages = (uint32_t)(ev - 1);
+        for (int k = 0; k + 1 < ev; k++) cudaEventElapsedTime(&sx.stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);
+        float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[ev - 1]); sx.device_ms = tot;
+    }
+    return UVOL_OK;
+}

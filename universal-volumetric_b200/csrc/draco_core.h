@@ -1,0 +1,579 @@
+// draco_core.h -- per-unit device logic of the Draco mesh decode (one function per serial unit or
+// per parallel element).  Kernels in draco_decode.cu are thin wrappers that pick the unit from
+// blockIdx/threadIdx.  The functions are __host__ __device__ so tests/tools/draco_emu.cpp can run
+// the very same code on the host to check the logic without a GPU (a debugging harness, not a
+// product path: libuvol_b200.so contains no host decode).
+//
+// Algorithm: SURVEY.md Appendix A (Draco bitstream 2.2, edgebreaker).  Reference call site:
+// src/lib/DRACOLoader.js:470-590.
+#pragma once
+#include "uvol_internal.h"
+
+#if defined(__CUDACC__)
+#define UVOL_HD __host__ __device__ __forceinline__
+#else
+#define UVOL_HD static inline
+#endif
+
+#define DINV (-1)
+
+UVOL_HD int cnext(int c) { return (c % 3 == 2) ? c - 2 : c + 1; }
+UVOL_HD int cprev(int c) { return (c % 3 == 0) ? c + 2 : c - 1; }
+
+// ---------------------------------------------------------------------------------------------
+// rABS bit stream (A.2): L = 4096, byte IO.
+struct Rabs { const uint8_t *buf; int off; uint32_t state, p; };
+UVOL_HD bool rabs_init(Rabs &a, const uint8_t *file, const RabsStream &s) {
+    const uint8_t *b = file + s.data_off; int n = (int)s.data_len;
+    a.buf = b; a.p = 256u - s.prob_zero;
+    unsigned x = b[n - 1] >> 6;
+    if (x == 0) { a.off = n - 1; a.state = b[n - 1] & 0x3f; }
+    else if (x == 1) { if (n < 2) return false; a.off = n - 2; a.state = (b[n - 2] | (b[n - 1] << 8)) & 0x3fff; }
+    else if (x == 2) { if (n < 3) return false; a.off = n - 3; a.state = (b[n - 3] | (b[n - 2] << 8) | (b[n - 1] << 16)) & 0x3fffff; }
+    else return false;
+    a.state += 4096u;
+    return true;
+}
+UVOL_HD int rabs_bit(Rabs &a) {
+    if (a.state < 4096u && a.off > 0) a.state = a.state * 256u + a.buf[--a.off];
+    uint32_t x = a.state, q = x >> 8, rem = x & 255u, xn = q * a.p;
+    if (rem < a.p) { a.state = xn + rem; return 1; }
+    a.state = x - xn - a.p; return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rANS symbol run (A.2).  cum[alphabet+1] and bucket[257] are prepared by the caller (shared
+// memory in the kernel): bucket[b] = first symbol whose range ends above b << (pb-8).
+struct RansTables { const uint32_t *cum; const uint16_t *bucket; uint32_t alphabet, pb; };
+
+UVOL_HD uint32_t rans_bucket_symbol(const uint32_t *cum, uint32_t alphabet, uint32_t target) {
+    // first s with cum[s+1] > target
+    uint32_t lo = 0, hi = alphabet - 1;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (cum[mid + 1] > target) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
+// Decodes `count` symbols.  mode 0: u8 out; mode 1: int32 zig-zag folded (A.2 "symbols -> signed");
+// mode 2: int32 raw (positive corrections).  Returns 0 or an error status.
+UVOL_HD int rans_decode_run(const uint8_t *data, uint32_t nbytes, const RansTables &t, uint32_t count, int mode, void *out) {
+    if (count == 0) return UVOL_OK;
+    if (nbytes == 0) return UVOL_ERR_CORRUPT;
+    const uint32_t pb = t.pb, prec = 1u << pb, lbase = prec * 4u, shift = pb - 8;
+    unsigned x = data[nbytes - 1] >> 6, k = x + 1;
+    if (nbytes < k) return UVOL_ERR_CORRUPT;
+    uint32_t st = 0;
+    for (unsigned i = 0; i < k; i++) st |= (uint32_t)data[nbytes - k + i] << (8 * i);
+    st &= (1u << (8 * k - 2)) - 1u;
+    int off = (int)(nbytes - k);
+    st += lbase;
+    uint8_t *o8 = (uint8_t *)out; int32_t *o32 = (int32_t *)out;
+    for (uint32_t i = 0; i < count; i++) {
+        while (st < lbase && off > 0) st = st * 256u + data[--off];
+        uint32_t q = st >> pb, rem = st & (prec - 1);
+        uint32_t s = t.bucket[rem >> shift];
+        while (t.cum[s + 1] <= rem) s++;
+        uint32_t c0 = t.cum[s];
+        st = q * (t.cum[s + 1] - c0) + rem - c0;
+        if (mode == 0) o8[i] = (uint8_t)s;
+        else if (mode == 1) o32[i] = (s & 1) ? -(int32_t)(s >> 1) - 1 : (int32_t)(s >> 1);
+        else o32[i] = (int32_t)s;
+    }
+    return UVOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Edgebreaker connectivity (A.3), one frame, serial.
+struct EbMem {
+    int *opp, *c2v, *lmc, *val, *stack, *skey, *sval, *invalid; uint8_t *hole;
+    const uint8_t *ctxsym[6];
+};
+
+UVOL_HD int b_swl(const int *opp, int c) { if (c < 0) return DINV; int o = opp[cnext(c)]; return o < 0 ? DINV : cnext(o); }
+UVOL_HD int b_swr(const int *opp, int c) { if (c < 0) return DINV; int o = opp[cprev(c)]; return o < 0 ? DINV : cprev(o); }
+
+UVOL_HD int eb_decode_frame(const DracoFrame &f, const uint8_t *file, const uint32_t *aux, EbMem &m, uint32_t *out_vertex_slots) {
+    const int F = (int)f.nf, maxv = (int)(f.nv_enc + f.nsplit), nsym = (int)f.nsym;
+    int *opp = m.opp, *c2v = m.c2v, *lmc = m.lmc, *val = m.val, *stack = m.stack;
+    uint8_t *hole = m.hole;
+    int cnt[6]; for (int i = 0; i < 6; i++) cnt[i] = (int)f.ctx[i].count;
+    const uint32_t *ts = aux + f.ts_off; int ts_top = (int)f.nts, nsa = 0;
+    int nverts = 0, numf = 0, sp = 0, ninv = 0, active_ctx = -1;
+    const uint8_t *symbuf = file + f.stdsym_off; uint64_t sym_bp = 0; const uint64_t sym_bits = (uint64_t)f.stdsym_len * 8;
+#define EB_FAIL(code) return (code)
+#define EB_ADDV(dst) do { if (nverts >= maxv) EB_FAIL(UVOL_ERR_CORRUPT); lmc[nverts] = DINV; val[nverts] = 0; hole[nverts] = 1; (dst) = nverts++; } while (0)
+#define EB_SETOPP(a, b) do { opp[(a)] = (b); opp[(b)] = (a); } while (0)
+    for (int sid = 0; sid < nsym; sid++) {
+        if (numf >= F) EB_FAIL(UVOL_ERR_CORRUPT);
+        const int face = numf++, c0 = 3 * face; int s, chk = 0;
+        if (f.trav == 2) {
+            if (active_ctx >= 0) {
+                if (cnt[active_ctx] <= 0) EB_FAIL(UVOL_ERR_CORRUPT);
+                s = m.ctxsym[active_ctx][--cnt[active_ctx]];
+                if (s > 4) EB_FAIL(UVOL_ERR_CORRUPT);
+            } else s = 4;
+        } else {
+            if (sym_bp >= sym_bits) EB_FAIL(UVOL_ERR_TRUNCATED);
+            int b0 = (symbuf[sym_bp >> 3] >> (sym_bp & 7)) & 1; sym_bp++;
+            if (!b0) s = 0;
+            else {
+                if (sym_bp + 2 > sym_bits) EB_FAIL(UVOL_ERR_TRUNCATED);
+                int suf = (symbuf[sym_bp >> 3] >> (sym_bp & 7)) & 1; sym_bp++;
+                suf |= ((symbuf[sym_bp >> 3] >> (sym_bp & 7)) & 1) << 1; sym_bp++;
+                s = suf + 1;     // S=1 L=2 R=3 E=4
+            }
+        }
+        opp[c0] = DINV; opp[c0 + 1] = DINV; opp[c0 + 2] = DINV;
+        if (s == 0) {                       // C
+            if (sp == 0) EB_FAIL(UVOL_ERR_CORRUPT);
+            int a = stack[sp - 1]; int vx = c2v[cnext(a)];
+            if (lmc[vx] < 0) EB_FAIL(UVOL_ERR_CORRUPT);
+            int b = cnext(lmc[vx]);
+            if (a == b || opp[a] >= 0 || opp[b] >= 0) EB_FAIL(UVOL_ERR_CORRUPT);
+            EB_SETOPP(a, c0 + 1); EB_SETOPP(b, c0 + 2);
+            int vap = c2v[cprev(a)], vbn = c2v[cnext(b)];
+            if (vx == vap || vx == vbn) EB_FAIL(UVOL_ERR_CORRUPT);
+            c2v[c0] = vx; c2v[c0 + 1] = vbn; c2v[c0 + 2] = vap;
+            lmc[vap] = c0 + 2; hole[vx] = 0; stack[sp - 1] = c0;
+        } else if (s == 3 || s == 2) {      // R / L
+            if (sp == 0) EB_FAIL(UVOL_ERR_CORRUPT);
+            int a = stack[sp - 1]; if (opp[a] >= 0) EB_FAIL(UVOL_ERR_CORRUPT);
+            int oc, cl, cr;
+            if (s == 3) { oc = c0 + 2; cl = c0 + 1; cr = c0; } else { oc = c0 + 1; cl = c0; cr = c0 + 2; }
+            EB_SETOPP(oc, a);
+            int nvx; EB_ADDV(nvx);
+            c2v[oc] = nvx; lmc[nvx] = oc;
+            int vr = c2v[cprev(a)]; c2v[cr] = vr; lmc[vr] = cr;
+            c2v[cl] = c2v[cnext(a)];
+            stack[sp - 1] = c0; chk = 1;
+        } else if (s == 1) {                // S
+            if (sp == 0) EB_FAIL(UVOL_ERR_CORRUPT);
+            int b = stack[--sp];
+            for (int k = 0; k < nsa; k++) if (m.skey[k] == sid) { stack[sp++] = m.sval[k]; break; }
+            if (sp == 0) EB_FAIL(UVOL_ERR_CORRUPT);
+            int a = stack[sp - 1];
+            if (a == b || opp[a] >= 0 || opp[b] >= 0) EB_FAIL(UVOL_ERR_CORRUPT);
+            EB_SETOPP(a, c0 + 2); EB_SETOPP(b, c0 + 1);
+            int vp = c2v[cprev(a)];
+            c2v[c0] = vp; c2v[c0 + 1] = c2v[cnext(a)];
+            int vbp = c2v[cprev(b)]; c2v[c0 + 2] = vbp; lmc[vbp] = c0 + 2;
+            int cn = cnext(b); const int vn = c2v[cn];
+            val[vp] += val[vn];
+            lmc[vp] = lmc[vn];
+            const int first = cn; int guard = 0;
+            while (cn >= 0) { c2v[cn] = vp; cn = b_swl(opp, cn); if (cn == first || ++guard > 3 * F) EB_FAIL(UVOL_ERR_CORRUPT); }
+            lmc[vn] = DINV; m.invalid[ninv++] = vn;
+            stack[sp - 1] = c0;
+        } else {                            // E
+            int v0, v1, v2; EB_ADDV(v0); EB_ADDV(v1); EB_ADDV(v2);
+            c2v[c0] = v0; c2v[c0 + 1] = v1; c2v[c0 + 2] = v2;
+            lmc[v0] = c0; lmc[v1] = c0 + 1; lmc[v2] = c0 + 2;
+            stack[sp++] = c0; chk = 1;
+        }
+        if (f.trav == 2) {
+            const int c = stack[sp - 1], vn_ = c2v[cnext(c)], vp_ = c2v[cprev(c)];
+            if (s == 0 || s == 1) { val[vn_] += 1; val[vp_] += 1; }
+            else if (s == 3) { val[c2v[c]] += 1; val[vn_] += 1; val[vp_] += 2; }
+            else if (s == 2) { val[c2v[c]] += 1; val[vn_] += 2; val[vp_] += 1; }
+            else { val[c2v[c]] += 2; val[vn_] += 2; val[vp_] += 2; }
+            int v = val[vn_]; v = v < 2 ? 2 : (v > 7 ? 7 : v);
+            active_ctx = v - 2;
+        }
+        if (chk) {
+            const uint32_t enc_id = (uint32_t)(nsym - sid - 1);
+            while (ts_top > 0 && ts[3 * (ts_top - 1)] == enc_id) {
+                --ts_top;
+                const int top = stack[sp - 1];
+                m.skey[nsa] = nsym - (int)ts[3 * ts_top + 1] - 1;
+                m.sval[nsa] = ts[3 * ts_top + 2] == 1 ? cnext(top) : cprev(top);
+                nsa++;
+            }
+        }
+    }
+    // start faces
+    if (sp > 0) {
+        Rabs sf; if (!rabs_init(sf, file, f.start_faces)) EB_FAIL(UVOL_ERR_CORRUPT);
+        while (sp > 0) {
+            const int corner = stack[--sp];
+            if (rabs_bit(sf)) {
+                const int a = corner, vn = c2v[cnext(a)];
+                if (lmc[vn] < 0) EB_FAIL(UVOL_ERR_CORRUPT);
+                const int cb = cnext(lmc[vn]), vx = c2v[cnext(cb)];
+                if (lmc[vx] < 0) EB_FAIL(UVOL_ERR_CORRUPT);
+                const int cc = cnext(lmc[vx]);
+                if (a == cb || cb == cc || a == cc || opp[a] >= 0 || opp[cb] >= 0 || opp[cc] >= 0) EB_FAIL(UVOL_ERR_CORRUPT);
+                const int vp = c2v[cnext(cc)];
+                if (numf >= F) EB_FAIL(UVOL_ERR_CORRUPT);
+                const int nc = 3 * numf++;
+                EB_SETOPP(nc, a); EB_SETOPP(nc + 1, cb); EB_SETOPP(nc + 2, cc);
+                c2v[nc] = vx; c2v[nc + 1] = vp; c2v[nc + 2] = vn;
+                hole[vx] = 0; hole[vp] = 0; hole[vn] = 0;
+            }
+        }
+    }
+    if (numf != F) EB_FAIL(UVOL_ERR_CORRUPT);
+    // fold isolated vertices away: the last valid vertex moves into each freed slot (defines final ids)
+    {
+        int num_vertices = nverts;
+        for (int k = 0; k < ninv; k++) {
+            const int iv = m.invalid[k];
+            int src = num_vertices - 1;
+            while (src >= 0 && lmc[src] == DINV) src = --num_vertices - 1;
+            if (src < iv) continue;
+            const int cs = lmc[src]; int c = cs, left = 1, guard = 0;
+            while (c >= 0) {
+                int nx;
+                if (left) { nx = b_swl(opp, c); if (nx < 0) { nx = b_swr(opp, cs); left = 0; } else if (nx == cs) nx = DINV; }
+                else nx = b_swr(opp, c);
+                if (c2v[c] != src || ++guard > 3 * F) EB_FAIL(UVOL_ERR_CORRUPT);
+                c2v[c] = iv; c = nx;
+            }
+            lmc[iv] = lmc[src]; lmc[src] = DINV;
+            hole[iv] = hole[src]; hole[src] = 0;
+            num_vertices--;
+        }
+    }
+    *out_vertex_slots = (uint32_t)nverts;
+    return UVOL_OK;
+#undef EB_FAIL
+#undef EB_ADDV
+#undef EB_SETOPP
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attribute corner table view: Opposite() is cut at seam edges (A.5).
+struct TableView { const int *opp; const int *c2v_base; const uint8_t *eos; const int *ac2v; const uint8_t *vos; };
+UVOL_HD int t_opp(const TableView &t, int c) { if (c < 0) return DINV; if (t.eos && t.eos[c]) return DINV; return t.opp[c]; }
+UVOL_HD int t_vert(const TableView &t, int c) { return t.ac2v ? t.ac2v[c] : t.c2v_base[c]; }
+UVOL_HD int t_swl(const TableView &t, int c) { if (c < 0) return DINV; int o = t_opp(t, cnext(c)); return o < 0 ? DINV : cnext(o); }
+UVOL_HD int t_swr(const TableView &t, int c) { if (c < 0) return DINV; int o = t_opp(t, cprev(c)); return o < 0 ? DINV : cprev(o); }
+
+// Seam marking for one corner c of attribute i whose edge is a seam (AddSeamEdge).
+UVOL_HD void seam_mark(int c, const int *opp, const int *c2v, uint8_t *eos, uint8_t *vos) {
+    eos[c] = 1; vos[c2v[cnext(c)]] = 1; vos[c2v[cprev(c)]] = 1;
+    int o = opp[c];
+    if (o >= 0) { eos[o] = 1; vos[c2v[cnext(o)]] = 1; vos[c2v[cprev(o)]] = 1; }
+}
+
+// RecomputeVertices, per base vertex: pass 0 counts the attribute vertices spawned by v and records
+// the first corner; pass 1 writes ids starting from `first_id`.
+UVOL_HD int attr_vertex_fan(int v, const int *opp, const int *lmc, const uint8_t *eos, const uint8_t *vos,
+                            int *afirst, int *ac2v, int first_id, int pass, int F, int *err) {
+    int c = lmc[v];
+    if (c < 0) return 0;
+    int fc;
+    if (pass == 0) {
+        fc = c;
+        if (vos[v]) {
+            TableView t{opp, nullptr, eos, nullptr, nullptr};
+            int x = t_swl(t, fc), guard = 0;
+            while (x >= 0) { fc = x; x = t_swl(t, x); if (x == c || ++guard > 3 * F) { *err = 1; return 0; } }
+        }
+        afirst[v] = fc;
+    } else fc = afirst[v];
+    int n = 1, fid = first_id, guard = 0;
+    if (pass) ac2v[fc] = fid;
+    int x = b_swr(opp, fc);
+    while (x >= 0 && x != fc) {
+        if (eos[cnext(x)]) { n++; fid++; }
+        if (pass) ac2v[x] = fid;
+        x = b_swr(opp, x);
+        if (++guard > 3 * F) { *err = 1; return 0; }
+    }
+    return n;
+}
+
+// AssignPointsToCorners, per base vertex (A.3): pass 0 counts points and records the
+// deduplication start corner; pass 1 writes corner->point ids and point->corner.
+UVOL_HD int point_fan(int v, const int *opp, const int *c2v, const int *lmc, const uint8_t *hole, int nad,
+                      const uint8_t *const *vos, const int *const *ac2v, int *pfirst, uint32_t *c2p, int *p2c,
+                      int first_id, int pass, int F, int *err) {
+    int c = lmc[v];
+    if (c < 0) return 0;
+    int dfc;
+    if (pass == 0) {
+        dfc = c;
+        if (!hole[v]) {
+            for (int i = 0; i < nad; i++) {
+                if (!vos[i][c2v[c]]) continue;
+                const int vid = ac2v[i][c]; int x = b_swr(opp, c), found = 0, guard = 0;
+                while (x != c) {
+                    if (x < 0 || ++guard > 3 * F) { *err = 1; return 0; }
+                    if (ac2v[i][x] != vid) { dfc = x; found = 1; break; }
+                    x = b_swr(opp, x);
+                }
+                if (found) break;
+            }
+        }
+        pfirst[v] = dfc;
+    } else dfc = pfirst[v];
+    int n = 1, pid = first_id, guard = 0;
+    if (pass) { c2p[dfc] = (uint32_t)pid; p2c[pid] = dfc; }
+    int pc = dfc; c = b_swr(opp, dfc);
+    while (c >= 0 && c != dfc) {
+        int seam = 0;
+        for (int i = 0; i < nad; i++) if (ac2v[i][c] != ac2v[i][pc]) { seam = 1; break; }
+        if (seam) { n++; pid++; if (pass) p2c[pid] = c; }
+        if (pass) c2p[c] = (uint32_t)pid;
+        pc = c; c = b_swr(opp, c);
+        if (++guard > 3 * F) { *err = 1; return 0; }
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depth-first traversal (A.3 "Traversal / sequencing"), one (frame, table), serial.
+// v2d1[v] = entry + 1 (0 = unvisited, zero-initialised by the caller); fvis zero-initialised.
+UVOL_HD int traverse_table(const TableView &t, const int *lmc_base, int F, uint8_t *fvis, int *v2d1, int *d2c, int *st, int max_entries, uint32_t *out_n) {
+    int n = 0;
+#define TR_VISIT(v, c) do { if (n >= max_entries) return UVOL_ERR_CORRUPT; v2d1[(v)] = n + 1; d2c[n++] = (c); } while (0)
+#define TR_FVIS(c) ((c) < 0 ? 1 : fvis[(c) / 3])
+    for (int f = 0; f < F; f++) {
+        if (fvis[f]) continue;
+        int c = 3 * f, sp = 0; st[sp++] = c;
+        const int nvx = t_vert(t, cnext(c)), pvx = t_vert(t, cprev(c));
+        if (nvx < 0 || pvx < 0) return UVOL_ERR_CORRUPT;
+        if (!v2d1[nvx]) TR_VISIT(nvx, cnext(c));
+        if (!v2d1[pvx]) TR_VISIT(pvx, cprev(c));
+        while (sp > 0) {
+            c = st[sp - 1];
+            if (c < 0 || fvis[c / 3]) { sp--; continue; }
+            for (;;) {
+                fvis[c / 3] = 1;
+                const int v = t_vert(t, c);
+                if (v < 0) return UVOL_ERR_CORRUPT;
+                if (!v2d1[v]) {
+                    int ob;
+                    if (t.ac2v) ob = t.vos[t.c2v_base[c]];                      // IsOnBoundary == IsCornerOnSeam(leftmost)
+                    else ob = b_swl(t.opp, lmc_base[v]) == DINV;
+                    TR_VISIT(v, c);
+                    if (!ob) { c = t_opp(t, cnext(c)); if (c < 0) return UVOL_ERR_CORRUPT; continue; }
+                }
+                const int rc = t_opp(t, cnext(c)), lc = t_opp(t, cprev(c));
+                if (TR_FVIS(rc)) {
+                    if (TR_FVIS(lc)) { sp--; break; }
+                    c = lc;
+                } else {
+                    if (TR_FVIS(lc)) c = rc;
+                    else { st[sp - 1] = lc; st[sp++] = rc; break; }
+                }
+            }
+        }
+    }
+#undef TR_VISIT
+#undef TR_FVIS
+    *out_n = (uint32_t)n;
+    return UVOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Prediction reversal.
+// Parallelogram parents of entry p (element-parallel): par = {opp entry, next entry, prev entry} or {-1,..}.
+UVOL_HD void parallelogram_parents(int p, const TableView &t, const int *d2c, const int *v2d1, int *par4) {
+    int eo = -1, en = -1, ep = -1;
+    const int ci = d2c[p], oci = t_opp(t, ci);
+    if (oci >= 0) {
+        eo = v2d1[t_vert(t, oci)] - 1; en = v2d1[t_vert(t, cnext(oci))] - 1; ep = v2d1[t_vert(t, cprev(oci))] - 1;
+        if (!(eo < p && en < p && ep < p && eo >= 0 && en >= 0 && ep >= 0)) eo = en = ep = -1;
+    }
+    par4[0] = eo; par4[1] = en; par4[2] = ep; par4[3] = 0;
+}
+
+UVOL_HD int32_t wrap_value(long long pred, int32_t corr, int32_t mn, int32_t mx) {
+    if (pred > mx) pred = mx;
+    if (pred < mn) pred = mn;
+    int32_t o = (int32_t)pred + corr;
+    const int32_t md = 1 + mx - mn;
+    if (o > mx) o -= md; else if (o < mn) o += md;
+    return o;
+}
+
+// One component k of the DIFFERENCE / PARALLELOGRAM + WRAP chain over all entries (serial in p).
+UVOL_HD void predict_wrap_component(int k, int nc, int n, int use_par, const int *par4, const int32_t *corr, int32_t *val, int32_t mn, int32_t mx) {
+    if (n <= 0) return;
+    val[k] = wrap_value(0, corr[k], mn, mx);
+    for (int p = 1; p < n; p++) {
+        long long pred;
+        int eo = use_par ? par4[4 * p] : -1;
+        if (eo >= 0) { const int en = par4[4 * p + 1], ep = par4[4 * p + 2]; pred = ((long long)val[en * nc + k] + val[ep * nc + k]) - val[eo * nc + k]; }
+        else pred = val[(p - 1) * nc + k];
+        val[p * nc + k] = wrap_value(pred, corr[p * nc + k], mn, mx);
+    }
+}
+
+UVOL_HD unsigned long long int_sqrt_u64(unsigned long long n) {
+    if (n == 0) return 0;
+    unsigned long long a = n, r = 1;
+    while (a >= 2) { r *= 2; a /= 4; }
+    do { r = (r + n / r) / 2; } while (r * r > n);
+    return r;
+}
+
+// TEX_COORDS_PORTABLE (A.5): position-only terms of entry p (element-parallel).
+struct UvPrep { int32_t nd, pd; long long pn2, dot, ns; };
+UVOL_HD void uv_prepare(int p, const TableView &t, const int *d2c, const int *v2d1, const int *pos_v2d1, const int32_t *pos, UvPrep &o) {
+    const int c = d2c[p], ncn = cnext(c), pcn = cprev(c);
+    o.nd = v2d1[t_vert(t, ncn)] - 1; o.pd = v2d1[t_vert(t, pcn)] - 1;
+    o.pn2 = 0; o.dot = 0; o.ns = 0;
+    if (o.pd < p && o.nd < p && o.pd >= 0 && o.nd >= 0) {
+        const int32_t *T = pos + 3 * (pos_v2d1[t.c2v_base[c]] - 1), *N = pos + 3 * (pos_v2d1[t.c2v_base[ncn]] - 1), *P = pos + 3 * (pos_v2d1[t.c2v_base[pcn]] - 1);
+        long long pn[3] = {(long long)P[0] - N[0], (long long)P[1] - N[1], (long long)P[2] - N[2]};
+        long long cn[3] = {(long long)T[0] - N[0], (long long)T[1] - N[1], (long long)T[2] - N[2]};
+        const long long pn2 = pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2];
+        o.pn2 = pn2;
+        if (pn2 != 0) {
+            const long long dot = pn[0] * cn[0] + pn[1] * cn[1] + pn[2] * cn[2];
+            long long dx[3];
+            for (int k = 0; k < 3; k++) { long long xp = N[k] + (dot * pn[k]) / pn2; dx[k] = T[k] - xp; }
+            const unsigned long long cx2 = (unsigned long long)(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+            o.dot = dot; o.ns = (long long)int_sqrt_u64(cx2 * (unsigned long long)pn2);
+        }
+    }
+}
+// The serial UV chain.  orient[] holds the decoded orientation flags (consumed from the back).
+UVOL_HD int predict_uv_chain(int n, const UvPrep *prep, const int32_t *corr, int32_t *uv, const uint8_t *orient, int num_orient, int32_t mn, int32_t mx) {
+    int nor = num_orient;
+    for (int p = 0; p < n; p++) {
+        const UvPrep q = prep[p];
+        long long pred[2]; int have = 0;
+        if (q.pd < p && q.nd < p && q.pd >= 0 && q.nd >= 0) {
+            const long long nuv[2] = {uv[q.nd * 2], uv[q.nd * 2 + 1]}, puv[2] = {uv[q.pd * 2], uv[q.pd * 2 + 1]};
+            if (nuv[0] == puv[0] && nuv[1] == puv[1]) { pred[0] = puv[0]; pred[1] = puv[1]; have = 1; }
+            else if (q.pn2 != 0) {
+                const long long pnuv[2] = {puv[0] - nuv[0], puv[1] - nuv[1]};
+                const long long xuv[2] = {nuv[0] * q.pn2 + q.dot * pnuv[0], nuv[1] * q.pn2 + q.dot * pnuv[1]};
+                const long long cxuv[2] = {pnuv[1] * q.ns, -pnuv[0] * q.ns};
+                if (nor <= 0) return UVOL_ERR_CORRUPT;
+                if (orient[--nor]) { pred[0] = (xuv[0] + cxuv[0]) / q.pn2; pred[1] = (xuv[1] + cxuv[1]) / q.pn2; }
+                else { pred[0] = (xuv[0] - cxuv[0]) / q.pn2; pred[1] = (xuv[1] - cxuv[1]) / q.pn2; }
+                pred[0] = (int32_t)pred[0]; pred[1] = (int32_t)pred[1];
+                have = 1;
+            }
+        }
+        if (!have) {
+            if (q.nd < p && q.nd >= 0) { pred[0] = uv[q.nd * 2]; pred[1] = uv[q.nd * 2 + 1]; }
+            else if (p > 0) { pred[0] = uv[(p - 1) * 2]; pred[1] = uv[(p - 1) * 2 + 1]; }
+            else { pred[0] = pred[1] = 0; }
+        }
+        uv[p * 2] = wrap_value(pred[0], corr[p * 2], mn, mx);
+        uv[p * 2 + 1] = wrap_value(pred[1], corr[p * 2 + 1], mn, mx);
+    }
+    return UVOL_OK;
+}
+
+// GEOMETRIC_NORMAL + canonicalised octahedron (A.5), element-parallel over entries.
+UVOL_HD void oct_invert_diamond(int32_t &s, int32_t &t, int32_t CEN) {
+    int32_t ss, st;
+    if (s >= 0 && t >= 0) { ss = 1; st = 1; } else if (s <= 0 && t <= 0) { ss = -1; st = -1; }
+    else { ss = s > 0 ? 1 : -1; st = t > 0 ? 1 : -1; }
+    const int32_t cs = ss * CEN, ct = st * CEN; int32_t us = 2 * s - cs, ut = 2 * t - ct;
+    if (ss * st >= 0) { int32_t tmp = us; us = -ut; ut = -tmp; } else { int32_t tmp = us; us = ut; ut = tmp; }
+    us += cs; ut += ct; s = us / 2; t = ut / 2;
+}
+UVOL_HD void oct_rotate(int32_t &x, int32_t &y, int k) {
+    const int32_t a = x, b = y;
+    if (k == 1) { x = b; y = -a; } else if (k == 2) { x = -a; y = -b; } else if (k == 3) { x = -b; y = a; }
+}
+UVOL_HD int32_t iabs32(int32_t v) { return v < 0 ? -v : v; }
+UVOL_HD long long iabs64(long long v) { return v < 0 ? -v : v; }
+
+UVOL_HD void normal_entry(int p, const TableView &t, const int *d2c, const int *pos_v2d1, const int32_t *pos, const int32_t *corr,
+                          const uint8_t *flips, int32_t max_q, int32_t *val) {
+    const int32_t MAXQ = max_q, MAXV = MAXQ - 1, CEN = MAXV / 2;
+    const int c0 = d2c[p];
+    const int32_t *C = pos + 3 * (pos_v2d1[t.c2v_base[c0]] - 1);
+    long long nrm[3] = {0, 0, 0};
+    int c = c0, left = 1;
+    while (c >= 0) {
+        const int32_t *N = pos + 3 * (pos_v2d1[t.c2v_base[cnext(c)]] - 1), *P = pos + 3 * (pos_v2d1[t.c2v_base[cprev(c)]] - 1);
+        const long long dn[3] = {(long long)N[0] - C[0], (long long)N[1] - C[1], (long long)N[2] - C[2]};
+        const long long dp[3] = {(long long)P[0] - C[0], (long long)P[1] - C[1], (long long)P[2] - C[2]};
+        nrm[0] += dn[1] * dp[2] - dn[2] * dp[1];
+        nrm[1] += dn[2] * dp[0] - dn[0] * dp[2];
+        nrm[2] += dn[0] * dp[1] - dn[1] * dp[0];
+        int nx;
+        if (left) { nx = t_swl(t, c); if (nx < 0) { nx = t_swr(t, c0); left = 0; } else if (nx == c0) nx = DINV; }
+        else nx = t_swr(t, c);
+        c = nx;
+    }
+    long long asum = iabs64(nrm[0]) + iabs64(nrm[1]) + iabs64(nrm[2]);
+    if (asum > (1 << 29)) { const long long q = asum / (1 << 29); nrm[0] /= q; nrm[1] /= q; nrm[2] /= q; }
+    int32_t v[3] = {(int32_t)nrm[0], (int32_t)nrm[1], (int32_t)nrm[2]};
+    const long long as2 = (long long)iabs32(v[0]) + iabs32(v[1]) + iabs32(v[2]);
+    if (as2 == 0) v[0] = CEN;
+    else {
+        v[0] = (int32_t)(((long long)v[0] * CEN) / as2);
+        v[1] = (int32_t)(((long long)v[1] * CEN) / as2);
+        if (v[2] >= 0) v[2] = CEN - iabs32(v[0]) - iabs32(v[1]); else v[2] = -(CEN - iabs32(v[0]) - iabs32(v[1]));
+    }
+    if (flips[p]) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }
+    int32_t s, tt;
+    if (v[0] >= 0) { s = v[1] + CEN; tt = v[2] + CEN; }
+    else { s = v[1] < 0 ? iabs32(v[2]) : MAXV - iabs32(v[2]); tt = v[2] < 0 ? iabs32(v[1]) : MAXV - iabs32(v[1]); }
+    if ((s == 0 && tt == 0) || (s == 0 && tt == MAXV) || (s == MAXV && tt == 0)) { s = MAXV; tt = MAXV; }
+    else if (s == 0 && tt > CEN) tt = CEN - (tt - CEN);
+    else if (s == MAXV && tt < CEN) tt = CEN + (CEN - tt);
+    else if (tt == MAXV && s < CEN) s = CEN + (CEN - s);
+    else if (tt == 0 && s > CEN) s = CEN - (s - CEN);
+    int32_t px = s - CEN, py = tt - CEN;
+    const int ind = iabs32(px) + iabs32(py) <= CEN;
+    if (!ind) oct_invert_diamond(px, py, CEN);
+    const int bl = (px == 0 && py == 0) || (px < 0 && py <= 0);
+    int rc;
+    if (px == 0) rc = py == 0 ? 0 : (py > 0 ? 3 : 1);
+    else if (px > 0) rc = py >= 0 ? 2 : 1;
+    else rc = py <= 0 ? 0 : 3;
+    if (!bl) oct_rotate(px, py, rc);
+    int32_t o0 = px + corr[p * 2], o1 = py + corr[p * 2 + 1];
+    o0 = o0 > CEN ? o0 - MAXQ : (o0 < -CEN ? o0 + MAXQ : o0);
+    o1 = o1 > CEN ? o1 - MAXQ : (o1 < -CEN ? o1 + MAXQ : o1);
+    if (!bl) oct_rotate(o0, o1, (4 - rc) % 4);
+    if (!ind) oct_invert_diamond(o0, o1, CEN);
+    val[p * 2] = o0 + CEN; val[p * 2 + 1] = o1 + CEN;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 tails.  Two separately rounded operations each (no FMA contraction), matching the
+// reference's WASM build; on the device the _rn intrinsics forbid contraction, on the host the
+// emulation harness is built with -ffp-contract=off.
+#if defined(__CUDA_ARCH__)
+#define UVOL_FMUL(a, b) __fmul_rn((a), (b))
+#define UVOL_FADD(a, b) __fadd_rn((a), (b))
+#define UVOL_FSUB(a, b) __fsub_rn((a), (b))
+#define UVOL_FDIV(a, b) __fdiv_rn((a), (b))
+#define UVOL_FSQRT(a) __fsqrt_rn((a))
+#define UVOL_FABS(a) fabsf((a))
+#else
+#include <math.h>
+#define UVOL_FMUL(a, b) ((a) * (b))
+#define UVOL_FADD(a, b) ((a) + (b))
+#define UVOL_FSUB(a, b) ((a) - (b))
+#define UVOL_FDIV(a, b) ((a) / (b))
+#define UVOL_FSQRT(a) sqrtf((a))
+#define UVOL_FABS(a) fabsf((a))
+#endif
+
+UVOL_HD float draco_dequant(int32_t q, float delta, float mn) { return UVOL_FADD(UVOL_FMUL((float)q, delta), mn); }
+UVOL_HD float draco_dequant_delta(float range, int qbits) { return UVOL_FDIV(range, (float)((1u << qbits) - 1u)); }
+UVOL_HD void draco_oct_to_unit(int32_t s, int32_t t, int32_t max_v, float *out) {
+    const float scale = UVOL_FDIV(2.0f, (float)max_v);
+    float y = UVOL_FSUB(UVOL_FMUL((float)s, scale), 1.0f), z = UVOL_FSUB(UVOL_FMUL((float)t, scale), 1.0f);
+    const float x = UVOL_FSUB(UVOL_FSUB(1.0f, UVOL_FABS(y)), UVOL_FABS(z));
+    float xo = -x; xo = xo < 0 ? 0 : xo;
+    y = UVOL_FADD(y, y < 0 ? xo : -xo); z = UVOL_FADD(z, z < 0 ? xo : -xo);
+    const float n2 = UVOL_FADD(UVOL_FADD(UVOL_FMUL(x, x), UVOL_FMUL(y, y)), UVOL_FMUL(z, z));
+    if (n2 < 1e-6f) { out[0] = out[1] = out[2] = 0; return; }
+    const float d = UVOL_FDIV(1.0f, UVOL_FSQRT(n2));
+    out[0] = UVOL_FMUL(x, d); out[1] = UVOL_FMUL(y, d); out[2] = UVOL_FMUL(z, d);
+}
+
+// Per-point expansion of one attribute (GetAttributeDataArrayForAllPoints, DT_FLOAT32).
+UVOL_HD void expand_point(int p, const int *p2c, const int *vert_of_corner, const int *v2d1, const DracoAttr &a, const int32_t *val, float *out) {
+    const int c = p2c[p]; const int e = v2d1[vert_of_corner[c]] - 1; const int nc = a.nc;
+    float *o = out + (size_t)p * nc;
+    if (a.seq == 2) { const float delta = draco_dequant_delta(a.qrange, a.qbits); for (int k = 0; k < nc; k++) o[k] = draco_dequant(val[e * nc + k], delta, a.qmin[k]); }
+    else if (a.seq == 3) draco_oct_to_unit(val[e * 2], val[e * 2 + 1], ((1 << a.qbits) - 1) - 1, o);
+    else {
+        const float tmax = a.dtype == 1 ? 127.f : a.dtype == 2 ? 255.f : a.dtype == 3 ? 32767.f : a.dtype == 4 ? 65535.f : a.dtype == 5 ? 2147483647.f : 4294967295.f;
+        for (int k = 0; k < nc; k++) { float v = (float)val[e * nc + k]; if (a.normalized && a.dtype >= 1 && a.dtype <= 6) v = UVOL_FDIV(v, tmax); o[k] = v; }
+    }
+}

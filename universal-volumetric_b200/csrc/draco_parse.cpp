@@ -1,0 +1,179 @@
+// draco_parse.cpp -- host-side structural parse of a .drc file into a DracoFrame descriptor.
+//
+// Replaces the header walk that draco::Decoder::DecodeArrayToMesh performs before any arithmetic
+// (reference call site src/lib/DRACOLoader.js:478-483).  It touches only section headers, varints
+// and probability tables -- a few hundred bytes per frame; every payload byte (rANS / rABS runs,
+// raw bit fields) is decoded on the GPU.  Bitstream layout: SURVEY.md Appendix A.2.
+#include <string.h>
+#include <vector>
+#include "uvol_internal.h"
+
+namespace {
+struct Rd {
+    const uint8_t *b; size_t n, p; bool err;
+    uint8_t u8() { if (p + 1 > n) { err = true; return 0; } return b[p++]; }
+    uint16_t u16() { uint16_t a = u8(), c = u8(); return (uint16_t)(a | (c << 8)); }
+    uint32_t u32() { if (p + 4 > n) { err = true; p = n; return 0; } uint32_t v; memcpy(&v, b + p, 4); p += 4; return v; }
+    float f32() { uint32_t v = u32(); float f; memcpy(&f, &v, 4); return f; }
+    uint64_t varint() {
+        uint64_t v = 0; int sh = 0;
+        for (;;) { uint8_t c = u8(); if (err) return 0; v |= (uint64_t)(c & 0x7f) << sh; sh += 7; if (!(c & 0x80)) return v; if (sh > 63) { err = true; return 0; } }
+    }
+};
+
+bool read_rabs(Rd &r, RabsStream &s) {
+    s.prob_zero = r.u8(); uint64_t sz = r.varint();
+    if (r.err || sz == 0 || sz > r.n - r.p) return false;
+    s.data_off = (uint32_t)r.p; s.data_len = (uint32_t)sz; s.pad = 0; r.p += sz;
+    return true;
+}
+
+// DecodeSymbols header: scheme, [max_bit_length], probability table, byte run.  Only RAW can be
+// located without decoding it; TAGGED needs the decoded tags to find its end -> unsupported here.
+int read_symbols(Rd &r, RansStream &s, std::vector<uint32_t> &aux) {
+    uint8_t scheme = r.u8();
+    if (r.err) return UVOL_ERR_TRUNCATED;
+    if (scheme != 1) return UVOL_ERR_UNSUPPORTED;
+    uint8_t mbl = r.u8();
+    uint64_t n = r.varint();
+    if (r.err || n == 0 || n > (1u << 20)) return UVOL_ERR_CORRUPT;
+    s.alphabet = (uint32_t)n; s.prob_off = (uint32_t)aux.size();
+    aux.resize(aux.size() + n, 0u);
+    uint32_t *prob = aux.data() + s.prob_off;
+    for (uint32_t i = 0; i < n;) {
+        uint8_t d = r.u8(); unsigned tok = d & 3;
+        if (r.err) return UVOL_ERR_TRUNCATED;
+        if (tok == 3) { uint32_t run = (d >> 2) + 1; if (i + run > n) return UVOL_ERR_CORRUPT; i += run; }
+        else { uint32_t pr = d >> 2; for (unsigned k = 0; k < tok; k++) pr |= (uint32_t)r.u8() << (8 * (k + 1) - 2); prob[i++] = pr; }
+    }
+    int pb = (3 * mbl) / 2; if (pb < 12) pb = 12; if (pb > 20) pb = 20;
+    s.pb = (uint32_t)pb;
+    uint64_t nb = r.varint();
+    if (r.err || nb > r.n - r.p) return UVOL_ERR_TRUNCATED;
+    s.data_off = (uint32_t)r.p; s.data_len = (uint32_t)nb; r.p += nb;
+    return UVOL_OK;
+}
+}  // namespace
+
+// Parses `data` into `f` (file_off/file_len are set by the caller).  Probability tables and
+// topology-split events are appended to `aux`.  Returns UVOL_OK or a negative status.
+int uvol_draco_parse(const uint8_t *data, size_t len, DracoFrame &f, std::vector<uint32_t> &aux) {
+    Rd r{data, len, 0, false};
+    if (len < 11 || memcmp(data, "DRACO", 5)) return UVOL_ERR_CORRUPT;
+    r.p = 5;
+    int maj = r.u8(), mino = r.u8(), etype = r.u8(), meth = r.u8(); int flags = r.u16();
+    if (maj != 2 || mino != 2 || etype != 1 || meth != 1 || (flags & 0x8000)) return UVOL_ERR_UNSUPPORTED;
+    f.trav = r.u8(); f.nv_enc = (uint32_t)r.varint(); f.nf = (uint32_t)r.varint(); f.nad = r.u8();
+    f.nsym = (uint32_t)r.varint(); f.nsplit = (uint32_t)r.varint();
+    if (r.err) return UVOL_ERR_TRUNCATED;
+    if (f.trav != 0 && f.trav != 2) return UVOL_ERR_UNSUPPORTED;
+    if (f.nad > UVOL_MAX_ATTR_DATA) return UVOL_ERR_UNSUPPORTED;
+    if (f.nf == 0 || f.nf > (1u << 26) || f.nsym > f.nf || f.nv_enc > 3 * f.nf + 3 || f.nsplit > f.nf) return UVOL_ERR_CORRUPT;
+    f.nts = (uint32_t)r.varint();
+    if (r.err || f.nts > f.nf) return UVOL_ERR_CORRUPT;
+    f.ts_off = (uint32_t)aux.size();
+    aux.resize(aux.size() + 3 * (size_t)f.nts);
+    uint32_t last = 0;
+    for (uint32_t i = 0; i < f.nts; i++) {
+        uint32_t d = (uint32_t)r.varint(); uint32_t src = last + d; uint32_t d2 = (uint32_t)r.varint();
+        aux[f.ts_off + 3 * i] = src; aux[f.ts_off + 3 * i + 1] = src - d2; last = src;
+    }
+    if (f.nts) {
+        size_t nb = ((size_t)f.nts + 7) / 8;
+        if (r.p + nb > r.n) return UVOL_ERR_TRUNCATED;
+        for (uint32_t i = 0; i < f.nts; i++) aux[f.ts_off + 3 * i + 2] = (data[r.p + (i >> 3)] >> (i & 7)) & 1;
+        r.p += nb;
+    }
+    f.stdsym_off = f.stdsym_len = 0;
+    if (f.trav == 0) {
+        uint64_t sz = r.varint();
+        if (r.err || sz > r.n - r.p) return UVOL_ERR_TRUNCATED;
+        f.stdsym_off = (uint32_t)r.p; f.stdsym_len = (uint32_t)sz; r.p += sz;
+    }
+    if (!read_rabs(r, f.start_faces)) return UVOL_ERR_TRUNCATED;
+    for (uint32_t i = 0; i < f.nad; i++) if (!read_rabs(r, f.seams[i])) return UVOL_ERR_TRUNCATED;
+    for (int i = 0; i < 6; i++) memset(&f.ctx[i], 0, sizeof(RansStream));
+    if (f.trav == 2) {
+        uint64_t total = 0;
+        for (int i = 0; i < 6; i++) {
+            uint64_t n = r.varint();
+            if (r.err || n > f.nsym) return UVOL_ERR_CORRUPT;
+            if (n) { int rc = read_symbols(r, f.ctx[i], aux); if (rc) return rc; }
+            f.ctx[i].count = (uint32_t)n; total += n;
+        }
+        if (f.nsym && total != (uint64_t)f.nsym - 1) return UVOL_ERR_CORRUPT;
+    }
+    // ---- attribute decoders
+    int ndec = r.u8();
+    if (r.err || ndec < 1 || ndec > 8) return UVOL_ERR_CORRUPT;
+    struct Dec { int att_data_id, dec_type, trav, natt, first; } dec[8];
+    for (int i = 0; i < ndec; i++) { dec[i].att_data_id = (int8_t)r.u8(); dec[i].dec_type = r.u8(); dec[i].trav = r.u8(); }
+    f.nattr = 0; f.pos_attr = -1;
+    for (int i = 0; i < ndec; i++) {
+        Dec &d = dec[i];
+        if (d.att_data_id >= (int)f.nad || d.trav != 0 || d.dec_type > 1) return UVOL_ERR_UNSUPPORTED;
+        if (d.dec_type == 1 && d.att_data_id < 0) return UVOL_ERR_CORRUPT;
+        d.natt = (int)r.varint(); d.first = f.nattr;
+        if (r.err || d.natt < 1 || f.nattr + d.natt > UVOL_MAX_ATTRS) return UVOL_ERR_UNSUPPORTED;
+        for (int j = 0; j < d.natt; j++) {
+            DracoAttr &a = f.attr[f.nattr + j]; memset(&a, 0, sizeof a);
+            a.type = (int8_t)r.u8(); a.dtype = (int8_t)r.u8(); a.nc = (int8_t)r.u8(); a.normalized = (int8_t)r.u8(); (void)r.varint();
+            if (a.nc < 1 || a.nc > 4) return UVOL_ERR_UNSUPPORTED;
+            a.table = (int8_t)(d.dec_type == 1 ? d.att_data_id : -1);
+            a.out_slot = -1;
+        }
+        for (int j = 0; j < d.natt; j++) f.attr[f.nattr + j].seq = (int8_t)r.u8();
+        f.nattr += d.natt;
+    }
+    if (r.err) return UVOL_ERR_TRUNCATED;
+    bool sem_done[4] = {false, false, false, false};
+    for (int i = 0; i < ndec; i++) {
+        Dec &d = dec[i];
+        for (int j = 0; j < d.natt; j++) {
+            DracoAttr &a = f.attr[d.first + j];
+            if (a.seq < 1 || a.seq > 3) return UVOL_ERR_UNSUPPORTED;
+            a.vnc = a.seq == 3 ? 2 : a.nc;
+            a.pred = (int8_t)r.u8(); a.xform = -1;
+            if (a.pred != -2) a.xform = (int8_t)r.u8();
+            int compressed = r.u8();
+            if (r.err) return UVOL_ERR_TRUNCATED;
+            if (!compressed) return UVOL_ERR_UNSUPPORTED;     // raw ints need the entry count to be skipped
+            int rc = read_symbols(r, a.sym, aux); if (rc) return rc;
+            a.sym.count = 0xFFFFFFFFu;
+            if (a.pred == -2) { /* no prediction data */ }
+            else if (a.pred == 0 || a.pred == 1) {
+                if (a.xform != 1) return UVOL_ERR_UNSUPPORTED;
+                a.wmin = (int32_t)r.u32(); a.wmax = (int32_t)r.u32();
+                if (a.wmax < a.wmin) return UVOL_ERR_CORRUPT;
+            } else if (a.pred == 5) {
+                if (a.xform != 1 || a.nc != 2 || f.pos_attr < 0) return UVOL_ERR_UNSUPPORTED;
+                a.num_orient = (int32_t)r.u32();
+                if (r.err || a.num_orient < 0) return UVOL_ERR_CORRUPT;
+                if (!read_rabs(r, a.aux_bits)) return UVOL_ERR_TRUNCATED;
+                a.wmin = (int32_t)r.u32(); a.wmax = (int32_t)r.u32();
+                if (a.wmax < a.wmin) return UVOL_ERR_CORRUPT;
+            } else if (a.pred == 6) {
+                if (a.xform != 3 || a.seq != 3 || f.pos_attr < 0) return UVOL_ERR_UNSUPPORTED;
+                a.wmin = (int32_t)r.u32(); a.wmax = (int32_t)r.u32();     // max_quantized_value, center_value
+                if (!read_rabs(r, a.aux_bits)) return UVOL_ERR_TRUNCATED;
+                if (a.wmin < 3 || (a.wmin & (a.wmin + 1)) != 0) return UVOL_ERR_CORRUPT;
+            } else return UVOL_ERR_UNSUPPORTED;
+            if (r.err) return UVOL_ERR_TRUNCATED;
+            if (a.type == 0 && f.pos_attr < 0 && a.nc == 3 && a.table < 0) f.pos_attr = d.first + j;
+            // DRACOLoader exports POSITION/NORMAL/COLOR/TEX_COORD by semantic, first match wins
+            // (src/lib/DRACOLoader.js:505-531); GENERIC is decoded past but not exported.
+            if (a.type >= 0 && a.type <= 3 && !sem_done[a.type]) {
+                sem_done[a.type] = true;
+                a.out_slot = a.type == 0 ? 0 : a.type == 1 ? 1 : a.type == 3 ? 2 : 3;
+            }
+        }
+        for (int j = 0; j < d.natt; j++) {
+            DracoAttr &a = f.attr[d.first + j];
+            if (a.seq == 2) { for (int k = 0; k < a.nc; k++) a.qmin[k] = r.f32(); a.qrange = r.f32(); a.qbits = r.u8(); if (a.qbits < 1 || a.qbits > 30) return UVOL_ERR_CORRUPT; }
+            else if (a.seq == 3) { a.qbits = r.u8(); if (a.qbits < 2 || a.qbits > 30) return UVOL_ERR_CORRUPT; }
+        }
+        if (r.err) return UVOL_ERR_TRUNCATED;
+    }
+    if (f.pos_attr < 0) return UVOL_ERR_UNSUPPORTED;
+    return UVOL_OK;
+}

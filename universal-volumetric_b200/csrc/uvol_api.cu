@@ -1,0 +1,49 @@
+// uvol_api.cu -- context management and the small C-ABI utilities of libuvol_b200.so.
+#include <string.h>
+#include "uvol_ctx.h"
+
+extern "C" const char *uvol_geo_stage_name(int i);
+extern "C" const char *uvol_tex_stage_name(int i);
+extern "C" const char *uvol_corto_stage_name(int i);
+
+extern "C" int uvol_create(int device, uvol_ctx **out) {
+    if (!out) return UVOL_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return UVOL_ERR_CUDA;   // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return UVOL_ERR_CUDA;
+    uvol_ctx *c = new uvol_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->s0, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->s1, cudaStreamNonBlocking) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    *out = c;
+    return UVOL_OK;
+}
+
+extern "C" void uvol_destroy(uvol_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf *db[] = {&c->d_blob, &c->d_desc, &c->d_aux, &c->d_counts, &c->d_scratch, &c->d_zscratch, &c->d_scratch2, &c->d_zscratch2, &c->d_jobs, &c->d_out_geo,
+                    &c->d_tblob, &c->d_tdesc, &c->d_tslices, &c->d_tscratch, &c->d_out_tex,
+                    &c->d_cblob, &c->d_cdesc, &c->d_cscratch, &c->d_czscratch, &c->d_out_corto, &c->d_ccounts, &c->d_caux};
+    for (auto *b : db) b->release();
+    PinBuf *pb[] = {&c->h_blob, &c->h_desc, &c->h_aux, &c->h_counts, &c->h_out, &c->h_tblob, &c->h_tdesc, &c->h_tout, &c->h_cblob, &c->h_cdesc, &c->h_cout, &c->h_ccounts};
+    for (auto *b : pb) b->release();
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->s0) cudaStreamDestroy(c->s0);
+    if (c->s1) cudaStreamDestroy(c->s1);
+    delete c;
+}
+
+extern "C" const char *uvol_last_error(const uvol_ctx *c) { return c ? c->err.c_str() : "null ctx"; }
+extern "C" int uvol_get_stats(const uvol_ctx *c, uvol_stats *out) { if (!c || !out) return UVOL_ERR_ARG; *out = c->stats; return UVOL_OK; }
+extern "C" int uvol_set_profiling(uvol_ctx *c, int enable) { if (!c) return UVOL_ERR_ARG; c->profile = enable != 0; return UVOL_OK; }
+extern "C" const char *uvol_stage_name(int kind, int stage) {
+    if (kind == 0) return uvol_geo_stage_name(stage);
+    if (kind == 1) return uvol_tex_stage_name(stage);
+    if (kind == 2) return uvol_corto_stage_name(stage);
+    return "";
+}

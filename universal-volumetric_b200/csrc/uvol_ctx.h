@@ -1,0 +1,68 @@
+// uvol_ctx.h -- per-GPU context: streams, grow-only device / pinned-host arenas, error text.
+// One ctx per GPU; calls on a ctx are stream-ordered (mirrors "one decoder instance per worker",
+// src/lib/DRACOLoader.js:439).  No torch types, no CPU decode path: every entry point fails with
+// UVOL_ERR_CUDA when the device is unusable.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "uvol_internal.h"
+#include "../../include/uvol_b200.h"
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + (1 << 20);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + (1 << 20);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct StageTimes { float ms[16]; };
+
+struct uvol_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t ev[20] = {};
+    std::string err;
+    // geometry path
+    PinBuf h_blob, h_desc, h_aux, h_counts, h_out;
+    DevBuf d_blob, d_desc, d_aux, d_counts, d_scratch, d_zscratch, d_scratch2, d_zscratch2, d_jobs;
+    DevBuf d_out_geo;             // library-owned geometry outputs (valid until the next geometry batch)
+    // texture path
+    PinBuf h_tblob, h_tdesc, h_tout;
+    DevBuf d_tblob, d_tdesc, d_tslices, d_tscratch, d_out_tex;
+    // V1 path
+    PinBuf h_cblob, h_cdesc, h_cout, h_ccounts;
+    DevBuf d_cblob, d_cdesc, d_cscratch, d_czscratch, d_out_corto, d_ccounts, d_caux;
+    // stats of the last batch
+    uvol_stats stats = {};
+    bool profile = false;
+};
+
+#define UVOL_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    char b_[256]; snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); (ctx)->err = b_; return UVOL_ERR_CUDA; } } while (0)
+
+static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+int uvol_draco_parse(const uint8_t *data, size_t len, DracoFrame &f, std::vector<uint32_t> &aux);

@@ -1,0 +1,101 @@
+// uvol_internal.h -- descriptors shared by the host parsers and the sm_100a kernels.
+//
+// Layout rules (DESIGN.md "Data layout in HBM"):
+//   * one batch = one contiguous byte blob of all input files (pinned host -> device, one copy),
+//     one descriptor per frame / KTX2 file, one scratch arena addressed by 64-bit byte offsets;
+//   * every per-frame array is 128-byte aligned so warps issue whole-line accesses;
+//   * serial stages (entropy streams, connectivity walk, traversal, prediction chains) run one
+//     warp per unit with the batch supplying the parallelism; everything else is element-parallel.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#define UVOL_MAX_ATTR_DATA 4      // non-position attribute connectivities per mesh
+#define UVOL_MAX_ATTRS 6          // attributes per mesh (all decoders flattened)
+
+enum { UVOL_OK = 0, UVOL_ERR_TRUNCATED = -1, UVOL_ERR_CORRUPT = -2, UVOL_ERR_UNSUPPORTED = -3, UVOL_ERR_CUDA = -4,
+       UVOL_ERR_ARG = -5, UVOL_ERR_IO = -6 };
+
+// ---- Draco ---------------------------------------------------------------------------------
+struct RansStream {          // one RAW rANS symbol run (SURVEY A.2 DecodeSymbols)
+    uint32_t data_off;       // byte offset inside the frame's file
+    uint32_t data_len;
+    uint32_t prob_off;       // u32 offset into the batch "aux" table area: alphabet probabilities
+    uint32_t alphabet;
+    uint32_t count;          // symbols to decode; 0xFFFFFFFF = filled on device (entries * comps)
+    uint32_t pb;             // rANS precision bits
+};
+struct RabsStream { uint32_t data_off, data_len, prob_zero, pad; };
+
+struct DracoAttr {
+    int8_t type, dtype, nc, normalized;       // GeometryAttribute type: 0 POSITION 1 NORMAL 2 COLOR 3 TEX_COORD 4 GENERIC
+    int8_t seq;                               // 1 INTEGER 2 QUANTIZATION 3 NORMALS
+    int8_t pred, xform;                       // prediction method / transform ids (A.1)
+    int8_t table;                             // -1: base corner table, else attribute-data id
+    int32_t vnc;                              // portable components (2 for NORMALS)
+    RansStream sym;
+    int32_t wmin, wmax;                       // WRAP bounds, or (max_q, center) for octahedron
+    RabsStream aux_bits;                      // TEX_COORDS orientations / GEOMETRIC_NORMAL flips
+    int32_t num_orient;
+    float qmin[4]; float qrange; int32_t qbits;
+    int32_t out_slot;                         // 0 position 1 normal 2 uv 3 color, -1 not exported
+};
+
+struct DracoFrame {
+    uint64_t file_off; uint32_t file_len; int32_t status;
+    uint32_t trav, nv_enc, nf, nad, nsym, nsplit, nts, ts_off;   // ts_off: aux u32 triples {src, split, edge}
+    uint32_t stdsym_off, stdsym_len;
+    RabsStream start_faces, seams[UVOL_MAX_ATTR_DATA];
+    RansStream ctx[6];
+    int32_t nattr; DracoAttr attr[UVOL_MAX_ATTRS];
+    int32_t pos_attr;                          // index of the POSITION attribute (parent of uv/normal predictors)
+    // ---- scratch arena byte offsets (filled by the host planner)
+    uint64_t o_opp, o_c2v, o_lmc, o_hole, o_val, o_stack, o_ctxsym[6], o_invalid;
+    uint64_t o_seambits[UVOL_MAX_ATTR_DATA], o_eos[UVOL_MAX_ATTR_DATA], o_vos[UVOL_MAX_ATTR_DATA], o_ac2v[UVOL_MAX_ATTR_DATA],
+             o_afirst[UVOL_MAX_ATTR_DATA], o_acnt[UVOL_MAX_ATTR_DATA];
+    uint64_t o_pcnt, o_pfirst, o_p2c;      // per-vertex point counts/offsets, dedup start corner, point -> corner
+    uint64_t o_d2c[UVOL_MAX_ATTR_DATA + 1], o_v2d[UVOL_MAX_ATTR_DATA + 1], o_fvis[UVOL_MAX_ATTR_DATA + 1], o_tstack[UVOL_MAX_ATTR_DATA + 1];
+    uint64_t o_corr[UVOL_MAX_ATTRS], o_val_attr[UVOL_MAX_ATTRS], o_par[UVOL_MAX_ATTRS], o_auxbits[UVOL_MAX_ATTRS];
+    // ---- outputs (device pointers as byte offsets into the output arena; filled after counts are known)
+    uint64_t out_index, out_attr[4];
+};
+
+// per-frame state written by the kernels (counts the host reads back once per batch)
+struct DracoCounts {
+    int32_t status;
+    uint32_t num_vertex_slots;    // V (incl. isolated tail)
+    uint32_t num_points;
+    uint32_t attr_vertices[UVOL_MAX_ATTR_DATA];
+    uint32_t entries[UVOL_MAX_ATTR_DATA + 1];   // per traversal table: [0] base, [1+i] attribute data i
+    uint32_t dbg[4];
+};
+
+// ---- KTX2 / BasisLZ ------------------------------------------------------------------------
+#define UVOL_HUFF_FAST_BITS 10
+struct HuffTable {            // canonical Huffman decode table built on device
+    uint32_t fast[1 << UVOL_HUFF_FAST_BITS];   // (sym << 8) | len ; len==0 -> slow path
+    uint32_t first_code[17], first_idx[17], count[17];
+    uint32_t total, used, maxl;
+    uint32_t sorted_off;      // u16 offset into the per-file sorted-symbol pool
+};
+
+struct Ktx2File {
+    uint64_t file_off; uint32_t file_len; int32_t status;
+    uint32_t width, height, layers, is_video, has_alpha, is_uastc;
+    uint32_t bx, by;
+    uint32_t endpoint_count, selector_count;
+    uint32_t ep_off, ep_len, sel_off, sel_len, tab_off, tab_len;   // byte offsets inside the file
+    uint32_t level_off;                                            // level-0 payload offset inside the file
+    uint32_t first_slice;                                          // index into the batch slice table
+    uint32_t dfd_transfer, dfd_flags;
+    // scratch / outputs
+    uint64_t o_endpoints, o_selectors, o_huff, o_sorted;           // u8x4[ec], u8x4[sc], HuffTable[4], u16 pool
+    uint64_t o_rgba;                                               // output arena offset, layers * w * h * 4
+    uint32_t hist_size, pad;
+};
+struct Ktx2Slice {
+    uint32_t file; uint32_t layer;
+    uint32_t data_off, data_len;       // inside the file (absolute)
+    uint32_t is_alpha, pad;
+    uint64_t o_pred, o_delta, o_sel, o_ep;   // per-block scratch: u8 pred, u16 delta symbol, u16 selector, u16 endpoint
+};

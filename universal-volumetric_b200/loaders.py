@@ -1,0 +1,135 @@
+"""Host-side mirror of the reference's loader interface for the decode hot path.
+
+The reference host is TypeScript (no node toolchain in this image), so the host side above the
+C ABI is Python here, keeping the reference's names and result shapes:
+
+* ``DRACOLoader.decode_batch`` ~ ``DRACOLoader.decodeGeometry`` / worker ``decodeGeometry``
+  (src/lib/DRACOLoader.js:104-187,470-554): result = ``{"index": u32[F*3], "attributes":
+  {"position": f32[P,3], "normal": f32[P,3], "uv": f32[P,2]}}`` in Draco point order.
+* ``KTX2Loader.transcode_batch`` ~ ``BasisWorker.transcode`` (src/lib/KTX2Loader.js:469-580):
+  result = ``{"width", "height", "layers", "hasAlpha", "format", "dfdTransferFn", "dfdFlags",
+  "data": u8[layers,h,w,4]}`` (all layers concatenated, :565).
+
+Every call goes through libuvol_b200.so; a failed item raises nothing and is reported with
+``status < 0`` / ``None`` arrays, like a frame that is simply missing from ``meshMap``
+(src/V2/player.ts:429-444).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native as N
+
+
+class Context:
+    """One context per GPU (mirrors one decoder instance per worker, DRACOLoader.js:439)."""
+
+    def __init__(self, device=0, profiling=False):
+        L = N.lib()
+        h = ctypes.c_void_p()
+        rc = L.uvol_create(int(device), ctypes.byref(h))
+        if rc != 0 or not h:
+            raise N.UvolError(f"uvol_create(device={device}) failed with status {rc}: a CUDA device is required "
+                              "(there is no CPU fallback)")
+        self._h, self._L = h, L
+        if profiling:
+            L.uvol_set_profiling(h, 1)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.uvol_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_error(self):
+        return self._L.uvol_last_error(self._h).decode()
+
+    def stats(self, kind=0):
+        s = N.Stats()
+        self._L.uvol_get_stats(self._h, ctypes.byref(s))
+        d = {k: getattr(s, k) for k in ("host_parse_ms", "h2d_ms", "device_ms", "d2h_ms", "total_ms", "kernel_launches", "bytes_in",
+                                        "bytes_out", "scratch_bytes")}
+        d["stages"] = {self._L.uvol_stage_name(kind, i).decode(): float(s.stage_ms[i]) for i in range(s.num_stages)}
+        return d
+
+
+def _pack(files):
+    n = len(files)
+    keep = [bytes(f) if not isinstance(f, (bytes, bytearray)) else f for f in files]
+    ptrs = (ctypes.c_void_p * n)()
+    sizes = (ctypes.c_size_t * n)()
+    for i, b in enumerate(keep):
+        ptrs[i] = ctypes.cast(ctypes.c_char_p(bytes(b)) if isinstance(b, bytearray) else ctypes.c_char_p(b), ctypes.c_void_p)
+        sizes[i] = len(b)
+    return keep, ptrs, sizes
+
+
+class DRACOLoader:
+    """Batch replacement of the reference's Draco worker pool (<=4 workers, DRACOLoader.js:24,312-364)."""
+
+    def __init__(self, ctx=None, device=0):
+        self.ctx = ctx or Context(device)
+
+    def decode_batch_raw(self, files, memory=N.MEM_HOST):
+        """Runs uvol_decode_draco_batch; returns the raw result structs (pointers stay valid until
+        the next geometry batch on this context)."""
+        keep, ptrs, sizes = _pack(files)
+        out = (N.Geometry * len(files))()
+        rc = self.ctx._L.uvol_decode_draco_batch(self.ctx._h, ptrs, sizes, len(files), memory, out)
+        if rc != 0:
+            raise N.UvolError(f"uvol_decode_draco_batch failed ({rc}): {self.ctx.last_error()}")
+        self._keep = keep
+        return out
+
+    def decode_batch(self, files):
+        """Decodes .drc byte strings; returns one dict per file (numpy copies of the host buffers)."""
+        raw = self.decode_batch_raw(files, N.MEM_HOST)
+        res = []
+        for g in raw:
+            if g.status != 0:
+                res.append({"status": int(g.status), "index": None, "attributes": {}})
+                continue
+            P, F = g.num_points, g.num_faces
+            attrs = {"position": np.ctypeslib.as_array(g.position, (P, 3)).copy()}
+            if g.normal:
+                attrs["normal"] = np.ctypeslib.as_array(g.normal, (P, 3)).copy()
+            if g.uv:
+                attrs["uv"] = np.ctypeslib.as_array(g.uv, (P, 2)).copy()
+            if g.color:
+                attrs["color"] = np.ctypeslib.as_array(g.color, (P, g.color_components)).copy()
+            res.append({"status": 0, "index": np.ctypeslib.as_array(g.index, (F * 3,)).copy(), "attributes": attrs,
+                        "num_points": int(P), "num_faces": int(F)})
+        return res
+
+
+class KTX2Loader:
+    """Batch replacement of the reference's Basis worker pool (<=4 workers FIFO, WorkerPool.js:5-102)."""
+
+    def __init__(self, ctx=None, device=0):
+        self.ctx = ctx or Context(device)
+
+    def transcode_batch_raw(self, files, memory=N.MEM_HOST, target=N.TEX_RGBA32):
+        keep, ptrs, sizes = _pack(files)
+        out = (N.Texture * len(files))()
+        rc = self.ctx._L.uvol_transcode_ktx2_batch(self.ctx._h, ptrs, sizes, len(files), target, memory, out)
+        if rc != 0:
+            raise N.UvolError(f"uvol_transcode_ktx2_batch failed ({rc}): {self.ctx.last_error()}")
+        self._keep = keep
+        return out
+
+    def transcode_batch(self, files):
+        raw = self.transcode_batch_raw(files, N.MEM_HOST)
+        res = []
+        for t in raw:
+            if t.status != 0:
+                res.append({"status": int(t.status), "data": None})
+                continue
+            data = np.ctypeslib.as_array(t.data, (t.layers, t.height, t.width, 4)).copy()
+            res.append({"status": 0, "width": int(t.width), "height": int(t.height), "layers": int(t.layers), "hasAlpha": bool(t.has_alpha),
+                        "format": "RGBAFormat", "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data})
+        return res
