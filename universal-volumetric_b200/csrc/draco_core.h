@@ -86,6 +86,9 @@ UVOL_HD int rans_decode_run(const uint8_t *data, uint32_t nbytes, const RansTabl
 struct EbMem {
     int *opp, *c2v, *lmc, *val, *stack, *skey, *sval, *invalid; uint8_t *hole;
     const uint8_t *ctxsym[6];
+    // Generator hook (tools/synth only; both null in the product): take the symbols from
+    // force_syms[] (decode order) instead of the context arrays and log the active context.
+    const uint8_t *force_syms = nullptr; int8_t *ctx_log = nullptr;
 };
 
 UVOL_HD int b_swl(const int *opp, int c) { if (c < 0) return DINV; int o = opp[cnext(c)]; return o < 0 ? DINV : cnext(o); }
@@ -105,7 +108,10 @@ UVOL_HD int eb_decode_frame(const DracoFrame &f, const uint8_t *file, const uint
     for (int sid = 0; sid < nsym; sid++) {
         if (numf >= F) EB_FAIL(UVOL_ERR_CORRUPT);
         const int face = numf++, c0 = 3 * face; int s, chk = 0;
-        if (f.trav == 2) {
+        if (m.force_syms) {
+            s = m.force_syms[sid];
+            if (m.ctx_log) m.ctx_log[sid] = (int8_t)active_ctx;
+        } else if (f.trav == 2) {
             if (active_ctx >= 0) {
                 if (cnt[active_ctx] <= 0) EB_FAIL(UVOL_ERR_CORRUPT);
                 s = m.ctxsym[active_ctx][--cnt[active_ctx]];
@@ -169,7 +175,7 @@ UVOL_HD int eb_decode_frame(const DracoFrame &f, const uint8_t *file, const uint
             lmc[v0] = c0; lmc[v1] = c0 + 1; lmc[v2] = c0 + 2;
             stack[sp++] = c0; chk = 1;
         }
-        if (f.trav == 2) {
+        if (f.trav == 2 || m.ctx_log) {
             const int c = stack[sp - 1], vn_ = c2v[cnext(c)], vp_ = c2v[cprev(c)];
             if (s == 0 || s == 1) { val[vn_] += 1; val[vp_] += 1; }
             else if (s == 3) { val[c2v[c]] += 1; val[vn_] += 1; val[vp_] += 2; }
@@ -476,8 +482,8 @@ UVOL_HD void oct_rotate(int32_t &x, int32_t &y, int k) {
 UVOL_HD int32_t iabs32(int32_t v) { return v < 0 ? -v : v; }
 UVOL_HD long long iabs64(long long v) { return v < 0 ? -v : v; }
 
-UVOL_HD void normal_entry(int p, const TableView &t, const int *d2c, const int *pos_v2d1, const int32_t *pos, const int32_t *corr,
-                          const uint8_t *flips, int32_t max_q, int32_t *val) {
+// Predicted octahedral coordinates (s,t) of entry p from the finished integer positions.
+UVOL_HD void normal_predict_oct(int p, const TableView &t, const int *d2c, const int *pos_v2d1, const int32_t *pos, int flip, int32_t max_q, int32_t *ps, int32_t *pt) {
     const int32_t MAXQ = max_q, MAXV = MAXQ - 1, CEN = MAXV / 2;
     const int c0 = d2c[p];
     const int32_t *C = pos + 3 * (pos_v2d1[t.c2v_base[c0]] - 1);
@@ -505,7 +511,7 @@ UVOL_HD void normal_entry(int p, const TableView &t, const int *d2c, const int *
         v[1] = (int32_t)(((long long)v[1] * CEN) / as2);
         if (v[2] >= 0) v[2] = CEN - iabs32(v[0]) - iabs32(v[1]); else v[2] = -(CEN - iabs32(v[0]) - iabs32(v[1]));
     }
-    if (flips[p]) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }
+    if (flip) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }
     int32_t s, tt;
     if (v[0] >= 0) { s = v[1] + CEN; tt = v[2] + CEN; }
     else { s = v[1] < 0 ? iabs32(v[2]) : MAXV - iabs32(v[2]); tt = v[2] < 0 ? iabs32(v[1]) : MAXV - iabs32(v[1]); }
@@ -514,6 +520,11 @@ UVOL_HD void normal_entry(int p, const TableView &t, const int *d2c, const int *
     else if (s == MAXV && tt < CEN) tt = CEN + (CEN - tt);
     else if (tt == MAXV && s < CEN) s = CEN + (CEN - s);
     else if (tt == 0 && s > CEN) s = CEN - (s - CEN);
+    *ps = s; *pt = tt;
+}
+// Canonicalised-octahedron inverse transform: (predicted s,t) + positive correction -> value.
+UVOL_HD void oct_apply_correction(int32_t s, int32_t tt, int32_t c0, int32_t c1, int32_t max_q, int32_t *o_s, int32_t *o_t) {
+    const int32_t MAXQ = max_q, MAXV = MAXQ - 1, CEN = MAXV / 2;
     int32_t px = s - CEN, py = tt - CEN;
     const int ind = iabs32(px) + iabs32(py) <= CEN;
     if (!ind) oct_invert_diamond(px, py, CEN);
@@ -523,12 +534,18 @@ UVOL_HD void normal_entry(int p, const TableView &t, const int *d2c, const int *
     else if (px > 0) rc = py >= 0 ? 2 : 1;
     else rc = py <= 0 ? 0 : 3;
     if (!bl) oct_rotate(px, py, rc);
-    int32_t o0 = px + corr[p * 2], o1 = py + corr[p * 2 + 1];
+    int32_t o0 = px + c0, o1 = py + c1;
     o0 = o0 > CEN ? o0 - MAXQ : (o0 < -CEN ? o0 + MAXQ : o0);
     o1 = o1 > CEN ? o1 - MAXQ : (o1 < -CEN ? o1 + MAXQ : o1);
     if (!bl) oct_rotate(o0, o1, (4 - rc) % 4);
     if (!ind) oct_invert_diamond(o0, o1, CEN);
-    val[p * 2] = o0 + CEN; val[p * 2 + 1] = o1 + CEN;
+    *o_s = o0 + CEN; *o_t = o1 + CEN;
+}
+UVOL_HD void normal_entry(int p, const TableView &t, const int *d2c, const int *pos_v2d1, const int32_t *pos, const int32_t *corr,
+                          const uint8_t *flips, int32_t max_q, int32_t *val) {
+    int32_t s, tt;
+    normal_predict_oct(p, t, d2c, pos_v2d1, pos, flips[p], max_q, &s, &tt);
+    oct_apply_correction(s, tt, corr[p * 2], corr[p * 2 + 1], max_q, &val[p * 2], &val[p * 2 + 1]);
 }
 
 // ---------------------------------------------------------------------------------------------
