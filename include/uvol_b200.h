@@ -67,7 +67,7 @@ typedef struct uvol_texture {
 /* Timing / traffic of the last batch call on a ctx (CUDA events on the ctx's stream). */
 typedef struct uvol_stats {
     double host_parse_ms, h2d_ms, device_ms, d2h_ms, total_ms;
-    float stage_ms[16];            /* per-kernel-stage device time; names via uvol_stage_name() */
+    float stage_ms[24];            /* per-kernel-stage device time; names via uvol_stage_name() */
     uint32_t num_stages, kernel_launches;
     uint64_t bytes_in, bytes_out;  /* compressed bytes consumed / final output bytes produced */
     uint64_t scratch_bytes;
@@ -87,11 +87,21 @@ int uvol_set_profiling(uvol_ctx *ctx, int enable);   /* per-stage CUDA events on
 int uvol_decode_draco_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n,
                             int memory, uvol_geometry *out);
 
+/* Re-runs the device pipeline on the batch still resident in HBM from the last
+ * uvol_decode_draco_batch call on this ctx (no parse, no input upload); n must match.  Measurement aid:
+ * times the kernels with inputs already in HBM. */
+int uvol_replay_draco_batch(uvol_ctx *ctx, int memory, uvol_geometry *out, int n);
+
 /* ---- V2 texture: replaces KTX2Loader._createTexture -> BasisWorker.transcode
  * (src/lib/KTX2Loader.js:297-337,469-580) for n .ktx2 segments at once; V2Player.decodeKTX2
  * (src/V2/player.ts:359-366) maps segment numbers to files. */
 int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n,
                               int target_format, int memory, uvol_texture *out);
+
+int uvol_replay_ktx2_batch(uvol_ctx *ctx, int memory, uvol_texture *out, int n);
+
+/* Writes a buffer larger than L2 (256 MiB) on the ctx's stream and waits: L2 flush between timed iterations. */
+int uvol_flush_l2(uvol_ctx *ctx);
 
 #ifdef __cplusplus
 }

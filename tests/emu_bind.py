@@ -1,0 +1,35 @@
+"""ctypes binding of the host-emulation harnesses in tests/tools (logic checks without a GPU)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+TOOLS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools")
+
+
+def _load(name):
+    subprocess.run(["make", "-s", "-C", TOOLS], check=True)
+    return ctypes.CDLL(os.path.join(TOOLS, name))
+
+
+def emu_draco(blob):
+    E = _load("libdraco_emu.so")
+    P = ctypes.c_uint32(); F = ctypes.c_uint32()
+    idx = ctypes.POINTER(ctypes.c_uint32)(); pos = ctypes.POINTER(ctypes.c_float)(); nrm = ctypes.POINTER(ctypes.c_float)(); uv = ctypes.POINTER(ctypes.c_float)()
+    rc = E.draco_emu_decode(blob, ctypes.c_size_t(len(blob)), ctypes.byref(P), ctypes.byref(F), ctypes.byref(idx), ctypes.byref(pos), ctypes.byref(nrm), ctypes.byref(uv))
+    if rc:
+        return {"status": rc}
+    p, f = P.value, F.value
+    return {"status": 0, "num_points": p, "num_faces": f, "index": np.ctypeslib.as_array(idx, (3 * f,)).copy(),
+            "position": np.ctypeslib.as_array(pos, (p, 3)).copy(), "normal": np.ctypeslib.as_array(nrm, (p, 3)).copy() if nrm else None,
+            "uv": np.ctypeslib.as_array(uv, (p, 2)).copy() if uv else None}
+
+
+def emu_ktx2(blob):
+    E = _load("libbasis_emu.so")
+    p = ctypes.POINTER(ctypes.c_uint8)(); w = ctypes.c_uint32(); h = ctypes.c_uint32(); l = ctypes.c_uint32()
+    rc = E.basis_emu_decode(blob, ctypes.c_size_t(len(blob)), ctypes.byref(p), ctypes.byref(w), ctypes.byref(h), ctypes.byref(l))
+    if rc:
+        return {"status": rc}
+    return {"status": 0, "rgba": np.ctypeslib.as_array(p, (l.value, h.value, w.value, 4)).copy()}

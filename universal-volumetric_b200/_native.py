@@ -33,7 +33,7 @@ class Texture(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [("host_parse_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("device_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
-                ("total_ms", ctypes.c_double), ("stage_ms", ctypes.c_float * 16), ("num_stages", ctypes.c_uint32),
+                ("total_ms", ctypes.c_double), ("stage_ms", ctypes.c_float * 24), ("num_stages", ctypes.c_uint32),
                 ("kernel_launches", ctypes.c_uint32), ("bytes_in", ctypes.c_uint64), ("bytes_out", ctypes.c_uint64),
                 ("scratch_bytes", ctypes.c_uint64)]
 
@@ -62,9 +62,12 @@ def lib():
     if hasattr(L, "uvol_transcode_ktx2_batch"):
         L.uvol_transcode_ktx2_batch.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz), i, i, i, ctypes.POINTER(Texture)]
         L.uvol_transcode_ktx2_batch.restype = i
+    L.uvol_replay_draco_batch.argtypes = [vp, i, ctypes.POINTER(Geometry), i]; L.uvol_replay_draco_batch.restype = i
+    L.uvol_replay_ktx2_batch.argtypes = [vp, i, ctypes.POINTER(Texture), i]; L.uvol_replay_ktx2_batch.restype = i
+    L.uvol_flush_l2.argtypes = [vp]; L.uvol_flush_l2.restype = i
     _lib = L
     return L
 
 
 EXPORTED_SYMBOLS = ["uvol_create", "uvol_destroy", "uvol_last_error", "uvol_get_stats", "uvol_stage_name", "uvol_set_profiling",
-                    "uvol_decode_draco_batch", "uvol_transcode_ktx2_batch"]
+                    "uvol_decode_draco_batch", "uvol_transcode_ktx2_batch", "uvol_replay_draco_batch", "uvol_replay_ktx2_batch", "uvol_flush_l2"]

@@ -149,30 +149,34 @@ uint64_t take(uint64_t &cur, uint64_t bytes) { uint64_t o = cur; cur = (cur + by
 static const char *kTexStages[] = {"h2d", "globals", "slices", "resolve", "blocks", "d2h"};
 extern "C" const char *uvol_tex_stage_name(int i) { return (i >= 0 && i < 6) ? kTexStages[i] : ""; }
 
-extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target_format, int memory, uvol_texture *out) {
-    if (!ctx || !out || n < 0 || (n > 0 && (!data || !size)) || n >= (1 << 19)) return UVOL_ERR_ARG;
-    if (target_format != UVOL_TEX_RGBA32) { ctx->err = "only UVOL_TEX_RGBA32 is implemented"; return UVOL_ERR_UNSUPPORTED; }
-    UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
-    memset(&ctx->stats, 0, sizeof ctx->stats);
-    for (int i = 0; i < n; i++) memset(&out[i], 0, sizeof out[i]);
-    if (n == 0) return UVOL_OK;
+struct TexBatch {
+    std::vector<Ktx2File> files; std::vector<Ktx2Slice> slices; std::vector<uint32_t> layer_list, uastc_layers;
+    int n = 0; uint64_t blob_bytes = 0, scratch = 0, out = 0, bytes_in = 0; uint32_t max_blocks = 1; bool any_alpha = false;
+    size_t desc_bytes = 0, off_sl = 0, off_ll = 0, off_ul = 0; double parse_ms = 0;
+};
+void uvol_tex_batch_free(TexBatch *b) { delete b; }
+
+static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n) {
     const double t_begin = now_ms();
-    cudaStream_t st = ctx->s0;
-    std::vector<Ktx2File> files((size_t)n); std::vector<Ktx2Slice> slices; std::vector<uint32_t> layer_list, uastc_layers;
-    uint64_t blob_bytes = 0, s = 0, o = 0; uint32_t max_blocks = 1; bool any_alpha = false;
+    if (!ctx->tex) ctx->tex = new TexBatch();
+    TexBatch &B = *ctx->tex;
+    B.n = n; B.files.assign((size_t)n, Ktx2File()); B.slices.clear(); B.layer_list.clear(); B.uastc_layers.clear();
+    B.max_blocks = 1; B.any_alpha = false; B.bytes_in = 0;
+    std::vector<Ktx2File> &files = B.files; std::vector<Ktx2Slice> &slices = B.slices;
+    uint64_t blob_bytes = 0, s = 0, o = 0;
     for (int i = 0; i < n; i++) {
         Ktx2File &f = files[i]; memset(&f, 0, sizeof f);
-        f.file_off = blob_bytes; f.file_len = (uint32_t)size[i];
+        f.file_off = blob_bytes; f.file_len = (uint32_t)size[i]; B.bytes_in += size[i];
         blob_bytes = align_up(blob_bytes + size[i] + 8, 16);
+        const size_t slices_before = slices.size();
         f.status = (data[i] && size[i] < (1ull << 31)) ? uvol_ktx2_parse(data[i], size[i], (uint32_t)i, f, slices) : UVOL_ERR_ARG;
-        if (f.status) { slices.resize(f.first_slice); continue; }
-        if (f.layers > 4095) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(f.first_slice); continue; }
+        if (f.status) { slices.resize(slices_before); continue; }
+        if (f.layers > 4095 || f.bx > 4096) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }
         const uint64_t nblk = (uint64_t)f.bx * f.by;
-        if (nblk > max_blocks) max_blocks = (uint32_t)nblk;
-        if (f.bx > 4096) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(f.first_slice); continue; }
+        if (nblk > B.max_blocks) B.max_blocks = (uint32_t)nblk;
         f.o_rgba = take(o, (uint64_t)f.layers * f.width * f.height * 4);
-        if (f.is_uastc) { f.status = UVOL_ERR_UNSUPPORTED; continue; }
-        any_alpha |= f.has_alpha != 0;
+        if (f.is_uastc) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }   // until uastc_transcode.cu lands
+        B.any_alpha |= f.has_alpha != 0;
         const uint64_t pool = (uint64_t)f.endpoint_count + f.selector_count + 8192 + 1024;
         f.o_endpoints = take(s, (uint64_t)f.endpoint_count * 4); f.o_selectors = take(s, (uint64_t)f.selector_count * 4);
         f.o_huff = take(s, sizeof(HuffTable) * 10); f.o_sorted = take(s, pool * 2 + 32768 + 64);
@@ -180,35 +184,45 @@ extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *da
             Ktx2Slice &sl = slices[k];
             sl.o_pred = take(s, nblk); sl.o_delta = take(s, nblk * 2); sl.o_sel = take(s, nblk * 2); sl.o_ep = take(s, nblk * 2);
         }
-        for (uint32_t L = 0; L < f.layers; L++) layer_list.push_back(((uint32_t)i << 12) | L);
+        for (uint32_t L = 0; L < f.layers; L++) B.layer_list.push_back(((uint32_t)i << 12) | L);
     }
-    const double t_parsed = now_ms();
-    const size_t nsl = slices.size(), nll = layer_list.size(), nul = uastc_layers.size();
+    B.blob_bytes = blob_bytes; B.scratch = s; B.out = o;
+    const size_t nsl = slices.size(), nll = B.layer_list.size(), nul = B.uastc_layers.size();
     UVOL_CUDA(ctx, ctx->h_tblob.reserve(blob_bytes + 64));
-    for (int i = 0; i < n; i++) if (data[i]) memcpy((uint8_t *)ctx->h_tblob.p + files[i].file_off, data[i], size[i]);
-    const size_t desc_bytes = sizeof(Ktx2File) * (size_t)n + sizeof(Ktx2Slice) * (nsl + 1) + 4 * (nll + nul + 2);
-    UVOL_CUDA(ctx, ctx->h_tdesc.reserve(desc_bytes));
-    UVOL_CUDA(ctx, ctx->d_tdesc.reserve(desc_bytes));
+    for (int i = 0; i < n; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_tblob.p + files[i].file_off, data[i], size[i]);
+    B.off_sl = sizeof(Ktx2File) * (size_t)n; B.off_ll = B.off_sl + sizeof(Ktx2Slice) * (nsl + 1); B.off_ul = B.off_ll + 4 * (nll + 1);
+    B.desc_bytes = B.off_ul + 4 * (nul + 1);
+    UVOL_CUDA(ctx, ctx->h_tdesc.reserve(B.desc_bytes));
+    UVOL_CUDA(ctx, ctx->d_tdesc.reserve(B.desc_bytes));
     UVOL_CUDA(ctx, ctx->d_tblob.reserve(blob_bytes + 64));
     UVOL_CUDA(ctx, ctx->d_tslices.reserve(sizeof(TexState) * (size_t)n));
     UVOL_CUDA(ctx, ctx->d_tscratch.reserve(s + 256));
     UVOL_CUDA(ctx, ctx->d_out_tex.reserve(o + 256));
     uint8_t *hd = (uint8_t *)ctx->h_tdesc.p;
     memcpy(hd, files.data(), sizeof(Ktx2File) * (size_t)n);
-    const size_t off_sl = sizeof(Ktx2File) * (size_t)n, off_ll = off_sl + sizeof(Ktx2Slice) * (nsl + 1), off_ul = off_ll + 4 * (nll + 1);
-    if (nsl) memcpy(hd + off_sl, slices.data(), sizeof(Ktx2Slice) * nsl);
-    if (nll) memcpy(hd + off_ll, layer_list.data(), 4 * nll);
-    if (nul) memcpy(hd + off_ul, uastc_layers.data(), 4 * nul);
-    int ev = 0;
-    auto stamp = [&]() { if (ctx->profile && ev < 20) cudaEventRecord(ctx->ev[ev++], st); };
-    stamp();
+    if (nsl) memcpy(hd + B.off_sl, slices.data(), sizeof(Ktx2Slice) * nsl);
+    if (nll) memcpy(hd + B.off_ll, B.layer_list.data(), 4 * nll);
+    if (nul) memcpy(hd + B.off_ul, B.uastc_layers.data(), 4 * nul);
+    B.parse_ms = now_ms() - t_begin;
+    cudaStream_t st = ctx->s0;
+    if (ctx->profile) cudaEventRecord(ctx->ev[0], st);
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_tblob.p, ctx->h_tblob.p, blob_bytes, cudaMemcpyHostToDevice, st));
-    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc.p, hd, desc_bytes, cudaMemcpyHostToDevice, st));
+    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc.p, hd, B.desc_bytes, cudaMemcpyHostToDevice, st));
+    return UVOL_OK;
+}
+
+static int ktx2_run(uvol_ctx *ctx, int memory, uvol_texture *out, bool fresh_upload) {
+    TexBatch &B = *ctx->tex; const int n = B.n;
+    cudaStream_t st = ctx->s0;
+    int ev = 1;
+    auto stamp = [&]() { if (ctx->profile && ev < 32) cudaEventRecord(ctx->ev[ev++], st); };
+    if (!fresh_upload && ctx->profile) cudaEventRecord(ctx->ev[0], st);
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_tslices.p, 0, sizeof(TexState) * (size_t)n, st));
     stamp();
+    const size_t nsl = B.slices.size(), nll = B.layer_list.size(), nul = B.uastc_layers.size();
     const uint8_t *dD = (const uint8_t *)ctx->d_tdesc.p;
-    const Ktx2File *dF = (const Ktx2File *)dD; const Ktx2Slice *dSl = (const Ktx2Slice *)(dD + off_sl);
-    const uint32_t *dLL = (const uint32_t *)(dD + off_ll), *dUL = (const uint32_t *)(dD + off_ul);
+    const Ktx2File *dF = (const Ktx2File *)dD; const Ktx2Slice *dSl = (const Ktx2Slice *)(dD + B.off_sl);
+    const uint32_t *dLL = (const uint32_t *)(dD + B.off_ll), *dUL = (const uint32_t *)(dD + B.off_ul);
     TexState *dSt = (TexState *)ctx->d_tslices.p; const uint8_t *dBlob = (const uint8_t *)ctx->d_tblob.p;
     uint8_t *dS = (uint8_t *)ctx->d_tscratch.p, *dO = (uint8_t *)ctx->d_out_tex.p;
     uint32_t launches = 0;
@@ -216,22 +230,23 @@ extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *da
     stamp();
     if (nsl) { k_etc1s_slices<<<(unsigned)nsl, 32, 0, st>>>(dF, dSt, dSl, dBlob, dS, (int)nsl); launches++; }
     stamp();
-    if (nsl) { k_etc1s_resolve<<<dim3(n, any_alpha ? 2 : 1), 32, 0, st>>>(dF, dSt, dSl, dS, n); launches++; }
+    if (nsl) { k_etc1s_resolve<<<dim3(n, B.any_alpha ? 2 : 1), 32, 0, st>>>(dF, dSt, dSl, dS, n); launches++; }
     stamp();
-    if (nll) { k_etc1s_blocks<<<dim3((max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO); launches++; }
-    if (nul) { uvol_uastc_launch(dF, (const int32_t *)dSt, dBlob, dO, dUL, (int)nul, max_blocks, st); launches++; }
+    if (nll) { k_etc1s_blocks<<<dim3((B.max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO); launches++; }
+    if (nul) { uvol_uastc_launch(dF, (const int32_t *)dSt, dBlob, dO, dUL, (int)nul, B.max_blocks, st); launches++; }
     stamp();
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
-    UVOL_CUDA(ctx, ctx->h_tout.reserve(st_bytes + (memory == UVOL_MEM_HOST ? o + 256 : 0)));
+    UVOL_CUDA(ctx, ctx->h_tout.reserve(st_bytes + (memory == UVOL_MEM_HOST ? B.out + 256 : 0)));
     TexState *hSt = (TexState *)ctx->h_tout.p; uint8_t *hO = (uint8_t *)ctx->h_tout.p + st_bytes;
     UVOL_CUDA(ctx, cudaMemcpyAsync(hSt, dSt, sizeof(TexState) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(hO, dO, o, cudaMemcpyDeviceToHost, st));
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(hO, dO, B.out, cudaMemcpyDeviceToHost, st));
     stamp();
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));
     UVOL_CUDA(ctx, cudaGetLastError());
     uint8_t *base = memory == UVOL_MEM_HOST ? hO : dO; uint64_t bytes_out = 0;
     for (int i = 0; i < n; i++) {
-        const Ktx2File &f = files[i]; uvol_texture &t = out[i];
+        const Ktx2File &f = B.files[i]; uvol_texture &t = out[i];
+        memset(&t, 0, sizeof t);
         t.status = f.status ? f.status : hSt[i].status;
         if (t.status) continue;
         t.width = f.width; t.height = f.height; t.layers = f.layers; t.format = UVOL_TEX_RGBA32; t.has_alpha = f.has_alpha;
@@ -239,13 +254,35 @@ extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *da
         t.bytes = (uint64_t)f.layers * f.width * f.height * 4; t.data = base + f.o_rgba; bytes_out += t.bytes;
     }
     uvol_stats &sx = ctx->stats;
-    sx.host_parse_ms = t_parsed - t_begin; sx.total_ms = now_ms() - t_begin; sx.kernel_launches = launches;
-    for (int i = 0; i < n; i++) sx.bytes_in += size[i];
-    sx.bytes_out = bytes_out; sx.scratch_bytes = s;
+    sx.kernel_launches = launches; sx.bytes_in = B.bytes_in; sx.bytes_out = bytes_out; sx.scratch_bytes = B.scratch;
     if (ctx->profile) {
         sx.num_stages = (uint32_t)(ev - 1);
-        for (int k = 0; k + 1 < ev; k++) cudaEventElapsedTime(&sx.stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);
-        float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[ev - 1]); sx.device_ms = tot;
+        for (int k = 0; k + 1 < ev && k < 24; k++) cudaEventElapsedTime(&sx.stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);
+        float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[1], ctx->ev[ev - 2]); sx.device_ms = tot;
+        sx.h2d_ms = sx.stage_ms[0]; sx.d2h_ms = sx.stage_ms[ev - 2];
     }
+    return UVOL_OK;
+}
+
+extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target_format, int memory, uvol_texture *out) {
+    if (!ctx || !out || n < 0 || (n > 0 && (!data || !size)) || n >= (1 << 19)) return UVOL_ERR_ARG;
+    if (target_format != UVOL_TEX_RGBA32) { ctx->err = "only UVOL_TEX_RGBA32 is implemented"; return UVOL_ERR_UNSUPPORTED; }
+    UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    if (n == 0) { if (ctx->tex) ctx->tex->n = 0; return UVOL_OK; }
+    const double t0 = now_ms();
+    int rc = ktx2_prepare(ctx, data, size, n); if (rc) return rc;
+    rc = ktx2_run(ctx, memory, out, true); if (rc) return rc;
+    ctx->stats.host_parse_ms = ctx->tex->parse_ms; ctx->stats.total_ms = now_ms() - t0;
+    return UVOL_OK;
+}
+
+extern "C" int uvol_replay_ktx2_batch(uvol_ctx *ctx, int memory, uvol_texture *out, int n) {
+    if (!ctx || !out || !ctx->tex || ctx->tex->n != n || n <= 0) return UVOL_ERR_ARG;
+    UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    const double t0 = now_ms();
+    const int rc = ktx2_run(ctx, memory, out, false); if (rc) return rc;
+    ctx->stats.total_ms = now_ms() - t0;
     return UVOL_OK;
 }

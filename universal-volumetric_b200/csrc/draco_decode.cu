@@ -335,88 +335,105 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
 
 }  // namespace
 
-static const char *kGeoStages[] = {"h2d", "rans_ctx+rabs_seams", "edgebreaker", "seams", "attr_tables", "point_count", "counts_readback",
-                                   "point_assign", "traverse", "rans_attr+rabs_aux", "predict_pos", "predict_uv+normals", "expand", "d2h"};
-extern "C" const char *uvol_geo_stage_name(int i) { return (i >= 0 && i < 14) ? kGeoStages[i] : ""; }
+static const char *kGeoStages[] = {"h2d", "rans_ctx", "rabs_seams", "edgebreaker", "seams", "attr_tables", "point_count", "counts_readback",
+                                   "point_assign", "traverse", "rans_attr", "rabs_aux", "parents", "predict_wrap", "uv_prepare", "predict_uv", "normals",
+                                   "expand", "d2h"};
+extern "C" const char *uvol_geo_stage_name(int i) { return (i >= 0 && i < 19) ? kGeoStages[i] : ""; }
 
-extern "C" int uvol_decode_draco_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int memory, uvol_geometry *out) {
-    if (!ctx || !out || n < 0 || (n > 0 && (!data || !size))) return UVOL_ERR_ARG;
-    UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
-    memset(&ctx->stats, 0, sizeof ctx->stats);
-    for (int i = 0; i < n; i++) { memset(&out[i], 0, sizeof out[i]); }
-    if (n == 0) return UVOL_OK;
+// Host-side state of the batch currently resident on the device (kept so that the device pipeline
+// can be re-run on HBM-resident inputs, uvol_replay_draco_batch).
+struct GeoBatch {
+    std::vector<DracoFrame> frames; std::vector<uint32_t> aux; std::vector<Job> jobs;
+    int n = 0, j_ransA = 0, j_rabsA = 0, j_trav = 0, j_ransB = 0, j_rabsB = 0, j_wrap = 0, j_uv = 0, j_end = 0;
+    uint32_t max_alpha_ctx = 1, max_alpha_attr = 1, maxnad = 0, maxV = 0, maxF = 0; int maxattr = 0;
+    uint64_t blob_bytes = 0, bytes_in = 0; DracoPlan pl; double parse_ms = 0;
+};
+void uvol_geo_batch_free(GeoBatch *b) { delete b; }
+
+static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n) {
     const double t_begin = now_ms();
-    cudaStream_t st = ctx->s0;
-    // ---- host: structural parse + pack
-    std::vector<DracoFrame> frames((size_t)n); std::vector<uint32_t> aux; aux.reserve((size_t)n * 2048);
-    uint64_t blob_bytes = 0; uint32_t max_alpha_ctx = 1, max_alpha_attr = 1;
+    if (!ctx->geo) ctx->geo = new GeoBatch();
+    GeoBatch &B = *ctx->geo;
+    B.n = n; B.frames.assign((size_t)n, DracoFrame()); B.aux.clear(); B.aux.reserve((size_t)n * 2048); B.jobs.clear();
+    B.max_alpha_ctx = B.max_alpha_attr = 1; B.maxnad = B.maxV = B.maxF = 0; B.maxattr = 0; B.bytes_in = 0;
+    std::vector<DracoFrame> &frames = B.frames; std::vector<uint32_t> &aux = B.aux;
+    uint64_t blob_bytes = 0;
     for (int i = 0; i < n; i++) {
         DracoFrame &f = frames[i]; memset(&f, 0, sizeof f);
-        f.file_off = blob_bytes; f.file_len = (uint32_t)size[i];
+        f.file_off = blob_bytes; f.file_len = (uint32_t)size[i]; B.bytes_in += size[i];
         blob_bytes = align_up(blob_bytes + size[i] + 8, 16);
         f.status = (data[i] && size[i] < (1ull << 31)) ? uvol_draco_parse(data[i], size[i], f, aux) : UVOL_ERR_ARG;
         if (f.status) continue;
-        for (int k = 0; k < 6; k++) if (f.ctx[k].count && f.ctx[k].alphabet > max_alpha_ctx) max_alpha_ctx = f.ctx[k].alphabet;
+        for (int k = 0; k < 6; k++) if (f.ctx[k].count && f.ctx[k].alphabet > B.max_alpha_ctx) B.max_alpha_ctx = f.ctx[k].alphabet;
         for (int j = 0; j < f.nattr; j++) {
             if (f.attr[j].sym.alphabet > 49000) { f.status = UVOL_ERR_UNSUPPORTED; break; }
-            if ((f.attr[j].out_slot >= 0 || j == f.pos_attr) && f.attr[j].sym.alphabet > max_alpha_attr) max_alpha_attr = f.attr[j].sym.alphabet;
+            if ((f.attr[j].out_slot >= 0 || j == f.pos_attr) && f.attr[j].sym.alphabet > B.max_alpha_attr) B.max_alpha_attr = f.attr[j].sym.alphabet;
         }
     }
     aux.push_back(0);
+    B.blob_bytes = blob_bytes;
     UVOL_CUDA(ctx, ctx->h_blob.reserve(blob_bytes + 64));
-    for (int i = 0; i < n; i++) if (data[i]) memcpy((uint8_t *)ctx->h_blob.p + frames[i].file_off, data[i], size[i]);
-    DracoPlan pl; draco_plan_phase1(frames, pl);
-    // job lists
-    std::vector<Job> jobs; jobs.reserve((size_t)n * 24);
+    for (int i = 0; i < n; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_blob.p + frames[i].file_off, data[i], size[i]);
+    draco_plan_phase1(frames, B.pl);
+    std::vector<Job> &jobs = B.jobs; jobs.reserve((size_t)n * 24);
     auto mark = [&]() { return (int)jobs.size(); };
-    const int j_ransA = mark();
+    B.j_ransA = mark();
     for (int i = 0; i < n; i++) if (!frames[i].status) for (int k = 0; k < 6; k++) if (frames[i].ctx[k].count) jobs.push_back({(uint32_t)i, k});
-    const int j_rabsA = mark();
+    B.j_rabsA = mark();
     for (int i = 0; i < n; i++) if (!frames[i].status) for (uint32_t k = 0; k < frames[i].nad; k++) jobs.push_back({(uint32_t)i, (int)k});
-    const int j_trav = mark();
-    uint32_t maxnad = 0, maxV = 0, maxF = 0; int maxattr = 0;
+    B.j_trav = mark();
     for (int i = 0; i < n; i++) {
         const DracoFrame &f = frames[i]; if (f.status) continue;
         bool need[UVOL_MAX_ATTR_DATA + 1] = {true, false, false, false, false};
         for (int j = 0; j < f.nattr; j++) if (f.attr[j].out_slot >= 0 || j == f.pos_attr) need[f.attr[j].table + 1] = true;
         for (uint32_t t = 0; t <= f.nad; t++) if (need[t]) jobs.push_back({(uint32_t)i, (int)t});
-        if (f.nad > maxnad) maxnad = f.nad;
-        if (f.nv_enc + f.nsplit > maxV) maxV = f.nv_enc + f.nsplit;
-        if (f.nf > maxF) maxF = f.nf;
-        if (f.nattr > maxattr) maxattr = f.nattr;
+        if (f.nad > B.maxnad) B.maxnad = f.nad;
+        if (f.nv_enc + f.nsplit > B.maxV) B.maxV = f.nv_enc + f.nsplit;
+        if (f.nf > B.maxF) B.maxF = f.nf;
+        if (f.nattr > B.maxattr) B.maxattr = f.nattr;
     }
-    const int j_ransB = mark();
+    B.j_ransB = mark();
     for (int i = 0; i < n; i++) if (!frames[i].status) for (int j = 0; j < frames[i].nattr; j++) if (frames[i].attr[j].out_slot >= 0 || j == frames[i].pos_attr) jobs.push_back({(uint32_t)i, 16 + j});
-    const int j_rabsB = mark();
+    B.j_rabsB = mark();
     for (int i = 0; i < n; i++) if (!frames[i].status) for (int j = 0; j < frames[i].nattr; j++) if ((frames[i].attr[j].out_slot >= 0) && (frames[i].attr[j].pred == 5 || frames[i].attr[j].pred == 6)) jobs.push_back({(uint32_t)i, 16 + j});
-    const int j_wrap = mark();
+    B.j_wrap = mark();
     for (int i = 0; i < n; i++) if (!frames[i].status) for (int j = 0; j < frames[i].nattr; j++) { const DracoAttr &a = frames[i].attr[j]; if ((a.out_slot >= 0 || j == frames[i].pos_attr) && (a.pred == -2 || a.pred == 0 || a.pred == 1)) jobs.push_back({(uint32_t)i, j}); }
-    const int j_uv = mark();
+    B.j_uv = mark();
     for (int i = 0; i < n; i++) if (!frames[i].status) for (int j = 0; j < frames[i].nattr; j++) if (frames[i].attr[j].out_slot >= 0 && frames[i].attr[j].pred == 5) jobs.push_back({(uint32_t)i, j});
-    const int j_end = mark();
-    const double t_parsed = now_ms();
-
-    // ---- device buffers + uploads
+    B.j_end = mark();
+    // device buffers + uploads
+    cudaStream_t st = ctx->s0;
     UVOL_CUDA(ctx, ctx->d_blob.reserve(blob_bytes + 64));
     UVOL_CUDA(ctx, ctx->d_desc.reserve(sizeof(DracoFrame) * (size_t)n));
     UVOL_CUDA(ctx, ctx->d_aux.reserve(aux.size() * 4));
     UVOL_CUDA(ctx, ctx->d_counts.reserve(sizeof(DracoCounts) * (size_t)n));
     UVOL_CUDA(ctx, ctx->h_counts.reserve(sizeof(DracoCounts) * (size_t)n));
     UVOL_CUDA(ctx, ctx->d_jobs.reserve(sizeof(Job) * (jobs.size() + 1)));
-    UVOL_CUDA(ctx, ctx->d_scratch.reserve(pl.scratch + 256));
-    UVOL_CUDA(ctx, ctx->d_zscratch.reserve(pl.zscratch + 256));
+    UVOL_CUDA(ctx, ctx->d_scratch.reserve(B.pl.scratch + 256));
+    UVOL_CUDA(ctx, ctx->d_zscratch.reserve(B.pl.zscratch + 256));
     UVOL_CUDA(ctx, ctx->h_desc.reserve(sizeof(DracoFrame) * (size_t)n + aux.size() * 4 + sizeof(Job) * (jobs.size() + 1)));
-    int ev = 0;
-    auto stamp = [&]() { if (ctx->profile && ev < 20) cudaEventRecord(ctx->ev[ev++], st); };
-    stamp();
+    B.parse_ms = now_ms() - t_begin;
+    if (ctx->profile) cudaEventRecord(ctx->ev[0], st);
     uint8_t *hd = (uint8_t *)ctx->h_desc.p;
-    memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
     uint8_t *h_aux = hd + sizeof(DracoFrame) * (size_t)n; memcpy(h_aux, aux.data(), aux.size() * 4);
     uint8_t *h_jobs = h_aux + aux.size() * 4; memcpy(h_jobs, jobs.data(), sizeof(Job) * jobs.size());
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_blob.p, ctx->h_blob.p, blob_bytes, cudaMemcpyHostToDevice, st));
-    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_aux.p, h_aux, aux.size() * 4, cudaMemcpyHostToDevice, st));
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs.p, h_jobs, sizeof(Job) * jobs.size(), cudaMemcpyHostToDevice, st));
+    return UVOL_OK;
+}
+
+static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_upload) {
+    GeoBatch &B = *ctx->geo; const int n = B.n;
+    std::vector<DracoFrame> &frames = B.frames; DracoPlan &pl = B.pl;
+    cudaStream_t st = ctx->s0;
+    int ev = 1;
+    auto stamp = [&]() { if (ctx->profile && ev < 32) cudaEventRecord(ctx->ev[ev++], st); };
+    if (!fresh_upload && ctx->profile) cudaEventRecord(ctx->ev[0], st);
+    uint8_t *hd = (uint8_t *)ctx->h_desc.p;
+    draco_plan_phase1(frames, pl);      // restores the phase-1 view of the descriptors (idempotent)
+    memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
+    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(DracoCounts) * (size_t)n, st));
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_zscratch.p, 0, pl.zscratch + 256, st));
     stamp();
@@ -426,23 +443,24 @@ extern "C" int uvol_decode_draco_batch(uvol_ctx *ctx, const uint8_t *const *data
     uint32_t launches = 0;
     auto rans_smem = [](uint32_t alphabet) { return (size_t)(alphabet + 1) * 4 + 257 * 2 + 16; };
     {
-        const size_t smA = rans_smem(max_alpha_ctx), smB = rans_smem(max_alpha_attr);
+        const size_t smA = rans_smem(B.max_alpha_ctx), smB = rans_smem(B.max_alpha_attr);
         const size_t smMax = smA > smB ? smA : smB;
         if (smMax > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_rans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smMax));
     }
     // ---- phase 1
-    if (j_rabsA - j_ransA > 0) { k_rans<<<j_rabsA - j_ransA, 32, rans_smem(max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + j_ransA, j_rabsA - j_ransA); launches++; }
-    if (j_trav - j_rabsA > 0) { k_rabs<<<j_trav - j_rabsA, 32, 0, st>>>(dF, dC, dBlob, dS, nullptr, dJ + j_rabsA, j_trav - j_rabsA); launches++; }
+    if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<B.j_rabsA - B.j_ransA, 32, rans_smem(B.max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + B.j_ransA, B.j_rabsA - B.j_ransA); launches++; }
+    stamp();
+    if (B.j_trav - B.j_rabsA > 0) { k_rabs<<<B.j_trav - B.j_rabsA, 32, 0, st>>>(dF, dC, dBlob, dS, nullptr, dJ + B.j_rabsA, B.j_trav - B.j_rabsA); launches++; }
     stamp();
     k_edgebreaker<<<n, 32, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++;
     stamp();
     k_seams<<<n, 256, 0, st>>>(dF, dC, dS, dZ, n); launches++;
     stamp();
-    const unsigned gv = (maxV + 127) / 128 > 0 ? (maxV + 127) / 128 : 1;
-    if (maxnad) {
-        k_attr_fan<0><<<dim3(gv, n, maxnad), 128, 0, st>>>(dF, dC, dS, dZ); launches++;
-        k_scan<<<dim3(n, maxnad), 1024, 0, st>>>(dF, dC, dS, 0); launches++;
-        k_attr_fan<1><<<dim3(gv, n, maxnad), 128, 0, st>>>(dF, dC, dS, dZ); launches++;
+    const unsigned gv = (B.maxV + 127) / 128 > 0 ? (B.maxV + 127) / 128 : 1;
+    if (B.maxnad) {
+        k_attr_fan<0><<<dim3(gv, n, B.maxnad), 128, 0, st>>>(dF, dC, dS, dZ); launches++;
+        k_scan<<<dim3(n, B.maxnad), 1024, 0, st>>>(dF, dC, dS, 0); launches++;
+        k_attr_fan<1><<<dim3(gv, n, B.maxnad), 128, 0, st>>>(dF, dC, dS, dZ); launches++;
     }
     stamp();
     k_point_fan<0><<<dim3(gv, n), 128, 0, st>>>(dF, dC, dS, dZ, nullptr, nullptr); launches++;
@@ -469,22 +487,24 @@ extern "C" int uvol_decode_draco_batch(uvol_ctx *ctx, const uint8_t *const *data
     // ---- phase 2
     k_point_fan<1><<<dim3(gv, n), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dO); launches++;
     stamp();
-    if (j_ransB - j_trav > 0) { k_traverse<<<j_ransB - j_trav, 32, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2, dJ + j_trav, j_ransB - j_trav); launches++; }
+    if (B.j_ransB - B.j_trav > 0) { k_traverse<<<B.j_ransB - B.j_trav, 32, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2, dJ + B.j_trav, B.j_ransB - B.j_trav); launches++; }
     stamp();
-    if (j_rabsB - j_ransB > 0) { k_rans<<<j_rabsB - j_ransB, 32, rans_smem(max_alpha_attr), st>>>(dF, dC, dBlob, dAux, dS, dS2, dJ + j_ransB, j_rabsB - j_ransB); launches++; }
-    if (j_wrap - j_rabsB > 0) { k_rabs<<<j_wrap - j_rabsB, 32, 0, st>>>(dF, dC, dBlob, dS, dS2, dJ + j_rabsB, j_wrap - j_rabsB); launches++; }
+    if (B.j_rabsB - B.j_ransB > 0) { k_rans<<<B.j_rabsB - B.j_ransB, 32, rans_smem(B.max_alpha_attr), st>>>(dF, dC, dBlob, dAux, dS, dS2, dJ + B.j_ransB, B.j_rabsB - B.j_ransB); launches++; }
+    stamp();
+    if (B.j_wrap - B.j_rabsB > 0) { k_rabs<<<B.j_wrap - B.j_rabsB, 32, 0, st>>>(dF, dC, dBlob, dS, dS2, dJ + B.j_rabsB, B.j_wrap - B.j_rabsB); launches++; }
     stamp();
     const unsigned gn = (maxN + 127) / 128;
-    if (maxattr) { k_parents<<<dim3(gn, n, maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++; }
-    if (j_uv - j_wrap > 0) { k_predict_wrap<<<j_uv - j_wrap, 32, 0, st>>>(dF, dC, dS2, dJ + j_wrap, j_uv - j_wrap); launches++; }
+    k_parents<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
     stamp();
-    if (maxattr) {
-        k_uv_prepare<<<dim3(gn, n, maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
-        if (j_end - j_uv > 0) { k_predict_uv<<<j_end - j_uv, 32, 0, st>>>(dF, dC, dS2, dJ + j_uv, j_end - j_uv); launches++; }
-        k_normals<<<dim3(gn, n, maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
-    }
+    if (B.j_uv - B.j_wrap > 0) { k_predict_wrap<<<B.j_uv - B.j_wrap, 32, 0, st>>>(dF, dC, dS2, dJ + B.j_wrap, B.j_uv - B.j_wrap); launches++; }
     stamp();
-    if (maxattr) { k_expand<<<dim3((maxP + 255) / 256, n, maxattr), 256, 0, st>>>(dF, dC, dS, dS2, dZ2, dO); launches++; }
+    k_uv_prepare<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
+    stamp();
+    if (B.j_end - B.j_uv > 0) { k_predict_uv<<<B.j_end - B.j_uv, 32, 0, st>>>(dF, dC, dS2, dJ + B.j_uv, B.j_end - B.j_uv); launches++; }
+    stamp();
+    k_normals<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
+    stamp();
+    k_expand<<<dim3((maxP + 255) / 256, n, B.maxattr), 256, 0, st>>>(dF, dC, dS, dS2, dZ2, dO); launches++;
     stamp();
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (memory == UVOL_MEM_HOST) {
@@ -499,6 +519,7 @@ extern "C" int uvol_decode_draco_batch(uvol_ctx *ctx, const uint8_t *const *data
     uint64_t bytes_out = 0;
     for (int i = 0; i < n; i++) {
         const DracoFrame &f = frames[i]; uvol_geometry &g = out[i];
+        memset(&g, 0, sizeof g);
         g.status = f.status ? f.status : hC[i].status;
         if (g.status) continue;
         g.num_points = hC[i].num_points; g.num_faces = f.nf;
@@ -510,13 +531,37 @@ extern "C" int uvol_decode_draco_batch(uvol_ctx *ctx, const uint8_t *const *data
         }
     }
     uvol_stats &s = ctx->stats;
-    s.host_parse_ms = t_parsed - t_begin; s.total_ms = now_ms() - t_begin; s.kernel_launches = launches;
-    s.bytes_in = 0; for (int i = 0; i < n; i++) s.bytes_in += size[i];
-    s.bytes_out = bytes_out; s.scratch_bytes = pl.scratch + pl.zscratch + pl.scratch2 + pl.zscratch2;
+    s.kernel_launches = launches; s.bytes_in = B.bytes_in; s.bytes_out = bytes_out;
+    s.scratch_bytes = pl.scratch + pl.zscratch + pl.scratch2 + pl.zscratch2;
     if (ctx->profile) {
         s.num_stages = (uint32_t)(ev - 1);
-        for (int k = 0; k + 1 < ev; k++) cudaEventElapsedTime(&s.stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);
-        float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[ev - 1]); s.device_ms = tot;
+        for (int k = 0; k + 1 < ev && k < 24; k++) cudaEventElapsedTime(&s.stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);
+        float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[1], ctx->ev[ev - 2]); s.device_ms = tot;   // kernels only: after h2d, before d2h
+        s.h2d_ms = s.stage_ms[0]; s.d2h_ms = s.stage_ms[ev - 2];
     }
+    return UVOL_OK;
+}
+
+extern "C" int uvol_decode_draco_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int memory, uvol_geometry *out) {
+    if (!ctx || !out || n < 0 || (n > 0 && (!data || !size))) return UVOL_ERR_ARG;
+    UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    if (n == 0) { if (ctx->geo) ctx->geo->n = 0; return UVOL_OK; }
+    const double t0 = now_ms();
+    int rc = draco_prepare(ctx, data, size, n); if (rc) return rc;
+    rc = draco_run(ctx, memory, out, true); if (rc) return rc;
+    ctx->stats.host_parse_ms = ctx->geo->parse_ms; ctx->stats.total_ms = now_ms() - t0;
+    return UVOL_OK;
+}
+
+// Re-runs the device pipeline on the batch that is still resident in HBM from the last
+// uvol_decode_draco_batch call (no parse, no input upload).  Used to time the kernels alone.
+extern "C" int uvol_replay_draco_batch(uvol_ctx *ctx, int memory, uvol_geometry *out, int n) {
+    if (!ctx || !out || !ctx->geo || ctx->geo->n != n || n <= 0) return UVOL_ERR_ARG;
+    UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    const double t0 = now_ms();
+    const int rc = draco_run(ctx, memory, out, false); if (rc) return rc;
+    ctx->stats.total_ms = now_ms() - t0;
     return UVOL_OK;
 }

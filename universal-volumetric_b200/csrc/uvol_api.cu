@@ -32,6 +32,10 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     for (auto *b : db) b->release();
     PinBuf *pb[] = {&c->h_blob, &c->h_desc, &c->h_aux, &c->h_counts, &c->h_out, &c->h_tblob, &c->h_tdesc, &c->h_tout, &c->h_cblob, &c->h_cdesc, &c->h_cout, &c->h_ccounts};
     for (auto *b : pb) b->release();
+    c->d_flush.release();
+    if (c->geo) uvol_geo_batch_free(c->geo);
+    if (c->tex) uvol_tex_batch_free(c->tex);
+    if (c->corto) uvol_corto_batch_free(c->corto);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->s0) cudaStreamDestroy(c->s0);
     if (c->s1) cudaStreamDestroy(c->s1);
@@ -46,4 +50,14 @@ extern "C" const char *uvol_stage_name(int kind, int stage) {
     if (kind == 1) return uvol_tex_stage_name(stage);
     if (kind == 2) return uvol_corto_stage_name(stage);
     return "";
+}
+
+extern "C" int uvol_flush_l2(uvol_ctx *c) {
+    if (!c) return UVOL_ERR_ARG;
+    UVOL_CUDA(c, cudaSetDevice(c->device));
+    const size_t bytes = 256ull << 20;
+    UVOL_CUDA(c, c->d_flush.reserve(bytes));
+    UVOL_CUDA(c, cudaMemsetAsync(c->d_flush.p, 0x5a, bytes, c->s0));
+    UVOL_CUDA(c, cudaStreamSynchronize(c->s0));
+    return UVOL_OK;
 }

@@ -37,13 +37,14 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-struct StageTimes { float ms[16]; };
+struct GeoBatch; struct TexBatch; struct CortoBatch;
+void uvol_geo_batch_free(GeoBatch *); void uvol_tex_batch_free(TexBatch *); void uvol_corto_batch_free(CortoBatch *);
 
 struct uvol_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t s0 = nullptr, s1 = nullptr;
-    cudaEvent_t ev[20] = {};
+    cudaEvent_t ev[32] = {};
     std::string err;
     // geometry path
     PinBuf h_blob, h_desc, h_aux, h_counts, h_out;
@@ -55,6 +56,8 @@ struct uvol_ctx {
     // V1 path
     PinBuf h_cblob, h_cdesc, h_cout, h_ccounts;
     DevBuf d_cblob, d_cdesc, d_cscratch, d_czscratch, d_out_corto, d_ccounts, d_caux;
+    GeoBatch *geo = nullptr; TexBatch *tex = nullptr; CortoBatch *corto = nullptr;
+    DevBuf d_flush;
     // stats of the last batch
     uvol_stats stats = {};
     bool profile = false;

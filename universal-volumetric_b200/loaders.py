@@ -46,6 +46,12 @@ class Context:
         except Exception:
             pass
 
+    def flush_l2(self):
+        self._L.uvol_flush_l2(self._h)
+
+    def set_profiling(self, on):
+        self._L.uvol_set_profiling(self._h, 1 if on else 0)
+
     def last_error(self):
         return self._L.uvol_last_error(self._h).decode()
 
@@ -86,6 +92,14 @@ class DRACOLoader:
         self._keep = keep
         return out
 
+    def replay_raw(self, n, memory=N.MEM_DEVICE):
+        """Re-runs the device pipeline on the batch still resident in HBM (measurement aid)."""
+        out = (N.Geometry * n)()
+        rc = self.ctx._L.uvol_replay_draco_batch(self.ctx._h, memory, out, n)
+        if rc != 0:
+            raise N.UvolError(f"uvol_replay_draco_batch failed ({rc}): {self.ctx.last_error()}")
+        return out
+
     def decode_batch(self, files):
         """Decodes .drc byte strings; returns one dict per file (numpy copies of the host buffers)."""
         raw = self.decode_batch_raw(files, N.MEM_HOST)
@@ -120,6 +134,13 @@ class KTX2Loader:
         if rc != 0:
             raise N.UvolError(f"uvol_transcode_ktx2_batch failed ({rc}): {self.ctx.last_error()}")
         self._keep = keep
+        return out
+
+    def replay_raw(self, n, memory=N.MEM_DEVICE):
+        out = (N.Texture * n)()
+        rc = self.ctx._L.uvol_replay_ktx2_batch(self.ctx._h, memory, out, n)
+        if rc != 0:
+            raise N.UvolError(f"uvol_replay_ktx2_batch failed ({rc}): {self.ctx.last_error()}")
         return out
 
     def transcode_batch(self, files):
