@@ -10,8 +10,9 @@ tools/synth (deterministic, seed 20260002).  One "step" = one pass of the hot pa
 sequence (300 .drc + 43 .ktx2).  N>1: every rank decodes its own 300-frame sequence (frames are
 independent units, no data-path collective) -> "scaling": "weak"; value = all frames / max-over-ranks time.
 
-  value     frames/s with the compressed inputs already resident in HBM (uvol_replay_*_batch), device
-            time from CUDA events on the library's stream, outputs left in HBM.
+  value     frames/s with the compressed inputs already resident in HBM (uvol_replay_v2_batch), device
+            time from CUDA events on the library's streams (geometry and texture run concurrently, the
+            step time is the longer of the two spans), outputs left in HBM.
   e2e       frames/s through the C ABI with HOST buffers: uvol_decode_draco_batch +
             uvol_transcode_ktx2_batch with UVOL_MEM_HOST (host parse, H2D of the compressed bytes,
             kernels, D2H of every decoded buffer into pinned host memory), wall clock around the calls.
@@ -193,7 +194,7 @@ def main():
     uv = importlib.import_module("universal-volumetric_b200")
     drc, ktx, info = make_workload(args.workload, rank)
     ctx = uv.Context(local, profiling=True)
-    dl, kl = uv.DRACOLoader(ctx), uv.KTX2Loader(ctx)
+    player = uv.V2Player(ctx)
     n_d, n_k = len(drc), len(ktx)
 
     def barrier():
@@ -202,14 +203,12 @@ def main():
         torch.cuda.synchronize()
 
     def e2e_step():
-        g = dl.decode_batch_raw(drc, uv.MEM_HOST); sg = ctx.stats(0)
-        t = kl.transcode_batch_raw(ktx, uv.MEM_HOST); st = ctx.stats(1)
-        return g, t, sg, st
+        g, t = player.decode_step_raw(drc, ktx, uv.MEM_HOST)
+        return g, t, ctx.stats(0, combined=True), ctx.stats(1, combined=True)
 
     def resident_step():
-        g = dl.replay_raw(n_d, uv.MEM_DEVICE); sg = ctx.stats(0)
-        t = kl.replay_raw(n_k, uv.MEM_DEVICE); st = ctx.stats(1)
-        return g, t, sg, st
+        g, t = player.replay_step_raw(n_d, n_k, uv.MEM_DEVICE)
+        return g, t, ctx.stats(0, combined=True), ctx.stats(1, combined=True)
 
     # warm-up (also uploads the batch that the resident steps replay)
     for _ in range(max(args.warmup, 1)):
@@ -227,7 +226,7 @@ def main():
     for _ in range(args.steps):
         ctx.flush_l2()
         g, t, sg, st = resident_step()
-        dev_ms += sg["device_ms"] + st["device_ms"]; launches += sg["kernel_launches"] + st["kernel_launches"]
+        dev_ms += max(sg["device_ms"], st["device_ms"]); launches += sg["kernel_launches"] + st["kernel_launches"]
         for k, v in list(sg["stages"].items()) + [("tex_" + k, v) for k, v in st["stages"].items()]:
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     barrier(); wall_resident = time.perf_counter() - t0
@@ -253,14 +252,14 @@ def main():
     gb, tb = stage_bytes(info, P_total, frames, sg["bytes_in"], st["bytes_in"])
     stages = {}
     for k, ms in stage_acc.items():
-        nbytes = gb.get(k) if not k.startswith("tex_") else tb.get(k[4:])
+        nbytes = gb.get(k.replace("(s1)", "")) if not k.startswith("tex_") else tb.get(k[4:])
         per = ms / args.steps
         stages[k] = {"ms": round(per, 4), "share": round(ms / (dev_ms if world == 1 else sum(stage_acc.values())), 4)}
         if nbytes and per > 0:
             stages[k]["gbs"] = round(nbytes / (per * 1e-3) / 1e9, 2); stages[k]["frac"] = round(stages[k]["gbs"] / peak, 5)
     kernel_stages = {k: v for k, v in stages.items() if k not in ("h2d", "d2h", "tex_h2d", "tex_d2h", "counts_readback")}
     dom = max(kernel_stages, key=lambda k: kernel_stages[k]["ms"])
-    dom_bytes = gb.get(dom) if not dom.startswith("tex_") else tb.get(dom[4:])
+    dom_bytes = gb.get(dom.replace("(s1)", "")) if not dom.startswith("tex_") else tb.get(dom[4:])
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernel_stages[dom].get("gbs"), "peak": peak, "unit": "GB/s", "frac": kernel_stages[dom].get("frac"),
             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": kernel_stages[dom]["ms"],
             "note": "dominant stage is a latency-bound serial walk (one warp per frame); HBM-bound stages are listed in `stages`"}
@@ -293,7 +292,7 @@ def main():
                 "roofline": roof, "pipeline_roofline": pipeline, "stages": stages,
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
-                        "path": "uvol_decode_draco_batch + uvol_transcode_ktx2_batch, UVOL_MEM_HOST"},
+                        "path": "uvol_decode_v2_batch (geometry and texture streams concurrent), UVOL_MEM_HOST"},
                 "gpu_launches": launches + launches_e2e * args.steps, "clocks": clk,
                 "wall_ms_per_step_resident": wall_resident / args.steps * 1e3, "workload_gen_s": info["gen_s"]}
         print(json.dumps(line))

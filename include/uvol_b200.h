@@ -100,6 +100,15 @@ int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const s
 
 int uvol_replay_ktx2_batch(uvol_ctx *ctx, int memory, uvol_texture *out, int n);
 
+/* ---- one V2 playback step: n_drc geometry frames and n_ktx2 texture segments decoded CONCURRENTLY
+ * (separate CUDA streams), like V2Player.fetchBuffers issuing decodeDraco and decodeKTX2 requests to its
+ * two worker pools at once (src/V2/player.ts:272-323).  Results as for the two single-kind calls. */
+int uvol_decode_v2_batch(uvol_ctx *ctx, const uint8_t *const *drc, const size_t *drc_size, int n_drc,
+                         const uint8_t *const *ktx2, const size_t *ktx2_size, int n_ktx2,
+                         int memory, uvol_geometry *out_geo, uvol_texture *out_tex);
+int uvol_replay_v2_batch(uvol_ctx *ctx, int memory, uvol_geometry *out_geo, int n_drc, uvol_texture *out_tex, int n_ktx2);
+int uvol_get_stats_kind(const uvol_ctx *ctx, int kind /*0 geometry, 1 texture*/, uvol_stats *out);
+
 /* Writes a buffer larger than L2 (256 MiB) on the ctx's stream and waits: L2 flush between timed iterations. */
 int uvol_flush_l2(uvol_ctx *ctx);
 

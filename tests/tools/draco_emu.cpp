@@ -83,7 +83,8 @@ extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_p
         if (f.o_d2c[t] == UVOL_NONE) continue;
         tv[t] = (t == 0) ? TableView{m.opp, m.c2v, nullptr, nullptr, nullptr} : TableView{m.opp, m.c2v, Z + f.o_eos[t - 1], ac2v[t - 1], vos[t - 1]};
         const int maxe = (int)(t == 0 ? cnt.num_vertex_slots : cnt.attr_vertices[t - 1]);
-        rc = traverse_table(tv[t], m.lmc, F, Z2 + f.o_fvis[t], (int *)(Z2 + f.o_v2d[t]), (int *)(S2 + f.o_d2c[t]), (int *)(S2 + f.o_tstack[t]), maxe, &cnt.entries[t]);
+        std::vector<uint8_t> fvis_t(F + 4, 0);
+        rc = traverse_table(tv[t], m.lmc, F, fvis_t.data(), (int *)(Z2 + f.o_v2d[t]), (int *)(S2 + f.o_d2c[t]), (int *)(S2 + f.o_tstack[t]), maxe, &cnt.entries[t]);
         if (rc) return rc;
     }
     // attribute symbol runs + aux bits

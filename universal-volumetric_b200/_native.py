@@ -65,9 +65,13 @@ def lib():
     L.uvol_replay_draco_batch.argtypes = [vp, i, ctypes.POINTER(Geometry), i]; L.uvol_replay_draco_batch.restype = i
     L.uvol_replay_ktx2_batch.argtypes = [vp, i, ctypes.POINTER(Texture), i]; L.uvol_replay_ktx2_batch.restype = i
     L.uvol_flush_l2.argtypes = [vp]; L.uvol_flush_l2.restype = i
+    pv, ps = ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz)
+    L.uvol_decode_v2_batch.argtypes = [vp, pv, ps, i, pv, ps, i, i, ctypes.POINTER(Geometry), ctypes.POINTER(Texture)]; L.uvol_decode_v2_batch.restype = i
+    L.uvol_replay_v2_batch.argtypes = [vp, i, ctypes.POINTER(Geometry), i, ctypes.POINTER(Texture), i]; L.uvol_replay_v2_batch.restype = i
+    L.uvol_get_stats_kind.argtypes = [vp, i, ctypes.POINTER(Stats)]; L.uvol_get_stats_kind.restype = i
     _lib = L
     return L
 
 
 EXPORTED_SYMBOLS = ["uvol_create", "uvol_destroy", "uvol_last_error", "uvol_get_stats", "uvol_stage_name", "uvol_set_profiling",
-                    "uvol_decode_draco_batch", "uvol_transcode_ktx2_batch", "uvol_replay_draco_batch", "uvol_replay_ktx2_batch", "uvol_flush_l2"]
+                    "uvol_decode_draco_batch", "uvol_transcode_ktx2_batch", "uvol_replay_draco_batch", "uvol_replay_ktx2_batch", "uvol_flush_l2", "uvol_decode_v2_batch", "uvol_replay_v2_batch", "uvol_get_stats_kind"]

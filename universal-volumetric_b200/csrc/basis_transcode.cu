@@ -152,7 +152,7 @@ extern "C" const char *uvol_tex_stage_name(int i) { return (i >= 0 && i < 6) ? k
 struct TexBatch {
     std::vector<Ktx2File> files; std::vector<Ktx2Slice> slices; std::vector<uint32_t> layer_list, uastc_layers;
     int n = 0; uint64_t blob_bytes = 0, scratch = 0, out = 0, bytes_in = 0; uint32_t max_blocks = 1; bool any_alpha = false;
-    size_t desc_bytes = 0, off_sl = 0, off_ll = 0, off_ul = 0; double parse_ms = 0;
+    size_t desc_bytes = 0, off_sl = 0, off_ll = 0, off_ul = 0; double parse_ms = 0; uint32_t launches = 0; int nev = 0;
 };
 void uvol_tex_batch_free(TexBatch *b) { delete b; }
 
@@ -204,19 +204,19 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
     if (nll) memcpy(hd + B.off_ll, B.layer_list.data(), 4 * nll);
     if (nul) memcpy(hd + B.off_ul, B.uastc_layers.data(), 4 * nul);
     B.parse_ms = now_ms() - t_begin;
-    cudaStream_t st = ctx->s0;
-    if (ctx->profile) cudaEventRecord(ctx->ev[0], st);
+    cudaStream_t st = ctx->s2;
+    if (ctx->profile) cudaEventRecord(ctx->tex_ev[0], st);
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_tblob.p, ctx->h_tblob.p, blob_bytes, cudaMemcpyHostToDevice, st));
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc.p, hd, B.desc_bytes, cudaMemcpyHostToDevice, st));
     return UVOL_OK;
 }
 
-static int ktx2_run(uvol_ctx *ctx, int memory, uvol_texture *out, bool fresh_upload) {
+// Enqueues the whole texture pipeline (kernels + result copies) on stream `st`; no host sync.
+static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_t st) {
     TexBatch &B = *ctx->tex; const int n = B.n;
-    cudaStream_t st = ctx->s0;
     int ev = 1;
-    auto stamp = [&]() { if (ctx->profile && ev < 32) cudaEventRecord(ctx->ev[ev++], st); };
-    if (!fresh_upload && ctx->profile) cudaEventRecord(ctx->ev[0], st);
+    auto stamp = [&]() { if (ctx->profile && ev < 8) cudaEventRecord(ctx->tex_ev[ev++], st); };
+    if (!fresh_upload && ctx->profile) cudaEventRecord(ctx->tex_ev[0], st);
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_tslices.p, 0, sizeof(TexState) * (size_t)n, st));
     stamp();
     const size_t nsl = B.slices.size(), nll = B.layer_list.size(), nul = B.uastc_layers.size();
@@ -241,9 +241,17 @@ static int ktx2_run(uvol_ctx *ctx, int memory, uvol_texture *out, bool fresh_upl
     UVOL_CUDA(ctx, cudaMemcpyAsync(hSt, dSt, sizeof(TexState) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(hO, dO, B.out, cudaMemcpyDeviceToHost, st));
     stamp();
-    UVOL_CUDA(ctx, cudaStreamSynchronize(st));
+    B.launches = launches; B.nev = ev;
+    return UVOL_OK;
+}
+
+// After the stream has been synchronised: fills the result structs and the statistics.
+static int ktx2_finish(uvol_ctx *ctx, int memory, uvol_texture *out, uvol_stats &sx) {
+    TexBatch &B = *ctx->tex; const int n = B.n;
     UVOL_CUDA(ctx, cudaGetLastError());
-    uint8_t *base = memory == UVOL_MEM_HOST ? hO : dO; uint64_t bytes_out = 0;
+    const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
+    TexState *hSt = (TexState *)ctx->h_tout.p; uint8_t *hO = (uint8_t *)ctx->h_tout.p + st_bytes;
+    uint8_t *base = memory == UVOL_MEM_HOST ? hO : (uint8_t *)ctx->d_out_tex.p; uint64_t bytes_out = 0;
     for (int i = 0; i < n; i++) {
         const Ktx2File &f = B.files[i]; uvol_texture &t = out[i];
         memset(&t, 0, sizeof t);
@@ -253,15 +261,21 @@ static int ktx2_run(uvol_ctx *ctx, int memory, uvol_texture *out, bool fresh_upl
         t.dfd_transfer = f.dfd_transfer; t.dfd_flags = f.dfd_flags;
         t.bytes = (uint64_t)f.layers * f.width * f.height * 4; t.data = base + f.o_rgba; bytes_out += t.bytes;
     }
-    uvol_stats &sx = ctx->stats;
-    sx.kernel_launches = launches; sx.bytes_in = B.bytes_in; sx.bytes_out = bytes_out; sx.scratch_bytes = B.scratch;
+    sx.kernel_launches = B.launches; sx.bytes_in = B.bytes_in; sx.bytes_out = bytes_out; sx.scratch_bytes = B.scratch;
     if (ctx->profile) {
+        const int ev = B.nev;
         sx.num_stages = (uint32_t)(ev - 1);
-        for (int k = 0; k + 1 < ev && k < 24; k++) cudaEventElapsedTime(&sx.stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);
-        float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[1], ctx->ev[ev - 2]); sx.device_ms = tot;
+        for (int k = 0; k + 1 < ev && k < 24; k++) cudaEventElapsedTime(&sx.stage_ms[k], ctx->tex_ev[k], ctx->tex_ev[k + 1]);
+        float tot = 0; cudaEventElapsedTime(&tot, ctx->tex_ev[1], ctx->tex_ev[ev - 2]); sx.device_ms = tot;
         sx.h2d_ms = sx.stage_ms[0]; sx.d2h_ms = sx.stage_ms[ev - 2];
     }
     return UVOL_OK;
+}
+
+static int ktx2_run(uvol_ctx *ctx, int memory, uvol_texture *out, bool fresh_upload) {
+    int rc = ktx2_launch(ctx, memory, fresh_upload, ctx->s2); if (rc) return rc;
+    UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s2));
+    return ktx2_finish(ctx, memory, out, ctx->stats);
 }
 
 extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target_format, int memory, uvol_texture *out) {
@@ -286,3 +300,38 @@ extern "C" int uvol_replay_ktx2_batch(uvol_ctx *ctx, int memory, uvol_texture *o
     ctx->stats.total_ms = now_ms() - t0;
     return UVOL_OK;
 }
+
+// ---- combined V2 step: geometry frames + texture segments decoded concurrently on separate streams,
+// like V2Player.fetchBuffers issuing decodeDraco and decodeKTX2 requests to two worker pools at once
+// (src/V2/player.ts:272-323).
+int uvol_geo_prepare_and_run(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int memory, uvol_geometry *out, bool replay);
+
+extern "C" int uvol_decode_v2_batch(uvol_ctx *ctx, const uint8_t *const *drc, const size_t *drc_size, int n_drc, const uint8_t *const *ktx2, const size_t *ktx2_size,
+                                    int n_ktx2, int memory, uvol_geometry *out_geo, uvol_texture *out_tex) {
+    if (!ctx || n_drc < 0 || n_ktx2 < 0 || (n_drc && (!drc || !drc_size || !out_geo)) || (n_ktx2 && (!ktx2 || !ktx2_size || !out_tex)) || n_ktx2 >= (1 << 19)) return UVOL_ERR_ARG;
+    UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(&ctx->stats, 0, sizeof ctx->stats); memset(&ctx->stats_tex, 0, sizeof ctx->stats_tex);
+    const double t0 = now_ms();
+    int rc;
+    if (n_ktx2) { rc = ktx2_prepare(ctx, ktx2, ktx2_size, n_ktx2); if (rc) return rc; rc = ktx2_launch(ctx, memory, true, ctx->s2); if (rc) return rc; }
+    if (n_drc) { rc = uvol_geo_prepare_and_run(ctx, drc, drc_size, n_drc, memory, out_geo, false); if (rc) return rc; }
+    if (n_ktx2) { UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s2)); rc = ktx2_finish(ctx, memory, out_tex, ctx->stats_tex); if (rc) return rc; ctx->stats_tex.host_parse_ms = ctx->tex->parse_ms; }
+    ctx->stats.total_ms = ctx->stats_tex.total_ms = now_ms() - t0;
+    return UVOL_OK;
+}
+
+// Same, on the batches still resident in HBM (no parse, no input upload).
+extern "C" int uvol_replay_v2_batch(uvol_ctx *ctx, int memory, uvol_geometry *out_geo, int n_drc, uvol_texture *out_tex, int n_ktx2) {
+    if (!ctx || (n_drc && (!ctx->geo || !out_geo)) || (n_ktx2 && (!ctx->tex || ctx->tex->n != n_ktx2 || !out_tex))) return UVOL_ERR_ARG;
+    UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(&ctx->stats, 0, sizeof ctx->stats); memset(&ctx->stats_tex, 0, sizeof ctx->stats_tex);
+    const double t0 = now_ms();
+    int rc;
+    if (n_ktx2) { rc = ktx2_launch(ctx, memory, false, ctx->s2); if (rc) return rc; }
+    if (n_drc) { rc = uvol_geo_prepare_and_run(ctx, nullptr, nullptr, n_drc, memory, out_geo, true); if (rc) return rc; }
+    if (n_ktx2) { UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s2)); rc = ktx2_finish(ctx, memory, out_tex, ctx->stats_tex); if (rc) return rc; }
+    ctx->stats.total_ms = ctx->stats_tex.total_ms = now_ms() - t0;
+    return UVOL_OK;
+}
+
+extern "C" int uvol_get_stats_kind(const uvol_ctx *c, int kind, uvol_stats *out) { if (!c || !out) return UVOL_ERR_ARG; *out = kind == 1 ? c->stats_tex : c->stats; return UVOL_OK; }

@@ -94,7 +94,7 @@ struct EbMem {
 UVOL_HD int b_swl(const int *opp, int c) { if (c < 0) return DINV; int o = opp[cnext(c)]; return o < 0 ? DINV : cnext(o); }
 UVOL_HD int b_swr(const int *opp, int c) { if (c < 0) return DINV; int o = opp[cprev(c)]; return o < 0 ? DINV : cprev(o); }
 
-UVOL_HD int eb_decode_frame(const DracoFrame &f, const uint8_t *file, const uint32_t *aux, EbMem &m, uint32_t *out_vertex_slots) {
+UVOL_HD int eb_decode_frame(const DracoFrame &f, const uint8_t *file, const uint32_t *aux, EbMem &m, uint32_t *out_vertex_slots, uint32_t *out_valid = nullptr) {
     const int F = (int)f.nf, maxv = (int)(f.nv_enc + f.nsplit), nsym = (int)f.nsym;
     int *opp = m.opp, *c2v = m.c2v, *lmc = m.lmc, *val = m.val, *stack = m.stack;
     uint8_t *hole = m.hole;
@@ -239,6 +239,7 @@ UVOL_HD int eb_decode_frame(const DracoFrame &f, const uint8_t *file, const uint
         }
     }
     *out_vertex_slots = (uint32_t)nverts;
+    if (out_valid) *out_valid = (uint32_t)(nverts - ninv);
     return UVOL_OK;
 #undef EB_FAIL
 #undef EB_ADDV

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(32) k_rans(const DracoFrame *frames, DracoCoun
         const DracoAttr &a = f.attr[jb.what - 16];
         s = a.sym; out = scratch2 + f.o_corr[jb.what - 16];
         mode = (a.pred != -2 && (a.xform == 2 || a.xform == 3)) ? 2 : 1;
-        count = counts[jb.frame].entries[a.table + 1] * (uint32_t)a.vnc;
+        count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
     }
     const uint32_t A = s.alphabet, lane = threadIdx.x;
     uint32_t *cum = smem; uint16_t *bucket = (uint16_t *)(smem + A + 1);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(32) k_rabs(const DracoFrame *frames, DracoCoun
         const DracoAttr &a = f.attr[jb.what - 16];
         if (!rabs_init(r, file, a.aux_bits)) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
         uint8_t *o = scratch2 + f.o_auxbits[jb.what - 16];
-        const uint32_t n = counts[jb.frame].entries[a.table + 1];
+        const uint32_t n = counts[jb.frame].expected[a.table + 1];
         if (a.pred == 5) {
             if ((uint32_t)a.num_orient > n) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
             int last = 1;
@@ -103,15 +103,208 @@ __global__ void __launch_bounds__(32) k_edgebreaker(const DracoFrame *frames, Dr
     const uint32_t fi = blockIdx.x;
     if ((int)fi >= nframes || threadIdx.x != 0) return;
     if (frames[fi].status) { counts[fi].status = frames[fi].status; return; }
-    if (counts[fi].status) return;
+    if (counts[fi].status || frames[fi].trav == 2) return;      // valence frames: k_edgebreaker_valence
     const DracoFrame &f = frames[fi];
     EbMem m; m.opp = (int *)(S + f.o_opp); m.c2v = (int *)(S + f.o_c2v); m.lmc = (int *)(S + f.o_lmc); m.val = (int *)(S + f.o_val);
     m.hole = S + f.o_hole; m.stack = (int *)(S + f.o_stack); m.skey = m.stack + f.nsym + 8; m.sval = m.skey + f.nts + 1; m.invalid = (int *)(S + f.o_invalid);
     for (int i = 0; i < 6; i++) m.ctxsym[i] = S + f.o_ctxsym[i];
-    uint32_t slots = 0;
-    const int rc = eb_decode_frame(f, blob + f.file_off, aux, m, &slots);
-    counts[fi].num_vertex_slots = slots;
+    uint32_t slots = 0, valid = 0;
+    const int rc = eb_decode_frame(f, blob + f.file_off, aux, m, &slots, &valid);
+    counts[fi].num_vertex_slots = slots; counts[fi].expected[0] = valid;
     if (rc) frame_fail(counts, fi, rc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Valence-mode edgebreaker, latency-optimised (the generic k_edgebreaker above remains the path for
+// the standard traversal).  The walk is a serial state machine (the next symbol's context depends on
+// the mesh built so far), so the only lever is the length of the dependent chain per symbol:
+//   * the active triangle (corner + its three vertices AND their vertex records) lives in registers;
+//   * per-vertex state is one 16-byte record {left-most corner, vertex before it on the boundary,
+//     valence, on-hole flag}: a C symbol needs exactly one record load (the boundary neighbour), R / L / E none;
+//   * records of the most recent EB_RING vertices sit in a shared-memory ring (the boundary vertices
+//     a C symbol touches were created about one strip earlier), older ones are read from global;
+//   * the next symbol of all six contexts is preloaded in registers, so the context -> symbol step
+//     is a select, not a load; opp / c2v are write-only here.
+// S symbols, topology-split events, start faces and the isolated-vertex fold use the generic memory path.
+#define EB_RING 2048
+struct VRec { int lmc, lpv, val, hole; };
+__device__ __forceinline__ VRec vr_unpack(uint4 u) { VRec r; r.lmc = (int)u.x; r.lpv = (int)u.y; r.val = (int)u.z; r.hole = (int)u.w; return r; }
+__device__ __forceinline__ uint4 vr_pack(const VRec &r) { return make_uint4((uint32_t)r.lmc, (uint32_t)r.lpv, (uint32_t)r.val, (uint32_t)r.hole); }
+
+__global__ void __launch_bounds__(32) k_edgebreaker_valence(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
+                                                            uint8_t *S, int nframes) {
+    __shared__ uint4 ring[EB_RING];
+    __shared__ int stk[512];
+    const uint32_t fi = blockIdx.x;
+    if ((int)fi >= nframes) return;
+    if (frames[fi].status) { if (threadIdx.x == 0) counts[fi].status = frames[fi].status; return; }
+    if (counts[fi].status || frames[fi].trav != 2) return;
+    const DracoFrame &f = frames[fi];
+    const int lane = threadIdx.x;
+    int *opp = (int *)(S + f.o_opp), *c2v = (int *)(S + f.o_c2v), *lmc = (int *)(S + f.o_lmc), *gstk = (int *)(S + f.o_stack);
+    uint8_t *hole = S + f.o_hole; uint4 *vrec = (uint4 *)(S + f.o_val);     // o_val is sized 16 B per vertex slot (see draco_plan.h)
+    int *skey = gstk + f.nsym + 8, *sval = skey + f.nts + 1, *invalid = (int *)(S + f.o_invalid);
+    const int F = (int)f.nf, maxv = (int)(f.nv_enc + f.nsplit), nsym = (int)f.nsym;
+    int nverts = 0, ninv = 0, sp = 0, status = 0, numf = 0;
+    if (lane == 0) {
+        const uint8_t *cs0 = S + f.o_ctxsym[0], *cs1 = S + f.o_ctxsym[1], *cs2 = S + f.o_ctxsym[2], *cs3 = S + f.o_ctxsym[3], *cs4 = S + f.o_ctxsym[4], *cs5 = S + f.o_ctxsym[5];
+        int k0 = (int)f.ctx[0].count, k1 = (int)f.ctx[1].count, k2 = (int)f.ctx[2].count, k3 = (int)f.ctx[3].count, k4 = (int)f.ctx[4].count, k5 = (int)f.ctx[5].count;
+        int n0 = k0 ? cs0[k0 - 1] : 255, n1 = k1 ? cs1[k1 - 1] : 255, n2 = k2 ? cs2[k2 - 1] : 255, n3 = k3 ? cs3[k3 - 1] : 255, n4 = k4 ? cs4[k4 - 1] : 255, n5 = k5 ? cs5[k5 - 1] : 255;
+        const uint32_t *ts = aux + f.ts_off; int ts_top = (int)f.nts, nsa = 0;
+        uint32_t next_ts = ts_top > 0 ? ts[3 * (ts_top - 1)] : 0xffffffffu;
+        int a = -1, ta = 0, na = 0, pa = 0; VRec rt = {0, 0, 0, 0}, rn = rt, rp = rt;
+        int ctx = -1;
+#define VLOAD(v) vr_unpack(((v) >= nverts - EB_RING) ? ring[(v) & (EB_RING - 1)] : vrec[(v)])
+#define VSTORE(v, r) do { const uint4 u_ = vr_pack(r); if ((v) >= nverts - EB_RING) ring[(v) & (EB_RING - 1)] = u_; vrec[(v)] = u_; } while (0)
+        for (int sid = 0; sid < nsym; sid++) {
+            int s;
+            if (ctx < 0) s = 4;
+            else {
+                switch (ctx) {
+                    case 0: s = n0; --k0; n0 = k0 > 0 ? cs0[k0 - 1] : 255; break;
+                    case 1: s = n1; --k1; n1 = k1 > 0 ? cs1[k1 - 1] : 255; break;
+                    case 2: s = n2; --k2; n2 = k2 > 0 ? cs2[k2 - 1] : 255; break;
+                    case 3: s = n3; --k3; n3 = k3 > 0 ? cs3[k3 - 1] : 255; break;
+                    case 4: s = n4; --k4; n4 = k4 > 0 ? cs4[k4 - 1] : 255; break;
+                    default: s = n5; --k5; n5 = k5 > 0 ? cs5[k5 - 1] : 255; break;
+                }
+                if (s > 4) { status = UVOL_ERR_CORRUPT; break; }
+            }
+            if (numf >= F) { status = UVOL_ERR_CORRUPT; break; }
+            const int c0 = 3 * numf; numf++;
+            if (s == 0) {                                   // C: close the fan at the vertex next to the gate
+                if (sp == 0 || rn.lmc < 0) { status = UVOL_ERR_CORRUPT; break; }
+                const int vx = na, b = cnext(rn.lmc), vbn = rn.lpv;
+                if (a == b || vx == pa || vx == vbn || vbn == pa) { status = UVOL_ERR_CORRUPT; break; }
+                VRec rb = VLOAD(vbn);
+                opp[c0] = DINV; opp[c0 + 1] = a; opp[c0 + 2] = b; opp[a] = c0 + 1; opp[b] = c0 + 2;
+                c2v[c0] = vx; c2v[c0 + 1] = vbn; c2v[c0 + 2] = pa;
+                rp.lmc = c0 + 2; rp.lpv = vbn; rp.val += 1; VSTORE(pa, rp);
+                rn.hole = 0; VSTORE(vx, rn);
+                rb.val += 1; VSTORE(vbn, rb);
+                a = c0; ta = vx; rt = rn; na = vbn; rn = rb;
+            } else if (s == 3) {                            // R: new vertex opposite the gate, continue to the left
+                if (sp == 0 || nverts >= maxv) { status = UVOL_ERR_CORRUPT; break; }
+                const int nvx = nverts++;
+                opp[c0] = DINV; opp[c0 + 1] = DINV; opp[c0 + 2] = a; opp[a] = c0 + 2;
+                c2v[c0] = pa; c2v[c0 + 1] = na; c2v[c0 + 2] = nvx;
+                VRec rnew = {c0 + 2, na, 2, 1}; VSTORE(nvx, rnew);
+                rp.lmc = c0; rp.lpv = nvx; rp.val += 1; VSTORE(pa, rp);
+                rn.val += 1; VSTORE(na, rn);
+                a = c0; ta = pa; rt = rp; pa = nvx; rp = rnew;
+            } else if (s == 2) {                            // L
+                if (sp == 0 || nverts >= maxv) { status = UVOL_ERR_CORRUPT; break; }
+                const int nvx = nverts++;
+                opp[c0] = DINV; opp[c0 + 1] = a; opp[c0 + 2] = DINV; opp[a] = c0 + 1;
+                c2v[c0] = na; c2v[c0 + 1] = nvx; c2v[c0 + 2] = pa;
+                VRec rnew = {c0 + 1, na, 2, 1}; VSTORE(nvx, rnew);
+                rp.lmc = c0 + 2; rp.lpv = nvx; rp.val += 1; VSTORE(pa, rp);
+                rn.val += 1; VSTORE(na, rn);
+                a = c0; ta = na; rt = rn; na = nvx; rn = rnew;
+            } else if (s == 4) {                            // E: isolated triangle, pushed on the stack
+                if (nverts + 3 > maxv) { status = UVOL_ERR_CORRUPT; break; }
+                const int v0 = nverts, v1 = nverts + 1, v2 = nverts + 2; nverts += 3;
+                opp[c0] = DINV; opp[c0 + 1] = DINV; opp[c0 + 2] = DINV;
+                c2v[c0] = v0; c2v[c0 + 1] = v1; c2v[c0 + 2] = v2;
+                rt = VRec{c0, v2, 2, 1}; rn = VRec{c0 + 1, v0, 2, 1}; rp = VRec{c0 + 2, v1, 2, 1};
+                VSTORE(v0, rt); VSTORE(v1, rn); VSTORE(v2, rp);
+                if (sp > 0) { if (sp <= 512) stk[sp - 1] = a; else gstk[sp - 1] = a; }
+                sp++; a = c0; ta = v0; na = v1; pa = v2;
+            } else {                                        // S: merge the two topmost components (memory path)
+                if (sp == 0) { status = UVOL_ERR_CORRUPT; break; }
+                const int b = a; sp--;
+                int a2 = -1;
+                for (int k = 0; k < nsa; k++) if (skey[k] == sid) { a2 = sval[k]; sp++; break; }
+                if (a2 < 0) { if (sp == 0) { status = UVOL_ERR_CORRUPT; break; } a2 = sp <= 512 ? stk[sp - 1] : gstk[sp - 1]; }
+                if (a2 == b || opp[a2] >= 0 || opp[b] >= 0) { status = UVOL_ERR_CORRUPT; break; }
+                opp[c0] = DINV; opp[c0 + 2] = a2; opp[a2] = c0 + 2; opp[c0 + 1] = b; opp[b] = c0 + 1;
+                const int vp = c2v[cprev(a2)], vnx = c2v[cnext(a2)], vbp = pa /* = c2v[cprev(b)] */;
+                c2v[c0] = vp; c2v[c0 + 1] = vnx; c2v[c0 + 2] = vbp;
+                { VRec r = VLOAD(vbp); r.lmc = c0 + 2; r.lpv = vnx; VSTORE(vbp, r); }
+                int cn = cnext(b); const int vn = na /* = c2v[cnext(b)] */;
+                VRec rvp = VLOAD(vp); const VRec rvn = VLOAD(vn);
+                rvp.val += rvn.val; rvp.lmc = rvn.lmc; rvp.lpv = rvn.lpv; VSTORE(vp, rvp);
+                const int first = cn; int guard = 0, bad = 0;
+                while (cn >= 0) {
+                    c2v[cn] = vp;
+                    const int cx = cnext(cn), x = c2v[cx];
+                    if (x != vn) { VRec rx = VLOAD(x); if (rx.lmc == cx) { rx.lpv = vp; VSTORE(x, rx); } }
+                    cn = b_swl(opp, cn);
+                    if (cn == first || ++guard > 3 * F) { bad = 1; break; }
+                }
+                if (bad) { status = UVOL_ERR_CORRUPT; break; }
+                { VRec r = rvn; r.lmc = DINV; VSTORE(vn, r); }
+                invalid[ninv++] = vn;
+                a = c0; ta = vp; na = vnx; pa = vbp;
+                rt = VLOAD(ta); rn = VLOAD(na); rp = VLOAD(pa);
+                rn.val += 1; rp.val += 1; VSTORE(na, rn); VSTORE(pa, rp);
+            }
+            { int v = rn.val; v = v < 2 ? 2 : (v > 7 ? 7 : v); ctx = v - 2; }
+            if (s >= 2 && (uint32_t)(nsym - sid - 1) == next_ts) {          // topology split events registered on this symbol (A.3)
+                while (ts_top > 0 && ts[3 * (ts_top - 1)] == (uint32_t)(nsym - sid - 1)) {
+                    --ts_top;
+                    skey[nsa] = nsym - (int)ts[3 * ts_top + 1] - 1;
+                    sval[nsa] = ts[3 * ts_top + 2] == 1 ? cnext(a) : cprev(a);
+                    nsa++;
+                }
+                next_ts = ts_top > 0 ? ts[3 * (ts_top - 1)] : 0xffffffffu;
+            }
+        }
+        if (sp > 0) { if (sp <= 512) stk[sp - 1] = a; else gstk[sp - 1] = a; }
+#undef VLOAD
+#undef VSTORE
+    }
+    __syncwarp();
+    nverts = __shfl_sync(0xffffffffu, nverts, 0); status = __shfl_sync(0xffffffffu, status, 0);
+    // records -> the plain arrays the later kernels read (all lanes)
+    if (!status) for (int v = lane; v < nverts; v += 32) { const uint4 u = vrec[v]; lmc[v] = (int)u.x; hole[v] = (uint8_t)u.w; }
+    __syncwarp();
+    if (lane != 0) return;
+    if (!status) {
+        // start faces (one rABS bit per remaining stack entry), then fold isolated vertices away
+        if (sp > 0) {
+            Rabs sf;
+            if (!rabs_init(sf, blob + f.file_off, f.start_faces)) status = UVOL_ERR_CORRUPT;
+            while (!status && sp > 0) {
+                const int corner = sp <= 512 ? stk[sp - 1] : gstk[sp - 1]; sp--;
+                if (rabs_bit(sf)) {
+                    const int a = corner, vn = c2v[cnext(a)];
+                    if (lmc[vn] < 0) { status = UVOL_ERR_CORRUPT; break; }
+                    const int cb = cnext(lmc[vn]), vx = c2v[cnext(cb)];
+                    if (lmc[vx] < 0) { status = UVOL_ERR_CORRUPT; break; }
+                    const int cc = cnext(lmc[vx]);
+                    if (a == cb || cb == cc || a == cc || opp[a] >= 0 || opp[cb] >= 0 || opp[cc] >= 0 || numf >= F) { status = UVOL_ERR_CORRUPT; break; }
+                    const int vp = c2v[cnext(cc)], nc = 3 * numf++;
+                    opp[nc] = a; opp[a] = nc; opp[nc + 1] = cb; opp[cb] = nc + 1; opp[nc + 2] = cc; opp[cc] = nc + 2;
+                    c2v[nc] = vx; c2v[nc + 1] = vp; c2v[nc + 2] = vn;
+                    hole[vx] = 0; hole[vp] = 0; hole[vn] = 0;
+                }
+            }
+        }
+        if (!status && numf != F) status = UVOL_ERR_CORRUPT;
+        if (!status) {
+            int num_vertices = nverts;
+            for (int k = 0; k < ninv && !status; k++) {
+                const int iv = invalid[k];
+                int src = num_vertices - 1;
+                while (src >= 0 && lmc[src] == DINV) src = --num_vertices - 1;
+                if (src < iv) continue;
+                const int cs = lmc[src]; int c = cs, left = 1, guard = 0;
+                while (c >= 0) {
+                    int nx;
+                    if (left) { nx = b_swl(opp, c); if (nx < 0) { nx = b_swr(opp, cs); left = 0; } else if (nx == cs) nx = DINV; }
+                    else nx = b_swr(opp, c);
+                    if (c2v[c] != src || ++guard > 3 * F) { status = UVOL_ERR_CORRUPT; break; }
+                    c2v[c] = iv; c = nx;
+                }
+                lmc[iv] = lmc[src]; lmc[src] = DINV;
+                hole[iv] = hole[src]; hole[src] = 0;
+                num_vertices--;
+            }
+        }
+    }
+    counts[fi].num_vertex_slots = (uint32_t)nverts; counts[fi].expected[0] = (uint32_t)(nverts - ninv);
+    if (status) frame_fail(counts, fi, status);
 }
 
 // Attribute seams: one CTA per frame.  The k-th bit of each seam stream belongs to the k-th corner
@@ -192,7 +385,7 @@ __global__ void __launch_bounds__(1024) k_scan(const DracoFrame *frames, DracoCo
         if (tid == 1023) carry_s = pre + inc;
         __syncthreads();
     }
-    if (tid == 0) { if (which < 4) counts[fi].attr_vertices[which] = (uint32_t)carry_s; else counts[fi].num_points = (uint32_t)carry_s; }
+    if (tid == 0) { if (which < 4) { counts[fi].attr_vertices[which] = (uint32_t)carry_s; counts[fi].expected[1 + which] = (uint32_t)carry_s; } else counts[fi].num_points = (uint32_t)carry_s; }
 }
 
 // AssignPointsToCorners per base vertex.  PASS 0 counts (phase 1), PASS 1 writes the index buffer and point->corner.
@@ -235,21 +428,122 @@ __device__ __forceinline__ TableView make_view(const DracoFrame &f, int t, const
     return tv;
 }
 
-// Depth-first traversal: one warp per (frame, table), lane 0 walks.  what = table (0 base, 1+i attribute data i).
-__global__ void __launch_bounds__(32) k_traverse(const DracoFrame *frames, DracoCounts *counts, const uint8_t *S, const uint8_t *Z,
-                                                 uint8_t *S2, uint8_t *Z2, const Job *jobs, int njobs) {
-    if ((int)blockIdx.x >= njobs || threadIdx.x != 0) return;
+// Corner records of one corner table (element-parallel): everything the serial traversal needs about
+// a corner in 16 bytes -- {vertex id | on-boundary << 31, right corner, left corner, 0} -- so that its
+// hot loop is one shared-memory load plus bitmap tests, with no division, no table indirection.
+// Corner ids follow the edgebreaker strip order and the depth-first traversal mostly walks the same
+// strips (94-99 % of its moves go to an adjacent face id), hence a small sliding window suffices.
+// grid = (ceil(3*maxF/128), traversal jobs)
+__global__ void __launch_bounds__(128) k_corner_records(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, const uint8_t *Z, uint8_t *S2,
+                                                        const Job *jobs) {
+    const Job jb = jobs[blockIdx.y];
+    if (frame_dead(frames, counts, jb.frame)) return;
+    const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
+    if (f.o_d2c[t] == UVOL_NONE) return;
+    const int C = 3 * (int)f.nf, c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= C) return;
+    const TableView tv = make_view(f, t, S, Z);
+    const int *lmc = (const int *)(S + f.o_lmc);
+    int ob;
+    if (tv.ac2v) ob = tv.vos[tv.c2v_base[c]]; else ob = b_swl(tv.opp, lmc[tv.c2v_base[c]]) == DINV;
+    const uint32_t v = (uint32_t)t_vert(tv, c) | ((uint32_t)ob << 31);
+    ((uint4 *)(S2 + f.o_frec[t]))[c] = make_uint4(v, (uint32_t)t_opp(tv, cnext(c)), (uint32_t)t_opp(tv, cprev(c)), 0u);
+}
+
+// Depth-first traversal (A.3): one warp per (frame, table).  Lane 0 walks; visited faces / vertices are
+// shared-memory bitmaps, corner records come from a shared-memory window that the whole warp refills
+// on a miss, the split stack lives in shared memory (spilling to global).  what = table.
+#define TRAV_WIN 512          // corners in the window (8 KiB)
+#define TRAV_STACK 512
+__device__ __forceinline__ unsigned face_of(int c) { return __umulhi((unsigned)c, 0xAAAAAAABu) >> 1; }
+__global__ void __launch_bounds__(32) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, uint8_t *Z2,
+                                                 const Job *jobs, int njobs, int fwords_max, int vwords_max) {
+    extern __shared__ uint32_t sm[];
+    if ((int)blockIdx.x >= njobs) return;
     const Job jb = jobs[blockIdx.x];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
     if (f.o_d2c[t] == UVOL_NONE) return;
-    const TableView tv = make_view(f, t, S, Z);
-    const int maxe = (int)(t == 0 ? counts[jb.frame].num_vertex_slots : counts[jb.frame].attr_vertices[t - 1]);
-    uint32_t n = 0;
-    const int rc = traverse_table(tv, (const int *)(S + f.o_lmc), (int)f.nf, Z2 + f.o_fvis[t], (int *)(Z2 + f.o_v2d[t]), (int *)(S2 + f.o_d2c[t]),
-                                  (int *)(S2 + f.o_tstack[t]), maxe, &n);
-    counts[jb.frame].entries[t] = n;
-    if (rc) frame_fail(counts, jb.frame, rc);
+    const int F = (int)f.nf, C = 3 * F, lane = threadIdx.x;
+    uint32_t *fbits = sm, *vbits = sm + fwords_max; uint4 *win = (uint4 *)(sm + fwords_max + vwords_max); int *stk = (int *)(win + TRAV_WIN);
+    for (int i = lane; i < fwords_max + vwords_max; i += 32) sm[i] = 0;
+    const uint4 *grec = (const uint4 *)(S2 + f.o_frec[t]);
+    int *d2c = (int *)(S2 + f.o_d2c[t]), *v2d1 = (int *)(Z2 + f.o_v2d[t]), *gst = (int *)(S2 + f.o_tstack[t]);
+    int w0 = 0;
+    for (int i = lane; i < min(TRAV_WIN, C); i += 32) win[i] = grec[i];
+    __syncwarp();
+    int n = 0, sp = 0, c = 0, fscan = 0, need = 0, status = 0, done = 0;
+    bool resume_first = false;       // a component start is pending on corner c (its record was outside the window)
+    bool walking = false;            // c is a corner of an unvisited face to be processed
+    for (;;) {
+        if (lane == 0) {
+            for (;;) {
+                if (!walking && !resume_first) {
+                    // ---- pick the next corner: stack top, else next unvisited face in id order
+                    if (sp == 0) {
+                        int w = fscan >> 5; uint32_t m = ~fbits[w] & (0xffffffffu << (fscan & 31));
+                        while (m == 0 && w + 1 < fwords_max) { w++; m = ~fbits[w]; }
+                        const int nf = m ? w * 32 + __ffs(m) - 1 : F;
+                        if (nf >= F) { done = 1; break; }
+                        fscan = nf; c = 3 * nf; stk[0] = c; sp = 1; resume_first = true;
+                    } else {
+                        c = sp <= TRAV_STACK ? stk[sp - 1] : gst[sp - 1];
+                        if (c < 0) { sp--; continue; }
+                        const unsigned fc = face_of(c);
+                        if ((fbits[fc >> 5] >> (fc & 31)) & 1u) { sp--; continue; }
+                        walking = true;
+                    }
+                }
+                const unsigned ci = (unsigned)(c - w0);
+                if (ci >= TRAV_WIN) { need = c; break; }
+                if (resume_first) {
+                    // first face of a component: its next / previous vertices are visited first
+                    const int k = c - 3 * (int)face_of(c);
+                    const int cn = k == 2 ? c - 2 : c + 1, cp = k == 0 ? c + 2 : c - 1;
+                    const unsigned in = (unsigned)(cn - w0), ip = (unsigned)(cp - w0);
+                    if (in >= TRAV_WIN || ip >= TRAV_WIN) { need = 3 * (int)face_of(c) + 1; if ((unsigned)(need - w0 - 1) < TRAV_WIN - 2) { status = UVOL_ERR_CORRUPT; done = 1; } break; }
+                    const unsigned vn = win[in].x & 0x7fffffffu, vp = win[ip].x & 0x7fffffffu;
+                    if (!((vbits[vn >> 5] >> (vn & 31)) & 1u)) { vbits[vn >> 5] |= 1u << (vn & 31); v2d1[vn] = ++n; d2c[n - 1] = cn; }
+                    if (!((vbits[vp >> 5] >> (vp & 31)) & 1u)) { vbits[vp >> 5] |= 1u << (vp & 31); v2d1[vp] = ++n; d2c[n - 1] = cp; }
+                    resume_first = false; walking = true;
+                }
+                // ---- hot loop: one step per face
+                const uint4 R = win[ci];
+                const unsigned fc = face_of(c);
+                fbits[fc >> 5] |= 1u << (fc & 31);
+                const unsigned v = R.x & 0x7fffffffu, vw = vbits[v >> 5], vm = 1u << (v & 31);
+                if (!(vw & vm)) {
+                    vbits[v >> 5] = vw | vm; v2d1[v] = ++n; d2c[n - 1] = c;
+                    if ((int)R.x >= 0) { c = (int)R.y; continue; }       // interior vertex: go to the right face
+                }
+                const int rc = (int)R.y, lc = (int)R.z;
+                bool fr = rc < 0, fl = lc < 0;
+                if (!fr) { const unsigned rf = face_of(rc); fr = (fbits[rf >> 5] >> (rf & 31)) & 1u; }
+                if (!fl) { const unsigned lf = face_of(lc); fl = (fbits[lf >> 5] >> (lf & 31)) & 1u; }
+                if (fr) {
+                    if (fl) { sp--; walking = false; } else c = lc;
+                } else if (fl) c = rc;
+                else {      // both open: the left face waits on the stack, the right one is walked now
+                    if (sp <= TRAV_STACK) stk[sp - 1] = lc; else gst[sp - 1] = lc;
+                    if (sp < TRAV_STACK) stk[sp] = rc; else gst[sp] = rc;
+                    sp++; c = rc;
+                }
+            }
+        }
+        __syncwarp();
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done) break;
+        need = __shfl_sync(0xffffffffu, need, 0);
+        if (need < 0 || need >= C) { if (lane == 0) status = UVOL_ERR_CORRUPT; break; }
+        w0 = max(0, min(need - TRAV_WIN / 2, C - TRAV_WIN));
+        for (int i = lane; i < min(TRAV_WIN, C - w0); i += 32) win[i] = grec[(size_t)w0 + i];
+        __syncwarp();
+    }
+    if (lane == 0) {
+        counts[jb.frame].entries[t] = (uint32_t)n;
+        if (!status && (uint32_t)n != counts[jb.frame].expected[t]) status = UVOL_ERR_CORRUPT;    // the entropy runs were sized from `expected`
+        if (status) frame_fail(counts, jb.frame, status);
+    }
 }
 
 // Parallelogram parents, element-parallel.  grid = (ceil(maxN/128), frames, attrs)
@@ -335,10 +629,8 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
 
 }  // namespace
 
-static const char *kGeoStages[] = {"h2d", "rans_ctx", "rabs_seams", "edgebreaker", "seams", "attr_tables", "point_count", "counts_readback",
-                                   "point_assign", "traverse", "rans_attr", "rabs_aux", "parents", "predict_wrap", "uv_prepare", "predict_uv", "normals",
-                                   "expand", "d2h"};
-extern "C" const char *uvol_geo_stage_name(int i) { return (i >= 0 && i < 19) ? kGeoStages[i] : ""; }
+static const char *g_geo_stage_names[32] = {};
+extern "C" const char *uvol_geo_stage_name(int i) { return (i >= 0 && i < 32 && g_geo_stage_names[i]) ? g_geo_stage_names[i] : ""; }
 
 // Host-side state of the batch currently resident on the device (kept so that the device pipeline
 // can be re-run on HBM-resident inputs, uvol_replay_draco_batch).
@@ -346,7 +638,7 @@ struct GeoBatch {
     std::vector<DracoFrame> frames; std::vector<uint32_t> aux; std::vector<Job> jobs;
     int n = 0, j_ransA = 0, j_rabsA = 0, j_trav = 0, j_ransB = 0, j_rabsB = 0, j_wrap = 0, j_uv = 0, j_end = 0;
     uint32_t max_alpha_ctx = 1, max_alpha_attr = 1, maxnad = 0, maxV = 0, maxF = 0; int maxattr = 0;
-    uint64_t blob_bytes = 0, bytes_in = 0; DracoPlan pl; double parse_ms = 0;
+    uint64_t blob_bytes = 0, bytes_in = 0; DracoPlan pl; double parse_ms = 0; bool any_valence = false, any_standard = false;
 };
 void uvol_geo_batch_free(GeoBatch *b) { delete b; }
 
@@ -355,7 +647,7 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
     if (!ctx->geo) ctx->geo = new GeoBatch();
     GeoBatch &B = *ctx->geo;
     B.n = n; B.frames.assign((size_t)n, DracoFrame()); B.aux.clear(); B.aux.reserve((size_t)n * 2048); B.jobs.clear();
-    B.max_alpha_ctx = B.max_alpha_attr = 1; B.maxnad = B.maxV = B.maxF = 0; B.maxattr = 0; B.bytes_in = 0;
+    B.max_alpha_ctx = B.max_alpha_attr = 1; B.maxnad = B.maxV = B.maxF = 0; B.maxattr = 0; B.bytes_in = 0; B.any_valence = B.any_standard = false;
     std::vector<DracoFrame> &frames = B.frames; std::vector<uint32_t> &aux = B.aux;
     uint64_t blob_bytes = 0;
     for (int i = 0; i < n; i++) {
@@ -364,6 +656,7 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
         blob_bytes = align_up(blob_bytes + size[i] + 8, 16);
         f.status = (data[i] && size[i] < (1ull << 31)) ? uvol_draco_parse(data[i], size[i], f, aux) : UVOL_ERR_ARG;
         if (f.status) continue;
+        if (f.trav == 2) B.any_valence = true; else B.any_standard = true;
         for (int k = 0; k < 6; k++) if (f.ctx[k].count && f.ctx[k].alphabet > B.max_alpha_ctx) B.max_alpha_ctx = f.ctx[k].alphabet;
         for (int j = 0; j < f.nattr; j++) {
             if (f.attr[j].sym.alphabet > 49000) { f.status = UVOL_ERR_UNSUPPORTED; break; }
@@ -427,8 +720,8 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     GeoBatch &B = *ctx->geo; const int n = B.n;
     std::vector<DracoFrame> &frames = B.frames; DracoPlan &pl = B.pl;
     cudaStream_t st = ctx->s0;
-    int ev = 1;
-    auto stamp = [&]() { if (ctx->profile && ev < 32) cudaEventRecord(ctx->ev[ev++], st); };
+    int ev = 1, i_seams = -1, i_rans = -1, i_rabs = -1;
+    auto stamp = [&](const char *name) { if (ev < 32) g_geo_stage_names[ev - 1] = name; if (ctx->profile && ev < 32) cudaEventRecord(ctx->ev[ev], st); ev++; };
     if (!fresh_upload && ctx->profile) cudaEventRecord(ctx->ev[0], st);
     uint8_t *hd = (uint8_t *)ctx->h_desc.p;
     draco_plan_phase1(frames, pl);      // restores the phase-1 view of the descriptors (idempotent)
@@ -436,7 +729,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(DracoCounts) * (size_t)n, st));
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_zscratch.p, 0, pl.zscratch + 256, st));
-    stamp();
+    stamp("h2d");
     const DracoFrame *dF = (const DracoFrame *)ctx->d_desc.p; DracoCounts *dC = (DracoCounts *)ctx->d_counts.p;
     const uint8_t *dBlob = (const uint8_t *)ctx->d_blob.p; const uint32_t *dAux = (const uint32_t *)ctx->d_aux.p;
     uint8_t *dS = (uint8_t *)ctx->d_scratch.p, *dZ = (uint8_t *)ctx->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
@@ -447,25 +740,33 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         const size_t smMax = smA > smB ? smA : smB;
         if (smMax > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_rans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smMax));
     }
-    // ---- phase 1
+    // ---- phase 1.  The seam-bit runs depend only on the file bytes: they run on the side stream s1
+    // next to the context-symbol runs and the connectivity walk.
+    cudaStream_t sx = ctx->s1;
+    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[0], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->sync_ev[0], 0));
+    if (ctx->profile) cudaEventRecord(ctx->aux_ev[0], sx);
+    if (B.j_trav - B.j_rabsA > 0) { k_rabs<<<B.j_trav - B.j_rabsA, 32, 0, sx>>>(dF, dC, dBlob, dS, nullptr, dJ + B.j_rabsA, B.j_trav - B.j_rabsA); launches++; }
+    if (ctx->profile) cudaEventRecord(ctx->aux_ev[1], sx);
+    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[1], sx));
     if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<B.j_rabsA - B.j_ransA, 32, rans_smem(B.max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + B.j_ransA, B.j_rabsA - B.j_ransA); launches++; }
-    stamp();
-    if (B.j_trav - B.j_rabsA > 0) { k_rabs<<<B.j_trav - B.j_rabsA, 32, 0, st>>>(dF, dC, dBlob, dS, nullptr, dJ + B.j_rabsA, B.j_trav - B.j_rabsA); launches++; }
-    stamp();
-    k_edgebreaker<<<n, 32, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++;
-    stamp();
+    stamp("rans_ctx");
+    stamp("rabs_seams(s1)"); i_seams = ev - 2;                                     // (stage slot of rabs_seams: timed on s1, filled in below)
+    if (B.any_valence) { k_edgebreaker_valence<<<n, 32, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
+    if (B.any_standard) { k_edgebreaker<<<n, 32, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
+    stamp("edgebreaker");
+    UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[1], 0));
     k_seams<<<n, 256, 0, st>>>(dF, dC, dS, dZ, n); launches++;
-    stamp();
+    stamp("seams");
     const unsigned gv = (B.maxV + 127) / 128 > 0 ? (B.maxV + 127) / 128 : 1;
     if (B.maxnad) {
         k_attr_fan<0><<<dim3(gv, n, B.maxnad), 128, 0, st>>>(dF, dC, dS, dZ); launches++;
         k_scan<<<dim3(n, B.maxnad), 1024, 0, st>>>(dF, dC, dS, 0); launches++;
         k_attr_fan<1><<<dim3(gv, n, B.maxnad), 128, 0, st>>>(dF, dC, dS, dZ); launches++;
     }
-    stamp();
+    stamp("attr_tables");
     k_point_fan<0><<<dim3(gv, n), 128, 0, st>>>(dF, dC, dS, dZ, nullptr, nullptr); launches++;
     k_scan<<<dim3(n, 1), 1024, 0, st>>>(dF, dC, dS, 4); launches++;
-    stamp();
+    stamp("point_count");
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));
     const DracoCounts *hC = (const DracoCounts *)ctx->h_counts.p;
@@ -476,7 +777,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_zscratch2.p, 0, pl.zscratch2 + 256, st));
-    stamp();
+    stamp("counts_readback");
     uint8_t *dS2 = (uint8_t *)ctx->d_scratch2.p, *dZ2 = (uint8_t *)ctx->d_zscratch2.p, *dO = (uint8_t *)ctx->d_out_geo.p;
     uint32_t maxP = 1, maxN = 1;
     for (int i = 0; i < n; i++) if (!frames[i].status && !hC[i].status) {
@@ -484,34 +785,49 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         if (hC[i].num_vertex_slots > maxN) maxN = hC[i].num_vertex_slots;
         for (uint32_t k = 0; k < frames[i].nad; k++) if (hC[i].attr_vertices[k] > maxN) maxN = hC[i].attr_vertices[k];
     }
-    // ---- phase 2
+    // ---- phase 2.  Attribute entropy runs (sized from counts.expected) go to s1 and overlap the traversals.
+    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[2], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->sync_ev[2], 0));
+    if (ctx->profile) cudaEventRecord(ctx->aux_ev[2], sx);
+    if (B.j_rabsB - B.j_ransB > 0) { k_rans<<<B.j_rabsB - B.j_ransB, 32, rans_smem(B.max_alpha_attr), sx>>>(dF, dC, dBlob, dAux, dS, dS2, dJ + B.j_ransB, B.j_rabsB - B.j_ransB); launches++; }
+    if (ctx->profile) cudaEventRecord(ctx->aux_ev[3], sx);
+    if (B.j_wrap - B.j_rabsB > 0) { k_rabs<<<B.j_wrap - B.j_rabsB, 32, 0, sx>>>(dF, dC, dBlob, dS, dS2, dJ + B.j_rabsB, B.j_wrap - B.j_rabsB); launches++; }
+    if (ctx->profile) cudaEventRecord(ctx->aux_ev[4], sx);
+    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[3], sx));
     k_point_fan<1><<<dim3(gv, n), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dO); launches++;
-    stamp();
-    if (B.j_ransB - B.j_trav > 0) { k_traverse<<<B.j_ransB - B.j_trav, 32, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2, dJ + B.j_trav, B.j_ransB - B.j_trav); launches++; }
-    stamp();
-    if (B.j_rabsB - B.j_ransB > 0) { k_rans<<<B.j_rabsB - B.j_ransB, 32, rans_smem(B.max_alpha_attr), st>>>(dF, dC, dBlob, dAux, dS, dS2, dJ + B.j_ransB, B.j_rabsB - B.j_ransB); launches++; }
-    stamp();
-    if (B.j_wrap - B.j_rabsB > 0) { k_rabs<<<B.j_wrap - B.j_rabsB, 32, 0, st>>>(dF, dC, dBlob, dS, dS2, dJ + B.j_rabsB, B.j_wrap - B.j_rabsB); launches++; }
-    stamp();
+    stamp("point_assign");
+    if (B.j_ransB - B.j_trav > 0) {
+        const int ntj = B.j_ransB - B.j_trav;
+        k_corner_records<<<dim3((3 * B.maxF + 127) / 128, ntj), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dJ + B.j_trav); launches++;
+        stamp("corner_records");
+        const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((maxN + 31) / 32 + 4) & ~3u);   // multiples of 4 words: the window stays 16 B aligned
+        const size_t smem = (size_t)(fwords + vwords) * 4 + TRAV_WIN * 16 + TRAV_STACK * 4;
+        if (smem > 200 * 1024) { ctx->err = "mesh too large for the traversal bitmaps"; return UVOL_ERR_UNSUPPORTED; }
+        if (smem > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_traverse<<<ntj, 32, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords); launches++;
+    }
+    stamp("traverse");
+    UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[3], 0));
+    stamp("rans_attr(s1)"); i_rans = ev - 2;                                     // (stage slots of rans_attr / rabs_aux: timed on s1)
+    stamp("rabs_aux(s1)"); i_rabs = ev - 2;
     const unsigned gn = (maxN + 127) / 128;
     k_parents<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
-    stamp();
+    stamp("parents");
     if (B.j_uv - B.j_wrap > 0) { k_predict_wrap<<<B.j_uv - B.j_wrap, 32, 0, st>>>(dF, dC, dS2, dJ + B.j_wrap, B.j_uv - B.j_wrap); launches++; }
-    stamp();
+    stamp("predict_wrap");
     k_uv_prepare<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
-    stamp();
+    stamp("uv_prepare");
     if (B.j_end - B.j_uv > 0) { k_predict_uv<<<B.j_end - B.j_uv, 32, 0, st>>>(dF, dC, dS2, dJ + B.j_uv, B.j_end - B.j_uv); launches++; }
-    stamp();
+    stamp("predict_uv");
     k_normals<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
-    stamp();
+    stamp("normals");
     k_expand<<<dim3((maxP + 255) / 256, n, B.maxattr), 256, 0, st>>>(dF, dC, dS, dS2, dZ2, dO); launches++;
-    stamp();
+    stamp("expand");
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (memory == UVOL_MEM_HOST) {
         UVOL_CUDA(ctx, ctx->h_out.reserve(pl.out + 256));
         UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.p, dO, pl.out, cudaMemcpyDeviceToHost, st));
     }
-    stamp();
+    stamp("d2h");
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));
     UVOL_CUDA(ctx, cudaGetLastError());
     // ---- results
@@ -538,6 +854,10 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         for (int k = 0; k + 1 < ev && k < 24; k++) cudaEventElapsedTime(&s.stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);
         float tot = 0; cudaEventElapsedTime(&tot, ctx->ev[1], ctx->ev[ev - 2]); s.device_ms = tot;   // kernels only: after h2d, before d2h
         s.h2d_ms = s.stage_ms[0]; s.d2h_ms = s.stage_ms[ev - 2];
+        // stages that ran on the side stream (overlapped with the main stream): their own event pairs
+        if (i_seams >= 0 && i_seams < 24) cudaEventElapsedTime(&s.stage_ms[i_seams], ctx->aux_ev[0], ctx->aux_ev[1]);
+        if (i_rans >= 0 && i_rans < 24) cudaEventElapsedTime(&s.stage_ms[i_rans], ctx->aux_ev[2], ctx->aux_ev[3]);
+        if (i_rabs >= 0 && i_rabs < 24) cudaEventElapsedTime(&s.stage_ms[i_rabs], ctx->aux_ev[3], ctx->aux_ev[4]);
     }
     return UVOL_OK;
 }
@@ -563,5 +883,14 @@ extern "C" int uvol_replay_draco_batch(uvol_ctx *ctx, int memory, uvol_geometry 
     const double t0 = now_ms();
     const int rc = draco_run(ctx, memory, out, false); if (rc) return rc;
     ctx->stats.total_ms = now_ms() - t0;
+    return UVOL_OK;
+}
+
+// used by the combined V2 entry point (basis_transcode.cu)
+int uvol_geo_prepare_and_run(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int memory, uvol_geometry *out, bool replay) {
+    if (replay) { if (!ctx->geo || ctx->geo->n != n) return UVOL_ERR_ARG; return draco_run(ctx, memory, out, false); }
+    int rc = draco_prepare(ctx, data, size, n); if (rc) return rc;
+    rc = draco_run(ctx, memory, out, true); if (rc) return rc;
+    ctx->stats.host_parse_ms = ctx->geo->parse_ms;
     return UVOL_OK;
 }

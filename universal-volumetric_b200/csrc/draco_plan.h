@@ -19,7 +19,7 @@ static inline void draco_plan_phase1(std::vector<DracoFrame> &frames, DracoPlan 
         if (f.status) continue;
         const uint64_t F = f.nf, C = 3 * F, maxv = (uint64_t)f.nv_enc + f.nsplit + 4;
         f.o_opp = plan_take(s, C * 4); f.o_c2v = plan_take(s, C * 4);
-        f.o_lmc = plan_take(s, maxv * 4); f.o_val = plan_take(s, maxv * 4); f.o_hole = plan_take(s, maxv);
+        f.o_lmc = plan_take(s, maxv * 4); f.o_val = plan_take(s, maxv * 16); f.o_hole = plan_take(s, maxv);   // o_val: int valences (generic path) or 16 B vertex records (valence path)
         f.o_stack = plan_take(s, ((uint64_t)f.nsym + 8) * 4 + ((uint64_t)f.nts + 1) * 8);
         f.o_invalid = plan_take(s, ((uint64_t)f.nsplit + 8) * 4);
         for (int i = 0; i < 6; i++) f.o_ctxsym[i] = plan_take(s, (uint64_t)f.ctx[i].count + 4);
@@ -47,10 +47,11 @@ static inline void draco_plan_phase2(std::vector<DracoFrame> &frames, const Drac
         bool need[UVOL_MAX_ATTR_DATA + 1] = {true, false, false, false, false};
         for (int j = 0; j < f.nattr; j++) if (f.attr[j].out_slot >= 0 || j == f.pos_attr) need[f.attr[j].table + 1] = true;
         for (uint32_t t = 0; t <= f.nad; t++) {
-            if (!need[t]) { f.o_d2c[t] = f.o_v2d[t] = f.o_fvis[t] = f.o_tstack[t] = UVOL_NONE; continue; }
+            if (!need[t]) { f.o_d2c[t] = f.o_v2d[t] = f.o_frec[t] = f.o_tstack[t] = UVOL_NONE; continue; }
             const uint64_t nv = (t == 0 ? c.num_vertex_slots : c.attr_vertices[t - 1]) + 4;
             f.o_d2c[t] = plan_take(s, nv * 4); f.o_tstack[t] = plan_take(s, (F + 8) * 4);
-            f.o_v2d[t] = plan_take(z, nv * 4); f.o_fvis[t] = plan_take(z, F + 4);
+            f.o_frec[t] = plan_take(s, (3 * F + 4) * 16);      // per-corner traversal records
+            f.o_v2d[t] = plan_take(z, nv * 4);
         }
         for (int j = 0; j < f.nattr; j++) {
             const DracoAttr &a = f.attr[j];

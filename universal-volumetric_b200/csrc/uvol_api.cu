@@ -17,7 +17,11 @@ extern "C" int uvol_create(int device, uvol_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->s0, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->s1, cudaStreamNonBlocking) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    for (auto &e : c->aux_ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    for (auto &e : c->tex_ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    for (auto &e : c->sync_ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     *out = c;
     return UVOL_OK;
 }
@@ -37,6 +41,10 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     if (c->tex) uvol_tex_batch_free(c->tex);
     if (c->corto) uvol_corto_batch_free(c->corto);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->aux_ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->tex_ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->sync_ev) if (e) cudaEventDestroy(e);
+    if (c->s2) cudaStreamDestroy(c->s2);
     if (c->s0) cudaStreamDestroy(c->s0);
     if (c->s1) cudaStreamDestroy(c->s1);
     delete c;

@@ -44,7 +44,8 @@ struct uvol_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t s0 = nullptr, s1 = nullptr;
-    cudaEvent_t ev[32] = {};
+    cudaEvent_t ev[32] = {}, aux_ev[8] = {}, tex_ev[8] = {}, sync_ev[8] = {};
+    cudaStream_t s2 = nullptr;
     std::string err;
     // geometry path
     PinBuf h_blob, h_desc, h_aux, h_counts, h_out;
@@ -59,7 +60,7 @@ struct uvol_ctx {
     GeoBatch *geo = nullptr; TexBatch *tex = nullptr; CortoBatch *corto = nullptr;
     DevBuf d_flush;
     // stats of the last batch
-    uvol_stats stats = {};
+    uvol_stats stats = {}, stats_tex = {};
     bool profile = false;
 };
 

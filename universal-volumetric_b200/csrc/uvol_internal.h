@@ -54,11 +54,15 @@ struct DracoFrame {
     uint64_t o_seambits[UVOL_MAX_ATTR_DATA], o_eos[UVOL_MAX_ATTR_DATA], o_vos[UVOL_MAX_ATTR_DATA], o_ac2v[UVOL_MAX_ATTR_DATA],
              o_afirst[UVOL_MAX_ATTR_DATA], o_acnt[UVOL_MAX_ATTR_DATA];
     uint64_t o_pcnt, o_pfirst, o_p2c;      // per-vertex point counts/offsets, dedup start corner, point -> corner
-    uint64_t o_d2c[UVOL_MAX_ATTR_DATA + 1], o_v2d[UVOL_MAX_ATTR_DATA + 1], o_fvis[UVOL_MAX_ATTR_DATA + 1], o_tstack[UVOL_MAX_ATTR_DATA + 1];
+    uint64_t o_d2c[UVOL_MAX_ATTR_DATA + 1], o_v2d[UVOL_MAX_ATTR_DATA + 1], o_frec[UVOL_MAX_ATTR_DATA + 1], o_tstack[UVOL_MAX_ATTR_DATA + 1];
     uint64_t o_corr[UVOL_MAX_ATTRS], o_val_attr[UVOL_MAX_ATTRS], o_par[UVOL_MAX_ATTRS], o_auxbits[UVOL_MAX_ATTRS];
     // ---- outputs (device pointers as byte offsets into the output arena; filled after counts are known)
     uint64_t out_index, out_attr[4];
 };
+
+// Per-face record of one corner table (base or attribute), built element-parallel and consumed by
+// the serial traversal through a shared-memory window: 32 bytes per face.
+struct FaceRec { int32_t v[3]; int32_t o[3]; int32_t flags; int32_t pad; };   // vertex ids, opposite corners (-1: boundary/seam), bit k: vertex k on boundary
 
 // per-frame state written by the kernels (counts the host reads back once per batch)
 struct DracoCounts {
@@ -66,7 +70,8 @@ struct DracoCounts {
     uint32_t num_vertex_slots;    // V (incl. isolated tail)
     uint32_t num_points;
     uint32_t attr_vertices[UVOL_MAX_ATTR_DATA];
-    uint32_t entries[UVOL_MAX_ATTR_DATA + 1];   // per traversal table: [0] base, [1+i] attribute data i
+    uint32_t entries[UVOL_MAX_ATTR_DATA + 1];   // per traversal table: [0] base, [1+i] attribute data i (written by the traversal)
+    uint32_t expected[UVOL_MAX_ATTR_DATA + 1];  // entry counts known after phase 1 (valid vertices / attribute vertices)
     uint32_t dbg[4];
 };
 

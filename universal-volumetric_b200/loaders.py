@@ -55,9 +55,13 @@ class Context:
     def last_error(self):
         return self._L.uvol_last_error(self._h).decode()
 
-    def stats(self, kind=0):
+    def stats(self, kind=0, combined=False):
+        """Statistics of the last call; with combined=True those of the last V2 step (kind 0 geometry, 1 texture)."""
         s = N.Stats()
-        self._L.uvol_get_stats(self._h, ctypes.byref(s))
+        if combined:
+            self._L.uvol_get_stats_kind(self._h, kind, ctypes.byref(s))
+        else:
+            self._L.uvol_get_stats(self._h, ctypes.byref(s))
         d = {k: getattr(s, k) for k in ("host_parse_ms", "h2d_ms", "device_ms", "d2h_ms", "total_ms", "kernel_launches", "bytes_in",
                                         "bytes_out", "scratch_bytes")}
         d["stages"] = {self._L.uvol_stage_name(kind, i).decode(): float(s.stage_ms[i]) for i in range(s.num_stages)}
@@ -154,3 +158,29 @@ class KTX2Loader:
             res.append({"status": 0, "width": int(t.width), "height": int(t.height), "layers": int(t.layers), "hasAlpha": bool(t.has_alpha),
                         "format": "RGBAFormat", "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data})
         return res
+
+
+class V2Player:
+    """Batch mirror of the decode side of the reference's V2 player (src/V2/player.ts): one step hands a
+    range of geometry frames and texture segments to the library, which decodes both kinds concurrently
+    (the reference issues decodeDraco / decodeKTX2 promises to two worker pools, :272-323, and stores
+    the results in meshMap / textureMap keyed by frame / segment number, :325-331,359-366)."""
+
+    def __init__(self, ctx=None, device=0):
+        self.ctx = ctx or Context(device)
+
+    def decode_step_raw(self, drc_files, ktx2_files, memory=N.MEM_HOST):
+        kd, pd, sd = _pack(drc_files); kk, pk, sk = _pack(ktx2_files)
+        og = (N.Geometry * max(1, len(drc_files)))(); ot = (N.Texture * max(1, len(ktx2_files)))()
+        rc = self.ctx._L.uvol_decode_v2_batch(self.ctx._h, pd, sd, len(drc_files), pk, sk, len(ktx2_files), memory, og, ot)
+        if rc != 0:
+            raise N.UvolError(f"uvol_decode_v2_batch failed ({rc}): {self.ctx.last_error()}")
+        self._keep = (kd, kk)
+        return og, ot
+
+    def replay_step_raw(self, n_drc, n_ktx2, memory=N.MEM_DEVICE):
+        og = (N.Geometry * max(1, n_drc))(); ot = (N.Texture * max(1, n_ktx2))()
+        rc = self.ctx._L.uvol_replay_v2_batch(self.ctx._h, memory, og, n_drc, ot, n_ktx2)
+        if rc != 0:
+            raise N.UvolError(f"uvol_replay_v2_batch failed ({rc}): {self.ctx.last_error()}")
+        return og, ot
