@@ -21,9 +21,10 @@ namespace {
 
 struct TexState { int32_t status; uint32_t hist_size; };
 
-__global__ void __launch_bounds__(32) k_basis_globals(const Ktx2File *files, TexState *state, const uint8_t *blob, uint8_t *S, int nfiles) {
-    const uint32_t fi = blockIdx.x;
-    if ((int)fi >= nfiles || threadIdx.x != 0) return;
+#define SERIAL_WARPS 4        // one unit per warp, four warps per block: spreads the serial walkers over the SM's four schedulers
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_basis_globals(const Ktx2File *files, TexState *state, const uint8_t *blob, uint8_t *S, int nfiles) {
+    const uint32_t fi = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+    if ((int)fi >= nfiles || (threadIdx.x & 31) != 0) return;
     const Ktx2File &f = files[fi];
     if (f.status) { state[fi].status = f.status; return; }
     if (f.is_uastc) return;
@@ -37,21 +38,22 @@ __global__ void __launch_bounds__(32) k_basis_globals(const Ktx2File *files, Tex
     if (rc) state[fi].status = rc;
 }
 
-__global__ void __launch_bounds__(32) k_etc1s_slices(const Ktx2File *files, TexState *state, const Ktx2Slice *slices, const uint8_t *blob, uint8_t *S, int nslices) {
-    __shared__ HuffTable tabs[4];
-    __shared__ uint8_t rowp[4096];
-    __shared__ uint16_t hist[1024];
-    const uint32_t si = blockIdx.x;
+#define SLICE_SMEM_BYTES (4 * sizeof(HuffTable) + 4096 + 2048)
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_etc1s_slices(const Ktx2File *files, TexState *state, const Ktx2Slice *slices, const uint8_t *blob, uint8_t *S, int nslices) {
+    extern __shared__ uint4 slice_smem[];
+    uint8_t *my = (uint8_t *)slice_smem + (size_t)(threadIdx.x >> 5) * SLICE_SMEM_BYTES;
+    HuffTable *tabs = (HuffTable *)my; uint8_t *rowp = my + 4 * sizeof(HuffTable); uint16_t *hist = (uint16_t *)(rowp + 4096);
+    const uint32_t si = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if ((int)si >= nslices) return;
     const Ktx2Slice &sl = slices[si]; const Ktx2File &f = files[sl.file];
     if (f.status || state[sl.file].status) return;
     const HuffTable *gt = (const HuffTable *)(S + f.o_huff);
     {   // stage the four slice tables in shared memory (word copy by the whole warp)
         const uint32_t *src = (const uint32_t *)gt; uint32_t *dst = (uint32_t *)tabs;
-        for (uint32_t i = threadIdx.x; i < 4 * sizeof(HuffTable) / 4; i += 32) dst[i] = src[i];
+        for (uint32_t i = threadIdx.x & 31; i < 4 * sizeof(HuffTable) / 4; i += 32) dst[i] = src[i];
     }
     __syncwarp();
-    if (threadIdx.x != 0) return;
+    if ((threadIdx.x & 31) != 0) return;
     BitRd b; br_init(b, blob + f.file_off + sl.data_off);
     SliceTables T{&tabs[0], &tabs[1], &tabs[2], &tabs[3], (const uint16_t *)(S + f.o_sorted)};
     const int rc = etc1s_slice_symbols(b, T, f.bx, f.by, f.selector_count, state[sl.file].hist_size, (int)f.is_video, rowp, hist,
@@ -61,8 +63,8 @@ __global__ void __launch_bounds__(32) k_etc1s_slices(const Ktx2File *files, TexS
 }
 
 // Endpoint prediction reversal.  One warp per (file, plane); layers and rows in order, 32 blocks per step.
-__global__ void __launch_bounds__(32) k_etc1s_resolve(const Ktx2File *files, TexState *state, const Ktx2Slice *slices, uint8_t *S, int nfiles) {
-    const uint32_t fi = blockIdx.x, plane = blockIdx.y, lane = threadIdx.x;
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_etc1s_resolve(const Ktx2File *files, TexState *state, const Ktx2Slice *slices, uint8_t *S, int nfiles) {
+    const uint32_t fi = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5), plane = blockIdx.y, lane = threadIdx.x & 31;
     if ((int)fi >= nfiles) return;
     const Ktx2File &f = files[fi];
     if (f.status || state[fi].status || f.is_uastc) return;
@@ -226,11 +228,15 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
     TexState *dSt = (TexState *)ctx->d_tslices.p; const uint8_t *dBlob = (const uint8_t *)ctx->d_tblob.p;
     uint8_t *dS = (uint8_t *)ctx->d_tscratch.p, *dO = (uint8_t *)ctx->d_out_tex.p;
     uint32_t launches = 0;
-    k_basis_globals<<<n, 32, 0, st>>>(dF, dSt, dBlob, dS, n); launches++;
+    const unsigned nb4 = (unsigned)((n + SERIAL_WARPS - 1) / SERIAL_WARPS);
+    k_basis_globals<<<nb4, 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dBlob, dS, n); launches++;
     stamp();
-    if (nsl) { k_etc1s_slices<<<(unsigned)nsl, 32, 0, st>>>(dF, dSt, dSl, dBlob, dS, (int)nsl); launches++; }
+    if (nsl) {
+        cudaFuncSetAttribute(k_etc1s_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SLICE_SMEM_BYTES * SERIAL_WARPS));
+        k_etc1s_slices<<<(unsigned)((nsl + SERIAL_WARPS - 1) / SERIAL_WARPS), 32 * SERIAL_WARPS, SLICE_SMEM_BYTES * SERIAL_WARPS, st>>>(dF, dSt, dSl, dBlob, dS, (int)nsl); launches++;
+    }
     stamp();
-    if (nsl) { k_etc1s_resolve<<<dim3(n, B.any_alpha ? 2 : 1), 32, 0, st>>>(dF, dSt, dSl, dS, n); launches++; }
+    if (nsl) { k_etc1s_resolve<<<dim3(nb4, B.any_alpha ? 2 : 1), 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dSl, dS, n); launches++; }
     stamp();
     if (nll) { k_etc1s_blocks<<<dim3((B.max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO); launches++; }
     if (nul) { uvol_uastc_launch(dF, (const int32_t *)dSt, dBlob, dO, dUL, (int)nul, B.max_blocks, st); launches++; }

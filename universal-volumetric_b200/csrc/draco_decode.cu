@@ -11,6 +11,7 @@
 // entries / points of all frames.  No tensor-core work exists on this path (HBM / latency bound).
 #include <chrono>
 #include <string.h>
+#include <stdlib.h>
 #include "uvol_ctx.h"
 #include "draco_core.h"
 #include "draco_plan.h"
@@ -18,6 +19,7 @@
 namespace {
 
 struct Job { uint32_t frame; int32_t what; };
+struct UvPrepD { int32_t nd, pd; long long pn2, dot, ns; double rcp; };      // UvPrep + reciprocal of |PN|^2 (40 bytes)
 
 __device__ __forceinline__ bool frame_dead(const DracoFrame *frames, const DracoCounts *counts, uint32_t f) {
     return frames[f].status != 0 || counts[f].status != 0;
@@ -29,11 +31,16 @@ __device__ __forceinline__ void frame_fail(DracoCounts *counts, uint32_t f, int 
 // first-symbol index in shared memory, then lane 0 walks the run (strictly serial state chain).
 // what: 0..5 = valence context i (u8 out) ; 16+j = attribute j (int32 out, zig-zag unless the
 // transform yields positive corrections).
-__global__ void __launch_bounds__(32) k_rans(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
-                                             uint8_t *scratch, uint8_t *scratch2, const Job *jobs, int njobs) {
-    extern __shared__ uint32_t smem[];
-    if ((int)blockIdx.x >= njobs) return;
-    const Job jb = jobs[blockIdx.x];
+// All serial kernels use SERIAL_WARPS warps per block, one unit of work per warp: single-warp blocks
+// would all be scheduled on the same SM sub-partition (warp id % 4) and contend for one issue port.
+#define SERIAL_WARPS 4
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
+                                             uint8_t *scratch, uint8_t *scratch2, const Job *jobs, int njobs, int smem_words_per_warp) {
+    extern __shared__ uint32_t smem_all[];
+    const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+    if (ji >= njobs) return;
+    uint32_t *smem = smem_all + (size_t)(threadIdx.x >> 5) * smem_words_per_warp;
+    const Job jb = jobs[ji];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame];
     const uint8_t *file = blob + f.file_off;
@@ -45,7 +52,7 @@ __global__ void __launch_bounds__(32) k_rans(const DracoFrame *frames, DracoCoun
         mode = (a.pred != -2 && (a.xform == 2 || a.xform == 3)) ? 2 : 1;
         count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
     }
-    const uint32_t A = s.alphabet, lane = threadIdx.x;
+    const uint32_t A = s.alphabet, lane = threadIdx.x & 31;
     uint32_t *cum = smem; uint16_t *bucket = (uint16_t *)(smem + A + 1);
     const uint32_t *prob = aux + s.prob_off;
     uint32_t run = 0;
@@ -72,10 +79,11 @@ __global__ void __launch_bounds__(32) k_rans(const DracoFrame *frames, DracoCoun
 // rABS bit runs: one warp per run (lane 0 walks).  what: 0..3 = seam bits of attribute data i
 // (upper bound 3F/2+1 bits); 16+j = attribute j aux bits (TEX_COORDS orientations incl. the
 // toggle decoding, or GEOMETRIC_NORMAL flip bits).
-__global__ void __launch_bounds__(32) k_rabs(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob,
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rabs(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob,
                                              uint8_t *scratch, uint8_t *scratch2, const Job *jobs, int njobs) {
-    if ((int)blockIdx.x >= njobs || threadIdx.x != 0) return;
-    const Job jb = jobs[blockIdx.x];
+    const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+    if (ji >= njobs || (threadIdx.x & 31) != 0) return;
+    const Job jb = jobs[ji];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame];
     const uint8_t *file = blob + f.file_off;
@@ -98,10 +106,10 @@ __global__ void __launch_bounds__(32) k_rabs(const DracoFrame *frames, DracoCoun
 }
 
 // Edgebreaker connectivity: one warp per frame, lane 0 walks the symbol sequence.
-__global__ void __launch_bounds__(32) k_edgebreaker(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
                                                     uint8_t *S, int nframes) {
-    const uint32_t fi = blockIdx.x;
-    if ((int)fi >= nframes || threadIdx.x != 0) return;
+    const uint32_t fi = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+    if ((int)fi >= nframes || (threadIdx.x & 31) != 0) return;
     if (frames[fi].status) { counts[fi].status = frames[fi].status; return; }
     if (counts[fi].status || frames[fi].trav == 2) return;      // valence frames: k_edgebreaker_valence
     const DracoFrame &f = frames[fi];
@@ -131,16 +139,17 @@ struct VRec { int lmc, lpv, val, hole; };
 __device__ __forceinline__ VRec vr_unpack(uint4 u) { VRec r; r.lmc = (int)u.x; r.lpv = (int)u.y; r.val = (int)u.z; r.hole = (int)u.w; return r; }
 __device__ __forceinline__ uint4 vr_pack(const VRec &r) { return make_uint4((uint32_t)r.lmc, (uint32_t)r.lpv, (uint32_t)r.val, (uint32_t)r.hole); }
 
-__global__ void __launch_bounds__(32) k_edgebreaker_valence(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
                                                             uint8_t *S, int nframes) {
-    __shared__ uint4 ring[EB_RING];
-    __shared__ int stk[512];
-    const uint32_t fi = blockIdx.x;
+    extern __shared__ uint4 eb_smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4 *ring = eb_smem + (size_t)wib * (EB_RING + 128);
+    int *stk = (int *)(ring + EB_RING);
+    const uint32_t fi = blockIdx.x * SERIAL_WARPS + wib;
     if ((int)fi >= nframes) return;
-    if (frames[fi].status) { if (threadIdx.x == 0) counts[fi].status = frames[fi].status; return; }
+    if (frames[fi].status) { if (lane == 0) counts[fi].status = frames[fi].status; return; }
     if (counts[fi].status || frames[fi].trav != 2) return;
     const DracoFrame &f = frames[fi];
-    const int lane = threadIdx.x;
     int *opp = (int *)(S + f.o_opp), *c2v = (int *)(S + f.o_c2v), *lmc = (int *)(S + f.o_lmc), *gstk = (int *)(S + f.o_stack);
     uint8_t *hole = S + f.o_hole; uint4 *vrec = (uint4 *)(S + f.o_val);     // o_val is sized 16 B per vertex slot (see draco_plan.h)
     int *skey = gstk + f.nsym + 8, *sval = skey + f.nts + 1, *invalid = (int *)(S + f.o_invalid);
@@ -453,18 +462,20 @@ __global__ void __launch_bounds__(128) k_corner_records(const DracoFrame *frames
 // Depth-first traversal (A.3): one warp per (frame, table).  Lane 0 walks; visited faces / vertices are
 // shared-memory bitmaps, corner records come from a shared-memory window that the whole warp refills
 // on a miss, the split stack lives in shared memory (spilling to global).  what = table.
-#define TRAV_WIN 512          // corners in the window (8 KiB)
+#define TRAV_WIN 256          // corners in the window (4 KiB)
 #define TRAV_STACK 512
 __device__ __forceinline__ unsigned face_of(int c) { return __umulhi((unsigned)c, 0xAAAAAAABu) >> 1; }
-__global__ void __launch_bounds__(32) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, uint8_t *Z2,
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, uint8_t *Z2,
                                                  const Job *jobs, int njobs, int fwords_max, int vwords_max) {
-    extern __shared__ uint32_t sm[];
-    if ((int)blockIdx.x >= njobs) return;
-    const Job jb = jobs[blockIdx.x];
+    extern __shared__ uint32_t sm_all[];
+    const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+    if (ji >= njobs) return;
+    uint32_t *sm = sm_all + (size_t)(threadIdx.x >> 5) * (fwords_max + vwords_max + TRAV_WIN * 4 + TRAV_STACK);
+    const Job jb = jobs[ji];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
     if (f.o_d2c[t] == UVOL_NONE) return;
-    const int F = (int)f.nf, C = 3 * F, lane = threadIdx.x;
+    const int F = (int)f.nf, C = 3 * F, lane = threadIdx.x & 31;
     uint32_t *fbits = sm, *vbits = sm + fwords_max; uint4 *win = (uint4 *)(sm + fwords_max + vwords_max); int *stk = (int *)(win + TRAV_WIN);
     for (int i = lane; i < fwords_max + vwords_max; i += 32) sm[i] = 0;
     const uint4 *grec = (const uint4 *)(S2 + f.o_frec[t]);
@@ -547,29 +558,107 @@ __global__ void __launch_bounds__(32) k_traverse(const DracoFrame *frames, Draco
 }
 
 // Parallelogram parents, element-parallel.  grid = (ceil(maxN/128), frames, attrs)
+// par4 = {opp entry, next entry, prev entry, kind}.  kind 1 ("scan-able"): the prediction is
+// x[p-1] + (x[far1] - x[far2]) with both far parents at least 32 entries back -- then a run of such
+// entries is a prefix sum (see k_predict_wrap); par4 is rewritten as {far1, far2, -, 1} (far = -1: term absent).
 __global__ void __launch_bounds__(128) k_parents(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, const uint8_t *Z, uint8_t *S2, const uint8_t *Z2) {
     const uint32_t fi = blockIdx.y, j = blockIdx.z;
     if (frame_dead(frames, counts, fi)) return;
     const DracoFrame &f = frames[fi];
-    if ((int)j >= f.nattr || f.o_corr[j] == UVOL_NONE || f.attr[j].pred != 1) return;
+    if ((int)j >= f.nattr || f.o_corr[j] == UVOL_NONE || (f.attr[j].pred != 1 && f.attr[j].pred != 0)) return;
     const int t = f.attr[j].table + 1, n = (int)counts[fi].entries[t], p = blockIdx.x * 128 + threadIdx.x;
     if (p >= n) return;
-    const TableView tv = make_view(f, t, S, Z);
-    parallelogram_parents(p, tv, (const int *)(S2 + f.o_d2c[t]), (const int *)(Z2 + f.o_v2d[t]), (int *)(S2 + f.o_par[j]) + 4 * p);
+    int par[4] = {-1, -1, -1, 0};
+    if (f.attr[j].pred == 1) {
+        const TableView tv = make_view(f, t, S, Z);
+        parallelogram_parents(p, tv, (const int *)(S2 + f.o_d2c[t]), (const int *)(Z2 + f.o_v2d[t]), par);
+    }
+    int4 out = make_int4(par[0], par[1], par[2], 0);
+    if (p > 0) {
+        if (par[0] < 0) out = make_int4(-1, -1, -1, 1);                                              // delta coding: x[p-1] + corr
+        else if (par[2] == p - 1 && par[0] <= p - 32 && par[1] <= p - 32) out = make_int4(par[1], par[0], -1, 1);   // + next - opp
+        else if (par[1] == p - 1 && par[0] <= p - 32 && par[2] <= p - 32) out = make_int4(par[2], par[0], -1, 1);   // + prev - opp
+    }
+    ((int4 *)(S2 + f.o_par[j]))[p] = out;
 }
 
-// DIFFERENCE / PARALLELOGRAM + WRAP chain (also the pass-through for "no prediction"): one warp per
-// (frame, attribute), lane k owns component k.  what = attribute index.
-__global__ void __launch_bounds__(32) k_predict_wrap(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S2, const Job *jobs, int njobs) {
-    if ((int)blockIdx.x >= njobs) return;
-    const Job jb = jobs[blockIdx.x];
+// DIFFERENCE / PARALLELOGRAM + WRAP reversal (also the pass-through for "no prediction"): one warp per
+// (frame, attribute).  Runs of scan-able entries (k_parents) are reversed 32 at a time with a warp prefix
+// sum; the wrap transform's clamp / wrap (rare: a handful per frame) is detected after the fact and the
+// offending entry is redone with the exact serial formula, as are the entries of any other shape.
+// Values of the last PW_RING entries are mirrored in a shared-memory ring (the far parents sit about one
+// strip back).  what = attribute index.
+#define PW_RING 512
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_wrap(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S2, const Job *jobs, int njobs) {
+    __shared__ int ring_all[SERIAL_WARPS][PW_RING * 4];
+    const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+    if (ji >= njobs) return;
+    int *ring = ring_all[threadIdx.x >> 5];
+    const Job jb = jobs[ji];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int j = jb.what; const DracoAttr &a = f.attr[j];
-    const int n = (int)counts[jb.frame].entries[a.table + 1], k = threadIdx.x;
+    const int n = (int)counts[jb.frame].entries[a.table + 1], lane = threadIdx.x & 31, nc = a.vnc;
     const int32_t *corr = (const int32_t *)(S2 + f.o_corr[j]); int32_t *val = (int32_t *)(S2 + f.o_val_attr[j]);
-    if (a.pred == -2) { for (int i = k; i < n * a.vnc; i += 32) val[i] = corr[i]; return; }
-    if (k >= a.vnc) return;
-    predict_wrap_component(k, a.vnc, n, a.pred == 1, (const int *)(S2 + f.o_par[j]), corr, val, a.wmin, a.wmax);
+    if (a.pred == -2) { for (int i = lane; i < n * nc; i += 32) val[i] = corr[i]; return; }
+    if (n <= 0) return;
+    const int4 *par = (const int4 *)(S2 + f.o_par[j]);
+    const int32_t mn = a.wmin, mx = a.wmax;
+    // x(e, k): value of entry e, from the ring when recent enough
+#define PW_GET(e, k, pcur) (((e) > (pcur) - PW_RING + 32) ? ring[((e) & (PW_RING - 1)) * 4 + (k)] : val[(e) * nc + (k)])
+    int carry[4] = {0, 0, 0, 0};
+    if (lane < nc) { const int32_t v = wrap_value(0, corr[lane], mn, mx); val[lane] = v; ring[lane] = v; }
+    __syncwarp();
+    for (int k = 0; k < nc; k++) carry[k] = ring[k];
+    int p = 1;
+    while (p < n) {
+        const int q = p + lane;
+        int4 pr = make_int4(-1, -1, -1, 0);
+        if (q < n) pr = par[q];
+        const unsigned amask = __ballot_sync(0xffffffffu, q < n && pr.w == 1);
+        const int L = amask == 0xffffffffu ? 32 : __ffs(~amask) - 1;
+        if (L > 0) {
+            int g[4] = {0, 0, 0, 0}, cr[4] = {0, 0, 0, 0};
+            if (lane < L) {
+                for (int k = 0; k < nc; k++) {
+                    cr[k] = corr[q * nc + k];
+                    int far = 0;
+                    if (pr.x >= 0) far = PW_GET(pr.x, k, p) - PW_GET(pr.y, k, p);
+                    g[k] = far + cr[k];
+                }
+            }
+            bool ok = true; int x[4];
+            for (int k = 0; k < nc; k++) {
+                int sc = g[k];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+                x[k] = carry[k] + sc;
+                const int pred = x[k] - cr[k];
+                ok = ok && pred >= mn && pred <= mx && x[k] >= mn && x[k] <= mx;
+            }
+            const unsigned okmask = __ballot_sync(0xffffffffu, ok || lane >= L);
+            const int L2 = okmask == 0xffffffffu ? L : min(L, __ffs(~okmask) - 1);
+            if (lane < L2) for (int k = 0; k < nc; k++) { val[q * nc + k] = x[k]; ring[(q & (PW_RING - 1)) * 4 + k] = x[k]; }
+            if (L2 > 0) for (int k = 0; k < nc; k++) carry[k] = __shfl_sync(0xffffffffu, x[k], L2 - 1);
+            p += L2;
+            __syncwarp();
+            if (L2 == L && L > 0) continue;
+        }
+        if (p >= n) break;
+        // exact serial step for entry p (any shape, clamp and wrap applied): lane k owns component k
+        const int4 ps = par[p];
+        if (lane < nc) {
+            long long pred;
+            if (ps.w == 1) pred = (long long)carry[lane] + (ps.x >= 0 ? (long long)PW_GET(ps.x, lane, p) - PW_GET(ps.y, lane, p) : 0);
+            else if (ps.x >= 0) pred = ((long long)PW_GET(ps.y, lane, p) + PW_GET(ps.z, lane, p)) - PW_GET(ps.x, lane, p);
+            else pred = carry[lane];
+            const int32_t v = wrap_value(pred, corr[p * nc + lane], mn, mx);
+            val[p * nc + lane] = v; ring[(p & (PW_RING - 1)) * 4 + lane] = v;
+        }
+        __syncwarp();
+        for (int k = 0; k < nc; k++) carry[k] = ring[(p & (PW_RING - 1)) * 4 + k];
+        p += 1;
+    }
+#undef PW_GET
 }
 
 // TEX_COORDS_PORTABLE position-only terms, element-parallel.  grid = (ceil(maxN/128), frames, attrs)
@@ -584,19 +673,83 @@ __global__ void __launch_bounds__(128) k_uv_prepare(const DracoFrame *frames, co
     UvPrep q;
     uv_prepare(p, tv, (const int *)(S2 + f.o_d2c[t]), (const int *)(Z2 + f.o_v2d[t]), (const int *)(Z2 + f.o_v2d[0]),
                (const int32_t *)(S2 + f.o_val_attr[f.pos_attr]), q);
-    ((UvPrep *)(S2 + f.o_par[j]))[p] = q;
+    UvPrepD o; o.nd = q.nd; o.pd = q.pd; o.pn2 = q.pn2; o.dot = q.dot; o.ns = q.ns; o.rcp = q.pn2 ? 1.0 / (double)q.pn2 : 0.0;
+    ((UvPrepD *)(S2 + f.o_par[j]))[p] = o;
 }
 
-// TEX_COORDS_PORTABLE chain: one warp per (frame, attribute), lane 0 walks.
-__global__ void __launch_bounds__(32) k_predict_uv(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, const Job *jobs, int njobs) {
-    if ((int)blockIdx.x >= njobs || threadIdx.x != 0) return;
-    const Job jb = jobs[blockIdx.x];
+// TEX_COORDS_PORTABLE chain: one warp per (frame, attribute).  The recurrence is non-linear (integer
+// division by |PN|^2), so it stays a serial walk by lane 0, but everything that is not on the dependency
+// chain is taken off it: the position-only terms and 1/|PN|^2 come from k_uv_prepare, tiles of 32 entries
+// (terms, corrections, orientation flags) are staged in shared memory by the whole warp, the last UV_RING
+// values are mirrored in a shared-memory ring, and the two truncating 64-bit divisions per entry are done as
+// double-precision multiplies by the prepared reciprocal with an exact remainder fix-up.
+#define UV_RING 1024
+__device__ __forceinline__ long long div_trunc_rcp(long long a, long long b, double rcp) {     // b > 0; exact C++ a / b
+    long long q = (long long)((double)a * rcp);
+    long long r = a - q * b;
+    if (a >= 0) { while (r < 0) { q--; r += b; } while (r >= b) { q++; r -= b; } }
+    else { while (r > 0) { q++; r -= b; } while (r <= -b) { q--; r += b; } }
+    return q;
+}
+struct UvTile { UvPrepD prep[32]; int32_t corr[64]; uint8_t orient[32]; int pad[8]; };
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_uv(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, const Job *jobs, int njobs) {
+    __shared__ int ring_all[SERIAL_WARPS][UV_RING * 2];
+    __shared__ UvTile tile_all[SERIAL_WARPS];
+    const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+    if (ji >= njobs) return;
+    int *ring = ring_all[threadIdx.x >> 5]; UvTile &T = tile_all[threadIdx.x >> 5];
+    const Job jb = jobs[ji];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int j = jb.what; const DracoAttr &a = f.attr[j];
-    const int n = (int)counts[jb.frame].entries[a.table + 1];
-    const int rc = predict_uv_chain(n, (const UvPrep *)(S2 + f.o_par[j]), (const int32_t *)(S2 + f.o_corr[j]), (int32_t *)(S2 + f.o_val_attr[j]),
-                                    S2 + f.o_auxbits[j], a.num_orient, a.wmin, a.wmax);
-    if (rc) frame_fail(counts, jb.frame, rc);
+    const int n = (int)counts[jb.frame].entries[a.table + 1], lane = threadIdx.x & 31;
+    const UvPrepD *prep = (const UvPrepD *)(S2 + f.o_par[j]); const int32_t *corr = (const int32_t *)(S2 + f.o_corr[j]);
+    int32_t *uv = (int32_t *)(S2 + f.o_val_attr[j]); const uint8_t *orient = S2 + f.o_auxbits[j];
+    const int32_t mn = a.wmin, mx = a.wmax;
+    int nor = a.num_orient, status = 0;
+    for (int base = 0; base < n; base += 32) {
+        // stage the tile (all lanes)
+        const int cnt = min(32, n - base);
+        if (lane < cnt) { T.prep[lane] = prep[base + lane]; T.corr[2 * lane] = corr[2 * (base + lane)]; T.corr[2 * lane + 1] = corr[2 * (base + lane) + 1]; }
+        const int nor0 = __shfl_sync(0xffffffffu, nor, 0);                  // flags [nor0-32, nor0) cover this tile
+        { const int oi = nor0 - 32 + lane; T.orient[lane] = oi >= 0 ? orient[oi] : 0; }
+        __syncwarp();
+        if (lane == 0) {
+            for (int i = 0; i < cnt; i++) {
+                const int p = base + i; const UvPrepD q = T.prep[i];
+                int pred0, pred1; bool have = false;
+                if (q.pd < p && q.nd < p && q.pd >= 0 && q.nd >= 0) {
+                    const int n0 = q.nd > p - UV_RING ? ring[(q.nd & (UV_RING - 1)) * 2] : uv[q.nd * 2], n1 = q.nd > p - UV_RING ? ring[(q.nd & (UV_RING - 1)) * 2 + 1] : uv[q.nd * 2 + 1];
+                    const int p0 = q.pd > p - UV_RING ? ring[(q.pd & (UV_RING - 1)) * 2] : uv[q.pd * 2], p1 = q.pd > p - UV_RING ? ring[(q.pd & (UV_RING - 1)) * 2 + 1] : uv[q.pd * 2 + 1];
+                    if (n0 == p0 && n1 == p1) { pred0 = p0; pred1 = p1; have = true; }
+                    else if (q.pn2 != 0) {
+                        const long long d0 = p0 - n0, d1 = p1 - n1;
+                        const long long x0 = (long long)n0 * q.pn2 + q.dot * d0, x1 = (long long)n1 * q.pn2 + q.dot * d1;
+                        const long long c0 = d1 * q.ns, c1 = -d0 * q.ns;
+                        if (nor <= 0) { status = UVOL_ERR_CORRUPT; break; }
+                        --nor;
+                        const bool o = T.orient[nor - (nor0 - 32)] != 0;
+                        const long long a0 = o ? x0 + c0 : x0 - c0, a1 = o ? x1 + c1 : x1 - c1;
+                        long long r0, r1;
+                        if ((a0 < 0 ? -a0 : a0) < (1ll << 51) && (a1 < 0 ? -a1 : a1) < (1ll << 51)) { r0 = div_trunc_rcp(a0, q.pn2, q.rcp); r1 = div_trunc_rcp(a1, q.pn2, q.rcp); }
+                        else { r0 = a0 / q.pn2; r1 = a1 / q.pn2; }
+                        pred0 = (int32_t)r0; pred1 = (int32_t)r1; have = true;
+                    }
+                }
+                if (!have) {
+                    if (q.nd < p && q.nd >= 0) { pred0 = q.nd > p - UV_RING ? ring[(q.nd & (UV_RING - 1)) * 2] : uv[q.nd * 2]; pred1 = q.nd > p - UV_RING ? ring[(q.nd & (UV_RING - 1)) * 2 + 1] : uv[q.nd * 2 + 1]; }
+                    else if (p > 0) { pred0 = ring[((p - 1) & (UV_RING - 1)) * 2]; pred1 = ring[((p - 1) & (UV_RING - 1)) * 2 + 1]; }
+                    else { pred0 = pred1 = 0; }
+                }
+                const int32_t u0 = wrap_value(pred0, T.corr[2 * i], mn, mx), u1 = wrap_value(pred1, T.corr[2 * i + 1], mn, mx);
+                ring[(p & (UV_RING - 1)) * 2] = u0; ring[(p & (UV_RING - 1)) * 2 + 1] = u1;
+                *(int2 *)(uv + 2 * p) = make_int2(u0, u1);
+            }
+        }
+        __syncwarp();
+        status = __shfl_sync(0xffffffffu, status, 0);
+        if (status) break;
+    }
+    if (status && lane == 0) frame_fail(counts, jb.frame, status);
 }
 
 // GEOMETRIC_NORMAL, element-parallel (each entry depends only on finished positions).
@@ -734,25 +887,28 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     const uint8_t *dBlob = (const uint8_t *)ctx->d_blob.p; const uint32_t *dAux = (const uint32_t *)ctx->d_aux.p;
     uint8_t *dS = (uint8_t *)ctx->d_scratch.p, *dZ = (uint8_t *)ctx->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
     uint32_t launches = 0;
-    auto rans_smem = [](uint32_t alphabet) { return (size_t)(alphabet + 1) * 4 + 257 * 2 + 16; };
+    auto rans_words = [](uint32_t alphabet) { return (int)(((size_t)(alphabet + 1) * 4 + 257 * 2 + 16 + 15) / 16 * 4); };
+    auto rans_smem = [&](uint32_t alphabet) { return (size_t)rans_words(alphabet) * 4 * SERIAL_WARPS; };
+    auto nblk = [](int jobs) { return (unsigned)((jobs + SERIAL_WARPS - 1) / SERIAL_WARPS); };
     {
         const size_t smA = rans_smem(B.max_alpha_ctx), smB = rans_smem(B.max_alpha_attr);
         const size_t smMax = smA > smB ? smA : smB;
         if (smMax > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_rans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smMax));
+        UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB_RING + 128) * 16)));
     }
     // ---- phase 1.  The seam-bit runs depend only on the file bytes: they run on the side stream s1
     // next to the context-symbol runs and the connectivity walk.
-    cudaStream_t sx = ctx->s1;
+    cudaStream_t sx = getenv("UVOL_NO_OVERLAP") ? ctx->s0 : ctx->s1;
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[0], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->sync_ev[0], 0));
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[0], sx);
-    if (B.j_trav - B.j_rabsA > 0) { k_rabs<<<B.j_trav - B.j_rabsA, 32, 0, sx>>>(dF, dC, dBlob, dS, nullptr, dJ + B.j_rabsA, B.j_trav - B.j_rabsA); launches++; }
+    if (B.j_trav - B.j_rabsA > 0) { k_rabs<<<nblk(B.j_trav - B.j_rabsA), 32 * SERIAL_WARPS, 0, sx>>>(dF, dC, dBlob, dS, nullptr, dJ + B.j_rabsA, B.j_trav - B.j_rabsA); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[1], sx);
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[1], sx));
-    if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<B.j_rabsA - B.j_ransA, 32, rans_smem(B.max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + B.j_ransA, B.j_rabsA - B.j_ransA); launches++; }
+    if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<nblk(B.j_rabsA - B.j_ransA), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + B.j_ransA, B.j_rabsA - B.j_ransA, rans_words(B.max_alpha_ctx)); launches++; }
     stamp("rans_ctx");
     stamp("rabs_seams(s1)"); i_seams = ev - 2;                                     // (stage slot of rabs_seams: timed on s1, filled in below)
-    if (B.any_valence) { k_edgebreaker_valence<<<n, 32, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
-    if (B.any_standard) { k_edgebreaker<<<n, 32, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
+    if (B.any_valence) { k_edgebreaker_valence<<<nblk(n), 32 * SERIAL_WARPS, (size_t)SERIAL_WARPS * (EB_RING + 128) * 16, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
+    if (B.any_standard) { k_edgebreaker<<<nblk(n), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
     stamp("edgebreaker");
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[1], 0));
     k_seams<<<n, 256, 0, st>>>(dF, dC, dS, dZ, n); launches++;
@@ -788,9 +944,9 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     // ---- phase 2.  Attribute entropy runs (sized from counts.expected) go to s1 and overlap the traversals.
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[2], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->sync_ev[2], 0));
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[2], sx);
-    if (B.j_rabsB - B.j_ransB > 0) { k_rans<<<B.j_rabsB - B.j_ransB, 32, rans_smem(B.max_alpha_attr), sx>>>(dF, dC, dBlob, dAux, dS, dS2, dJ + B.j_ransB, B.j_rabsB - B.j_ransB); launches++; }
+    if (B.j_rabsB - B.j_ransB > 0) { k_rans<<<nblk(B.j_rabsB - B.j_ransB), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_attr), sx>>>(dF, dC, dBlob, dAux, dS, dS2, dJ + B.j_ransB, B.j_rabsB - B.j_ransB, rans_words(B.max_alpha_attr)); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[3], sx);
-    if (B.j_wrap - B.j_rabsB > 0) { k_rabs<<<B.j_wrap - B.j_rabsB, 32, 0, sx>>>(dF, dC, dBlob, dS, dS2, dJ + B.j_rabsB, B.j_wrap - B.j_rabsB); launches++; }
+    if (B.j_wrap - B.j_rabsB > 0) { k_rabs<<<nblk(B.j_wrap - B.j_rabsB), 32 * SERIAL_WARPS, 0, sx>>>(dF, dC, dBlob, dS, dS2, dJ + B.j_rabsB, B.j_wrap - B.j_rabsB); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[4], sx);
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[3], sx));
     k_point_fan<1><<<dim3(gv, n), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dO); launches++;
@@ -800,10 +956,10 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         k_corner_records<<<dim3((3 * B.maxF + 127) / 128, ntj), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dJ + B.j_trav); launches++;
         stamp("corner_records");
         const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((maxN + 31) / 32 + 4) & ~3u);   // multiples of 4 words: the window stays 16 B aligned
-        const size_t smem = (size_t)(fwords + vwords) * 4 + TRAV_WIN * 16 + TRAV_STACK * 4;
+        const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_WIN * 16 + TRAV_STACK * 4) * SERIAL_WARPS;
         if (smem > 200 * 1024) { ctx->err = "mesh too large for the traversal bitmaps"; return UVOL_ERR_UNSUPPORTED; }
         if (smem > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_traverse<<<ntj, 32, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords); launches++;
+        k_traverse<<<nblk(ntj), 32 * SERIAL_WARPS, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords); launches++;
     }
     stamp("traverse");
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[3], 0));
@@ -812,11 +968,11 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     const unsigned gn = (maxN + 127) / 128;
     k_parents<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
     stamp("parents");
-    if (B.j_uv - B.j_wrap > 0) { k_predict_wrap<<<B.j_uv - B.j_wrap, 32, 0, st>>>(dF, dC, dS2, dJ + B.j_wrap, B.j_uv - B.j_wrap); launches++; }
+    if (B.j_uv - B.j_wrap > 0) { k_predict_wrap<<<nblk(B.j_uv - B.j_wrap), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dS2, dJ + B.j_wrap, B.j_uv - B.j_wrap); launches++; }
     stamp("predict_wrap");
     k_uv_prepare<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
     stamp("uv_prepare");
-    if (B.j_end - B.j_uv > 0) { k_predict_uv<<<B.j_end - B.j_uv, 32, 0, st>>>(dF, dC, dS2, dJ + B.j_uv, B.j_end - B.j_uv); launches++; }
+    if (B.j_end - B.j_uv > 0) { k_predict_uv<<<nblk(B.j_end - B.j_uv), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dS2, dJ + B.j_uv, B.j_end - B.j_uv); launches++; }
     stamp("predict_uv");
     k_normals<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
     stamp("normals");

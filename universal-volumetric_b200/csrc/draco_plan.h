@@ -58,7 +58,7 @@ static inline void draco_plan_phase2(std::vector<DracoFrame> &frames, const Drac
             if (a.out_slot < 0 && j != f.pos_attr) { f.o_corr[j] = f.o_val_attr[j] = f.o_par[j] = f.o_auxbits[j] = UVOL_NONE; continue; }
             const uint64_t n = (a.table < 0 ? c.num_vertex_slots : c.attr_vertices[a.table]) + 4;
             f.o_corr[j] = plan_take(s, n * a.vnc * 4); f.o_val_attr[j] = plan_take(s, n * a.vnc * 4);
-            f.o_par[j] = plan_take(s, n * (a.pred == 5 ? 32 : 16));
+            f.o_par[j] = plan_take(s, n * (a.pred == 5 ? 40 : 16));
             f.o_auxbits[j] = plan_take(s, n + 8);
         }
         f.out_index = plan_take(o, F * 12);
