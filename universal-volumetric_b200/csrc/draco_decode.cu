@@ -459,10 +459,41 @@ __global__ void __launch_bounds__(128) k_corner_records(const DracoFrame *frames
     ((uint4 *)(S2 + f.o_frec[t]))[c] = make_uint4(v, (uint32_t)t_opp(tv, cnext(c)), (uint32_t)t_opp(tv, cprev(c)), 0u);
 }
 
-// Depth-first traversal (A.3): one warp per (frame, table).  Lane 0 walks; visited faces / vertices are
-// shared-memory bitmaps, corner records come from a shared-memory window that the whole warp refills
-// on a miss, the split stack lives in shared memory (spilling to global).  what = table.
-#define TRAV_WIN 256          // corners in the window (4 KiB)
+// Per-face entry records (element-parallel): the corner record of the corner through which the
+// traversal ENTERS face f when it arrives from face f-1 ("up") or from face f+1 ("down"), i.e. the corner
+// of f whose opposite corner lies in that neighbour; w = the corner id, -1 when f does not touch it.
+// grid = (ceil(maxF/128), traversal jobs)
+__global__ void __launch_bounds__(128) k_face_entries(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S2, const Job *jobs) {
+    const Job jb = jobs[blockIdx.y];
+    if (frame_dead(frames, counts, jb.frame)) return;
+    const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
+    if (f.o_d2c[t] == UVOL_NONE) return;
+    const int F = (int)f.nf, fi = blockIdx.x * 128 + threadIdx.x;
+    if (fi >= F) return;
+    const uint4 *rec = (const uint4 *)(S2 + f.o_frec[t]);
+    uint4 *up = (uint4 *)(S2 + f.o_frec[t]) + 3 * (size_t)F + 4, *dn = up + F + 4;
+    uint4 u = make_uint4(0, 0xffffffffu, 0xffffffffu, 0xffffffffu), d = u;
+    // corner k of face fi is entered across the edge opposite k; its opposite corner is the "right" link of prev(k)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int c = 3 * fi + k, kp = k == 0 ? 2 : k - 1;
+        const int o = (int)rec[3 * fi + kp].y;                    // t_opp(cnext(prev(c))) = t_opp(c)
+        if (o < 0) continue;
+        const int of = (int)(__umulhi((unsigned)o, 0xAAAAAAABu) >> 1);
+        uint4 r = rec[c]; r.w = (uint32_t)c;
+        if (of == fi - 1 && (int)u.w < 0) u = r;
+        if (of == fi + 1 && (int)d.w < 0) d = r;
+    }
+    up[fi] = u; dn[fi] = d;
+}
+
+// Depth-first traversal (A.3): one warp per (frame, table), 32 faces per step.
+// Face ids follow the edgebreaker strip order and the traversal walks along the same strips (94-99 % of its
+// moves go to face id +-1), so lane i SPECULATES that the walk reaches face f0 + i*dir through that face's
+// static entry corner (k_face_entries).  Every lane evaluates the exact step rule for its face against the
+// visited bitmaps plus the effects of the lanes before it (warp match / ballot), the longest prefix whose
+// transitions really lead to the next lane's corner is committed at once, and the first lane that deviates
+// (pop, push, turn) hands its exact outcome to the next step.  Output order is identical to the serial walk.
 #define TRAV_STACK 512
 __device__ __forceinline__ unsigned face_of(int c) { return __umulhi((unsigned)c, 0xAAAAAAABu) >> 1; }
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, uint8_t *Z2,
@@ -470,86 +501,124 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_traverse(const DracoFrame
     extern __shared__ uint32_t sm_all[];
     const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if (ji >= njobs) return;
-    uint32_t *sm = sm_all + (size_t)(threadIdx.x >> 5) * (fwords_max + vwords_max + TRAV_WIN * 4 + TRAV_STACK);
+    uint32_t *sm = sm_all + (size_t)(threadIdx.x >> 5) * (fwords_max + vwords_max + TRAV_STACK);
     const Job jb = jobs[ji];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
     if (f.o_d2c[t] == UVOL_NONE) return;
     const int F = (int)f.nf, C = 3 * F, lane = threadIdx.x & 31;
-    uint32_t *fbits = sm, *vbits = sm + fwords_max; uint4 *win = (uint4 *)(sm + fwords_max + vwords_max); int *stk = (int *)(win + TRAV_WIN);
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t *fbits = sm, *vbits = sm + fwords_max; int *stk = (int *)(sm + fwords_max + vwords_max);
     for (int i = lane; i < fwords_max + vwords_max; i += 32) sm[i] = 0;
-    const uint4 *grec = (const uint4 *)(S2 + f.o_frec[t]);
+    const uint4 *grec = (const uint4 *)(S2 + f.o_frec[t]), *gup = grec + 3 * (size_t)F + 4, *gdn = gup + F + 4;
     int *d2c = (int *)(S2 + f.o_d2c[t]), *v2d1 = (int *)(Z2 + f.o_v2d[t]), *gst = (int *)(S2 + f.o_tstack[t]);
-    int w0 = 0;
-    for (int i = lane; i < min(TRAV_WIN, C); i += 32) win[i] = grec[i];
     __syncwarp();
-    int n = 0, sp = 0, c = 0, fscan = 0, need = 0, status = 0, done = 0;
-    bool resume_first = false;       // a component start is pending on corner c (its record was outside the window)
-    bool walking = false;            // c is a corner of an unvisited face to be processed
+    int n = 0, sp = 0, c = -1, fscan = 0, status = 0;
+#define FBIT(x) ((fbits[(x) >> 5] >> ((x) & 31)) & 1u)
+#define VBIT(x) ((vbits[(x) >> 5] >> ((x) & 31)) & 1u)
     for (;;) {
-        if (lane == 0) {
-            for (;;) {
-                if (!walking && !resume_first) {
-                    // ---- pick the next corner: stack top, else next unvisited face in id order
+        if (c < 0) {
+            // ---- pick the next corner (lane 0): stack top, else the next unvisited face starts a component
+            int done = 0;
+            if (lane == 0) {
+                for (;;) {
                     if (sp == 0) {
                         int w = fscan >> 5; uint32_t m = ~fbits[w] & (0xffffffffu << (fscan & 31));
                         while (m == 0 && w + 1 < fwords_max) { w++; m = ~fbits[w]; }
                         const int nf = m ? w * 32 + __ffs(m) - 1 : F;
                         if (nf >= F) { done = 1; break; }
-                        fscan = nf; c = 3 * nf; stk[0] = c; sp = 1; resume_first = true;
-                    } else {
-                        c = sp <= TRAV_STACK ? stk[sp - 1] : gst[sp - 1];
-                        if (c < 0) { sp--; continue; }
-                        const unsigned fc = face_of(c);
-                        if ((fbits[fc >> 5] >> (fc & 31)) & 1u) { sp--; continue; }
-                        walking = true;
+                        fscan = nf; c = 3 * nf; stk[0] = c; sp = 1;
+                        const unsigned vn = grec[c + 1].x & 0x7fffffffu, vp = grec[c + 2].x & 0x7fffffffu;     // next / previous vertices first
+                        if (!VBIT(vn)) { vbits[vn >> 5] |= 1u << (vn & 31); v2d1[vn] = ++n; d2c[n - 1] = c + 1; }
+                        if (!VBIT(vp)) { vbits[vp >> 5] |= 1u << (vp & 31); v2d1[vp] = ++n; d2c[n - 1] = c + 2; }
+                        break;
                     }
-                }
-                const unsigned ci = (unsigned)(c - w0);
-                if (ci >= TRAV_WIN) { need = c; break; }
-                if (resume_first) {
-                    // first face of a component: its next / previous vertices are visited first
-                    const int k = c - 3 * (int)face_of(c);
-                    const int cn = k == 2 ? c - 2 : c + 1, cp = k == 0 ? c + 2 : c - 1;
-                    const unsigned in = (unsigned)(cn - w0), ip = (unsigned)(cp - w0);
-                    if (in >= TRAV_WIN || ip >= TRAV_WIN) { need = 3 * (int)face_of(c) + 1; if ((unsigned)(need - w0 - 1) < TRAV_WIN - 2) { status = UVOL_ERR_CORRUPT; done = 1; } break; }
-                    const unsigned vn = win[in].x & 0x7fffffffu, vp = win[ip].x & 0x7fffffffu;
-                    if (!((vbits[vn >> 5] >> (vn & 31)) & 1u)) { vbits[vn >> 5] |= 1u << (vn & 31); v2d1[vn] = ++n; d2c[n - 1] = cn; }
-                    if (!((vbits[vp >> 5] >> (vp & 31)) & 1u)) { vbits[vp >> 5] |= 1u << (vp & 31); v2d1[vp] = ++n; d2c[n - 1] = cp; }
-                    resume_first = false; walking = true;
-                }
-                // ---- hot loop: one step per face
-                const uint4 R = win[ci];
-                const unsigned fc = face_of(c);
-                fbits[fc >> 5] |= 1u << (fc & 31);
-                const unsigned v = R.x & 0x7fffffffu, vw = vbits[v >> 5], vm = 1u << (v & 31);
-                if (!(vw & vm)) {
-                    vbits[v >> 5] = vw | vm; v2d1[v] = ++n; d2c[n - 1] = c;
-                    if ((int)R.x >= 0) { c = (int)R.y; continue; }       // interior vertex: go to the right face
-                }
-                const int rc = (int)R.y, lc = (int)R.z;
-                bool fr = rc < 0, fl = lc < 0;
-                if (!fr) { const unsigned rf = face_of(rc); fr = (fbits[rf >> 5] >> (rf & 31)) & 1u; }
-                if (!fl) { const unsigned lf = face_of(lc); fl = (fbits[lf >> 5] >> (lf & 31)) & 1u; }
-                if (fr) {
-                    if (fl) { sp--; walking = false; } else c = lc;
-                } else if (fl) c = rc;
-                else {      // both open: the left face waits on the stack, the right one is walked now
-                    if (sp <= TRAV_STACK) stk[sp - 1] = lc; else gst[sp - 1] = lc;
-                    if (sp < TRAV_STACK) stk[sp] = rc; else gst[sp] = rc;
-                    sp++; c = rc;
+                    c = sp <= TRAV_STACK ? stk[sp - 1] : gst[sp - 1];
+                    if (c < 0 || FBIT(face_of(c))) { sp--; c = -1; continue; }
+                    break;
                 }
             }
+            __syncwarp();
+            done = __shfl_sync(0xffffffffu, done, 0);
+            if (done) break;
+            c = __shfl_sync(0xffffffffu, c, 0); n = __shfl_sync(0xffffffffu, n, 0); sp = __shfl_sync(0xffffffffu, sp, 0); fscan = __shfl_sync(0xffffffffu, fscan, 0);
         }
+        if (c >= C) { status = UVOL_ERR_CORRUPT; break; }
+        // ---- one speculative step over up to 32 faces
+        const int f0 = (int)face_of(c);
+        const uint4 R0 = grec[c];
+        const int fu = f0 + lane, fd = f0 - lane;
+        uint4 U = make_uint4(0, 0, 0, 0xffffffffu), D = U;
+        if (lane > 0 && fu < F) U = gup[fu];
+        if (lane > 0 && fd >= 0) D = gdn[fd];
+        // lane 0's exact decision (computed by every lane) fixes the direction
+        int dir;
+        {
+            const unsigned v = R0.x & 0x7fffffffu; const int rc = (int)R0.y, lc = (int)R0.z; int nx = -1;
+            if (!VBIT(v) && (int)R0.x >= 0) nx = rc;
+            else {
+                const bool fr = rc < 0 || FBIT(face_of(rc)) || face_of(rc) == (unsigned)f0, fl = lc < 0 || FBIT(face_of(lc)) || face_of(lc) == (unsigned)f0;
+                if (fr && !fl) nx = lc; else if (!fr) nx = rc;
+            }
+            const int nf = nx >= 0 ? (int)face_of(nx) : -9;
+            dir = nf == f0 + 1 ? 1 : (nf == f0 - 1 ? -1 : 0);
+        }
+        uint4 R = lane == 0 ? R0 : (dir > 0 ? U : D);
+        if (lane == 0) R.w = (uint32_t)c;
+        if (lane > 0 && dir == 0) R.w = 0xffffffffu;
+        const int ci = (int)R.w;                                   // my corner (-1: no such entry)
+        const int fi = f0 + lane * dir;
+        const unsigned v = R.x & 0x7fffffffu; const bool ob = (int)R.x < 0; const int rc = (int)R.y, lc = (int)R.z;
+        const bool selfopen = ci >= 0 && !FBIT(fi);
+        // vertex visited before my step: bitmap, or the tip of an earlier lane
+        const unsigned same = __match_any_sync(0xffffffffu, ci >= 0 ? v : 0x80000000u + lane);
+        const bool vis = ci >= 0 && (VBIT(v) || (same & lt) != 0);
+        // neighbour faces visited before / during this step (faces of the lanes up to and including me)
+        bool fr = true, fl = true;
+        if (ci >= 0) {
+            if (rc >= 0) { const int rf = (int)face_of(rc), k = (rf - f0) * dir; fr = FBIT(rf) || (dir != 0 ? (k >= 0 && k <= lane) : rf == f0); }
+            if (lc >= 0) { const int lf = (int)face_of(lc), k = (lf - f0) * dir; fl = FBIT(lf) || (dir != 0 ? (k >= 0 && k <= lane) : lf == f0); }
+        }
+        int act = 0 /*0 continue to nx, 1 pop, 2 push*/, nx = -1;
+        if (!vis && !ob) nx = rc;
+        else if (fr) { if (fl) act = 1; else nx = lc; }
+        else if (fl) nx = rc;
+        else { act = 2; nx = rc; }
+        // does my transition lead exactly to the next lane's corner?
+        const int cnext_lane = __shfl_down_sync(0xffffffffu, ci, 1);
+        const bool open_next = __shfl_down_sync(0xffffffffu, (int)selfopen, 1) != 0;
+        const bool trans = act == 0 && nx >= 0 && lane < 31 && nx == cnext_lane && open_next;
+        const unsigned tmask = __ballot_sync(0xffffffffu, trans);
+        const int m = __ffs(~tmask) - 1;                             // lanes 0..m execute (lane 31 never transitions)
+        const bool exec = lane <= m;
+        if (lane == 0 && !selfopen) status = UVOL_ERR_CORRUPT;        // the walk only ever moves to unvisited faces
+        const unsigned newv = __ballot_sync(0xffffffffu, exec && !vis);
+        if (exec) {
+            atomicOr(&fbits[fi >> 5], 1u << (fi & 31));
+            if (!vis) {
+                const int idx = n + __popc(newv & lt);
+                atomicOr(&vbits[v >> 5], 1u << (v & 31));
+                v2d1[v] = idx + 1; d2c[idx] = ci;
+            }
+        }
+        n += __popc(newv);
+        // outcome of the last executed lane
+        const int act_m = __shfl_sync(0xffffffffu, act, m), nx_m = __shfl_sync(0xffffffffu, nx, m), lc_m = __shfl_sync(0xffffffffu, lc, m);
         __syncwarp();
-        done = __shfl_sync(0xffffffffu, done, 0);
-        if (done) break;
-        need = __shfl_sync(0xffffffffu, need, 0);
-        if (need < 0 || need >= C) { if (lane == 0) status = UVOL_ERR_CORRUPT; break; }
-        w0 = max(0, min(need - TRAV_WIN / 2, C - TRAV_WIN));
-        for (int i = lane; i < min(TRAV_WIN, C - w0); i += 32) win[i] = grec[(size_t)w0 + i];
-        __syncwarp();
+        if (status) break;
+        if (act_m == 0) { c = nx_m; if (c < 0) { status = UVOL_ERR_CORRUPT; break; } }
+        else if (act_m == 1) { sp--; c = -1; }
+        else {      // both neighbours open: the left face waits on the stack, the right one is walked next
+            if (lane == 0) {
+                if (sp <= TRAV_STACK) stk[sp - 1] = lc_m; else gst[sp - 1] = lc_m;
+                if (sp < TRAV_STACK) stk[sp] = nx_m; else gst[sp] = nx_m;
+            }
+            sp++; c = nx_m;
+            __syncwarp();
+        }
     }
+#undef FBIT
+#undef VBIT
     if (lane == 0) {
         counts[jb.frame].entries[t] = (uint32_t)n;
         if (!status && (uint32_t)n != counts[jb.frame].expected[t]) status = UVOL_ERR_CORRUPT;    // the entropy runs were sized from `expected`
@@ -954,9 +1023,10 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     if (B.j_ransB - B.j_trav > 0) {
         const int ntj = B.j_ransB - B.j_trav;
         k_corner_records<<<dim3((3 * B.maxF + 127) / 128, ntj), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dJ + B.j_trav); launches++;
+        k_face_entries<<<dim3((B.maxF + 127) / 128, ntj), 128, 0, st>>>(dF, dC, dS2, dJ + B.j_trav); launches++;
         stamp("corner_records");
-        const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((maxN + 31) / 32 + 4) & ~3u);   // multiples of 4 words: the window stays 16 B aligned
-        const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_WIN * 16 + TRAV_STACK * 4) * SERIAL_WARPS;
+        const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((maxN + 31) / 32 + 4) & ~3u);
+        const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_STACK * 4) * SERIAL_WARPS;
         if (smem > 200 * 1024) { ctx->err = "mesh too large for the traversal bitmaps"; return UVOL_ERR_UNSUPPORTED; }
         if (smem > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_traverse<<<nblk(ntj), 32 * SERIAL_WARPS, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords); launches++;

@@ -50,7 +50,7 @@ static inline void draco_plan_phase2(std::vector<DracoFrame> &frames, const Drac
             if (!need[t]) { f.o_d2c[t] = f.o_v2d[t] = f.o_frec[t] = f.o_tstack[t] = UVOL_NONE; continue; }
             const uint64_t nv = (t == 0 ? c.num_vertex_slots : c.attr_vertices[t - 1]) + 4;
             f.o_d2c[t] = plan_take(s, nv * 4); f.o_tstack[t] = plan_take(s, (F + 8) * 4);
-            f.o_frec[t] = plan_take(s, (3 * F + 4) * 16);      // per-corner traversal records
+            f.o_frec[t] = plan_take(s, (3 * F + 4) * 16 + 2 * (F + 4) * 16);      // per-corner traversal records + per-face up / down entry records
             f.o_v2d[t] = plan_take(z, nv * 4);
         }
         for (int j = 0; j < f.nattr; j++) {
