@@ -156,9 +156,16 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence(const
     const int F = (int)f.nf, maxv = (int)(f.nv_enc + f.nsplit), nsym = (int)f.nsym;
     int nverts = 0, ninv = 0, sp = 0, status = 0, numf = 0;
     if (lane == 0) {
-        const uint8_t *cs0 = S + f.o_ctxsym[0], *cs1 = S + f.o_ctxsym[1], *cs2 = S + f.o_ctxsym[2], *cs3 = S + f.o_ctxsym[3], *cs4 = S + f.o_ctxsym[4], *cs5 = S + f.o_ctxsym[5];
-        int k0 = (int)f.ctx[0].count, k1 = (int)f.ctx[1].count, k2 = (int)f.ctx[2].count, k3 = (int)f.ctx[3].count, k4 = (int)f.ctx[4].count, k5 = (int)f.ctx[5].count;
-        int n0 = k0 ? cs0[k0 - 1] : 255, n1 = k1 ? cs1[k1 - 1] : 255, n2 = k2 ? cs2[k2 - 1] : 255, n3 = k3 ? cs3[k3 - 1] : 255, n4 = k4 ? cs4[k4 - 1] : 255, n5 = k5 ? cs5[k5 - 1] : 255;
+        // Context symbol arrays are consumed from the back.  Each context keeps its next 8 symbols packed in a
+        // 64-bit register (byte 0 = next symbol); refills are aligned 8-byte loads issued when a register runs dry,
+        // so the symbol select is pure register work in the common case.
+        const uint8_t *csb[6]; int kk[6];
+        for (int i = 0; i < 6; i++) { csb[i] = S + f.o_ctxsym[i]; kk[i] = (int)f.ctx[i].count; }
+        unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0; int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, h5 = 0;   // packed symbols, how many are valid
+#define CTX_REFILL(W, H, I) do { int take_ = kk[I] < 8 ? kk[I] : 8; unsigned long long v_ = 0; \
+            for (int b_ = 0; b_ < take_; b_++) v_ |= (unsigned long long)csb[I][kk[I] - 1 - b_] << (8 * b_); \
+            W = v_; H = take_; kk[I] -= take_; } while (0)
+#define CTX_TAKE(W, H, I) do { if (H == 0) { if (kk[I] <= 0) { s = 255; break; } CTX_REFILL(W, H, I); } s = (int)(W & 255u); W >>= 8; H--; } while (0)
         const uint32_t *ts = aux + f.ts_off; int ts_top = (int)f.nts, nsa = 0;
         uint32_t next_ts = ts_top > 0 ? ts[3 * (ts_top - 1)] : 0xffffffffu;
         int a = -1, ta = 0, na = 0, pa = 0; VRec rt = {0, 0, 0, 0}, rn = rt, rp = rt;
@@ -170,12 +177,12 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence(const
             if (ctx < 0) s = 4;
             else {
                 switch (ctx) {
-                    case 0: s = n0; --k0; n0 = k0 > 0 ? cs0[k0 - 1] : 255; break;
-                    case 1: s = n1; --k1; n1 = k1 > 0 ? cs1[k1 - 1] : 255; break;
-                    case 2: s = n2; --k2; n2 = k2 > 0 ? cs2[k2 - 1] : 255; break;
-                    case 3: s = n3; --k3; n3 = k3 > 0 ? cs3[k3 - 1] : 255; break;
-                    case 4: s = n4; --k4; n4 = k4 > 0 ? cs4[k4 - 1] : 255; break;
-                    default: s = n5; --k5; n5 = k5 > 0 ? cs5[k5 - 1] : 255; break;
+                    case 0: CTX_TAKE(w0, h0, 0); break;
+                    case 1: CTX_TAKE(w1, h1, 1); break;
+                    case 2: CTX_TAKE(w2, h2, 2); break;
+                    case 3: CTX_TAKE(w3, h3, 3); break;
+                    case 4: CTX_TAKE(w4, h4, 4); break;
+                    default: CTX_TAKE(w5, h5, 5); break;
                 }
                 if (s > 4) { status = UVOL_ERR_CORRUPT; break; }
             }
@@ -513,7 +520,7 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_traverse(const DracoFrame
     const uint4 *grec = (const uint4 *)(S2 + f.o_frec[t]), *gup = grec + 3 * (size_t)F + 4, *gdn = gup + F + 4;
     int *d2c = (int *)(S2 + f.o_d2c[t]), *v2d1 = (int *)(Z2 + f.o_v2d[t]), *gst = (int *)(S2 + f.o_tstack[t]);
     __syncwarp();
-    int n = 0, sp = 0, c = -1, fscan = 0, status = 0;
+    int n = 0, sp = 0, c = -1, fscan = 0, status = 0, pdir = 1;
 #define FBIT(x) ((fbits[(x) >> 5] >> ((x) & 31)) & 1u)
 #define VBIT(x) ((vbits[(x) >> 5] >> ((x) & 31)) & 1u)
     for (;;) {
@@ -563,6 +570,7 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_traverse(const DracoFrame
             const int nf = nx >= 0 ? (int)face_of(nx) : -9;
             dir = nf == f0 + 1 ? 1 : (nf == f0 - 1 ? -1 : 0);
         }
+        if (dir != 0) pdir = dir;
         uint4 R = lane == 0 ? R0 : (dir > 0 ? U : D);
         if (lane == 0) R.w = (uint32_t)c;
         if (lane > 0 && dir == 0) R.w = 0xffffffffu;
