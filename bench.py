@@ -258,10 +258,20 @@ def main():
         if nbytes and per > 0:
             stages[k]["gbs"] = round(nbytes / (per * 1e-3) / 1e9, 2); stages[k]["frac"] = round(stages[k]["gbs"] / peak, 5)
     kernel_stages = {k: v for k, v in stages.items() if k not in ("h2d", "d2h", "tex_h2d", "tex_d2h", "counts_readback")}
+    ksum = sum(v["ms"] for v in kernel_stages.values()) or 1.0
+    for v in kernel_stages.values():
+        v["share_of_kernel_time"] = round(v["ms"] / ksum, 4)          # comparable with the ncu launch-list shares
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tr.get("workload") == args.workload:
+            traffic = tr
+    except Exception:
+        pass
     dom = max(kernel_stages, key=lambda k: kernel_stages[k]["ms"])
     dom_bytes = gb.get(dom.replace("(s1)", "")) if not dom.startswith("tex_") else tb.get(dom[4:])
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernel_stages[dom].get("gbs"), "peak": peak, "unit": "GB/s", "frac": kernel_stages[dom].get("frac"),
-            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": kernel_stages[dom]["ms"],
+            "traffic": (traffic or {}).get(dom.replace("(s1)", "")), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": kernel_stages[dom]["ms"],
             "note": "dominant stage is a latency-bound serial walk (one warp per frame); HBM-bound stages are listed in `stages`"}
     step_bytes = sg["bytes_in"] + st["bytes_in"] + sg["bytes_out"] + st["bytes_out"]
     pipeline = {"bytes_per_frame": step_bytes / frames, "achieved_gbs": step_bytes * world * args.steps / (dev_ms / 1e3) / 1e9}
