@@ -109,6 +109,20 @@ int uvol_decode_v2_batch(uvol_ctx *ctx, const uint8_t *const *drc, const size_t 
 int uvol_replay_v2_batch(uvol_ctx *ctx, int memory, uvol_geometry *out_geo, int n_drc, uvol_texture *out_tex, int n_ktx2);
 int uvol_get_stats_kind(const uvol_ctx *ctx, int kind /*0 geometry, 1 texture*/, uvol_stats *out);
 
+/* ---- V1 geometry: replaces the worker's per-frame `new CortoDecoder(slice).decode()` loop (src/V1/worker.ts:48-68;
+ * src/lib/corto.ts:73-140 == crt::Decoder::decode, deprecated/encoder/dev/src/decoder.cpp:122-173) for n frames sliced
+ * out of a .drcs by the manifest's startBytePosition / meshLength (src/Interfaces.ts:1-8).  Result = the
+ * bufferGeometry of src/V1/player.ts:289-297: index (u32 here; the JS path narrows to u16 when nface < 65536,
+ * corto.ts:675-680), position f32[V*3], uv f32[V*2].  The single-frame C ABI of the reference is in corto_codec.h. */
+typedef struct uvol_corto_mesh {
+    int32_t status;
+    uint32_t num_vertices, num_faces, pad;
+    uint32_t *index;       /* u32[num_faces*3] */
+    float *position;       /* f32[num_vertices*3] */
+    float *uv;             /* f32[num_vertices*2] or NULL */
+} uvol_corto_mesh;
+int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int memory, uvol_corto_mesh *out);
+
 /* Writes a buffer larger than L2 (256 MiB) on the ctx's stream and waits: L2 flush between timed iterations. */
 int uvol_flush_l2(uvol_ctx *ctx);
 

@@ -6,6 +6,6 @@ interface.  Import it with ``importlib.import_module("universal-volumetric_b200"
 """
 from . import _native
 from ._native import UvolError, MEM_DEVICE, MEM_HOST
-from .loaders import Context, DRACOLoader, KTX2Loader, V2Player
+from .loaders import Context, CortoDecoder, DRACOLoader, KTX2Loader, V2Player
 
-__all__ = ["Context", "DRACOLoader", "KTX2Loader", "V2Player", "UvolError", "MEM_DEVICE", "MEM_HOST", "_native"]
+__all__ = ["Context", "DRACOLoader", "KTX2Loader", "V2Player", "CortoDecoder", "UvolError", "MEM_DEVICE", "MEM_HOST", "_native"]

@@ -31,6 +31,15 @@ class Texture(ctypes.Structure):
                 ("data", ctypes.POINTER(ctypes.c_uint8)), ("bytes", ctypes.c_uint64)]
 
 
+class CortoMesh(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_int32), ("num_vertices", ctypes.c_uint32), ("num_faces", ctypes.c_uint32), ("pad", ctypes.c_uint32),
+                ("index", ctypes.POINTER(ctypes.c_uint32)), ("position", ctypes.POINTER(ctypes.c_float)), ("uv", ctypes.POINTER(ctypes.c_float))]
+
+
+class Vector2(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_float), ("y", ctypes.c_float)]
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("host_parse_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("device_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
                 ("total_ms", ctypes.c_double), ("stage_ms", ctypes.c_float * 24), ("num_stages", ctypes.c_uint32),
@@ -69,9 +78,14 @@ def lib():
     L.uvol_decode_v2_batch.argtypes = [vp, pv, ps, i, pv, ps, i, i, ctypes.POINTER(Geometry), ctypes.POINTER(Texture)]; L.uvol_decode_v2_batch.restype = i
     L.uvol_replay_v2_batch.argtypes = [vp, i, ctypes.POINTER(Geometry), i, ctypes.POINTER(Texture), i]; L.uvol_replay_v2_batch.restype = i
     L.uvol_get_stats_kind.argtypes = [vp, i, ctypes.POINTER(Stats)]; L.uvol_get_stats_kind.restype = i
+    L.uvol_decode_corto_batch.argtypes = [vp, pv, ps, i, i, ctypes.POINTER(CortoMesh)]; L.uvol_decode_corto_batch.restype = i
+    L.CreateDecoder.argtypes = [i, ctypes.c_char_p, ctypes.POINTER(Vector2)]; L.CreateDecoder.restype = vp
+    L.DestroyDecoder.argtypes = [vp]; L.DestroyDecoder.restype = None
+    L.DecodeMesh.argtypes = [vp, vp, vp, vp, vp, vp]; L.DecodeMesh.restype = i
     _lib = L
     return L
 
 
 EXPORTED_SYMBOLS = ["uvol_create", "uvol_destroy", "uvol_last_error", "uvol_get_stats", "uvol_stage_name", "uvol_set_profiling",
-                    "uvol_decode_draco_batch", "uvol_transcode_ktx2_batch", "uvol_replay_draco_batch", "uvol_replay_ktx2_batch", "uvol_flush_l2", "uvol_decode_v2_batch", "uvol_replay_v2_batch", "uvol_get_stats_kind"]
+                    "uvol_decode_draco_batch", "uvol_transcode_ktx2_batch", "uvol_replay_draco_batch", "uvol_replay_ktx2_batch", "uvol_flush_l2", "uvol_decode_v2_batch", "uvol_replay_v2_batch", "uvol_get_stats_kind", "uvol_decode_corto_batch",
+                    "CreateDecoder", "DestroyDecoder", "DecodeMesh"]

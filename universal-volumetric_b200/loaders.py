@@ -184,3 +184,33 @@ class V2Player:
         if rc != 0:
             raise N.UvolError(f"uvol_replay_v2_batch failed ({rc}): {self.ctx.last_error()}")
         return og, ot
+
+
+class CortoDecoder:
+    """Batch mirror of the V1 worker loop `new CortoDecoder(slice).decode()` (src/V1/worker.ts:48-68, src/lib/corto.ts:73-140).
+    `decode_batch` takes the per-frame .crt slices of a .drcs and returns, per frame, the bufferGeometry of
+    src/V1/player.ts:289-297: {"index", "position", "uv"}."""
+
+    def __init__(self, ctx=None, device=0):
+        self.ctx = ctx or Context(device)
+
+    def decode_batch_raw(self, frames, memory=N.MEM_HOST):
+        keep, ptrs, sizes = _pack(frames)
+        out = (N.CortoMesh * max(1, len(frames)))()
+        rc = self.ctx._L.uvol_decode_corto_batch(self.ctx._h, ptrs, sizes, len(frames), memory, out)
+        if rc != 0:
+            raise N.UvolError(f"uvol_decode_corto_batch failed ({rc}): {self.ctx.last_error()}")
+        self._keep = keep
+        return out
+
+    def decode_batch(self, frames):
+        raw = self.decode_batch_raw(frames, N.MEM_HOST)
+        res = []
+        for m in raw[: len(frames)]:
+            if m.status != 0:
+                res.append({"status": int(m.status)})
+                continue
+            V, F = m.num_vertices, m.num_faces
+            res.append({"status": 0, "index": np.ctypeslib.as_array(m.index, (F * 3,)).copy(), "position": np.ctypeslib.as_array(m.position, (V, 3)).copy(),
+                        "uv": np.ctypeslib.as_array(m.uv, (V, 2)).copy() if m.uv else None})
+        return res
