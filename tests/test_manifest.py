@@ -1,0 +1,101 @@
+"""CPU: manifest schema, URL templates, frame mapping and fetch windows behave like the reference's TypeScript
+(src/utils.ts, src/V2/player.ts); frame sharding covers every frame exactly once (also across 2 gloo ranks)."""
+import importlib
+import json
+import os
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+man = importlib.import_module("universal-volumetric_b200.manifest")
+
+LIAM = {"version": "v2", "audio": {"path": "liam/output/liam[ext]", "format": "mp3"},
+        "geometry": {"targets": {"draco": {"format": "draco", "frameRate": 30, "frameCount": 250}}, "path": "liam/output/geometry_[target]/[#####][ext]"},
+        "texture": {"targets": {"ktx2-fps30-1k": {"format": "ktx2", "resolution": [1024, 1024], "type": "baseColor", "tag": "default",
+                                                   "sequenceSize": 5, "sequenceCount": 50, "frameRate": 30}},
+                    "path": "liam/output/texture_[target]_[type]_[tag]/[#####][ext]"}}
+
+
+def test_url_helpers():
+    assert man.pad(7, 5) == "00007" and man.pad(123456, 5) == "123456"                   # src/utils.ts:10-14
+    assert man.count_hash_char("a/[####]/[##]") == 6
+    assert man.get_absolute_url("https://h/x/liam.uvol.json", "liam/output/a.drc") == "https://h/x/liam/output/a.drc"
+    assert man.get_absolute_url("/data/liam.uvol.json", "http://cdn/a.drc") == "http://cdn/a.drc"
+
+
+def test_v2_paths_and_mapping():
+    m = man.V2Manifest(LIAM, "/data/public/liam.uvol.json")
+    assert m.geometry_target == "draco" and m.texture_target == "ktx2-fps30-1k"
+    assert m.geometry_url(0) == "/data/public/liam/output/geometry_draco/00000.drc"
+    assert m.geometry_url(137) == "/data/public/liam/output/geometry_draco/00137.drc"
+    assert m.texture_url(49) == "/data/public/liam/output/texture_ktx2-fps30-1k_baseColor_default/00049.ktx2"
+    assert (m.geometry_frame_count, m.batch_size, m.texture_segment_count) == (250, 5, 50)
+    f = m.frames_at(1.25)                                                               # round(30 * 1.25) = 38 (Math.round: 37.5 -> 38)
+    assert f == {"geometry_frame": 38, "texture_frame": 38, "segment": 7, "layer": 3}
+    assert m.frames_at(0.0)["layer"] == 0
+    with pytest.raises(ValueError):
+        man.V2Manifest({"version": "v1"}, "x")
+
+
+def test_fetch_window_leaky_bucket():
+    m = man.V2Manifest(LIAM, "liam.uvol.json")
+    geo, tex, lg, ls = m.fetch_window(0.0, -1, -1, buffer_duration=4)                    # first fetchBuffers of a track
+    assert geo == list(range(0, 121)) and lg == 120                                      # frames (−1, 0 + 4*30]
+    assert tex == list(range(0, 25)) and ls == 24                                        # ceil(30/5) = 6 segments per second
+    geo, tex, lg, ls = m.fetch_window(2.0, lg, ls)                                       # two seconds later: only the new tail
+    assert geo == list(range(121, 181)) and tex == list(range(25, 37))
+    geo, tex, lg, ls = m.fetch_window(9.0, 249, 49)
+    assert geo == [] and tex == []                                                       # everything already requested
+
+
+def test_v1_manifest(tmp_path):
+    fd = [{"frameNumber": i, "keyframeNumber": i, "startBytePosition": 100 * i, "vertices": 10, "faces": 12, "meshLength": 100 - i} for i in range(5)]
+    p = tmp_path / "clip.manifest"; p.write_text(json.dumps({"maxVertices": 10, "maxTriangles": 12, "frameRate": 30, "frameData": fd}))
+    m = man.V1Manifest.load(str(p))
+    assert m.mesh_file.endswith("clip.drcs")
+    assert m.byte_range(1, 4) == (100, 300 + 97)
+    blob = bytes(range(256)) * 2
+    sl = m.slices(blob[100:397], 100, 1, 4)
+    assert [s[0] for s in sl] == [1, 2, 3] and [len(s[2]) for s in sl] == [99, 98, 97] and sl[1][2] == blob[200:298]
+
+
+@pytest.mark.parametrize("frames,seq,world", [(300, 7, 1), (300, 7, 2), (300, 7, 8), (1000, 7, 8), (250, 5, 4), (6, 7, 8)])
+def test_sharding_covers_everything_once(frames, seq, world):
+    nseg = (frames + seq - 1) // seq
+    got_f, got_s = [], []
+    for r in range(world):
+        f0, f1, s0, s1 = man.shard_v2(frames, seq, nseg, world, r)
+        assert f0 % seq == 0 or f0 == frames
+        got_f += list(range(f0, f1)); got_s += list(range(s0, s1))
+    assert got_f == list(range(frames)) and got_s == list(range(nseg))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    f0, f1, s0, s1 = man.shard_v2(300, 7, 43, world, rank)
+    counts = torch.tensor([f1 - f0, s1 - s0, f0, s0], dtype=torch.int64)
+    out = [torch.zeros(4, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(out, counts)                                     # the optional final gather exchanges per-rank sizes first
+    t = torch.tensor([float(rank + 1)]); dist.all_reduce(t, op=dist.ReduceOp.MAX)   # bench: max-over-ranks timing
+    if rank == 0:
+        q.put(([o.tolist() for o in out], float(t)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo():
+    """world_size-2 run on CPU (gloo): the two ranks' shards tile the clip, sizes are exchanged, timing is max-reduced."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn"); q = ctx.Queue(); port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res, tmax = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert tmax == 2.0
+    assert res[0][0] + res[1][0] == 300 and res[0][1] + res[1][1] == 43
+    assert res[0][2] == 0 and res[1][2] == res[0][0] and res[1][3] == res[0][1]

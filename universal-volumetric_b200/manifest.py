@@ -1,0 +1,199 @@
+"""Manifest layer: the reference's V1 / V2 manifest schema, URL templates and frame -> file / layer mapping, kept
+verbatim as the drop-in surface, plus the frame sharding used for multi-GPU decode.
+
+Mirrors (paths relative to the reference repo):
+* `V2Schema`, `GeometryTarget`, `KTX2TextureTarget`, `FORMATS_TO_EXT`           src/Interfaces.ts:21-37,60-73,75-132,156-161
+* `pad`, `countHashChar`, `getAbsoluteURL`                                      src/utils.ts:10-45
+* `getGeometryURL`, `getTextureURL`, target choice in `playTrack`              src/V2/player.ts:141-174,199-221
+* `getCurrentFrame`, segment / layer selection in `processFrame`                src/V2/player.ts:43-45,418-420,446
+* `fetchBuffers` request windows (leaky bucket)                                 src/V2/player.ts:272-323
+* `V1Schema`, `V1FrameData`; .manifest -> .drcs; per-frame slices               src/Interfaces.ts:1-15; src/V1/player.ts:337; src/V1/worker.ts:48-56
+Everything here is host logic (no decode); the decode calls go through libuvol_b200.so.
+"""
+import json
+import math
+import os
+
+FORMATS_TO_EXT = {"mp3": ".mp3", "draco": ".drc", "ktx2": ".ktx2", "etc2": ".etc2"}          # src/Interfaces.ts:156-161
+TEXTURE_FORMAT_PRIORITY = {"ktx2": 0, "etc2": 1, "etc1": 2}                                   # src/Interfaces.ts:165-169
+
+
+def pad(n, width):
+    """src/utils.ts:10-14"""
+    s = str(int(n))
+    return s if len(s) >= width else "0" * (width - len(s)) + s
+
+
+def count_hash_char(url):
+    """src/utils.ts:16-24"""
+    return url.count("#")
+
+
+def get_absolute_url(manifest_url, new_segment):
+    """src/utils.ts:38-45: absolute (http...) paths pass through, relative ones replace the manifest's file name."""
+    if new_segment.startswith("http"):
+        return new_segment
+    parts = manifest_url.split("/")
+    parts.pop()
+    parts.append(new_segment)
+    return "/".join(parts)
+
+
+def js_round(x):
+    """Math.round: half away from floor (src/V2/player.ts:43-45 uses Math.round(frameRate * currentTime))."""
+    return math.floor(x + 0.5)
+
+
+class V2Manifest:
+    """A V2 manifest (`version == 'v2'`) with the player's target choice and path expansion."""
+
+    texture_type = "baseColor"        # src/V2/player.ts:82
+    texture_tag = "default"           # src/V2/player.ts:83
+
+    def __init__(self, manifest, manifest_path):
+        if manifest.get("version") != "v2":
+            raise ValueError("not a V2 manifest (src/Player.ts:127-132 dispatches on version == 'v2')")
+        self.m, self.path = manifest, manifest_path
+        # playTrack: first geometry target; texture targets sorted by TEXTURE_FORMAT_PRIORITY, first supported one
+        # (isTextureFormatSupported: 'ktx2' always, src/utils.ts:26-32); note the reference compares the target KEY
+        # against format names there, so with ordinary keys the first key wins -- reproduced here.
+        self.geometry_target = next(iter(manifest["geometry"]["targets"]))
+        self.texture_target = next(iter(manifest["texture"]["targets"]))
+        keys = list(manifest["texture"]["targets"])
+        keys.sort(key=lambda k: -TEXTURE_FORMAT_PRIORITY.get(manifest["texture"]["targets"][k]["format"], -1))
+        for k in keys:
+            if k in ("ktx2", "mp4"):
+                self.texture_target = k
+                break
+
+    @classmethod
+    def load(cls, path):
+        with open(path) as fh:
+            return cls(json.load(fh), path)
+
+    # ---- counts (src/V2/player.ts:183-196)
+    @property
+    def geometry(self):
+        return self.m["geometry"]["targets"][self.geometry_target]
+
+    @property
+    def texture(self):
+        return self.m["texture"]["targets"][self.texture_target]
+
+    @property
+    def geometry_frame_count(self):
+        return self.geometry["frameCount"]
+
+    @property
+    def batch_size(self):
+        return self.texture["sequenceSize"]
+
+    @property
+    def texture_segment_count(self):
+        return self.texture["sequenceCount"]
+
+    # ---- URL templates (src/V2/player.ts:141-174)
+    def geometry_url(self, frame_no):
+        tpl = self.m["geometry"]["path"]
+        w = count_hash_char(tpl)
+        subs = {"[target]": self.geometry_target, "[ext]": FORMATS_TO_EXT[self.geometry["format"]], "[" + "#" * w + "]": pad(frame_no, w)}
+        for k, v in subs.items():
+            tpl = tpl.replace(k, v, 1)
+        return get_absolute_url(self.path, tpl)
+
+    def texture_url(self, segment_no):
+        tpl = self.m["texture"]["path"]
+        w = count_hash_char(tpl)
+        subs = {"[target]": self.texture_target, "[type]": self.texture_type, "[tag]": self.texture_tag,
+                "[ext]": FORMATS_TO_EXT[self.texture["format"]], "[" + "#" * w + "]": pad(segment_no, w)}
+        for k, v in subs.items():
+            tpl = tpl.replace(k, v, 1)
+        return get_absolute_url(self.path, tpl)
+
+    # ---- time -> frame / segment / layer (src/V2/player.ts:418-420,446)
+    def frames_at(self, t):
+        gf = js_round(self.geometry["frameRate"] * t)
+        tf = js_round(self.texture["frameRate"] * t)
+        return {"geometry_frame": gf, "texture_frame": tf, "segment": tf // self.batch_size, "layer": tf % self.batch_size}
+
+    # ---- leaky-bucket request window (src/V2/player.ts:272-323): what fetchBuffers asks for at time t
+    def fetch_window(self, t, last_geometry, last_segment, buffer_duration=4):
+        gsize = self.geometry["frameRate"]
+        cur_g = js_round(gsize * t)
+        tsize = math.ceil(self.texture["frameRate"] / self.batch_size)
+        cur_s = js_round(self.texture["frameRate"] * t) // self.batch_size
+        geo, tex = [], []
+        for i in range(buffer_duration):
+            g_end = min(cur_g + (i + 1) * gsize, self.geometry_frame_count - 1)
+            if last_geometry != self.geometry_frame_count - 1 and last_geometry < g_end:
+                geo += list(range(last_geometry + 1, g_end + 1)); last_geometry = g_end
+            s_end = min(cur_s + (i + 1) * tsize, self.texture_segment_count - 1)
+            if last_segment != self.texture_segment_count - 1 and last_segment < s_end:
+                tex += list(range(last_segment + 1, s_end + 1)); last_segment = s_end
+        return geo, tex, last_geometry, last_segment
+
+
+def shard_v2(frame_count, sequence_size, segment_count, world, rank):
+    """Frame sharding for multi-GPU decode: contiguous blocks of whole KTX2 segments (ETC1S P-frames chain
+    inside one file, so a segment is never split); rank r owns segments [r*S/G, (r+1)*S/G) and the geometry frames they
+    cover.  Returns (first_frame, end_frame, first_segment, end_segment)."""
+    s0 = rank * segment_count // world
+    s1 = (rank + 1) * segment_count // world
+    f0 = min(s0 * sequence_size, frame_count)
+    f1 = frame_count if rank == world - 1 else min(s1 * sequence_size, frame_count)
+    return f0, f1, s0, s1
+
+
+class V2Sequence:
+    """A V2 clip on local storage: reads the files the manifest names and decodes ranges through the library."""
+
+    def __init__(self, manifest_path, player):
+        self.man = V2Manifest.load(manifest_path)
+        self.player = player                      # universal-volumetric_b200.V2Player
+
+    def read_geometry(self, frames):
+        return [open(self.man.geometry_url(f), "rb").read() for f in frames]
+
+    def read_textures(self, segments):
+        return [open(self.man.texture_url(s), "rb").read() for s in segments]
+
+    def decode(self, frames, segments, memory=1):
+        """-> (meshMap, textureMap): dicts keyed by frame / segment number (src/V2/player.ts:68-69,328,362)."""
+        g, t = self.player.decode_step_raw(self.read_geometry(frames), self.read_textures(segments), memory)
+        return ({f: g[i] for i, f in enumerate(frames) if g[i].status == 0}, {s: t[i] for i, s in enumerate(segments) if t[i].status == 0})
+
+
+class V1Manifest:
+    """A V1 manifest (src/Interfaces.ts:1-15; writer deprecated/encoder/src/Encoder30.js:155-160)."""
+
+    def __init__(self, manifest, manifest_path):
+        for k in ("maxVertices", "maxTriangles", "frameData", "frameRate"):
+            if k not in manifest:
+                raise ValueError(f"V1 manifest lacks {k}")
+        self.m, self.path = manifest, manifest_path
+
+    @classmethod
+    def load(cls, path):
+        with open(path) as fh:
+            return cls(json.load(fh), path)
+
+    @property
+    def mesh_file(self):
+        """src/V1/player.ts:337: manifestFilePath.replace('.manifest', '.drcs')"""
+        return self.path.replace(".manifest", ".drcs", 1)
+
+    def byte_range(self, frame_start, frame_end):
+        """src/V1/worker.ts:33-40: one Range request covering frames [frame_start, frame_end)."""
+        fd = self.m["frameData"]
+        start = fd[frame_start]["startBytePosition"]
+        last = fd[frame_end - 1]
+        return start, last["startBytePosition"] + last["meshLength"]
+
+    def slices(self, blob, base, frame_start, frame_end):
+        """src/V1/worker.ts:48-56: per-frame slices of the fetched range (each copied, hence aligned)."""
+        out = []
+        for i in range(frame_start, frame_end):
+            fd = self.m["frameData"][i]
+            s = fd["startBytePosition"] - base
+            out.append((fd["frameNumber"], fd["keyframeNumber"], bytes(blob[s:s + fd["meshLength"]])))
+        return out
