@@ -323,6 +323,233 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence(const
     if (status) frame_fail(counts, fi, status);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Valence-mode edgebreaker, second generation: the whole warp runs the state machine redundantly
+// (uniform control flow costs nothing extra) so that lanes can specialise where it saves
+// instructions on the serial chain:
+//   * lanes 0..5 each own one context's symbol stream (eight symbols packed in a 64-bit register, the
+//     next aligned word already prefetched); the context -> symbol step is one shuffle;
+//   * only the two gate vertices' records live in registers (the tip never changes while it is the
+//     tip, so it is written back the moment a vertex becomes the tip: one record store per symbol);
+//   * the record keeps next(left-most corner) instead of the corner itself, so no modulo appears on
+//     the chain; the gate corner is always corner 0 of the previous face and is not state at all;
+//   * faces are staged as 16-byte records in shared memory and written to opp / c2v 32 at a time,
+//     one face per lane (own links, then -- after a warp barrier -- the links into older faces);
+//   * consistency checks accumulate in a sticky flag (all indices stay in range whatever the stream
+//     says) that is examined when the walk ends.
+// S symbols (component merges) flush the staged faces and use the memory path, executed uniformly.
+#define EB2_STAGE 32
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence2(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
+                                                             uint8_t *S, int nframes) {
+    extern __shared__ uint4 eb_smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4 *ring = eb_smem + (size_t)wib * (EB_RING + 128 + EB2_STAGE);
+    int *stk = (int *)(ring + EB_RING);
+    uint4 *stage = ring + EB_RING + 128;
+    const uint32_t fi = blockIdx.x * SERIAL_WARPS + wib;
+    if ((int)fi >= nframes) return;
+    if (frames[fi].status) { if (lane == 0) counts[fi].status = frames[fi].status; return; }
+    if (counts[fi].status || frames[fi].trav != 2) return;
+    const DracoFrame &f = frames[fi];
+    int *opp = (int *)(S + f.o_opp), *c2v = (int *)(S + f.o_c2v), *lmc = (int *)(S + f.o_lmc), *gstk = (int *)(S + f.o_stack);
+    uint8_t *hole = S + f.o_hole; uint4 *vrec = (uint4 *)(S + f.o_val);     // o_val is sized 16 B per vertex slot (see draco_plan.h)
+    int *skey = gstk + f.nsym + 8, *sval = skey + f.nts + 1, *invalid = (int *)(S + f.o_invalid);
+    const int F = (int)f.nf, maxv = (int)(f.nv_enc + f.nsplit), nsym = (int)f.nsym;
+    int nverts = 0, ninv = 0, sp = 0, status = 0;
+    if (nsym > F || nsym < 1) status = UVOL_ERR_CORRUPT;
+
+    // ---- per-lane symbol stream (lanes 0..5); lanes >= 6 answer E forever (used for the very first symbol).
+    // w holds up to eight symbols, pos is the byte index of the next one (counting down), cur the symbol itself.
+    uint32_t wlo = 0x04040404u, whi = 0x04040404u; unsigned long long nxt = 0; int pos = 0x40000007, blk = 0; const unsigned long long *cs8 = nullptr;
+    if (lane < 6) {
+        const int kk = (int)f.ctx[lane].count; cs8 = (const unsigned long long *)(S + f.o_ctxsym[lane]);
+        if (kk <= 0) { wlo = whi = ~0u; }
+        else {
+            blk = (kk - 1) >> 3; pos = kk - 8 * blk - 1;
+            const unsigned long long w0 = cs8[blk]; wlo = (uint32_t)w0; whi = (uint32_t)(w0 >> 32);
+            if (blk > 0) nxt = cs8[blk - 1];
+        }
+    }
+    int cur = (int)(__byte_perm(wlo, whi, (uint32_t)pos) & 255u);
+    const uint32_t *ts = aux + f.ts_off; int ts_top = (int)f.nts, nsa = 0;
+    int next_ts_sid = ts_top > 0 ? nsym - 1 - (int)ts[3 * (ts_top - 1)] : -1;
+    // record: x = next(left-most corner) (or DINV), y = vertex before it on the boundary, z = 2 * valence + on-hole flag
+    int na = 0, pa = 0; int rn_c = 0, rn_p = 0, rn_v = 0, rp_c = 0, rp_p = 0, rp_v = 0;
+    int ctx = 6, lo = -EB_RING, fbase = 0, pend = 0;
+#define VLOAD2(v, C_, P_, V_) do { uint4 u_; if ((v) >= lo) u_ = ring[(v) & (EB_RING - 1)]; else u_ = vrec[(v)]; C_ = (int)u_.x; P_ = (int)u_.y; V_ = (int)u_.z; } while (0)
+#define VSTORE2(v, C_, P_, V_) do { const uint4 u_ = make_uint4((uint32_t)(C_), (uint32_t)(P_), (uint32_t)(V_), 0u); if ((v) >= lo) ring[(v) & (EB_RING - 1)] = u_; vrec[(v)] = u_; } while (0)
+#define EB2_FLUSH() do { \
+        int s_ = 4, x_ = DINV, c_ = 0; \
+        if (lane < pend) { const uint4 r_ = stage[lane]; c_ = 3 * (fbase + lane); s_ = (int)(r_.w >> 28); x_ = (int)(r_.w & 0x0fffffffu); \
+            c2v[c_] = (int)r_.x; c2v[c_ + 1] = (int)r_.y; c2v[c_ + 2] = (int)r_.z; \
+            opp[c_] = DINV; opp[c_ + 1] = (s_ == 0 || s_ == 2) ? c_ - 3 : DINV; opp[c_ + 2] = s_ == 0 ? x_ : (s_ == 3 ? c_ - 3 : DINV); } \
+        __syncwarp(); \
+        if (lane < pend && s_ < 4) { opp[c_ - 3] = s_ == 3 ? c_ + 2 : c_ + 1; if (s_ == 0 && x_ < c_) opp[x_] = c_ + 2; } \
+        __syncwarp(); \
+        fbase += pend; pend = 0; } while (0)
+    int sid = 0;
+    for (; sid < nsym && !status; sid++) {
+        const int s = __shfl_sync(0xffffffffu, cur, ctx);
+        {
+            const bool mine = lane == ctx;
+            if (mine && (pos & 7) == 0) {               // that was the last symbol of this word (one lane, every eighth symbol)
+                if (blk == 0) { wlo = whi = ~0u; pos = 0x40000008; }
+                else { wlo = (uint32_t)nxt; whi = (uint32_t)(nxt >> 32); pos = 8; --blk; if (blk > 0) nxt = cs8[blk - 1]; }
+            }
+            if (mine) pos--;
+            cur = (int)(__byte_perm(wlo, whi, (uint32_t)pos) & 255u);
+        }
+        const int c0 = 3 * sid;
+        int s_rl = s, s_rare = s;                       // opaque copies: keep the dispatch a compare chain ordered by frequency, not a jump table
+        asm volatile("" : "+r"(s_rl)); asm volatile("" : "+r"(s_rare));
+        if (s == 0) {              // C: close the fan at the vertex next to the gate
+            const int vbn = rn_p, b = rn_c;
+            if ((b < 0) | (b == c0 - 3) | (vbn == na) | (vbn == pa)) { status = UVOL_ERR_CORRUPT; break; }
+            int rb_c, rb_p, rb_v; VLOAD2(vbn, rb_c, rb_p, rb_v);
+            stage[pend] = make_uint4((uint32_t)na, (uint32_t)vbn, (uint32_t)pa, (uint32_t)(b & 0x0fffffff));
+            rp_c = c0; rp_p = vbn; rp_v += 2;
+            rn_v &= ~1; VSTORE2(na, rn_c, rn_p, rn_v);
+            na = vbn; rn_c = rb_c; rn_p = rb_p; rn_v = rb_v + 2;
+        } else if (s_rl == 3) {                         // R: new vertex opposite the gate, continue to the left
+            if (nverts >= maxv) { status = UVOL_ERR_CORRUPT; break; }
+            const int nvx = nverts++; lo = nverts - EB_RING;
+            stage[pend] = make_uint4((uint32_t)pa, (uint32_t)na, (uint32_t)nvx, 3u << 28);
+            rp_c = c0 + 1; rp_p = nvx; rp_v += 2; VSTORE2(pa, rp_c, rp_p, rp_v);
+            rn_v += 2;
+            pa = nvx; rp_c = c0; rp_p = na; rp_v = 5;
+        } else if (s_rl == 2) {                         // L
+            if (nverts >= maxv) { status = UVOL_ERR_CORRUPT; break; }
+            const int nvx = nverts++; lo = nverts - EB_RING;
+            stage[pend] = make_uint4((uint32_t)na, (uint32_t)nvx, (uint32_t)pa, 2u << 28);
+            rp_c = c0; rp_p = nvx; rp_v += 2;
+            rn_v += 2; VSTORE2(na, rn_c, rn_p, rn_v);
+            rn_c = c0 + 2; rn_p = na; rn_v = 5; na = nvx;
+        } else if (s_rare == 4) {                       // E: isolated triangle, the old gate goes on the stack
+            if (nverts + 3 > maxv) { status = UVOL_ERR_CORRUPT; break; }
+            const int v0 = nverts, v1 = nverts + 1, v2 = nverts + 2; nverts += 3; lo = nverts - EB_RING;
+            if (sid > 0) { VSTORE2(na, rn_c, rn_p, rn_v); VSTORE2(pa, rp_c, rp_p, rp_v); }
+            stage[pend] = make_uint4((uint32_t)v0, (uint32_t)v1, (uint32_t)v2, 4u << 28);
+            VSTORE2(v0, c0 + 1, v2, 5);
+            na = v1; rn_c = c0 + 2; rn_p = v0; rn_v = 5;
+            pa = v2; rp_c = c0; rp_p = v1; rp_v = 5;
+            if (sp > 0) { if (sp <= 512) stk[sp - 1] = c0 - 3; else gstk[sp - 1] = c0 - 3; }
+            sp++;
+        } else if (s_rare == 1) {                       // S: merge the two topmost components (memory path on lane 0, state broadcast)
+            VSTORE2(na, rn_c, rn_p, rn_v); VSTORE2(pa, rp_c, rp_p, rp_v);
+            EB2_FLUSH();
+            fbase = sid + 1;                            // this face is written directly below
+            if (lane == 0) do {
+                const int b = c0 - 3; sp--;
+                int a2 = -1;
+                for (int k = 0; k < nsa; k++) if (skey[k] == sid) { a2 = sval[k]; sp++; break; }
+                if (a2 < 0) { if (sp == 0) { status = UVOL_ERR_CORRUPT; break; } a2 = sp <= 512 ? stk[sp - 1] : gstk[sp - 1]; }
+                if (a2 == b || opp[a2] >= 0 || opp[b] >= 0) { status = UVOL_ERR_CORRUPT; break; }
+                const int vp = c2v[cprev(a2)], vnx = c2v[cnext(a2)], vbp = pa, vn = na;
+                opp[c0] = DINV; opp[c0 + 2] = a2; opp[a2] = c0 + 2; opp[c0 + 1] = b; opp[b] = c0 + 1;
+                c2v[c0] = vp; c2v[c0 + 1] = vnx; c2v[c0 + 2] = vbp;
+                int t_c, t_p, t_v;
+                VLOAD2(vbp, t_c, t_p, t_v); VSTORE2(vbp, c0, vnx, t_v);
+                int p_c, p_p, p_v, n_c, n_p, n_v;
+                VLOAD2(vp, p_c, p_p, p_v); VLOAD2(vn, n_c, n_p, n_v);
+                p_v = ((p_v >> 1) + (n_v >> 1)) * 2 + (p_v & 1); VSTORE2(vp, n_c, n_p, p_v);
+                int cn = cnext(b); const int first = cn; int guard = 0;
+                while (cn >= 0) {
+                    c2v[cn] = vp;
+                    const int cx = cnext(cn), x = c2v[cx];
+                    if (x != vn) { int x_c, x_p, x_v; VLOAD2(x, x_c, x_p, x_v); if (x_c == cnext(cx)) VSTORE2(x, x_c, vp, x_v); }
+                    cn = b_swl(opp, cn);
+                    if (cn == first || ++guard > 3 * F) { status = UVOL_ERR_CORRUPT; break; }
+                }
+                if (status) break;
+                VSTORE2(vn, DINV, n_p, n_v);
+                invalid[ninv] = vn;
+                na = vnx; pa = vbp;
+                VLOAD2(na, rn_c, rn_p, rn_v); VLOAD2(pa, rp_c, rp_p, rp_v);
+                rn_v += 2; rp_v += 2;                   // the new tip (vp) is already in memory
+            } while (0);
+            __syncwarp();
+            ninv++;
+            status = __shfl_sync(0xffffffffu, status, 0); sp = __shfl_sync(0xffffffffu, sp, 0);
+            na = __shfl_sync(0xffffffffu, na, 0); pa = __shfl_sync(0xffffffffu, pa, 0);
+            rn_c = __shfl_sync(0xffffffffu, rn_c, 0); rn_p = __shfl_sync(0xffffffffu, rn_p, 0); rn_v = __shfl_sync(0xffffffffu, rn_v, 0);
+            rp_c = __shfl_sync(0xffffffffu, rp_c, 0); rp_p = __shfl_sync(0xffffffffu, rp_p, 0); rp_v = __shfl_sync(0xffffffffu, rp_v, 0);
+            if (status) break;
+            pend = -1;                                  // ++ below makes it 0: nothing staged for this face
+        } else { status = UVOL_ERR_CORRUPT; break; }
+        if (++pend == EB2_STAGE) EB2_FLUSH();
+        { int v = rn_v >> 1; v = v < 2 ? 2 : (v > 7 ? 7 : v); ctx = v - 2; }
+        if (sid == next_ts_sid) {                       // topology split events registered on this symbol (A.3)
+            if (s >= 2) {
+                while (ts_top > 0 && ts[3 * (ts_top - 1)] == (uint32_t)(nsym - sid - 1)) {
+                    --ts_top;
+                    if (lane == 0) { skey[nsa] = nsym - (int)ts[3 * ts_top + 1] - 1; sval[nsa] = ts[3 * ts_top + 2] == 1 ? c0 + 1 : c0 + 2; }
+                    nsa++;
+                }
+                __syncwarp();
+            }
+            next_ts_sid = ts_top > 0 ? nsym - 1 - (int)ts[3 * (ts_top - 1)] : -1;
+        }
+    }
+    if (!status) {
+        VSTORE2(na, rn_c, rn_p, rn_v); VSTORE2(pa, rp_c, rp_p, rp_v);
+        EB2_FLUSH();
+        if (sp > 0) { if (sp <= 512) stk[sp - 1] = 3 * (nsym - 1); else gstk[sp - 1] = 3 * (nsym - 1); }
+    }
+    __syncwarp();
+#undef VLOAD2
+#undef VSTORE2
+    int numf = nsym;
+    // records -> the plain arrays the later kernels read (all lanes)
+    if (!status) for (int v = lane; v < nverts; v += 32) { const uint4 u = vrec[v]; const int c = (int)u.x; lmc[v] = c < 0 ? DINV : cprev(c); hole[v] = (uint8_t)(u.z & 1u); }
+    __syncwarp();
+    if (lane != 0) return;
+    if (!status) {
+        // start faces (one rABS bit per remaining stack entry), then fold isolated vertices away
+        if (sp > 0) {
+            Rabs sf;
+            if (!rabs_init(sf, blob + f.file_off, f.start_faces)) status = UVOL_ERR_CORRUPT;
+            while (!status && sp > 0) {
+                const int corner = sp <= 512 ? stk[sp - 1] : gstk[sp - 1]; sp--;
+                if (rabs_bit(sf)) {
+                    const int a = corner, vn = c2v[cnext(a)];
+                    if (lmc[vn] < 0) { status = UVOL_ERR_CORRUPT; break; }
+                    const int cb = cnext(lmc[vn]), vx = c2v[cnext(cb)];
+                    if (lmc[vx] < 0) { status = UVOL_ERR_CORRUPT; break; }
+                    const int cc = cnext(lmc[vx]);
+                    if (a == cb || cb == cc || a == cc || opp[a] >= 0 || opp[cb] >= 0 || opp[cc] >= 0 || numf >= F) { status = UVOL_ERR_CORRUPT; break; }
+                    const int vp = c2v[cnext(cc)], nc = 3 * numf++;
+                    opp[nc] = a; opp[a] = nc; opp[nc + 1] = cb; opp[cb] = nc + 1; opp[nc + 2] = cc; opp[cc] = nc + 2;
+                    c2v[nc] = vx; c2v[nc + 1] = vp; c2v[nc + 2] = vn;
+                    hole[vx] = 0; hole[vp] = 0; hole[vn] = 0;
+                }
+            }
+        }
+        if (!status && numf != F) status = UVOL_ERR_CORRUPT;
+        if (!status) {
+            int num_vertices = nverts;
+            for (int k = 0; k < ninv && !status; k++) {
+                const int iv = invalid[k];
+                int src = num_vertices - 1;
+                while (src >= 0 && lmc[src] == DINV) src = --num_vertices - 1;
+                if (src < iv) continue;
+                const int cs = lmc[src]; int c = cs, left = 1, guard = 0;
+                while (c >= 0) {
+                    int nx;
+                    if (left) { nx = b_swl(opp, c); if (nx < 0) { nx = b_swr(opp, cs); left = 0; } else if (nx == cs) nx = DINV; }
+                    else nx = b_swr(opp, c);
+                    if (c2v[c] != src || ++guard > 3 * F) { status = UVOL_ERR_CORRUPT; break; }
+                    c2v[c] = iv; c = nx;
+                }
+                lmc[iv] = lmc[src]; lmc[src] = DINV;
+                hole[iv] = hole[src]; hole[src] = 0;
+                num_vertices--;
+            }
+        }
+    }
+    counts[fi].num_vertex_slots = (uint32_t)nverts; counts[fi].expected[0] = (uint32_t)(nverts - ninv);
+    if (status) frame_fail(counts, fi, status);
+}
+
 // Attribute seams: one CTA per frame.  The k-th bit of each seam stream belongs to the k-th corner
 // (in corner order) whose opposite face is not older than its own; a ballot-based block scan turns
 // that into a parallel lookup.
@@ -972,6 +1199,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         const size_t smMax = smA > smB ? smA : smB;
         if (smMax > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_rans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smMax));
         UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB_RING + 128) * 16)));
+        UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB_RING + 128 + EB2_STAGE) * 16)));
     }
     // ---- phase 1.  The seam-bit runs depend only on the file bytes: they run on the side stream s1
     // next to the context-symbol runs and the connectivity walk.
@@ -984,7 +1212,12 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<nblk(B.j_rabsA - B.j_ransA), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + B.j_ransA, B.j_rabsA - B.j_ransA, rans_words(B.max_alpha_ctx)); launches++; }
     stamp("rans_ctx");
     stamp("rabs_seams(s1)"); i_seams = ev - 2;                                     // (stage slot of rabs_seams: timed on s1, filled in below)
-    if (B.any_valence) { k_edgebreaker_valence<<<nblk(n), 32 * SERIAL_WARPS, (size_t)SERIAL_WARPS * (EB_RING + 128) * 16, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
+    if (B.any_valence) {
+        static const bool eb_v1 = getenv("UVOL_EB_V1") != nullptr;
+        if (eb_v1) k_edgebreaker_valence<<<nblk(n), 32 * SERIAL_WARPS, (size_t)SERIAL_WARPS * (EB_RING + 128) * 16, st>>>(dF, dC, dBlob, dAux, dS, n);
+        else k_edgebreaker_valence2<<<nblk(n), 32 * SERIAL_WARPS, (size_t)SERIAL_WARPS * (EB_RING + 128 + EB2_STAGE) * 16, st>>>(dF, dC, dBlob, dAux, dS, n);
+        launches++;
+    }
     if (B.any_standard) { k_edgebreaker<<<nblk(n), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
     stamp("edgebreaker");
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[1], 0));

@@ -22,7 +22,7 @@ static inline void draco_plan_phase1(std::vector<DracoFrame> &frames, DracoPlan 
         f.o_lmc = plan_take(s, maxv * 4); f.o_val = plan_take(s, maxv * 16); f.o_hole = plan_take(s, maxv);   // o_val: int valences (generic path) or 16 B vertex records (valence path)
         f.o_stack = plan_take(s, ((uint64_t)f.nsym + 8) * 4 + ((uint64_t)f.nts + 1) * 8);
         f.o_invalid = plan_take(s, ((uint64_t)f.nsplit + 8) * 4);
-        for (int i = 0; i < 6; i++) f.o_ctxsym[i] = plan_take(s, (uint64_t)f.ctx[i].count + 4);
+        for (int i = 0; i < 6; i++) f.o_ctxsym[i] = plan_take(s, (uint64_t)f.ctx[i].count + 16);   // read back to front in aligned 8-byte words
         for (uint32_t i = 0; i < f.nad; i++) {
             f.o_seambits[i] = plan_take(s, C / 2 + 8);
             f.o_ac2v[i] = plan_take(s, C * 4);
