@@ -21,7 +21,9 @@ namespace {
 
 struct TexState { int32_t status; uint32_t hist_size; };
 
-#define SERIAL_WARPS 4        // one unit per warp, four warps per block: spreads the serial walkers over the SM's four schedulers
+#ifndef SERIAL_WARPS
+#define SERIAL_WARPS 1        // one unit per warp, one warp per block (small blocks pack around the geometry stream's blocks)
+#endif
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_basis_globals(const Ktx2File *files, TexState *state, const uint8_t *blob, uint8_t *S, int nfiles) {
     const uint32_t fi = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if ((int)fi >= nfiles || (threadIdx.x & 31) != 0) return;

@@ -31,9 +31,12 @@ __device__ __forceinline__ void frame_fail(DracoCounts *counts, uint32_t f, int 
 // first-symbol index in shared memory, then lane 0 walks the run (strictly serial state chain).
 // what: 0..5 = valence context i (u8 out) ; 16+j = attribute j (int32 out, zig-zag unless the
 // transform yields positive corrections).
-// All serial kernels use SERIAL_WARPS warps per block, one unit of work per warp: single-warp blocks
-// would all be scheduled on the same SM sub-partition (warp id % 4) and contend for one issue port.
-#define SERIAL_WARPS 4
+// All serial kernels give one unit of work to one warp, SERIAL_WARPS warps per block.  One warp per block keeps
+// the shared-memory footprint of a block small, so the blocks of the concurrently running stages (geometry main
+// stream, entropy side stream, texture stream) pack onto the SMs without forcing a second wave.
+#ifndef SERIAL_WARPS
+#define SERIAL_WARPS 1
+#endif
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
                                              uint8_t *scratch, uint8_t *scratch2, const Job *jobs, int njobs, int smem_words_per_warp) {
     extern __shared__ uint32_t smem_all[];
@@ -338,14 +341,15 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence(const
 //   * consistency checks accumulate in a sticky flag (all indices stay in range whatever the stream
 //     says) that is examined when the walk ends.
 // S symbols (component merges) flush the staged faces and use the memory path, executed uniformly.
+#define EB2_RING 1024
 #define EB2_STAGE 32
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence2(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
                                                              uint8_t *S, int nframes) {
     extern __shared__ uint4 eb_smem[];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint4 *ring = eb_smem + (size_t)wib * (EB_RING + 128 + EB2_STAGE);
-    int *stk = (int *)(ring + EB_RING);
-    uint4 *stage = ring + EB_RING + 128;
+    uint4 *ring = eb_smem + (size_t)wib * (EB2_RING + 128 + EB2_STAGE);
+    int *stk = (int *)(ring + EB2_RING);
+    uint4 *stage = ring + EB2_RING + 128;
     const uint32_t fi = blockIdx.x * SERIAL_WARPS + wib;
     if ((int)fi >= nframes) return;
     if (frames[fi].status) { if (lane == 0) counts[fi].status = frames[fi].status; return; }
@@ -375,9 +379,9 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence2(cons
     int next_ts_sid = ts_top > 0 ? nsym - 1 - (int)ts[3 * (ts_top - 1)] : -1;
     // record: x = next(left-most corner) (or DINV), y = vertex before it on the boundary, z = 2 * valence + on-hole flag
     int na = 0, pa = 0; int rn_c = 0, rn_p = 0, rn_v = 0, rp_c = 0, rp_p = 0, rp_v = 0;
-    int ctx = 6, lo = -EB_RING, fbase = 0, pend = 0;
-#define VLOAD2(v, C_, P_, V_) do { uint4 u_; if ((v) >= lo) u_ = ring[(v) & (EB_RING - 1)]; else u_ = vrec[(v)]; C_ = (int)u_.x; P_ = (int)u_.y; V_ = (int)u_.z; } while (0)
-#define VSTORE2(v, C_, P_, V_) do { const uint4 u_ = make_uint4((uint32_t)(C_), (uint32_t)(P_), (uint32_t)(V_), 0u); if ((v) >= lo) ring[(v) & (EB_RING - 1)] = u_; vrec[(v)] = u_; } while (0)
+    int ctx = 6, lo = -EB2_RING, fbase = 0, pend = 0;
+#define VLOAD2(v, C_, P_, V_) do { uint4 u_; if ((v) >= lo) u_ = ring[(v) & (EB2_RING - 1)]; else u_ = vrec[(v)]; C_ = (int)u_.x; P_ = (int)u_.y; V_ = (int)u_.z; } while (0)
+#define VSTORE2(v, C_, P_, V_) do { const uint4 u_ = make_uint4((uint32_t)(C_), (uint32_t)(P_), (uint32_t)(V_), 0u); if ((v) >= lo) ring[(v) & (EB2_RING - 1)] = u_; vrec[(v)] = u_; } while (0)
 #define EB2_FLUSH() do { \
         int s_ = 4, x_ = DINV, c_ = 0; \
         if (lane < pend) { const uint4 r_ = stage[lane]; c_ = 3 * (fbase + lane); s_ = (int)(r_.w >> 28); x_ = (int)(r_.w & 0x0fffffffu); \
@@ -412,21 +416,21 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence2(cons
             na = vbn; rn_c = rb_c; rn_p = rb_p; rn_v = rb_v + 2;
         } else if (s_rl == 3) {                         // R: new vertex opposite the gate, continue to the left
             if (nverts >= maxv) { status = UVOL_ERR_CORRUPT; break; }
-            const int nvx = nverts++; lo = nverts - EB_RING;
+            const int nvx = nverts++; lo = nverts - EB2_RING;
             stage[pend] = make_uint4((uint32_t)pa, (uint32_t)na, (uint32_t)nvx, 3u << 28);
             rp_c = c0 + 1; rp_p = nvx; rp_v += 2; VSTORE2(pa, rp_c, rp_p, rp_v);
             rn_v += 2;
             pa = nvx; rp_c = c0; rp_p = na; rp_v = 5;
         } else if (s_rl == 2) {                         // L
             if (nverts >= maxv) { status = UVOL_ERR_CORRUPT; break; }
-            const int nvx = nverts++; lo = nverts - EB_RING;
+            const int nvx = nverts++; lo = nverts - EB2_RING;
             stage[pend] = make_uint4((uint32_t)na, (uint32_t)nvx, (uint32_t)pa, 2u << 28);
             rp_c = c0; rp_p = nvx; rp_v += 2;
             rn_v += 2; VSTORE2(na, rn_c, rn_p, rn_v);
             rn_c = c0 + 2; rn_p = na; rn_v = 5; na = nvx;
         } else if (s_rare == 4) {                       // E: isolated triangle, the old gate goes on the stack
             if (nverts + 3 > maxv) { status = UVOL_ERR_CORRUPT; break; }
-            const int v0 = nverts, v1 = nverts + 1, v2 = nverts + 2; nverts += 3; lo = nverts - EB_RING;
+            const int v0 = nverts, v1 = nverts + 1, v2 = nverts + 2; nverts += 3; lo = nverts - EB2_RING;
             if (sid > 0) { VSTORE2(na, rn_c, rn_p, rn_v); VSTORE2(pa, rp_c, rp_p, rp_v); }
             stage[pend] = make_uint4((uint32_t)v0, (uint32_t)v1, (uint32_t)v2, 4u << 28);
             VSTORE2(v0, c0 + 1, v2, 5);
@@ -729,11 +733,12 @@ __global__ void __launch_bounds__(128) k_face_entries(const DracoFrame *frames, 
 // transitions really lead to the next lane's corner is committed at once, and the first lane that deviates
 // (pop, push, turn) hands its exact outcome to the next step.  Output order is identical to the serial walk.
 #define TRAV_STACK 512
+#define TRAV_WARPS 1          // one walk per block: 21 KB of bitmaps each, so the blocks pack around whatever else is resident (entropy runs, texture slices)
 __device__ __forceinline__ unsigned face_of(int c) { return __umulhi((unsigned)c, 0xAAAAAAABu) >> 1; }
-__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, uint8_t *Z2,
+__global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, uint8_t *Z2,
                                                  const Job *jobs, int njobs, int fwords_max, int vwords_max) {
     extern __shared__ uint32_t sm_all[];
-    const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+    const int ji = blockIdx.x * TRAV_WARPS + (threadIdx.x >> 5);
     if (ji >= njobs) return;
     uint32_t *sm = sm_all + (size_t)(threadIdx.x >> 5) * (fwords_max + vwords_max + TRAV_STACK);
     const Job jb = jobs[ji];
@@ -1199,7 +1204,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         const size_t smMax = smA > smB ? smA : smB;
         if (smMax > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_rans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smMax));
         UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB_RING + 128) * 16)));
-        UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB_RING + 128 + EB2_STAGE) * 16)));
+        UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB2_RING + 128 + EB2_STAGE) * 16)));
     }
     // ---- phase 1.  The seam-bit runs depend only on the file bytes: they run on the side stream s1
     // next to the context-symbol runs and the connectivity walk.
@@ -1215,7 +1220,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     if (B.any_valence) {
         static const bool eb_v1 = getenv("UVOL_EB_V1") != nullptr;
         if (eb_v1) k_edgebreaker_valence<<<nblk(n), 32 * SERIAL_WARPS, (size_t)SERIAL_WARPS * (EB_RING + 128) * 16, st>>>(dF, dC, dBlob, dAux, dS, n);
-        else k_edgebreaker_valence2<<<nblk(n), 32 * SERIAL_WARPS, (size_t)SERIAL_WARPS * (EB_RING + 128 + EB2_STAGE) * 16, st>>>(dF, dC, dBlob, dAux, dS, n);
+        else k_edgebreaker_valence2<<<nblk(n), 32 * SERIAL_WARPS, (size_t)SERIAL_WARPS * (EB2_RING + 128 + EB2_STAGE) * 16, st>>>(dF, dC, dBlob, dAux, dS, n);
         launches++;
     }
     if (B.any_standard) { k_edgebreaker<<<nblk(n), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
@@ -1267,10 +1272,10 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         k_face_entries<<<dim3((B.maxF + 127) / 128, ntj), 128, 0, st>>>(dF, dC, dS2, dJ + B.j_trav); launches++;
         stamp("corner_records");
         const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((maxN + 31) / 32 + 4) & ~3u);
-        const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_STACK * 4) * SERIAL_WARPS;
+        const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_STACK * 4) * TRAV_WARPS;
         if (smem > 200 * 1024) { ctx->err = "mesh too large for the traversal bitmaps"; return UVOL_ERR_UNSUPPORTED; }
         if (smem > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_traverse<<<nblk(ntj), 32 * SERIAL_WARPS, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords); launches++;
+        k_traverse<<<(ntj + TRAV_WARPS - 1) / TRAV_WARPS, 32 * TRAV_WARPS, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords); launches++;
     }
     stamp("traverse");
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[3], 0));
