@@ -19,7 +19,10 @@
 namespace {
 
 struct Job { uint32_t frame; int32_t what; };
-struct UvPrepD { int32_t nd, pd; long long pn2, dot, ns; double rcp; };      // UvPrep + reciprocal of |PN|^2 (40 bytes)
+// UvPrep for the serial chain (40 bytes).  rcp > 0: pn2 / dot / ns are exact doubles and every product of the chain stays
+// below 2^52 (fast path, all arithmetic exact in fp64); rcp == 0: |PN|^2 == 0; rcp < 0: the three fields hold the
+// long long bit patterns (64-bit integer path).
+struct UvPrepD { int32_t nd, pd; double pn2, dot, ns, rcp; };
 
 __device__ __forceinline__ bool frame_dead(const DracoFrame *frames, const DracoCounts *counts, uint32_t f) {
     return frames[f].status != 0 || counts[f].status != 0;
@@ -37,6 +40,7 @@ __device__ __forceinline__ void frame_fail(DracoCounts *counts, uint32_t f, int 
 #ifndef SERIAL_WARPS
 #define SERIAL_WARPS 1
 #endif
+#define RANS_LUT_BITS 12
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
                                              uint8_t *scratch, uint8_t *scratch2, const Job *jobs, int njobs, int smem_words_per_warp) {
     extern __shared__ uint32_t smem_all[];
@@ -55,8 +59,12 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *fr
         mode = (a.pred != -2 && (a.xform == 2 || a.xform == 3)) ? 2 : 1;
         count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
     }
-    const uint32_t A = s.alphabet, lane = threadIdx.x & 31;
-    uint32_t *cum = smem; uint16_t *bucket = (uint16_t *)(smem + A + 1);
+    // Tables in shared memory (built by the whole warp): sf[s] = {first slot, frequency} of symbol s (sf[A].x = total) and
+    // a 2^min(pb,12)-entry index "first symbol whose range reaches into this bucket", so that the symbol search on the
+    // serial chain is one table load plus one 8-byte load in the common case (exact when pb <= 12).
+    const uint32_t A = s.alphabet, pb = s.pb, lane = threadIdx.x & 31;
+    const uint32_t lb = pb < RANS_LUT_BITS ? pb : RANS_LUT_BITS;
+    uint2 *sf = (uint2 *)smem; uint16_t *bucket = (uint16_t *)(sf + A + 1);
     const uint32_t *prob = aux + s.prob_off;
     uint32_t run = 0;
     for (uint32_t base = 0; base < A; base += 32) {
@@ -64,18 +72,51 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *fr
         uint32_t inc = p;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
-        if (base + lane < A) cum[base + lane] = run + inc - p;
+        if (base + lane < A) sf[base + lane] = make_uint2(run + inc - p, p);
         run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) cum[A] = run;
+    if (lane == 0) sf[A] = make_uint2(run, 0u);
     __syncwarp();
-    if (run != (1u << s.pb)) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
-    for (uint32_t b = lane; b < 256; b += 32) bucket[b] = (uint16_t)rans_bucket_symbol(cum, A, b << (s.pb - 8));
+    if (run != (1u << pb)) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
+    for (uint32_t b = lane; b < (1u << lb); b += 32) {          // first s with cum[s+1] > b << (pb - lb)
+        const uint32_t target = b << (pb - lb);
+        uint32_t lo = 0, hi = A - 1;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sf[mid + 1].x > target) hi = mid; else lo = mid + 1; }
+        bucket[b] = (uint16_t)lo;
+    }
     __syncwarp();
-    if (lane == 0) {
-        RansTables t{cum, bucket, A, s.pb};
-        const int rc = rans_decode_run(file + s.data_off, s.data_len, t, count, mode, out);
-        if (rc) frame_fail(counts, jb.frame, rc);
+    if (lane != 0 || count == 0) return;
+    // ---- the run (lane 0).  Bytes are consumed back to front through a register window of aligned 32-bit words,
+    // the next word always prefetched, so renormalisation never waits on memory.
+    const uint8_t *data = file + s.data_off; const uint32_t nbytes = s.data_len;
+    if (nbytes == 0) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
+    const uint32_t prec = 1u << pb, lbase = prec * 4u, shift = pb - lb;
+    const unsigned x = data[nbytes - 1] >> 6, k = x + 1;
+    if (nbytes < k) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
+    uint32_t st = 0;
+    for (unsigned i = 0; i < k; i++) st |= (uint32_t)data[nbytes - k + i] << (8 * i);
+    st &= (1u << (8 * k - 2)) - 1u;
+    st += lbase;
+    const uint8_t *p = data + (nbytes - k);                   // next byte to consume is p[-1]
+    const uint32_t *wp = (const uint32_t *)((uintptr_t)(p - 1) & ~(uintptr_t)3);     // aligned word holding it (the blob is padded on both sides)
+    uint32_t w = p > data ? wp[0] : 0u, wn = p > data ? wp[-1] : 0u;
+    uint32_t bi = (uint32_t)((uintptr_t)(p - 1) & 3);         // byte index inside w
+    int left = (int)(nbytes - k);                             // bytes not yet consumed
+    uint8_t *o8 = (uint8_t *)out; int32_t *o32 = (int32_t *)out;
+    for (uint32_t i = 0; i < count; i++) {
+        while (st < lbase && left > 0) {
+            st = st * 256u + (__byte_perm(w, 0u, bi | 0x4440u));
+            left--;
+            if (bi == 0) { w = wn; --wp; wn = wp[-1]; bi = 3; } else bi--;
+        }
+        const uint32_t q = st >> pb, rem = st & (prec - 1);
+        uint32_t sy = bucket[rem >> shift];
+        uint2 e = sf[sy];
+        while (rem >= e.x + e.y) { sy++; e = sf[sy]; }
+        st = q * e.y + rem - e.x;
+        if (mode == 0) o8[i] = (uint8_t)sy;
+        else if (mode == 1) o32[i] = (sy & 1) ? -(int32_t)(sy >> 1) - 1 : (int32_t)(sy >> 1);
+        else o32[i] = (int32_t)sy;
     }
 }
 
@@ -982,7 +1023,13 @@ __global__ void __launch_bounds__(128) k_uv_prepare(const DracoFrame *frames, co
     UvPrep q;
     uv_prepare(p, tv, (const int *)(S2 + f.o_d2c[t]), (const int *)(Z2 + f.o_v2d[t]), (const int *)(Z2 + f.o_v2d[0]),
                (const int32_t *)(S2 + f.o_val_attr[f.pos_attr]), q);
-    UvPrepD o; o.nd = q.nd; o.pd = q.pd; o.pn2 = q.pn2; o.dot = q.dot; o.ns = q.ns; o.rcp = q.pn2 ? 1.0 / (double)q.pn2 : 0.0;
+    UvPrepD o; o.nd = q.nd; o.pd = q.pd; o.pn2 = o.dot = o.ns = o.rcp = 0.0;
+    if (q.pn2 != 0) {
+        const double vmax = fmax(fabs((double)f.attr[j].wmin), fabs((double)f.attr[j].wmax)) + 1.0, lim = 2251799813685248.0 /* 2^51 */;
+        const double dpn2 = (double)q.pn2, ddot = (double)q.dot, dns = (double)q.ns;
+        if ((fabs(ddot) + dns) * 2.0 * vmax < lim && dpn2 * vmax < lim && dpn2 < lim) { o.pn2 = dpn2; o.dot = ddot; o.ns = dns; o.rcp = 1.0 / dpn2; }
+        else { o.pn2 = __longlong_as_double(q.pn2); o.dot = __longlong_as_double(q.dot); o.ns = __longlong_as_double(q.ns); o.rcp = -1.0; }
+    }
     ((UvPrepD *)(S2 + f.o_par[j]))[p] = o;
 }
 
@@ -993,16 +1040,19 @@ __global__ void __launch_bounds__(128) k_uv_prepare(const DracoFrame *frames, co
 // values are mirrored in a shared-memory ring, and the two truncating 64-bit divisions per entry are done as
 // double-precision multiplies by the prepared reciprocal with an exact remainder fix-up.
 #define UV_RING 1024
-__device__ __forceinline__ long long div_trunc_rcp(long long a, long long b, double rcp) {     // b > 0; exact C++ a / b
-    long long q = (long long)((double)a * rcp);
-    long long r = a - q * b;
-    if (a >= 0) { while (r < 0) { q--; r += b; } while (r >= b) { q++; r -= b; } }
-    else { while (r > 0) { q++; r -= b; } while (r <= -b) { q--; r += b; } }
-    return q;
+// trunc((n * pn2 + y) / pn2) for integers held exactly in doubles (|y|, |n * pn2| < 2^52): floor(y / pn2) by reciprocal
+// multiply with a one-step exact remainder fix-up, then the toward-zero correction from the sign of the total.
+__device__ __forceinline__ int32_t uv_div_fast(int32_t n, double y, double pn2, double rcp) {
+    double qd = floor(y * rcp), rd = fma(-qd, pn2, y);
+    if (rd < 0.0) { qd -= 1.0; rd += pn2; }
+    if (rd >= pn2) { qd += 1.0; rd -= pn2; }
+    const double total = fma((double)n, pn2, y);
+    const int32_t adj = (total < 0.0 && rd != 0.0) ? 1 : 0;
+    return (int32_t)((uint32_t)(unsigned long long)(long long)qd + (uint32_t)n + (uint32_t)adj);
 }
 struct UvTile { UvPrepD prep[32]; int32_t corr[64]; uint8_t orient[32]; int pad[8]; };
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_uv(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, const Job *jobs, int njobs) {
-    __shared__ int ring_all[SERIAL_WARPS][UV_RING * 2];
+    __shared__ __align__(16) int ring_all[SERIAL_WARPS][UV_RING * 2];
     __shared__ UvTile tile_all[SERIAL_WARPS];
     const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if (ji >= njobs) return;
@@ -1027,30 +1077,36 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_uv(const DracoFra
                 const int p = base + i; const UvPrepD q = T.prep[i];
                 int pred0, pred1; bool have = false;
                 if (q.pd < p && q.nd < p && q.pd >= 0 && q.nd >= 0) {
-                    const int n0 = q.nd > p - UV_RING ? ring[(q.nd & (UV_RING - 1)) * 2] : uv[q.nd * 2], n1 = q.nd > p - UV_RING ? ring[(q.nd & (UV_RING - 1)) * 2 + 1] : uv[q.nd * 2 + 1];
-                    const int p0 = q.pd > p - UV_RING ? ring[(q.pd & (UV_RING - 1)) * 2] : uv[q.pd * 2], p1 = q.pd > p - UV_RING ? ring[(q.pd & (UV_RING - 1)) * 2 + 1] : uv[q.pd * 2 + 1];
+                    const int2 nv = q.nd > p - UV_RING ? ((const int2 *)ring)[q.nd & (UV_RING - 1)] : ((const int2 *)uv)[q.nd];
+                    const int2 pv = q.pd > p - UV_RING ? ((const int2 *)ring)[q.pd & (UV_RING - 1)] : ((const int2 *)uv)[q.pd];
+                    const int n0 = nv.x, n1 = nv.y, p0 = pv.x, p1 = pv.y;
                     if (n0 == p0 && n1 == p1) { pred0 = p0; pred1 = p1; have = true; }
-                    else if (q.pn2 != 0) {
-                        const long long d0 = p0 - n0, d1 = p1 - n1;
-                        const long long x0 = (long long)n0 * q.pn2 + q.dot * d0, x1 = (long long)n1 * q.pn2 + q.dot * d1;
-                        const long long c0 = d1 * q.ns, c1 = -d0 * q.ns;
+                    else if (q.rcp != 0.0) {
                         if (nor <= 0) { status = UVOL_ERR_CORRUPT; break; }
                         --nor;
                         const bool o = T.orient[nor - (nor0 - 32)] != 0;
-                        const long long a0 = o ? x0 + c0 : x0 - c0, a1 = o ? x1 + c1 : x1 - c1;
-                        long long r0, r1;
-                        if ((a0 < 0 ? -a0 : a0) < (1ll << 51) && (a1 < 0 ? -a1 : a1) < (1ll << 51)) { r0 = div_trunc_rcp(a0, q.pn2, q.rcp); r1 = div_trunc_rcp(a1, q.pn2, q.rcp); }
-                        else { r0 = a0 / q.pn2; r1 = a1 / q.pn2; }
-                        pred0 = (int32_t)r0; pred1 = (int32_t)r1; have = true;
+                        if (q.rcp > 0.0) {              // exact fp64: y = dot*d +- ns*d', pred = n + trunc-corrected floor(y / pn2)
+                            const double dd0 = (double)(p0 - n0), dd1 = (double)(p1 - n1), sns = o ? q.ns : -q.ns;
+                            const double y0 = fma(q.dot, dd0, sns * dd1), y1 = fma(q.dot, dd1, -(sns * dd0));
+                            pred0 = uv_div_fast(n0, y0, q.pn2, q.rcp); pred1 = uv_div_fast(n1, y1, q.pn2, q.rcp);
+                        } else {
+                            const long long pn2 = __double_as_longlong(q.pn2), dot = __double_as_longlong(q.dot), ns = __double_as_longlong(q.ns);
+                            const long long d0 = (long long)p0 - n0, d1 = (long long)p1 - n1;
+                            const long long x0 = (long long)n0 * pn2 + dot * d0, x1 = (long long)n1 * pn2 + dot * d1;
+                            const long long c0 = d1 * ns, c1 = -d0 * ns;
+                            const long long a0 = o ? x0 + c0 : x0 - c0, a1 = o ? x1 + c1 : x1 - c1;
+                            pred0 = (int32_t)(a0 / pn2); pred1 = (int32_t)(a1 / pn2);
+                        }
+                        have = true;
                     }
                 }
                 if (!have) {
-                    if (q.nd < p && q.nd >= 0) { pred0 = q.nd > p - UV_RING ? ring[(q.nd & (UV_RING - 1)) * 2] : uv[q.nd * 2]; pred1 = q.nd > p - UV_RING ? ring[(q.nd & (UV_RING - 1)) * 2 + 1] : uv[q.nd * 2 + 1]; }
-                    else if (p > 0) { pred0 = ring[((p - 1) & (UV_RING - 1)) * 2]; pred1 = ring[((p - 1) & (UV_RING - 1)) * 2 + 1]; }
+                    if (q.nd < p && q.nd >= 0) { const int2 nv = q.nd > p - UV_RING ? ((const int2 *)ring)[q.nd & (UV_RING - 1)] : ((const int2 *)uv)[q.nd]; pred0 = nv.x; pred1 = nv.y; }
+                    else if (p > 0) { const int2 lv = ((const int2 *)ring)[(p - 1) & (UV_RING - 1)]; pred0 = lv.x; pred1 = lv.y; }
                     else { pred0 = pred1 = 0; }
                 }
                 const int32_t u0 = wrap_value(pred0, T.corr[2 * i], mn, mx), u1 = wrap_value(pred1, T.corr[2 * i + 1], mn, mx);
-                ring[(p & (UV_RING - 1)) * 2] = u0; ring[(p & (UV_RING - 1)) * 2 + 1] = u1;
+                ((int2 *)ring)[p & (UV_RING - 1)] = make_int2(u0, u1);
                 *(int2 *)(uv + 2 * p) = make_int2(u0, u1);
             }
         }
@@ -1196,12 +1252,13 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     const uint8_t *dBlob = (const uint8_t *)ctx->d_blob.p; const uint32_t *dAux = (const uint32_t *)ctx->d_aux.p;
     uint8_t *dS = (uint8_t *)ctx->d_scratch.p, *dZ = (uint8_t *)ctx->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
     uint32_t launches = 0;
-    auto rans_words = [](uint32_t alphabet) { return (int)(((size_t)(alphabet + 1) * 4 + 257 * 2 + 16 + 15) / 16 * 4); };
+    auto rans_words = [](uint32_t alphabet) { return (int)(((size_t)(alphabet + 1) * 8 + (2u << RANS_LUT_BITS) + 16 + 15) / 16 * 4); };
     auto rans_smem = [&](uint32_t alphabet) { return (size_t)rans_words(alphabet) * 4 * SERIAL_WARPS; };
     auto nblk = [](int jobs) { return (unsigned)((jobs + SERIAL_WARPS - 1) / SERIAL_WARPS); };
     {
         const size_t smA = rans_smem(B.max_alpha_ctx), smB = rans_smem(B.max_alpha_attr);
         const size_t smMax = smA > smB ? smA : smB;
+        if (smMax > 200 * 1024) { ctx->err = "rANS alphabet too large for the shared-memory tables"; return UVOL_ERR_UNSUPPORTED; }
         if (smMax > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_rans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smMax));
         UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB_RING + 128) * 16)));
         UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB2_RING + 128 + EB2_STAGE) * 16)));
