@@ -40,7 +40,38 @@ __device__ __forceinline__ void frame_fail(DracoCounts *counts, uint32_t f, int 
 #ifndef SERIAL_WARPS
 #define SERIAL_WARPS 1
 #endif
-#define RANS_LUT_BITS 12
+// The serial rANS walk of one run (lane 0).  Everything on the dependent chain is kept to one shared-memory load per
+// symbol: a 2048-entry index keyed by the top bits of the slot holds the first symbol reaching into that bucket together
+// with its {start, frequency}; only when the slot lies beyond that symbol (rare) does
+// the walk scan on through the per-symbol table.  WIDE = alphabet > 4096 (symbol id split over both words).
+struct RansRun { const uint2 *sf; const uint2 *lut; const uint32_t *wp; uint32_t w, wn, bi; int left; uint32_t st, pb, shift; };
+template <int MODE, bool WIDE>
+__device__ __forceinline__ void rans_walk(RansRun r, uint32_t count, void *out) {
+    const uint2 *sf = r.sf; const uint2 *lut = r.lut; const uint32_t *wp = r.wp;
+    uint32_t w = r.w, wn = r.wn, bi = r.bi, st = r.st; int left = r.left;
+    const uint32_t pb = r.pb, shift = r.shift, prec = 1u << pb, lbase = prec * 4u;
+    uint8_t *o8 = (uint8_t *)out; int32_t *o32 = (int32_t *)out;
+#pragma unroll 4
+    for (uint32_t i = 0; i < count; i++) {
+        if (st < lbase) {
+            while (st < lbase && left > 0) {
+                st = st * 256u + (__byte_perm(w, 0u, bi | 0x4440u));
+                left--;
+                if (bi == 0) { w = wn; --wp; wn = wp[-1]; bi = 3; } else bi--;
+            }
+        }
+        const uint32_t q = st >> pb, rem = st & (prec - 1);
+        const uint2 e = lut[rem >> shift];
+        uint32_t sy = WIDE ? (e.x >> 20) | ((e.y >> 21) << 12) : e.x >> 20, start = e.x & 0xfffffu, freq = WIDE ? e.y & 0x1fffffu : e.y;
+        if (rem >= start + freq) { do { sy++; const uint2 t = sf[sy]; start = t.x; freq = t.y; } while (rem >= start + freq); }
+        st = q * freq + rem - start;
+        if (MODE == 0) o8[i] = (uint8_t)sy;
+        else if (MODE == 1) o32[i] = (sy & 1) ? -(int32_t)(sy >> 1) - 1 : (int32_t)(sy >> 1);
+        else o32[i] = (int32_t)sy;
+    }
+}
+
+#define RANS_LUT_BITS 11          // 16 KB index + 8 B per symbol: all runs of a 300-frame batch stay resident in one wave
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
                                              uint8_t *scratch, uint8_t *scratch2, const Job *jobs, int njobs, int smem_words_per_warp) {
     extern __shared__ uint32_t smem_all[];
@@ -59,12 +90,12 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *fr
         mode = (a.pred != -2 && (a.xform == 2 || a.xform == 3)) ? 2 : 1;
         count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
     }
-    // Tables in shared memory (built by the whole warp): sf[s] = {first slot, frequency} of symbol s (sf[A].x = total) and
-    // a 2^min(pb,12)-entry index "first symbol whose range reaches into this bucket", so that the symbol search on the
-    // serial chain is one table load plus one 8-byte load in the common case (exact when pb <= 12).
+    // Tables in shared memory (built by the whole warp): sf[s] = {first slot, frequency} of symbol s (sf[A].x = total),
+    // lut[b] = {first slot | symbol << 20, frequency} of the first symbol whose range reaches into bucket b.
     const uint32_t A = s.alphabet, pb = s.pb, lane = threadIdx.x & 31;
     const uint32_t lb = pb < RANS_LUT_BITS ? pb : RANS_LUT_BITS;
-    uint2 *sf = (uint2 *)smem; uint16_t *bucket = (uint16_t *)(sf + A + 1);
+    if (A > (1u << 18) || pb > 20u) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }      // the RAW scheme allows 18-bit symbols, 20-bit precision
+    uint2 *lut = (uint2 *)smem; uint2 *sf = lut + (1u << RANS_LUT_BITS);
     const uint32_t *prob = aux + s.prob_off;
     uint32_t run = 0;
     for (uint32_t base = 0; base < A; base += 32) {
@@ -82,7 +113,8 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *fr
         const uint32_t target = b << (pb - lb);
         uint32_t lo = 0, hi = A - 1;
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sf[mid + 1].x > target) hi = mid; else lo = mid + 1; }
-        bucket[b] = (uint16_t)lo;
+        const uint2 t = sf[lo];
+        lut[b] = make_uint2(t.x | ((lo & 0xfffu) << 20), t.y | ((lo >> 12) << 21));
     }
     __syncwarp();
     if (lane != 0 || count == 0) return;
@@ -102,22 +134,9 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *fr
     uint32_t w = p > data ? wp[0] : 0u, wn = p > data ? wp[-1] : 0u;
     uint32_t bi = (uint32_t)((uintptr_t)(p - 1) & 3);         // byte index inside w
     int left = (int)(nbytes - k);                             // bytes not yet consumed
-    uint8_t *o8 = (uint8_t *)out; int32_t *o32 = (int32_t *)out;
-    for (uint32_t i = 0; i < count; i++) {
-        while (st < lbase && left > 0) {
-            st = st * 256u + (__byte_perm(w, 0u, bi | 0x4440u));
-            left--;
-            if (bi == 0) { w = wn; --wp; wn = wp[-1]; bi = 3; } else bi--;
-        }
-        const uint32_t q = st >> pb, rem = st & (prec - 1);
-        uint32_t sy = bucket[rem >> shift];
-        uint2 e = sf[sy];
-        while (rem >= e.x + e.y) { sy++; e = sf[sy]; }
-        st = q * e.y + rem - e.x;
-        if (mode == 0) o8[i] = (uint8_t)sy;
-        else if (mode == 1) o32[i] = (sy & 1) ? -(int32_t)(sy >> 1) - 1 : (int32_t)(sy >> 1);
-        else o32[i] = (int32_t)sy;
-    }
+    RansRun r{sf, lut, wp, w, wn, bi, left, st, pb, shift};
+    if (A <= 4096u) { if (mode == 0) rans_walk<0, false>(r, count, out); else if (mode == 1) rans_walk<1, false>(r, count, out); else rans_walk<2, false>(r, count, out); }
+    else { if (mode == 0) rans_walk<0, true>(r, count, out); else if (mode == 1) rans_walk<1, true>(r, count, out); else rans_walk<2, true>(r, count, out); }
 }
 
 // rABS bit runs: one warp per run (lane 0 walks).  what: 0..3 = seam bits of attribute data i
@@ -1252,7 +1271,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     const uint8_t *dBlob = (const uint8_t *)ctx->d_blob.p; const uint32_t *dAux = (const uint32_t *)ctx->d_aux.p;
     uint8_t *dS = (uint8_t *)ctx->d_scratch.p, *dZ = (uint8_t *)ctx->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
     uint32_t launches = 0;
-    auto rans_words = [](uint32_t alphabet) { return (int)(((size_t)(alphabet + 1) * 8 + (2u << RANS_LUT_BITS) + 16 + 15) / 16 * 4); };
+    auto rans_words = [](uint32_t alphabet) { return (int)(((size_t)(alphabet + 1) * 8 + (8u << RANS_LUT_BITS) + 16 + 15) / 16 * 4); };
     auto rans_smem = [&](uint32_t alphabet) { return (size_t)rans_words(alphabet) * 4 * SERIAL_WARPS; };
     auto nblk = [](int jobs) { return (unsigned)((jobs + SERIAL_WARPS - 1) / SERIAL_WARPS); };
     {

@@ -16,8 +16,12 @@ extern "C" int uvol_create(int device, uvol_ctx **out) {
     c->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->s0, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->s1, cudaStreamNonBlocking) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
-    if (cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    // s0 carries the geometry critical path and gets the highest priority: the block scheduler serves pending grids in
+    // priority order, so the wide side-stream grids (entropy runs on s1, textures on s2) never hold back a main-stream kernel.
+    int prio_lo = 0, prio_hi = 0; cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const int prio_mid = prio_hi < prio_lo - 1 ? prio_hi + 1 : prio_lo;
+    if (cudaStreamCreateWithPriority(&c->s0, cudaStreamNonBlocking, prio_hi) != cudaSuccess || cudaStreamCreateWithPriority(&c->s1, cudaStreamNonBlocking, prio_mid) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    if (cudaStreamCreateWithPriority(&c->s2, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     for (auto &e : c->aux_ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     for (auto &e : c->tex_ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
