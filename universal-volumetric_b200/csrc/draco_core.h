@@ -346,6 +346,9 @@ UVOL_HD int traverse_table(const TableView &t, const int *lmc_base, int F, uint8
             if (c < 0 || fvis[c / 3]) { sp--; continue; }
             for (;;) {
                 fvis[c / 3] = 1;
+#ifdef UVOL_TRAV_LOG
+                UVOL_TRAV_LOG(c);      // debugging hook of the host harness (never defined in the product build)
+#endif
                 const int v = t_vert(t, c);
                 if (v < 0) return UVOL_ERR_CORRUPT;
                 if (!v2d1[v]) {

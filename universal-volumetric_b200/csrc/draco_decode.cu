@@ -41,90 +41,114 @@ __device__ __forceinline__ void frame_fail(DracoCounts *counts, uint32_t f, int 
 #define SERIAL_WARPS 1
 #endif
 // The serial rANS walk of one run (lane 0).  Everything on the dependent chain is kept to one shared-memory load per
-// symbol: a 2048-entry index keyed by the top bits of the slot holds the first symbol reaching into that bucket together
-// with its {start, frequency}; only when the slot lies beyond that symbol (rare) does
-// the walk scan on through the per-symbol table.  WIDE = alphabet > 4096 (symbol id split over both words).
-struct RansRun { const uint2 *sf; const uint2 *lut; const uint32_t *wp; uint32_t w, wn, bi; int left; uint32_t st, pb, shift; };
-template <int MODE, bool WIDE>
-__device__ __forceinline__ void rans_walk(RansRun r, uint32_t count, void *out) {
-    const uint2 *sf = r.sf; const uint2 *lut = r.lut; const uint32_t *wp = r.wp;
+// symbol: a 1024-entry index keyed by the top bits of the slot holds the first symbol reaching into that bucket together
+// with its {start, frequency}; only when the slot lies beyond that symbol does the walk scan on through the compact table
+// of the symbols that have a non-zero probability (kidx = that symbol's rank).  WIDE = alphabet > 4096 (symbol id split
+// over both words).  EARLY = run until the coder is back in its initial state with all bytes consumed (at most `count`
+// symbols): while no byte is left every encoder step strictly increases the state, so the initial state can only be met at the
+// true end of the run -- this lets the attribute runs start before the connectivity has produced their symbol counts.
+struct RansRun { const uint4 *cs; const uint2 *lut; const uint16_t *kidx; const uint32_t *wp; uint32_t w, wn, bi; int left; uint32_t st, pb, shift; };
+template <int MODE, bool WIDE, bool EARLY>
+__device__ __forceinline__ uint32_t rans_walk(RansRun r, uint32_t count, void *out) {
+    const uint4 *cs = r.cs; const uint2 *lut = r.lut; const uint32_t *wp = r.wp;
     uint32_t w = r.w, wn = r.wn, bi = r.bi, st = r.st; int left = r.left;
     const uint32_t pb = r.pb, shift = r.shift, prec = 1u << pb, lbase = prec * 4u;
     uint8_t *o8 = (uint8_t *)out; int32_t *o32 = (int32_t *)out;
+    uint32_t i = 0;
+#define RANS_SYMBOL() do { \
+        const uint32_t q = st >> pb, rem = st & (prec - 1); \
+        const uint2 e = lut[rem >> shift]; \
+        uint32_t sy = WIDE ? (e.x >> 20) | ((e.y >> 21) << 12) : e.x >> 20, start = e.x & 0xfffffu, freq = WIDE ? e.y & 0x1fffffu : e.y; \
+        if (rem >= start + freq) { uint32_t k = r.kidx[rem >> shift]; do { const uint4 t = cs[++k]; start = t.x; freq = t.y; sy = t.z; } while (rem >= start + freq); } \
+        st = q * freq + rem - start; \
+        if (MODE == 0) o8[i] = (uint8_t)sy; \
+        else if (MODE == 1) o32[i] = (sy & 1) ? -(int32_t)(sy >> 1) - 1 : (int32_t)(sy >> 1); \
+        else o32[i] = (int32_t)sy; } while (0)
 #pragma unroll 4
-    for (uint32_t i = 0; i < count; i++) {
+    for (; i < count && (!EARLY || left > 0); i++) {
         if (st < lbase) {
             while (st < lbase && left > 0) {
                 st = st * 256u + (__byte_perm(w, 0u, bi | 0x4440u));
                 left--;
                 if (bi == 0) { w = wn; --wp; wn = wp[-1]; bi = 3; } else bi--;
             }
+            if (EARLY && left == 0 && st == lbase) return i;
         }
-        const uint32_t q = st >> pb, rem = st & (prec - 1);
-        const uint2 e = lut[rem >> shift];
-        uint32_t sy = WIDE ? (e.x >> 20) | ((e.y >> 21) << 12) : e.x >> 20, start = e.x & 0xfffffu, freq = WIDE ? e.y & 0x1fffffu : e.y;
-        if (rem >= start + freq) { do { sy++; const uint2 t = sf[sy]; start = t.x; freq = t.y; } while (rem >= start + freq); }
-        st = q * freq + rem - start;
-        if (MODE == 0) o8[i] = (uint8_t)sy;
-        else if (MODE == 1) o32[i] = (sy & 1) ? -(int32_t)(sy >> 1) - 1 : (int32_t)(sy >> 1);
-        else o32[i] = (int32_t)sy;
+        RANS_SYMBOL();
     }
+    if (EARLY) for (; i < count && st != lbase; i++) RANS_SYMBOL();          // all bytes consumed: run down to the initial state
+#undef RANS_SYMBOL
+    return i;
 }
 
-#define RANS_LUT_BITS 11          // 16 KB index + 8 B per symbol: all runs of a 300-frame batch stay resident in one wave
+#define RANS_LUT_BITS 10          // 8 KB index + 2 KB ranks + 16 B per used symbol: every run of a 300-frame batch is resident at once
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
-                                             uint8_t *scratch, uint8_t *scratch2, const Job *jobs, int njobs, int smem_words_per_warp) {
+                                             uint8_t *scratch, uint8_t *scratch2, const Job *jobs, int njobs, int smem_words_per_warp, int early) {
     extern __shared__ uint32_t smem_all[];
     const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if (ji >= njobs) return;
     uint32_t *smem = smem_all + (size_t)(threadIdx.x >> 5) * smem_words_per_warp;
     const Job jb = jobs[ji];
-    if (frame_dead(frames, counts, jb.frame)) return;
+    const uint32_t lane = threadIdx.x & 31;
+    if (early) { if (frames[jb.frame].status) return; }
+    else if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame];
     const uint8_t *file = blob + f.file_off;
     RansStream s; void *out; int mode; uint32_t count;
     if (jb.what < 16) { s = f.ctx[jb.what]; out = scratch + f.o_ctxsym[jb.what]; mode = 0; count = s.count; }
     else {
-        const DracoAttr &a = f.attr[jb.what - 16];
-        s = a.sym; out = scratch2 + f.o_corr[jb.what - 16];
+        const int j = jb.what - 16; const DracoAttr &a = f.attr[j];
+        s = a.sym;
         mode = (a.pred != -2 && (a.xform == 2 || a.xform == 3)) ? 2 : 1;
-        count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
+        if (early) { out = scratch + f.o_corr_early[j]; count = f.corr_early_cap[j]; if (lane == 0) counts[jb.frame].rans_early[j] = 0xffffffffu; }
+        else {
+            out = scratch2 + f.o_corr[j]; count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
+            if (counts[jb.frame].rans_early[j] == count) return;               // the early run produced exactly these symbols (k_corr_settle copies them)
+        }
     }
-    // Tables in shared memory (built by the whole warp): sf[s] = {first slot, frequency} of symbol s (sf[A].x = total),
-    // lut[b] = {first slot | symbol << 20, frequency} of the first symbol whose range reaches into bucket b.
-    const uint32_t A = s.alphabet, pb = s.pb, lane = threadIdx.x & 31;
+    // Tables in shared memory (built by the whole warp): cs[k] = {first slot, frequency, symbol} of the k-th symbol with a
+    // non-zero probability (cs[nnz].x = total), lut[b] = {first slot | symbol, frequency} and kidx[b] = rank of the first
+    // symbol whose range reaches into bucket b.
+    const uint32_t A = s.alphabet, pb = s.pb;
     const uint32_t lb = pb < RANS_LUT_BITS ? pb : RANS_LUT_BITS;
     if (A > (1u << 18) || pb > 20u) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }      // the RAW scheme allows 18-bit symbols, 20-bit precision
-    uint2 *lut = (uint2 *)smem; uint2 *sf = lut + (1u << RANS_LUT_BITS);
+    uint2 *lut = (uint2 *)smem; uint16_t *kidx = (uint16_t *)(lut + (1u << RANS_LUT_BITS)); uint4 *cs = (uint4 *)(kidx + (1u << RANS_LUT_BITS));
     const uint32_t *prob = aux + s.prob_off;
-    uint32_t run = 0;
+    uint32_t run = 0, nk = 0;
     for (uint32_t base = 0; base < A; base += 32) {
         const uint32_t p = (base + lane < A) ? prob[base + lane] : 0u;
         uint32_t inc = p;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
-        if (base + lane < A) sf[base + lane] = make_uint2(run + inc - p, p);
-        run += __shfl_sync(0xffffffffu, inc, 31);
+        const unsigned nzm = __ballot_sync(0xffffffffu, p != 0);
+        if (p != 0) { const uint32_t k = nk + __popc(nzm & ((1u << lane) - 1u)); if (k < s.nnz) cs[k] = make_uint4(run + inc - p, p, base + lane, 0u); }
+        run += __shfl_sync(0xffffffffu, inc, 31); nk += __popc(nzm);
     }
-    if (lane == 0) sf[A] = make_uint2(run, 0u);
+    if (lane == 0) cs[s.nnz] = make_uint4(run, 0u, A, 0u);
     __syncwarp();
-    if (run != (1u << pb)) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
-    for (uint32_t b = lane; b < (1u << lb); b += 32) {          // first s with cum[s+1] > b << (pb - lb)
+    if (run != (1u << pb) || nk != s.nnz) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
+    for (uint32_t b = lane; b < (1u << lb); b += 32) {          // first k with cs[k+1].start > b << (pb - lb)
         const uint32_t target = b << (pb - lb);
-        uint32_t lo = 0, hi = A - 1;
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sf[mid + 1].x > target) hi = mid; else lo = mid + 1; }
-        const uint2 t = sf[lo];
-        lut[b] = make_uint2(t.x | ((lo & 0xfffu) << 20), t.y | ((lo >> 12) << 21));
+        uint32_t lo = 0, hi = nk - 1;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (cs[mid + 1].x > target) hi = mid; else lo = mid + 1; }
+        const uint4 t = cs[lo];
+        lut[b] = make_uint2(t.x | ((t.z & 0xfffu) << 20), t.y | ((t.z >> 12) << 21)); kidx[b] = (uint16_t)lo;
     }
     __syncwarp();
+    if (nk == 1 && !early) {          // a single symbol with probability one: the coder state never moves and no byte is read
+        const uint32_t sy = cs[0].z; const int32_t val = mode == 1 ? ((sy & 1) ? -(int32_t)(sy >> 1) - 1 : (int32_t)(sy >> 1)) : (int32_t)sy;
+        if (mode == 0) for (uint32_t i = lane; i < count; i += 32) ((uint8_t *)out)[i] = (uint8_t)sy;
+        else for (uint32_t i = lane; i < count; i += 32) ((int32_t *)out)[i] = val;
+        return;
+    }
     if (lane != 0 || count == 0) return;
     // ---- the run (lane 0).  Bytes are consumed back to front through a register window of aligned 32-bit words,
     // the next word always prefetched, so renormalisation never waits on memory.
     const uint8_t *data = file + s.data_off; const uint32_t nbytes = s.data_len;
-    if (nbytes == 0) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
+    if (nbytes == 0) { if (!early) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
     const uint32_t prec = 1u << pb, lbase = prec * 4u, shift = pb - lb;
     const unsigned x = data[nbytes - 1] >> 6, k = x + 1;
-    if (nbytes < k) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
+    if (nbytes < k) { if (!early) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
     uint32_t st = 0;
     for (unsigned i = 0; i < k; i++) st |= (uint32_t)data[nbytes - k + i] << (8 * i);
     st &= (1u << (8 * k - 2)) - 1u;
@@ -134,9 +158,28 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *fr
     uint32_t w = p > data ? wp[0] : 0u, wn = p > data ? wp[-1] : 0u;
     uint32_t bi = (uint32_t)((uintptr_t)(p - 1) & 3);         // byte index inside w
     int left = (int)(nbytes - k);                             // bytes not yet consumed
-    RansRun r{sf, lut, wp, w, wn, bi, left, st, pb, shift};
-    if (A <= 4096u) { if (mode == 0) rans_walk<0, false>(r, count, out); else if (mode == 1) rans_walk<1, false>(r, count, out); else rans_walk<2, false>(r, count, out); }
-    else { if (mode == 0) rans_walk<0, true>(r, count, out); else if (mode == 1) rans_walk<1, true>(r, count, out); else rans_walk<2, true>(r, count, out); }
+    RansRun r{cs, lut, kidx, wp, w, wn, bi, left, st, pb, shift};
+    const bool wide = A > 4096u;
+    if (early) {
+        uint32_t got;
+        if (!wide) got = mode == 1 ? rans_walk<1, false, true>(r, count, out) : rans_walk<2, false, true>(r, count, out);
+        else got = mode == 1 ? rans_walk<1, true, true>(r, count, out) : rans_walk<2, true, true>(r, count, out);
+        counts[jb.frame].rans_early[jb.what - 16] = got;
+    } else if (!wide) { if (mode == 0) rans_walk<0, false, false>(r, count, out); else if (mode == 1) rans_walk<1, false, false>(r, count, out); else rans_walk<2, false, false>(r, count, out); }
+    else { if (mode == 0) rans_walk<0, true, false>(r, count, out); else if (mode == 1) rans_walk<1, true, false>(r, count, out); else rans_walk<2, true, false>(r, count, out); }
+}
+
+// Moves the symbols of the early attribute runs that came out with exactly the expected count into their phase-2 place
+// (runs that did not are decoded again, by count, by the regular k_rans launch that follows).  grid = (ceil(max/1024), jobs)
+__global__ void __launch_bounds__(256) k_corr_settle(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, uint8_t *S2, const Job *jobs) {
+    const Job jb = jobs[blockIdx.y];
+    if (frame_dead(frames, counts, jb.frame)) return;
+    const DracoFrame &f = frames[jb.frame]; const int j = jb.what - 16; const DracoAttr &a = f.attr[j];
+    const uint32_t count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
+    if (counts[jb.frame].rans_early[j] != count) return;
+    const uint4 *src = (const uint4 *)(S + f.o_corr_early[j]); uint4 *dst = (uint4 *)(S2 + f.o_corr[j]);
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i * 4 < count) dst[i] = src[i];
 }
 
 // rABS bit runs: one warp per run (lane 0 walks).  what: 0..3 = seam bits of attribute data i
@@ -785,6 +828,38 @@ __global__ void __launch_bounds__(128) k_face_entries(const DracoFrame *frames, 
     up[fi] = u; dn[fi] = d;
 }
 
+// Duplicate distances (element-parallel): for the up entry of face f the smallest k in 1..31 such that the up entry of
+// face f-k has the same tip vertex (0: none), for the down entry the same towards f+k; stored in bits 26..30 of x.
+// The traversal uses it to know, without any exchange between lanes, that a tip was already reached by an earlier
+// face of the same 32-face run.   grid = (ceil(maxF/256), traversal jobs)
+#define TIP_MASK 0x03ffffffu          // x = tip vertex | duplicate distance << 26 | on-boundary << 31
+__global__ void __launch_bounds__(256) k_face_dups(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S2, const Job *jobs) {
+    __shared__ uint32_t tipU[256 + 32], tipD[256 + 32];
+    const Job jb = jobs[blockIdx.y];
+    if (frame_dead(frames, counts, jb.frame)) return;
+    const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
+    if (f.o_d2c[t] == UVOL_NONE) return;
+    const int F = (int)f.nf, base = blockIdx.x * 256;
+    if (base >= F) return;
+    uint4 *up = (uint4 *)(S2 + f.o_frec[t]) + 3 * (size_t)F + 4, *dn = up + F + 4;
+    for (int i = threadIdx.x; i < 256 + 31; i += 256) {
+        const int gu = base - 31 + i, gd = base + i;
+        uint32_t a = 0xffffffffu, b = 0xffffffffu;
+        if (gu >= 0 && gu < F) { const uint4 r = up[gu]; if ((int)r.w >= 0) a = r.x & TIP_MASK; }
+        if (gd < F) { const uint4 r = dn[gd]; if ((int)r.w >= 0) b = r.x & TIP_MASK; }
+        tipU[i] = a; tipD[i] = b;
+    }
+    __syncthreads();
+    const int fi = base + threadIdx.x;
+    if (fi >= F) return;
+    const uint32_t mu = tipU[threadIdx.x + 31], md = tipD[threadIdx.x];
+    uint32_t du = 0, dd = 0;
+    if (mu != 0xffffffffu) { for (int k = 1; k < 32; k++) if (tipU[threadIdx.x + 31 - k] == mu) { du = (uint32_t)k; break; } }
+    if (md != 0xffffffffu) { for (int k = 1; k < 32; k++) if (tipD[threadIdx.x + k] == md) { dd = (uint32_t)k; break; } }
+    if (du) ((uint32_t *)(up + fi))[0] |= du << 26;
+    if (dd) ((uint32_t *)(dn + fi))[0] |= dd << 26;
+}
+
 // Depth-first traversal (A.3): one warp per (frame, table), 32 faces per step.
 // Face ids follow the edgebreaker strip order and the traversal walks along the same strips (94-99 % of its
 // moves go to face id +-1), so lane i SPECULATES that the walk reaches face f0 + i*dir through that face's
@@ -827,7 +902,7 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
                         const int nf = m ? w * 32 + __ffs(m) - 1 : F;
                         if (nf >= F) { done = 1; break; }
                         fscan = nf; c = 3 * nf; stk[0] = c; sp = 1;
-                        const unsigned vn = grec[c + 1].x & 0x7fffffffu, vp = grec[c + 2].x & 0x7fffffffu;     // next / previous vertices first
+                        const unsigned vn = grec[c + 1].x & TIP_MASK, vp = grec[c + 2].x & TIP_MASK;     // next / previous vertices first
                         if (!VBIT(vn)) { vbits[vn >> 5] |= 1u << (vn & 31); v2d1[vn] = ++n; d2c[n - 1] = c + 1; }
                         if (!VBIT(vp)) { vbits[vp >> 5] |= 1u << (vp & 31); v2d1[vp] = ++n; d2c[n - 1] = c + 2; }
                         break;
@@ -853,7 +928,7 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
         // lane 0's exact decision (computed by every lane) fixes the direction
         int dir;
         {
-            const unsigned v = R0.x & 0x7fffffffu; const int rc = (int)R0.y, lc = (int)R0.z; int nx = -1;
+            const unsigned v = R0.x & TIP_MASK; const int rc = (int)R0.y, lc = (int)R0.z; int nx = -1;
             if (!VBIT(v) && (int)R0.x >= 0) nx = rc;
             else {
                 const bool fr = rc < 0 || FBIT(face_of(rc)) || face_of(rc) == (unsigned)f0, fl = lc < 0 || FBIT(face_of(lc)) || face_of(lc) == (unsigned)f0;
@@ -868,11 +943,12 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
         if (lane > 0 && dir == 0) R.w = 0xffffffffu;
         const int ci = (int)R.w;                                   // my corner (-1: no such entry)
         const int fi = f0 + lane * dir;
-        const unsigned v = R.x & 0x7fffffffu; const bool ob = (int)R.x < 0; const int rc = (int)R.y, lc = (int)R.z;
+        const unsigned v = R.x & TIP_MASK, pd = lane == 0 ? 0u : (R.x >> 26) & 31u; const bool ob = (int)R.x < 0; const int rc = (int)R.y, lc = (int)R.z;
         const bool selfopen = ci >= 0 && !FBIT(fi);
         // vertex visited before my step: bitmap, or the tip of an earlier lane
-        const unsigned same = __match_any_sync(0xffffffffu, ci >= 0 ? v : 0x80000000u + lane);
-        const bool vis = ci >= 0 && (VBIT(v) || (same & lt) != 0);
+        const unsigned v_first = __shfl_sync(0xffffffffu, v, 0);
+        const bool dup = lane > 0 && (v == v_first || (pd != 0 && (int)pd < lane));      // lane 0's actual tip, or the static distance to an earlier face of the run
+        const bool vis = ci >= 0 && (VBIT(v) || dup);
         // neighbour faces visited before / during this step (faces of the lanes up to and including me)
         bool fr = true, fl = true;
         if (ci >= 0) {
@@ -1194,10 +1270,10 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
         f.status = (data[i] && size[i] < (1ull << 31)) ? uvol_draco_parse(data[i], size[i], f, aux) : UVOL_ERR_ARG;
         if (f.status) continue;
         if (f.trav == 2) B.any_valence = true; else B.any_standard = true;
-        for (int k = 0; k < 6; k++) if (f.ctx[k].count && f.ctx[k].alphabet > B.max_alpha_ctx) B.max_alpha_ctx = f.ctx[k].alphabet;
+        for (int k = 0; k < 6; k++) if (f.ctx[k].count && f.ctx[k].nnz > B.max_alpha_ctx) B.max_alpha_ctx = f.ctx[k].nnz;      // (table sizes follow the used symbols)
         for (int j = 0; j < f.nattr; j++) {
-            if (f.attr[j].sym.alphabet > 49000) { f.status = UVOL_ERR_UNSUPPORTED; break; }
-            if ((f.attr[j].out_slot >= 0 || j == f.pos_attr) && f.attr[j].sym.alphabet > B.max_alpha_attr) B.max_alpha_attr = f.attr[j].sym.alphabet;
+            if (f.attr[j].sym.nnz > 8192) { f.status = UVOL_ERR_UNSUPPORTED; break; }
+            if ((f.attr[j].out_slot >= 0 || j == f.pos_attr) && f.attr[j].sym.nnz > B.max_alpha_attr) B.max_alpha_attr = f.attr[j].sym.nnz;
         }
     }
     aux.push_back(0);
@@ -1271,7 +1347,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     const uint8_t *dBlob = (const uint8_t *)ctx->d_blob.p; const uint32_t *dAux = (const uint32_t *)ctx->d_aux.p;
     uint8_t *dS = (uint8_t *)ctx->d_scratch.p, *dZ = (uint8_t *)ctx->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
     uint32_t launches = 0;
-    auto rans_words = [](uint32_t alphabet) { return (int)(((size_t)(alphabet + 1) * 8 + (8u << RANS_LUT_BITS) + 16 + 15) / 16 * 4); };
+    auto rans_words = [](uint32_t nnz) { return (int)(((size_t)(nnz + 1) * 16 + (10u << RANS_LUT_BITS) + 16 + 15) / 16 * 4); };
     auto rans_smem = [&](uint32_t alphabet) { return (size_t)rans_words(alphabet) * 4 * SERIAL_WARPS; };
     auto nblk = [](int jobs) { return (unsigned)((jobs + SERIAL_WARPS - 1) / SERIAL_WARPS); };
     {
@@ -1290,7 +1366,14 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     if (B.j_trav - B.j_rabsA > 0) { k_rabs<<<nblk(B.j_trav - B.j_rabsA), 32 * SERIAL_WARPS, 0, sx>>>(dF, dC, dBlob, dS, nullptr, dJ + B.j_rabsA, B.j_trav - B.j_rabsA); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[1], sx);
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[1], sx));
-    if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<nblk(B.j_rabsA - B.j_ransA), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + B.j_ransA, B.j_rabsA - B.j_ransA, rans_words(B.max_alpha_ctx)); launches++; }
+    // The attribute symbol runs do not wait for the connectivity: they run to the coder's terminal state (k_rans, early
+    // mode) next to the connectivity walk; k_corr_settle adopts every run that came out with exactly the expected count.
+    static const bool no_early = getenv("UVOL_NO_EARLY_RANS") != nullptr;
+    if (ctx->profile) cudaEventRecord(ctx->aux_ev[2], sx);
+    if (!no_early && B.j_rabsB - B.j_ransB > 0) { k_rans<<<nblk(B.j_rabsB - B.j_ransB), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_attr), sx>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + B.j_ransB, B.j_rabsB - B.j_ransB, rans_words(B.max_alpha_attr), 1); launches++; }
+    if (ctx->profile) cudaEventRecord(ctx->aux_ev[3], sx);
+    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[4], sx));
+    if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<nblk(B.j_rabsA - B.j_ransA), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + B.j_ransA, B.j_rabsA - B.j_ransA, rans_words(B.max_alpha_ctx), 0); launches++; }
     stamp("rans_ctx");
     stamp("rabs_seams(s1)"); i_seams = ev - 2;                                     // (stage slot of rabs_seams: timed on s1, filled in below)
     if (B.any_valence) {
@@ -1334,9 +1417,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     }
     // ---- phase 2.  Attribute entropy runs (sized from counts.expected) go to s1 and overlap the traversals.
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[2], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->sync_ev[2], 0));
-    if (ctx->profile) cudaEventRecord(ctx->aux_ev[2], sx);
-    if (B.j_rabsB - B.j_ransB > 0) { k_rans<<<nblk(B.j_rabsB - B.j_ransB), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_attr), sx>>>(dF, dC, dBlob, dAux, dS, dS2, dJ + B.j_ransB, B.j_rabsB - B.j_ransB, rans_words(B.max_alpha_attr)); launches++; }
-    if (ctx->profile) cudaEventRecord(ctx->aux_ev[3], sx);
+    if (ctx->profile) cudaEventRecord(ctx->aux_ev[5], sx);
     if (B.j_wrap - B.j_rabsB > 0) { k_rabs<<<nblk(B.j_wrap - B.j_rabsB), 32 * SERIAL_WARPS, 0, sx>>>(dF, dC, dBlob, dS, dS2, dJ + B.j_rabsB, B.j_wrap - B.j_rabsB); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[4], sx);
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[3], sx));
@@ -1346,14 +1427,22 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         const int ntj = B.j_ransB - B.j_trav;
         k_corner_records<<<dim3((3 * B.maxF + 127) / 128, ntj), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dJ + B.j_trav); launches++;
         k_face_entries<<<dim3((B.maxF + 127) / 128, ntj), 128, 0, st>>>(dF, dC, dS2, dJ + B.j_trav); launches++;
+        k_face_dups<<<dim3((B.maxF + 255) / 256, ntj), 256, 0, st>>>(dF, dC, dS2, dJ + B.j_trav); launches++;
         stamp("corner_records");
         const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((maxN + 31) / 32 + 4) & ~3u);
         const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_STACK * 4) * TRAV_WARPS;
-        if (smem > 200 * 1024) { ctx->err = "mesh too large for the traversal bitmaps"; return UVOL_ERR_UNSUPPORTED; }
+        if (smem > 200 * 1024 || maxN >= (1u << 26)) { ctx->err = "mesh too large for the traversal bitmaps"; return UVOL_ERR_UNSUPPORTED; }
         if (smem > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_traverse<<<(ntj + TRAV_WARPS - 1) / TRAV_WARPS, 32 * TRAV_WARPS, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords); launches++;
     }
     stamp("traverse");
+    UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[4], 0));
+    if (B.j_rabsB - B.j_ransB > 0) {
+        const int nrj = B.j_rabsB - B.j_ransB;
+        k_corr_settle<<<dim3((4 * maxN + 1023) / 1024 + 1, nrj), 256, 0, st>>>(dF, dC, dS, dS2, dJ + B.j_ransB); launches++;
+        k_rans<<<nblk(nrj), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_attr), st>>>(dF, dC, dBlob, dAux, dS, dS2, dJ + B.j_ransB, nrj, rans_words(B.max_alpha_attr), 0); launches++;
+    }
+    stamp("corr_settle");
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[3], 0));
     stamp("rans_attr(s1)"); i_rans = ev - 2;                                     // (stage slots of rans_attr / rabs_aux: timed on s1)
     stamp("rabs_aux(s1)"); i_rabs = ev - 2;
@@ -1405,7 +1494,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         // stages that ran on the side stream (overlapped with the main stream): their own event pairs
         if (i_seams >= 0 && i_seams < 24) cudaEventElapsedTime(&s.stage_ms[i_seams], ctx->aux_ev[0], ctx->aux_ev[1]);
         if (i_rans >= 0 && i_rans < 24) cudaEventElapsedTime(&s.stage_ms[i_rans], ctx->aux_ev[2], ctx->aux_ev[3]);
-        if (i_rabs >= 0 && i_rabs < 24) cudaEventElapsedTime(&s.stage_ms[i_rabs], ctx->aux_ev[3], ctx->aux_ev[4]);
+        if (i_rabs >= 0 && i_rabs < 24) cudaEventElapsedTime(&s.stage_ms[i_rabs], ctx->aux_ev[5], ctx->aux_ev[4]);
     }
     return UVOL_OK;
 }

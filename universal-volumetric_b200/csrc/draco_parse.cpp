@@ -48,6 +48,7 @@ int read_symbols(Rd &r, RansStream &s, std::vector<uint32_t> &aux) {
     }
     int pb = (3 * mbl) / 2; if (pb < 12) pb = 12; if (pb > 20) pb = 20;
     s.pb = (uint32_t)pb;
+    s.nnz = 0; for (uint32_t i = 0; i < n; i++) s.nnz += aux[s.prob_off + i] != 0;
     uint64_t nb = r.varint();
     if (r.err || nb > r.n - r.p) return UVOL_ERR_TRUNCATED;
     s.data_off = (uint32_t)r.p; s.data_len = (uint32_t)nb; r.p += nb;

@@ -32,6 +32,12 @@ static inline void draco_plan_phase1(std::vector<DracoFrame> &frames, DracoPlan 
         }
         f.o_pcnt = plan_take(s, (maxv + 1) * 4);
         f.o_pfirst = plan_take(s, maxv * 4);               // dedup start corner per vertex
+        for (int j = 0; j < f.nattr; j++) {                // early attribute symbol runs: capacity from the largest possible entry count
+            const DracoAttr &a = f.attr[j];
+            if (a.out_slot < 0 && j != f.pos_attr) { f.o_corr_early[j] = UVOL_NONE; f.corr_early_cap[j] = 0; continue; }
+            const uint64_t cap = (a.table < 0 ? maxv : C) * (uint64_t)a.vnc;
+            f.corr_early_cap[j] = (uint32_t)cap; f.o_corr_early[j] = plan_take(s, (cap + 4) * 4);
+        }
     }
     pl.scratch = s; pl.zscratch = z;
 }

@@ -24,6 +24,7 @@ struct RansStream {          // one RAW rANS symbol run (SURVEY A.2 DecodeSymbol
     uint32_t alphabet;
     uint32_t count;          // symbols to decode; 0xFFFFFFFF = filled on device (entries * comps)
     uint32_t pb;             // rANS precision bits
+    uint32_t nnz;            // symbols with a non-zero probability
 };
 struct RabsStream { uint32_t data_off, data_len, prob_zero, pad; };
 
@@ -56,6 +57,7 @@ struct DracoFrame {
     uint64_t o_pcnt, o_pfirst, o_p2c;      // per-vertex point counts/offsets, dedup start corner, point -> corner
     uint64_t o_d2c[UVOL_MAX_ATTR_DATA + 1], o_v2d[UVOL_MAX_ATTR_DATA + 1], o_frec[UVOL_MAX_ATTR_DATA + 1], o_tstack[UVOL_MAX_ATTR_DATA + 1];
     uint64_t o_corr[UVOL_MAX_ATTRS], o_val_attr[UVOL_MAX_ATTRS], o_par[UVOL_MAX_ATTRS], o_auxbits[UVOL_MAX_ATTRS];
+    uint64_t o_corr_early[UVOL_MAX_ATTRS]; uint32_t corr_early_cap[UVOL_MAX_ATTRS];   // phase-1 arena: symbols decoded before the entry counts are known (and the capacity in symbols)
     // ---- outputs (device pointers as byte offsets into the output arena; filled after counts are known)
     uint64_t out_index, out_attr[4];
 };
@@ -72,6 +74,7 @@ struct DracoCounts {
     uint32_t attr_vertices[UVOL_MAX_ATTR_DATA];
     uint32_t entries[UVOL_MAX_ATTR_DATA + 1];   // per traversal table: [0] base, [1+i] attribute data i (written by the traversal)
     uint32_t expected[UVOL_MAX_ATTR_DATA + 1];  // entry counts known after phase 1 (valid vertices / attribute vertices)
+    uint32_t rans_early[UVOL_MAX_ATTRS];        // symbols the early (self-terminating) attribute runs produced
     uint32_t dbg[4];
 };
 
