@@ -128,3 +128,67 @@ def test_device_memory_outputs(uv, ctx):
     host = np.empty(g.num_faces * 3, np.uint32)
     assert rt.cudaMemcpy(host.ctypes.data_as(ctypes.c_void_p), ctypes.cast(g.index, ctypes.c_void_p), ctypes.c_size_t(host.nbytes), 2) == 0
     assert np.array_equal(host, oracle_draco(blobs[0])["index"])
+
+
+# ---- UASTC (KTX2 colour model 166): element-parallel block kernel vs oracle/uastc_oracle.c -------------------------
+def _uastc_file(size, layers, seed, mask=None, alpha=True, crop=None):
+    img = synth.texture_layers(size, 0, layers, seed)
+    if alpha:
+        img[..., 3] = ((np.arange(size)[None, :, None] * 5 + np.arange(size)[None, None, :] * 3) & 255).astype(np.uint8)
+    if crop:
+        img = img[:, :crop[0], :crop[1]]
+    return synth.encode_uastc(img, mode_mask=synth.UASTC_ALL_MODES if mask is None else mask, seed=seed, has_alpha=alpha)
+
+
+def test_uastc_every_mode(uv, ctx):
+    blobs = [_uastc_file(64, 2, 100 + m, mask=(1 << m)) for m in range(19)] + [_uastc_file(256, 3, 7)]
+    for r, b in zip(uv.KTX2Loader(ctx).transcode_batch(blobs), blobs):
+        o = oracle_ktx2(b)
+        assert r["status"] == o["status"] == 0 and (r["width"], r["height"], r["layers"]) == (o["width"], o["height"], o["layers"])
+        assert r["hasAlpha"] == o["has_alpha"]
+        assert np.array_equal(r["data"], o["rgba"])                                     # bit-exact texels
+
+
+def test_uastc_random_blocks(uv, ctx):
+    """Blocks of random bits exercise every field combination an encoder would never write; blocks the
+    transcoder rejects (reserved mode, pattern id out of range) are replaced so the file stays decodable."""
+    import struct
+    rng = np.random.default_rng(20260003)
+    blob = bytearray(_uastc_file(256, 1, 1))
+    lv = struct.unpack_from("<Q", blob, 80)[0]; n = 64 * 64
+    rnd = rng.integers(0, 256, (n, 16), dtype=np.uint8)
+    import ctypes
+    from oracle_bind import lib as olib
+    L = olib(); px = (ctypes.c_uint8 * 64)(); ok = 0
+    for i in range(n):
+        if L.uvo_uastc_block_to_rgba(rnd[i].ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), px) == 0:
+            blob[lv + 16 * i: lv + 16 * i + 16] = rnd[i].tobytes(); ok += 1
+    assert ok > n // 2
+    r = uv.KTX2Loader(ctx).transcode_batch([bytes(blob)])[0]
+    assert r["status"] == 0 and np.array_equal(r["data"], oracle_ktx2(bytes(blob))["rgba"])
+
+
+def test_uastc_edges_and_failures(uv, ctx):
+    import struct
+    good = _uastc_file(32, 1, 3)
+    ragged = _uastc_file(16, 2, 4, crop=(10, 13))
+    lv = struct.unpack_from("<Q", good, 80)[0]
+    reserved = bytearray(good); reserved[lv + 16 * 5] = 0x45                                 # mode 19
+    badpat = bytearray(good); badpat[lv:lv + 4] = struct.pack("<I", 0x1D | (0x7FFF << 5) | (31 << 20))
+    etc1s = synth.encode_etc1s(synth.texture_layers(64, 0, 2, 4))
+    blobs = [good, ragged, bytes(reserved), etc1s, bytes(badpat), good[:lv + 64]]
+    res = uv.KTX2Loader(ctx).transcode_batch(blobs)
+    assert [r["status"] for r in res] == [0, 0, -2, 0, -2, -1]
+    assert [oracle_ktx2(b)["status"] for b in blobs] == [0, 0, -2, 0, -2, -1]
+    for i in (0, 1, 3):
+        assert np.array_equal(res[i]["data"], oracle_ktx2(blobs[i])["rgba"])
+    assert res[1]["data"].shape == (2, 10, 13, 4)
+
+
+def test_uastc_full_size(uv, ctx):
+    """C3 texture size (2048^2, 7 layers): oracle parity on one segment, determinism across the batch."""
+    a = _uastc_file(2048, 7, 20260003, mask=synth.UASTC_OPAQUE_MODES, alpha=False)
+    res = uv.KTX2Loader(ctx).transcode_batch([a, a])
+    assert res[0]["status"] == 0 and res[0]["data"].shape == (7, 2048, 2048, 4) and (res[0]["data"][..., 3] == 255).all()
+    assert np.array_equal(res[0]["data"], res[1]["data"])
+    assert np.array_equal(res[0]["data"], oracle_ktx2(a)["rgba"])

@@ -31,6 +31,9 @@ def lib():
         L.uvsynth_draco_encode.restype = ctypes.c_size_t
         L.uvsynth_etc1s_encode.argtypes = [P(ctypes.c_uint8), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, P(P(ctypes.c_uint8))]
         L.uvsynth_etc1s_encode.restype = ctypes.c_size_t
+        L.uvsynth_uastc_encode.argtypes = [P(ctypes.c_uint8), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                           ctypes.c_int, P(P(ctypes.c_uint8))]
+        L.uvsynth_uastc_encode.restype = ctypes.c_size_t
         L.uvsynth_free.argtypes = [ctypes.c_void_p]
         _lib = L
     return _lib
@@ -147,6 +150,24 @@ def encode_etc1s(layers_rgba, max_endpoints=4096):
     n = L.uvsynth_etc1s_encode(a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), a.shape[2], a.shape[1], a.shape[0], max_endpoints, ctypes.byref(out))
     if n == 0:
         raise RuntimeError("uvsynth_etc1s_encode failed")
+    blob = ctypes.string_at(out, n)
+    L.uvsynth_free(out)
+    return blob
+
+
+UASTC_OPAQUE_MODES = 0x401FF          # modes 0-8 and 18: what an encoder picks for opaque RGB content
+UASTC_ALL_MODES = 0x7FFFF
+
+
+def encode_uastc(layers_rgba, mode_mask=UASTC_OPAQUE_MODES, seed=1, has_alpha=False):
+    """KTX2 (UASTC, no supercompression) of `layers_rgba` [layers, h, w, 4]; any width / height."""
+    L = lib()
+    a = np.ascontiguousarray(layers_rgba, np.uint8)
+    out = ctypes.POINTER(ctypes.c_uint8)()
+    n = L.uvsynth_uastc_encode(a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), a.shape[2], a.shape[1], a.shape[0], mode_mask, seed, int(has_alpha),
+                               ctypes.byref(out))
+    if n == 0:
+        raise RuntimeError("uvsynth_uastc_encode failed")
     blob = ctypes.string_at(out, n)
     L.uvsynth_free(out)
     return blob

@@ -14,8 +14,8 @@
 #include "basis_core.h"
 
 int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
-void uvol_uastc_launch(const Ktx2File *dF, const int32_t *dStatus, const uint8_t *dBlob, uint8_t *dOut, const uint32_t *dLayerList, int nlayers,
-                       uint32_t max_blocks, cudaStream_t st);
+int uvol_uastc_launch(int device, const Ktx2File *dF, int32_t *status2, const uint8_t *dBlob, uint8_t *dOut, const uint32_t *dLayerList, int nlayers,
+                      uint32_t max_blocks, cudaStream_t st);
 
 namespace {
 
@@ -179,7 +179,7 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
         const uint64_t nblk = (uint64_t)f.bx * f.by;
         if (nblk > B.max_blocks) B.max_blocks = (uint32_t)nblk;
         f.o_rgba = take(o, (uint64_t)f.layers * f.width * f.height * 4);
-        if (f.is_uastc) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }   // until uastc_transcode.cu lands
+        if (f.is_uastc) { for (uint32_t L = 0; L < f.layers; L++) B.uastc_layers.push_back(((uint32_t)i << 12) | L); continue; }   // no entropy stage, no scratch
         B.any_alpha |= f.has_alpha != 0;
         const uint64_t pool = (uint64_t)f.endpoint_count + f.selector_count + 8192 + 1024;
         f.o_endpoints = take(s, (uint64_t)f.endpoint_count * 4); f.o_selectors = take(s, (uint64_t)f.selector_count * 4);
@@ -241,7 +241,7 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
     if (nsl) { k_etc1s_resolve<<<dim3(nb4, B.any_alpha ? 2 : 1), 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dSl, dS, n); launches++; }
     stamp();
     if (nll) { k_etc1s_blocks<<<dim3((B.max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO); launches++; }
-    if (nul) { uvol_uastc_launch(dF, (const int32_t *)dSt, dBlob, dO, dUL, (int)nul, B.max_blocks, st); launches++; }
+    if (nul) { UVOL_CUDA(ctx, (cudaError_t)uvol_uastc_launch(ctx->device, dF, (int32_t *)dSt, dBlob, dO, dUL, (int)nul, B.max_blocks, st)); launches++; }
     stamp();
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
     UVOL_CUDA(ctx, ctx->h_tout.reserve(st_bytes + (memory == UVOL_MEM_HOST ? B.out + 256 : 0)));
