@@ -4,11 +4,14 @@
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
 prints ONE JSON line on rank 0.
 
-Workload at N=1: BASELINE.json configs[1] -- a synthetic 300-frame V2 sequence, 50k verts/frame
-Draco geometry, 1024^2 ETC1S KTX2 textures with sequenceSize 7 (43 segments), built by
-tools/synth (deterministic, seed 20260002).  One "step" = one pass of the hot path over the whole
-sequence (300 .drc + 43 .ktx2).  N>1: every rank decodes its own 300-frame sequence (frames are
-independent units, no data-path collective) -> "scaling": "weak"; value = all frames / max-over-ranks time.
+Workload at N=1 (default `--workload c3`): the configuration BASELINE.json's metric is quoted on, configs[2] -- a
+synthetic 1000-frame V2 sequence, 200k verts/frame Draco geometry, 2048^2 UASTC KTX2 textures with sequenceSize 7
+(143 segments), built by tools/synth (deterministic).  `--workload c2` is configs[1] (300 frames, 50k verts, 1024^2
+ETC1S).  One "step" = one pass of the hot path over the whole sequence.  A sequence whose scratch does not fit HBM at
+once is decoded in WINDOWS of whole segments (the prefetch window of src/V2/player.ts:272-323); every window's
+compressed inputs stay resident in HBM (one ctx per window), the scratch / output arenas exist once (uvol_share_arenas).
+N>1: every rank decodes its own sequence (frames are independent units, no data-path collective) -> "scaling": "weak";
+value = all frames / max-over-ranks time.
 
   value     frames/s with the compressed inputs already resident in HBM (uvol_replay_v2_batch), device
             time from CUDA events on the library's streams (geometry and texture run concurrently, the
@@ -39,9 +42,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "decoded frames/sec (geom+tex)"
 WORKLOADS = {
-    # name: (frames, verts, tex_size, sequence_size, seed)
-    "c2": (300, 50000, 1024, 7, 20260002),
-    "tiny": (14, 2000, 64, 7, 20260009),
+    # window_segments: segments decoded per library call (None = the whole sequence at once); distinct_*: how many distinct
+    # frames / segments are actually encoded by the generator (the rest cycle through them) to bound generation time.
+    "c3": dict(frames=1000, verts=200000, tex=2048, seq=7, seed=20260003, fmt="uastc", window_segments=72, distinct_geo=32, distinct_tex=6,
+               label="configs[2]: 1000-frame V2 seq, 200k verts/frame Draco, 2048^2 UASTC KTX2 batch=7"),
+    "c2": dict(frames=300, verts=50000, tex=1024, seq=7, seed=20260002, fmt="etc1s", window_segments=None, distinct_geo=None, distinct_tex=None,
+               label="configs[1]: 300-frame V2 seq, 50k verts/frame Draco, 1024^2 ETC1S KTX2 batch=7"),
+    "tiny": dict(frames=28, verts=2000, tex=64, seq=7, seed=20260009, fmt="uastc", window_segments=2, distinct_geo=None, distinct_tex=None,
+                 label="tiny smoke workload"),
 }
 
 
@@ -89,11 +97,18 @@ class ClockSampler:
 
 def make_workload(name, rank):
     from tools.synth import synth
-    frames, verts, tex, seq, seed = WORKLOADS[name]
+    w = WORKLOADS[name]
     t0 = time.time()
-    drc, ktx, info = synth.make_sequence(frames, verts, tex, sequence_size=seq, seed=seed + 1000 * rank)
+    drc, ktx, info = synth.make_sequence(w["frames"], w["verts"], w["tex"], sequence_size=w["seq"], seed=w["seed"] + 1000 * rank,
+                                         distinct_geometry=w["distinct_geo"], distinct_textures=w["distinct_tex"], texture_format=w["fmt"])
     info["gen_s"] = round(time.time() - t0, 2)
     return drc, ktx, info
+
+
+def make_windows(drc, ktx, seq, window_segments):
+    """Splits the sequence into windows of whole segments: [(drc files, ktx2 files)]."""
+    ws = window_segments or max(1, len(ktx))
+    return [(drc[s * seq:(s + ws) * seq], ktx[s:s + ws]) for s in range(0, max(1, len(ktx)), ws)]
 
 
 def cpu_oracle_run(drc, ktx, threads):
@@ -119,12 +134,12 @@ def cpu_oracle_run(drc, ktx, threads):
 
 
 def cpu_sample(drc, ktx, seq, nseg):
-    """Bounded sample of the same workload: nseg segments and the geometry frames they cover."""
-    nseg = min(nseg, len(ktx))
+    """Bounded sample of the same workload: the first nseg FULL segments and the geometry frames they cover."""
+    nseg = max(1, min(nseg, len(ktx) - 1 if len(drc) % seq else len(ktx)))
     return drc[: nseg * seq], ktx[:nseg]
 
 
-def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex):
+def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex, fmt):
     """ALGORITHMIC bytes per step for each kernel stage (DESIGN.md 'Kernels and rooflines')."""
     F, V = info["faces"], info["verts"]
     nblk = (info["tex_size"] // 4) ** 2
@@ -144,7 +159,7 @@ def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex):
     t = {
         "slices": bytes_in_tex + frames * nblk * 5,                            # VLC bits in, {pred u8, delta/selector u16} out
         "resolve": frames * nblk * (1 + 2 + 2 + 2),
-        "blocks": frames * nblk * (4 + 64),                                    # 2x u16 indices in, 64 B RGBA out
+        "blocks": frames * nblk * ((16 if fmt == "uastc" else 4) + 64),          # UASTC: 16 B block in; ETC1S: 2x u16 indices in; 64 B RGBA out
     }
     return g, t
 
@@ -155,20 +170,24 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--window-segments", type=int, default=0, help="override the workload's window size (segments per library call)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    frames, verts, tex, seq, seed = WORKLOADS[args.workload]
+    W = dict(WORKLOADS[args.workload])
+    if args.window_segments > 0:
+        W["window_segments"] = args.window_segments
+    frames, verts, tex, seq, seed = W["frames"], W["verts"], W["tex"], W["seq"], W["seed"]
     ncores = os.cpu_count() or 1
-    workload_name = f"configs[1]: {frames}-frame V2 seq, {verts // 1000}k verts/frame Draco, {tex}^2 ETC1S KTX2 batch={seq} (synthetic, tools/synth seed {seed})"
+    workload_name = f"{W['label']} (synthetic, tools/synth seed {seed})"
 
     # ------------------------------------------------------------------ reference arm (CPU oracle)
     if args.impl == "reference":
         if rank != 0:
             return 0
         drc, ktx, info = make_workload(args.workload, 0)
-        sd, sk = cpu_sample(drc, ktx, seq, 6)                       # 42 frames + 6 segments per step
+        sd, sk = cpu_sample(drc, ktx, seq, ncores)                  # one segment per host thread (+ the frames they cover) per step
         for _ in range(max(1, min(args.warmup, 1))):
             cpu_oracle_run(sd[:seq], sk[:1], ncores)
         t0 = time.perf_counter(); pts = tx = 0
@@ -193,31 +212,48 @@ def main():
     torch.cuda.set_device(local)
     uv = importlib.import_module("universal-volumetric_b200")
     drc, ktx, info = make_workload(args.workload, rank)
-    ctx = uv.Context(local, profiling=True)
-    player = uv.V2Player(ctx)
-    n_d, n_k = len(drc), len(ktx)
+    windows = make_windows(drc, ktx, seq, W["window_segments"])
+    ctxs = [uv.Context(local, profiling=True) for _ in windows]
+    for c in ctxs[1:]:
+        c.share_arenas(ctxs[0])
+    players = [uv.V2Player(c) for c in ctxs]
+    ctx = ctxs[0]
+    n_k = len(ktx)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def e2e_step():
-        g, t = player.decode_step_raw(drc, ktx, uv.MEM_HOST)
-        return g, t, ctx.stats(0, combined=True), ctx.stats(1, combined=True)
+    def merge(acc, s):
+        if acc is None:
+            return {**s, "stages": dict(s["stages"])}
+        for k in ("device_ms", "kernel_launches", "bytes_in", "bytes_out", "host_parse_ms", "h2d_ms", "d2h_ms", "total_ms"):
+            acc[k] += s[k]
+        acc["scratch_bytes"] = max(acc["scratch_bytes"], s["scratch_bytes"])
+        for k, v in s["stages"].items():
+            acc["stages"][k] = acc["stages"].get(k, 0.0) + v
+        return acc
 
-    def resident_step():
-        g, t = player.replay_step_raw(n_d, n_k, uv.MEM_DEVICE)
-        return g, t, ctx.stats(0, combined=True), ctx.stats(1, combined=True)
+    def run_step(resident):
+        """One pass over the sequence, window by window.  Returns per-window results of the LAST window only (the arenas are
+        shared), the summed statistics, the device time (per window: the longer of the geometry / texture spans) and counts."""
+        sg = st = None; dev = 0.0; pts = fcs = txl = bad = 0
+        for p, c, (wd, wk) in zip(players, ctxs, windows):
+            g, t = p.replay_step_raw(len(wd), len(wk), uv.MEM_DEVICE) if resident else p.decode_step_raw(wd, wk, uv.MEM_HOST)
+            a, b = c.stats(0, combined=True), c.stats(1, combined=True)
+            dev += max(a["device_ms"], b["device_ms"]); sg = merge(sg, a); st = merge(st, b)
+            bad += sum(x.status != 0 for x in g[:len(wd)]) + sum(x.status != 0 for x in t[:len(wk)])
+            pts += sum(x.num_points for x in g[:len(wd)]); fcs += sum(x.num_faces for x in g[:len(wd)])
+            txl += sum(x.width * x.height * x.layers for x in t[:len(wk)])
+        return sg, st, dev, (pts, fcs, txl, bad)
 
     # warm-up (also uploads the batch that the resident steps replay)
     for _ in range(max(args.warmup, 1)):
-        g, t, sg, st = e2e_step()
-    assert all(x.status == 0 for x in g) and all(x.status == 0 for x in t), "decode failed on the bench workload"
-    P_total = sum(x.num_points for x in g); F_total = sum(x.num_faces for x in g)
-    texels = sum(x.width * x.height * x.layers for x in t)
+        sg, st, _, (P_total, F_total, texels, bad) = run_step(False)
+    assert bad == 0, "decode failed on the bench workload"
     for _ in range(max(args.warmup, 1)):
-        resident_step()
+        run_step(True)
 
     clocks = ClockSampler(local); clocks.start()
     # ---- timed: resident inputs (value)
@@ -225,8 +261,8 @@ def main():
     barrier(); t0 = time.perf_counter()
     for _ in range(args.steps):
         ctx.flush_l2()
-        g, t, sg, st = resident_step()
-        dev_ms += max(sg["device_ms"], st["device_ms"]); launches += sg["kernel_launches"] + st["kernel_launches"]
+        sg, st, dms, _ = run_step(True)
+        dev_ms += dms; launches += sg["kernel_launches"] + st["kernel_launches"]
         for k, v in list(sg["stages"].items()) + [("tex_" + k, v) for k, v in st["stages"].items()]:
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     barrier(); wall_resident = time.perf_counter() - t0
@@ -235,7 +271,7 @@ def main():
     barrier()
     for _ in range(args.steps):
         ctx.flush_l2()
-        t1 = time.perf_counter(); g, t, sg, st = e2e_step(); e2e_s += time.perf_counter() - t1
+        t1 = time.perf_counter(); sg, st, _, _ = run_step(False); e2e_s += time.perf_counter() - t1
         launches_e2e = sg["kernel_launches"] + st["kernel_launches"]
     barrier()
     clk = clocks.stop()
@@ -249,7 +285,7 @@ def main():
 
     # ---- roofline per stage
     peak, peak_src = measured_peak()
-    gb, tb = stage_bytes(info, P_total, frames, sg["bytes_in"], st["bytes_in"])
+    gb, tb = stage_bytes(info, P_total, frames, sg["bytes_in"], st["bytes_in"], W["fmt"])
     stages = {}
     for k, ms in stage_acc.items():
         nbytes = gb.get(k.replace("(s1)", "")) if not k.startswith("tex_") else tb.get(k[4:])
@@ -282,11 +318,11 @@ def main():
         # ---- cpu baseline on a bounded sample (rank 0, N=1 only)
         cpu = None
         if world == 1:
-            nseg = 2
+            nseg = min(ncores, len(ktx))
             sd, sk = cpu_sample(drc, ktx, seq, nseg)
             tg, tt, p, x = cpu_oracle_run(sd, sk, ncores)          # probe
             per_seg = max(tg + tt, 1e-3) / nseg
-            nseg = int(max(2, min(len(ktx), args.cpu_seconds / per_seg)))
+            nseg = int(max(min(ncores, len(ktx)), min(len(ktx), args.cpu_seconds / per_seg)))
             sd, sk = cpu_sample(drc, ktx, seq, nseg)
             tg, tt, p, x = cpu_oracle_run(sd, sk, ncores)
             cpu = {"value": len(sd) / (tg + tt), "unit": "frames/s", "cores": ncores, "kind": "port",
@@ -296,17 +332,22 @@ def main():
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
                 "data": "synthetic",
                 "config": {"workload": workload_name, "frames_per_gpu": frames, "segments_per_gpu": n_k, "verts": info["verts"], "faces": info["faces"],
-                           "points_per_frame": P_total / frames, "distinct_geometry_frames": info["distinct_geometry"], "l2": "flushed between timed iterations (256 MiB memset)",
+                           "points_per_frame": P_total / frames, "distinct_geometry_frames": info["distinct_geometry"], "distinct_texture_segments": info["distinct_textures"],
+                           "windows": [len(wd) for wd, _ in windows], "scratch_gb": round((sg["scratch_bytes"] + st["scratch_bytes"]) / 1e9, 2),
+                           "l2": "flushed between timed iterations (256 MiB memset); every window's working set is far larger than L2",
                            "parallelism": f"frames sharded, {world} rank(s), no data-path collective"},
                 "mverts_per_s": P_total * world * args.steps / (dev_ms / 1e3) / 1e6, "mtexels_per_s": texels * world * args.steps / (dev_ms / 1e3) / 1e6,
                 "roofline": roof, "pipeline_roofline": pipeline, "stages": stages,
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
-                        "path": "uvol_decode_v2_batch (geometry and texture streams concurrent), UVOL_MEM_HOST"},
+                        "path": "uvol_decode_v2_batch per window (geometry and texture streams concurrent), UVOL_MEM_HOST",
+                        "breakdown_ms_per_step": {"geo_host_parse": sg["host_parse_ms"], "geo_h2d": sg["h2d_ms"], "geo_kernels": sg["device_ms"], "geo_d2h": sg["d2h_ms"],
+                                                  "geo_call_total": sg["total_ms"], "tex_host_parse": st["host_parse_ms"], "tex_h2d": st["h2d_ms"], "tex_kernels": st["device_ms"], "tex_d2h": st["d2h_ms"]}},
                 "gpu_launches": launches + launches_e2e * args.steps, "clocks": clk,
                 "wall_ms_per_step_resident": wall_resident / args.steps * 1e3, "workload_gen_s": info["gen_s"]}
         print(json.dumps(line))
-    ctx.close()
+    for c in reversed(ctxs):
+        c.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -123,6 +123,12 @@ typedef struct uvol_corto_mesh {
 } uvol_corto_mesh;
 int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int memory, uvol_corto_mesh *out);
 
+/* Makes `ctx` use the scratch / output arenas of `owner` (same device) instead of allocating its own.  For sequences
+ * decoded in WINDOWS (the prefetch window of src/V2/player.ts:272-323, `fps x bufferDuration` frames): one ctx per window
+ * keeps that window's compressed inputs resident in HBM, all of them share one set of scratch / output arenas.  Results of
+ * a ctx are then valid until the next batch call on ANY ctx sharing the arenas; calls must be serialised across them. */
+int uvol_share_arenas(uvol_ctx *ctx, uvol_ctx *owner);
+
 /* Writes a buffer larger than L2 (256 MiB) on the ctx's stream and waits: L2 flush between timed iterations. */
 int uvol_flush_l2(uvol_ctx *ctx);
 

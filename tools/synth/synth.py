@@ -173,9 +173,11 @@ def encode_uastc(layers_rgba, mode_mask=UASTC_OPAQUE_MODES, seed=1, has_alpha=Fa
     return blob
 
 
-def make_sequence(frames, verts, tex_size, sequence_size=7, seed=20260002, threads=None, want_textures=True, distinct_geometry=None):
-    """Returns (list of .drc bytes, list of .ktx2 bytes, info).  `distinct_geometry` bounds the number of
-    distinct frames that are actually encoded (the rest cycle through them), to bound generation time."""
+def make_sequence(frames, verts, tex_size, sequence_size=7, seed=20260002, threads=None, want_textures=True, distinct_geometry=None,
+                  distinct_textures=None, texture_format="etc1s"):
+    """Returns (list of .drc bytes, list of .ktx2 bytes, info).  `distinct_geometry` / `distinct_textures` bound the number
+    of distinct frames / segments that are actually encoded (the rest cycle through them), to bound generation time.
+    texture_format: "etc1s" (BasisLZ video) or "uastc"."""
     rings, segs = sphere_dims(verts)
     fp, fu, uv, nv = sphere_topology(rings, segs)
     ng = frames if distinct_geometry is None else min(frames, distinct_geometry)
@@ -188,13 +190,17 @@ def make_sequence(frames, verts, tex_size, sequence_size=7, seed=20260002, threa
     def one_tex(s):
         first = s * sequence_size
         cnt = min(sequence_size, frames - first)
-        return encode_etc1s(texture_layers(tex_size, first, cnt, seed + 7))
+        layers = texture_layers(tex_size, first, cnt, seed + 7)
+        return encode_uastc(layers, seed=seed + s) if texture_format == "uastc" else encode_etc1s(layers)
 
     nseg = (frames + sequence_size - 1) // sequence_size
+    nt = nseg if distinct_textures is None else min(nseg, distinct_textures)
+    todo = list(range(nt)) + ([nseg - 1] if nt < nseg and frames % sequence_size else [])     # a short last segment is encoded as itself
     with ThreadPoolExecutor(threads) as ex:
         geo = list(ex.map(one_geo, range(ng)))
-        tex = list(ex.map(one_tex, range(nseg))) if want_textures else []
+        enc = dict(zip(todo, ex.map(one_tex, todo))) if want_textures else {}
+    tex = [enc.get(s, enc.get(s % nt)) for s in range(nseg)] if want_textures else []
     drc = [geo[i % ng] for i in range(frames)]
     info = {"verts": nv, "faces": len(fp), "rings": rings, "segs": segs, "frames": frames, "segments": nseg, "sequence_size": sequence_size,
-            "tex_size": tex_size, "distinct_geometry": ng, "seed": seed}
+            "tex_size": tex_size, "distinct_geometry": ng, "distinct_textures": nt, "texture_format": texture_format, "seed": seed}
     return drc, tex, info

@@ -10,6 +10,7 @@
 // UASTC files skip the first three stages (no entropy coding) and run the block kernel in uastc_transcode.cu.
 #include <chrono>
 #include <string.h>
+#include <thread>
 #include "uvol_ctx.h"
 #include "basis_core.h"
 
@@ -193,15 +194,24 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
     B.blob_bytes = blob_bytes; B.scratch = s; B.out = o;
     const size_t nsl = slices.size(), nll = B.layer_list.size(), nul = B.uastc_layers.size();
     UVOL_CUDA(ctx, ctx->h_tblob.reserve(blob_bytes + 64));
-    for (int i = 0; i < n; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_tblob.p + files[i].file_off, data[i], size[i]);
+    {   // staging copy into the pinned blob; UASTC segments are large (29 MB each at 2048^2 x 7), so big batches are copied by several threads
+        auto copy_range = [&](int lo, int hi) { for (int i = lo; i < hi; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_tblob.p + files[i].file_off, data[i], size[i]); };
+        const int nthreads = B.bytes_in > (64ull << 20) ? (int)std::min<uint64_t>(8, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1;
+        if (nthreads <= 1 || n < 2) copy_range(0, n);
+        else {
+            std::vector<std::thread> pool; int lo = 0; uint64_t acc = 0; const uint64_t per = B.bytes_in / nthreads + 1;
+            for (int i = 0; i < n; i++) { acc += size[i]; if (acc >= per || i == n - 1) { pool.emplace_back(copy_range, lo, i + 1); lo = i + 1; acc = 0; } }
+            for (auto &t : pool) t.join();
+        }
+    }
     B.off_sl = sizeof(Ktx2File) * (size_t)n; B.off_ll = B.off_sl + sizeof(Ktx2Slice) * (nsl + 1); B.off_ul = B.off_ll + 4 * (nll + 1);
     B.desc_bytes = B.off_ul + 4 * (nul + 1);
     UVOL_CUDA(ctx, ctx->h_tdesc.reserve(B.desc_bytes));
     UVOL_CUDA(ctx, ctx->d_tdesc.reserve(B.desc_bytes));
     UVOL_CUDA(ctx, ctx->d_tblob.reserve(blob_bytes + 64));
     UVOL_CUDA(ctx, ctx->d_tslices.reserve(sizeof(TexState) * (size_t)n));
-    UVOL_CUDA(ctx, ctx->d_tscratch.reserve(s + 256));
-    UVOL_CUDA(ctx, ctx->d_out_tex.reserve(o + 256));
+    UVOL_CUDA(ctx, ctx->ar->d_tscratch.reserve(s + 256));
+    UVOL_CUDA(ctx, ctx->ar->d_out_tex.reserve(o + 256));
     uint8_t *hd = (uint8_t *)ctx->h_tdesc.p;
     memcpy(hd, files.data(), sizeof(Ktx2File) * (size_t)n);
     if (nsl) memcpy(hd + B.off_sl, slices.data(), sizeof(Ktx2Slice) * nsl);
@@ -228,7 +238,7 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
     const Ktx2File *dF = (const Ktx2File *)dD; const Ktx2Slice *dSl = (const Ktx2Slice *)(dD + B.off_sl);
     const uint32_t *dLL = (const uint32_t *)(dD + B.off_ll), *dUL = (const uint32_t *)(dD + B.off_ul);
     TexState *dSt = (TexState *)ctx->d_tslices.p; const uint8_t *dBlob = (const uint8_t *)ctx->d_tblob.p;
-    uint8_t *dS = (uint8_t *)ctx->d_tscratch.p, *dO = (uint8_t *)ctx->d_out_tex.p;
+    uint8_t *dS = (uint8_t *)ctx->ar->d_tscratch.p, *dO = (uint8_t *)ctx->ar->d_out_tex.p;
     uint32_t launches = 0;
     const unsigned nb4 = (unsigned)((n + SERIAL_WARPS - 1) / SERIAL_WARPS);
     k_basis_globals<<<nb4, 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dBlob, dS, n); launches++;
@@ -244,8 +254,8 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
     if (nul) { UVOL_CUDA(ctx, (cudaError_t)uvol_uastc_launch(ctx->device, dF, (int32_t *)dSt, dBlob, dO, dUL, (int)nul, B.max_blocks, st)); launches++; }
     stamp();
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
-    UVOL_CUDA(ctx, ctx->h_tout.reserve(st_bytes + (memory == UVOL_MEM_HOST ? B.out + 256 : 0)));
-    TexState *hSt = (TexState *)ctx->h_tout.p; uint8_t *hO = (uint8_t *)ctx->h_tout.p + st_bytes;
+    UVOL_CUDA(ctx, ctx->ar->h_tout.reserve(st_bytes + (memory == UVOL_MEM_HOST ? B.out + 256 : 0)));
+    TexState *hSt = (TexState *)ctx->ar->h_tout.p; uint8_t *hO = (uint8_t *)ctx->ar->h_tout.p + st_bytes;
     UVOL_CUDA(ctx, cudaMemcpyAsync(hSt, dSt, sizeof(TexState) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(hO, dO, B.out, cudaMemcpyDeviceToHost, st));
     stamp();
@@ -258,8 +268,8 @@ static int ktx2_finish(uvol_ctx *ctx, int memory, uvol_texture *out, uvol_stats 
     TexBatch &B = *ctx->tex; const int n = B.n;
     UVOL_CUDA(ctx, cudaGetLastError());
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
-    TexState *hSt = (TexState *)ctx->h_tout.p; uint8_t *hO = (uint8_t *)ctx->h_tout.p + st_bytes;
-    uint8_t *base = memory == UVOL_MEM_HOST ? hO : (uint8_t *)ctx->d_out_tex.p; uint64_t bytes_out = 0;
+    TexState *hSt = (TexState *)ctx->ar->h_tout.p; uint8_t *hO = (uint8_t *)ctx->ar->h_tout.p + st_bytes;
+    uint8_t *base = memory == UVOL_MEM_HOST ? hO : (uint8_t *)ctx->ar->d_out_tex.p; uint64_t bytes_out = 0;
     for (int i = 0; i < n; i++) {
         const Ktx2File &f = B.files[i]; uvol_texture &t = out[i];
         memset(&t, 0, sizeof t);
@@ -320,9 +330,19 @@ extern "C" int uvol_decode_v2_batch(uvol_ctx *ctx, const uint8_t *const *drc, co
     UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->stats, 0, sizeof ctx->stats); memset(&ctx->stats_tex, 0, sizeof ctx->stats_tex);
     const double t0 = now_ms();
-    int rc;
-    if (n_ktx2) { rc = ktx2_prepare(ctx, ktx2, ktx2_size, n_ktx2); if (rc) return rc; rc = ktx2_launch(ctx, memory, true, ctx->s2); if (rc) return rc; }
-    if (n_drc) { rc = uvol_geo_prepare_and_run(ctx, drc, drc_size, n_drc, memory, out_geo, false); if (rc) return rc; }
+    int rc = UVOL_OK, rc_tex = UVOL_OK;
+    // The texture side (container parse, staging copy of the segments, upload, kernels, result copy on s2) is driven by a helper
+    // thread while this thread drives the geometry side, so neither side's host work delays the other's GPU work.
+    std::thread tex_thread;
+    if (n_ktx2) tex_thread = std::thread([&]() {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) { rc_tex = UVOL_ERR_CUDA; return; }
+        rc_tex = ktx2_prepare(ctx, ktx2, ktx2_size, n_ktx2);
+        if (!rc_tex) rc_tex = ktx2_launch(ctx, memory, true, ctx->s2);
+    });
+    if (n_drc) rc = uvol_geo_prepare_and_run(ctx, drc, drc_size, n_drc, memory, out_geo, false);
+    if (n_ktx2) tex_thread.join();
+    if (rc) return rc;
+    if (rc_tex) return rc_tex;
     if (n_ktx2) { UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s2)); rc = ktx2_finish(ctx, memory, out_tex, ctx->stats_tex); if (rc) return rc; ctx->stats_tex.host_parse_ms = ctx->tex->parse_ms; }
     ctx->stats.total_ms = ctx->stats_tex.total_ms = now_ms() - t0;
     return UVOL_OK;

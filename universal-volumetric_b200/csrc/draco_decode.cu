@@ -12,6 +12,7 @@
 #include <chrono>
 #include <string.h>
 #include <stdlib.h>
+#include <thread>
 #include "uvol_ctx.h"
 #include "draco_core.h"
 #include "draco_plan.h"
@@ -870,46 +871,71 @@ __global__ void __launch_bounds__(256) k_face_dups(const DracoFrame *frames, con
 #define TRAV_STACK 512
 #define TRAV_WARPS 1          // one walk per block: 21 KB of bitmaps each, so the blocks pack around whatever else is resident (entropy runs, texture slices)
 __device__ __forceinline__ unsigned face_of(int c) { return __umulhi((unsigned)c, 0xAAAAAAABu) >> 1; }
+// GMAP = false: visited-face / visited-vertex bitmaps in shared memory (F/8 + V/8 bytes per walk: fastest while all walks of
+// the batch are co-resident).  GMAP = true: a byte per face in global memory plus the vertex -> entry map itself as the
+// visited-vertex test -- 2 KB of shared memory per walk, so large meshes (C3: 77 KB of bitmaps per walk) no longer cap the
+// SM at two walks.  Only this warp touches those bytes, so plain (L1-cached) loads / stores ordered by warp barriers suffice.
+template <bool GMAP>
 __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, uint8_t *Z2,
                                                  const Job *jobs, int njobs, int fwords_max, int vwords_max) {
     extern __shared__ uint32_t sm_all[];
     const int ji = blockIdx.x * TRAV_WARPS + (threadIdx.x >> 5);
     if (ji >= njobs) return;
-    uint32_t *sm = sm_all + (size_t)(threadIdx.x >> 5) * (fwords_max + vwords_max + TRAV_STACK);
+    uint32_t *sm = sm_all + (size_t)(threadIdx.x >> 5) * ((GMAP ? 0 : fwords_max + vwords_max) + TRAV_STACK);
     const Job jb = jobs[ji];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
     if (f.o_d2c[t] == UVOL_NONE) return;
     const int F = (int)f.nf, C = 3 * F, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    uint32_t *fbits = sm, *vbits = sm + fwords_max; int *stk = (int *)(sm + fwords_max + vwords_max);
-    for (int i = lane; i < fwords_max + vwords_max; i += 32) sm[i] = 0;
+    uint32_t *fbits = sm, *vbits = sm + (GMAP ? 0 : fwords_max); int *stk = (int *)(sm + (GMAP ? 0 : fwords_max + vwords_max));
+    if (!GMAP) for (int i = lane; i < fwords_max + vwords_max; i += 32) sm[i] = 0;
     const uint4 *grec = (const uint4 *)(S2 + f.o_frec[t]), *gup = grec + 3 * (size_t)F + 4, *gdn = gup + F + 4;
     int *d2c = (int *)(S2 + f.o_d2c[t]), *v2d1 = (int *)(Z2 + f.o_v2d[t]), *gst = (int *)(S2 + f.o_tstack[t]);
+    uint8_t *fvis = Z2 + f.o_fvis[t];                        // GMAP only (zero-initialised with the arena)
     __syncwarp();
     int n = 0, sp = 0, c = -1, fscan = 0, status = 0, pdir = 1;
-#define FBIT(x) ((fbits[(x) >> 5] >> ((x) & 31)) & 1u)
-#define VBIT(x) ((vbits[(x) >> 5] >> ((x) & 31)) & 1u)
+#define FBIT(x) (GMAP ? (uint32_t)fvis[(x)] : ((fbits[(x) >> 5] >> ((x) & 31)) & 1u))
+#define VBIT(x) (GMAP ? (uint32_t)(v2d1[(x)] != 0) : ((vbits[(x) >> 5] >> ((x) & 31)) & 1u))
     for (;;) {
         if (c < 0) {
-            // ---- pick the next corner (lane 0): stack top, else the next unvisited face starts a component
-            int done = 0;
+            // ---- pick the next corner: stack top (lane 0), else the next unvisited face starts a component
+            int done = 0, scan = 0;
             if (lane == 0) {
                 for (;;) {
-                    if (sp == 0) {
-                        int w = fscan >> 5; uint32_t m = ~fbits[w] & (0xffffffffu << (fscan & 31));
-                        while (m == 0 && w + 1 < fwords_max) { w++; m = ~fbits[w]; }
-                        const int nf = m ? w * 32 + __ffs(m) - 1 : F;
-                        if (nf >= F) { done = 1; break; }
-                        fscan = nf; c = 3 * nf; stk[0] = c; sp = 1;
-                        const unsigned vn = grec[c + 1].x & TIP_MASK, vp = grec[c + 2].x & TIP_MASK;     // next / previous vertices first
-                        if (!VBIT(vn)) { vbits[vn >> 5] |= 1u << (vn & 31); v2d1[vn] = ++n; d2c[n - 1] = c + 1; }
-                        if (!VBIT(vp)) { vbits[vp >> 5] |= 1u << (vp & 31); v2d1[vp] = ++n; d2c[n - 1] = c + 2; }
-                        break;
-                    }
+                    if (sp == 0) { scan = 1; break; }
                     c = sp <= TRAV_STACK ? stk[sp - 1] : gst[sp - 1];
                     if (c < 0 || FBIT(face_of(c))) { sp--; c = -1; continue; }
                     break;
+                }
+            }
+            scan = __shfl_sync(0xffffffffu, scan, 0);
+            if (scan) {
+                int nf = F;
+                if (GMAP) {          // all lanes: 128 faces per round, four visited-bytes per lane
+                    fscan = __shfl_sync(0xffffffffu, fscan, 0);
+                    for (int base = fscan & ~127; base < F && nf == F; base += 128) {
+                        const int i0 = base + lane * 4;
+                        const uint32_t w = i0 < F ? *(const uint32_t *)(fvis + i0) : 0x01010101u;
+                        int first = F;
+#pragma unroll
+                        for (int k = 3; k >= 0; k--) if (((w >> (8 * k)) & 255u) == 0 && i0 + k < F && i0 + k >= fscan) first = i0 + k;
+                        const unsigned any = __ballot_sync(0xffffffffu, first < F);
+                        if (any) nf = __shfl_sync(0xffffffffu, first, __ffs(any) - 1);
+                    }
+                } else if (lane == 0) {
+                    int w = fscan >> 5; uint32_t m = ~fbits[w] & (0xffffffffu << (fscan & 31));
+                    while (m == 0 && w + 1 < fwords_max) { w++; m = ~fbits[w]; }
+                    nf = m ? w * 32 + __ffs(m) - 1 : F;
+                }
+                if (lane == 0) {
+                    if (nf >= F) done = 1;
+                    else {
+                        fscan = nf; c = 3 * nf; stk[0] = c; sp = 1;
+                        const unsigned vn = grec[c + 1].x & TIP_MASK, vp = grec[c + 2].x & TIP_MASK;     // next / previous vertices first
+                        if (!VBIT(vn)) { if (!GMAP) vbits[vn >> 5] |= 1u << (vn & 31); v2d1[vn] = ++n; d2c[n - 1] = c + 1; }
+                        if (!VBIT(vp)) { if (!GMAP) vbits[vp >> 5] |= 1u << (vp & 31); v2d1[vp] = ++n; d2c[n - 1] = c + 2; }
+                    }
                 }
             }
             __syncwarp();
@@ -970,10 +996,10 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
         if (lane == 0 && !selfopen) status = UVOL_ERR_CORRUPT;        // the walk only ever moves to unvisited faces
         const unsigned newv = __ballot_sync(0xffffffffu, exec && !vis);
         if (exec) {
-            atomicOr(&fbits[fi >> 5], 1u << (fi & 31));
+            if (GMAP) fvis[fi] = 1; else atomicOr(&fbits[fi >> 5], 1u << (fi & 31));
             if (!vis) {
                 const int idx = n + __popc(newv & lt);
-                atomicOr(&vbits[v >> 5], 1u << (v & 31));
+                if (!GMAP) atomicOr(&vbits[v >> 5], 1u << (v & 31));
                 v2d1[v] = idx + 1; d2c[idx] = ci;
             }
         }
@@ -1279,7 +1305,16 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
     aux.push_back(0);
     B.blob_bytes = blob_bytes;
     UVOL_CUDA(ctx, ctx->h_blob.reserve(blob_bytes + 64));
-    for (int i = 0; i < n; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_blob.p + frames[i].file_off, data[i], size[i]);
+    {   // staging copy into the pinned blob, by a few threads when the batch is large (it sits in front of the first kernel)
+        auto copy_range = [&](int lo, int hi) { for (int i = lo; i < hi; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_blob.p + frames[i].file_off, data[i], size[i]); };
+        const int nthreads = B.bytes_in > (32ull << 20) ? (int)std::min<uint64_t>(8, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1;
+        if (nthreads <= 1) copy_range(0, n);
+        else {
+            std::vector<std::thread> pool; const int per = (n + nthreads - 1) / nthreads;
+            for (int lo = 0; lo < n; lo += per) pool.emplace_back(copy_range, lo, std::min(n, lo + per));
+            for (auto &t : pool) t.join();
+        }
+    }
     draco_plan_phase1(frames, B.pl);
     std::vector<Job> &jobs = B.jobs; jobs.reserve((size_t)n * 24);
     auto mark = [&]() { return (int)jobs.size(); };
@@ -1315,8 +1350,8 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
     UVOL_CUDA(ctx, ctx->d_counts.reserve(sizeof(DracoCounts) * (size_t)n));
     UVOL_CUDA(ctx, ctx->h_counts.reserve(sizeof(DracoCounts) * (size_t)n));
     UVOL_CUDA(ctx, ctx->d_jobs.reserve(sizeof(Job) * (jobs.size() + 1)));
-    UVOL_CUDA(ctx, ctx->d_scratch.reserve(B.pl.scratch + 256));
-    UVOL_CUDA(ctx, ctx->d_zscratch.reserve(B.pl.zscratch + 256));
+    UVOL_CUDA(ctx, ctx->ar->d_scratch.reserve(B.pl.scratch + 256));
+    UVOL_CUDA(ctx, ctx->ar->d_zscratch.reserve(B.pl.zscratch + 256));
     UVOL_CUDA(ctx, ctx->h_desc.reserve(sizeof(DracoFrame) * (size_t)n + aux.size() * 4 + sizeof(Job) * (jobs.size() + 1)));
     B.parse_ms = now_ms() - t_begin;
     if (ctx->profile) cudaEventRecord(ctx->ev[0], st);
@@ -1341,11 +1376,11 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(DracoCounts) * (size_t)n, st));
-    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_zscratch.p, 0, pl.zscratch + 256, st));
+    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->ar->d_zscratch.p, 0, pl.zscratch + 256, st));
     stamp("h2d");
     const DracoFrame *dF = (const DracoFrame *)ctx->d_desc.p; DracoCounts *dC = (DracoCounts *)ctx->d_counts.p;
     const uint8_t *dBlob = (const uint8_t *)ctx->d_blob.p; const uint32_t *dAux = (const uint32_t *)ctx->d_aux.p;
-    uint8_t *dS = (uint8_t *)ctx->d_scratch.p, *dZ = (uint8_t *)ctx->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
+    uint8_t *dS = (uint8_t *)ctx->ar->d_scratch.p, *dZ = (uint8_t *)ctx->ar->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
     uint32_t launches = 0;
     auto rans_words = [](uint32_t nnz) { return (int)(((size_t)(nnz + 1) * 16 + (10u << RANS_LUT_BITS) + 16 + 15) / 16 * 4); };
     auto rans_smem = [&](uint32_t alphabet) { return (size_t)rans_words(alphabet) * 4 * SERIAL_WARPS; };
@@ -1401,14 +1436,14 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));
     const DracoCounts *hC = (const DracoCounts *)ctx->h_counts.p;
     draco_plan_phase2(frames, hC, pl);
-    UVOL_CUDA(ctx, ctx->d_scratch2.reserve(pl.scratch2 + 256));
-    UVOL_CUDA(ctx, ctx->d_zscratch2.reserve(pl.zscratch2 + 256));
-    UVOL_CUDA(ctx, ctx->d_out_geo.reserve(pl.out + 256));
+    UVOL_CUDA(ctx, ctx->ar->d_scratch2.reserve(pl.scratch2 + 256));
+    UVOL_CUDA(ctx, ctx->ar->d_zscratch2.reserve(pl.zscratch2 + 256));
+    UVOL_CUDA(ctx, ctx->ar->d_out_geo.reserve(pl.out + 256));
     memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
-    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_zscratch2.p, 0, pl.zscratch2 + 256, st));
+    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->ar->d_zscratch2.p, 0, pl.zscratch2 + 256, st));
     stamp("counts_readback");
-    uint8_t *dS2 = (uint8_t *)ctx->d_scratch2.p, *dZ2 = (uint8_t *)ctx->d_zscratch2.p, *dO = (uint8_t *)ctx->d_out_geo.p;
+    uint8_t *dS2 = (uint8_t *)ctx->ar->d_scratch2.p, *dZ2 = (uint8_t *)ctx->ar->d_zscratch2.p, *dO = (uint8_t *)ctx->ar->d_out_geo.p;
     uint32_t maxP = 1, maxN = 1;
     for (int i = 0; i < n; i++) if (!frames[i].status && !hC[i].status) {
         if (hC[i].num_points > maxP) maxP = hC[i].num_points;
@@ -1431,9 +1466,16 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         stamp("corner_records");
         const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((maxN + 31) / 32 + 4) & ~3u);
         const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_STACK * 4) * TRAV_WARPS;
-        if (smem > 200 * 1024 || maxN >= (1u << 26)) { ctx->err = "mesh too large for the traversal bitmaps"; return UVOL_ERR_UNSUPPORTED; }
-        if (smem > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_traverse<<<(ntj + TRAV_WARPS - 1) / TRAV_WARPS, 32 * TRAV_WARPS, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords); launches++;
+        if (maxN >= (1u << 26)) { ctx->err = "mesh too large for the traversal records"; return UVOL_ERR_UNSUPPORTED; }
+        // shared-memory bitmaps while every walk of the batch is resident at once (<= 200 KB of them per SM), else the global maps
+        static const int force = getenv("UVOL_TRAV_GMAP") ? atoi(getenv("UVOL_TRAV_GMAP")) : -1;
+        const bool gmap = force >= 0 ? force != 0 : (smem > 200 * 1024 || (size_t)((ntj + ctx->num_sms - 1) / ctx->num_sms) * smem > 200 * 1024);
+        if (gmap) k_traverse<true><<<(ntj + TRAV_WARPS - 1) / TRAV_WARPS, 32 * TRAV_WARPS, TRAV_STACK * 4 * TRAV_WARPS, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
+        else {
+            if (smem > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_traverse<false><<<(ntj + TRAV_WARPS - 1) / TRAV_WARPS, 32 * TRAV_WARPS, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
+        }
+        launches++;
     }
     stamp("traverse");
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[4], 0));
@@ -1461,14 +1503,14 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     stamp("expand");
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (memory == UVOL_MEM_HOST) {
-        UVOL_CUDA(ctx, ctx->h_out.reserve(pl.out + 256));
-        UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.p, dO, pl.out, cudaMemcpyDeviceToHost, st));
+        UVOL_CUDA(ctx, ctx->ar->h_out.reserve(pl.out + 256));
+        UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->ar->h_out.p, dO, pl.out, cudaMemcpyDeviceToHost, st));
     }
     stamp("d2h");
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));
     UVOL_CUDA(ctx, cudaGetLastError());
     // ---- results
-    uint8_t *base = memory == UVOL_MEM_HOST ? (uint8_t *)ctx->h_out.p : dO;
+    uint8_t *base = memory == UVOL_MEM_HOST ? (uint8_t *)ctx->ar->h_out.p : dO;
     uint64_t bytes_out = 0;
     for (int i = 0; i < n; i++) {
         const DracoFrame &f = frames[i]; uvol_geometry &g = out[i];

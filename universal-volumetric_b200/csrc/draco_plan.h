@@ -35,7 +35,9 @@ static inline void draco_plan_phase1(std::vector<DracoFrame> &frames, DracoPlan 
         for (int j = 0; j < f.nattr; j++) {                // early attribute symbol runs: capacity from the largest possible entry count
             const DracoAttr &a = f.attr[j];
             if (a.out_slot < 0 && j != f.pos_attr) { f.o_corr_early[j] = UVOL_NONE; f.corr_early_cap[j] = 0; continue; }
-            const uint64_t cap = (a.table < 0 ? maxv : C) * (uint64_t)a.vnc;
+            // attribute tables can have up to C vertices; real meshes stay far below 2 per base vertex, and a run that hits the
+            // capacity is simply decoded again by count once the count is known (k_corr_settle / k_rans)
+            const uint64_t cap = (a.table < 0 ? maxv : (C < 2 * maxv + 1024 ? C : 2 * maxv + 1024)) * (uint64_t)a.vnc;
             f.corr_early_cap[j] = (uint32_t)cap; f.o_corr_early[j] = plan_take(s, (cap + 4) * 4);
         }
     }
@@ -53,11 +55,12 @@ static inline void draco_plan_phase2(std::vector<DracoFrame> &frames, const Drac
         bool need[UVOL_MAX_ATTR_DATA + 1] = {true, false, false, false, false};
         for (int j = 0; j < f.nattr; j++) if (f.attr[j].out_slot >= 0 || j == f.pos_attr) need[f.attr[j].table + 1] = true;
         for (uint32_t t = 0; t <= f.nad; t++) {
-            if (!need[t]) { f.o_d2c[t] = f.o_v2d[t] = f.o_frec[t] = f.o_tstack[t] = UVOL_NONE; continue; }
+            if (!need[t]) { f.o_d2c[t] = f.o_v2d[t] = f.o_frec[t] = f.o_tstack[t] = f.o_fvis[t] = UVOL_NONE; continue; }
             const uint64_t nv = (t == 0 ? c.num_vertex_slots : c.attr_vertices[t - 1]) + 4;
             f.o_d2c[t] = plan_take(s, nv * 4); f.o_tstack[t] = plan_take(s, (F + 8) * 4);
             f.o_frec[t] = plan_take(s, (3 * F + 4) * 16 + 2 * (F + 4) * 16);      // per-corner traversal records + per-face up / down entry records
             f.o_v2d[t] = plan_take(z, nv * 4);
+            f.o_fvis[t] = plan_take(z, F + 16);             // visited-face bytes of the global-map traversal
         }
         for (int j = 0; j < f.nattr; j++) {
             const DracoAttr &a = f.attr[j];

@@ -34,11 +34,11 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *db[] = {&c->d_blob, &c->d_desc, &c->d_aux, &c->d_counts, &c->d_scratch, &c->d_zscratch, &c->d_scratch2, &c->d_zscratch2, &c->d_jobs, &c->d_out_geo,
-                    &c->d_tblob, &c->d_tdesc, &c->d_tslices, &c->d_tscratch, &c->d_out_tex,
+    DevBuf *db[] = {&c->d_blob, &c->d_desc, &c->d_aux, &c->d_counts, &c->own_arenas.d_scratch, &c->own_arenas.d_zscratch, &c->own_arenas.d_scratch2, &c->own_arenas.d_zscratch2, &c->d_jobs, &c->own_arenas.d_out_geo,
+                    &c->d_tblob, &c->d_tdesc, &c->d_tslices, &c->own_arenas.d_tscratch, &c->own_arenas.d_out_tex,
                     &c->d_cblob, &c->d_cdesc, &c->d_cscratch, &c->d_czscratch, &c->d_out_corto, &c->d_ccounts, &c->d_caux};
     for (auto *b : db) b->release();
-    PinBuf *pb[] = {&c->h_blob, &c->h_desc, &c->h_aux, &c->h_counts, &c->h_out, &c->h_tblob, &c->h_tdesc, &c->h_tout, &c->h_cblob, &c->h_cdesc, &c->h_cout, &c->h_ccounts};
+    PinBuf *pb[] = {&c->h_blob, &c->h_desc, &c->h_aux, &c->h_counts, &c->own_arenas.h_out, &c->h_tblob, &c->h_tdesc, &c->own_arenas.h_tout, &c->h_cblob, &c->h_cdesc, &c->h_cout, &c->h_ccounts};
     for (auto *b : pb) b->release();
     c->d_flush.release();
     if (c->geo) uvol_geo_batch_free(c->geo);
@@ -52,6 +52,14 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     if (c->s0) cudaStreamDestroy(c->s0);
     if (c->s1) cudaStreamDestroy(c->s1);
     delete c;
+}
+
+// Lets `ctx` use the scratch / output arenas of `owner` (same device) instead of its own.  Used to keep the compressed
+// inputs of several windows of one sequence resident (one ctx per window) with a single set of scratch arenas.
+extern "C" int uvol_share_arenas(uvol_ctx *ctx, uvol_ctx *owner) {
+    if (!ctx || !owner || ctx->device != owner->device) return UVOL_ERR_ARG;
+    ctx->ar = owner->ar;
+    return UVOL_OK;
 }
 
 extern "C" const char *uvol_last_error(const uvol_ctx *c) { return c ? c->err.c_str() : "null ctx"; }

@@ -37,6 +37,14 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// The large arenas of the V2 path (scratch, device outputs, pinned host outputs).  A ctx normally owns its set; contexts
+// created for consecutive WINDOWS of one sequence can share one set (uvol_share_arenas), so each window keeps its
+// compressed inputs resident while the scratch exists once.
+struct Arenas {
+    DevBuf d_scratch, d_zscratch, d_scratch2, d_zscratch2, d_out_geo, d_tscratch, d_out_tex;
+    PinBuf h_out, h_tout;
+};
+
 struct GeoBatch; struct TexBatch; struct CortoBatch;
 void uvol_geo_batch_free(GeoBatch *); void uvol_tex_batch_free(TexBatch *); void uvol_corto_batch_free(CortoBatch *);
 
@@ -48,12 +56,12 @@ struct uvol_ctx {
     cudaStream_t s2 = nullptr;
     std::string err;
     // geometry path
-    PinBuf h_blob, h_desc, h_aux, h_counts, h_out;
-    DevBuf d_blob, d_desc, d_aux, d_counts, d_scratch, d_zscratch, d_scratch2, d_zscratch2, d_jobs;
-    DevBuf d_out_geo;             // library-owned geometry outputs (valid until the next geometry batch)
+    Arenas own_arenas; Arenas *ar = &own_arenas;      // scratch + library-owned outputs (valid until the next batch on any ctx sharing them)
+    PinBuf h_blob, h_desc, h_aux, h_counts;
+    DevBuf d_blob, d_desc, d_aux, d_counts, d_jobs;
     // texture path
-    PinBuf h_tblob, h_tdesc, h_tout;
-    DevBuf d_tblob, d_tdesc, d_tslices, d_tscratch, d_out_tex;
+    PinBuf h_tblob, h_tdesc;
+    DevBuf d_tblob, d_tdesc, d_tslices;
     // V1 path
     PinBuf h_cblob, h_cdesc, h_cout, h_ccounts;
     DevBuf d_cblob, d_cdesc, d_cscratch, d_czscratch, d_out_corto, d_ccounts, d_caux;

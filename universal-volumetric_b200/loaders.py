@@ -46,6 +46,12 @@ class Context:
         except Exception:
             pass
 
+    def share_arenas(self, owner):
+        """Use `owner`'s scratch / output arenas (one ctx per window of a sequence, one set of arenas)."""
+        if self._L.uvol_share_arenas(self._h, owner._h) != 0:
+            raise N.UvolError("uvol_share_arenas failed")
+        self._owner = owner          # keep the owner alive
+
     def flush_l2(self):
         self._L.uvol_flush_l2(self._h)
 
