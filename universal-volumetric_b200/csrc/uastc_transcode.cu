@@ -9,6 +9,7 @@
 // (lanes of a warp look up different modes, which a __constant__ bank would serialise).  Control flow is table-driven
 // rather than a switch per mode, so blocks of different modes in one warp mostly share instructions.
 // Block format: see oracle/uastc_oracle.c (the CPU restatement this kernel is checked against bit for bit).
+#include <string.h>
 #include "uvol_ctx.h"
 #include "uastc_tables.h"
 
@@ -17,18 +18,15 @@ namespace {
 // per-mode parameters packed in a word: comps[0:3) subsets[3:5) planes[5:7) wbits[7:10) eprow[10:13) hints[13:18) epbits[18:22) tq[22:24) codelen[24:27)
 #define MP(comps, subsets, planes, wbits, eprow, hints, epbits, tq, codelen) \
     ((comps) | ((subsets) << 3) | ((planes) << 5) | ((wbits) << 7) | ((eprow) << 10) | ((hints) << 13) | ((epbits) << 18) | ((tq) << 22) | ((codelen) << 24))
-__constant__ uint32_t c_mode[20] = {
+static const uint32_t H_MODE[20] = {
     MP(3, 1, 1, 4, 6, 15, 6, 1, 4), MP(3, 1, 1, 2, 7, 15, 8, 0, 6), MP(3, 2, 1, 3, 1, 15, 4, 0, 5), MP(3, 3, 1, 2, 0, 15, 2, 1, 5),
     MP(3, 2, 1, 2, 3, 15, 3, 2, 5), MP(3, 1, 1, 3, 7, 15, 8, 0, 5), MP(3, 1, 2, 2, 5, 15, 5, 2, 5), MP(3, 2, 1, 2, 3, 15, 3, 2, 5),
     MP(0, 0, 0, 0, 0, 0, 0, 0, 5),  MP(4, 2, 1, 2, 1, 23, 4, 0, 5), MP(4, 1, 1, 4, 4, 17, 4, 1, 3), MP(4, 1, 2, 2, 4, 17, 4, 1, 2),
     MP(4, 1, 1, 3, 6, 17, 6, 1, 3), MP(4, 1, 2, 1, 7, 23, 8, 0, 5), MP(4, 1, 1, 2, 7, 23, 8, 0, 5), MP(2, 1, 1, 4, 7, 23, 8, 0, 7),
     MP(2, 2, 1, 2, 7, 23, 8, 0, 6), MP(2, 1, 2, 2, 7, 23, 8, 0, 6), MP(3, 1, 1, 5, 2, 15, 5, 0, 4), 0};
-__constant__ uint8_t c_code[20] = {0x01, 0x35, 0x1D, 0x03, 0x13, 0x0B, 0x1B, 0x07, 0x17, 0x0F, 0x02, 0x00, 0x06, 0x1F, 0x0D, 0x05, 0x15, 0x25, 0x09, 0x45};
-__constant__ uint8_t c_codelen[20] = {4, 6, 5, 5, 5, 5, 5, 5, 5, 5, 3, 2, 3, 5, 5, 7, 6, 6, 4, 7};
-__constant__ uint32_t c_pattern[60];
-__constant__ uint16_t c_anchor[60];
-__constant__ uint8_t c_unquant[8 * 256];
-__constant__ uint8_t c_weight[6 * 32] = {      // row = weight bits (row 0 unused)
+static const uint8_t H_CODE[20] = {0x01, 0x35, 0x1D, 0x03, 0x13, 0x0B, 0x1B, 0x07, 0x17, 0x0F, 0x02, 0x00, 0x06, 0x1F, 0x0D, 0x05, 0x15, 0x25, 0x09, 0x45};
+static const uint8_t H_CODELEN[20] = {4, 6, 5, 5, 5, 5, 5, 5, 5, 5, 3, 2, 3, 5, 5, 7, 6, 6, 4, 7};
+static const uint8_t H_WEIGHT[6 * 32] = {      // row = weight bits (row 0 unused)
     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
     0, 64, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
     0, 21, 43, 64, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
@@ -46,6 +44,8 @@ __device__ __forceinline__ uint32_t take(Bits &x, uint32_t n) {          // n in
 struct UastcShared {
     uint32_t mode[20]; uint32_t pattern[60]; uint16_t anchor[60]; uint8_t mode_of[128]; uint8_t weight[6 * 32]; uint8_t unquant[8 * 256];
 };
+static_assert(sizeof(UastcShared) % 4 == 0, "copied word by word");
+__device__ uint32_t g_tables[sizeof(UastcShared) / 4];      // image of UastcShared, filled once per device by the launcher
 
 // One block -> four pixel rows of packed RGBA.  false: the transcoder rejects the block.
 __device__ __forceinline__ bool uastc_block(const UastcShared &T, uint4 blk, uint32_t rows[4][4]) {
@@ -117,52 +117,54 @@ __device__ __forceinline__ bool uastc_block(const UastcShared &T, uint4 blk, uin
         const uint32_t w0 = wtab[take(x, nb)];
         uint32_t w1 = w0;
         if (planes == 2u) w1 = wtab[take(x, nb)];
-        uint32_t px = 0;
-#pragma unroll
-        for (uint32_t c = 0; c < 4; c++) {
-            const uint32_t w = c == ccs ? w1 : w0;
-            const uint32_t lc = (l >> (8u * c)) & 255u, hc = (h >> (8u * c)) & 255u;
-            const uint32_t t = lc * (64u - w) + hc * w;                    // (lc*257*(64-w) + hc*257*w + 32) >> 14
-            px |= ((t * 257u + 32u) >> 14) << (8u * c);
+        // ASTC interpolation ((l*257*(64-w) + h*257*w + 32) >> 6) >> 8 == (t + ((t + 32) >> 8)) >> 6 with t = l*(64-w) + h*w <= 16320,
+        // evaluated for two channels at a time in 16-bit halves (R|B and G|A); the second-plane channel is patched in afterwards
+        const uint32_t lrb = l & 0x00ff00ffu, lga = (l >> 8) & 0x00ff00ffu, hrb = h & 0x00ff00ffu, hga = (h >> 8) & 0x00ff00ffu;
+        uint32_t trb = lrb * (64u - w0) + hrb * w0, tga = lga * (64u - w0) + hga * w0;
+        trb = ((trb + (((trb + 0x00200020u) >> 8) & 0x00ff00ffu)) >> 6) & 0x00ff00ffu;
+        tga = ((tga + (((tga + 0x00200020u) >> 8) & 0x00ff00ffu)) >> 6) & 0x00ff00ffu;
+        uint32_t px = trb | (tga << 8);
+        if (planes == 2u) {
+            const uint32_t lc = (l >> (8u * ccs)) & 255u, hc = (h >> (8u * ccs)) & 255u, t = lc * (64u - w1) + hc * w1;
+            px = (px & ~(255u << (8u * ccs))) | (((t + ((t + 32u) >> 8)) >> 6) << (8u * ccs));
         }
         rows[i >> 2][i & 3] = px;
     }
     return true;
 }
 
-// grid = (ceil(max blocks / 256), UASTC layer list)
+// grid = (ceil(max blocks / (256 * UASTC_CHUNKS)), UASTC layer list): a CTA loads the tables once and decodes UASTC_CHUNKS x 256 blocks
+#define UASTC_CHUNKS 8
 __global__ void __launch_bounds__(256) k_uastc_blocks(const Ktx2File *files, int32_t *status2, const uint8_t *blob, uint8_t *O, const uint32_t *layer_list) {
     __shared__ UastcShared T;
-    for (uint32_t i = threadIdx.x; i < 8 * 256; i += 256) T.unquant[i] = c_unquant[i];
-    if (threadIdx.x < 6 * 32) T.weight[threadIdx.x] = c_weight[threadIdx.x];
-    if (threadIdx.x < 60) { T.pattern[threadIdx.x] = c_pattern[threadIdx.x]; T.anchor[threadIdx.x] = c_anchor[threadIdx.x]; }
-    if (threadIdx.x < 20) T.mode[threadIdx.x] = c_mode[threadIdx.x];
-    if (threadIdx.x < 128) {
-        uint32_t m = 19;
-        for (uint32_t k = 0; k < 20; k++) if ((threadIdx.x & ((1u << c_codelen[k]) - 1u)) == c_code[k]) m = k;
-        T.mode_of[threadIdx.x] = (uint8_t)m;
-    }
+    for (uint32_t i = threadIdx.x; i < sizeof(UastcShared) / 4; i += 256) ((uint32_t *)&T)[i] = g_tables[i];
     __syncthreads();
     const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
     const Ktx2File &f = files[fi];
     if (f.status || !f.is_uastc) return;
-    const uint32_t nblk = f.bx * f.by, bi = blockIdx.x * 256 + threadIdx.x;
-    if (bi >= nblk) return;
-    const uint8_t *src = blob + f.file_off + f.level_off + ((size_t)L * nblk + bi) * 16;
-    uint4 blk;
-    if (((uintptr_t)src & 15) == 0) blk = __ldg((const uint4 *)src);
-    else { uint32_t w[4]; for (int k = 0; k < 4; k++) w[k] = src[4 * k] | (src[4 * k + 1] << 8) | (src[4 * k + 2] << 16) | ((uint32_t)src[4 * k + 3] << 24); blk = make_uint4(w[0], w[1], w[2], w[3]); }
-    uint32_t rows[4][4];
-    if (!uastc_block(T, blk, rows)) { status2[2 * fi] = UVOL_ERR_CORRUPT; return; }      // like a failed transcodeImage: the whole segment is an error
-    const uint32_t xb = bi % f.bx, yb = bi / f.bx, W = f.width, H = f.height;
+    const uint32_t nblk = f.bx * f.by, W = f.width, H = f.height, bxn = f.bx;
+    const uint8_t *src0 = blob + f.file_off + f.level_off + (size_t)L * nblk * 16;
     uint8_t *dst = O + f.o_rgba + (size_t)L * W * H * 4;
-    if (xb * 4 + 4 <= W && (W & 3) == 0) {
+    const bool aligned = (((uintptr_t)src0) & 15) == 0, whole = (W & 3) == 0;
+#pragma unroll 1
+    for (uint32_t k = 0; k < UASTC_CHUNKS; k++) {
+        const uint32_t bi = (blockIdx.x * UASTC_CHUNKS + k) * 256 + threadIdx.x;
+        if (bi >= nblk) return;
+        const uint8_t *src = src0 + (size_t)bi * 16;
+        uint4 blk;
+        if (aligned) blk = __ldcs((const uint4 *)src);
+        else { uint32_t w[4]; for (int q = 0; q < 4; q++) w[q] = src[4 * q] | (src[4 * q + 1] << 8) | (src[4 * q + 2] << 16) | ((uint32_t)src[4 * q + 3] << 24); blk = make_uint4(w[0], w[1], w[2], w[3]); }
+        uint32_t rows[4][4];
+        if (!uastc_block(T, blk, rows)) { status2[2 * fi] = UVOL_ERR_CORRUPT; continue; }      // like a failed transcodeImage: the whole segment is an error
+        const uint32_t xb = bi % bxn, yb = bi / bxn;
+        if (whole && xb * 4 + 4 <= W) {
 #pragma unroll
-        for (uint32_t y = 0; y < 4; y++) if (yb * 4 + y < H)
-            __stcs((uint4 *)(dst + ((size_t)(yb * 4 + y) * W + xb * 4) * 4), make_uint4(rows[y][0], rows[y][1], rows[y][2], rows[y][3]));
-    } else {
-        for (uint32_t y = 0; y < 4 && yb * 4 + y < H; y++) for (uint32_t x = 0; x < 4 && xb * 4 + x < W; x++)
-            *(uint32_t *)(dst + ((size_t)(yb * 4 + y) * W + xb * 4 + x) * 4) = rows[y][x];
+            for (uint32_t y = 0; y < 4; y++) if (yb * 4 + y < H)
+                __stcs((uint4 *)(dst + ((size_t)(yb * 4 + y) * W + xb * 4) * 4), make_uint4(rows[y][0], rows[y][1], rows[y][2], rows[y][3]));
+        } else {
+            for (uint32_t y = 0; y < 4 && yb * 4 + y < H; y++) for (uint32_t x = 0; x < 4 && xb * 4 + x < W; x++)
+                *(uint32_t *)(dst + ((size_t)(yb * 4 + y) * W + xb * 4 + x) * 4) = rows[y][x];
+        }
     }
 }
 
@@ -172,13 +174,15 @@ bool g_tables_ready[16] = {};
 // status2: the launcher's per-file {status, aux} pairs.  layer list entries: file << 12 | layer.
 int uvol_uastc_launch(int device, const Ktx2File *dF, int32_t *status2, const uint8_t *dBlob, uint8_t *dOut, const uint32_t *dLayerList, int nlayers,
                       uint32_t max_blocks, cudaStream_t st) {
-    if (device < 0 || device >= 16 || !g_tables_ready[device]) {
-        cudaError_t e = cudaMemcpyToSymbol(c_pattern, UASTC_PATTERN_INIT, sizeof UASTC_PATTERN_INIT);       // once per device, synchronous
-        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_anchor, UASTC_ANCHOR_INIT, sizeof UASTC_ANCHOR_INIT);
-        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_unquant, UASTC_UNQUANT_INIT, sizeof UASTC_UNQUANT_INIT);
+    if (device < 0 || device >= 16 || !g_tables_ready[device]) {      // once per device, synchronous
+        UastcShared h; memset(&h, 0, sizeof h);
+        memcpy(h.mode, H_MODE, sizeof h.mode); memcpy(h.pattern, UASTC_PATTERN_INIT, sizeof h.pattern); memcpy(h.anchor, UASTC_ANCHOR_INIT, sizeof h.anchor);
+        memcpy(h.weight, H_WEIGHT, sizeof h.weight); memcpy(h.unquant, UASTC_UNQUANT_INIT, sizeof h.unquant);
+        for (uint32_t v = 0; v < 128; v++) { uint32_t m = 19; for (uint32_t k = 0; k < 20; k++) if ((v & ((1u << H_CODELEN[k]) - 1u)) == H_CODE[k]) m = k; h.mode_of[v] = (uint8_t)m; }
+        const cudaError_t e = cudaMemcpyToSymbol(g_tables, &h, sizeof h);
         if (e != cudaSuccess) return (int)e;
         if (device >= 0 && device < 16) g_tables_ready[device] = true;
     }
-    k_uastc_blocks<<<dim3((max_blocks + 255) / 256, (unsigned)nlayers), 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList);
+    k_uastc_blocks<<<dim3((max_blocks + 256 * UASTC_CHUNKS - 1) / (256 * UASTC_CHUNKS), (unsigned)nlayers), 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList);
     return 0;
 }
