@@ -48,6 +48,8 @@ WORKLOADS = {
                label="configs[2]: 1000-frame V2 seq, 200k verts/frame Draco, 2048^2 UASTC KTX2 batch=7"),
     "c2": dict(frames=300, verts=50000, tex=1024, seq=7, seed=20260002, fmt="etc1s", window_segments=None, distinct_geo=None, distinct_tex=None,
                label="configs[1]: 300-frame V2 seq, 50k verts/frame Draco, 1024^2 ETC1S KTX2 batch=7"),
+    "c5": dict(frames=300, verts=50000, tex=1024, seq=1, seed=20260005, fmt="corto", window_segments=None, distinct_geo=8, distinct_tex=None,
+               label="configs[4]: V1 manifest, 300-frame Corto .crt geometry (position 12 bit + uv 12 bit, u32 index); V1's mp4 texture leg is out of scope"),
     "tiny": dict(frames=28, verts=2000, tex=64, seq=7, seed=20260009, fmt="uastc", window_segments=2, distinct_geo=None, distinct_tex=None,
                  label="tiny smoke workload"),
 }
@@ -164,6 +166,115 @@ def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex, fmt):
     return g, t
 
 
+def bench_v1(args, W, rank, world, local):
+    """configs[4]: V1 Corto geometry.  Frames are encoded AND (for the CPU baseline / reference arm) decoded by the reference's own
+    C++ (oracle/_ref/libcorto_ref.so, built from deprecated/encoder/dev/src) -- cpu_baseline.kind = "reference"."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    import corto_bind
+    from tools.synth import synth
+    frames, verts = W["frames"], W["verts"]; ncores = os.cpu_count() or 1
+    workload_name = f"{W['label']} (synthetic sphere, reference encoder, seed {W['seed']})"
+    if not corto_bind.available():
+        if rank == 0:
+            print(json.dumps({"impl": args.impl, "unavailable": "oracle/_ref/libcorto_ref.so not built (needs the reference tree at build time)"}))
+        return 0
+    rings, segs = synth.sphere_dims(verts); fp, fu, uvs, nv = synth.sphere_topology(rings, segs)
+    t0 = time.time(); enc = []
+    for i in range(W["distinct_geo"]):
+        pos = synth.sphere_frame(rings, segs, i / 30.0, W["seed"] + 1000 * rank)
+        uvv = np.stack([np.arctan2(pos[:, 2], pos[:, 0]) / (2 * np.pi) + 0.5, pos[:, 1] / 2000.0 + 0.5], 1).astype(np.float32)
+        enc.append(corto_bind.ref_encode(pos, uvv, fp, 12, 12))
+    gen_s = time.time() - t0
+    crt = [enc[i % len(enc)] for i in range(frames)]
+    blobs = [c[0] for c in crt]
+
+    def cpu_pass(items, threads):
+        t = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:          # ctypes releases the GIL inside the reference decoder
+            list(ex.map(lambda c: corto_bind.ref_decode(c[0], c[1], c[2]), items))
+        return time.perf_counter() - t
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = crt[: max(ncores * 4, 32)]
+        cpu_pass(sample[:ncores], ncores)
+        dt = sum(cpu_pass(sample, ncores) for _ in range(args.steps)); fps = len(sample) * args.steps / dt
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+                          "config": {"workload": workload_name, "frames_per_step": len(sample)},
+                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": "reference",
+                                           "sample": f"{len(sample)} frames per step, {ncores} threads, the reference's own crt::Decoder (oracle/_ref/libcorto_ref.so)"},
+                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return 0
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    uv = importlib.import_module("universal-volumetric_b200")
+    ctx = uv.Context(local, profiling=True); dec = uv.CortoDecoder(ctx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 1)):
+        out = dec.decode_batch_raw(blobs, uv.MEM_HOST)
+    assert all(m.status == 0 for m in out[:frames]), "corto decode failed on the bench workload"
+    V_total = sum(m.num_vertices for m in out[:frames]); F_total = sum(m.num_faces for m in out[:frames])
+    for _ in range(max(args.warmup, 1)):
+        dec.decode_batch_raw(blobs, uv.MEM_DEVICE)
+    clocks = ClockSampler(local); clocks.start()
+    dev_ms = 0.0; launches = 0; stage_acc = {}
+    barrier()
+    for _ in range(args.steps):
+        ctx.flush_l2(); dec.decode_batch_raw(blobs, uv.MEM_DEVICE); st = ctx.stats(2)
+        dev_ms += st["device_ms"]; launches += st["kernel_launches"]
+        for k, v in st["stages"].items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    barrier(); e2e_s = 0.0
+    for _ in range(args.steps):
+        ctx.flush_l2(); t1 = time.perf_counter(); dec.decode_batch_raw(blobs, uv.MEM_HOST); e2e_s += time.perf_counter() - t1
+        st = ctx.stats(2); launches += st["kernel_launches"]
+    barrier(); clk = clocks.stop()
+    if world > 1:
+        v = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(v, op=dist.ReduceOp.MAX); dev_ms, e2e_s = float(v[0]), float(v[1])
+    peak, peak_src = measured_peak()
+    total = frames * world * args.steps
+    stages = {k: {"ms": round(v / args.steps, 4)} for k, v in stage_acc.items()}
+    kst = {k: v for k, v in stages.items() if k not in ("h2d", "d2h")}
+    dom = max(kst, key=lambda k: kst[k]["ms"])
+    # algorithmic bytes per step: compressed bytes in + index / position / uv out (SURVEY 8d); the dominant stage's share: faces = clers in, index out
+    alg = {"faces": F_total * (1 + 12), "dequant": V_total * 5 * 8, "delta": V_total * 5 * 8, "values": st["bytes_in"] + V_total * 5 * 4, "tunstall": st["bytes_in"]}
+    ach = alg.get(dom, 0) / (kst[dom]["ms"] * 1e-3) / 1e9 if kst[dom]["ms"] > 0 else None
+    if rank == 0:
+        cpu = None
+        if world == 1:
+            sample = crt[: max(ncores * 4, 32)]; cpu_pass(sample[:ncores], ncores); dt = cpu_pass(sample, ncores)
+            cpu = {"value": len(sample) / dt, "unit": "frames/s", "cores": ncores, "kind": "reference",
+                   "sample": f"first {len(sample)} frames, {ncores} threads, the reference's own crt::Decoder compiled from deprecated/encoder/dev/src (oracle/_ref/libcorto_ref.so)"}
+        print(json.dumps({"metric": METRIC, "value": total / (dev_ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+                          "config": {"workload": workload_name, "frames_per_gpu": frames, "verts": int(V_total / frames), "faces": int(F_total / frames),
+                                     "distinct_geometry_frames": W["distinct_geo"], "l2": "flushed between timed iterations (256 MiB memset)",
+                                     "value_note": "device time from CUDA events around the kernels (upload of the .crt bytes outside, outputs left in HBM)",
+                                     "parallelism": f"frames sharded, {world} rank(s), no data-path collective"},
+                          "mverts_per_s": V_total * world * args.steps / (dev_ms / 1e3) / 1e6,
+                          "roofline": {"bound": "hbm", "kernel": "corto_" + dom, "achieved": ach and round(ach, 2), "peak": peak, "unit": "GB/s", "frac": ach and round(ach / peak, 5),
+                                       "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom), "ms_per_launch": kst[dom]["ms"],
+                                       "note": "dominant stage is a latency-bound serial walk (one warp per frame)"},
+                          "stages": stages, "cpu_baseline": cpu,
+                          "e2e": {"value": total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": st["bytes_in"], "d2h_bytes_per_step": st["bytes_out"], "ms_per_step": e2e_s / args.steps * 1e3,
+                                  "path": "uvol_decode_corto_batch, UVOL_MEM_HOST"},
+                          "gpu_launches": launches, "clocks": clk, "workload_gen_s": round(gen_s, 2)}))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +283,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--window-segments", type=int, default=0, help="override the workload's window size (segments per library call)")
+    ap.add_argument("--gather", action="store_true", help="N>1: also time the optional final NCCL all-gather of decoded geometry (first <=64 frames of the last window per rank)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -180,6 +292,8 @@ def main():
         W["window_segments"] = args.window_segments
     frames, verts, tex, seq, seed = W["frames"], W["verts"], W["tex"], W["seq"], W["seed"]
     ncores = os.cpu_count() or 1
+    if W["fmt"] == "corto":
+        return bench_v1(args, W, rank, world, local)
     workload_name = f"{W['label']} (synthetic, tools/synth seed {seed})"
 
     # ------------------------------------------------------------------ reference arm (CPU oracle)
@@ -276,6 +390,25 @@ def main():
     barrier()
     clk = clocks.stop()
     h2d = sg["bytes_in"] + st["bytes_in"]; d2h = sg["bytes_out"] + st["bytes_out"]
+    gather_info = None
+    if world > 1 and args.gather:
+        # optional final gather: not part of the metric; decoded buffers of the last window go device -> device over NCCL
+        wd, wk = windows[-1]
+        g, t = players[-1].replay_step_raw(len(wd), len(wk), uv.MEM_DEVICE)
+        ng = min(len(wd), 64)
+        uv.gather.all_gather_geometry(g, ng, f"cuda:{local}")                                  # warm-up (communicator set-up)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); e0.record()
+        tables, arenas = uv.gather.all_gather_geometry(g, ng, f"cuda:{local}")
+        e1.record(); torch.cuda.synchronize()
+        _, base, nbytes = uv.gather.geometry_table(g, ng)
+        same = bool(torch.equal(arenas[rank][:nbytes], uv.gather.arena_tensor(base, nbytes, f"cuda:{local}")))
+        sums = arenas[:, : arenas.shape[1] // 8 * 8].view(torch.int64).sum(dim=1)                 # every rank must hold identical copies
+        lo, hi = sums.clone(), sums.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        gms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64); dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        gather_info = {"frames_per_rank": ng, "bytes_per_rank": int(nbytes), "ms": float(gms[0]), "recv_gbs_per_gpu": nbytes * (world - 1) / (float(gms[0]) * 1e-3) / 1e9,
+                       "own_slot_identical": same, "all_ranks_identical": bool(torch.equal(lo, hi)), "backend": "nccl all_gather_into_tensor on the library's device buffers"}
     # max over ranks
     if world > 1:
         v = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
@@ -343,7 +476,7 @@ def main():
                         "path": "uvol_decode_v2_batch per window (geometry and texture streams concurrent), UVOL_MEM_HOST",
                         "breakdown_ms_per_step": {"geo_host_parse": sg["host_parse_ms"], "geo_h2d": sg["h2d_ms"], "geo_kernels": sg["device_ms"], "geo_d2h": sg["d2h_ms"],
                                                   "geo_call_total": sg["total_ms"], "tex_host_parse": st["host_parse_ms"], "tex_h2d": st["h2d_ms"], "tex_kernels": st["device_ms"], "tex_d2h": st["d2h_ms"]}},
-                "gpu_launches": launches + launches_e2e * args.steps, "clocks": clk,
+                "gather": gather_info, "gpu_launches": launches + launches_e2e * args.steps, "clocks": clk,
                 "wall_ms_per_step_resident": wall_resident / args.steps * 1e3, "workload_gen_s": info["gen_s"]}
         print(json.dumps(line))
     for c in reversed(ctxs):

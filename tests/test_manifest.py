@@ -99,3 +99,61 @@ def test_two_rank_sharding_gloo():
     assert tmax == 2.0
     assert res[0][0] + res[1][0] == 300 and res[0][1] + res[1][1] == 43
     assert res[0][2] == 0 and res[1][2] == res[0][0] and res[1][3] == res[0][1]
+
+
+class _G:        # stands in for uvol_geometry: pointers into one host arena
+    pass
+
+
+def _fake_results(rank, nframes):
+    """A rank's 'decoded' frames laid out in one host arena like the library's output arena (128-byte aligned arrays)."""
+    import ctypes
+    import numpy as np
+    rng = np.random.default_rng(100 + rank)
+    sizes = [(50 + 7 * i + rank, 90 + 11 * i) for i in range(nframes)]                  # (points, faces)
+    total = sum(((F * 12 + 127) // 128 + (P * 12 + 127) // 128 * 2 + (P * 8 + 127) // 128) * 128 for P, F in sizes)
+    arena = np.zeros(total, np.uint8); base = arena.ctypes.data; cur = 0; res = []; truth = []
+    for P, F in sizes:
+        g = _G(); g.status = 0; g.num_points = P; g.num_faces = F; t = {}
+        for name, n, dt in (("index", F * 3, np.int32), ("position", P * 3, np.float32), ("normal", P * 3, np.float32), ("uv", P * 2, np.float32)):
+            vals = (rng.integers(0, P, n) if dt == np.int32 else rng.random(n)).astype(dt)
+            arena[cur:cur + 4 * n] = vals.view(np.uint8); setattr(g, name, ctypes.c_void_p(base + cur)); t[name] = vals
+            cur = (cur + 4 * n + 127) // 128 * 128
+        res.append(g); truth.append(t)
+    bad = _G(); bad.status = -2; bad.num_points = bad.num_faces = 0
+    bad.index = bad.position = bad.normal = bad.uv = None
+    res.append(bad); truth.append(None)
+    return res, truth, arena
+
+
+def _gather_worker(rank, world, port, q):
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gather = importlib.import_module("universal-volumetric_b200.gather")
+    res, truth, arena = _fake_results(rank, 3 + rank)                                  # ragged: ranks hold different frame counts
+    tables, arenas = gather.all_gather_geometry(res, len(res), "cpu")
+    ok = True
+    for r in range(world):
+        _, tr, _ = _fake_results(r, 3 + r)
+        for i, t in enumerate(tr):
+            v = gather.frame_views(tables, arenas, r, i)
+            if t is None:
+                ok &= v is None
+            else:
+                ok &= all(np.array_equal(v[k].numpy().ravel(), t[k]) for k in t)
+    q.put((rank, bool(ok), tuple(tables.shape)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_final_gather_gloo():
+    """The optional final gather: after it every rank holds every rank's frames byte for byte, including a failed frame."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn"); q = ctx.Queue(); port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=180) for _ in range(2)]
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert all(ok for _, ok, _ in got) and all(shape == (2, 5, 8) for _, _, shape in got)

@@ -8,5 +8,6 @@ from . import _native
 from ._native import UvolError, MEM_DEVICE, MEM_HOST
 from .loaders import Context, CortoDecoder, DRACOLoader, KTX2Loader, V2Player
 from .manifest import V1Manifest, V2Manifest, V2Sequence, shard_v2
+from . import gather
 
-__all__ = ["Context", "DRACOLoader", "KTX2Loader", "V2Player", "CortoDecoder", "V1Manifest", "V2Manifest", "V2Sequence", "shard_v2", "UvolError", "MEM_DEVICE", "MEM_HOST", "_native"]
+__all__ = ["Context", "DRACOLoader", "KTX2Loader", "V2Player", "CortoDecoder", "V1Manifest", "V2Manifest", "V2Sequence", "shard_v2", "gather", "UvolError", "MEM_DEVICE", "MEM_HOST", "_native"]
