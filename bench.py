@@ -290,6 +290,14 @@ def main():
     W = dict(WORKLOADS[args.workload])
     if args.window_segments > 0:
         W["window_segments"] = args.window_segments
+    elif W["fmt"] == "uastc" and W["window_segments"] and W["frames"] >= 500:
+        # pinned host buffers of the e2e path: ~25 GB per rank with 72-segment windows of C3; halve the window if the host cannot hold that for every rank
+        try:
+            import psutil
+            if psutil.virtual_memory().available / max(1, world) < 40e9:
+                W["window_segments"] = max(1, W["window_segments"] // 2); W["label"] += " [window halved: host memory]"
+        except Exception:
+            pass
     frames, verts, tex, seq, seed = W["frames"], W["verts"], W["tex"], W["seq"], W["seed"]
     ncores = os.cpu_count() or 1
     if W["fmt"] == "corto":
