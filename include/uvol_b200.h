@@ -123,11 +123,17 @@ typedef struct uvol_corto_mesh {
 } uvol_corto_mesh;
 int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int memory, uvol_corto_mesh *out);
 
-/* Makes `ctx` use the scratch / output arenas of `owner` (same device) instead of allocating its own.  For sequences
+/* Makes `ctx` use the phase-2 geometry scratch of `owner` (same device) instead of allocating its own.  For sequences
  * decoded in WINDOWS (the prefetch window of src/V2/player.ts:272-323, `fps x bufferDuration` frames): one ctx per window
- * keeps that window's compressed inputs resident in HBM, all of them share one set of scratch / output arenas.  Results of
- * a ctx are then valid until the next batch call on ANY ctx sharing the arenas; calls must be serialised across them. */
+ * keeps that window's compressed inputs, phase-1 scratch and outputs; the largest arena (about three quarters of a batch's
+ * scratch) exists once.  Calls on the sharing contexts may be issued concurrently from one host thread per ctx: the arena is
+ * handed over under a mutex, so window k+1's entropy / connectivity stages and window k's result copy overlap the other
+ * window's phase 2 (mirrors the reference keeping several decode requests in flight across its worker pool). */
 int uvol_share_arenas(uvol_ctx *ctx, uvol_ctx *owner);
+
+/* Device time (ms, CUDA events) spanned by the last calls of `n` contexts that ran concurrently: first kernel of any of them
+ * to last kernel of any of them.  Measurement aid; needs uvol_set_profiling(ctx, 1). */
+int uvol_span_ms(uvol_ctx *const *ctxs, int n, float *ms);
 
 /* Writes a buffer larger than L2 (256 MiB) on the ctx's stream and waits: L2 flush between timed iterations. */
 int uvol_flush_l2(uvol_ctx *ctx);

@@ -210,8 +210,8 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
     UVOL_CUDA(ctx, ctx->d_tdesc.reserve(B.desc_bytes));
     UVOL_CUDA(ctx, ctx->d_tblob.reserve(blob_bytes + 64));
     UVOL_CUDA(ctx, ctx->d_tslices.reserve(sizeof(TexState) * (size_t)n));
-    UVOL_CUDA(ctx, ctx->ar->d_tscratch.reserve(s + 256));
-    UVOL_CUDA(ctx, ctx->ar->d_out_tex.reserve(o + 256));
+    UVOL_CUDA(ctx, ctx->d_tscratch.reserve(s + 256));
+    UVOL_CUDA(ctx, ctx->d_out_tex.reserve(o + 256));
     uint8_t *hd = (uint8_t *)ctx->h_tdesc.p;
     memcpy(hd, files.data(), sizeof(Ktx2File) * (size_t)n);
     if (nsl) memcpy(hd + B.off_sl, slices.data(), sizeof(Ktx2Slice) * nsl);
@@ -238,7 +238,7 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
     const Ktx2File *dF = (const Ktx2File *)dD; const Ktx2Slice *dSl = (const Ktx2Slice *)(dD + B.off_sl);
     const uint32_t *dLL = (const uint32_t *)(dD + B.off_ll), *dUL = (const uint32_t *)(dD + B.off_ul);
     TexState *dSt = (TexState *)ctx->d_tslices.p; const uint8_t *dBlob = (const uint8_t *)ctx->d_tblob.p;
-    uint8_t *dS = (uint8_t *)ctx->ar->d_tscratch.p, *dO = (uint8_t *)ctx->ar->d_out_tex.p;
+    uint8_t *dS = (uint8_t *)ctx->d_tscratch.p, *dO = (uint8_t *)ctx->d_out_tex.p;
     uint32_t launches = 0;
     const unsigned nb4 = (unsigned)((n + SERIAL_WARPS - 1) / SERIAL_WARPS);
     k_basis_globals<<<nb4, 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dBlob, dS, n); launches++;
@@ -253,9 +253,10 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
     if (nll) { k_etc1s_blocks<<<dim3((B.max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO); launches++; }
     if (nul) { UVOL_CUDA(ctx, (cudaError_t)uvol_uastc_launch(ctx->device, dF, (int32_t *)dSt, dBlob, dO, dUL, (int)nul, B.max_blocks, st)); launches++; }
     stamp();
+    ctx->span_tex_end = ev - 1;
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
-    UVOL_CUDA(ctx, ctx->ar->h_tout.reserve(st_bytes + (memory == UVOL_MEM_HOST ? B.out + 256 : 0)));
-    TexState *hSt = (TexState *)ctx->ar->h_tout.p; uint8_t *hO = (uint8_t *)ctx->ar->h_tout.p + st_bytes;
+    UVOL_CUDA(ctx, ctx->h_tout.reserve(st_bytes + (memory == UVOL_MEM_HOST ? B.out + 256 : 0)));
+    TexState *hSt = (TexState *)ctx->h_tout.p; uint8_t *hO = (uint8_t *)ctx->h_tout.p + st_bytes;
     UVOL_CUDA(ctx, cudaMemcpyAsync(hSt, dSt, sizeof(TexState) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(hO, dO, B.out, cudaMemcpyDeviceToHost, st));
     stamp();
@@ -268,8 +269,8 @@ static int ktx2_finish(uvol_ctx *ctx, int memory, uvol_texture *out, uvol_stats 
     TexBatch &B = *ctx->tex; const int n = B.n;
     UVOL_CUDA(ctx, cudaGetLastError());
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
-    TexState *hSt = (TexState *)ctx->ar->h_tout.p; uint8_t *hO = (uint8_t *)ctx->ar->h_tout.p + st_bytes;
-    uint8_t *base = memory == UVOL_MEM_HOST ? hO : (uint8_t *)ctx->ar->d_out_tex.p; uint64_t bytes_out = 0;
+    TexState *hSt = (TexState *)ctx->h_tout.p; uint8_t *hO = (uint8_t *)ctx->h_tout.p + st_bytes;
+    uint8_t *base = memory == UVOL_MEM_HOST ? hO : (uint8_t *)ctx->d_out_tex.p; uint64_t bytes_out = 0;
     for (int i = 0; i < n; i++) {
         const Ktx2File &f = B.files[i]; uvol_texture &t = out[i];
         memset(&t, 0, sizeof t);

@@ -12,6 +12,7 @@
 #include <chrono>
 #include <string.h>
 #include <stdlib.h>
+#include <mutex>
 #include <thread>
 #include "uvol_ctx.h"
 #include "draco_core.h"
@@ -875,28 +876,31 @@ __device__ __forceinline__ unsigned face_of(int c) { return __umulhi((unsigned)c
 // the batch are co-resident).  GMAP = true: a byte per face in global memory plus the vertex -> entry map itself as the
 // visited-vertex test -- 2 KB of shared memory per walk, so large meshes (C3: 77 KB of bitmaps per walk) no longer cap the
 // SM at two walks.  Only this warp touches those bytes, so plain (L1-cached) loads / stores ordered by warp barriers suffice.
-template <bool GMAP>
+// GMAP = 2: faces in a shared-memory bitmap, vertices through the global vertex -> entry map (two thirds of the footprint).
+template <int GMAP>
 __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, uint8_t *Z2,
                                                  const Job *jobs, int njobs, int fwords_max, int vwords_max) {
     extern __shared__ uint32_t sm_all[];
     const int ji = blockIdx.x * TRAV_WARPS + (threadIdx.x >> 5);
     if (ji >= njobs) return;
-    uint32_t *sm = sm_all + (size_t)(threadIdx.x >> 5) * ((GMAP ? 0 : fwords_max + vwords_max) + TRAV_STACK);
+    constexpr bool FG = GMAP == 1, VG = GMAP != 0;          // faces / vertices tested through global memory
+    const int bitwords = (FG ? 0 : fwords_max) + (VG ? 0 : vwords_max);
+    uint32_t *sm = sm_all + (size_t)(threadIdx.x >> 5) * (bitwords + TRAV_STACK);
     const Job jb = jobs[ji];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
     if (f.o_d2c[t] == UVOL_NONE) return;
     const int F = (int)f.nf, C = 3 * F, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    uint32_t *fbits = sm, *vbits = sm + (GMAP ? 0 : fwords_max); int *stk = (int *)(sm + (GMAP ? 0 : fwords_max + vwords_max));
-    if (!GMAP) for (int i = lane; i < fwords_max + vwords_max; i += 32) sm[i] = 0;
+    uint32_t *fbits = sm, *vbits = sm + (FG ? 0 : fwords_max); int *stk = (int *)(sm + bitwords);
+    for (int i = lane; i < bitwords; i += 32) sm[i] = 0;
     const uint4 *grec = (const uint4 *)(S2 + f.o_frec[t]), *gup = grec + 3 * (size_t)F + 4, *gdn = gup + F + 4;
     int *d2c = (int *)(S2 + f.o_d2c[t]), *v2d1 = (int *)(Z2 + f.o_v2d[t]), *gst = (int *)(S2 + f.o_tstack[t]);
     uint8_t *fvis = Z2 + f.o_fvis[t];                        // GMAP only (zero-initialised with the arena)
     __syncwarp();
     int n = 0, sp = 0, c = -1, fscan = 0, status = 0, pdir = 1;
-#define FBIT(x) (GMAP ? (uint32_t)fvis[(x)] : ((fbits[(x) >> 5] >> ((x) & 31)) & 1u))
-#define VBIT(x) (GMAP ? (uint32_t)(v2d1[(x)] != 0) : ((vbits[(x) >> 5] >> ((x) & 31)) & 1u))
+#define FBIT(x) (FG ? (uint32_t)fvis[(x)] : ((fbits[(x) >> 5] >> ((x) & 31)) & 1u))
+#define VBIT(x) (VG ? (uint32_t)(v2d1[(x)] != 0) : ((vbits[(x) >> 5] >> ((x) & 31)) & 1u))
     for (;;) {
         if (c < 0) {
             // ---- pick the next corner: stack top (lane 0), else the next unvisited face starts a component
@@ -912,7 +916,7 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
             scan = __shfl_sync(0xffffffffu, scan, 0);
             if (scan) {
                 int nf = F;
-                if (GMAP) {          // all lanes: 128 faces per round, four visited-bytes per lane
+                if (FG) {            // all lanes: 128 faces per round, four visited-bytes per lane
                     fscan = __shfl_sync(0xffffffffu, fscan, 0);
                     for (int base = fscan & ~127; base < F && nf == F; base += 128) {
                         const int i0 = base + lane * 4;
@@ -933,8 +937,8 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
                     else {
                         fscan = nf; c = 3 * nf; stk[0] = c; sp = 1;
                         const unsigned vn = grec[c + 1].x & TIP_MASK, vp = grec[c + 2].x & TIP_MASK;     // next / previous vertices first
-                        if (!VBIT(vn)) { if (!GMAP) vbits[vn >> 5] |= 1u << (vn & 31); v2d1[vn] = ++n; d2c[n - 1] = c + 1; }
-                        if (!VBIT(vp)) { if (!GMAP) vbits[vp >> 5] |= 1u << (vp & 31); v2d1[vp] = ++n; d2c[n - 1] = c + 2; }
+                        if (!VBIT(vn)) { if (!VG) vbits[vn >> 5] |= 1u << (vn & 31); v2d1[vn] = ++n; d2c[n - 1] = c + 1; }
+                        if (!VBIT(vp)) { if (!VG) vbits[vp >> 5] |= 1u << (vp & 31); v2d1[vp] = ++n; d2c[n - 1] = c + 2; }
                     }
                 }
             }
@@ -996,10 +1000,10 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
         if (lane == 0 && !selfopen) status = UVOL_ERR_CORRUPT;        // the walk only ever moves to unvisited faces
         const unsigned newv = __ballot_sync(0xffffffffu, exec && !vis);
         if (exec) {
-            if (GMAP) fvis[fi] = 1; else atomicOr(&fbits[fi >> 5], 1u << (fi & 31));
+            if (FG) fvis[fi] = 1; else atomicOr(&fbits[fi >> 5], 1u << (fi & 31));
             if (!vis) {
                 const int idx = n + __popc(newv & lt);
-                if (!GMAP) atomicOr(&vbits[v >> 5], 1u << (v & 31));
+                if (!VG) atomicOr(&vbits[v >> 5], 1u << (v & 31));
                 v2d1[v] = idx + 1; d2c[idx] = ci;
             }
         }
@@ -1350,8 +1354,8 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
     UVOL_CUDA(ctx, ctx->d_counts.reserve(sizeof(DracoCounts) * (size_t)n));
     UVOL_CUDA(ctx, ctx->h_counts.reserve(sizeof(DracoCounts) * (size_t)n));
     UVOL_CUDA(ctx, ctx->d_jobs.reserve(sizeof(Job) * (jobs.size() + 1)));
-    UVOL_CUDA(ctx, ctx->ar->d_scratch.reserve(B.pl.scratch + 256));
-    UVOL_CUDA(ctx, ctx->ar->d_zscratch.reserve(B.pl.zscratch + 256));
+    UVOL_CUDA(ctx, ctx->d_scratch.reserve(B.pl.scratch + 256));
+    UVOL_CUDA(ctx, ctx->d_zscratch.reserve(B.pl.zscratch + 256));
     UVOL_CUDA(ctx, ctx->h_desc.reserve(sizeof(DracoFrame) * (size_t)n + aux.size() * 4 + sizeof(Job) * (jobs.size() + 1)));
     B.parse_ms = now_ms() - t_begin;
     if (ctx->profile) cudaEventRecord(ctx->ev[0], st);
@@ -1376,11 +1380,11 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(DracoCounts) * (size_t)n, st));
-    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->ar->d_zscratch.p, 0, pl.zscratch + 256, st));
+    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_zscratch.p, 0, pl.zscratch + 256, st));
     stamp("h2d");
     const DracoFrame *dF = (const DracoFrame *)ctx->d_desc.p; DracoCounts *dC = (DracoCounts *)ctx->d_counts.p;
     const uint8_t *dBlob = (const uint8_t *)ctx->d_blob.p; const uint32_t *dAux = (const uint32_t *)ctx->d_aux.p;
-    uint8_t *dS = (uint8_t *)ctx->ar->d_scratch.p, *dZ = (uint8_t *)ctx->ar->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
+    uint8_t *dS = (uint8_t *)ctx->d_scratch.p, *dZ = (uint8_t *)ctx->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
     uint32_t launches = 0;
     auto rans_words = [](uint32_t nnz) { return (int)(((size_t)(nnz + 1) * 16 + (10u << RANS_LUT_BITS) + 16 + 15) / 16 * 4); };
     auto rans_smem = [&](uint32_t alphabet) { return (size_t)rans_words(alphabet) * 4 * SERIAL_WARPS; };
@@ -1436,14 +1440,18 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));
     const DracoCounts *hC = (const DracoCounts *)ctx->h_counts.p;
     draco_plan_phase2(frames, hC, pl);
-    UVOL_CUDA(ctx, ctx->ar->d_scratch2.reserve(pl.scratch2 + 256));
-    UVOL_CUDA(ctx, ctx->ar->d_zscratch2.reserve(pl.zscratch2 + 256));
-    UVOL_CUDA(ctx, ctx->ar->d_out_geo.reserve(pl.out + 256));
+    UVOL_CUDA(ctx, ctx->d_out_geo.reserve(pl.out + 256));
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, ctx->h_out.reserve(pl.out + 256));
+    // The phase-2 scratch may be shared with the contexts of other windows (uvol_share_arenas): it is ours from here until
+    // the last phase-2 kernel has finished (released before the result copy, so the next window starts while we copy out).
+    std::unique_lock<std::mutex> p2_lock(ctx->p2->mu);
+    UVOL_CUDA(ctx, ctx->p2->d_scratch2.reserve(pl.scratch2 + 256));
+    UVOL_CUDA(ctx, ctx->p2->d_zscratch2.reserve(pl.zscratch2 + 256));
     memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
-    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->ar->d_zscratch2.p, 0, pl.zscratch2 + 256, st));
+    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->p2->d_zscratch2.p, 0, pl.zscratch2 + 256, st));
     stamp("counts_readback");
-    uint8_t *dS2 = (uint8_t *)ctx->ar->d_scratch2.p, *dZ2 = (uint8_t *)ctx->ar->d_zscratch2.p, *dO = (uint8_t *)ctx->ar->d_out_geo.p;
+    uint8_t *dS2 = (uint8_t *)ctx->p2->d_scratch2.p, *dZ2 = (uint8_t *)ctx->p2->d_zscratch2.p, *dO = (uint8_t *)ctx->d_out_geo.p;
     uint32_t maxP = 1, maxN = 1;
     for (int i = 0; i < n; i++) if (!frames[i].status && !hC[i].status) {
         if (hC[i].num_points > maxP) maxP = hC[i].num_points;
@@ -1467,13 +1475,23 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((maxN + 31) / 32 + 4) & ~3u);
         const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_STACK * 4) * TRAV_WARPS;
         if (maxN >= (1u << 26)) { ctx->err = "mesh too large for the traversal records"; return UVOL_ERR_UNSUPPORTED; }
-        // shared-memory bitmaps while every walk of the batch is resident at once (<= 200 KB of them per SM), else the global maps
+        // mode 0: both bitmaps in shared memory -- fastest while the walks of the batch need at most ~3 waves of the SMs' shared memory;
+        // mode 1: byte map + vertex -> entry map in global memory, every walk resident at once (measured at C3: 504 frames = 1512 walks of
+        // 77 KB: 211 ms in mode 0, 146 ms in mode 1; 252 frames: 130 vs 140 ms); mode 2 (faces in shared memory only) never wins, kept for experiments.
         static const int force = getenv("UVOL_TRAV_GMAP") ? atoi(getenv("UVOL_TRAV_GMAP")) : -1;
-        const bool gmap = force >= 0 ? force != 0 : (smem > 200 * 1024 || (size_t)((ntj + ctx->num_sms - 1) / ctx->num_sms) * smem > 200 * 1024);
-        if (gmap) k_traverse<true><<<(ntj + TRAV_WARPS - 1) / TRAV_WARPS, 32 * TRAV_WARPS, TRAV_STACK * 4 * TRAV_WARPS, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
-        else {
-            if (smem > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_traverse<false><<<(ntj + TRAV_WARPS - 1) / TRAV_WARPS, 32 * TRAV_WARPS, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
+        const size_t per_sm = (size_t)((ntj + ctx->num_sms - 1) / ctx->num_sms), fit = smem <= 200 * 1024 ? (200 * 1024) / smem : 0;
+        const size_t smem2 = ((size_t)fwords * 4 + TRAV_STACK * 4) * TRAV_WARPS;
+        int mode = force >= 0 ? force : (fit > 0 && per_sm <= 3 * fit ? 0 : 1);
+        if (mode == 2 && smem2 > 200 * 1024) mode = 1;
+        if (mode == 0 && fit == 0) mode = 1;
+        const unsigned tgrid = (ntj + TRAV_WARPS - 1) / TRAV_WARPS;
+        if (mode == 1) k_traverse<1><<<tgrid, 32 * TRAV_WARPS, TRAV_STACK * 4 * TRAV_WARPS, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
+        else if (mode == 2) {
+            if (smem2 > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            k_traverse<2><<<tgrid, 32 * TRAV_WARPS, smem2, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
+        } else {
+            if (smem > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_traverse<0><<<tgrid, 32 * TRAV_WARPS, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
         }
         launches++;
     }
@@ -1501,16 +1519,17 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     stamp("normals");
     k_expand<<<dim3((maxP + 255) / 256, n, B.maxattr), 256, 0, st>>>(dF, dC, dS, dS2, dZ2, dO); launches++;
     stamp("expand");
+    ctx->span_geo_end = ev - 1 < 32 ? ev - 1 : 31;
+    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[7], st));
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (memory == UVOL_MEM_HOST) {
-        UVOL_CUDA(ctx, ctx->ar->h_out.reserve(pl.out + 256));
-        UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->ar->h_out.p, dO, pl.out, cudaMemcpyDeviceToHost, st));
-    }
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.p, dO, pl.out, cudaMemcpyDeviceToHost, st));
     stamp("d2h");
+    UVOL_CUDA(ctx, cudaEventSynchronize(ctx->sync_ev[7]));
+    p2_lock.unlock();
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));
     UVOL_CUDA(ctx, cudaGetLastError());
     // ---- results
-    uint8_t *base = memory == UVOL_MEM_HOST ? (uint8_t *)ctx->ar->h_out.p : dO;
+    uint8_t *base = memory == UVOL_MEM_HOST ? (uint8_t *)ctx->h_out.p : dO;
     uint64_t bytes_out = 0;
     for (int i = 0; i < n; i++) {
         const DracoFrame &f = frames[i]; uvol_geometry &g = out[i];

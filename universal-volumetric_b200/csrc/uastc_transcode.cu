@@ -10,6 +10,7 @@
 // rather than a switch per mode, so blocks of different modes in one warp mostly share instructions.
 // Block format: see oracle/uastc_oracle.c (the CPU restatement this kernel is checked against bit for bit).
 #include <string.h>
+#include <mutex>
 #include "uvol_ctx.h"
 #include "uastc_tables.h"
 
@@ -174,6 +175,8 @@ bool g_tables_ready[16] = {};
 // status2: the launcher's per-file {status, aux} pairs.  layer list entries: file << 12 | layer.
 int uvol_uastc_launch(int device, const Ktx2File *dF, int32_t *status2, const uint8_t *dBlob, uint8_t *dOut, const uint32_t *dLayerList, int nlayers,
                       uint32_t max_blocks, cudaStream_t st) {
+    static std::mutex table_mu;
+    std::lock_guard<std::mutex> table_lock(table_mu);
     if (device < 0 || device >= 16 || !g_tables_ready[device]) {      // once per device, synchronous
         UastcShared h; memset(&h, 0, sizeof h);
         memcpy(h.mode, H_MODE, sizeof h.mode); memcpy(h.pattern, UASTC_PATTERN_INIT, sizeof h.pattern); memcpy(h.anchor, UASTC_ANCHOR_INIT, sizeof h.anchor);

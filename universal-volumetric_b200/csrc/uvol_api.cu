@@ -34,11 +34,11 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *db[] = {&c->d_blob, &c->d_desc, &c->d_aux, &c->d_counts, &c->own_arenas.d_scratch, &c->own_arenas.d_zscratch, &c->own_arenas.d_scratch2, &c->own_arenas.d_zscratch2, &c->d_jobs, &c->own_arenas.d_out_geo,
-                    &c->d_tblob, &c->d_tdesc, &c->d_tslices, &c->own_arenas.d_tscratch, &c->own_arenas.d_out_tex,
+    DevBuf *db[] = {&c->d_blob, &c->d_desc, &c->d_aux, &c->d_counts, &c->d_scratch, &c->d_zscratch, &c->own_p2.d_scratch2, &c->own_p2.d_zscratch2, &c->d_jobs, &c->d_out_geo,
+                    &c->d_tblob, &c->d_tdesc, &c->d_tslices, &c->d_tscratch, &c->d_out_tex,
                     &c->d_cblob, &c->d_cdesc, &c->d_cscratch, &c->d_czscratch, &c->d_out_corto, &c->d_ccounts, &c->d_caux};
     for (auto *b : db) b->release();
-    PinBuf *pb[] = {&c->h_blob, &c->h_desc, &c->h_aux, &c->h_counts, &c->own_arenas.h_out, &c->h_tblob, &c->h_tdesc, &c->own_arenas.h_tout, &c->h_cblob, &c->h_cdesc, &c->h_cout, &c->h_ccounts};
+    PinBuf *pb[] = {&c->h_blob, &c->h_desc, &c->h_aux, &c->h_counts, &c->h_out, &c->h_tblob, &c->h_tdesc, &c->h_tout, &c->h_cblob, &c->h_cdesc, &c->h_cout, &c->h_ccounts};
     for (auto *b : pb) b->release();
     c->d_flush.release();
     if (c->geo) uvol_geo_batch_free(c->geo);
@@ -54,11 +54,38 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     delete c;
 }
 
-// Lets `ctx` use the scratch / output arenas of `owner` (same device) instead of its own.  Used to keep the compressed
-// inputs of several windows of one sequence resident (one ctx per window) with a single set of scratch arenas.
+// Lets `ctx` use the phase-2 geometry scratch of `owner` (same device) instead of its own: one ctx per window of a sequence,
+// the largest arena exists once.  Calls on the sharing contexts may run concurrently (one host thread per ctx): the arena is
+// handed over under a mutex, so one window's phase 1 and result copies overlap another window's phase 2.
 extern "C" int uvol_share_arenas(uvol_ctx *ctx, uvol_ctx *owner) {
     if (!ctx || !owner || ctx->device != owner->device) return UVOL_ERR_ARG;
-    ctx->ar = owner->ar;
+    ctx->p2 = owner->p2;
+    return UVOL_OK;
+}
+
+// Device time spanned by the last V2 / geometry / texture calls of `n` contexts that ran concurrently: from the first kernel
+// of any of them to the last kernel of any of them (CUDA events of the contexts' streams; requires profiling on).
+extern "C" int uvol_span_ms(uvol_ctx *const *ctxs, int n, float *ms) {
+    if (!ctxs || n <= 0 || !ms || !ctxs[0]) return UVOL_ERR_ARG;
+    float lo = 0.f, hi = 0.f; bool any = false;
+    cudaEvent_t ref = nullptr;
+    for (int i = 0; i < n && !ref; i++) if (ctxs[i] && ctxs[i]->span_geo_end > 0) ref = ctxs[i]->ev[1];
+    for (int i = 0; i < n && !ref; i++) if (ctxs[i] && ctxs[i]->span_tex_end > 0) ref = ctxs[i]->tex_ev[1];
+    if (!ref) return UVOL_ERR_ARG;
+    auto add = [&](cudaEvent_t b, cudaEvent_t e) {
+        float tb = 0.f, te = 0.f;
+        if (cudaEventElapsedTime(&tb, ref, b) != cudaSuccess || cudaEventElapsedTime(&te, ref, e) != cudaSuccess) { cudaGetLastError(); return; }
+        if (!any || tb < lo) lo = tb;
+        if (!any || te > hi) hi = te;
+        any = true;
+    };
+    for (int i = 0; i < n; i++) {
+        uvol_ctx *c = ctxs[i]; if (!c) continue;
+        if (c->span_geo_end > 0) add(c->ev[1], c->ev[c->span_geo_end]);
+        if (c->span_tex_end > 0) add(c->tex_ev[1], c->tex_ev[c->span_tex_end]);
+    }
+    if (!any) return UVOL_ERR_ARG;
+    *ms = hi - lo;
     return UVOL_OK;
 }
 

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "uvol_internal.h"
@@ -16,7 +17,7 @@ struct DevBuf {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = n + n / 8 + (1 << 20);
+        size_t want = n + (n / 8 < (256u << 20) ? n / 8 : (256u << 20)) + (1 << 20);      // grow-only with bounded slack
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -29,7 +30,7 @@ struct PinBuf {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        size_t want = n + n / 8 + (1 << 20);
+        size_t want = n + (n / 8 < (256u << 20) ? n / 8 : (256u << 20)) + (1 << 20);
         cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -37,13 +38,11 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-// The large arenas of the V2 path (scratch, device outputs, pinned host outputs).  A ctx normally owns its set; contexts
-// created for consecutive WINDOWS of one sequence can share one set (uvol_share_arenas), so each window keeps its
-// compressed inputs resident while the scratch exists once.
-struct Arenas {
-    DevBuf d_scratch, d_zscratch, d_scratch2, d_zscratch2, d_out_geo, d_tscratch, d_out_tex;
-    PinBuf h_out, h_tout;
-};
+// The phase-2 geometry scratch (traversal records, corrections, parent tables: about three quarters of a batch's scratch).
+// A ctx normally owns one; contexts created for consecutive WINDOWS of one sequence share one (uvol_share_arenas), under
+// a mutex held for the duration of a window's phase 2.  Everything else (phase-1 scratch, outputs, inputs) stays per ctx,
+// so window k+1 runs its phase 1 -- and window k copies its results out -- while window k's / k+1's phase 2 owns the arena.
+struct Phase2Arena { DevBuf d_scratch2, d_zscratch2; std::mutex mu; };
 
 struct GeoBatch; struct TexBatch; struct CortoBatch;
 void uvol_geo_batch_free(GeoBatch *); void uvol_tex_batch_free(TexBatch *); void uvol_corto_batch_free(CortoBatch *);
@@ -56,12 +55,13 @@ struct uvol_ctx {
     cudaStream_t s2 = nullptr;
     std::string err;
     // geometry path
-    Arenas own_arenas; Arenas *ar = &own_arenas;      // scratch + library-owned outputs (valid until the next batch on any ctx sharing them)
-    PinBuf h_blob, h_desc, h_aux, h_counts;
-    DevBuf d_blob, d_desc, d_aux, d_counts, d_jobs;
+    Phase2Arena own_p2; Phase2Arena *p2 = &own_p2;
+    PinBuf h_blob, h_desc, h_aux, h_counts, h_out;
+    DevBuf d_blob, d_desc, d_aux, d_counts, d_scratch, d_zscratch, d_jobs;
+    DevBuf d_out_geo;             // library-owned geometry outputs (valid until the next geometry batch on this ctx)
     // texture path
-    PinBuf h_tblob, h_tdesc;
-    DevBuf d_tblob, d_tdesc, d_tslices;
+    PinBuf h_tblob, h_tdesc, h_tout;
+    DevBuf d_tblob, d_tdesc, d_tslices, d_tscratch, d_out_tex;
     // V1 path
     PinBuf h_cblob, h_cdesc, h_cout, h_ccounts;
     DevBuf d_cblob, d_cdesc, d_cscratch, d_czscratch, d_out_corto, d_ccounts, d_caux;
@@ -70,6 +70,7 @@ struct uvol_ctx {
     // stats of the last batch
     uvol_stats stats = {}, stats_tex = {};
     bool profile = false;
+    int span_geo_end = 0, span_tex_end = 0;      // event index of the last kernel stamp of the last geometry / texture run (0: none)
 };
 
 #define UVOL_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \

@@ -47,7 +47,7 @@ class Context:
             pass
 
     def share_arenas(self, owner):
-        """Use `owner`'s scratch / output arenas (one ctx per window of a sequence, one set of arenas)."""
+        """Use `owner`'s phase-2 geometry scratch (one ctx per window of a sequence; calls may then run from one thread per ctx)."""
         if self._L.uvol_share_arenas(self._h, owner._h) != 0:
             raise N.UvolError("uvol_share_arenas failed")
         self._owner = owner          # keep the owner alive
@@ -72,6 +72,16 @@ class Context:
                                         "bytes_out", "scratch_bytes")}
         d["stages"] = {self._L.uvol_stage_name(kind, i).decode(): float(s.stage_ms[i]) for i in range(s.num_stages)}
         return d
+
+
+def span_ms(contexts):
+    """Device time (CUDA events) from the first kernel to the last kernel of the last calls of `contexts` (run concurrently)."""
+    L = N.lib()
+    arr = (ctypes.c_void_p * len(contexts))(*[c._h for c in contexts])
+    ms = ctypes.c_float()
+    if L.uvol_span_ms(arr, len(contexts), ctypes.byref(ms)) != 0:
+        raise N.UvolError("uvol_span_ms failed (profiling off, or no call yet)")
+    return float(ms.value)
 
 
 def _pack(files):
