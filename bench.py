@@ -483,7 +483,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": workload_name, "frames_per_gpu": frames, "segments_per_gpu": n_k, "verts": info["verts"], "faces": info["faces"],
                            "points_per_frame": P_total / frames, "distinct_geometry_frames": info["distinct_geometry"], "distinct_texture_segments": info["distinct_textures"],
-                           "windows": [len(wd) for wd, _ in windows], "scratch_gb": round((sg["scratch_bytes"] + st["scratch_bytes"]) / 1e9, 2),
+                           "windows": [len(wd) for wd, _ in windows], "windows_concurrent": len(windows) > 1,
+                           "scratch_gb_largest_window": round((sg["scratch_bytes"] + st["scratch_bytes"]) / 1e9, 2),
                            "l2": "flushed between timed iterations (256 MiB memset); every window's working set is far larger than L2",
                            "parallelism": f"frames sharded, {world} rank(s), no data-path collective"},
                 "mverts_per_s": P_total * world * args.steps / (dev_ms / 1e3) / 1e6, "mtexels_per_s": texels * world * args.steps / (dev_ms / 1e3) / 1e6,

@@ -72,7 +72,8 @@ extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_p
     if (err) return UVOL_ERR_CORRUPT;
     // ---- phase 2
     draco_plan_phase2(frames, &cnt, pl);
-    std::vector<uint8_t> scratch2(pl.scratch2 + 256), zs2(pl.zscratch2 + 256, 0), outb(pl.out + 256);
+    draco_plan_rebase_traversal(frames, pl.scratch2 + 256);      // one host buffer: phase-2 scratch, then the traversal records
+    std::vector<uint8_t> scratch2(pl.scratch2 + 256 + pl.tscratch + 256), zs2(pl.zscratch2 + 256, 0), outb(pl.out + 256);
     uint8_t *S2 = scratch2.data(), *Z2 = zs2.data(), *O = outb.data();
     const int P = (int)cnt.num_points;
     uint32_t *c2p = (uint32_t *)(O + f.out_index); int *p2c = (int *)(S2 + f.o_p2c);

@@ -1442,16 +1442,18 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     draco_plan_phase2(frames, hC, pl);
     UVOL_CUDA(ctx, ctx->d_out_geo.reserve(pl.out + 256));
     if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, ctx->h_out.reserve(pl.out + 256));
-    // The phase-2 scratch may be shared with the contexts of other windows (uvol_share_arenas): it is ours from here until
-    // the last phase-2 kernel has finished (released before the result copy, so the next window starts while we copy out).
+    UVOL_CUDA(ctx, ctx->d_scratch2.reserve(pl.scratch2 + 256));
+    UVOL_CUDA(ctx, ctx->d_zscratch2.reserve(pl.zscratch2 + 256));
+    // The traversal-record arena may be shared with the contexts of other windows (uvol_share_arenas): it is ours from here
+    // until our traversal kernel has finished; the prediction stages that follow and the result copy do not touch it.
     std::unique_lock<std::mutex> p2_lock(ctx->p2->mu);
-    UVOL_CUDA(ctx, ctx->p2->d_scratch2.reserve(pl.scratch2 + 256));
-    UVOL_CUDA(ctx, ctx->p2->d_zscratch2.reserve(pl.zscratch2 + 256));
+    UVOL_CUDA(ctx, ctx->p2->d_frec.reserve(pl.tscratch + 256));
+    draco_plan_rebase_traversal(frames, (uint64_t)(uintptr_t)ctx->p2->d_frec.p - (uint64_t)(uintptr_t)ctx->d_scratch2.p);
     memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
-    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->p2->d_zscratch2.p, 0, pl.zscratch2 + 256, st));
+    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_zscratch2.p, 0, pl.zscratch2 + 256, st));
     stamp("counts_readback");
-    uint8_t *dS2 = (uint8_t *)ctx->p2->d_scratch2.p, *dZ2 = (uint8_t *)ctx->p2->d_zscratch2.p, *dO = (uint8_t *)ctx->d_out_geo.p;
+    uint8_t *dS2 = (uint8_t *)ctx->d_scratch2.p, *dZ2 = (uint8_t *)ctx->d_zscratch2.p, *dO = (uint8_t *)ctx->d_out_geo.p;
     uint32_t maxP = 1, maxN = 1;
     for (int i = 0; i < n; i++) if (!frames[i].status && !hC[i].status) {
         if (hC[i].num_points > maxP) maxP = hC[i].num_points;
@@ -1496,6 +1498,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         launches++;
     }
     stamp("traverse");
+    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[7], st));          // the traversal records are dead from here on
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[4], 0));
     if (B.j_rabsB - B.j_ransB > 0) {
         const int nrj = B.j_rabsB - B.j_ransB;
@@ -1520,7 +1523,6 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     k_expand<<<dim3((maxP + 255) / 256, n, B.maxattr), 256, 0, st>>>(dF, dC, dS, dS2, dZ2, dO); launches++;
     stamp("expand");
     ctx->span_geo_end = ev - 1 < 32 ? ev - 1 : 31;
-    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[7], st));
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.p, dO, pl.out, cudaMemcpyDeviceToHost, st));
     stamp("d2h");
@@ -1546,7 +1548,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     }
     uvol_stats &s = ctx->stats;
     s.kernel_launches = launches; s.bytes_in = B.bytes_in; s.bytes_out = bytes_out;
-    s.scratch_bytes = pl.scratch + pl.zscratch + pl.scratch2 + pl.zscratch2;
+    s.scratch_bytes = pl.scratch + pl.zscratch + pl.scratch2 + pl.zscratch2 + pl.tscratch;
     if (ctx->profile) {
         s.num_stages = (uint32_t)(ev - 1);
         for (int k = 0; k + 1 < ev && k < 24; k++) cudaEventElapsedTime(&s.stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);

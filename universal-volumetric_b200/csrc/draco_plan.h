@@ -8,7 +8,7 @@
 #include <vector>
 #include "uvol_internal.h"
 
-struct DracoPlan { uint64_t scratch = 0, zscratch = 0, scratch2 = 0, zscratch2 = 0, out = 0; };
+struct DracoPlan { uint64_t scratch = 0, zscratch = 0, scratch2 = 0, zscratch2 = 0, tscratch = 0, out = 0; };
 
 #define UVOL_NONE (~0ull)
 static inline uint64_t plan_take(uint64_t &cursor, uint64_t bytes) { uint64_t o = cursor; cursor = (cursor + bytes + 127) / 128 * 128; return o; }
@@ -46,7 +46,7 @@ static inline void draco_plan_phase1(std::vector<DracoFrame> &frames, DracoPlan 
 
 // counts[i] must hold the values read back from the device for frame i.
 static inline void draco_plan_phase2(std::vector<DracoFrame> &frames, const DracoCounts *counts, DracoPlan &pl) {
-    uint64_t s = 0, z = 0, o = 0;
+    uint64_t s = 0, z = 0, o = 0, tr = 0;      // tr: the traversal-record arena (dead once the traversal is done; shareable between windows)
     for (size_t i = 0; i < frames.size(); i++) {
         DracoFrame &f = frames[i]; const DracoCounts &c = counts[i];
         if (f.status || c.status) continue;
@@ -57,8 +57,8 @@ static inline void draco_plan_phase2(std::vector<DracoFrame> &frames, const Drac
         for (uint32_t t = 0; t <= f.nad; t++) {
             if (!need[t]) { f.o_d2c[t] = f.o_v2d[t] = f.o_frec[t] = f.o_tstack[t] = f.o_fvis[t] = UVOL_NONE; continue; }
             const uint64_t nv = (t == 0 ? c.num_vertex_slots : c.attr_vertices[t - 1]) + 4;
-            f.o_d2c[t] = plan_take(s, nv * 4); f.o_tstack[t] = plan_take(s, (F + 8) * 4);
-            f.o_frec[t] = plan_take(s, (3 * F + 4) * 16 + 2 * (F + 4) * 16);      // per-corner traversal records + per-face up / down entry records
+            f.o_d2c[t] = plan_take(s, nv * 4); f.o_tstack[t] = plan_take(tr, (F + 8) * 4);
+            f.o_frec[t] = plan_take(tr, (3 * F + 4) * 16 + 2 * (F + 4) * 16);      // per-corner traversal records + per-face up / down entry records
             f.o_v2d[t] = plan_take(z, nv * 4);
             f.o_fvis[t] = plan_take(z, F + 16);             // visited-face bytes of the global-map traversal
         }
@@ -74,5 +74,11 @@ static inline void draco_plan_phase2(std::vector<DracoFrame> &frames, const Drac
         for (int k = 0; k < 4; k++) f.out_attr[k] = UVOL_NONE;
         for (int j = 0; j < f.nattr; j++) if (f.attr[j].out_slot >= 0) f.out_attr[f.attr[j].out_slot] = plan_take(o, P * f.attr[j].nc * 4);
     }
-    pl.scratch2 = s; pl.zscratch2 = z; pl.out = o;
+    pl.scratch2 = s; pl.zscratch2 = z; pl.tscratch = tr; pl.out = o;
+}
+
+// o_frec / o_tstack come out of phase 2 relative to the traversal-record arena; the kernels address everything relative to the
+// phase-2 scratch base, so the launcher adds (traversal arena base - phase-2 scratch base), modulo 2^64.
+static inline void draco_plan_rebase_traversal(std::vector<DracoFrame> &frames, uint64_t delta) {
+    for (auto &f : frames) for (uint32_t t = 0; t <= UVOL_MAX_ATTR_DATA; t++) if (f.o_frec[t] != UVOL_NONE) { f.o_frec[t] += delta; f.o_tstack[t] += delta; }
 }

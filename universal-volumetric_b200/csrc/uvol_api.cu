@@ -34,7 +34,7 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *db[] = {&c->d_blob, &c->d_desc, &c->d_aux, &c->d_counts, &c->d_scratch, &c->d_zscratch, &c->own_p2.d_scratch2, &c->own_p2.d_zscratch2, &c->d_jobs, &c->d_out_geo,
+    DevBuf *db[] = {&c->d_blob, &c->d_desc, &c->d_aux, &c->d_counts, &c->d_scratch, &c->d_zscratch, &c->d_scratch2, &c->d_zscratch2, &c->own_p2.d_frec, &c->d_jobs, &c->d_out_geo,
                     &c->d_tblob, &c->d_tdesc, &c->d_tslices, &c->d_tscratch, &c->d_out_tex,
                     &c->d_cblob, &c->d_cdesc, &c->d_cscratch, &c->d_czscratch, &c->d_out_corto, &c->d_ccounts, &c->d_caux};
     for (auto *b : db) b->release();

@@ -38,11 +38,12 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-// The phase-2 geometry scratch (traversal records, corrections, parent tables: about three quarters of a batch's scratch).
-// A ctx normally owns one; contexts created for consecutive WINDOWS of one sequence share one (uvol_share_arenas), under
-// a mutex held for the duration of a window's phase 2.  Everything else (phase-1 scratch, outputs, inputs) stays per ctx,
-// so window k+1 runs its phase 1 -- and window k copies its results out -- while window k's / k+1's phase 2 owns the arena.
-struct Phase2Arena { DevBuf d_scratch2, d_zscratch2; std::mutex mu; };
+// The traversal-record arena of the geometry path (16 B per corner + 32 B per face per corner table: more than half of a
+// batch's scratch, dead as soon as the traversal has finished).  A ctx normally owns one; contexts created for consecutive
+// WINDOWS of one sequence share one (uvol_share_arenas), under a mutex held from a window's corner-record kernels to the end
+// of its traversal.  Everything else (other scratch, outputs, inputs) stays per ctx, so the other window's connectivity
+// stages, prediction stages and result copies run concurrently.
+struct Phase2Arena { DevBuf d_frec; std::mutex mu; };
 
 struct GeoBatch; struct TexBatch; struct CortoBatch;
 void uvol_geo_batch_free(GeoBatch *); void uvol_tex_batch_free(TexBatch *); void uvol_corto_batch_free(CortoBatch *);
@@ -57,7 +58,7 @@ struct uvol_ctx {
     // geometry path
     Phase2Arena own_p2; Phase2Arena *p2 = &own_p2;
     PinBuf h_blob, h_desc, h_aux, h_counts, h_out;
-    DevBuf d_blob, d_desc, d_aux, d_counts, d_scratch, d_zscratch, d_jobs;
+    DevBuf d_blob, d_desc, d_aux, d_counts, d_scratch, d_zscratch, d_scratch2, d_zscratch2, d_jobs;
     DevBuf d_out_geo;             // library-owned geometry outputs (valid until the next geometry batch on this ctx)
     // texture path
     PinBuf h_tblob, h_tdesc, h_tout;
