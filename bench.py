@@ -448,16 +448,18 @@ def main():
     for v in kernel_stages.values():
         v["share_of_kernel_time"] = round(v["ms"] / ksum, 4)          # comparable with the ncu launch-list shares
     traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if tr.get("workload") == args.workload:
-            traffic = tr
-    except Exception:
-        pass
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):        # measured DRAM bytes per launch (ncu --set full), newest last
+        try:
+            tr = json.load(open(path))
+            if tr.get("workload") == args.workload:
+                traffic = dict(tr, source=os.path.basename(path))
+        except Exception:
+            pass
     dom = max(main_stream, key=lambda k: main_stream[k]["ms"])
     dom_bytes = gb.get(dom.replace("(s1)", "")) if not dom.startswith("tex_") else tb.get(dom[4:])
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernel_stages[dom].get("gbs"), "peak": peak, "unit": "GB/s", "frac": kernel_stages[dom].get("frac"),
-            "traffic": (traffic or {}).get(dom.replace("(s1)", "")), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes and dom_bytes / nwin, "ms_per_launch": kernel_stages[dom]["ms"] / nwin, "launches_per_step": nwin,
+            "traffic": (traffic or {}).get(dom.replace("(s1)", "")), "traffic_source": (traffic or {}).get("source"), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes and dom_bytes / nwin, "ms_per_launch": kernel_stages[dom]["ms"] / nwin, "launches_per_step": nwin,
             "note": "dominant stage is a latency-bound serial walk (one warp per frame); HBM-bound stages are listed in `stages`"}
     step_bytes = sg["bytes_in"] + st["bytes_in"] + sg["bytes_out"] + st["bytes_out"]
     pipeline = {"bytes_per_frame": step_bytes / frames, "achieved_gbs": step_bytes * world * args.steps / (dev_ms / 1e3) / 1e9}

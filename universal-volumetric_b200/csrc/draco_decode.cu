@@ -1468,6 +1468,10 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[3], sx));
     k_point_fan<1><<<dim3(gv, n), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dO); launches++;
     stamp("point_assign");
+    if (memory == UVOL_MEM_HOST && pl.out_index) {      // the index buffers are final: copy them out on s3 while the rest of phase 2 runs
+        UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[6], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(ctx->s3, ctx->sync_ev[6], 0));
+        UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.p, dO, pl.out_index, cudaMemcpyDeviceToHost, ctx->s3));
+    }
     if (B.j_ransB - B.j_trav > 0) {
         const int ntj = B.j_ransB - B.j_trav;
         k_corner_records<<<dim3((3 * B.maxF + 127) / 128, ntj), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dJ + B.j_trav); launches++;
@@ -1524,11 +1528,12 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     stamp("expand");
     ctx->span_geo_end = ev - 1 < 32 ? ev - 1 : 31;
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.p, dO, pl.out, cudaMemcpyDeviceToHost, st));
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->h_out.p + pl.out_index, dO + pl.out_index, pl.out - pl.out_index, cudaMemcpyDeviceToHost, st));
     stamp("d2h");
     UVOL_CUDA(ctx, cudaEventSynchronize(ctx->sync_ev[7]));
     p2_lock.unlock();
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s3));
     UVOL_CUDA(ctx, cudaGetLastError());
     // ---- results
     uint8_t *base = memory == UVOL_MEM_HOST ? (uint8_t *)ctx->h_out.p : dO;

@@ -8,7 +8,7 @@
 #include <vector>
 #include "uvol_internal.h"
 
-struct DracoPlan { uint64_t scratch = 0, zscratch = 0, scratch2 = 0, zscratch2 = 0, tscratch = 0, out = 0; };
+struct DracoPlan { uint64_t scratch = 0, zscratch = 0, scratch2 = 0, zscratch2 = 0, tscratch = 0, out = 0, out_index = 0; };   // out_index: bytes of the index region at the head of the output arena
 
 #define UVOL_NONE (~0ull)
 static inline uint64_t plan_take(uint64_t &cursor, uint64_t bytes) { uint64_t o = cursor; cursor = (cursor + bytes + 127) / 128 * 128; return o; }
@@ -70,9 +70,15 @@ static inline void draco_plan_phase2(std::vector<DracoFrame> &frames, const Drac
             f.o_par[j] = plan_take(s, n * (a.pred == 5 ? 40 : 16));
             f.o_auxbits[j] = plan_take(s, n + 8);
         }
-        f.out_index = plan_take(o, F * 12);
+    }
+    // Output arena: the index buffers of all frames first (final as soon as the points are assigned, so their copy to the host can
+    // start while the traversal and prediction stages still run), then the per-point attribute arrays.
+    for (size_t i = 0; i < frames.size(); i++) { DracoFrame &f = frames[i]; if (!f.status && !counts[i].status) f.out_index = plan_take(o, (uint64_t)f.nf * 12); }
+    pl.out_index = o;
+    for (size_t i = 0; i < frames.size(); i++) {
+        DracoFrame &f = frames[i]; if (f.status || counts[i].status) continue;
         for (int k = 0; k < 4; k++) f.out_attr[k] = UVOL_NONE;
-        for (int j = 0; j < f.nattr; j++) if (f.attr[j].out_slot >= 0) f.out_attr[f.attr[j].out_slot] = plan_take(o, P * f.attr[j].nc * 4);
+        for (int j = 0; j < f.nattr; j++) if (f.attr[j].out_slot >= 0) f.out_attr[f.attr[j].out_slot] = plan_take(o, (uint64_t)counts[i].num_points * f.attr[j].nc * 4);
     }
     pl.scratch2 = s; pl.zscratch2 = z; pl.tscratch = tr; pl.out = o;
 }

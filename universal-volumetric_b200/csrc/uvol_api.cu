@@ -22,6 +22,7 @@ extern "C" int uvol_create(int device, uvol_ctx **out) {
     const int prio_mid = prio_hi < prio_lo - 1 ? prio_hi + 1 : prio_lo;
     if (cudaStreamCreateWithPriority(&c->s0, cudaStreamNonBlocking, prio_hi) != cudaSuccess || cudaStreamCreateWithPriority(&c->s1, cudaStreamNonBlocking, prio_mid) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     if (cudaStreamCreateWithPriority(&c->s2, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    if (cudaStreamCreateWithPriority(&c->s3, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     for (auto &e : c->aux_ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     for (auto &e : c->tex_ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
@@ -49,6 +50,7 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     for (auto &e : c->tex_ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->sync_ev) if (e) cudaEventDestroy(e);
     if (c->s2) cudaStreamDestroy(c->s2);
+    if (c->s3) cudaStreamDestroy(c->s3);
     if (c->s0) cudaStreamDestroy(c->s0);
     if (c->s1) cudaStreamDestroy(c->s1);
     delete c;

@@ -54,6 +54,7 @@ struct uvol_ctx {
     cudaStream_t s0 = nullptr, s1 = nullptr;
     cudaEvent_t ev[32] = {}, aux_ev[8] = {}, tex_ev[8] = {}, sync_ev[8] = {};
     cudaStream_t s2 = nullptr;
+    cudaStream_t s3 = nullptr;                    // early result copies (index buffers) next to the geometry kernels
     std::string err;
     // geometry path
     Phase2Arena own_p2; Phase2Arena *p2 = &own_p2;
