@@ -192,3 +192,43 @@ def test_uastc_full_size(uv, ctx):
     assert res[0]["status"] == 0 and res[0]["data"].shape == (7, 2048, 2048, 4) and (res[0]["data"][..., 3] == 255).all()
     assert np.array_equal(res[0]["data"], res[1]["data"])
     assert np.array_equal(res[0]["data"], oracle_ktx2(a)["rgba"])
+
+
+def test_geometry_c3_size(uv, ctx):
+    """BASELINE configs[2] geometry size (200k verts, 400k faces): oracle parity on one frame, determinism on the batch."""
+    drc, _, info = synth.make_sequence(3, 200000, 32, want_textures=False, seed=20260003, distinct_geometry=2)
+    res = uv.DRACOLoader(ctx).decode_batch(drc)
+    assert all(r["status"] == 0 and r["num_faces"] == info["faces"] for r in res)
+    check_geometry(res[:1], drc[:1])
+    assert np.array_equal(res[0]["index"], res[2]["index"]) and np.array_equal(res[0]["attributes"]["uv"], res[2]["attributes"]["uv"])
+
+
+def test_windows_share_the_traversal_arena(uv):
+    """Two contexts (two windows of one sequence) share the traversal-record arena and are driven from two host threads, as
+    bench.py does for C3: both windows must still match the oracle, fresh and replayed, device and host outputs."""
+    from concurrent.futures import ThreadPoolExecutor
+    drc, ktx, info = synth.make_sequence(28, 3000, 64, sequence_size=7, seed=20260011, texture_format="uastc")
+    wins = [(drc[:14], ktx[:2]), (drc[14:], ktx[2:])]
+    c0, c1 = uv.Context(0, profiling=True), uv.Context(0, profiling=True)
+    c1.share_arenas(c0)
+    players = [uv.V2Player(c0), uv.V2Player(c1)]
+    want = [[oracle_draco(b) for b in wd] for wd, _ in wins]
+
+    def run(w):
+        out = []
+        for rep in range(3):
+            g, t = players[w].decode_step_raw(*wins[w], uv.MEM_HOST) if rep != 1 else players[w].replay_step_raw(len(wins[w][0]), len(wins[w][1]), uv.MEM_HOST)
+            ok = all(x.status == 0 for x in g[:len(wins[w][0])]) and all(x.status == 0 for x in t[:len(wins[w][1])])
+            for x, o in zip(g, want[w]):
+                ok &= x.num_points == o["num_points"] and np.array_equal(np.ctypeslib.as_array(x.index, (x.num_faces * 3,)), o["index"])
+                ok &= np.array_equal(np.ctypeslib.as_array(x.position, (x.num_points, 3)).view(np.uint32), o["position"].view(np.uint32))
+                ok &= np.array_equal(np.ctypeslib.as_array(x.uv, (x.num_points, 2)).view(np.uint32), o["uv"].view(np.uint32))
+            for x, b in zip(t, wins[w][1]):
+                ok &= np.array_equal(np.ctypeslib.as_array(x.data, (x.layers, x.height, x.width, 4)), oracle_ktx2(b)["rgba"].reshape(x.layers, x.height, x.width, 4))
+            out.append(bool(ok))
+        return out
+    with ThreadPoolExecutor(2) as ex:
+        res = list(ex.map(run, [0, 1]))
+    assert res == [[True] * 3, [True] * 3]
+    assert uv.span_ms([c0, c1]) > 0
+    c1.close(); c0.close()
