@@ -232,3 +232,37 @@ def test_windows_share_the_traversal_arena(uv):
     assert res == [[True] * 3, [True] * 3]
     assert uv.span_ms([c0, c1]) > 0
     c1.close(); c0.close()
+
+
+def test_playback_from_manifest(uv, ctx, tmp_path):
+    """a V2 manifest on disk played through V2Playback (leaky-bucket look-ahead -> batched decode -> per-tick frame /
+    segment / layer selection); what the renderer would show is the oracle's decode of the right file and layer."""
+    import json
+    frames, seq = 35, 7
+    drc, ktx, info = synth.make_sequence(frames, 2000, 64, sequence_size=seq, seed=20260021)
+    gd = tmp_path / "clip" / "geometry_draco"; td = tmp_path / "clip" / "texture_ktx2-1k_baseColor_default"
+    gd.mkdir(parents=True); td.mkdir(parents=True)
+    for i, b in enumerate(drc):
+        (gd / ("%05d.drc" % i)).write_bytes(b)
+    for i, b in enumerate(ktx):
+        (td / ("%05d.ktx2" % i)).write_bytes(b)
+    manifest = {"version": "v2", "geometry": {"targets": {"draco": {"format": "draco", "frameRate": 30, "frameCount": frames}}, "path": "clip/geometry_[target]/[#####][ext]"},
+                "texture": {"targets": {"ktx2-1k": {"format": "ktx2", "resolution": [64, 64], "type": "baseColor", "tag": "default", "sequenceSize": seq,
+                                                    "sequenceCount": len(ktx), "frameRate": 30}}, "path": "clip/texture_[target]_[type]_[tag]/[#####][ext]"}}
+    mp = tmp_path / "clip.uvol.json"; mp.write_text(json.dumps(manifest))
+    sq = uv.V2Sequence(str(mp), uv.V2Player(ctx))
+    pb = uv.V2Playback(sq.man, sq.decode_copy, buffer_duration=1)
+    seen = {}
+    for tick in range(0, frames * 4):
+        t = tick / 120.0
+        if tick % 12 == 0:
+            pb.fetch_buffers(t)
+        r = pb.update(t)
+        if r is not None:
+            seen[r["frame"]] = r
+            if r["frame"] in (0, 17, 34) and "checked" not in r:
+                o = oracle_draco(drc[r["frame"]])
+                assert np.array_equal(r["geometry"]["index"], o["index"]) and np.array_equal(r["geometry"]["position"].view(np.uint32), o["position"].view(np.uint32))
+                rgba = oracle_ktx2(ktx[r["segment"]])["rgba"].reshape(-1, 64, 64, 4)
+                assert r["texture"] is not None and np.array_equal(r["texture"]["data"][r["layer"]], rgba[r["layer"]])
+    assert sorted(seen) == list(range(frames)) and pb.requests >= 2 and len(pb.mesh_map) <= 30 + 6

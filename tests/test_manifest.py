@@ -157,3 +157,34 @@ def test_two_rank_final_gather_gloo():
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert all(ok for _, ok, _ in got) and all(shape == (2, 5, 8) for _, _, shape in got)
+
+
+def test_playback_buffer_follows_the_reference_scheduler():
+    """V2Playback vs src/V2/player.ts:272-323,388-470,531-562 with a stub decoder: the look-ahead stays `bufferDuration` seconds
+    ahead, every frame / segment is requested exactly once, a failed mesh is skipped, a missing segment shows the mesh untextured,
+    played buffers are dropped ceil(120 / fps) frames behind the clock."""
+    m = man.V2Manifest(LIAM, "/data/public/liam.uvol.json")
+    asked_g, asked_s = [], []
+
+    def decode(frames, segments):
+        asked_g.extend(frames); asked_s.extend(segments)
+        return {f: ("mesh", f) for f in frames if f != 37}, {s: ("tex", s) for s in segments if s != 9}      # frame 37 and segment 9 fail to decode
+
+    pb = man.V2Playback(m, decode, buffer_duration=4)
+    assert pb.fetch_buffers(0.0) == (121, 25) and pb.buffered_fraction() == pytest.approx(120 / 120)      # frames 0..120, segments 0..24; frame 37 failed
+    assert pb.fetch_buffers(0.0) == (0, 0)                                   # nothing new until the clock moves
+    shown = []
+    for tick in range(0, 250 * 4 + 40):                                      # 120 Hz render loop over the 250-frame clip (+ overrun)
+        t = tick / 120.0
+        if tick % 12 == 0:
+            pb.fetch_buffers(t)                                             # the reference polls every intervalDuration
+        r = pb.update(t)
+        if r is not None:
+            shown.append((r["frame"], r["segment"], r["layer"], r["texture"] is not None))
+            assert r["geometry"] == ("mesh", r["frame"]) and r["segment"] == r["frame"] // 5 and r["layer"] == r["frame"] % 5
+            assert min(pb.mesh_map) >= r["frame"] - 4 - 1 and max(pb.mesh_map) <= min(249, r["frame"] + 4 * 30 + 3)
+    frames_shown = sorted({f for f, _, _, _ in shown})
+    assert frames_shown == [f for f in range(250) if f != 37]                 # the failed frame is simply absent (:435-437)
+    assert all(tex == (seg != 9) for _, seg, _, tex in shown)                # segment 9 missing -> failMaterial (:439-444)
+    assert sorted(asked_g) == list(range(250)) and sorted(asked_s) == list(range(50))      # each requested exactly once
+    assert pb.process_frame(250 / 30.0 + 0.1) is None                        # past the last frame: track end

@@ -162,6 +162,16 @@ class V2Sequence:
         g, t = self.player.decode_step_raw(self.read_geometry(frames), self.read_textures(segments), memory)
         return ({f: g[i] for i, f in enumerate(frames) if g[i].status == 0}, {s: t[i] for i, s in enumerate(segments) if t[i].status == 0})
 
+    def decode_copy(self, frames, segments):
+        """Like decode, with host results copied into numpy arrays that outlive the next batch (what V2Playback stores)."""
+        import numpy as np
+        g, t = self.decode(frames, segments, memory=1)
+        arr = lambda p, shape, dt: np.ctypeslib.as_array(p, shape).view(dt).copy() if p else None
+        meshes = {f: {"index": arr(x.index, (x.num_faces * 3,), np.uint32), "position": arr(x.position, (x.num_points, 3), np.float32),
+                      "normal": arr(x.normal, (x.num_points, 3), np.float32), "uv": arr(x.uv, (x.num_points, 2), np.float32)} for f, x in g.items()}
+        textures = {s: {"width": x.width, "height": x.height, "layers": x.layers, "data": np.ctypeslib.as_array(x.data, (x.layers, x.height, x.width, 4)).copy()} for s, x in t.items()}
+        return meshes, textures
+
 
 class V1Manifest:
     """A V1 manifest (src/Interfaces.ts:1-15; writer deprecated/encoder/src/Encoder30.js:155-160)."""
@@ -197,3 +207,56 @@ class V1Manifest:
             s = fd["startBytePosition"] - base
             out.append((fd["frameNumber"], fd["keyframeNumber"], bytes(blob[s:s + fd["meshLength"]])))
         return out
+
+
+class V2Playback:
+    """Host-side playback buffer of the V2 player: keeps `buffer_duration` seconds decoded ahead of a clock.
+
+    Mirrors src/V2/player.ts: `fetch_buffers` = fetchBuffers' leaky bucket (:272-323; every call requests what is missing up
+    to `buffer_duration` seconds ahead and hands ALL of it to the library as one batch, instead of one worker request per
+    file), `process_frame` = processFrame's selection rule (:388-470: geometry first; a frame whose mesh is missing is
+    skipped, a missing texture segment gives the mesh without texture -- the reference's failMaterial), `update` =
+    update + removePlayedBuffer (:531-562).  `decode(frames, segments) -> (meshMap part, textureMap part)` is injected:
+    `V2Sequence.decode` copies in production, a stub in the CPU tests.  Results are copied out of the library-owned
+    arenas (they are only valid until the next batch), like the transferables the workers post back.
+    """
+
+    def __init__(self, man, decode, buffer_duration=4):
+        self.man, self.decode, self.buffer_duration = man, decode, buffer_duration
+        self.mesh_map, self.texture_map = {}, {}                 # frame -> geometry, segment -> texture (:68-69)
+        self.last_geometry, self.last_segment = -1, -1           # lastRequestedGeometryFrame / lastRequestedTextureSegment
+        self.requests = 0
+
+    def fetch_buffers(self, t):
+        geo, tex, self.last_geometry, self.last_segment = self.man.fetch_window(t, self.last_geometry, self.last_segment, self.buffer_duration)
+        if geo or tex:
+            meshes, textures = self.decode(geo, tex)
+            self.mesh_map.update(meshes); self.texture_map.update(textures); self.requests += 1
+        return len(geo), len(tex)
+
+    def buffered_fraction(self):
+        """onMeshBuffering's argument (:409): share of the look-ahead window that is decoded."""
+        return len(self.mesh_map) / (self.man.geometry["frameRate"] * self.buffer_duration)
+
+    def process_frame(self, t):
+        """What the renderer shows at time t: None (track ended or mesh not decoded: the frame is skipped), else
+        {"frame", "geometry", "segment", "layer", "texture"} with texture None when its segment is missing."""
+        at = self.man.frames_at(t)
+        g = at["geometry_frame"]
+        if g >= self.man.geometry_frame_count or g not in self.mesh_map:
+            return None
+        return {"frame": g, "geometry": self.mesh_map[g], "segment": at["segment"], "layer": at["layer"], "texture": self.texture_map.get(at["segment"])}
+
+    def remove_played_buffer(self, frame_no, segment_no):
+        for k in [k for k in self.mesh_map if k < frame_no]:
+            del self.mesh_map[k]
+        for k in [k for k in self.texture_map if k < segment_no]:
+            del self.texture_map[k]
+
+    def update(self, t):
+        shown = self.process_frame(t)
+        at = self.man.frames_at(t)
+        g_keep = math.ceil(120 / self.man.geometry["frameRate"])                                  # :544-546 (screens up to 120 Hz)
+        s_keep = math.ceil(120 / (self.man.texture["frameRate"] * self.man.batch_size))
+        self.remove_played_buffer(at["geometry_frame"] - g_keep, at["segment"] - s_keep)
+        return shown
