@@ -149,9 +149,12 @@ UVOL_HD int etc1s_slice_symbols(BitRd &b, const SliceTables &T, uint32_t bx, uin
 
 // ---------------------------------------------------------------------------------------------
 // ETC1S block -> 16 RGBA texels (B.5).  ep = {r5,g5,b5,inten}, sel = 4 row bytes (2 bits/pixel).
+// The intensity table {-b, -a, a, b} per table id: a = 2 5 9 13 18 24 33 47, b = 8 17 29 42 60 80 106 183, packed one byte per id
+// (pure register arithmetic: an indexed local array would live in local memory and cost L1 traffic in the block kernels).
 UVOL_HD uint32_t etc1s_color(uint32_t ep, int k) {
-    const int tab[8][4] = {{-8, -2, 2, 8}, {-17, -5, 5, 17}, {-29, -9, 9, 29}, {-42, -13, 13, 42}, {-60, -18, 18, 60}, {-80, -24, 24, 80}, {-106, -33, 33, 106}, {-183, -47, 47, 183}};
-    const int d = tab[(ep >> 24) & 7][k];
+    const unsigned t8 = 8u * ((ep >> 24) & 7u);
+    const int a = (int)((0x2F2118120D090502ull >> t8) & 255u), b = (int)((0xB76A503C2A1D1108ull >> t8) & 255u);
+    const int d = k == 0 ? -b : (k == 1 ? -a : (k == 2 ? a : b));
     uint32_t out = 0;
     for (int c = 0; c < 3; c++) { const int c5 = (int)((ep >> (8 * c)) & 31); int v = ((c5 << 3) | (c5 >> 2)) + d; v = v < 0 ? 0 : (v > 255 ? 255 : v); out |= (uint32_t)v << (8 * c); }
     return out;
@@ -235,7 +238,9 @@ UVOL_HD int basis_build_globals(const Ktx2File &f, const uint8_t *file, BasisGlo
 
 // One ETC1S block -> RGBA32 rows.  rows[r] receives 4 packed RGBA texels of pixel row r.
 UVOL_HD void etc1s_block_rows(uint32_t ep, uint32_t sel, uint32_t rows[4][4]) {
-    uint32_t col[4];
-    for (int k = 0; k < 4; k++) col[k] = etc1s_color(ep, k) | 0xff000000u;
-    for (int y = 0; y < 4; y++) { const uint32_t rb = (sel >> (8 * y)) & 255u; for (int x = 0; x < 4; x++) rows[y][x] = col[(rb >> (2 * x)) & 3u]; }
+    const uint32_t c0 = etc1s_color(ep, 0) | 0xff000000u, c1 = etc1s_color(ep, 1) | 0xff000000u, c2 = etc1s_color(ep, 2) | 0xff000000u, c3 = etc1s_color(ep, 3) | 0xff000000u;
+    for (int y = 0; y < 4; y++) {
+        const uint32_t rb = (sel >> (8 * y)) & 255u;
+        for (int x = 0; x < 4; x++) { const uint32_t q = (rb >> (2 * x)) & 3u; rows[y][x] = (q & 2u) ? ((q & 1u) ? c3 : c2) : ((q & 1u) ? c1 : c0); }      // selects, not an indexed array
+    }
 }

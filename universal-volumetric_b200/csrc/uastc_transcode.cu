@@ -140,12 +140,19 @@ __global__ void __launch_bounds__(256) k_uastc_blocks(const Ktx2File *files, int
     __shared__ UastcShared T;
     for (uint32_t i = threadIdx.x; i < sizeof(UastcShared) / 4; i += 256) ((uint32_t *)&T)[i] = g_tables[i];
     __syncthreads();
-    const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
-    const Ktx2File &f = files[fi];
-    if (f.status || !f.is_uastc) return;
-    const uint32_t nblk = f.bx * f.by, W = f.width, H = f.height, bxn = f.bx;
-    const uint8_t *src0 = blob + f.file_off + f.level_off + (size_t)L * nblk * 16;
-    uint8_t *dst = O + f.o_rgba + (size_t)L * W * H * 4;
+    __shared__ struct { const uint8_t *src0; uint8_t *dst; uint32_t nblk, W, H, bxn, fi, skip; } K;      // per-layer constants, fetched once per CTA
+    if (threadIdx.x == 0) {
+        const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
+        const Ktx2File &f = files[fi];
+        K.skip = f.status || !f.is_uastc; K.fi = fi;
+        K.nblk = f.bx * f.by; K.W = f.width; K.H = f.height; K.bxn = f.bx;
+        K.src0 = blob + f.file_off + f.level_off + (size_t)L * K.nblk * 16;
+        K.dst = O + f.o_rgba + (size_t)L * f.width * f.height * 4;
+    }
+    __syncthreads();
+    if (K.skip) return;
+    const uint32_t nblk = K.nblk, W = K.W, H = K.H, bxn = K.bxn, fi = K.fi;
+    const uint8_t *src0 = K.src0; uint8_t *dst = K.dst;
     const bool aligned = (((uintptr_t)src0) & 15) == 0, whole = (W & 3) == 0;
 #pragma unroll 1
     for (uint32_t k = 0; k < UASTC_CHUNKS; k++) {
