@@ -290,15 +290,17 @@ def main():
     W = dict(WORKLOADS[args.workload])
     if args.window_segments > 0:
         W["window_segments"] = args.window_segments
-    elif W["fmt"] == "uastc" and W["window_segments"] and W["frames"] >= 500:
-        # pinned host buffers of the e2e path: ~25 GB per rank with 72-segment windows of C3; halve the window if the host cannot hold that for every rank
-        try:
-            import psutil
-            if psutil.virtual_memory().available / max(1, world) < 40e9:
-                W["window_segments"] = max(1, W["window_segments"] // 2); W["label"] += " [window halved: host memory]"
-        except Exception:
-            pass
-    frames, verts, tex, seq, seed = W["frames"], W["verts"], W["tex"], W["seq"], W["seed"]
+    # Pinned host memory of the e2e path: every window ctx holds its own result buffers (C3: 28 GB of results + 5 GB of staged inputs
+    # per rank).  If the host cannot hold that for every rank, the windows share one set of result buffers and the e2e pass runs
+    # them one after the other (the resident pass keeps running them concurrently).
+    low_host_memory = False
+    try:
+        import psutil
+        low_host_memory = W["fmt"] == "uastc" and W["frames"] >= 500 and psutil.virtual_memory().available / max(1, world) < 48e9
+    except Exception:
+        pass
+    if os.environ.get("UVOL_BENCH_LOW_HOST_MEMORY"):
+        low_host_memory = os.environ["UVOL_BENCH_LOW_HOST_MEMORY"] == "1"
     ncores = os.cpu_count() or 1
     if W["fmt"] == "corto":
         return bench_v1(args, W, rank, world, local)
@@ -338,6 +340,8 @@ def main():
     ctxs = [uv.Context(local, profiling=True) for _ in windows]
     for c in ctxs[1:]:
         c.share_arenas(ctxs[0])
+        if low_host_memory:
+            c.share_host_outputs(ctxs[0])
     players = [uv.V2Player(c) for c in ctxs]
     ctx = ctxs[0]
     n_k = len(ktx)
@@ -373,7 +377,8 @@ def main():
         shared phase-2 scratch from window to window, so the other windows' phase 1 and result copies overlap it.  Returns the summed
         statistics, the device time spanned by the whole step (first kernel to last kernel, CUDA events) and counts."""
         sg = st = None; tot = [0, 0, 0, 0]
-        for a, b, cnt in pool.map(one_window, [(w, resident) for w in range(len(windows))]):
+        jobs_ = [(w, resident) for w in range(len(windows))]
+        for a, b, cnt in (pool.map(one_window, jobs_) if resident or not low_host_memory else map(one_window, jobs_)):
             sg = merge(sg, a); st = merge(st, b); tot = [x + y for x, y in zip(tot, cnt)]
         return sg, st, uv.span_ms(ctxs), tuple(tot)
 
@@ -485,7 +490,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": workload_name, "frames_per_gpu": frames, "segments_per_gpu": n_k, "verts": info["verts"], "faces": info["faces"],
                            "points_per_frame": P_total / frames, "distinct_geometry_frames": info["distinct_geometry"], "distinct_texture_segments": info["distinct_textures"],
-                           "windows": [len(wd) for wd, _ in windows], "windows_concurrent": len(windows) > 1,
+                           "windows": [len(wd) for wd, _ in windows], "windows_concurrent": len(windows) > 1, "e2e_windows_sequential_low_host_memory": low_host_memory,
                            "scratch_gb_largest_window": round((sg["scratch_bytes"] + st["scratch_bytes"]) / 1e9, 2),
                            "l2": "flushed between timed iterations (256 MiB memset); every window's working set is far larger than L2",
                            "parallelism": f"frames sharded, {world} rank(s), no data-path collective"},

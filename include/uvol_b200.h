@@ -131,6 +131,11 @@ int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data, const siz
  * window's phase 2 (mirrors the reference keeping several decode requests in flight across its worker pool). */
 int uvol_share_arenas(uvol_ctx *ctx, uvol_ctx *owner);
 
+/* Makes `ctx` return its UVOL_MEM_HOST results in the pinned host buffers of `owner` (bounds the pinned memory of a windowed
+ * sequence to one window's outputs).  Results of either ctx are then valid until the next UVOL_MEM_HOST call on the other; such
+ * calls must be serialised by the caller. */
+int uvol_share_host_outputs(uvol_ctx *ctx, uvol_ctx *owner);
+
 /* Device time (ms, CUDA events) spanned by the last calls of `n` contexts that ran concurrently: first kernel of any of them
  * to last kernel of any of them.  Measurement aid; needs uvol_set_profiling(ctx, 1). */
 int uvol_span_ms(uvol_ctx *const *ctxs, int n, float *ms);

@@ -303,8 +303,9 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
     stamp();
     ctx->span_tex_end = ev - 1;
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
-    UVOL_CUDA(ctx, ctx->h_tout.reserve(st_bytes + (memory == UVOL_MEM_HOST ? B.out + 256 : 0)));
-    TexState *hSt = (TexState *)ctx->h_tout.p; uint8_t *hO = (uint8_t *)ctx->h_tout.p + st_bytes;
+    UVOL_CUDA(ctx, ctx->h_tstate.reserve(st_bytes));                       // per-ctx even when the bulk result buffer is shared
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, ctx->ph_tout->reserve(B.out + 256));
+    TexState *hSt = (TexState *)ctx->h_tstate.p; uint8_t *hO = (uint8_t *)ctx->ph_tout->p;
     UVOL_CUDA(ctx, cudaMemcpyAsync(hSt, dSt, sizeof(TexState) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(hO, dO, B.out, cudaMemcpyDeviceToHost, st));
     stamp();
@@ -316,8 +317,7 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
 static int ktx2_finish(uvol_ctx *ctx, int memory, uvol_texture *out, uvol_stats &sx) {
     TexBatch &B = *ctx->tex; const int n = B.n;
     UVOL_CUDA(ctx, cudaGetLastError());
-    const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
-    TexState *hSt = (TexState *)ctx->h_tout.p; uint8_t *hO = (uint8_t *)ctx->h_tout.p + st_bytes;
+    TexState *hSt = (TexState *)ctx->h_tstate.p; uint8_t *hO = (uint8_t *)ctx->ph_tout->p;
     uint8_t *base = memory == UVOL_MEM_HOST ? hO : (uint8_t *)ctx->d_out_tex.p; uint64_t bytes_out = 0;
     for (int i = 0; i < n; i++) {
         const Ktx2File &f = B.files[i]; uvol_texture &t = out[i];

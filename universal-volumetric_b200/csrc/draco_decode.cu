@@ -1441,7 +1441,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     const DracoCounts *hC = (const DracoCounts *)ctx->h_counts.p;
     draco_plan_phase2(frames, hC, pl);
     UVOL_CUDA(ctx, ctx->d_out_geo.reserve(pl.out + 256));
-    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, ctx->h_out.reserve(pl.out + 256));
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, ctx->ph_out->reserve(pl.out + 256));
     UVOL_CUDA(ctx, ctx->d_scratch2.reserve(pl.scratch2 + 256));
     UVOL_CUDA(ctx, ctx->d_zscratch2.reserve(pl.zscratch2 + 256));
     // The traversal-record arena may be shared with the contexts of other windows (uvol_share_arenas): it is ours from here
@@ -1470,7 +1470,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     stamp("point_assign");
     if (memory == UVOL_MEM_HOST && pl.out_index) {      // the index buffers are final: copy them out on s3 while the rest of phase 2 runs
         UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[6], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(ctx->s3, ctx->sync_ev[6], 0));
-        UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.p, dO, pl.out_index, cudaMemcpyDeviceToHost, ctx->s3));
+        UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->ph_out->p, dO, pl.out_index, cudaMemcpyDeviceToHost, ctx->s3));
     }
     if (B.j_ransB - B.j_trav > 0) {
         const int ntj = B.j_ransB - B.j_trav;
@@ -1528,7 +1528,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     stamp("expand");
     ctx->span_geo_end = ev - 1 < 32 ? ev - 1 : 31;
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->h_out.p + pl.out_index, dO + pl.out_index, pl.out - pl.out_index, cudaMemcpyDeviceToHost, st));
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->ph_out->p + pl.out_index, dO + pl.out_index, pl.out - pl.out_index, cudaMemcpyDeviceToHost, st));
     stamp("d2h");
     UVOL_CUDA(ctx, cudaEventSynchronize(ctx->sync_ev[7]));
     p2_lock.unlock();
@@ -1536,7 +1536,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s3));
     UVOL_CUDA(ctx, cudaGetLastError());
     // ---- results
-    uint8_t *base = memory == UVOL_MEM_HOST ? (uint8_t *)ctx->h_out.p : dO;
+    uint8_t *base = memory == UVOL_MEM_HOST ? (uint8_t *)ctx->ph_out->p : dO;
     uint64_t bytes_out = 0;
     for (int i = 0; i < n; i++) {
         const DracoFrame &f = frames[i]; uvol_geometry &g = out[i];

@@ -39,7 +39,7 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
                     &c->d_tblob, &c->d_tdesc, &c->d_tslices, &c->d_tscratch, &c->d_out_tex,
                     &c->d_cblob, &c->d_cdesc, &c->d_cscratch, &c->d_czscratch, &c->d_out_corto, &c->d_ccounts, &c->d_caux};
     for (auto *b : db) b->release();
-    PinBuf *pb[] = {&c->h_blob, &c->h_desc, &c->h_aux, &c->h_counts, &c->h_out, &c->h_tblob, &c->h_tdesc, &c->h_tout, &c->h_cblob, &c->h_cdesc, &c->h_cout, &c->h_ccounts};
+    PinBuf *pb[] = {&c->h_blob, &c->h_desc, &c->h_aux, &c->h_counts, &c->h_out, &c->h_tblob, &c->h_tdesc, &c->h_tout, &c->h_tstate, &c->h_cblob, &c->h_cdesc, &c->h_cout, &c->h_ccounts};
     for (auto *b : pb) b->release();
     c->d_flush.release();
     if (c->geo) uvol_geo_batch_free(c->geo);
@@ -62,6 +62,15 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
 extern "C" int uvol_share_arenas(uvol_ctx *ctx, uvol_ctx *owner) {
     if (!ctx || !owner || ctx->device != owner->device) return UVOL_ERR_ARG;
     ctx->p2 = owner->p2;
+    return UVOL_OK;
+}
+
+// Lets `ctx` write its UVOL_MEM_HOST results into the pinned host buffers of `owner` instead of its own (bounds the pinned memory
+// of a windowed sequence to one window).  The results of either ctx are then valid only until the next UVOL_MEM_HOST call on the
+// other, and such calls must not run concurrently.
+extern "C" int uvol_share_host_outputs(uvol_ctx *ctx, uvol_ctx *owner) {
+    if (!ctx || !owner || ctx->device != owner->device) return UVOL_ERR_ARG;
+    ctx->ph_out = owner->ph_out; ctx->ph_tout = owner->ph_tout;
     return UVOL_OK;
 }
 

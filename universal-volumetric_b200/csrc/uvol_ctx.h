@@ -62,7 +62,7 @@ struct uvol_ctx {
     DevBuf d_blob, d_desc, d_aux, d_counts, d_scratch, d_zscratch, d_scratch2, d_zscratch2, d_jobs;
     DevBuf d_out_geo;             // library-owned geometry outputs (valid until the next geometry batch on this ctx)
     // texture path
-    PinBuf h_tblob, h_tdesc, h_tout;
+    PinBuf h_tblob, h_tdesc, h_tout, h_tstate;
     DevBuf d_tblob, d_tdesc, d_tslices, d_tscratch, d_out_tex;
     // V1 path
     PinBuf h_cblob, h_cdesc, h_cout, h_ccounts;
@@ -71,6 +71,7 @@ struct uvol_ctx {
     DevBuf d_flush;
     // stats of the last batch
     uvol_stats stats = {}, stats_tex = {};
+    PinBuf *ph_out = &h_out, *ph_tout = &h_tout;   // pinned host outputs: own, or another ctx's (uvol_share_host_outputs)
     bool profile = false;
     int span_geo_end = 0, span_tex_end = 0;      // event index of the last kernel stamp of the last geometry / texture run (0: none)
 };

@@ -52,6 +52,12 @@ class Context:
             raise N.UvolError("uvol_share_arenas failed")
         self._owner = owner          # keep the owner alive
 
+    def share_host_outputs(self, owner):
+        """Return UVOL_MEM_HOST results in `owner`'s pinned buffers (such calls on the two contexts must then be serialised)."""
+        if self._L.uvol_share_host_outputs(self._h, owner._h) != 0:
+            raise N.UvolError("uvol_share_host_outputs failed")
+        self._owner_host = owner
+
     def flush_l2(self):
         self._L.uvol_flush_l2(self._h)
 
