@@ -301,6 +301,7 @@ def main():
         pass
     if os.environ.get("UVOL_BENCH_LOW_HOST_MEMORY"):
         low_host_memory = os.environ["UVOL_BENCH_LOW_HOST_MEMORY"] == "1"
+    frames, verts, tex, seq, seed = W["frames"], W["verts"], W["tex"], W["seq"], W["seed"]
     ncores = os.cpu_count() or 1
     if W["fmt"] == "corto":
         return bench_v1(args, W, rank, world, local)
