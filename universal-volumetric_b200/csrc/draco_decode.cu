@@ -1376,10 +1376,6 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     auto stamp = [&](const char *name) { if (ev < 32) g_geo_stage_names[ev - 1] = name; if (ctx->profile && ev < 32) cudaEventRecord(ctx->ev[ev], st); ev++; };
     if (!fresh_upload && ctx->profile) cudaEventRecord(ctx->ev[0], st);
     uint8_t *hd = (uint8_t *)ctx->h_desc.p;
-    // Windows that share the traversal arena run their phase 1 one after the other: the second window's entropy / connectivity
-    // stages then overlap the first window's traversal (which they would have to wait for anyway) instead of competing with the
-    // first window's own phase 1 for the same SM sub-partitions.
-    std::unique_lock<std::mutex> p1_lock(ctx->p2->mu_p1);
     draco_plan_phase1(frames, pl);      // restores the phase-1 view of the descriptors (idempotent)
     memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -1442,7 +1438,6 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     stamp("point_count");
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));
-    p1_lock.unlock();
     const DracoCounts *hC = (const DracoCounts *)ctx->h_counts.p;
     draco_plan_phase2(frames, hC, pl);
     UVOL_CUDA(ctx, ctx->d_out_geo.reserve(pl.out + 256));

@@ -43,7 +43,7 @@ struct PinBuf {
 // WINDOWS of one sequence share one (uvol_share_arenas), under a mutex held from a window's corner-record kernels to the end
 // of its traversal.  Everything else (other scratch, outputs, inputs) stays per ctx, so the other window's connectivity
 // stages, prediction stages and result copies run concurrently.
-struct Phase2Arena { DevBuf d_frec; std::mutex mu, mu_p1; };   // mu: the arena itself; mu_p1: staggers the sharing windows' phase 1 (see draco_run)
+struct Phase2Arena { DevBuf d_frec; std::mutex mu; };
 
 struct GeoBatch; struct TexBatch; struct CortoBatch;
 void uvol_geo_batch_free(GeoBatch *); void uvol_tex_batch_free(TexBatch *); void uvol_corto_batch_free(CortoBatch *);
