@@ -97,6 +97,25 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_cpus(local, world):
+    """One process per GPU: pin this rank to the CPUs NVML reports as local to its GPU (pinned staging / result buffers are then
+    allocated and touched on the GPU's NUMA node) and split the staging threads between the ranks.  Returns the CPU count used."""
+    ncpu = len(os.sched_getaffinity(0))
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+        words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys), (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & os.sched_getaffinity(0)
+        if cpus and world > 1:
+            os.sched_setaffinity(0, cpus); ncpu = len(cpus)
+    except Exception:
+        pass
+    os.environ.setdefault("UVOL_STAGING_THREADS", str(max(1, min(8, (os.cpu_count() or 1) // (2 * max(1, world))))))
+    return ncpu
+
+
 def make_workload(name, rank):
     from tools.synth import synth
     w = WORKLOADS[name]
@@ -330,6 +349,7 @@ def main():
         print(json.dumps(line)); return 0
 
     # ------------------------------------------------------------------ our arm
+    rank_cpus = bind_to_gpu_cpus(local, world)
     import torch
     import torch.distributed as dist
     if world > 1:
@@ -494,7 +514,8 @@ def main():
                            "windows": [len(wd) for wd, _ in windows], "windows_concurrent": len(windows) > 1, "e2e_windows_sequential_low_host_memory": low_host_memory,
                            "scratch_gb_largest_window": round((sg["scratch_bytes"] + st["scratch_bytes"]) / 1e9, 2),
                            "l2": "flushed between timed iterations (256 MiB memset); every window's working set is far larger than L2",
-                           "parallelism": f"frames sharded, {world} rank(s), no data-path collective"},
+                           "parallelism": f"frames sharded, {world} rank(s), no data-path collective",
+                           "host": {"cpus_of_rank0": rank_cpus, "staging_threads": int(os.environ.get("UVOL_STAGING_THREADS", "0"))}},
                 "mverts_per_s": P_total * world * args.steps / (dev_ms / 1e3) / 1e6, "mtexels_per_s": texels * world * args.steps / (dev_ms / 1e3) / 1e6,
                 "roofline": roof, "pipeline_roofline": pipeline, "stages": stages,
                 "cpu_baseline": cpu,

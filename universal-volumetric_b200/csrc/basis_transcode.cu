@@ -236,7 +236,7 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
     UVOL_CUDA(ctx, ctx->h_tblob.reserve(blob_bytes + 64));
     {   // staging copy into the pinned blob; UASTC segments are large (29 MB each at 2048^2 x 7), so big batches are copied by several threads
         auto copy_range = [&](int lo, int hi) { for (int i = lo; i < hi; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_tblob.p + files[i].file_off, data[i], size[i]); };
-        const int nthreads = B.bytes_in > (64ull << 20) ? (int)std::min<uint64_t>(8, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1;
+        const int nthreads = B.bytes_in > (64ull << 20) ? uvol_staging_threads() : 1;
         if (nthreads <= 1 || n < 2) copy_range(0, n);
         else {
             std::vector<std::thread> pool; int lo = 0; uint64_t acc = 0; const uint64_t per = B.bytes_in / nthreads + 1;

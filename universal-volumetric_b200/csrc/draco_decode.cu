@@ -1311,7 +1311,7 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
     UVOL_CUDA(ctx, ctx->h_blob.reserve(blob_bytes + 64));
     {   // staging copy into the pinned blob, by a few threads when the batch is large (it sits in front of the first kernel)
         auto copy_range = [&](int lo, int hi) { for (int i = lo; i < hi; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_blob.p + frames[i].file_off, data[i], size[i]); };
-        const int nthreads = B.bytes_in > (32ull << 20) ? (int)std::min<uint64_t>(8, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1;
+        const int nthreads = B.bytes_in > (32ull << 20) ? uvol_staging_threads() : 1;
         if (nthreads <= 1) copy_range(0, n);
         else {
             std::vector<std::thread> pool; const int per = (n + nthreads - 1) / nthreads;

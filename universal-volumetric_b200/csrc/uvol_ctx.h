@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <mutex>
+#include <stdlib.h>
+#include <thread>
 #include <string>
 #include <vector>
 #include "uvol_internal.h"
@@ -78,6 +80,15 @@ struct uvol_ctx {
 
 #define UVOL_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     char b_[256]; snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); (ctx)->err = b_; return UVOL_ERR_CUDA; } } while (0)
+
+// Host threads used to stage a large batch into the pinned input blob: UVOL_STAGING_THREADS, else min(8, cores / 2).  A launcher that
+// runs one process per GPU divides the cores between its ranks through the variable.
+static inline int uvol_staging_threads() {
+    static const int n = [] { const char *e = getenv("UVOL_STAGING_THREADS"); int v = e ? atoi(e) : 0;
+                              if (v <= 0) { v = (int)std::thread::hardware_concurrency() / 2; if (v > 8) v = 8; }
+                              return v < 1 ? 1 : (v > 64 ? 64 : v); }();
+    return n;
+}
 
 static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
