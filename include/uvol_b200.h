@@ -140,6 +140,13 @@ int uvol_share_host_outputs(uvol_ctx *ctx, uvol_ctx *owner);
  * to last kernel of any of them.  Measurement aid; needs uvol_set_profiling(ctx, 1). */
 int uvol_span_ms(uvol_ctx *const *ctxs, int n, float *ms);
 
+/* Zstandard frame decoder (RFC 8878) used for KTX2 supercompressionScheme 2 (replaces src/lib/zstddec.module.js, the WASM zstd the
+ * reference inflates levels with, src/lib/KTX2Loader.js:803-817).  Host code: inflates every frame in src[0..n) into dst[0..cap);
+ * *out_len receives the byte count.  No dictionaries; the content checksum is not verified. */
+int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
+/* Test aid: how often each part of the format was decoded since the last reset (see csrc/zstd_inflate.cpp for the 16 slots). */
+void uvol_zstd_feature_counts(uint64_t *out16, int reset);
+
 /* Writes a buffer larger than L2 (256 MiB) on the ctx's stream and waits: L2 flush between timed iterations. */
 int uvol_flush_l2(uvol_ctx *ctx);
 

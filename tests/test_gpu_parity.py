@@ -266,3 +266,28 @@ def test_playback_from_manifest(uv, ctx, tmp_path):
                 rgba = oracle_ktx2(ktx[r["segment"]])["rgba"].reshape(-1, 64, 64, 4)
                 assert r["texture"] is not None and np.array_equal(r["texture"]["data"][r["layer"]], rgba[r["layer"]])
     assert sorted(seen) == list(range(frames)) and pb.requests >= 2 and len(pb.mesh_map) <= 30 + 6
+
+
+def _zstd_wrap(plain, level=3):
+    """Re-wraps a scheme-0 UASTC KTX2 as supercompressionScheme 2: the level becomes one Zstandard frame (made by libzstd, test-only)."""
+    import struct
+    from test_zstd import Z, compress
+    if Z is None:
+        pytest.skip("libzstd not present (needed to build the test vector)")
+    lv_off, lv_len = struct.unpack_from("<QQ", plain, 80)
+    z = compress(plain[lv_off:lv_off + lv_len], level)
+    out = bytearray(plain[:lv_off]) + z
+    struct.pack_into("<I", out, 44, 2); struct.pack_into("<QQQ", out, 80, lv_off, len(z), lv_len)
+    return bytes(out)
+
+
+def test_uastc_zstd_supercompression(uv, ctx):
+    """KTX2 supercompressionScheme 2 (what `basisu -uastc -ktx2` writes by default): the level is inflated by the library's own
+    Zstandard decoder on the host, then goes through the same block kernel -- texels must equal the oracle's decode of the plain file."""
+    plain = [_uastc_file(256, 3, 31), _uastc_file(64, 2, 32, crop=(50, 61)), _uastc_file(512, 7, 33, mask=synth.UASTC_OPAQUE_MODES, alpha=False)]
+    zs = [_zstd_wrap(p, lvl) for p, lvl in zip(plain, (1, 9, 3))]
+    broken = zs[0][:len(zs[0]) - 100]
+    res = uv.KTX2Loader(ctx).transcode_batch([zs[0], plain[1], zs[1], zs[2], broken])
+    assert [r["status"] for r in res[:4]] == [0, 0, 0, 0] and res[4]["status"] < 0
+    for r, p in zip(res[:4], [plain[0], plain[1], plain[1], plain[2]]):
+        assert np.array_equal(r["data"], oracle_ktx2(p)["rgba"])

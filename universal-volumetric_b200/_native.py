@@ -76,6 +76,7 @@ def lib():
     L.uvol_flush_l2.argtypes = [vp]; L.uvol_flush_l2.restype = i
     L.uvol_share_arenas.argtypes = [vp, vp]; L.uvol_share_arenas.restype = i
     L.uvol_share_host_outputs.argtypes = [vp, vp]; L.uvol_share_host_outputs.restype = i
+    L.uvol_zstd_inflate.argtypes = [ctypes.c_char_p, sz, ctypes.c_void_p, sz, ctypes.POINTER(sz)]; L.uvol_zstd_inflate.restype = i
     L.uvol_span_ms.argtypes = [ctypes.POINTER(vp), i, ctypes.POINTER(ctypes.c_float)]; L.uvol_span_ms.restype = i
     pv, ps = ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(sz)
     L.uvol_decode_v2_batch.argtypes = [vp, pv, ps, i, pv, ps, i, i, ctypes.POINTER(Geometry), ctypes.POINTER(Texture)]; L.uvol_decode_v2_batch.restype = i

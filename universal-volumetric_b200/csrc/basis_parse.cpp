@@ -41,9 +41,17 @@ int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File 
     }
     f.level_off = (uint32_t)lvOff; f.first_slice = (uint32_t)slices.size();
     const uint64_t nblk = (uint64_t)f.bx * f.by;
+    f.zstd = 0;
     if (f.is_uastc) {
-        if (sc != 0) return UVOL_ERR_UNSUPPORTED;      // Zstd-supercompressed levels are not handled
+        if (sc != 0 && sc != 2) return UVOL_ERR_UNSUPPORTED;      // none or Zstandard (KTX2Loader.js:46-47); zlib (3) is not used by basisu
         f.has_alpha = chan0 == 3;
+        if (sc == 2) {          // the level is one Zstandard frame: inflated by the host into the staging blob (csrc/zstd_inflate.cpp)
+            const uint64_t ulen = rd64(b + 96);
+            if (ulen < (uint64_t)nl * nblk * 16 || ulen >= (1ull << 31) || lvLen >= (1ull << 31) || lvLen == 0) return ulen >= (1ull << 31) ? UVOL_ERR_UNSUPPORTED : UVOL_ERR_TRUNCATED;
+            f.zstd = 1; f.z_src_off = (uint32_t)lvOff; f.z_src_len = (uint32_t)lvLen; f.z_len = (uint32_t)ulen; f.level_off = 0;
+            f.endpoint_count = f.selector_count = 0;
+            return UVOL_OK;
+        }
         if (lvLen < (uint64_t)nl * nblk * 16) return UVOL_ERR_TRUNCATED;
         f.endpoint_count = f.selector_count = 0;
         return UVOL_OK;

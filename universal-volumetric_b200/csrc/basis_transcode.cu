@@ -10,11 +10,13 @@
 // UASTC files skip the first three stages (no entropy coding) and run the block kernel in uastc_transcode.cu.
 #include <chrono>
 #include <string.h>
+#include <atomic>
 #include <thread>
 #include "uvol_ctx.h"
 #include "basis_core.h"
 
 int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
+extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
 int uvol_uastc_launch(int device, const Ktx2File *dF, int32_t *status2, const uint8_t *dBlob, uint8_t *dOut, const uint32_t *dLayerList, int nlayers,
                       uint32_t max_blocks, cudaStream_t st);
 
@@ -195,7 +197,7 @@ extern "C" const char *uvol_tex_stage_name(int i) { return (i >= 0 && i < 6) ? k
 
 struct TexBatch {
     std::vector<Ktx2File> files; std::vector<Ktx2Slice> slices; std::vector<uint32_t> layer_list, uastc_layers;
-    int n = 0; uint64_t blob_bytes = 0, scratch = 0, out = 0, bytes_in = 0; uint32_t max_blocks = 1, max_codebook = 0; bool any_alpha = false;
+    int n = 0; uint64_t blob_bytes = 0, scratch = 0, out = 0, bytes_in = 0; uint32_t max_blocks = 1, max_codebook = 0; bool any_alpha = false, any_zstd = false;
     size_t desc_bytes = 0, off_sl = 0, off_ll = 0, off_ul = 0; double parse_ms = 0; uint32_t launches = 0; int nev = 0;
 };
 void uvol_tex_batch_free(TexBatch *b) { delete b; }
@@ -205,15 +207,17 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
     if (!ctx->tex) ctx->tex = new TexBatch();
     TexBatch &B = *ctx->tex;
     B.n = n; B.files.assign((size_t)n, Ktx2File()); B.slices.clear(); B.layer_list.clear(); B.uastc_layers.clear();
-    B.max_blocks = 1; B.max_codebook = 0; B.any_alpha = false; B.bytes_in = 0;
+    B.max_blocks = 1; B.max_codebook = 0; B.any_alpha = false; B.any_zstd = false; B.bytes_in = 0;
     std::vector<Ktx2File> &files = B.files; std::vector<Ktx2Slice> &slices = B.slices;
     uint64_t blob_bytes = 0, s = 0, o = 0;
     for (int i = 0; i < n; i++) {
         Ktx2File &f = files[i]; memset(&f, 0, sizeof f);
-        f.file_off = blob_bytes; f.file_len = (uint32_t)size[i]; B.bytes_in += size[i];
-        blob_bytes = align_up(blob_bytes + size[i] + 8, 16);
+        f.file_len = (uint32_t)size[i]; B.bytes_in += size[i];
         const size_t slices_before = slices.size();
         f.status = (data[i] && size[i] < (1ull << 31)) ? uvol_ktx2_parse(data[i], size[i], (uint32_t)i, f, slices) : UVOL_ERR_ARG;
+        f.file_off = blob_bytes;                                      // the file itself, or (Zstd levels) the inflated level
+        blob_bytes = align_up(blob_bytes + (!f.status && f.zstd ? (uint64_t)f.z_len : (uint64_t)size[i]) + 8, 16);
+        if (!f.status && f.zstd) B.any_zstd = true;
         if (f.status) { slices.resize(slices_before); continue; }
         if (f.layers > 4095 || f.bx > 4096) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }
         const uint64_t nblk = (uint64_t)f.bx * f.by;
@@ -234,15 +238,24 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
     B.blob_bytes = blob_bytes; B.scratch = s; B.out = o;
     const size_t nsl = slices.size(), nll = B.layer_list.size(), nul = B.uastc_layers.size();
     UVOL_CUDA(ctx, ctx->h_tblob.reserve(blob_bytes + 64));
-    {   // staging copy into the pinned blob; UASTC segments are large (29 MB each at 2048^2 x 7), so big batches are copied by several threads
-        auto copy_range = [&](int lo, int hi) { for (int i = lo; i < hi; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_tblob.p + files[i].file_off, data[i], size[i]); };
-        const int nthreads = B.bytes_in > (64ull << 20) ? uvol_staging_threads() : 1;
-        if (nthreads <= 1 || n < 2) copy_range(0, n);
-        else {
-            std::vector<std::thread> pool; int lo = 0; uint64_t acc = 0; const uint64_t per = B.bytes_in / nthreads + 1;
-            for (int i = 0; i < n; i++) { acc += size[i]; if (acc >= per || i == n - 1) { pool.emplace_back(copy_range, lo, i + 1); lo = i + 1; acc = 0; } }
-            for (auto &t : pool) t.join();
-        }
+    {   // staging into the pinned blob by a few host threads: a copy of the file, or the inflated level of a Zstd-supercompressed file
+        std::atomic<int> next{0};
+        auto work = [&]() {
+            for (int i; (i = next.fetch_add(1)) < n;) {
+                if (!data[i] || size[i] >= (1ull << 31)) continue;
+                uint8_t *dst = (uint8_t *)ctx->h_tblob.p + files[i].file_off;
+                if (!files[i].status && files[i].zstd) {
+                    size_t got = 0;
+                    const int rc = uvol_zstd_inflate(data[i] + files[i].z_src_off, files[i].z_src_len, dst, files[i].z_len, &got);
+                    if (rc || got != files[i].z_len) files[i].status = rc ? rc : UVOL_ERR_CORRUPT;
+                } else memcpy(dst, data[i], size[i]);
+            }
+        };
+        int nthreads = B.bytes_in > (64ull << 20) || B.any_zstd ? uvol_staging_threads() : 1;
+        if (B.any_zstd && !getenv("UVOL_STAGING_THREADS")) nthreads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));   // inflating is ~20x slower than copying
+        if (nthreads > n) nthreads = n;
+        if (nthreads <= 1) work();
+        else { std::vector<std::thread> pool; for (int t = 0; t < nthreads; t++) pool.emplace_back(work); for (auto &t : pool) t.join(); }
     }
     B.off_sl = sizeof(Ktx2File) * (size_t)n; B.off_ll = B.off_sl + sizeof(Ktx2Slice) * (nsl + 1); B.off_ul = B.off_ll + 4 * (nll + 1);
     B.desc_bytes = B.off_ul + 4 * (nul + 1);

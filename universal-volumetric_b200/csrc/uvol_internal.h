@@ -100,6 +100,8 @@ struct Ktx2File {
     uint64_t o_endpoints, o_selectors, o_huff, o_sorted;           // u8x4[ec], u8x4[sc], HuffTable[4], u16 pool
     uint64_t o_rgba;                                               // output arena offset, layers * w * h * 4
     uint32_t hist_size, pad;
+    // Zstd-supercompressed level (scheme 2, UASTC only): inflated on the host into the blob at file_off (level_off = 0)
+    uint32_t zstd, z_src_off, z_src_len, z_len;
 };
 struct Ktx2Slice {
     uint32_t file; uint32_t layer;
