@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker(const DracoFr
     const uint32_t fi = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if ((int)fi >= nframes || (threadIdx.x & 31) != 0) return;
     if (frames[fi].status) { counts[fi].status = frames[fi].status; return; }
-    if (counts[fi].status || frames[fi].trav == 2) return;      // valence frames: k_edgebreaker_valence
+    if (counts[fi].status || frames[fi].trav == 2) return;      // valence frames: k_edgebreaker_valence2
     const DracoFrame &f = frames[fi];
     EbMem m; m.opp = (int *)(S + f.o_opp); m.c2v = (int *)(S + f.o_c2v); m.lmc = (int *)(S + f.o_lmc); m.val = (int *)(S + f.o_val);
     m.hole = S + f.o_hole; m.stack = (int *)(S + f.o_stack); m.skey = m.stack + f.nsym + 8; m.sval = m.skey + f.nts + 1; m.invalid = (int *)(S + f.o_invalid);
@@ -231,208 +231,9 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker(const DracoFr
 }
 
 // ---------------------------------------------------------------------------------------------
-// Valence-mode edgebreaker, latency-optimised (the generic k_edgebreaker above remains the path for
-// the standard traversal).  The walk is a serial state machine (the next symbol's context depends on
-// the mesh built so far), so the only lever is the length of the dependent chain per symbol:
-//   * the active triangle (corner + its three vertices AND their vertex records) lives in registers;
-//   * per-vertex state is one 16-byte record {left-most corner, vertex before it on the boundary,
-//     valence, on-hole flag}: a C symbol needs exactly one record load (the boundary neighbour), R / L / E none;
-//   * records of the most recent EB_RING vertices sit in a shared-memory ring (the boundary vertices
-//     a C symbol touches were created about one strip earlier), older ones are read from global;
-//   * the next symbol of all six contexts is preloaded in registers, so the context -> symbol step
-//     is a select, not a load; opp / c2v are write-only here.
-// S symbols, topology-split events, start faces and the isolated-vertex fold use the generic memory path.
-#define EB_RING 2048
-struct VRec { int lmc, lpv, val, hole; };
-__device__ __forceinline__ VRec vr_unpack(uint4 u) { VRec r; r.lmc = (int)u.x; r.lpv = (int)u.y; r.val = (int)u.z; r.hole = (int)u.w; return r; }
-__device__ __forceinline__ uint4 vr_pack(const VRec &r) { return make_uint4((uint32_t)r.lmc, (uint32_t)r.lpv, (uint32_t)r.val, (uint32_t)r.hole); }
-
-__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
-                                                            uint8_t *S, int nframes) {
-    extern __shared__ uint4 eb_smem[];
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint4 *ring = eb_smem + (size_t)wib * (EB_RING + 128);
-    int *stk = (int *)(ring + EB_RING);
-    const uint32_t fi = blockIdx.x * SERIAL_WARPS + wib;
-    if ((int)fi >= nframes) return;
-    if (frames[fi].status) { if (lane == 0) counts[fi].status = frames[fi].status; return; }
-    if (counts[fi].status || frames[fi].trav != 2) return;
-    const DracoFrame &f = frames[fi];
-    int *opp = (int *)(S + f.o_opp), *c2v = (int *)(S + f.o_c2v), *lmc = (int *)(S + f.o_lmc), *gstk = (int *)(S + f.o_stack);
-    uint8_t *hole = S + f.o_hole; uint4 *vrec = (uint4 *)(S + f.o_val);     // o_val is sized 16 B per vertex slot (see draco_plan.h)
-    int *skey = gstk + f.nsym + 8, *sval = skey + f.nts + 1, *invalid = (int *)(S + f.o_invalid);
-    const int F = (int)f.nf, maxv = (int)(f.nv_enc + f.nsplit), nsym = (int)f.nsym;
-    int nverts = 0, ninv = 0, sp = 0, status = 0, numf = 0;
-    if (lane == 0) {
-        // Context symbol arrays are consumed from the back.  Each context keeps its next 8 symbols packed in a
-        // 64-bit register (byte 0 = next symbol); refills are aligned 8-byte loads issued when a register runs dry,
-        // so the symbol select is pure register work in the common case.
-        const uint8_t *csb[6]; int kk[6];
-        for (int i = 0; i < 6; i++) { csb[i] = S + f.o_ctxsym[i]; kk[i] = (int)f.ctx[i].count; }
-        unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0; int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, h5 = 0;   // packed symbols, how many are valid
-#define CTX_REFILL(W, H, I) do { int take_ = kk[I] < 8 ? kk[I] : 8; unsigned long long v_ = 0; \
-            for (int b_ = 0; b_ < take_; b_++) v_ |= (unsigned long long)csb[I][kk[I] - 1 - b_] << (8 * b_); \
-            W = v_; H = take_; kk[I] -= take_; } while (0)
-#define CTX_TAKE(W, H, I) do { if (H == 0) { if (kk[I] <= 0) { s = 255; break; } CTX_REFILL(W, H, I); } s = (int)(W & 255u); W >>= 8; H--; } while (0)
-        const uint32_t *ts = aux + f.ts_off; int ts_top = (int)f.nts, nsa = 0;
-        uint32_t next_ts = ts_top > 0 ? ts[3 * (ts_top - 1)] : 0xffffffffu;
-        int a = -1, ta = 0, na = 0, pa = 0; VRec rt = {0, 0, 0, 0}, rn = rt, rp = rt;
-        int ctx = -1;
-#define VLOAD(v) vr_unpack(((v) >= nverts - EB_RING) ? ring[(v) & (EB_RING - 1)] : vrec[(v)])
-#define VSTORE(v, r) do { const uint4 u_ = vr_pack(r); if ((v) >= nverts - EB_RING) ring[(v) & (EB_RING - 1)] = u_; vrec[(v)] = u_; } while (0)
-        for (int sid = 0; sid < nsym; sid++) {
-            int s;
-            if (ctx < 0) s = 4;
-            else {
-                switch (ctx) {
-                    case 0: CTX_TAKE(w0, h0, 0); break;
-                    case 1: CTX_TAKE(w1, h1, 1); break;
-                    case 2: CTX_TAKE(w2, h2, 2); break;
-                    case 3: CTX_TAKE(w3, h3, 3); break;
-                    case 4: CTX_TAKE(w4, h4, 4); break;
-                    default: CTX_TAKE(w5, h5, 5); break;
-                }
-                if (s > 4) { status = UVOL_ERR_CORRUPT; break; }
-            }
-            if (numf >= F) { status = UVOL_ERR_CORRUPT; break; }
-            const int c0 = 3 * numf; numf++;
-            if (s == 0) {                                   // C: close the fan at the vertex next to the gate
-                if (sp == 0 || rn.lmc < 0) { status = UVOL_ERR_CORRUPT; break; }
-                const int vx = na, b = cnext(rn.lmc), vbn = rn.lpv;
-                if (a == b || vx == pa || vx == vbn || vbn == pa) { status = UVOL_ERR_CORRUPT; break; }
-                VRec rb = VLOAD(vbn);
-                opp[c0] = DINV; opp[c0 + 1] = a; opp[c0 + 2] = b; opp[a] = c0 + 1; opp[b] = c0 + 2;
-                c2v[c0] = vx; c2v[c0 + 1] = vbn; c2v[c0 + 2] = pa;
-                rp.lmc = c0 + 2; rp.lpv = vbn; rp.val += 1; VSTORE(pa, rp);
-                rn.hole = 0; VSTORE(vx, rn);
-                rb.val += 1; VSTORE(vbn, rb);
-                a = c0; ta = vx; rt = rn; na = vbn; rn = rb;
-            } else if (s == 3) {                            // R: new vertex opposite the gate, continue to the left
-                if (sp == 0 || nverts >= maxv) { status = UVOL_ERR_CORRUPT; break; }
-                const int nvx = nverts++;
-                opp[c0] = DINV; opp[c0 + 1] = DINV; opp[c0 + 2] = a; opp[a] = c0 + 2;
-                c2v[c0] = pa; c2v[c0 + 1] = na; c2v[c0 + 2] = nvx;
-                VRec rnew = {c0 + 2, na, 2, 1}; VSTORE(nvx, rnew);
-                rp.lmc = c0; rp.lpv = nvx; rp.val += 1; VSTORE(pa, rp);
-                rn.val += 1; VSTORE(na, rn);
-                a = c0; ta = pa; rt = rp; pa = nvx; rp = rnew;
-            } else if (s == 2) {                            // L
-                if (sp == 0 || nverts >= maxv) { status = UVOL_ERR_CORRUPT; break; }
-                const int nvx = nverts++;
-                opp[c0] = DINV; opp[c0 + 1] = a; opp[c0 + 2] = DINV; opp[a] = c0 + 1;
-                c2v[c0] = na; c2v[c0 + 1] = nvx; c2v[c0 + 2] = pa;
-                VRec rnew = {c0 + 1, na, 2, 1}; VSTORE(nvx, rnew);
-                rp.lmc = c0 + 2; rp.lpv = nvx; rp.val += 1; VSTORE(pa, rp);
-                rn.val += 1; VSTORE(na, rn);
-                a = c0; ta = na; rt = rn; na = nvx; rn = rnew;
-            } else if (s == 4) {                            // E: isolated triangle, pushed on the stack
-                if (nverts + 3 > maxv) { status = UVOL_ERR_CORRUPT; break; }
-                const int v0 = nverts, v1 = nverts + 1, v2 = nverts + 2; nverts += 3;
-                opp[c0] = DINV; opp[c0 + 1] = DINV; opp[c0 + 2] = DINV;
-                c2v[c0] = v0; c2v[c0 + 1] = v1; c2v[c0 + 2] = v2;
-                rt = VRec{c0, v2, 2, 1}; rn = VRec{c0 + 1, v0, 2, 1}; rp = VRec{c0 + 2, v1, 2, 1};
-                VSTORE(v0, rt); VSTORE(v1, rn); VSTORE(v2, rp);
-                if (sp > 0) { if (sp <= 512) stk[sp - 1] = a; else gstk[sp - 1] = a; }
-                sp++; a = c0; ta = v0; na = v1; pa = v2;
-            } else {                                        // S: merge the two topmost components (memory path)
-                if (sp == 0) { status = UVOL_ERR_CORRUPT; break; }
-                const int b = a; sp--;
-                int a2 = -1;
-                for (int k = 0; k < nsa; k++) if (skey[k] == sid) { a2 = sval[k]; sp++; break; }
-                if (a2 < 0) { if (sp == 0) { status = UVOL_ERR_CORRUPT; break; } a2 = sp <= 512 ? stk[sp - 1] : gstk[sp - 1]; }
-                if (a2 == b || opp[a2] >= 0 || opp[b] >= 0) { status = UVOL_ERR_CORRUPT; break; }
-                opp[c0] = DINV; opp[c0 + 2] = a2; opp[a2] = c0 + 2; opp[c0 + 1] = b; opp[b] = c0 + 1;
-                const int vp = c2v[cprev(a2)], vnx = c2v[cnext(a2)], vbp = pa /* = c2v[cprev(b)] */;
-                c2v[c0] = vp; c2v[c0 + 1] = vnx; c2v[c0 + 2] = vbp;
-                { VRec r = VLOAD(vbp); r.lmc = c0 + 2; r.lpv = vnx; VSTORE(vbp, r); }
-                int cn = cnext(b); const int vn = na /* = c2v[cnext(b)] */;
-                VRec rvp = VLOAD(vp); const VRec rvn = VLOAD(vn);
-                rvp.val += rvn.val; rvp.lmc = rvn.lmc; rvp.lpv = rvn.lpv; VSTORE(vp, rvp);
-                const int first = cn; int guard = 0, bad = 0;
-                while (cn >= 0) {
-                    c2v[cn] = vp;
-                    const int cx = cnext(cn), x = c2v[cx];
-                    if (x != vn) { VRec rx = VLOAD(x); if (rx.lmc == cx) { rx.lpv = vp; VSTORE(x, rx); } }
-                    cn = b_swl(opp, cn);
-                    if (cn == first || ++guard > 3 * F) { bad = 1; break; }
-                }
-                if (bad) { status = UVOL_ERR_CORRUPT; break; }
-                { VRec r = rvn; r.lmc = DINV; VSTORE(vn, r); }
-                invalid[ninv++] = vn;
-                a = c0; ta = vp; na = vnx; pa = vbp;
-                rt = VLOAD(ta); rn = VLOAD(na); rp = VLOAD(pa);
-                rn.val += 1; rp.val += 1; VSTORE(na, rn); VSTORE(pa, rp);
-            }
-            { int v = rn.val; v = v < 2 ? 2 : (v > 7 ? 7 : v); ctx = v - 2; }
-            if (s >= 2 && (uint32_t)(nsym - sid - 1) == next_ts) {          // topology split events registered on this symbol (A.3)
-                while (ts_top > 0 && ts[3 * (ts_top - 1)] == (uint32_t)(nsym - sid - 1)) {
-                    --ts_top;
-                    skey[nsa] = nsym - (int)ts[3 * ts_top + 1] - 1;
-                    sval[nsa] = ts[3 * ts_top + 2] == 1 ? cnext(a) : cprev(a);
-                    nsa++;
-                }
-                next_ts = ts_top > 0 ? ts[3 * (ts_top - 1)] : 0xffffffffu;
-            }
-        }
-        if (sp > 0) { if (sp <= 512) stk[sp - 1] = a; else gstk[sp - 1] = a; }
-#undef VLOAD
-#undef VSTORE
-    }
-    __syncwarp();
-    nverts = __shfl_sync(0xffffffffu, nverts, 0); status = __shfl_sync(0xffffffffu, status, 0);
-    // records -> the plain arrays the later kernels read (all lanes)
-    if (!status) for (int v = lane; v < nverts; v += 32) { const uint4 u = vrec[v]; lmc[v] = (int)u.x; hole[v] = (uint8_t)u.w; }
-    __syncwarp();
-    if (lane != 0) return;
-    if (!status) {
-        // start faces (one rABS bit per remaining stack entry), then fold isolated vertices away
-        if (sp > 0) {
-            Rabs sf;
-            if (!rabs_init(sf, blob + f.file_off, f.start_faces)) status = UVOL_ERR_CORRUPT;
-            while (!status && sp > 0) {
-                const int corner = sp <= 512 ? stk[sp - 1] : gstk[sp - 1]; sp--;
-                if (rabs_bit(sf)) {
-                    const int a = corner, vn = c2v[cnext(a)];
-                    if (lmc[vn] < 0) { status = UVOL_ERR_CORRUPT; break; }
-                    const int cb = cnext(lmc[vn]), vx = c2v[cnext(cb)];
-                    if (lmc[vx] < 0) { status = UVOL_ERR_CORRUPT; break; }
-                    const int cc = cnext(lmc[vx]);
-                    if (a == cb || cb == cc || a == cc || opp[a] >= 0 || opp[cb] >= 0 || opp[cc] >= 0 || numf >= F) { status = UVOL_ERR_CORRUPT; break; }
-                    const int vp = c2v[cnext(cc)], nc = 3 * numf++;
-                    opp[nc] = a; opp[a] = nc; opp[nc + 1] = cb; opp[cb] = nc + 1; opp[nc + 2] = cc; opp[cc] = nc + 2;
-                    c2v[nc] = vx; c2v[nc + 1] = vp; c2v[nc + 2] = vn;
-                    hole[vx] = 0; hole[vp] = 0; hole[vn] = 0;
-                }
-            }
-        }
-        if (!status && numf != F) status = UVOL_ERR_CORRUPT;
-        if (!status) {
-            int num_vertices = nverts;
-            for (int k = 0; k < ninv && !status; k++) {
-                const int iv = invalid[k];
-                int src = num_vertices - 1;
-                while (src >= 0 && lmc[src] == DINV) src = --num_vertices - 1;
-                if (src < iv) continue;
-                const int cs = lmc[src]; int c = cs, left = 1, guard = 0;
-                while (c >= 0) {
-                    int nx;
-                    if (left) { nx = b_swl(opp, c); if (nx < 0) { nx = b_swr(opp, cs); left = 0; } else if (nx == cs) nx = DINV; }
-                    else nx = b_swr(opp, c);
-                    if (c2v[c] != src || ++guard > 3 * F) { status = UVOL_ERR_CORRUPT; break; }
-                    c2v[c] = iv; c = nx;
-                }
-                lmc[iv] = lmc[src]; lmc[src] = DINV;
-                hole[iv] = hole[src]; hole[src] = 0;
-                num_vertices--;
-            }
-        }
-    }
-    counts[fi].num_vertex_slots = (uint32_t)nverts; counts[fi].expected[0] = (uint32_t)(nverts - ninv);
-    if (status) frame_fail(counts, fi, status);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Valence-mode edgebreaker, second generation: the whole warp runs the state machine redundantly
+// Valence-mode edgebreaker (the generic k_edgebreaker above remains the path for the standard traversal).  The walk is a
+// serial state machine (the next symbol's context depends on the mesh built so far), so the only lever is the length of the
+// dependent chain per symbol.  The whole warp runs the state machine redundantly
 // (uniform control flow costs nothing extra) so that lanes can specialise where it saves
 // instructions on the serial chain:
 //   * lanes 0..5 each own one context's symbol stream (eight symbols packed in a 64-bit register, the
@@ -1394,7 +1195,6 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         const size_t smMax = smA > smB ? smA : smB;
         if (smMax > 200 * 1024) { ctx->err = "rANS alphabet too large for the shared-memory tables"; return UVOL_ERR_UNSUPPORTED; }
         if (smMax > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_rans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smMax));
-        UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB_RING + 128) * 16)));
         UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB2_RING + 128 + EB2_STAGE) * 16)));
     }
     // ---- phase 1.  The seam-bit runs depend only on the file bytes: they run on the side stream s1
@@ -1416,9 +1216,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     stamp("rans_ctx");
     stamp("rabs_seams(s1)"); i_seams = ev - 2;                                     // (stage slot of rabs_seams: timed on s1, filled in below)
     if (B.any_valence) {
-        static const bool eb_v1 = getenv("UVOL_EB_V1") != nullptr;
-        if (eb_v1) k_edgebreaker_valence<<<nblk(n), 32 * SERIAL_WARPS, (size_t)SERIAL_WARPS * (EB_RING + 128) * 16, st>>>(dF, dC, dBlob, dAux, dS, n);
-        else k_edgebreaker_valence2<<<nblk(n), 32 * SERIAL_WARPS, (size_t)SERIAL_WARPS * (EB2_RING + 128 + EB2_STAGE) * 16, st>>>(dF, dC, dBlob, dAux, dS, n);
+        k_edgebreaker_valence2<<<nblk(n), 32 * SERIAL_WARPS, (size_t)SERIAL_WARPS * (EB2_RING + 128 + EB2_STAGE) * 16, st>>>(dF, dC, dBlob, dAux, dS, n);
         launches++;
     }
     if (B.any_standard) { k_edgebreaker<<<nblk(n), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }

@@ -265,9 +265,12 @@ bool block_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t
         const int modes = src[p++];
         if (modes & 3) return false;
         size_t u;
-        if ((u = seq_table((modes >> 6) & 3, src + p, n - p, fs.seq.ll, fs.seq.have_ll, LL_DEF, 36, 6, 35, 9)) == (size_t)-1) return false; p += u;
-        if ((u = seq_table((modes >> 4) & 3, src + p, n - p, fs.seq.of, fs.seq.have_of, OF_DEF, 29, 5, 31, 8)) == (size_t)-1) return false; p += u;
-        if ((u = seq_table((modes >> 2) & 3, src + p, n - p, fs.seq.ml, fs.seq.have_ml, ML_DEF, 53, 6, 52, 9)) == (size_t)-1) return false; p += u;
+        if ((u = seq_table((modes >> 6) & 3, src + p, n - p, fs.seq.ll, fs.seq.have_ll, LL_DEF, 36, 6, 35, 9)) == (size_t)-1) return false;
+        p += u;
+        if ((u = seq_table((modes >> 4) & 3, src + p, n - p, fs.seq.of, fs.seq.have_of, OF_DEF, 29, 5, 31, 8)) == (size_t)-1) return false;
+        p += u;
+        if ((u = seq_table((modes >> 2) & 3, src + p, n - p, fs.seq.ml, fs.seq.have_ml, ML_DEF, 53, 6, 52, 9)) == (size_t)-1) return false;
+        p += u;
         BackBits b; if (!back_init(b, src + p, n - p)) return false;
         const FseTable &LL = fs.seq.ll, &OF = fs.seq.of, &ML = fs.seq.ml;
         uint32_t sl = (uint32_t)back_read(b, LL.log), so = (uint32_t)back_read(b, OF.log), sm = (uint32_t)back_read(b, ML.log);
