@@ -172,18 +172,56 @@ size_t huf_read_table(const uint8_t *p, size_t n, HufTable &t) {
     if (!huf_build(t, w, nsym)) return 0;
     return used;
 }
-bool huf_decode_stream(const HufTable &t, const uint8_t *p, size_t n, uint8_t *out, size_t count) {
-    BackBits b; if (!back_init(b, p, n)) return false;
-    const int mb = t.maxbits;
-    // window: the next maxbits bits, refilled after every symbol
-    uint32_t state = (uint32_t)back_read(b, mb);
-    for (size_t i = 0; i < count; i++) {
-        const uint16_t e = t.e[state]; const int nb = e & 255;
-        out[i] = (uint8_t)(e >> 8);
-        state = ((state << nb) & ((1u << mb) - 1)) | (uint32_t)back_read(b, nb);
+// Fast backward reader for the Huffman streams: a 64-bit container loaded from the byte pointer, `consumed` counted from its top.
+struct BackFast {
+    const uint8_t *start, *ptr; uint64_t c; unsigned consumed;
+    bool init(const uint8_t *p, size_t n) {
+        if (n == 0 || p[n - 1] == 0) return false;
+        start = p;
+        if (n >= 8) { ptr = p + n - 8; memcpy(&c, ptr, 8); consumed = 8u - (unsigned)highbit(p[n - 1]); }
+        else { ptr = p; c = 0; for (size_t i = 0; i < n; i++) c |= (uint64_t)p[i] << (8 * i); consumed = 8u - (unsigned)highbit(p[n - 1]) + (unsigned)(8 - n) * 8u; }
+        return true;
     }
-    return b.bits == -(int64_t)mb;                                 // every real bit consumed, the window drained to padding
+    inline void reload() {
+        if (ptr - start >= 8) { ptr -= consumed >> 3; consumed &= 7u; memcpy(&c, ptr, 8); }
+        else if (ptr != start) { size_t nb = consumed >> 3; if (nb > (size_t)(ptr - start)) nb = (size_t)(ptr - start); ptr -= nb; consumed -= (unsigned)(8 * nb); memcpy(&c, ptr, 8); }
+    }
+    inline bool roomy() const { return ptr - start >= 8; }         // a reload brings at least 57 unread bits
+    inline bool done() const { return ptr == start && consumed == 64; }
+};
+#define HUF_SYM(B, O) do { const uint16_t e_ = t.e[((B).c << (B).consumed) >> sh]; *(O)++ = (uint8_t)(e_ >> 8); (B).consumed += e_ & 255u; } while (0)
+inline bool huf_tail(const HufTable &t, BackFast &b, uint8_t *o, uint8_t *end) {
+    const unsigned sh = 64u - (unsigned)t.maxbits;
+    while (o < end) {
+        b.reload();
+        if (b.consumed >= 64) return false;                        // symbols left but no bits
+        HUF_SYM(b, o);
+        if (b.consumed > 64) return false;
+    }
+    b.reload();
+    return b.done();
 }
+bool huf_decode_stream(const HufTable &t, const uint8_t *p, size_t n, uint8_t *out, size_t count) {
+    BackFast b; if (!b.init(p, n)) return false;
+    const unsigned sh = 64u - (unsigned)t.maxbits;
+    uint8_t *o = out, *end = out + count;
+    while (end - o >= 5 && b.roomy()) { b.reload(); HUF_SYM(b, o); HUF_SYM(b, o); HUF_SYM(b, o); HUF_SYM(b, o); HUF_SYM(b, o); }      // 5 x 11 bits <= 57
+    return huf_tail(t, b, o, end);
+}
+// Four streams in lock step: four independent dependency chains keep the core busy.
+bool huf_decode_4(const HufTable &t, const uint8_t *const p[4], const size_t n[4], uint8_t *const out[4], const size_t count[4]) {
+    BackFast b0, b1, b2, b3;
+    if (!b0.init(p[0], n[0]) || !b1.init(p[1], n[1]) || !b2.init(p[2], n[2]) || !b3.init(p[3], n[3])) return false;
+    const unsigned sh = 64u - (unsigned)t.maxbits;
+    uint8_t *o0 = out[0], *o1 = out[1], *o2 = out[2], *o3 = out[3];
+    uint8_t *e0 = o0 + count[0], *e1 = o1 + count[1], *e2 = o2 + count[2], *e3 = o3 + count[3];
+    while (e0 - o0 >= 5 && e1 - o1 >= 5 && e2 - o2 >= 5 && e3 - o3 >= 5 && b0.roomy() && b1.roomy() && b2.roomy() && b3.roomy()) {
+        b0.reload(); b1.reload(); b2.reload(); b3.reload();
+        for (int k = 0; k < 5; k++) { HUF_SYM(b0, o0); HUF_SYM(b1, o1); HUF_SYM(b2, o2); HUF_SYM(b3, o3); }
+    }
+    return huf_tail(t, b0, o0, e0) && huf_tail(t, b1, o1, e1) && huf_tail(t, b2, o2, e2) && huf_tail(t, b3, o3, e3);
+}
+#undef HUF_SYM
 
 // ---- sequences
 const int16_t LL_DEF[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
@@ -243,8 +281,9 @@ bool block_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t
             const size_t s4 = cn - 6 - s1 - s2 - s3, q = (regen + 3) / 4;
             if (3 * q > regen) return false;
             const uint8_t *b = c + 6;
-            if (!huf_decode_stream(fs.huf, b, s1, lit_buf, q) || !huf_decode_stream(fs.huf, b + s1, s2, lit_buf + q, q) ||
-                !huf_decode_stream(fs.huf, b + s1 + s2, s3, lit_buf + 2 * q, q) || !huf_decode_stream(fs.huf, b + s1 + s2 + s3, s4, lit_buf + 3 * q, regen - 3 * q)) return false;
+            const uint8_t *const sp[4] = {b, b + s1, b + s1 + s2, b + s1 + s2 + s3}; const size_t sn[4] = {s1, s2, s3, s4};
+            uint8_t *const so[4] = {lit_buf, lit_buf + q, lit_buf + 2 * q, lit_buf + 3 * q}; const size_t sc[4] = {q, q, q, regen - 3 * q};
+            if (!huf_decode_4(fs.huf, sp, sn, so, sc)) return false;
         }
         lit = lit_buf; p += csize;
     }
