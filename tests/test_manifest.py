@@ -188,3 +188,30 @@ def test_playback_buffer_follows_the_reference_scheduler():
     assert all(tex == (seg != 9) for _, seg, _, tex in shown)                # segment 9 missing -> failMaterial (:439-444)
     assert sorted(asked_g) == list(range(250)) and sorted(asked_s) == list(range(50))      # each requested exactly once
     assert pb.process_frame(250 / 30.0 + 0.1) is None                        # past the last frame: track end
+
+
+def test_manifest_tooling_both_dialects(tmp_path):
+    """the player's schema and the encoder script's dialect describe the same clip; the frame-count check follows
+    scripts/Encoder.py:103-154; the V1 writer follows Encoder30.js:155-160 and round-trips through V1Manifest."""
+    import struct
+    enc = man.emit_v2("DRACO/frame_[#####].drc", 30, 250, "KTX2/texture_[#######].ktx2", 30, 7, 36, dialect="encoder")
+    assert isinstance(enc["texture"]["targets"], list) and "targets" not in enc["geometry"]          # exactly what Encoder.py writes
+    ply = man.emit_v2("DRACO/frame_[#####].drc", 30, 250, "KTX2/texture_[#######].ktx2", 30, 7, 36, dialect="player", resolution=(1024, 1024))
+    a, b = man.V2Manifest(enc, "/clips/a/manifest.json"), man.V2Manifest(ply, "/clips/a/manifest.json")
+    for m in (a, b):
+        assert (m.geometry_frame_count, m.batch_size, m.texture_segment_count) == (250, 7, 36)
+        assert m.geometry_url(12) == "/clips/a/DRACO/frame_00012.drc" and m.texture_url(3) == "/clips/a/KTX2/texture_0000003.ktx2"
+        assert m.frames_at(1.0) == {"geometry_frame": 30, "texture_frame": 30, "segment": 4, "layer": 2}
+    ktx = lambda layers: b"\xabKTX 20\xbb\r\n\x1a\n" + struct.pack("<IIIIIIIII", 0, 1, 64, 64, 0, layers, 1, 1, 0)
+    segs = [ktx(7)] * 35 + [ktx(5)]                                                                   # 35 full segments + a short last one = 250 frames
+    ok = man.check_total_frames(250, 30, segs, 7, 30)
+    assert ok["compatible"] and ok["texture_frames"] == 250 and ok["durations"]["geometry"] == pytest.approx(250 / 30)
+    assert not man.check_total_frames(250, 30, [ktx(7)] * 36, 7, 30)["compatible"]                   # 252 texture frames for 250 meshes
+    assert man.check_total_frames(250, 30, [ktx(7)] * 17 + [ktx(6)], 7, 15)["compatible"]            # half-rate texture: 125 frames at 15 fps
+    with pytest.raises(ValueError):
+        man.ktx2_layer_count(b"not a ktx2 file at all, really not............")
+    v1 = man.emit_v1(30, [(100, 196, 1500), (101, 198, 1520), (99, 194, 1480)])
+    p = tmp_path / "clip.manifest"; p.write_text(json.dumps(v1))
+    m1 = man.V1Manifest.load(str(p))
+    assert v1["maxVertices"] == 101 and v1["maxTriangles"] == 198 and v1["frameData"][2]["startBytePosition"] == 3020
+    assert m1.byte_range(1, 2) == (1500, 3020) and m1.byte_range(1, 3) == (1500, 4500)      # [start, end) frames

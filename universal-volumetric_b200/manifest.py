@@ -53,6 +53,7 @@ class V2Manifest:
     def __init__(self, manifest, manifest_path):
         if manifest.get("version") != "v2":
             raise ValueError("not a V2 manifest (src/Player.ts:127-132 dispatches on version == 'v2')")
+        manifest = normalize_v2(manifest)              # accepts the encoder script's dialect too (scripts/Encoder.py:311-328)
         self.m, self.path = manifest, manifest_path
         # playTrack: first geometry target; texture targets sorted by TEXTURE_FORMAT_PRIORITY, first supported one
         # (isTextureFormatSupported: 'ktx2' always, src/utils.ts:26-32); note the reference compares the target KEY
@@ -260,3 +261,79 @@ class V2Playback:
         s_keep = math.ceil(120 / (self.man.texture["frameRate"] * self.man.batch_size))
         self.remove_played_buffer(at["geometry_frame"] - g_keep, at["segment"] - s_keep)
         return shown
+
+
+# ---- manifest tooling: the two V2 dialects, the V1 writer, the encoder's frame-count check -----------------
+def normalize_v2(manifest):
+    """The reference has TWO V2 dialects: the player's schema (src/Interfaces.ts:75-132: `geometry.targets{name: {...}}`, one
+    `geometry.path` template with [target] / [ext] / [####] tags, `texture.targets{name: {...}}`) and what its encoder script
+    writes (scripts/Encoder.py:311-328: a flat `geometry{format, frameRate, frameCount, path}` and `texture.targets[ {...,
+    path} ]` as a LIST, paths with [####] only).  Returns the player's schema for either input (a copy)."""
+    m = json.loads(json.dumps(manifest))
+    if m.get("version") != "v2":
+        raise ValueError("not a V2 manifest")
+    g = m["geometry"]
+    if "targets" not in g:                                   # encoder dialect
+        g = {"targets": {g["format"]: {"format": g["format"], "frameRate": g["frameRate"], "frameCount": g["frameCount"]}}, "path": g["path"]}
+        m["geometry"] = g
+    t = m["texture"]
+    if isinstance(t.get("targets"), list):
+        targets, path = {}, None
+        for i, e in enumerate(t["targets"]):
+            e = dict(e); p = e.pop("path", None); path = path or p
+            e.setdefault("type", V2Manifest.texture_type); e.setdefault("tag", V2Manifest.texture_tag)
+            targets[e["format"] if e["format"] not in targets else "%s-%d" % (e["format"], i)] = e
+        m["texture"] = {"targets": targets, "path": path if path is not None else t.get("path")}
+    return m
+
+
+def emit_v2(geometry_path, geometry_frame_rate, geometry_frame_count, texture_path, texture_frame_rate, sequence_size, sequence_count,
+            dialect="player", resolution=None, audio=None):
+    """A V2 manifest dict in the player's schema (dialect="player") or exactly as scripts/Encoder.py:311-328 writes it
+    (dialect="encoder").  Paths are templates relative to the manifest ([#####] = zero-padded index)."""
+    if dialect == "encoder":
+        m = {"version": "v2", "geometry": {"format": "draco", "frameRate": geometry_frame_rate, "frameCount": geometry_frame_count, "path": geometry_path},
+             "texture": {"targets": [{"format": "ktx2", "frameRate": texture_frame_rate, "sequenceCount": sequence_count, "sequenceSize": sequence_size, "path": texture_path}]}}
+    elif dialect == "player":
+        tex = {"format": "ktx2", "type": V2Manifest.texture_type, "tag": V2Manifest.texture_tag, "sequenceSize": sequence_size, "sequenceCount": sequence_count, "frameRate": texture_frame_rate}
+        if resolution:
+            tex["resolution"] = list(resolution)
+        m = {"version": "v2", "geometry": {"targets": {"draco": {"format": "draco", "frameRate": geometry_frame_rate, "frameCount": geometry_frame_count}}, "path": geometry_path},
+             "texture": {"targets": {"ktx2": tex}, "path": texture_path}}
+    else:
+        raise ValueError("dialect must be 'player' or 'encoder'")
+    if audio:
+        m["audio"] = dict(audio)
+    return m
+
+
+def ktx2_layer_count(blob):
+    """layerCount of a KTX2 file (bytes 32..36 of the header), as scripts/Encoder.py:128-131 reads it."""
+    import struct
+    if len(blob) < 36 or blob[:12] != b"\xabKTX 20\xbb\r\n\x1a\n":
+        raise ValueError("not a KTX2 file")
+    return struct.unpack_from("<I", blob, 32)[0]
+
+
+def check_total_frames(geometry_frame_count, geometry_frame_rate, texture_segments, sequence_size, texture_frame_rate, read=None):
+    """scripts/Encoder.py:103-154: texture frames = (segments - 1) * sequenceSize + layerCount of the LAST segment (it may be short);
+    compatible iff geometry_frames * texture_fps == texture_frames * geometry_fps.  `texture_segments` = paths (or blobs when
+    `read` is None and items are bytes).  Returns {"compatible", "geometry_frames", "texture_frames", "durations"}."""
+    if not texture_segments:
+        raise ValueError("no texture segments")
+    last = texture_segments[-1]
+    blob = last if isinstance(last, (bytes, bytearray)) else (read(last) if read else open(last, "rb").read())
+    tex_frames = (len(texture_segments) - 1) * sequence_size + max(1, ktx2_layer_count(blob))
+    return {"compatible": geometry_frame_count * texture_frame_rate == tex_frames * geometry_frame_rate,
+            "geometry_frames": geometry_frame_count, "texture_frames": tex_frames,
+            "durations": {"geometry": geometry_frame_count / geometry_frame_rate, "texture": tex_frames / texture_frame_rate}}
+
+
+def emit_v1(frame_rate, frames):
+    """The V1 `.manifest` next to a `.drcs` (deprecated/encoder/src/Encoder30.js:155-160; schema src/Interfaces.ts:1-15).
+    `frames` = [(vertices, faces, crt_byte_length)] in file order; every frame is a keyframe of itself, as the encoder writes."""
+    pos, data, maxv, maxf = 0, [], 0, 0
+    for i, (nv, nf, nbytes) in enumerate(frames):
+        data.append({"frameNumber": i, "keyframeNumber": i, "startBytePosition": pos, "vertices": nv, "faces": nf, "meshLength": nbytes})
+        pos += nbytes; maxv = max(maxv, nv); maxf = max(maxf, nf)
+    return {"frameRate": frame_rate, "maxVertices": maxv, "maxTriangles": maxf, "frameData": data}
