@@ -40,7 +40,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "decoded frames/sec (geom+tex)"
+def _metric():
+    """BASELINE.json's metric string (quoted on the 200k-vert / 2048^2 sequence = the default workload c3)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    except Exception:
+        return "decoded frames/sec (geom+tex) on 200k-vert/2048\u00b2 seq; Mverts/s + Mtexels/s"
+
+
+METRIC = _metric()
 WORKLOADS = {
     # window_segments: segments decoded per library call (None = the whole sequence at once); distinct_*: how many distinct
     # frames / segments are actually encoded by the generator (the rest cycle through them) to bound generation time.
