@@ -360,7 +360,7 @@ static int ktx2_run(uvol_ctx *ctx, int memory, uvol_texture *out, bool fresh_upl
 
 extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target_format, int memory, uvol_texture *out) {
     if (!ctx || !out || n < 0 || (n > 0 && (!data || !size)) || n >= (1 << 19)) return UVOL_ERR_ARG;
-    if (target_format != UVOL_TEX_RGBA32) { ctx->err = "only UVOL_TEX_RGBA32 is implemented"; return UVOL_ERR_UNSUPPORTED; }
+    if (target_format != UVOL_TEX_RGBA32) { ctx->set_error("only UVOL_TEX_RGBA32 is implemented"); return UVOL_ERR_UNSUPPORTED; }
     UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->stats, 0, sizeof ctx->stats);
     if (n == 0) { if (ctx->tex) ctx->tex->n = 0; return UVOL_OK; }

@@ -1193,7 +1193,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     {
         const size_t smA = rans_smem(B.max_alpha_ctx), smB = rans_smem(B.max_alpha_attr);
         const size_t smMax = smA > smB ? smA : smB;
-        if (smMax > 200 * 1024) { ctx->err = "rANS alphabet too large for the shared-memory tables"; return UVOL_ERR_UNSUPPORTED; }
+        if (smMax > 200 * 1024) { ctx->set_error("rANS alphabet too large for the shared-memory tables"); return UVOL_ERR_UNSUPPORTED; }
         if (smMax > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_rans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smMax));
         UVOL_CUDA(ctx, cudaFuncSetAttribute(k_edgebreaker_valence2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SERIAL_WARPS * (EB2_RING + 128 + EB2_STAGE) * 16)));
     }
@@ -1278,7 +1278,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
         stamp("corner_records");
         const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((maxN + 31) / 32 + 4) & ~3u);
         const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_STACK * 4) * TRAV_WARPS;
-        if (maxN >= (1u << 26)) { ctx->err = "mesh too large for the traversal records"; return UVOL_ERR_UNSUPPORTED; }
+        if (maxN >= (1u << 26)) { ctx->set_error("mesh too large for the traversal records"); return UVOL_ERR_UNSUPPORTED; }
         // mode 0: both bitmaps in shared memory -- fastest while the walks of the batch need at most ~3 waves of the SMs' shared memory;
         // mode 1: byte map + vertex -> entry map in global memory, every walk resident at once (measured at C3: 504 frames = 1512 walks of
         // 77 KB: 211 ms in mode 0, 146 ms in mode 1; 252 frames: 130 vs 140 ms); mode 2 (faces in shared memory only) never wins, kept for experiments.

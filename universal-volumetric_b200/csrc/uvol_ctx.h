@@ -57,7 +57,8 @@ struct uvol_ctx {
     cudaEvent_t ev[32] = {}, aux_ev[8] = {}, tex_ev[8] = {}, sync_ev[8] = {};
     cudaStream_t s2 = nullptr;
     cudaStream_t s3 = nullptr;                    // early result copies (index buffers) next to the geometry kernels
-    std::string err;
+    std::string err; std::mutex err_mu;           // the texture side of uvol_decode_v2_batch runs on a helper thread: error text is set under err_mu
+    void set_error(const char *msg) { std::lock_guard<std::mutex> g(err_mu); err = msg; }
     // geometry path
     Phase2Arena own_p2; Phase2Arena *p2 = &own_p2;
     PinBuf h_blob, h_desc, h_aux, h_counts, h_out;
@@ -79,7 +80,7 @@ struct uvol_ctx {
 };
 
 #define UVOL_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
-    char b_[256]; snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); (ctx)->err = b_; return UVOL_ERR_CUDA; } } while (0)
+    char b_[256]; snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); (ctx)->set_error(b_); return UVOL_ERR_CUDA; } } while (0)
 
 // Host threads used to stage a large batch into the pinned input blob: UVOL_STAGING_THREADS, else min(8, cores / 2).  A launcher that
 // runs one process per GPU divides the cores between its ranks through the variable.
