@@ -460,20 +460,47 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence2(cons
     if (status) frame_fail(counts, fi, status);
 }
 
-// Attribute seams: one CTA per frame.  The k-th bit of each seam stream belongs to the k-th corner
-// (in corner order) whose opposite face is not older than its own; a ballot-based block scan turns
-// that into a parallel lookup.
+// Attribute seams.  The k-th bit of each seam stream belongs to the k-th corner (in corner order) whose opposite face is not
+// older than its own, so a corner needs the number of such corners before it: k_seam_count totals them per chunk of
+// SEAM_CHUNK corners, k_seams adds up the chunks before its own (at most a few hundred) and runs a ballot-based block
+// scan inside the chunk.  grid = (ceil(3 * maxF / SEAM_CHUNK), frames), 256 threads.
+#define SEAM_CHUNK 8192
+__global__ void __launch_bounds__(256) k_seam_count(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S) {
+    __shared__ int warp_tot[8];
+    const uint32_t fi = blockIdx.y;
+    if (frame_dead(frames, counts, fi)) return;
+    const DracoFrame &f = frames[fi];
+    const int C = 3 * (int)f.nf, base = (int)blockIdx.x * SEAM_CHUNK, tid = threadIdx.x;
+    if (f.nad == 0 || base >= C) return;
+    const int *opp = (const int *)(S + f.o_opp);
+    int mine = 0;
+    for (int c = base + tid; c < min(C, base + SEAM_CHUNK); c += 256) { const int o = opp[c]; mine += (o >= 0 && o / 3 >= c / 3); }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
+    if ((tid & 31) == 0) warp_tot[tid >> 5] = mine;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int k = 0; k < 8; k++) t += warp_tot[k]; ((int *)(S + f.o_seamcnt))[blockIdx.x] = t; }
+}
 __global__ void __launch_bounds__(256) k_seams(const DracoFrame *frames, DracoCounts *counts, uint8_t *S, uint8_t *Z, int nframes) {
     __shared__ int warp_tot[8]; __shared__ int carry;
-    const uint32_t fi = blockIdx.x;
+    const uint32_t fi = blockIdx.y;
     if (frame_dead(frames, counts, fi)) return;
     const DracoFrame &f = frames[fi];
     const int C = 3 * (int)f.nf, nad = (int)f.nad, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (nad == 0) return;
+    const int chunk0 = (int)blockIdx.x * SEAM_CHUNK;
+    if (nad == 0 || chunk0 >= C) return;
     const int *opp = (const int *)(S + f.o_opp), *c2v = (const int *)(S + f.o_c2v);
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < C; base += 256) {
+    {   // flagged corners in the chunks before this one
+        const int *cnt = (const int *)(S + f.o_seamcnt); int mine = 0;
+        for (int k = tid; k < (int)blockIdx.x; k += 256) mine += cnt[k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
+        if (lane == 0) warp_tot[w] = mine;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int k = 0; k < 8; k++) t += warp_tot[k]; carry = t; }
+        __syncthreads();
+    }
+    for (int base = chunk0; base < min(C, chunk0 + SEAM_CHUNK); base += 256) {
         const int c = base + tid; int o = -2, flag = 0;
         if (c < C) { o = opp[c]; flag = (o >= 0 && o / 3 >= c / 3); }
         const unsigned bal = __ballot_sync(0xffffffffu, flag);
@@ -1222,7 +1249,10 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     if (B.any_standard) { k_edgebreaker<<<nblk(n), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
     stamp("edgebreaker");
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[1], 0));
-    k_seams<<<n, 256, 0, st>>>(dF, dC, dS, dZ, n); launches++;
+    if (B.maxnad) {
+        const dim3 sg((3 * B.maxF + SEAM_CHUNK - 1) / SEAM_CHUNK, (unsigned)n);
+        k_seam_count<<<sg, 256, 0, st>>>(dF, dC, dS); k_seams<<<sg, 256, 0, st>>>(dF, dC, dS, dZ, n); launches += 2;
+    }
     stamp("seams");
     const unsigned gv = (B.maxV + 127) / 128 > 0 ? (B.maxV + 127) / 128 : 1;
     if (B.maxnad) {

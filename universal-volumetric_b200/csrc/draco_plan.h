@@ -30,6 +30,7 @@ static inline void draco_plan_phase1(std::vector<DracoFrame> &frames, DracoPlan 
             f.o_afirst[i] = plan_take(s, maxv * 4);        // first corner of each vertex fan
             f.o_eos[i] = plan_take(z, C); f.o_vos[i] = plan_take(z, maxv);
         }
+        f.o_seamcnt = plan_take(s, (C / 8192 + 2) * 4);      // SEAM_CHUNK corners per count
         f.o_pcnt = plan_take(s, (maxv + 1) * 4);
         f.o_pfirst = plan_take(s, maxv * 4);               // dedup start corner per vertex
         for (int j = 0; j < f.nattr; j++) {                // early attribute symbol runs: capacity from the largest possible entry count

@@ -54,6 +54,7 @@ struct DracoFrame {
     uint64_t o_opp, o_c2v, o_lmc, o_hole, o_val, o_stack, o_ctxsym[6], o_invalid;
     uint64_t o_seambits[UVOL_MAX_ATTR_DATA], o_eos[UVOL_MAX_ATTR_DATA], o_vos[UVOL_MAX_ATTR_DATA], o_ac2v[UVOL_MAX_ATTR_DATA],
              o_afirst[UVOL_MAX_ATTR_DATA], o_acnt[UVOL_MAX_ATTR_DATA];
+    uint64_t o_seamcnt;                    // per chunk of corners: how many carry a seam bit (k_seam_count)
     uint64_t o_pcnt, o_pfirst, o_p2c;      // per-vertex point counts/offsets, dedup start corner, point -> corner
     uint64_t o_d2c[UVOL_MAX_ATTR_DATA + 1], o_v2d[UVOL_MAX_ATTR_DATA + 1], o_frec[UVOL_MAX_ATTR_DATA + 1], o_tstack[UVOL_MAX_ATTR_DATA + 1], o_fvis[UVOL_MAX_ATTR_DATA + 1];
     uint64_t o_corr[UVOL_MAX_ATTRS], o_val_attr[UVOL_MAX_ATTRS], o_par[UVOL_MAX_ATTRS], o_auxbits[UVOL_MAX_ATTRS];
