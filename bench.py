@@ -451,8 +451,9 @@ def main():
         barrier(); e0.record()
         tables, arenas = uv.gather.all_gather_geometry(g, ng, f"cuda:{local}")
         e1.record(); torch.cuda.synchronize()
-        _, base, nbytes = uv.gather.geometry_table(g, ng)
-        same = bool(torch.equal(arenas[rank][:nbytes], uv.gather.arena_tensor(base, nbytes, f"cuda:{local}")))
+        _, runs = uv.gather.geometry_table(g, ng)
+        mine = uv.gather.pack_runs(runs, f"cuda:{local}"); nbytes = int(mine.numel())
+        same = bool(torch.equal(arenas[rank][:nbytes], mine))
         sums = arenas[:, : arenas.shape[1] // 8 * 8].view(torch.int64).sum(dim=1)                 # every rank must hold identical copies
         lo, hi = sums.clone(), sums.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)

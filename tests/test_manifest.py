@@ -106,19 +106,27 @@ class _G:        # stands in for uvol_geometry: pointers into one host arena
 
 
 def _fake_results(rank, nframes):
-    """A rank's 'decoded' frames laid out in one host arena like the library's output arena (128-byte aligned arrays)."""
+    """A rank's 'decoded' frames laid out like the library's output arena: all index buffers first, then (after the index buffers of
+    frames that are NOT gathered, here a 256 KB hole) the per-point arrays, every array 128-byte aligned."""
     import ctypes
     import numpy as np
     rng = np.random.default_rng(100 + rank)
     sizes = [(50 + 7 * i + rank, 90 + 11 * i) for i in range(nframes)]                  # (points, faces)
-    total = sum(((F * 12 + 127) // 128 + (P * 12 + 127) // 128 * 2 + (P * 8 + 127) // 128) * 128 for P, F in sizes)
-    arena = np.zeros(total, np.uint8); base = arena.ctypes.data; cur = 0; res = []; truth = []
-    for P, F in sizes:
+    al = lambda n: (n + 127) // 128 * 128
+    total = sum(al(F * 12) + 2 * al(P * 12) + al(P * 8) for P, F in sizes) + (256 << 10)
+    arena = np.zeros(total, np.uint8); base = arena.ctypes.data; res = []; truth = []
+    cur = 0; slots = []
+    for P, F in sizes:                                                                  # index region
+        slots.append({"index": cur}); cur += al(F * 12)
+    cur += 256 << 10                                                                    # index buffers of other frames
+    for (P, F), sl in zip(sizes, slots):                                                # attribute region
+        for name, nbytes in (("position", P * 12), ("normal", P * 12), ("uv", P * 8)):
+            sl[name] = cur; cur += al(nbytes)
+    for (P, F), sl in zip(sizes, slots):
         g = _G(); g.status = 0; g.num_points = P; g.num_faces = F; t = {}
         for name, n, dt in (("index", F * 3, np.int32), ("position", P * 3, np.float32), ("normal", P * 3, np.float32), ("uv", P * 2, np.float32)):
             vals = (rng.integers(0, P, n) if dt == np.int32 else rng.random(n)).astype(dt)
-            arena[cur:cur + 4 * n] = vals.view(np.uint8); setattr(g, name, ctypes.c_void_p(base + cur)); t[name] = vals
-            cur = (cur + 4 * n + 127) // 128 * 128
+            arena[sl[name]:sl[name] + 4 * n] = vals.view(np.uint8); setattr(g, name, ctypes.c_void_p(base + sl[name])); t[name] = vals
         res.append(g); truth.append(t)
     bad = _G(); bad.status = -2; bad.num_points = bad.num_faces = 0
     bad.index = bad.position = bad.normal = bad.uv = None
@@ -143,6 +151,7 @@ def _gather_worker(rank, world, port, q):
                 ok &= v is None
             else:
                 ok &= all(np.array_equal(v[k].numpy().ravel(), t[k]) for k in t)
+    ok &= int(arenas.shape[1]) < (128 << 10)                                          # the 256 KB hole between the two runs does not travel
     q.put((rank, bool(ok), tuple(tables.shape)))
     dist.destroy_process_group()
 

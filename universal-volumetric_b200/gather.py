@@ -3,7 +3,7 @@
 The decode itself never communicates: geometry frames and KTX2 segments are independent units, rank r decodes its own
 contiguous shard (manifest.shard_v2).  Only when the caller wants EVERY frame on EVERY rank (one renderer process fed by
 all GPUs) are the decoded buffers exchanged -- one all_gather of a small per-frame table (status, counts, byte offsets
-inside the rank's output arena) and one all_gather of the arenas themselves, padded to the largest rank.  With the NCCL
+inside the rank's output arena) and one all_gather of the frames' bytes (contiguous runs of the output arena packed back to back), padded to the largest rank.  With the NCCL
 backend the arenas are the library's device buffers (no host staging; NVLink / NVSwitch carries the payload); the same
 code runs on CPU tensors under gloo for the tests.  `torch.distributed` is plumbing here, not the product.
 """
@@ -25,8 +25,11 @@ def _addr(p):
     return ctypes.cast(p, ctypes.c_void_p).value or 0
 
 
-def geometry_table(raw, n):
-    """(table int64[n, COLS], base address, arena bytes) of the first n results of a *_batch call (device or host pointers)."""
+def geometry_table(raw, n, gap=1 << 16):
+    """(table int64[n, COLS], runs) of the first n results of a *_batch call (device or host pointers).  The arrays of those frames
+    are grouped into contiguous RUNS of the library's output arena (the arena holds all index buffers first, then the per-point
+    arrays, so a prefix of the frames is two runs); `runs` = [(address, bytes)], and the table's offsets are relative to the
+    runs packed back to back -- only the bytes of the selected frames travel."""
     t = np.full((n, COLS), -1, np.int64)
     spans = []
     for i in range(n):
@@ -41,13 +44,38 @@ def geometry_table(raw, n):
                 t[i, col] = a
                 spans.append((a, a + nbytes))
     if not spans:
-        return t, 0, 0
-    base = min(s for s, _ in spans); end = max(e for _, e in spans)
+        return t, []
+    spans.sort()
+    runs = [list(spans[0])]
+    for a, e in spans[1:]:
+        if a <= runs[-1][1] + gap:
+            runs[-1][1] = max(runs[-1][1], e)
+        else:
+            runs.append([a, e])
+    packed, starts = 0, []
+    for a, e in runs:
+        starts.append((a, e, packed)); packed += (e - a + 127) // 128 * 128
     for col in range(3, 7):
-        m = t[:, col] >= 0
-        t[m, col] -= base
-    t[:, 7] = end - base
-    return t, base, end - base
+        for i in range(n):
+            a = t[i, col]
+            if a >= 0:
+                for ra, re_, off in starts:
+                    if ra <= a < re_:
+                        t[i, col] = a - ra + off
+                        break
+    t[:, 7] = packed
+    return t, [(a, e - a) for a, e in runs]
+
+
+def pack_runs(runs, device):
+    """One contiguous uint8 tensor holding the runs back to back (128-byte aligned), copied on `device`."""
+    import torch
+    total = sum((nb + 127) // 128 * 128 for _, nb in runs)
+    out = torch.zeros(total, dtype=torch.uint8, device=device)
+    off = 0
+    for a, nb in runs:
+        out[off:off + nb] = arena_tensor(a, nb, device); off += (nb + 127) // 128 * 128
+    return out
 
 
 def arena_tensor(base, nbytes, device):
@@ -66,7 +94,8 @@ def all_gather_geometry(raw, n, device, group=None):
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    table, base, nbytes = geometry_table(raw, n)
+    table, runs = geometry_table(raw, n)
+    mine_packed = pack_runs(runs, device); nbytes = int(mine_packed.numel())
     sizes = torch.tensor([n, nbytes], dtype=torch.int64, device=device)
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes, group=group)
@@ -77,7 +106,7 @@ def all_gather_geometry(raw, n, device, group=None):
         dist.all_gather(list(tables.unbind(0)), tpad, group=group)
     mine = torch.zeros(max_b, dtype=torch.uint8, device=device)
     if nbytes:
-        mine[:nbytes] = arena_tensor(base, nbytes, device)
+        mine[:nbytes] = mine_packed
     arenas = torch.empty((world, max_b), dtype=torch.uint8, device=device)
     if torch.device(device).type == "cuda":
         dist.all_gather_into_tensor(arenas, mine, group=group)
