@@ -5,6 +5,9 @@
 #include <vector>
 #include "../../universal-volumetric_b200/csrc/uvol_internal.h"
 #include "../../universal-volumetric_b200/csrc/basis_core.h"
+#include "../../universal-volumetric_b200/csrc/uastc_core.h"
+
+extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
 
 int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
 
@@ -13,7 +16,28 @@ extern "C" int basis_emu_decode(const uint8_t *data, size_t len, uint8_t **rgba,
     const uint8_t *file = padded.data();
     Ktx2File f; memset(&f, 0, sizeof f); std::vector<Ktx2Slice> slices;
     int rc = uvol_ktx2_parse(file, len, 0, f, slices); if (rc) return rc;
-    if (f.is_uastc) return UVOL_ERR_UNSUPPORTED;
+    if (f.is_uastc) {          // the kernel's per-block function (uastc_core.h) over every block, Zstd levels inflated by the product's decoder
+        const uint32_t nblk = f.bx * f.by;
+        std::vector<uint8_t> inflated; const uint8_t *level = file + f.level_off;
+        if (f.zstd) {
+            inflated.resize(f.z_len); size_t got = 0;
+            rc = uvol_zstd_inflate(file + f.z_src_off, f.z_src_len, inflated.data(), inflated.size(), &got);
+            if (rc || got != f.z_len) return rc ? rc : UVOL_ERR_CORRUPT;
+            level = inflated.data();
+        }
+        UastcShared T; uastc_fill_tables(T);
+        uint8_t *out = (uint8_t *)malloc((size_t)f.layers * f.width * f.height * 4 + 16);
+        for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
+            uint32_t w[4]; memcpy(w, level + ((size_t)L * nblk + bi) * 16, 16);
+            uint32_t rows[4][4];
+            if (!uastc_block(T, w[0], w[1], w[2], w[3], rows)) { free(out); return UVOL_ERR_CORRUPT; }
+            const uint32_t xb = bi % f.bx, yb = bi / f.bx;
+            for (uint32_t y = 0; y < 4 && yb * 4 + y < f.height; y++) for (uint32_t x = 0; x < 4 && xb * 4 + x < f.width; x++)
+                memcpy(out + (((size_t)L * f.height + yb * 4 + y) * f.width + xb * 4 + x) * 4, &rows[y][x], 4);
+        }
+        *rgba = out; *w = f.width; *h = f.height; *layers = f.layers;
+        return UVOL_OK;
+    }
     const uint32_t pool_cap = f.endpoint_count + f.selector_count + 8192 + 1024, nblk = f.bx * f.by;
     std::vector<uint32_t> eps(f.endpoint_count), sels(f.selector_count); std::vector<HuffTable> tabs(10);
     std::vector<uint16_t> pool(pool_cap + 16384 + 64);
