@@ -66,3 +66,27 @@ def test_reference_c_abi(uv):
     assert rc == e["nface"]
     assert (d(idx.view(np.uint32)), d(pos), d(uvs)) == (e["index"], e["position"], e["uv"])
     assert not L.CreateDecoder(16, b"\0" * 16, info)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not corto_bind.available(), reason="oracle/_ref/libcorto_ref.so not staged")
+def test_v1_sequence_from_disk(uv, ctx, tmp_path):
+    """A V1 clip on disk (`.manifest` + `.drcs` as deprecated/encoder/src/Encoder30.js writes them, frames encoded by the reference's own
+    encoder) decoded through V1Sequence: per keyframe the worker's bufferGeometry, bit-exact against the reference decoder."""
+    import json
+    rings, segs = synth.sphere_dims(3000); fp, fu, uvs, nv = synth.sphere_topology(rings, segs)
+    enc = []
+    for i in range(5):
+        pos = synth.sphere_frame(rings, segs, i / 30.0, 33)
+        uvv = np.stack([np.arctan2(pos[:, 2], pos[:, 0]) / (2 * np.pi) + 0.5, pos[:, 1] / 2000.0 + 0.5], 1).astype(np.float32)
+        enc.append(corto_bind.ref_encode(pos, uvv, fp, 12, 12))
+    (tmp_path / "clip.drcs").write_bytes(b"".join(b for b, _, _ in enc))
+    (tmp_path / "clip.manifest").write_text(json.dumps(uv.emit_v1(30, [(ev, ef, len(b)) for b, ev, ef in enc])))
+    out = uv.V1Sequence(str(tmp_path / "clip.manifest"), uv.CortoDecoder(ctx)).decode(1, 5)
+    assert sorted(out) == [1, 2, 3, 4]
+    for k, r in out.items():
+        b, ev, ef = enc[k]
+        idx, p, u = corto_bind.ref_decode(b, ev, ef)
+        g = r["bufferGeometry"]
+        assert r["frameNumber"] == k and np.array_equal(g["index"], idx)
+        assert np.array_equal(g["position"].view(np.uint32), p.view(np.uint32)) and np.array_equal(g["uv"].view(np.uint32), u.view(np.uint32))

@@ -224,3 +224,25 @@ def test_manifest_tooling_both_dialects(tmp_path):
     m1 = man.V1Manifest.load(str(p))
     assert v1["maxVertices"] == 101 and v1["maxTriangles"] == 198 and v1["frameData"][2]["startBytePosition"] == 3020
     assert m1.byte_range(1, 2) == (1500, 3020) and m1.byte_range(1, 3) == (1500, 4500)      # [start, end) frames
+
+
+def test_v1_sequence_slices_and_keys(tmp_path):
+    """V1Sequence (src/V1/worker.ts:24-74) with a stub decoder: one range read, per-frame slices in file order, results keyed by
+    keyframeNumber, failed frames absent, the range clamped to the clip."""
+    frames = [(10, 16, 100), (11, 18, 140), (12, 20, 90), (9, 14, 60)]
+    v1 = man.emit_v1(30, frames)
+    (tmp_path / "clip.manifest").write_text(json.dumps(v1))
+    payload = b"".join(bytes([65 + i]) * n for i, (_, _, n) in enumerate(frames))
+    (tmp_path / "clip.drcs").write_bytes(payload)
+    seen = []
+
+    class Stub:
+        def decode_batch(self, blobs):
+            seen.append([bytes(b) for b in blobs])
+            return [{"status": 0 if b[:1] != b"C" else -2, "index": len(b), "position": b[:1], "uv": None} for b in blobs]
+
+    sq = man.V1Sequence(str(tmp_path / "clip.manifest"), Stub())
+    out = sq.decode(1, 9)
+    assert seen == [[b"B" * 140, b"C" * 90, b"D" * 60]] and sorted(out) == [1, 3]                    # frame 2 failed to decode -> absent
+    assert out[3]["frameNumber"] == 3 and out[3]["bufferGeometry"]["index"] == 60 and out[1]["bufferGeometry"]["position"] == b"B"
+    assert sq.decode(4, 9) == {} and sq.man.mesh_file.endswith("clip.drcs")

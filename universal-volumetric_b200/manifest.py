@@ -210,6 +210,35 @@ class V1Manifest:
         return out
 
 
+class V1Sequence:
+    """A V1 clip on local storage (`clip.manifest` + `clip.drcs`): the worker's fetch-slice-decode loop (src/V1/worker.ts:24-74) as
+    one batched call -- read the byte range of frames [start, end), cut the per-frame `.crt` slices, decode them all at once and
+    emit what the worker posts per frame: {frameNumber, keyframeNumber, bufferGeometry{index, position, uv}} (:58-66), which
+    `handleFrameData` keys by keyframeNumber (src/V1/player.ts:289-303)."""
+
+    def __init__(self, manifest_path, decoder):
+        self.man = V1Manifest.load(manifest_path)
+        self.decoder = decoder                     # universal-volumetric_b200.CortoDecoder
+
+    def read_range(self, frame_start, frame_end):
+        lo, hi = self.man.byte_range(frame_start, frame_end)
+        with open(self.man.mesh_file, "rb") as fh:
+            fh.seek(lo)
+            return lo, fh.read(hi - lo)
+
+    def decode(self, frame_start, frame_end):
+        """-> {keyframeNumber: {"frameNumber", "keyframeNumber", "bufferGeometry": {"index", "position", "uv"}}}; frames that fail to
+        decode are simply absent (the worker logs and skips them)."""
+        frame_end = min(frame_end, len(self.man.m["frameData"]))
+        if frame_end <= frame_start:
+            return {}
+        base, blob = self.read_range(frame_start, frame_end)
+        sl = self.man.slices(blob, base, frame_start, frame_end)
+        res = self.decoder.decode_batch([b for _, _, b in sl])
+        return {kf: {"frameNumber": fn, "keyframeNumber": kf, "bufferGeometry": {k: r[k] for k in ("index", "position", "uv")}}
+                for (fn, kf, _), r in zip(sl, res) if r["status"] == 0}
+
+
 class V2Playback:
     """Host-side playback buffer of the V2 player: keeps `buffer_duration` seconds decoded ahead of a clock.
 
