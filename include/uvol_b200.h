@@ -32,9 +32,11 @@ typedef struct uvol_ctx uvol_ctx;
 enum uvol_status { UVOL_STATUS_OK = 0, UVOL_STATUS_TRUNCATED = -1, UVOL_STATUS_CORRUPT = -2, UVOL_STATUS_UNSUPPORTED = -3,
                    UVOL_STATUS_CUDA = -4, UVOL_STATUS_ARG = -5, UVOL_STATUS_IO = -6 };
 enum uvol_memory { UVOL_MEM_DEVICE = 0, UVOL_MEM_HOST = 1 };
-/* Target texture format.  RGBA32 is the parity target (and the reference's own fallback,
- * src/lib/KTX2Loader.js:682-687). */
-enum uvol_texture_format { UVOL_TEX_RGBA32 = 0 };
+/* Target texture format (the reference picks it from the GPU's capabilities, getTranscoderFormat / FORMAT_OPTIONS,
+ * src/lib/KTX2Loader.js:591-689).  RGBA32 is the parity target and the reference's own fallback (:682-687).  ETC1 is the
+ * `etc1Supported` / opaque `etc2Supported` choice (:619-636; an RGB ETC2 texture of ETC1S content is its ETC1 blocks): 8 bytes per
+ * 4x4 block in block raster order, layers back to back; opaque ETC1S sources only (others report UVOL_STATUS_UNSUPPORTED per item). */
+enum uvol_texture_format { UVOL_TEX_RGBA32 = 0, UVOL_TEX_ETC1 = 1 };
 
 /* Result of one geometry frame.  Replaces the Draco worker reply
  *   {type:'decode', geometry:{index:{array:Uint32Array(F*3)}, attributes:[{name, array:Float32Array(P*itemSize), itemSize}]}}
@@ -60,7 +62,7 @@ typedef struct uvol_texture {
     uint32_t width, height, layers;
     uint32_t format;       /* uvol_texture_format */
     uint32_t has_alpha, dfd_transfer, dfd_flags;
-    uint8_t *data;         /* u8[layers * width * height * 4] for RGBA32 */
+    uint8_t *data;         /* RGBA32: u8[layers * width * height * 4]; ETC1: u8[layers * ceil(w/4) * ceil(h/4) * 8] */
     uint64_t bytes;
 } uvol_texture;
 

@@ -33,3 +33,14 @@ def emu_ktx2(blob):
     if rc:
         return {"status": rc}
     return {"status": 0, "rgba": np.ctypeslib.as_array(p, (l.value, h.value, w.value, 4)).copy()}
+
+
+def emu_ktx2_etc1(blob):
+    """Target ETC1 through the product's repack function on the host: u8[layers, blocks, 8]."""
+    E = _load("libbasis_emu.so")
+    p = ctypes.POINTER(ctypes.c_uint8)(); w = ctypes.c_uint32(); h = ctypes.c_uint32(); l = ctypes.c_uint32()
+    rc = E.basis_emu_decode_etc1(blob, ctypes.c_size_t(len(blob)), ctypes.byref(p), ctypes.byref(w), ctypes.byref(h), ctypes.byref(l))
+    if rc:
+        return {"status": rc}
+    nb = ((w.value + 3) // 4) * ((h.value + 3) // 4)
+    return {"status": 0, "width": w.value, "height": h.value, "layers": l.value, "blocks": np.ctypeslib.as_array(p, (l.value, nb, 8)).copy()}

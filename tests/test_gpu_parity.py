@@ -291,3 +291,21 @@ def test_uastc_zstd_supercompression(uv, ctx):
     assert [r["status"] for r in res[:4]] == [0, 0, 0, 0] and res[4]["status"] < 0
     for r, p in zip(res[:4], [plain[0], plain[1], plain[1], plain[2]]):
         assert np.array_equal(r["data"], oracle_ktx2(p)["rgba"])
+
+
+def test_texture_target_etc1(uv, ctx):
+    """Target format ETC1 (the reference's etc1Supported / opaque etc2Supported choice, KTX2Loader.js:619-636): the GPU's blocks equal
+    the host run of the same repack function byte for byte, decode (independent ETC1 decoder) to the oracle's RGBA32 texels, and
+    sources the target cannot take (UASTC) are reported per item without failing the batch."""
+    from emu_bind import emu_ktx2_etc1
+    from etc1_decode import decode_etc1
+    real = read(golden_ktx2()[0]); small = synth.encode_etc1s(synth.texture_layers(64, 0, 3, 4)); ua = _uastc_file(32, 1, 3)
+    res = uv.KTX2Loader(ctx).transcode_batch([real, ua, small], target=uv.TEX_ETC1)
+    assert [r["status"] for r in res] == [0, -3, 0]
+    for r, f in ((res[0], real), (res[2], small)):
+        e = emu_ktx2_etc1(f)
+        assert r["format"] == "RGB_ETC1_Format" and np.array_equal(r["data"], e["blocks"])
+        rgba = oracle_ktx2(f)["rgba"].reshape(r["layers"], r["height"], r["width"], 4)
+        assert np.array_equal(decode_etc1(r["data"][1], r["width"], r["height"]), rgba[1])
+    again = uv.KTX2Loader(ctx).transcode_batch([small])[0]                                        # the default target is unaffected
+    assert again["status"] == 0 and np.array_equal(again["data"], oracle_ktx2(small)["rgba"])

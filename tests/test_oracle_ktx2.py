@@ -53,3 +53,23 @@ def test_malformed_inputs(built, mutation):
     assert o["status"] in (0, -1, -2, -3)
     if mutation != "flip":
         assert o["status"] < 0
+
+
+def test_etc1_target_decodes_to_the_oracle_texels(built):
+    """Target format ETC1 (src/lib/KTX2Loader.js:619-636): the product's ETC1S -> ETC1 repack (csrc/basis_core.h, run on the host by
+    tests/tools/basis_emu.cpp), decoded by an independent ETC1 decoder written from the Khronos format description, gives exactly
+    the oracle's RGBA32 texels -- on a real fixture segment and on synthetic video segments."""
+    import sys
+    from conftest import ROOT, golden_ktx2, read
+    sys.path.insert(0, ROOT)
+    from emu_bind import emu_ktx2_etc1
+    from etc1_decode import decode_etc1
+    from tools.synth import synth
+    files = [read(golden_ktx2()[0]), synth.encode_etc1s(synth.texture_layers(64, 0, 3, 4)), synth.encode_etc1s(synth.texture_layers(8, 0, 1, 2))]
+    for f in files:
+        e, o = emu_ktx2_etc1(f), oracle_ktx2(f)
+        assert e["status"] == 0 and o["status"] == 0
+        rgba = o["rgba"].reshape(o["layers"], o["height"], o["width"], 4)
+        for L in range(e["layers"]):
+            assert np.array_equal(decode_etc1(e["blocks"][L], e["width"], e["height"]), rgba[L])
+        assert (e["blocks"][..., 3] & 3 == 3).all() and (e["blocks"][..., :3] & 7 == 0).all()        # differential, flipped, zero deltas

@@ -11,11 +11,16 @@ extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, siz
 
 int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
 
-extern "C" int basis_emu_decode(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers) {
+static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers, int etc1);
+extern "C" int basis_emu_decode(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, rgba, w, h, layers, 0); }
+// target ETC1: *rgba receives layers * blocks * 8 bytes (opaque ETC1S files only)
+extern "C" int basis_emu_decode_etc1(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 1); }
+static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers, int etc1) {
     std::vector<uint8_t> padded(len + 64, 0); memcpy(padded.data(), data, len);   // the launcher pads the blob the same way
     const uint8_t *file = padded.data();
     Ktx2File f; memset(&f, 0, sizeof f); std::vector<Ktx2Slice> slices;
     int rc = uvol_ktx2_parse(file, len, 0, f, slices); if (rc) return rc;
+    if (f.is_uastc && etc1) return UVOL_ERR_UNSUPPORTED;
     if (f.is_uastc) {          // the kernel's per-block function (uastc_core.h) over every block, Zstd levels inflated by the product's decoder
         const uint32_t nblk = f.bx * f.by;
         std::vector<uint8_t> inflated; const uint8_t *level = file + f.level_off;
@@ -67,6 +72,15 @@ extern "C" int basis_emu_decode(const uint8_t *data, size_t len, uint8_t **rgba,
         }
     }
     *w = f.width; *h = f.height; *layers = f.layers;
+    if (etc1) {                 // the kernel's repack function (basis_core.h etc1s_to_etc1) over every block
+        if (f.has_alpha) return UVOL_ERR_UNSUPPORTED;
+        *rgba = (uint8_t *)malloc((size_t)f.layers * nblk * 8 + 8);
+        for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
+            const Etc1Words e = etc1s_to_etc1(eps[ep[L][bi]], sels[sel[L][bi]]);
+            memcpy(*rgba + ((size_t)L * nblk + bi) * 8, &e.x, 4); memcpy(*rgba + ((size_t)L * nblk + bi) * 8 + 4, &e.y, 4);
+        }
+        return 0;
+    }
     *rgba = (uint8_t *)malloc((size_t)f.layers * f.width * f.height * 4);
     for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
         uint32_t rows[4][4]; etc1s_block_rows(eps[ep[L][bi]], sels[sel[L][bi]], rows);

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libuvol_b200.so")
 
 MEM_DEVICE, MEM_HOST = 0, 1
 TEX_RGBA32 = 0
+TEX_ETC1 = 1
 
 
 class UvolError(RuntimeError):

@@ -236,6 +236,28 @@ UVOL_HD int basis_build_globals(const Ktx2File &f, const uint8_t *file, BasisGlo
     return UVOL_OK;
 }
 
+// One ETC1S block -> one ETC1 block (target format ETC1, src/lib/KTX2Loader.js:628-636): differential mode with a zero delta (both
+// sub-blocks share the 5:5:5 base colour and the intensity table), flip bit set, selectors re-ordered to ETC1's pixel indices
+// (column-major, value 0 1 2 3 = +a +b -a -b where the codebook stores 0 1 2 3 = -b -a +a +b).  Returned as the two 32-bit words a
+// little-endian store writes: x = bytes 0-3 (R, G, B, table / diff / flip), y = bytes 4-7 (index MSBs, then LSBs, big-endian).
+struct Etc1Words { uint32_t x, y; };
+UVOL_HD Etc1Words etc1s_to_etc1(uint32_t ep, uint32_t sel) {
+    const uint32_t r5 = ep & 31u, g5 = (ep >> 8) & 31u, b5 = (ep >> 16) & 31u, inten = (ep >> 24) & 7u;
+    Etc1Words o;
+    o.x = (r5 << 3) | (g5 << 11) | (b5 << 19) | (((inten << 5) | (inten << 2) | 3u) << 24);
+    uint32_t msb = 0, lsb = 0;
+    for (int y = 0; y < 4; y++) {
+        const uint32_t rb = (sel >> (8 * y)) & 255u;
+        for (int x = 0; x < 4; x++) {
+            const uint32_t q = (rb >> (2 * x)) & 3u, e = (0x4Bu >> (2 * q)) & 3u;          // 0 1 2 3 -> 3 2 0 1
+            const int p = x * 4 + y;
+            msb |= (e >> 1) << p; lsb |= (e & 1u) << p;
+        }
+    }
+    o.y = (msb >> 8) | ((msb & 255u) << 8) | ((lsb >> 8) << 16) | ((lsb & 255u) << 24);
+    return o;
+}
+
 // One ETC1S block -> RGBA32 rows.  rows[r] receives 4 packed RGBA texels of pixel row r.
 UVOL_HD void etc1s_block_rows(uint32_t ep, uint32_t sel, uint32_t rows[4][4]) {
     const uint32_t c0 = etc1s_color(ep, 0) | 0xff000000u, c1 = etc1s_color(ep, 1) | 0xff000000u, c2 = etc1s_color(ep, 2) | 0xff000000u, c3 = etc1s_color(ep, 3) | 0xff000000u;

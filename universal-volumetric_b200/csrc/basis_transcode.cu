@@ -187,6 +187,22 @@ __global__ void __launch_bounds__(256) k_etc1s_blocks(const Ktx2File *files, con
     }
 }
 
+// Block -> ETC1 (target format ETC1): 4 B of indices in, one 8-byte block out per thread; a warp writes 256 contiguous bytes.
+// grid = (ceil(nblk / 256), layer list).  Opaque ETC1S files only (an alpha slice would need an EAC block next to it).
+__global__ void __launch_bounds__(256) k_etc1s_blocks_etc1(const Ktx2File *files, const TexState *state, const Ktx2Slice *slices, const uint32_t *layer_list,
+                                                           const uint8_t *S, uint8_t *O) {
+    const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
+    const Ktx2File &f = files[fi];
+    if (f.status || state[fi].status || f.is_uastc || f.has_alpha) return;
+    const uint32_t nblk = f.bx * f.by, bi = blockIdx.x * 256 + threadIdx.x;
+    if (bi >= nblk) return;
+    const Ktx2Slice &sl = slices[f.first_slice + L];
+    const uint32_t *eps = (const uint32_t *)(S + f.o_endpoints), *sels = (const uint32_t *)(S + f.o_selectors);
+    const uint32_t ei = min((uint32_t)((const uint16_t *)(S + sl.o_ep))[bi], f.endpoint_count - 1), si = min((uint32_t)((const uint16_t *)(S + sl.o_sel))[bi], f.selector_count - 1);
+    const Etc1Words w = etc1s_to_etc1(eps[ei], sels[si]);
+    ((uint2 *)(O + f.o_rgba + (size_t)L * nblk * 8))[bi] = make_uint2(w.x, w.y);
+}
+
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 uint64_t take(uint64_t &cur, uint64_t bytes) { uint64_t o = cur; cur = (cur + bytes + 127) / 128 * 128; return o; }
 
@@ -197,17 +213,17 @@ extern "C" const char *uvol_tex_stage_name(int i) { return (i >= 0 && i < 6) ? k
 
 struct TexBatch {
     std::vector<Ktx2File> files; std::vector<Ktx2Slice> slices; std::vector<uint32_t> layer_list, uastc_layers;
-    int n = 0; uint64_t blob_bytes = 0, scratch = 0, out = 0, bytes_in = 0; uint32_t max_blocks = 1, max_codebook = 0; bool any_alpha = false, any_zstd = false;
+    int n = 0; uint64_t blob_bytes = 0, scratch = 0, out = 0, bytes_in = 0; uint32_t max_blocks = 1, max_codebook = 0; bool any_alpha = false, any_zstd = false; int target = UVOL_TEX_RGBA32;
     size_t desc_bytes = 0, off_sl = 0, off_ll = 0, off_ul = 0; double parse_ms = 0; uint32_t launches = 0; int nev = 0;
 };
 void uvol_tex_batch_free(TexBatch *b) { delete b; }
 
-static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n) {
+static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target = UVOL_TEX_RGBA32) {
     const double t_begin = now_ms();
     if (!ctx->tex) ctx->tex = new TexBatch();
     TexBatch &B = *ctx->tex;
     B.n = n; B.files.assign((size_t)n, Ktx2File()); B.slices.clear(); B.layer_list.clear(); B.uastc_layers.clear();
-    B.max_blocks = 1; B.max_codebook = 0; B.any_alpha = false; B.any_zstd = false; B.bytes_in = 0;
+    B.max_blocks = 1; B.max_codebook = 0; B.any_alpha = false; B.any_zstd = false; B.bytes_in = 0; B.target = target;
     std::vector<Ktx2File> &files = B.files; std::vector<Ktx2Slice> &slices = B.slices;
     uint64_t blob_bytes = 0, s = 0, o = 0;
     for (int i = 0; i < n; i++) {
@@ -216,13 +232,14 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
         const size_t slices_before = slices.size();
         f.status = (data[i] && size[i] < (1ull << 31)) ? uvol_ktx2_parse(data[i], size[i], (uint32_t)i, f, slices) : UVOL_ERR_ARG;
         f.file_off = blob_bytes;                                      // the file itself, or (Zstd levels) the inflated level
-        blob_bytes = align_up(blob_bytes + (!f.status && f.zstd ? (uint64_t)f.z_len : (uint64_t)size[i]) + 8, 16);
+        blob_bytes = align_up(blob_bytes + (!f.status && f.zstd ? std::max<uint64_t>(f.z_len, size[i]) : (uint64_t)size[i]) + 8, 16);   // (a file rejected later is still copied as is)
         if (!f.status && f.zstd) B.any_zstd = true;
         if (f.status) { slices.resize(slices_before); continue; }
         if (f.layers > 4095 || f.bx > 4096) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }
         const uint64_t nblk = (uint64_t)f.bx * f.by;
         if (nblk > B.max_blocks) B.max_blocks = (uint32_t)nblk;
-        f.o_rgba = take(o, (uint64_t)f.layers * f.width * f.height * 4);
+        if (target == UVOL_TEX_ETC1 && (f.is_uastc || f.has_alpha)) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }   // ETC1 target: opaque ETC1S sources only
+        f.o_rgba = take(o, target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * nblk * 8 : (uint64_t)f.layers * f.width * f.height * 4);
         if (f.is_uastc) { for (uint32_t L = 0; L < f.layers; L++) B.uastc_layers.push_back(((uint32_t)i << 12) | L); continue; }   // no entropy stage, no scratch
         B.any_alpha |= f.has_alpha != 0;
         if (f.endpoint_count + f.selector_count > B.max_codebook) B.max_codebook = f.endpoint_count + f.selector_count;
@@ -303,7 +320,8 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
     stamp();
     if (nsl) { k_etc1s_resolve<<<dim3(nb4, B.any_alpha ? 2 : 1), 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dSl, dS, n); launches++; }
     stamp();
-    if (nll) {
+    if (nll && B.target == UVOL_TEX_ETC1) { k_etc1s_blocks_etc1<<<dim3((B.max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO); launches++; }
+    else if (nll) {
         const dim3 grid((B.max_blocks + 256 * ETC1S_CHUNKS - 1) / (256 * ETC1S_CHUNKS), (unsigned)nll);
         const size_t cb = (size_t)B.max_codebook * 4;
         if (cb <= 160 * 1024) {
@@ -337,9 +355,9 @@ static int ktx2_finish(uvol_ctx *ctx, int memory, uvol_texture *out, uvol_stats 
         memset(&t, 0, sizeof t);
         t.status = f.status ? f.status : hSt[i].status;
         if (t.status) continue;
-        t.width = f.width; t.height = f.height; t.layers = f.layers; t.format = UVOL_TEX_RGBA32; t.has_alpha = f.has_alpha;
+        t.width = f.width; t.height = f.height; t.layers = f.layers; t.format = (uint32_t)B.target; t.has_alpha = f.has_alpha;
         t.dfd_transfer = f.dfd_transfer; t.dfd_flags = f.dfd_flags;
-        t.bytes = (uint64_t)f.layers * f.width * f.height * 4; t.data = base + f.o_rgba; bytes_out += t.bytes;
+        t.bytes = B.target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * f.bx * f.by * 8 : (uint64_t)f.layers * f.width * f.height * 4; t.data = base + f.o_rgba; bytes_out += t.bytes;
     }
     sx.kernel_launches = B.launches; sx.bytes_in = B.bytes_in; sx.bytes_out = bytes_out; sx.scratch_bytes = B.scratch;
     if (ctx->profile) {
@@ -360,12 +378,12 @@ static int ktx2_run(uvol_ctx *ctx, int memory, uvol_texture *out, bool fresh_upl
 
 extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target_format, int memory, uvol_texture *out) {
     if (!ctx || !out || n < 0 || (n > 0 && (!data || !size)) || n >= (1 << 19)) return UVOL_ERR_ARG;
-    if (target_format != UVOL_TEX_RGBA32) { ctx->set_error("only UVOL_TEX_RGBA32 is implemented"); return UVOL_ERR_UNSUPPORTED; }
+    if (target_format != UVOL_TEX_RGBA32 && target_format != UVOL_TEX_ETC1) { ctx->set_error("target formats: UVOL_TEX_RGBA32, UVOL_TEX_ETC1"); return UVOL_ERR_UNSUPPORTED; }
     UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->stats, 0, sizeof ctx->stats);
     if (n == 0) { if (ctx->tex) ctx->tex->n = 0; return UVOL_OK; }
     const double t0 = now_ms();
-    int rc = ktx2_prepare(ctx, data, size, n); if (rc) return rc;
+    int rc = ktx2_prepare(ctx, data, size, n, target_format); if (rc) return rc;
     rc = ktx2_run(ctx, memory, out, true); if (rc) return rc;
     ctx->stats.host_parse_ms = ctx->tex->parse_ms; ctx->stats.total_ms = now_ms() - t0;
     return UVOL_OK;

@@ -169,16 +169,22 @@ class KTX2Loader:
             raise N.UvolError(f"uvol_replay_ktx2_batch failed ({rc}): {self.ctx.last_error()}")
         return out
 
-    def transcode_batch(self, files):
-        raw = self.transcode_batch_raw(files, N.MEM_HOST)
+    def transcode_batch(self, files, target=N.TEX_RGBA32):
+        """target = TEX_RGBA32 (default; data u8[layers, h, w, 4]) or TEX_ETC1 (data u8[layers, blocks, 8], the reference's
+        RGB_ETC1_Format / opaque RGB_ETC2_Format choice, KTX2Loader.js:619-636)."""
+        raw = self.transcode_batch_raw(files, N.MEM_HOST, target)
         res = []
         for t in raw:
             if t.status != 0:
                 res.append({"status": int(t.status), "data": None})
                 continue
-            data = np.ctypeslib.as_array(t.data, (t.layers, t.height, t.width, 4)).copy()
+            if target == N.TEX_ETC1:
+                nb = ((t.width + 3) // 4) * ((t.height + 3) // 4)
+                data = np.ctypeslib.as_array(t.data, (t.layers, nb, 8)).copy()
+            else:
+                data = np.ctypeslib.as_array(t.data, (t.layers, t.height, t.width, 4)).copy()
             res.append({"status": 0, "width": int(t.width), "height": int(t.height), "layers": int(t.layers), "hasAlpha": bool(t.has_alpha),
-                        "format": "RGBAFormat", "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data})
+                        "format": "RGB_ETC1_Format" if target == N.TEX_ETC1 else "RGBAFormat", "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data})
         return res
 
 
