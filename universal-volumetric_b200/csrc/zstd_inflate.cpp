@@ -186,6 +186,12 @@ struct BackFast {
         if (ptr - start >= 8) { ptr -= consumed >> 3; consumed &= 7u; memcpy(&c, ptr, 8); }
         else if (ptr != start) { size_t nb = consumed >> 3; if (nb > (size_t)(ptr - start)) nb = (size_t)(ptr - start); ptr -= nb; consumed -= (unsigned)(8 * nb); memcpy(&c, ptr, 8); }
     }
+    inline uint64_t read(unsigned nb) {                            // nb <= 32; call reload() so that the bits are in the container; past the first byte: zeros
+        if (consumed >= 64) { consumed += nb; return 0; }
+        const uint64_t v = ((c << consumed) >> 1) >> (63u - nb);
+        consumed += nb;
+        return v;
+    }
     inline bool roomy() const { return ptr - start >= 8; }         // a reload brings at least 57 unread bits
     inline bool done() const { return ptr == start && consumed == 64; }
 };
@@ -310,15 +316,20 @@ bool block_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t
         p += u;
         if ((u = seq_table((modes >> 2) & 3, src + p, n - p, fs.seq.ml, fs.seq.have_ml, ML_DEF, 53, 6, 52, 9)) == (size_t)-1) return false;
         p += u;
-        BackBits b; if (!back_init(b, src + p, n - p)) return false;
+        BackFast b; if (!b.init(src + p, n - p)) return false;
         const FseTable &LL = fs.seq.ll, &OF = fs.seq.of, &ML = fs.seq.ml;
-        uint32_t sl = (uint32_t)back_read(b, LL.log), so = (uint32_t)back_read(b, OF.log), sm = (uint32_t)back_read(b, ML.log);
+        uint32_t sl = (uint32_t)b.read((unsigned)LL.log), so = (uint32_t)b.read((unsigned)OF.log), sm = (uint32_t)b.read((unsigned)ML.log);   // <= 26 bits
+        // 16-byte copies may overshoot: the literal source is readable up to lit_lim, the destination up to cap
+        const uint8_t *const lit_lim = lit == lit_buf ? lit_buf + (128u << 10) + 32 : src + n;
         for (size_t i = 0; i < nseq; i++) {
-            const int lc = LL.e[sl].sym, oc = OF.e[so].sym, mc = ML.e[sm].sym;
+            const FseEntry el = LL.e[sl], eo = OF.e[so], em = ML.e[sm];
+            const unsigned lc = el.sym, oc = eo.sym, mc = em.sym;
             if (lc > 35 || mc > 52 || oc > 31) return false;
-            const uint64_t ov = (1ull << oc) + back_read(b, oc);
-            const size_t mlen = ML_BASE[mc] + (size_t)back_read(b, ML_BITS[mc]);
-            const size_t llen = LL_BASE[lc] + (size_t)back_read(b, LL_BITS[lc]);
+            b.reload();
+            const uint64_t ov = (1ull << oc) + b.read(oc);                       // <= 31 bits
+            if (oc + ML_BITS[mc] + LL_BITS[lc] > 56) b.reload();
+            const size_t mlen = ML_BASE[mc] + (size_t)b.read(ML_BITS[mc]);       // <= 16 + 16 bits
+            const size_t llen = LL_BASE[lc] + (size_t)b.read(LL_BITS[lc]);
             uint64_t offset;
             if (ov > 3) { offset = ov - 3; fs.rep[2] = fs.rep[1]; fs.rep[1] = fs.rep[0]; fs.rep[0] = offset; }
             else {
@@ -332,18 +343,24 @@ bool block_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t
                     fs.rep[1] = fs.rep[0]; fs.rep[0] = offset;
                 }
             }
-            if (i + 1 < nseq) {                                    // state updates: literals length, match length, offset
-                sl = LL.e[sl].base + (uint32_t)back_read(b, LL.e[sl].nbits);
-                sm = ML.e[sm].base + (uint32_t)back_read(b, ML.e[sm].nbits);
-                so = OF.e[so].base + (uint32_t)back_read(b, OF.e[so].nbits);
+            if (i + 1 < nseq) {                                    // state updates: literals length, match length, offset (<= 26 bits)
+                b.reload();
+                sl = el.base + (uint32_t)b.read(el.nbits);
+                sm = em.base + (uint32_t)b.read(em.nbits);
+                so = eo.base + (uint32_t)b.read(eo.nbits);
             }
             if (lpos + llen > regen || d + llen + mlen > cap || offset > d + llen) return false;
-            memcpy(dst + d, lit + lpos, llen); d += llen; lpos += llen;
-            const uint8_t *m = dst + d - offset;
-            if (offset >= mlen) memcpy(dst + d, m, mlen); else for (size_t k = 0; k < mlen; k++) dst[d + k] = m[k];
+            uint8_t *o = dst + d; const uint8_t *ls = lit + lpos;
+            if (llen <= 16 && ls + 16 <= lit_lim && d + 16 <= cap) memcpy(o, ls, 16); else memcpy(o, ls, llen);
+            d += llen; lpos += llen; o += llen;
+            const uint8_t *m = o - offset;
+            if (offset >= 16 && d + mlen + 16 <= cap) { for (size_t k = 0; k < mlen; k += 16) memcpy(o + k, m + k, 16); }
+            else if (offset >= mlen) memcpy(o, m, mlen);
+            else for (size_t k = 0; k < mlen; k++) o[k] = m[k];
             d += mlen;
         }
-        if (b.bits != 0) return false;
+        b.reload();
+        if (!b.done()) return false;
     }
     if (d + (regen - lpos) > cap) return false;
     memcpy(dst + d, lit + lpos, regen - lpos); d += regen - lpos;
