@@ -54,7 +54,7 @@ static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba
     std::vector<uint8_t> rowp(4096); std::vector<uint16_t> hist(1024);
     for (size_t k = 0; k < ns; k++) {
         pred[k].resize(nblk); delta[k].resize(nblk); sel[k].resize(nblk); ep[k].resize(nblk);
-        BitRd b; br_init(b, file + slices[k].data_off);
+        BitRd b; br_init(b, file + slices[k].data_off, slices[k].data_len);
         SliceTables T{&tabs[0], &tabs[1], &tabs[2], &tabs[3], pool.data()};
         rc = etc1s_slice_symbols(b, T, f.bx, f.by, f.selector_count, hs, (int)f.is_video, rowp.data(), hist.data(), pred[k].data(), delta[k].data(), sel[k].data());
         if (rc) return rc;

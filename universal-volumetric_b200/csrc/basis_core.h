@@ -12,14 +12,16 @@
 #endif
 
 // ---------------------------------------------------------------------------------------------
-// LSB-first bit reader over 32-bit aligned words (the batch blob is padded so that reading one
-// word past a section is always in bounds).
-struct BitRd { const uint32_t *w; uint32_t wi; uint64_t buf; int nbits; uint64_t consumed; };
-UVOL_HD void br_init(BitRd &b, const uint8_t *p) {
+// LSB-first bit reader over 32-bit aligned words, bounded by the section's byte length: past the last word that holds a
+// section byte it yields zeros (a corrupt stream is then caught by the callers' `consumed` check instead of walking out of the
+// blob).  The batch blob is padded, so the aligned words that straddle the section's ends are always readable.
+struct BitRd { const uint32_t *w; uint32_t wi, lim; uint64_t buf; int nbits; uint64_t consumed; };
+UVOL_HD void br_init(BitRd &b, const uint8_t *p, uint32_t nbytes) {
     const uintptr_t a = (uintptr_t)p; const unsigned mis = (unsigned)(a & 3);
-    b.w = (const uint32_t *)(a - mis); b.buf = (uint64_t)b.w[0] >> (8 * mis); b.nbits = 32 - 8 * (int)mis; b.wi = 1; b.consumed = 0;
+    b.w = (const uint32_t *)(a - mis); b.lim = (mis + nbytes + 3) / 4;
+    b.buf = b.lim ? (uint64_t)b.w[0] >> (8 * mis) : 0; b.nbits = 32 - 8 * (int)mis; b.wi = 1; b.consumed = 0;
 }
-UVOL_HD void br_refill(BitRd &b) { if (b.nbits <= 32) { b.buf |= (uint64_t)b.w[b.wi++] << b.nbits; b.nbits += 32; } }
+UVOL_HD void br_refill(BitRd &b) { if (b.nbits <= 32) { const uint32_t v = b.wi < b.lim ? b.w[b.wi] : 0u; b.wi++; b.buf |= (uint64_t)v << b.nbits; b.nbits += 32; } }
 UVOL_HD uint32_t br_peek(BitRd &b) { br_refill(b); return (uint32_t)b.buf; }
 UVOL_HD void br_skip(BitRd &b, int n) { b.buf >>= n; b.nbits -= n; b.consumed += (uint64_t)n; }
 UVOL_HD uint32_t br_get(BitRd &b, int n) { if (n == 0) return 0; br_refill(b); uint32_t v = (uint32_t)b.buf & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u)); br_skip(b, n); return v; }
@@ -185,7 +187,7 @@ UVOL_HD int basis_build_globals(const Ktx2File &f, const uint8_t *file, BasisGlo
     uint32_t pool_used = 0; int rc;
     // slice tables first (they persist at the front of the pool)
     {
-        BitRd b; br_init(b, file + f.tab_off);
+        BitRd b; br_init(b, file + f.tab_off, f.tab_len);
         if ((rc = basis_read_table(b, m.tables[0], m, pool_used, 32768))) return rc;
         if ((rc = basis_read_table(b, m.tables[1], m, pool_used, 32768))) return rc;
         if ((rc = basis_read_table(b, m.tables[2], m, pool_used, 32768))) return rc;
@@ -196,7 +198,7 @@ UVOL_HD int basis_build_globals(const Ktx2File &f, const uint8_t *file, BasisGlo
         if ((b.consumed + 7) / 8 > f.tab_len) return UVOL_ERR_CORRUPT;
     }
     {   // endpoints
-        BitRd b; br_init(b, file + f.ep_off);
+        BitRd b; br_init(b, file + f.ep_off, f.ep_len);
         for (int k = 0; k < 4; k++) if ((rc = basis_read_table(b, m.tables[4 + k], m, pool_used, 256))) return rc;
         const uint32_t gray = br_get(b, 1);
         uint32_t prev[3] = {16, 16, 16}, pint = 0;
@@ -214,7 +216,7 @@ UVOL_HD int basis_build_globals(const Ktx2File &f, const uint8_t *file, BasisGlo
         if ((b.consumed + 7) / 8 > f.ep_len) return UVOL_ERR_CORRUPT;
     }
     {   // selectors
-        BitRd b; br_init(b, file + f.sel_off);
+        BitRd b; br_init(b, file + f.sel_off, f.sel_len);
         const uint32_t glob = br_get(b, 1), hyb = br_get(b, 1), raw = br_get(b, 1);
         if (glob || hyb) return UVOL_ERR_UNSUPPORTED;
         if (raw) { for (uint32_t i = 0; i < f.selector_count; i++) { uint32_t v = 0; for (int j = 0; j < 4; j++) v |= br_get(b, 8) << (8 * j); m.selectors[i] = v; } }

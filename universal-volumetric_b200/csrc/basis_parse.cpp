@@ -24,20 +24,24 @@ int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File 
     if (levels == 0) levels = 1;
     if (levels != 1) return UVOL_ERR_UNSUPPORTED;      // UVOL textures carry no mips (scripts/Encoder.py:290)
     const uint32_t nl = layers ? layers : 1;
-    if ((uint64_t)dfdOff + dfdLen > len || (uint64_t)kvdOff + kvdLen > len || sgdOff + sgdLen > len || dfdLen < 44) return UVOL_ERR_CORRUPT;
+    // every (offset, length) pair comes from the file: compare without forming offset + length (a 64-bit sum wraps)
+    auto inside = [len](uint64_t off, uint64_t n) { return off <= len && n <= len - off; };
+    if (!inside(dfdOff, dfdLen) || !inside(kvdOff, kvdLen) || !inside(sgdOff, sgdLen) || dfdLen < 44) return UVOL_ERR_CORRUPT;
     const uint64_t lvOff = rd64(b + 80), lvLen = rd64(b + 88);
-    if (lvOff + lvLen > len || lvOff > 0xffffffffull) return UVOL_ERR_TRUNCATED;
+    if (!inside(lvOff, lvLen) || lvOff > 0xffffffffull) return UVOL_ERR_TRUNCATED;
     const int color_model = b[dfdOff + 12];
     f.dfd_transfer = b[dfdOff + 14]; f.dfd_flags = b[dfdOff + 15];
     const int nsamples = (int)((rd16(b + dfdOff + 10) - 24) / 16);
     const int chan0 = b[dfdOff + 28 + 3] & 0xF;
     f.width = w; f.height = h; f.layers = nl; f.bx = (w + 3) / 4; f.by = (h + 3) / 4;
     f.is_uastc = color_model == 166; f.is_video = 0;
-    for (uint32_t p = kvdOff; p + 4 <= kvdOff + kvdLen;) {
-        const uint32_t kl = rd32(b + p); p += 4;
-        if (p + kl > kvdOff + kvdLen) break;
+    for (uint64_t p = kvdOff, end = (uint64_t)kvdOff + kvdLen; end - p >= 4;) {          // 64-bit cursor: keyAndValueByteLength is attacker-controlled
+        const uint64_t kl = rd32(b + p); p += 4;
+        if (kl > end - p) break;
         if (kl >= 11 && !memcmp(b + p, "KTXanimData", 11)) f.is_video = 1;
-        p += (kl + 3) & ~3u;
+        const uint64_t adv = (kl + 3) & ~3ull;                                           // always forward, never past the block
+        if (adv == 0 || adv > end - p) break;
+        p += adv;
     }
     f.level_off = (uint32_t)lvOff; f.first_slice = (uint32_t)slices.size();
     const uint64_t nblk = (uint64_t)f.bx * f.by;
@@ -47,7 +51,8 @@ int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File 
         f.has_alpha = chan0 == 3;
         if (sc == 2) {          // the level is one Zstandard frame: inflated by the host into the staging blob (csrc/zstd_inflate.cpp)
             const uint64_t ulen = rd64(b + 96);
-            if (ulen < (uint64_t)nl * nblk * 16 || ulen >= (1ull << 31) || lvLen >= (1ull << 31) || lvLen == 0) return ulen >= (1ull << 31) ? UVOL_ERR_UNSUPPORTED : UVOL_ERR_TRUNCATED;
+            // the inflated level is exactly the block payload: a header asking for more than that is rejected before anything is reserved
+            if (ulen != (uint64_t)nl * nblk * 16 || ulen >= (1ull << 31) || lvLen >= (1ull << 31) || lvLen == 0) return ulen >= (1ull << 31) ? UVOL_ERR_UNSUPPORTED : UVOL_ERR_TRUNCATED;
             f.zstd = 1; f.z_src_off = (uint32_t)lvOff; f.z_src_len = (uint32_t)lvLen; f.z_len = (uint32_t)ulen; f.level_off = 0;
             f.endpoint_count = f.selector_count = 0;
             return UVOL_OK;
@@ -61,7 +66,7 @@ int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File 
     if (sgdLen < 20 + 20ull * nl) return UVOL_ERR_CORRUPT;
     const uint8_t *g = b + sgdOff;
     const uint32_t ec = rd16(g), scnt = rd16(g + 2), eb = rd32(g + 4), sb = rd32(g + 8), tb = rd32(g + 12);
-    if (20 + 20ull * nl + eb + sb + tb > sgdLen || ec == 0 || scnt == 0) return UVOL_ERR_CORRUPT;
+    if (20 + 20ull * nl + eb + sb + tb > sgdLen || ec == 0 || scnt == 0 || sgdOff + sgdLen > 0xffffffffull) return UVOL_ERR_CORRUPT;
     f.endpoint_count = ec; f.selector_count = scnt;
     f.ep_off = (uint32_t)(sgdOff + 20 + 20ull * nl); f.ep_len = eb;
     f.sel_off = f.ep_off + eb; f.sel_len = sb; f.tab_off = f.sel_off + sb; f.tab_len = tb;
@@ -69,7 +74,7 @@ int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File 
         for (uint32_t L = 0; L < nl; L++) {
             const uint8_t *d = g + 20 + 20 * L;
             const uint32_t off = rd32(d + 4 + 8 * plane), ln = rd32(d + 8 + 8 * plane);
-            if ((uint64_t)off + ln > lvLen || ln == 0) return UVOL_ERR_TRUNCATED;
+            if (off > lvLen || ln > lvLen - off || ln == 0 || lvOff + off + ln > len) return UVOL_ERR_TRUNCATED;
             Ktx2Slice s; memset(&s, 0, sizeof s);
             s.file = file_index; s.layer = L; s.data_off = (uint32_t)(lvOff + off); s.data_len = ln; s.is_alpha = (uint32_t)plane;
             slices.push_back(s);

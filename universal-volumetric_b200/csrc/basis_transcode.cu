@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_etc1s_slices(const Ktx2Fi
     }
     __syncwarp();
     if ((threadIdx.x & 31) != 0) return;
-    BitRd b; br_init(b, blob + f.file_off + sl.data_off);
+    BitRd b; br_init(b, blob + f.file_off + sl.data_off, sl.data_len);
     SliceTables T{&tabs[0], &tabs[1], &tabs[2], &tabs[3], (const uint16_t *)(S + f.o_sorted)};
     const int rc = etc1s_slice_symbols(b, T, f.bx, f.by, f.selector_count, state[sl.file].hist_size, (int)f.is_video, rowp, hist,
                                        S + sl.o_pred, (uint16_t *)(S + sl.o_delta), (uint16_t *)(S + sl.o_sel));
@@ -234,6 +234,8 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
         f.file_off = blob_bytes;                                      // the file itself, or (Zstd levels) the inflated level
         blob_bytes = align_up(blob_bytes + (!f.status && f.zstd ? std::max<uint64_t>(f.z_len, size[i]) : (uint64_t)size[i]) + 8, 16);   // (a file rejected later is still copied as is)
         if (!f.status && f.zstd) B.any_zstd = true;
+        for (size_t k = slices_before; k < slices.size() && !f.status; k++)      // what the slice kernel dereferences lies inside this file (the parser guarantees it; checked again at the trust boundary)
+            if ((uint64_t)slices[k].data_off + slices[k].data_len > size[i]) f.status = UVOL_ERR_CORRUPT;
         if (f.status) { slices.resize(slices_before); continue; }
         if (f.layers > 4095 || f.bx > 4096) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }
         const uint64_t nblk = (uint64_t)f.bx * f.by;

@@ -114,8 +114,11 @@ int uvol_draco_parse(const uint8_t *data, size_t len, DracoFrame &f, std::vector
         Dec &d = dec[i];
         if (d.att_data_id >= (int)f.nad || d.trav != 0 || d.dec_type > 1) return UVOL_ERR_UNSUPPORTED;
         if (d.dec_type == 1 && d.att_data_id < 0) return UVOL_ERR_CORRUPT;
-        d.natt = (int)r.varint(); d.first = f.nattr;
-        if (r.err || d.natt < 1 || f.nattr + d.natt > UVOL_MAX_ATTRS) return UVOL_ERR_UNSUPPORTED;
+        // the count is attacker-controlled: compare as unsigned 64-bit BEFORE any int arithmetic (a varint of INT_MAX used to wrap
+        // the signed sum and let the loop below write past f.attr[])
+        const uint64_t na = r.varint(); d.first = f.nattr;
+        if (r.err || na < 1 || na > (uint64_t)(UVOL_MAX_ATTRS - f.nattr)) return UVOL_ERR_UNSUPPORTED;
+        d.natt = (int)na;
         for (int j = 0; j < d.natt; j++) {
             DracoAttr &a = f.attr[f.nattr + j]; memset(&a, 0, sizeof a);
             a.type = (int8_t)r.u8(); a.dtype = (int8_t)r.u8(); a.nc = (int8_t)r.u8(); a.normalized = (int8_t)r.u8(); (void)r.varint();

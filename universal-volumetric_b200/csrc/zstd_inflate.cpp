@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <string.h>
+#include <atomic>
 #include "uvol_internal.h"
 
 namespace {
@@ -18,7 +19,7 @@ namespace {
 // Feature counters (test aid: which parts of the format the vectors exercised; not synchronised).
 // 0 raw blocks, 1 RLE blocks, 2 compressed blocks, 3 raw literals, 4 RLE literals, 5 Huffman literals, 6 treeless literals, 7 four-stream
 // literals, 8 direct weights, 9 FSE-coded weights, 10 predefined tables, 11 RLE tables, 12 FSE tables, 13 repeat tables, 14 repeat offsets, 15 frames
-uint64_t g_feat[16];
+std::atomic<uint64_t> g_feat[16];          // test aid (feature coverage); relaxed atomics: the staging threads inflate concurrently
 
 struct FseEntry { uint8_t sym, nbits; uint16_t base; };          // next state = base + read(nbits)
 struct FseTable { FseEntry e[512]; int log; };                    // accuracy log <= 9
@@ -144,7 +145,7 @@ size_t huf_read_table(const uint8_t *p, size_t n, HufTable &t) {
     if (n < 1) return 0;
     uint8_t w[257]; int nsym = 0; size_t used;
     const int hb = p[0];
-    g_feat[hb >= 128 ? 8 : 9]++;
+    g_feat[hb >= 128 ? 8 : 9].fetch_add(1, std::memory_order_relaxed);
     if (hb >= 128) {                                               // direct 4-bit weights
         nsym = hb - 127; used = 1 + (size_t)(nsym + 1) / 2;
         if (used > n) return 0;
@@ -240,7 +241,7 @@ const uint8_t ML_BITS[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 
 
 // One of the three sequence tables according to its 2-bit mode.  Returns bytes consumed (may be 0), (size_t)-1 on error.
 size_t seq_table(int mode, const uint8_t *p, size_t n, FseTable &t, bool &have, const int16_t *def, int def_n, int def_log, int max_sym, int max_log) {
-    g_feat[10 + mode]++;
+    g_feat[10 + mode].fetch_add(1, std::memory_order_relaxed);
     if (mode == 0) { if (!fse_build(t, def, def_n, def_log)) return (size_t)-1; have = true; return 0; }
     if (mode == 1) { if (n < 1 || p[0] > max_sym) return (size_t)-1; t.log = 0; t.e[0].sym = p[0]; t.e[0].nbits = 0; t.e[0].base = 0; have = true; return 1; }
     if (mode == 2) {
@@ -270,7 +271,7 @@ bool block_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t
         else { if (n < 5) return false; const uint64_t v = src[0] | (src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint64_t)src[3] << 24) | ((uint64_t)src[4] << 32); regen = (size_t)((v >> 4) & 262143); csize = (size_t)(v >> 22); hdr = 5; streams = 4; }
     }
     if (regen > (128u << 10)) return false;
-    g_feat[3 + ltype]++; if (streams == 4) g_feat[7]++;
+    g_feat[3 + ltype].fetch_add(1, std::memory_order_relaxed); if (streams == 4) g_feat[7].fetch_add(1, std::memory_order_relaxed);
     const uint8_t *lit; size_t p = hdr;
     if (ltype == 0) { if (p + regen > n) return false; lit = src + p; p += regen; }
     else if (ltype == 1) { if (p + 1 > n) return false; memset(lit_buf, src[p], regen); lit = lit_buf; p += 1; }
@@ -333,7 +334,7 @@ bool block_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t
             uint64_t offset;
             if (ov > 3) { offset = ov - 3; fs.rep[2] = fs.rep[1]; fs.rep[1] = fs.rep[0]; fs.rep[0] = offset; }
             else {
-                g_feat[14]++;
+                g_feat[14].fetch_add(1, std::memory_order_relaxed);
                 const uint64_t idx = ov - 1 + (llen == 0 ? 1 : 0);          // 0..3
                 if (idx == 0) offset = fs.rep[0];
                 else {
@@ -370,7 +371,7 @@ bool block_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t
 
 }  // namespace
 
-extern "C" void uvol_zstd_feature_counts(uint64_t *out16, int reset) { for (int i = 0; i < 16; i++) { out16[i] = g_feat[i]; if (reset) g_feat[i] = 0; } }
+extern "C" void uvol_zstd_feature_counts(uint64_t *out16, int reset) { for (int i = 0; i < 16; i++) { out16[i] = g_feat[i].load(std::memory_order_relaxed); if (reset) g_feat[i].store(0, std::memory_order_relaxed); } }
 
 // Inflates every frame in src[0..n) into dst (capacity cap).  Returns UVOL_OK and the byte count, or a negative status.
 extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len) {
@@ -402,13 +403,13 @@ extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, siz
         if (fcs_bytes == 2) fcs += 256;
         p += fcs_bytes;
         const size_t frame_start = d;
-        g_feat[15]++;
+        g_feat[15].fetch_add(1, std::memory_order_relaxed);
         FrameState fs;
         for (;;) {
             if (p + 3 > n) { rc = UVOL_ERR_TRUNCATED; break; }
             const uint32_t bh = src[p] | (src[p + 1] << 8) | ((uint32_t)src[p + 2] << 16); p += 3;
             const int last = bh & 1, type = (bh >> 1) & 3; const size_t bsize = bh >> 3;
-            if (type < 3) g_feat[type]++;
+            if (type < 3) g_feat[type].fetch_add(1, std::memory_order_relaxed);
             if (type == 0) { if (p + bsize > n) { rc = UVOL_ERR_TRUNCATED; break; } if (d + bsize > cap) { rc = UVOL_ERR_CORRUPT; break; } memcpy(dst + d, src + p, bsize); d += bsize; p += bsize; }
             else if (type == 1) { if (p + 1 > n) { rc = UVOL_ERR_TRUNCATED; break; } if (d + bsize > cap) { rc = UVOL_ERR_CORRUPT; break; } memset(dst + d, src[p], bsize); d += bsize; p += 1; }
             else if (type == 2) {
