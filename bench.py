@@ -10,8 +10,11 @@ synthetic 1000-frame V2 sequence, 200k verts/frame Draco geometry, 2048^2 UASTC 
 ETC1S).  One "step" = one pass of the hot path over the whole sequence.  A sequence whose scratch does not fit HBM at
 once is decoded in WINDOWS of whole segments (the prefetch window of src/V2/player.ts:272-323); every window's
 compressed inputs stay resident in HBM (one ctx per window), the scratch / output arenas exist once (uvol_share_arenas).
-N>1: every rank decodes its own sequence (frames are independent units, no data-path collective) -> "scaling": "weak";
-value = all frames / max-over-ranks time.
+N>1 (BASELINE configs[3]): ONE sequence (same seed on every rank) is frame-sharded with manifest.shard_v2 -- rank r decodes only
+its contiguous block of whole KTX2 segments and the geometry frames they cover, no data-path collective -- and the decoded
+shards (geometry AND textures) are then gathered on every rank over NCCL / NVLink (gather.all_gather_shard).  "scaling":
+"strong"; a step = decode of the shard + the gather; value = frames of the sequence / max-over-ranks step time.  The old
+weak-scaling figure (every rank decodes a whole sequence of its own) is kept under the extra key "weak".
 
   value     frames/s with the compressed inputs already resident in HBM (uvol_replay_v2_batch), device
             time from CUDA events on the library's streams (geometry and texture run concurrently, the
@@ -52,14 +55,18 @@ METRIC = _metric()
 WORKLOADS = {
     # window_segments: segments decoded per library call (None = the whole sequence at once); distinct_*: how many distinct
     # frames / segments are actually encoded by the generator (the rest cycle through them) to bound generation time.
-    "c3": dict(frames=1000, verts=200000, tex=2048, seq=7, seed=20260003, fmt="uastc", window_segments=72, distinct_geo=32, distinct_tex=6,
+    "c3": dict(frames=1000, verts=200000, tex=2048, seq=7, seed=20260003, fmt="uastc", window_segments=None, distinct_geo=32, distinct_tex=6,
                label="configs[2]: 1000-frame V2 seq, 200k verts/frame Draco, 2048^2 UASTC KTX2 batch=7"),
     "c2": dict(frames=300, verts=50000, tex=1024, seq=7, seed=20260002, fmt="etc1s", window_segments=None, distinct_geo=None, distinct_tex=None,
                label="configs[1]: 300-frame V2 seq, 50k verts/frame Draco, 1024^2 ETC1S KTX2 batch=7"),
     "c5": dict(frames=300, verts=50000, tex=1024, seq=1, seed=20260005, fmt="corto", window_segments=None, distinct_geo=8, distinct_tex=None,
                label="configs[4]: V1 manifest, 300-frame Corto .crt geometry (position 12 bit + uv 12 bit, u32 index); V1's mp4 texture leg is out of scope"),
-    "tiny": dict(frames=28, verts=2000, tex=64, seq=7, seed=20260009, fmt="uastc", window_segments=2, distinct_geo=None, distinct_tex=None,
+    "tiny": dict(frames=28, verts=2000, tex=64, seq=7, seed=20260009, fmt="uastc", window_segments=None, distinct_geo=None, distinct_tex=None,
                  label="tiny smoke workload"),
+    # the reference's own capture (example/public/liam/output): 250 real .drc frames and 50 real ETC1S segments of 5 x 1024^2, cycled to
+    # 1000 frames / 200 segments -- real entropy statistics, real seams (SURVEY 8d "liam x N")
+    "liam": dict(frames=1000, verts=26145, tex=1024, seq=5, seed=0, fmt="etc1s", window_segments=None, distinct_geo=250, distinct_tex=50,
+                 label="liam x4: the reference's 250 real Draco frames (26k verts, 52k faces) + 50 real ETC1S KTX2 segments (5 x 1024^2), cycled to 1000 frames"),
 }
 
 
@@ -124,14 +131,37 @@ def bind_to_gpu_cpus(local, world):
     return ncpu
 
 
-def make_workload(name, rank):
-    from tools.synth import synth
+def make_workload(name, rank=0):
+    """The workload's files.  `rank` only varies the seed of the synthetic generators (the weak-scaling side figure); the headline
+    decodes ONE sequence, rank 0's."""
     w = WORKLOADS[name]
     t0 = time.time()
-    drc, ktx, info = synth.make_sequence(w["frames"], w["verts"], w["tex"], sequence_size=w["seq"], seed=w["seed"] + 1000 * rank,
-                                         distinct_geometry=w["distinct_geo"], distinct_textures=w["distinct_tex"], texture_format=w["fmt"])
+    if name == "liam":
+        import glob
+        fx = os.path.join(ROOT, "oracle", "_ref", "fixtures")
+        d = sorted(glob.glob(os.path.join(fx, "geometry_draco", "*.drc"))) or sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "liam", "*.drc")))
+        k = sorted(glob.glob(os.path.join(fx, "texture_ktx2", "*.ktx2"))) or sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "liam", "*.ktx2")))
+        db = [open(f, "rb").read() for f in d]; kb = [open(f, "rb").read() for f in k]
+        nseg = (w["frames"] + w["seq"] - 1) // w["seq"]
+        drc = [db[i % len(db)] for i in range(w["frames"])]; ktx = [kb[i % len(kb)] for i in range(nseg)]
+        info = {"verts": w["verts"], "faces": 2 * w["verts"], "tex_size": w["tex"], "distinct_geometry": len(db), "distinct_textures": len(kb),
+                "source": "oracle/_ref/fixtures" if len(db) > 3 else "tests/golden/liam (full fixture set not staged)"}
+    else:
+        from tools.synth import synth
+        drc, ktx, info = synth.make_sequence(w["frames"], w["verts"], w["tex"], sequence_size=w["seq"], seed=w["seed"] + 1000 * rank,
+                                             distinct_geometry=w["distinct_geo"], distinct_textures=w["distinct_tex"], texture_format=w["fmt"])
     info["gen_s"] = round(time.time() - t0, 2)
     return drc, ktx, info
+
+
+def workload_config(name, W, info, n_gpus, n_segments, target):
+    """`config` of the JSON line: the same keys and values in our arm and in the reference arm."""
+    return {"workload": f"{W['label']} ({'real fixtures' if name == 'liam' else 'synthetic, tools/synth seed %d' % W['seed']})",
+            "frames": W["frames"], "segments": n_segments, "sequence_size": W["seq"], "verts": info["verts"], "faces": info["faces"],
+            "texture": f"{W['tex']}x{W['tex']} {W['fmt']}", "texture_target": target,
+            "distinct_geometry_frames": info["distinct_geometry"], "distinct_texture_segments": info["distinct_textures"],
+            "l2": "flushed between timed iterations (256 MiB memset); the working set is far larger than L2",
+            "parallelism": f"one sequence frame-sharded over {n_gpus} GPU(s) (manifest.shard_v2), NCCL gather of the decoded shards when > 1"}
 
 
 def make_windows(drc, ktx, seq, window_segments):
@@ -168,19 +198,23 @@ def cpu_sample(drc, ktx, seq, nseg):
     return drc[: nseg * seq], ktx[:nseg]
 
 
-def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex, fmt):
+TARGETS = {"rgba32": 0, "etc1": 1, "bc7": 2}
+
+
+def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex, fmt, target="rgba32"):
     """ALGORITHMIC bytes per step for each kernel stage (DESIGN.md 'Kernels and rooflines')."""
     F, V = info["faces"], info["verts"]
     nblk = (info["tex_size"] // 4) ** 2
     P = P_total / frames
     g = {
         "edgebreaker": frames * (F * 1 + 2 * 3 * F * 4),                       # symbols in, corner table (opp + c2v) out
-        "traverse": frames * 3 * (3 * F * 4 + 2 * V * 4),                     # per table: corner table in, entry maps out
+        "traverse": frames * 3 * (F * 32 + F + 2 * V * 4),                    # per table: 32 B face records in, visited bytes + entry maps out
+        "face_records": frames * 3 * (2 * 3 * F * 4 + 3 * F + F * 32),        # per table: corner table + seam flags in, 32 B records out
         "rans_attr": bytes_in_geo + frames * (3 * V + 2 * P + 2 * V) * 4,      # compressed in, int32 corrections out
         "predict_wrap": frames * (V * 16 + 2 * V * 12),                       # parents + corrections in, values out
         "predict_uv": frames * P * (32 + 8 + 8),
         "normals": frames * V * (8 + 8 + 7 * 12),
-        "expand": frames * (P * 4 + P * 32 + P * 32),                          # p2c + gathers in, 32 B/point out
+        "expand": frames * (P * 4 + P * 3 * 8 + P * 28 + P * 32),              # p2c + (corner->vertex, vertex->entry) x 3 + 28 B of int values in, 32 B/point out
         "seams": frames * (3 * F * 4 + 2 * 3 * F),
         "attr_tables": frames * 2 * (3 * F * 4 + 3 * F * 4),
         "point_assign": frames * (3 * F * 4 * 3),
@@ -188,7 +222,7 @@ def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex, fmt):
     t = {
         "slices": bytes_in_tex + frames * nblk * 5,                            # VLC bits in, {pred u8, delta/selector u16} out
         "resolve": frames * nblk * (1 + 2 + 2 + 2),
-        "blocks": frames * nblk * ((16 if fmt == "uastc" else 4) + 64),          # UASTC: 16 B block in; ETC1S: 2x u16 indices in; 64 B RGBA out
+        "blocks": frames * nblk * ((16 if fmt == "uastc" else 4) + {"rgba32": 64, "etc1": 8, "bc7": 16}[target]),   # UASTC: 16 B block in; ETC1S: 2x u16 indices in; 64 B RGBA / 16 B BC7 / 8 B ETC1 out
     }
     return g, t
 
@@ -309,30 +343,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--window-segments", type=int, default=0, help="override the workload's window size (segments per library call)")
-    ap.add_argument("--gather", action="store_true", help="N>1: also time the optional final NCCL all-gather of decoded geometry (first <=64 frames of the last window per rank)")
+    ap.add_argument("--window-segments", type=int, default=0, help="decode the (shard of the) sequence in windows of this many segments instead of at once")
+    ap.add_argument("--texture-target", default="rgba32", choices=sorted(TARGETS), help="output texture format (rgba32 = the parity target)")
+    ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather of the decoded shards (then a step is the decode alone)")
+    ap.add_argument("--no-weak", action="store_true", help="N>1: skip the weak-scaling side figure (every rank decoding a whole sequence of its own)")
+    ap.add_argument("--no-extra-targets", action="store_true", help="skip the short side pass with the BC7 texture target")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     W = dict(WORKLOADS[args.workload])
     if args.window_segments > 0:
         W["window_segments"] = args.window_segments
-    # Pinned host memory of the e2e path: every window ctx holds its own result buffers (C3: 28 GB of results + 5 GB of staged inputs
-    # per rank).  If the host cannot hold that for every rank, the windows share one set of result buffers and the e2e pass runs
-    # them one after the other (the resident pass keeps running them concurrently).
-    low_host_memory = False
-    try:
-        import psutil
-        low_host_memory = W["fmt"] == "uastc" and W["frames"] >= 500 and psutil.virtual_memory().available / max(1, world) < 48e9
-    except Exception:
-        pass
-    if os.environ.get("UVOL_BENCH_LOW_HOST_MEMORY"):
-        low_host_memory = os.environ["UVOL_BENCH_LOW_HOST_MEMORY"] == "1"
-    frames, verts, tex, seq, seed = W["frames"], W["verts"], W["tex"], W["seq"], W["seed"]
+    frames, seq = W["frames"], W["seq"]
     ncores = os.cpu_count() or 1
     if W["fmt"] == "corto":
         return bench_v1(args, W, rank, world, local)
-    workload_name = f"{W['label']} (synthetic, tools/synth seed {seed})"
 
     # ------------------------------------------------------------------ reference arm (CPU oracle)
     if args.impl == "reference":
@@ -348,8 +373,9 @@ def main():
         dt = time.perf_counter() - t0
         nfr = len(sd) * args.steps; fps = nfr / dt
         line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
-                "data": "synthetic", "config": {"workload": workload_name, "frames_per_step": len(sd), "segments_per_step": len(sk)},
+                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "int32+f32",
+                "data": "real fixtures" if args.workload == "liam" else "synthetic", "config": workload_config(args.workload, W, info, args.gpus, len(ktx), "rgba32"),
+                "sample_frames_per_step": len(sd), "sample_segments_per_step": len(sk),
                 "mverts_per_s": pts / dt / 1e6, "mtexels_per_s": tx / dt / 1e6,
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": "port",
                                  "sample": f"{len(sd)} frames + {len(sk)} segments of the workload per step, {ncores} threads, oracle/liboracle.so (CPU restatement of Draco 1.4.3 / Basis decode; upstream binaries unavailable)"},
@@ -364,16 +390,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     uv = importlib.import_module("universal-volumetric_b200")
-    drc, ktx, info = make_workload(args.workload, rank)
-    windows = make_windows(drc, ktx, seq, W["window_segments"])
-    ctxs = [uv.Context(local, profiling=True) for _ in windows]
-    for c in ctxs[1:]:
-        c.share_arenas(ctxs[0])
-        if low_host_memory:
-            c.share_host_outputs(ctxs[0])
-    players = [uv.V2Player(c) for c in ctxs]
-    ctx = ctxs[0]
-    n_k = len(ktx)
+    from concurrent.futures import ThreadPoolExecutor
+    drc_all, ktx_all, info = make_workload(args.workload, 0)            # ONE sequence, the same on every rank
+    n_seg_all = len(ktx_all)
+    f0, f1, s0, s1 = uv.shard_v2(frames, seq, n_seg_all, world, rank)   # this rank's block of whole segments and the frames they cover
+    peak, peak_src = measured_peak()
 
     def barrier():
         if world > 1:
@@ -390,101 +411,134 @@ def main():
             acc["stages"][k] = acc["stages"].get(k, 0.0) + v
         return acc
 
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(len(windows))
+    class Runner:
+        """The (shard of the) sequence resident on this GPU: one ctx per window (normally one window)."""
 
-    def one_window(args_):
-        w, resident = args_
-        p, c, (wd, wk) = players[w], ctxs[w], windows[w]
-        g, t = p.replay_step_raw(len(wd), len(wk), uv.MEM_DEVICE) if resident else p.decode_step_raw(wd, wk, uv.MEM_HOST)
-        a, b = c.stats(0, combined=True), c.stats(1, combined=True)
-        bad = sum(x.status != 0 for x in g[:len(wd)]) + sum(x.status != 0 for x in t[:len(wk)])
-        return a, b, (sum(x.num_points for x in g[:len(wd)]), sum(x.num_faces for x in g[:len(wd)]), sum(x.width * x.height * x.layers for x in t[:len(wk)]), bad)
+        def __init__(self, drc, ktx, target):
+            self.windows = make_windows(drc, ktx, seq, W["window_segments"])
+            self.ctxs = [uv.Context(local, profiling=True, texture_target=TARGETS[target]) for _ in self.windows]
+            self.players = [uv.V2Player(c) for c in self.ctxs]
+            self.pool = ThreadPoolExecutor(len(self.windows))
+            self.last = [None] * len(self.windows)
 
-    def run_step(resident):
-        """One pass over the sequence: every window is driven by its own host thread (ctypes releases the GIL); the library hands the
-        shared phase-2 scratch from window to window, so the other windows' phase 1 and result copies overlap it.  Returns the summed
-        statistics, the device time spanned by the whole step (first kernel to last kernel, CUDA events) and counts."""
-        sg = st = None; tot = [0, 0, 0, 0]
-        jobs_ = [(w, resident) for w in range(len(windows))]
-        for a, b, cnt in (pool.map(one_window, jobs_) if resident or not low_host_memory else map(one_window, jobs_)):
-            sg = merge(sg, a); st = merge(st, b); tot = [x + y for x, y in zip(tot, cnt)]
-        return sg, st, uv.span_ms(ctxs), tuple(tot)
+        def _one(self, a):
+            w, resident = a
+            p, c, (wd, wk) = self.players[w], self.ctxs[w], self.windows[w]
+            g, t = p.replay_step_raw(len(wd), len(wk), uv.MEM_DEVICE) if resident else p.decode_step_raw(wd, wk, uv.MEM_HOST)
+            self.last[w] = (g, len(wd), t, len(wk))
+            a_, b_ = c.stats(0, combined=True), c.stats(1, combined=True)
+            bad = sum(x.status != 0 for x in g[:len(wd)]) + sum(x.status != 0 for x in t[:len(wk)])
+            return a_, b_, (sum(x.num_points for x in g[:len(wd)]), sum(x.num_faces for x in g[:len(wd)]), sum(x.width * x.height * x.layers for x in t[:len(wk)]), bad)
 
-    # warm-up (also uploads the batch that the resident steps replay)
-    for _ in range(max(args.warmup, 1)):
-        sg, st, _, (P_total, F_total, texels, bad) = run_step(False)
-    assert bad == 0, "decode failed on the bench workload"
-    for _ in range(max(args.warmup, 1)):
-        run_step(True)
+        def step(self, resident):
+            """One pass over the shard.  Returns the summed statistics, the device time spanned (first kernel to last kernel, CUDA events) and counts."""
+            sg = st = None; tot = [0, 0, 0, 0]
+            for a_, b_, cnt in self.pool.map(self._one, [(w, resident) for w in range(len(self.windows))]):
+                sg = merge(sg, a_); st = merge(st, b_); tot = [x + y for x, y in zip(tot, cnt)]
+            return sg, st, uv.span_ms(self.ctxs), tuple(tot)
 
+        def close(self):
+            for c in reversed(self.ctxs):
+                c.close()
+
+    def measure(runner, steps, warmup, with_gather):
+        """warm-up, `steps` resident steps (device-timed; + gather), `steps` end-to-end steps (wall clock).  -> dict"""
+        for _ in range(max(warmup, 1)):
+            sg, st, _, (P_total, F_total, texels, bad) = runner.step(False)
+        assert bad == 0, "decode failed on the bench workload"
+        garena = [None]
+
+        def gather_once():
+            # the whole decoded shard (geometry and textures) of the last resident step, from the library's device buffers
+            g, ng, t, nt = runner.last[-1] if len(runner.windows) == 1 else (None, 0, None, 0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            G = uv.gather.all_gather_shard(g, ng, t, nt, f"cuda:{local}", arena=garena[0])
+            e1.record(); torch.cuda.synchronize()
+            garena[0] = G["arena"]
+            return e0.elapsed_time(e1), G
+        for _ in range(max(warmup, 1)):
+            runner.step(True)
+            if with_gather:
+                gather_once()
+        dev_ms = gat_ms = 0.0; launches = 0; stage_acc = {}; G = None
+        barrier(); t0 = time.perf_counter()
+        for _ in range(steps):
+            runner.ctxs[0].flush_l2()
+            sg, st, dms, _ = runner.step(True)
+            dev_ms += dms; launches += sg["kernel_launches"] + st["kernel_launches"]
+            for k, v in list(sg["stages"].items()) + [("tex_" + k, v) for k, v in st["stages"].items()]:
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+            if with_gather:
+                gm, G = gather_once(); gat_ms += gm
+        barrier(); wall_resident = time.perf_counter() - t0
+        e2e_s = 0.0
+        barrier()
+        for _ in range(steps):
+            runner.ctxs[0].flush_l2()
+            t1 = time.perf_counter(); sg2, st2, _, _ = runner.step(False); e2e_s += time.perf_counter() - t1
+            launches += sg2["kernel_launches"] + st2["kernel_launches"]
+        barrier()
+        return dict(sg=sg, st=st, sg2=sg2, st2=st2, dev_ms=dev_ms, gat_ms=gat_ms, e2e_s=e2e_s, launches=launches, stage_acc=stage_acc, wall_resident=wall_resident,
+                    P_total=P_total, F_total=F_total, texels=texels, G=G)
+
+    def maxr(*vals):
+        if world == 1:
+            return list(vals)
+        v = torch.tensor(list(vals), device="cuda", dtype=torch.float64); dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return [float(x) for x in v]
+
+    def sumr(*vals):
+        if world == 1:
+            return list(vals)
+        v = torch.tensor(list(vals), device="cuda", dtype=torch.float64); dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        return [float(x) for x in v]
+
+    # ---- headline: this rank's shard, resident + end to end (+ gather)
+    with_gather = world > 1 and not args.no_gather and not W["window_segments"]
+    runner = Runner(drc_all[f0:f1], ktx_all[s0:s1], args.texture_target)
     clocks = ClockSampler(local); clocks.start()
-    # ---- timed: resident inputs (value)
-    dev_ms = 0.0; launches = 0; stage_acc = {}
-    barrier(); t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.flush_l2()
-        sg, st, dms, _ = run_step(True)
-        dev_ms += dms; launches += sg["kernel_launches"] + st["kernel_launches"]
-        for k, v in list(sg["stages"].items()) + [("tex_" + k, v) for k, v in st["stages"].items()]:
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
-    barrier(); wall_resident = time.perf_counter() - t0
-    nwin = len(windows)
-    # ---- timed: end to end through the C ABI with host buffers (e2e)
-    e2e_s = 0.0
-    barrier()
-    for _ in range(args.steps):
-        ctx.flush_l2()
-        t1 = time.perf_counter(); sg, st, _, _ = run_step(False); e2e_s += time.perf_counter() - t1
-        launches_e2e = sg["kernel_launches"] + st["kernel_launches"]
-    barrier()
+    M = measure(runner, args.steps, args.warmup, with_gather)
     clk = clocks.stop()
-    h2d = sg["bytes_in"] + st["bytes_in"]; d2h = sg["bytes_out"] + st["bytes_out"]
     gather_info = None
-    if world > 1 and args.gather:
-        # optional final gather (SURVEY 8e): not part of the metric; decoded buffers of the last window go device -> device over NCCL
-        wd, wk = windows[-1]
-        g, t = players[-1].replay_step_raw(len(wd), len(wk), uv.MEM_DEVICE)
-        ng = min(len(wd), 64)
-        uv.gather.all_gather_geometry(g, ng, f"cuda:{local}")                                  # warm-up (communicator set-up)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier(); e0.record()
-        tables, arenas = uv.gather.all_gather_geometry(g, ng, f"cuda:{local}")
-        e1.record(); torch.cuda.synchronize()
-        _, runs = uv.gather.geometry_table(g, ng)
-        mine = uv.gather.pack_runs(runs, f"cuda:{local}"); nbytes = int(mine.numel())
-        same = bool(torch.equal(arenas[rank][:nbytes], mine))
-        sums = arenas[:, : arenas.shape[1] // 8 * 8].view(torch.int64).sum(dim=1)                 # every rank must hold identical copies
-        lo, hi = sums.clone(), sums.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        gms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64); dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        gather_info = {"frames_per_rank": ng, "bytes_per_rank": int(nbytes), "ms": float(gms[0]), "recv_gbs_per_gpu": nbytes * (world - 1) / (float(gms[0]) * 1e-3) / 1e9,
-                       "own_slot_identical": same, "all_ranks_identical": bool(torch.equal(lo, hi)), "backend": "nccl all_gather_into_tensor on the library's device buffers"}
-    # max over ranks
-    if world > 1:
-        v = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(v, op=dist.ReduceOp.MAX); dev_ms, e2e_s = float(v[0]), float(v[1])
-    total_frames = frames * world * args.steps
-    value = total_frames / (dev_ms / 1e3); e2e = total_frames / e2e_s
+    if with_gather:
+        G = M["G"]
+        # every rank must now hold the same bytes: compare a checksum of the gathered arena across ranks
+        ssum = G["arena"][: G["arena"].numel() // 8 * 8].view(torch.int64).sum().reshape(1)
+        lo, hi = ssum.clone(), ssum.clone(); dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        gather_info = {"what": "whole decoded shard of every rank (geometry index / position / normal / uv + texture layers), gather.all_gather_shard: per-rank sized broadcasts from the library's device buffers",
+                       "bytes_received_per_gpu": int(sum(G["bytes"]) - G["bytes"][rank]), "bytes_total": int(sum(G["bytes"])), "all_ranks_identical": bool(torch.equal(lo, hi))}
+    dev_ms, gat_ms, e2e_s = maxr(M["dev_ms"], M["gat_ms"], M["e2e_s"])
+    P_all, F_all, tex_all, bin_g, bin_t, bout_g, bout_t, bout_g2, bout_t2, launches_all = sumr(M["P_total"], M["F_total"], M["texels"], M["sg"]["bytes_in"], M["st"]["bytes_in"], M["sg"]["bytes_out"], M["st"]["bytes_out"],
+                                                                                               M["sg2"]["bytes_out"], M["st2"]["bytes_out"], M["launches"])
+    step_ms = (dev_ms + gat_ms) / args.steps
+    value = frames / (step_ms / 1e3); e2e = frames * args.steps / e2e_s
+    if with_gather:
+        gather_info["ms_per_step"] = gat_ms / args.steps
+        gather_info["recv_gbs_per_gpu"] = gather_info["bytes_received_per_gpu"] / (gat_ms / args.steps * 1e-3) / 1e9 if gat_ms > 0 else None
+    scratch_gb = (M["sg"]["scratch_bytes"] + M["st"]["scratch_bytes"]) / 1e9
+    my_frames = f1 - f0
 
-    # ---- roofline per stage
-    peak, peak_src = measured_peak()
-    gb, tb = stage_bytes(info, P_total, frames, sg["bytes_in"], st["bytes_in"], W["fmt"])
+    # ---- roofline per stage (this rank's shard; ranks hold equal shares)
+    sg, st, stage_acc = M["sg"], M["st"], M["stage_acc"]
+    gb, tb = stage_bytes(info, M["P_total"], max(my_frames, 1), sg["bytes_in"], st["bytes_in"], W["fmt"], args.texture_target)
     stages = {}
     for k, ms in stage_acc.items():
-        nbytes = gb.get(k.replace("(s1)", "")) if not k.startswith("tex_") else tb.get(k[4:])
         per = ms / args.steps
+        if per < 0.02 and k not in ("h2d", "d2h"):
+            continue                                                                   # stages that did not launch for this workload (e.g. the ETC1S entropy stages on UASTC input)
+        nbytes = gb.get(k.replace("(s1)", "")) if not k.startswith("tex_") else tb.get(k[4:])
         stages[k] = {"ms": round(per, 4), "share": round(ms / sum(stage_acc.values()), 4)}
         if nbytes and per > 0:
             stages[k]["gbs"] = round(nbytes / (per * 1e-3) / 1e9, 2); stages[k]["frac"] = round(stages[k]["gbs"] / peak, 5)
-    kernel_stages = {k: v for k, v in stages.items() if k not in ("h2d", "d2h", "tex_h2d", "tex_d2h", "counts_readback")}
+    kernel_stages = {k: v for k, v in stages.items() if k not in ("h2d", "d2h", "tex_h2d", "tex_d2h")}
     main_stream = {k: v for k, v in kernel_stages.items() if "(s1)" not in k}          # side-stream spans include waiting for the main stream
     ksum = sum(v["ms"] for v in kernel_stages.values()) or 1.0
     for v in kernel_stages.values():
         v["share_of_kernel_time"] = round(v["ms"] / ksum, 4)          # comparable with the ncu launch-list shares
     traffic = None
     import glob
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):        # measured DRAM bytes per launch (ncu --set full), newest last
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02*_traffic.json"))):        # measured DRAM bytes per launch (ncu --set full), newest last
         try:
             tr = json.load(open(path))
             if tr.get("workload") == args.workload:
@@ -493,50 +547,87 @@ def main():
             pass
     dom = max(main_stream, key=lambda k: main_stream[k]["ms"])
     dom_bytes = gb.get(dom.replace("(s1)", "")) if not dom.startswith("tex_") else tb.get(dom[4:])
+    nwin = len(runner.windows)
+    tr_dom = (traffic or {}).get(dom.replace("(s1)", ""))
+    if tr_dom and traffic.get("frames"):
+        tr_dom = tr_dom * my_frames / traffic["frames"]                                # the capture decodes fewer frames per launch than the bench: scaled per frame
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernel_stages[dom].get("gbs"), "peak": peak, "unit": "GB/s", "frac": kernel_stages[dom].get("frac"),
-            "traffic": (traffic or {}).get(dom.replace("(s1)", "")), "traffic_source": (traffic or {}).get("source"), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes and dom_bytes / nwin, "ms_per_launch": kernel_stages[dom]["ms"] / nwin, "launches_per_step": nwin,
-            "note": "dominant stage is a latency-bound serial walk (one warp per frame); HBM-bound stages are listed in `stages`"}
-    step_bytes = sg["bytes_in"] + st["bytes_in"] + sg["bytes_out"] + st["bytes_out"]
-    pipeline = {"bytes_per_frame": step_bytes / frames, "achieved_gbs": step_bytes * world * args.steps / (dev_ms / 1e3) / 1e9}
+            "traffic": tr_dom, "traffic_source": (traffic or {}).get("source"), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes and dom_bytes / nwin,
+            "ms_per_launch": kernel_stages[dom]["ms"] / nwin, "launches_per_step": nwin,
+            "note": "dominant stage is a latency-bound serial walk (one warp per frame and table); the HBM-bound stages (expand, blocks, face_records) are listed in `stages`"}
+    step_bytes = bin_g + bin_t + bout_g + bout_t
+    pipeline = {"bytes_per_frame": step_bytes / frames, "achieved_gbs": step_bytes / (dev_ms / args.steps / 1e3) / 1e9}
     pipeline["frac"] = pipeline["achieved_gbs"] / (peak * world)
+    windows_cfg = [len(wd) for wd, _ in runner.windows]
+    runner.close(); del runner
 
-    line = None
+    # ---- side figures
+    extra = {}
+    if args.texture_target == "rgba32" and not args.no_extra_targets and W["fmt"] in ("uastc", "etc1s"):
+        try:       # the target the reference itself picks on desktop NVIDIA (BC7, KTX2Loader.js:602-604): 4x fewer texture bytes cross PCIe
+            r2 = Runner(drc_all[f0:f1], ktx_all[s0:s1], "bc7")
+            M2 = measure(r2, max(2, min(args.steps, 3)), 1, False)
+            d2, e2 = maxr(M2["dev_ms"], M2["e2e_s"]); k2 = max(2, min(args.steps, 3))
+            o2 = sumr(M2["sg2"]["bytes_out"] + M2["st2"]["bytes_out"])[0]
+            extra["bc7_target"] = {"value": frames * k2 / (d2 / 1e3), "e2e": frames * k2 / e2, "unit": "frames/s", "steps": k2, "d2h_bytes_per_step": o2,
+                                   "note": "same sequence, UVOL_TEX_BC7 output (decode only, no gather); BC7 blocks are validated by an independent BC7 decoder, not bit-matched to basisu (DESIGN.md)"}
+            r2.close(); del r2
+        except Exception as ex:                                       # never lose the headline to a side figure
+            extra["bc7_target"] = {"error": str(ex)[:200]}
+    if world > 1 and not args.no_weak:
+        try:       # last round's weak-scaling figure: every rank decodes a whole sequence of its own
+            dw, kw, _ = make_workload(args.workload, rank)
+            r3 = Runner(dw, kw, args.texture_target)
+            M3 = measure(r3, 2, 1, False)
+            d3, e3 = maxr(M3["dev_ms"], M3["e2e_s"])
+            extra["weak"] = {"value": frames * world * 2 / (d3 / 1e3), "e2e": frames * world * 2 / e3, "unit": "frames/s", "steps": 2, "frames_per_gpu": frames,
+                             "note": "every rank decodes its own whole sequence, no gather (round-1 definition)"}
+            r3.close(); del r3
+        except Exception as ex:
+            extra["weak"] = {"error": str(ex)[:200]}
+
     if rank == 0:
         # ---- cpu baseline on a bounded sample (rank 0, N=1 only)
         cpu = None
         if world == 1:
-            nseg = min(ncores, len(ktx))
-            sd, sk = cpu_sample(drc, ktx, seq, nseg)
+            nseg = min(ncores, n_seg_all)
+            sd, sk = cpu_sample(drc_all, ktx_all, seq, nseg)
             tg, tt, p, x = cpu_oracle_run(sd, sk, ncores)          # probe
             per_seg = max(tg + tt, 1e-3) / nseg
-            nseg = int(max(min(ncores, len(ktx)), min(len(ktx), args.cpu_seconds / per_seg)))
-            sd, sk = cpu_sample(drc, ktx, seq, nseg)
+            nseg = int(max(min(ncores, n_seg_all), min(n_seg_all, args.cpu_seconds / per_seg)))
+            sd, sk = cpu_sample(drc_all, ktx_all, seq, nseg)
             tg, tt, p, x = cpu_oracle_run(sd, sk, ncores)
             cpu = {"value": len(sd) / (tg + tt), "unit": "frames/s", "cores": ncores, "kind": "port",
                    "sample": f"first {len(sd)} frames + {len(sk)} segments of the workload, {ncores} threads (thread pool over frames/segments), oracle/liboracle.so",
                    "geometry_ms_per_frame_per_core": tg / len(sd) * 1e3 * min(ncores, len(sd)), "texture_ms_per_frame_per_core": tt / len(sd) * 1e3 * min(ncores, len(sk))}
+        # scaling efficiency against this repo's own committed N=1 line of the same workload, when there is one (the driver computes its own)
+        eff = None
+        try:
+            n1 = json.load(open(os.path.join(ROOT, "profiles", f"r02_bench_{args.workload}.json")))
+            if world > 1 and n1.get("n_gpus") == 1:
+                eff = {"value": value / (world * n1["value"]), "e2e": e2e / (world * n1["e2e"]["value"]), "against": f"profiles/r02_bench_{args.workload}.json (N=1: {n1['value']:.0f} / {n1['e2e']['value']:.0f} frames/s)"}
+        except Exception:
+            pass
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
-                "data": "synthetic",
-                "config": {"workload": workload_name, "frames_per_gpu": frames, "segments_per_gpu": n_k, "verts": info["verts"], "faces": info["faces"],
-                           "points_per_frame": P_total / frames, "distinct_geometry_frames": info["distinct_geometry"], "distinct_texture_segments": info["distinct_textures"],
-                           "windows": [len(wd) for wd, _ in windows], "windows_concurrent": len(windows) > 1, "e2e_windows_sequential_low_host_memory": low_host_memory,
-                           "scratch_gb_largest_window": round((sg["scratch_bytes"] + st["scratch_bytes"]) / 1e9, 2),
-                           "l2": "flushed between timed iterations (256 MiB memset); every window's working set is far larger than L2",
-                           "parallelism": f"frames sharded, {world} rank(s), no data-path collective",
-                           "host": {"cpus_of_rank0": rank_cpus, "staging_threads": int(os.environ.get("UVOL_STAGING_THREADS", "0"))}},
-                "mverts_per_s": P_total * world * args.steps / (dev_ms / 1e3) / 1e6, "mtexels_per_s": texels * world * args.steps / (dev_ms / 1e3) / 1e6,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "int32+f32",
+                "data": "real fixtures" if args.workload == "liam" else "synthetic",
+                "config": workload_config(args.workload, W, info, world, n_seg_all, args.texture_target),
+                "run": {"frames_this_rank": my_frames, "segments_this_rank": s1 - s0, "points_per_frame": P_all / frames,
+                        "windows": windows_cfg, "scratch_gb": round(scratch_gb, 2), "scratch_mb_per_frame": round(scratch_gb * 1e3 / max(my_frames, 1), 1),
+                        "decode_ms_per_step": dev_ms / args.steps, "gather_ms_per_step": gat_ms / args.steps if with_gather else None,
+                        "value_note": "inputs resident in HBM; CUDA events from the first to the last kernel of the step (max over ranks), plus the gather (CUDA events) when N > 1",
+                        "host": {"cpus_of_rank0": rank_cpus, "staging_threads": int(os.environ.get("UVOL_STAGING_THREADS", "0"))}},
+                "mverts_per_s": P_all / (dev_ms / args.steps / 1e3) / 1e6, "mtexels_per_s": tex_all / (dev_ms / args.steps / 1e3) / 1e6,
                 "roofline": roof, "pipeline_roofline": pipeline, "stages": stages,
                 "cpu_baseline": cpu,
-                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
-                        "path": "uvol_decode_v2_batch per window (geometry and texture streams concurrent), UVOL_MEM_HOST",
-                        "breakdown_ms_per_step": {"geo_host_parse": sg["host_parse_ms"], "geo_h2d": sg["h2d_ms"], "geo_kernels": sg["device_ms"], "geo_d2h": sg["d2h_ms"],
-                                                  "geo_call_total": sg["total_ms"], "tex_host_parse": st["host_parse_ms"], "tex_h2d": st["h2d_ms"], "tex_kernels": st["device_ms"], "tex_d2h": st["d2h_ms"]}},
-                "gather": gather_info, "gpu_launches": launches + launches_e2e * args.steps, "clocks": clk,
-                "wall_ms_per_step_resident": wall_resident / args.steps * 1e3, "workload_gen_s": info["gen_s"]}
+                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": bin_g + bin_t, "d2h_bytes_per_step": bout_g2 + bout_t2, "ms_per_step": e2e_s / args.steps * 1e3,
+                        "path": "uvol_decode_v2_batch on every rank's shard (geometry and texture streams concurrent), host buffers in, pinned host buffers out (UVOL_MEM_HOST); wall clock, max over ranks",
+                        "breakdown_ms_per_step_rank0": {"geo_host_parse": M["sg2"]["host_parse_ms"], "geo_h2d": M["sg2"]["h2d_ms"], "geo_kernels": M["sg2"]["device_ms"], "geo_d2h": M["sg2"]["d2h_ms"],
+                                                        "geo_call_total": M["sg2"]["total_ms"], "tex_host_parse": M["st2"]["host_parse_ms"], "tex_h2d": M["st2"]["h2d_ms"], "tex_kernels": M["st2"]["device_ms"], "tex_d2h": M["st2"]["d2h_ms"]}},
+                "gather": gather_info, "scaling_efficiency": eff, "gpu_launches": int(launches_all), "clocks": clk,
+                "wall_ms_per_step_resident": M["wall_resident"] / args.steps * 1e3, "workload_gen_s": info["gen_s"]}
+        line.update(extra)
         print(json.dumps(line))
-    for c in reversed(ctxs):
-        c.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

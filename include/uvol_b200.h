@@ -36,7 +36,7 @@ enum uvol_memory { UVOL_MEM_DEVICE = 0, UVOL_MEM_HOST = 1 };
  * src/lib/KTX2Loader.js:591-689).  RGBA32 is the parity target and the reference's own fallback (:682-687).  ETC1 is the
  * `etc1Supported` / opaque `etc2Supported` choice (:619-636; an RGB ETC2 texture of ETC1S content is its ETC1 blocks): 8 bytes per
  * 4x4 block in block raster order, layers back to back; opaque ETC1S sources only (others report UVOL_STATUS_UNSUPPORTED per item). */
-enum uvol_texture_format { UVOL_TEX_RGBA32 = 0, UVOL_TEX_ETC1 = 1 };
+enum uvol_texture_format { UVOL_TEX_RGBA32 = 0, UVOL_TEX_ETC1 = 1, UVOL_TEX_BC7 = 2 };
 
 /* Result of one geometry frame.  Replaces the Draco worker reply
  *   {type:'decode', geometry:{index:{array:Uint32Array(F*3)}, attributes:[{name, array:Float32Array(P*itemSize), itemSize}]}}
@@ -75,8 +75,27 @@ typedef struct uvol_stats {
     uint64_t scratch_bytes;
 } uvol_stats;
 
+/* Tunables of a context (SURVEY 5 "config / flags").  The reference takes constructor arguments only (bufferDuration = 4,
+ * intervalDuration = 2, src/Player.ts:50-51) and derives the texture target from the GPU's capabilities
+ * (src/lib/KTX2Loader.js:591-689); here they are one struct.  uvol_config_default() fills the defaults and then applies the
+ * environment overrides UVOL_TEXTURE_TARGET (rgba32 | etc1 | bc7), UVOL_CORTO_INDEX_U16, UVOL_STAGING_THREADS, UVOL_MAX_FACES,
+ * UVOL_MAX_TEXTURE_BYTES, UVOL_BUFFER_DURATION, UVOL_INTERVAL_DURATION. */
+typedef struct uvol_config {
+    uint32_t struct_size;            /* sizeof(uvol_config) */
+    uint32_t texture_target;         /* uvol_texture_format of uvol_decode_v2_batch and of sequences opened with uvol_open */
+    uint32_t corto_index_u16;        /* V1: narrow the index to u16 when nface < 65536, the web player's layout (src/V1/player.ts:292, corto.ts:675-680) */
+    uint32_t staging_threads;        /* host threads staging a large batch into pinned memory; 0 = min(8, cores / 2) */
+    uint64_t max_faces_per_frame;    /* resource limit per .drc / .crt (default 2^24): larger headers fail per item with UVOL_STATUS_UNSUPPORTED */
+    uint64_t max_texture_bytes;      /* resource limit per .ktx2 segment, decoded bytes (default 2^31) */
+    double buffer_duration_s;        /* playback: seconds decoded ahead of the clock (default 4) */
+    double interval_duration_s;      /* playback: seconds between prefetch rounds (default 2) */
+} uvol_config;
+void uvol_config_default(uvol_config *cfg);
+
 /* ---- context ------------------------------------------------------------------------------- */
-int uvol_create(int device, uvol_ctx **out);
+int uvol_create(int device, uvol_ctx **out);                                  /* = uvol_create_with_config(device, NULL, out) */
+int uvol_create_with_config(int device, const uvol_config *cfg, uvol_ctx **out);
+int uvol_get_config(const uvol_ctx *ctx, uvol_config *out);
 void uvol_destroy(uvol_ctx *ctx);
 const char *uvol_last_error(const uvol_ctx *ctx);
 int uvol_get_stats(const uvol_ctx *ctx, uvol_stats *out);

@@ -43,8 +43,23 @@ def test_geometry_all_fixtures(uv, ctx):
     files = fixture_drc()
     if not files:
         pytest.skip("full fixture set not staged (oracle/_ref/fixtures)")
-    blobs = [read(p) for p in files[::5]]
+    blobs = [read(p) for p in files]                                   # all 250 frames, one batch
     check_geometry(uv.DRACOLoader(ctx).decode_batch(blobs), blobs)
+
+
+def test_geometry_replan_paths(uv, monkeypatch):
+    """The count-sized arrays are laid out on the device from optimistic reservations.  Shrunk reservations force both re-plan
+    paths -- a frame whose attribute tables outgrow their capacity (full bounds, second run) and a batch that outgrows the
+    count-sized arenas (exact sizes, second run) -- and the results must not change."""
+    blobs = [read(p) for p in golden_drc()] + synth.make_sequence(2, 3000, 32, want_textures=False, seed=20260002)[0]
+    for var, val in (("UVOL_CAP_PERMILLE", "300"), ("UVOL_EST_PERMILLE", "400")):
+        monkeypatch.setenv(var, val)
+        c = uv.Context(0)
+        try:
+            check_geometry(uv.DRACOLoader(c).decode_batch(blobs), blobs)
+            check_geometry(uv.DRACOLoader(c).decode_batch(blobs[:2]), blobs[:2])      # arenas grown by the first call are reused
+        finally:
+            c.close(); monkeypatch.delenv(var)
 
 
 def test_texture_golden(uv, ctx):
@@ -60,7 +75,7 @@ def test_texture_all_fixtures(uv, ctx):
     files = fixture_ktx2()
     if not files:
         pytest.skip("full fixture set not staged (oracle/_ref/fixtures)")
-    blobs = [read(p) for p in files[::4]]
+    blobs = [read(p) for p in files]                                   # all 50 segments, one batch
     for r, b in zip(uv.KTX2Loader(ctx).transcode_batch(blobs), blobs):
         assert r["status"] == 0 and np.array_equal(r["data"], oracle_ktx2(b)["rgba"])
 

@@ -12,6 +12,77 @@
 
 int uvol_draco_parse(const uint8_t *data, size_t len, DracoFrame &f, std::vector<uint32_t> &aux);
 
+
+// ---- host emulation of the speculative traversal (k_traverse): 32 lanes as arrays, the warp collectives as loops.
+static int g_spec_check = 1; static long g_spec_steps[UVOL_MAX_ATTR_DATA + 1]; static long g_spec_faces = 0;
+extern "C" void draco_emu_spec(int enable, long *steps5, long *faces) { g_spec_check = enable; if (steps5) for (int i = 0; i <= UVOL_MAX_ATTR_DATA; i++) steps5[i] = g_spec_steps[i]; if (faces) *faces = g_spec_faces; }
+static void build_face_records(const TableView &tv, const int *lmc, int F, FaceRec *rec) {
+    for (int f = 0; f < F; f++) face_record(f, tv, lmc, rec[f]);
+    for (int f = 0; f < F; f++) {          // duplicate distances (k_face_dups)
+        const uint32_t mu = face_entry_tip(f, F, 1, tv), md = face_entry_tip(f, F, -1, tv); uint32_t du = 0, dd = 0;
+        if (mu != 0xffffffffu) for (int k = 1; k < 32; k++) if (face_entry_tip(f - k, F, 1, tv) == mu) { du = (uint32_t)k; break; }
+        if (md != 0xffffffffu) for (int k = 1; k < 32; k++) if (face_entry_tip(f + k, F, -1, tv) == md) { dd = (uint32_t)k; break; }
+        rec[f].meta |= (du << 4) | (dd << 9);
+    }
+}
+static int traverse_spec_emu(const FaceRec *rec, int F, uint8_t *fvis, int *v2d1, int *d2c, int *stk, int max_entries, uint32_t *out_n, long *steps) {
+    const int C = 3 * F; int n = 0, sp = 0, c = -1, fscan = 0, pdir = 1; *steps = 0;
+    for (;;) {
+        if (c < 0) {
+            bool scan = false;
+            for (;;) { if (sp == 0) { scan = true; break; } c = stk[sp - 1]; if (c < 0 || fvis[c / 3]) { sp--; c = -1; continue; } break; }
+            if (scan) {
+                int nf = fscan; while (nf < F && fvis[nf]) nf++;
+                if (nf >= F) break;
+                fscan = nf; c = 3 * nf; stk[0] = c; sp = 1;
+                const int vn = rec[nf].v[1], vp = rec[nf].v[2];
+                if (!v2d1[vn]) { if (n >= max_entries) return UVOL_ERR_CORRUPT; v2d1[vn] = ++n; d2c[n - 1] = c + 1; }
+                if (!v2d1[vp]) { if (n >= max_entries) return UVOL_ERR_CORRUPT; v2d1[vp] = ++n; d2c[n - 1] = c + 2; }
+            }
+        }
+        if (c >= C) return UVOL_ERR_CORRUPT;
+        ++*steps;
+        const int f0 = c / 3, k0 = c - 3 * f0;
+        TravLane L[32]; bool selfopen[32], vis[32]; int act[32], nx[32];
+        for (int l = 0; l < 32; l++) {
+            const int fi = f0 + l * pdir; const bool inr = fi >= 0 && fi < F;
+            const FaceRec z{}; const FaceRec &r = inr ? rec[fi] : z;
+            L[l] = trav_lane(r.v[0], r.v[1], r.v[2], r.o[0], r.o[1], r.o[2], r.meta, fi, l == 0 ? k0 : -1, pdir, inr);
+            selfopen[l] = L[l].ci >= 0 && !fvis[fi];
+        }
+        for (int l = 0; l < 32; l++) {
+            const bool dup = l > 0 && (L[l].v == L[0].v || (L[l].pd != 0 && (int)L[l].pd < l));
+            vis[l] = L[l].ci >= 0 && (v2d1[L[l].v] != 0 || dup);
+            bool fr = true, fl = true;
+            if (L[l].ci >= 0) {
+                if (L[l].rc >= 0) { const int rf = L[l].rc / 3, k = (rf - f0) * pdir; fr = fvis[rf] || (k >= 0 && k <= l); }
+                if (L[l].lc >= 0) { const int lf = L[l].lc / 3, k = (lf - f0) * pdir; fl = fvis[lf] || (k >= 0 && k <= l); }
+            }
+            trav_decide(vis[l], L[l].ob, fr, fl, L[l].rc, L[l].lc, &act[l], &nx[l]);
+        }
+        int m = 31;
+        for (int l = 0; l < 32; l++) { const bool trans = act[l] == 0 && nx[l] >= 0 && l < 31 && nx[l] == L[l + 1].ci && selfopen[l + 1]; if (!trans) { m = l; break; } }
+        if (getenv("EMU_TRAV_SEQ")) { static long cnt2 = 0; if (cnt2 > 20000 && cnt2 < 20080) fprintf(stderr, "step f0=%d c=%d pdir=%d m=%d act=%d nx=%d(face %d)\n", f0, c, pdir, m, act[m], nx[m], nx[m] / 3); cnt2++; }
+        if (getenv("EMU_TRAV_DEBUG")) {
+            static long hist[8]; static long cnt = 0; int why;
+            if (m == 31) why = 0; else if (act[m] == 1) why = 1; else if (act[m] == 2) why = 2; else if (nx[m] < 0) why = 3;
+            else { const int nf = nx[m] / 3, fm = f0 + m * pdir; if (nf == fm + pdir) why = (nx[m] == L[m + 1].ci) ? 4 /*next not open*/ : 5 /*adjacent face, other corner*/; else if (nf == fm - pdir) why = 6; else why = 7; }
+            hist[why]++; if (++cnt % 5000 == 0) fprintf(stderr, "steps %ld: full %ld pop %ld push %ld bad %ld nextclosed %ld othercorner %ld reverse %ld jump %ld\n", cnt, hist[0], hist[1], hist[2], hist[3], hist[4], hist[5], hist[6], hist[7]);
+        }
+        if (!selfopen[0]) return UVOL_ERR_CORRUPT;
+        for (int l = 0; l <= m; l++) {
+            fvis[f0 + l * pdir] = 1;
+            if (!vis[l]) { if (n >= max_entries) return UVOL_ERR_CORRUPT; v2d1[L[l].v] = n + 1; d2c[n] = L[l].ci; n++; }
+        }
+        if (act[m] == 0) { c = nx[m]; if (c < 0) return UVOL_ERR_CORRUPT; }
+        else if (act[m] == 1) { sp--; c = -1; }
+        else { stk[sp - 1] = L[m].lc; stk[sp] = nx[m]; sp++; c = nx[m]; }
+        if (c >= 0) { const int nf = c / 3, fm = f0 + m * pdir; if (nf == fm + 1) pdir = 1; else if (nf == fm - 1) pdir = -1; }
+    }
+    *out_n = (uint32_t)n;
+    return UVOL_OK;
+}
+
 extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_points, uint32_t *num_faces,
                                 uint32_t **index, float **position, float **normal, float **uv) {
     std::vector<DracoFrame> frames(1); std::vector<uint32_t> aux;
@@ -70,10 +141,9 @@ extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_p
     for (int v = 0; v < V; v++) pcnt[v] = point_fan(v, m.opp, m.c2v, m.lmc, m.hole, nad, vos, ac2v, pfirst, nullptr, nullptr, 0, 0, F, &err);
     { int run = 0; for (int v = 0; v < V; v++) { int c = pcnt[v]; pcnt[v] = run; run += c; } cnt.num_points = (uint32_t)run; }
     if (err) return UVOL_ERR_CORRUPT;
-    // ---- phase 2
+    // ---- phase 2 (count-sized arrays: the same planning function the device planner kernel runs)
     draco_plan_phase2(frames, &cnt, pl);
-    draco_plan_rebase_traversal(frames, pl.scratch2 + 256);      // one host buffer: phase-2 scratch, then the traversal records
-    std::vector<uint8_t> scratch2(pl.scratch2 + 256 + pl.tscratch + 256), zs2(pl.zscratch2 + 256, 0), outb(pl.out + 256);
+    std::vector<uint8_t> scratch2(pl.scratch2 + 256), zs2(pl.zscratch2 + 256, 0), outb(pl.out + 256);
     uint8_t *S2 = scratch2.data(), *Z2 = zs2.data(), *O = outb.data();
     const int P = (int)cnt.num_points;
     uint32_t *c2p = (uint32_t *)(O + f.out_index); int *p2c = (int *)(S2 + f.o_p2c);
@@ -85,8 +155,17 @@ extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_p
         tv[t] = (t == 0) ? TableView{m.opp, m.c2v, nullptr, nullptr, nullptr} : TableView{m.opp, m.c2v, Z + f.o_eos[t - 1], ac2v[t - 1], vos[t - 1]};
         const int maxe = (int)(t == 0 ? cnt.num_vertex_slots : cnt.attr_vertices[t - 1]);
         std::vector<uint8_t> fvis_t(F + 4, 0);
-        rc = traverse_table(tv[t], m.lmc, F, fvis_t.data(), (int *)(Z2 + f.o_v2d[t]), (int *)(S2 + f.o_d2c[t]), (int *)(S2 + f.o_tstack[t]), maxe, &cnt.entries[t]);
+        rc = traverse_table(tv[t], m.lmc, F, fvis_t.data(), (int *)(Z2 + f.o_v2d[t]), (int *)(S2 + f.o_d2c[t]), (int *)(S + f.o_tstack[t]), maxe, &cnt.entries[t]);
         if (rc) return rc;
+        if (g_spec_check) {          // the speculative 32-lane traversal of k_traverse, emulated lane by lane on the same records: must give the same order
+            std::vector<FaceRec> rec(F + 2); build_face_records(tv[t], m.lmc, F, rec.data());
+            std::vector<uint8_t> fv2(F + 16, 0); std::vector<int> v2d2(maxe + 4, 0), d2c2(maxe + 4, 0), stk2(F + 8);
+            uint32_t n2 = 0; long steps = 0;
+            rc = traverse_spec_emu(rec.data(), F, fv2.data(), v2d2.data(), d2c2.data(), stk2.data(), maxe, &n2, &steps);
+            if (rc) return rc;
+            if (n2 != cnt.entries[t] || memcmp(d2c2.data(), S2 + f.o_d2c[t], (size_t)n2 * 4) || memcmp(v2d2.data(), Z2 + f.o_v2d[t], (size_t)maxe * 4)) return -77;
+            g_spec_steps[t] = steps; g_spec_faces = F;
+        }
     }
     // attribute symbol runs + aux bits
     for (int j = 0; j < f.nattr; j++) {
@@ -98,33 +177,34 @@ extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_p
         for (uint32_t b = 0; b < 256; b++) bucket[b] = (uint16_t)rans_bucket_symbol(cum.data(), s.alphabet, b << (s.pb - 8));
         RansTables t{cum.data(), bucket.data(), s.alphabet, s.pb};
         const int positive = a.pred != -2 && (a.xform == 2 || a.xform == 3);
-        rc = rans_decode_run(file + s.data_off, s.data_len, t, n * a.vnc, positive ? 2 : 1, S2 + f.o_corr[j]); if (rc) return rc;
+        if (n * (uint32_t)a.vnc > f.corr_cap[j]) return UVOL_ERR_FRAME_CAPACITY;
+        rc = rans_decode_run(file + s.data_off, s.data_len, t, n * a.vnc, positive ? 2 : 1, S + f.o_corr[j]); if (rc) return rc;
         if (a.pred == 5 || a.pred == 6) {
             Rabs r; if (!rabs_init(r, file, a.aux_bits)) return UVOL_ERR_CORRUPT;
-            uint8_t *o = S2 + f.o_auxbits[j];
+            uint8_t *o = S + f.o_auxbits[j];
             if (a.pred == 5) { if ((uint32_t)a.num_orient > n) return UVOL_ERR_CORRUPT; int last = 1; for (int k = 0; k < a.num_orient; k++) { if (!rabs_bit(r)) last = !last; o[k] = (uint8_t)last; } }
             else for (uint32_t k = 0; k < n; k++) o[k] = (uint8_t)rabs_bit(r);
         }
     }
     // prediction reversal: position-like first, then uv / normal
     const DracoAttr &pa = f.attr[f.pos_attr];
-    const int *pos_v2d1 = (int *)(Z2 + f.o_v2d[0]); const int32_t *posq = (int32_t *)(S2 + f.o_val_attr[f.pos_attr]);
+    const int *pos_v2d1 = (int *)(Z2 + f.o_v2d[0]); const int32_t *posq = (int32_t *)(S + f.o_corr[f.pos_attr]);
     for (int pass = 0; pass < 2; pass++) for (int j = 0; j < f.nattr; j++) {
         const DracoAttr &a = f.attr[j]; if (f.o_corr[j] == UVOL_NONE) continue;
         const int t = a.table + 1, n = (int)cnt.entries[t];
-        const int32_t *corr = (int32_t *)(S2 + f.o_corr[j]); int32_t *val = (int32_t *)(S2 + f.o_val_attr[j]);
+        const int32_t *corr = (int32_t *)(S + f.o_corr[j]); int32_t *val = (int32_t *)(S + f.o_corr[j]);          // values reconstructed in place
         const int *d2c = (int *)(S2 + f.o_d2c[t]), *v2d1 = (int *)(Z2 + f.o_v2d[t]);
         if (pass == 0 && (a.pred == 0 || a.pred == 1 || a.pred == -2)) {
-            if (a.pred == -2) { memcpy(val, corr, (size_t)n * a.vnc * 4); continue; }
-            int *par = (int *)(S2 + f.o_par[j]);
+            if (a.pred == -2) continue;
+            int *par = (int *)(S + f.o_par[j]);
             if (a.pred == 1) for (int p = 0; p < n; p++) parallelogram_parents(p, tv[t], d2c, v2d1, par + 4 * p);
             for (int k = 0; k < a.vnc; k++) predict_wrap_component(k, a.vnc, n, a.pred == 1, par, corr, val, a.wmin, a.wmax);
         } else if (pass == 1 && a.pred == 5) {
-            UvPrep *prep = (UvPrep *)(S2 + f.o_par[j]);
+            UvPrep *prep = (UvPrep *)(S + f.o_par[j]);
             for (int p = 0; p < n; p++) uv_prepare(p, tv[t], d2c, v2d1, pos_v2d1, posq, prep[p]);
-            rc = predict_uv_chain(n, prep, corr, val, S2 + f.o_auxbits[j], a.num_orient, a.wmin, a.wmax); if (rc) return rc;
+            rc = predict_uv_chain(n, prep, corr, val, S + f.o_auxbits[j], a.num_orient, a.wmin, a.wmax); if (rc) return rc;
         } else if (pass == 1 && a.pred == 6) {
-            for (int p = 0; p < n; p++) normal_entry(p, tv[t], d2c, pos_v2d1, posq, corr, S2 + f.o_auxbits[j], a.wmin, val);
+            for (int p = 0; p < n; p++) normal_entry(p, tv[t], d2c, pos_v2d1, posq, corr, S + f.o_auxbits[j], a.wmin, val);
         }
     }
     (void)pa;
@@ -137,7 +217,7 @@ extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_p
         const int t = a.table + 1;
         float *o = (float *)(O + f.out_attr[a.out_slot]);
         const int *voc = t == 0 ? m.c2v : ac2v[t - 1];
-        for (int p = 0; p < P; p++) expand_point(p, p2c, voc, (int *)(Z2 + f.o_v2d[t]), a, (int32_t *)(S2 + f.o_val_attr[j]), o);
+        for (int p = 0; p < P; p++) expand_point(p, p2c, voc, (int *)(Z2 + f.o_v2d[t]), a, (int32_t *)(S + f.o_corr[j]), o);
         *dst[a.out_slot] = (float *)malloc((size_t)P * a.nc * 4); memcpy(*dst[a.out_slot], o, (size_t)P * a.nc * 4);
     }
     return err ? UVOL_ERR_CORRUPT : UVOL_OK;

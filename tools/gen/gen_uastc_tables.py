@@ -82,6 +82,39 @@ ANCHORS2 = [(0, 2), (0, 3), (1, 0), (0, 3), (7, 0), (0, 2), (3, 0), (7, 0), (0, 
             (1, 0), (8, 0), (0, 1), (0, 2), (0, 4), (8, 0), (1, 0), (0, 2), (4, 0), (0, 1), (4, 0), (1, 0), (4, 0), (1, 0)]
 
 
+# BC7 anchor ("fix-up") texels of the second subset of the 64 two-subset partitions and of the second / third subset of the 64
+# three-subset partitions (the first subset's anchor is always texel 0).  check() verifies that every anchor lies in its subset.
+BC7_ANCHOR2 = [15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 2, 8, 2, 2, 8, 8, 15, 2, 8, 2, 2, 8, 8, 2, 2,
+               15, 15, 6, 8, 2, 8, 15, 15, 2, 8, 2, 2, 2, 15, 15, 6, 6, 2, 6, 8, 15, 15, 2, 2, 15, 15, 15, 15, 15, 2, 2, 15]
+BC7_ANCHOR3A = [3, 3, 15, 15, 8, 3, 15, 15, 8, 8, 6, 6, 6, 5, 3, 3, 3, 3, 8, 15, 3, 3, 6, 10, 5, 8, 8, 6, 8, 5, 15, 15,
+                8, 15, 3, 5, 6, 10, 8, 15, 15, 3, 15, 5, 15, 15, 15, 15, 3, 15, 5, 5, 5, 8, 5, 10, 5, 10, 8, 13, 15, 12, 3, 3]
+BC7_ANCHOR3B = [15, 8, 8, 3, 15, 15, 3, 8, 15, 15, 15, 15, 15, 15, 15, 8, 15, 8, 15, 3, 15, 8, 15, 8, 3, 15, 6, 10, 15, 15, 10, 8,
+                15, 3, 15, 10, 10, 8, 9, 10, 6, 15, 8, 15, 3, 6, 6, 8, 15, 3, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 3, 15, 15, 8]
+BC7_W = {2: [0, 21, 43, 64], 3: [0, 9, 18, 27, 37, 46, 55, 64], 4: [0, 4, 9, 13, 17, 21, 26, 30, 34, 38, 43, 47, 51, 55, 60, 64]}
+ASTC_W = {1: [0, 64], 2: [0, 21, 43, 64], 3: [0, 9, 18, 27, 37, 46, 55, 64], 4: [0, 4, 8, 12, 17, 21, 25, 29, 35, 39, 43, 47, 52, 56, 60, 64],
+          5: [0, 2, 4, 6, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 34, 36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60, 62, 64]}
+
+
+def expand7(q):
+    return (q << 1) | (q >> 6)
+
+
+def solid_mode5():
+    """For every 8-bit value the pair of 7-bit BC7 mode-5 endpoints that, at colour index 1 (weight 21), reproduces it exactly."""
+    out = []
+    for v in range(256):
+        best = None
+        for lo in range(128):
+            for hi in range(128):
+                got = ((64 - 21) * expand7(lo) + 21 * expand7(hi) + 32) >> 6
+                e = abs(got - v)
+                if best is None or e < best[0] or (e == best[0] and abs(lo - hi) < abs(best[1] - best[2])):
+                    best = (e, lo, hi)
+        assert best[0] == 0, v
+        out.append((best[1], best[2]))
+    return out
+
+
 def check():
     """The redundancy checks that pin the tables (also run by tests/test_oracle_uastc.py)."""
     for b, s, inv in COMMON2:
@@ -100,6 +133,9 @@ def check():
     for (b, s, inv), anc in zip(COMMON2, ANCHORS2):
         a = astc(s, 2)
         assert (a.index(0), a.index(1)) == anc, (b, s)
+    for b in range(64):          # BC7 anchors lie in the subset they anchor, and texel 0 is always in subset 0
+        assert BC7_2[b][0] == 0 and BC7_2[b][BC7_ANCHOR2[b]] == 1, b
+        assert BC7_3[b][0] == 0 and BC7_3[b][BC7_ANCHOR3A[b]] == 1 and BC7_3[b][BC7_ANCHOR3B[b]] == 2, b
     return True
 
 
@@ -144,6 +180,38 @@ def main():
         levels = (3 if tr else 5 if qu else 1) << bits
         row = [unquant_endpoint(v, bits, tr, qu) if v < levels else 0 for v in range(256)]
         out.append("    {" + ", ".join(str(v) for v in row) + "},   // range %d" % rng)
+    out.append("};")
+    # ---- BC7 target (bc7_core.h): per UASTC pattern the BC7 partition id, how UASTC subsets map to BC7 subsets and the BC7 anchors
+    out += ["// BC7 view of the 60 patterns: bits 0-5 BC7 partition id, 6-8 transform (two subsets: invert; three: index into PERM3; mode 7:",
+            "// index into MERGE), 9-12 anchor texel of BC7 subset 1, 13-16 anchor texel of BC7 subset 2, 17-22 UASTC subset (2 bits each) that BC7",
+            "// subset 0 / 1 / 2 takes its endpoints from.  UASTC_BC7_PAT3: the BC7 three-subset pattern of the mode-7 entries (2 bits per texel).",
+            "static const uint32_t UASTC_BC7_INFO_INIT[60] = {"]
+    info = []
+    for b, s_, inv in COMMON2:
+        src = [0 ^ inv, 1 ^ inv, 0]          # BC7 subset x = astc ^ inv  ->  astc = x ^ inv
+        info.append(b | (inv << 6) | (BC7_ANCHOR2[b] << 9) | (0 << 13) | (src[0] << 17) | (src[1] << 19) | (src[2] << 21))
+    for b, s_, k in COMMON3:
+        inv_perm = [PERM3[k].index(x) for x in range(3)]
+        info.append(b | (k << 6) | (BC7_ANCHOR3A[b] << 9) | (BC7_ANCHOR3B[b] << 13) | (inv_perm[0] << 17) | (inv_perm[1] << 19) | (inv_perm[2] << 21))
+    for b, s_, k in BC7_3_ASTC2:
+        info.append(b | (k << 6) | (BC7_ANCHOR3A[b] << 9) | (BC7_ANCHOR3B[b] << 13) | (MERGE[k][0] << 17) | (MERGE[k][1] << 19) | (MERGE[k][2] << 21))
+    out += ["    " + ", ".join("0x%08xu" % w for w in info[i:i + 6]) + "," for i in range(0, 60, 6)]
+    out += ["};", "static const uint32_t UASTC_BC7_PAT3_INIT[19] = {"]
+    p3 = [sum(v << (2 * i) for i, v in enumerate(BC7_3[b])) for b, _, _ in BC7_3_ASTC2]
+    out += ["    " + ", ".join("0x%08xu" % w for w in p3[i:i + 6]) + "," for i in range(0, 19, 6)]
+    out += ["};", "// ASTC weight index (row = UASTC weight bits 1..5) -> nearest BC7 index of 2 / 3 / 4 index bits", "static const uint8_t UASTC_BC7_WMAP_INIT[3][6][32] = {"]
+    for ib in (2, 3, 4):
+        out.append("  {")
+        for wb in range(6):
+            row = [0] * 32
+            if wb in ASTC_W:
+                for i, wv in enumerate(ASTC_W[wb]):
+                    row[i] = min(range(len(BC7_W[ib])), key=lambda j: (abs(BC7_W[ib][j] - wv), j))
+            out.append("    {" + ", ".join(str(v) for v in row) + "},")
+        out.append("  },")
+    out += ["};", "// BC7 mode 5, solid colours: 7-bit endpoints {lo, hi} that give exactly v at colour index 1 (weight 21), v = 0..255", "static const uint8_t BC7_SOLID5_INIT[256][2] = {"]
+    sol = solid_mode5()
+    out += ["    " + ", ".join("{%d, %d}" % sol[v] for v in range(i, i + 8)) + "," for i in range(0, 256, 8)]
     out.append("};")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "universal-volumetric_b200", "csrc", "uastc_tables.h")
     with open(path, "w") as f:

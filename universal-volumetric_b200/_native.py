@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libuvol_b200.so")
 MEM_DEVICE, MEM_HOST = 0, 1
 TEX_RGBA32 = 0
 TEX_ETC1 = 1
+TEX_BC7 = 2
 
 
 class UvolError(RuntimeError):
@@ -35,6 +36,12 @@ class Texture(ctypes.Structure):
 class CortoMesh(ctypes.Structure):
     _fields_ = [("status", ctypes.c_int32), ("num_vertices", ctypes.c_uint32), ("num_faces", ctypes.c_uint32), ("pad", ctypes.c_uint32),
                 ("index", ctypes.POINTER(ctypes.c_uint32)), ("position", ctypes.POINTER(ctypes.c_float)), ("uv", ctypes.POINTER(ctypes.c_float))]
+
+
+class Config(ctypes.Structure):
+    """uvol_config (include/uvol_b200.h)."""
+    _fields_ = [("struct_size", ctypes.c_uint32), ("texture_target", ctypes.c_uint32), ("corto_index_u16", ctypes.c_uint32), ("staging_threads", ctypes.c_uint32),
+                ("max_faces_per_frame", ctypes.c_uint64), ("max_texture_bytes", ctypes.c_uint64), ("buffer_duration_s", ctypes.c_double), ("interval_duration_s", ctypes.c_double)]
 
 
 class Vector2(ctypes.Structure):
@@ -62,6 +69,9 @@ def lib():
     L = ctypes.CDLL(LIB_PATH)
     vp, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
     L.uvol_create.argtypes = [i, ctypes.POINTER(vp)]; L.uvol_create.restype = i
+    L.uvol_config_default.argtypes = [ctypes.POINTER(Config)]; L.uvol_config_default.restype = None
+    L.uvol_create_with_config.argtypes = [i, ctypes.POINTER(Config), ctypes.POINTER(vp)]; L.uvol_create_with_config.restype = i
+    L.uvol_get_config.argtypes = [vp, ctypes.POINTER(Config)]; L.uvol_get_config.restype = i
     L.uvol_destroy.argtypes = [vp]; L.uvol_destroy.restype = None
     L.uvol_last_error.argtypes = [vp]; L.uvol_last_error.restype = ctypes.c_char_p
     L.uvol_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]; L.uvol_get_stats.restype = i
@@ -91,6 +101,6 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = ["uvol_create", "uvol_destroy", "uvol_last_error", "uvol_get_stats", "uvol_stage_name", "uvol_set_profiling",
+EXPORTED_SYMBOLS = ["uvol_create", "uvol_create_with_config", "uvol_config_default", "uvol_get_config", "uvol_destroy", "uvol_last_error", "uvol_get_stats", "uvol_stage_name", "uvol_set_profiling",
                     "uvol_decode_draco_batch", "uvol_transcode_ktx2_batch", "uvol_replay_draco_batch", "uvol_replay_ktx2_batch", "uvol_flush_l2", "uvol_decode_v2_batch", "uvol_replay_v2_batch", "uvol_get_stats_kind", "uvol_decode_corto_batch",
                     "CreateDecoder", "DestroyDecoder", "DecodeMesh"]

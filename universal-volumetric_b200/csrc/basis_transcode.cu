@@ -418,7 +418,7 @@ extern "C" int uvol_decode_v2_batch(uvol_ctx *ctx, const uint8_t *const *drc, co
     std::thread tex_thread;
     if (n_ktx2) tex_thread = std::thread([&]() {
         if (cudaSetDevice(ctx->device) != cudaSuccess) { rc_tex = UVOL_ERR_CUDA; return; }
-        rc_tex = ktx2_prepare(ctx, ktx2, ktx2_size, n_ktx2);
+        rc_tex = ktx2_prepare(ctx, ktx2, ktx2_size, n_ktx2, (int)ctx->cfg.texture_target);
         if (!rc_tex) rc_tex = ktx2_launch(ctx, memory, true, ctx->s2);
     });
     if (n_drc) rc = uvol_geo_prepare_and_run(ctx, drc, drc_size, n_drc, memory, out_geo, false);

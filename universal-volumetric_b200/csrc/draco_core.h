@@ -376,6 +376,60 @@ UVOL_HD int traverse_table(const TableView &t, const int *lmc_base, int F, uint8
 }
 
 // ---------------------------------------------------------------------------------------------
+// Traversal records (uvol_internal.h FaceRec) and the per-lane rules of the speculative traversal (k_traverse).  Face ids follow
+// the edgebreaker strip order and the depth-first traversal walks along the same strips, so the kernel lets lane i assume that the
+// walk reaches face f0 + i * dir through that face's static entry corner; these helpers are shared with the host emulation.
+UVOL_HD int table_on_boundary(const TableView &t, const int *lmc_base, int c) {
+    if (t.ac2v) return t.vos[t.c2v_base[c]] != 0;                      // IsOnBoundary == IsCornerOnSeam(leftmost)
+    return b_swl(t.opp, lmc_base[t.c2v_base[c]]) == DINV;
+}
+UVOL_HD void face_record(int f, const TableView &t, const int *lmc_base, FaceRec &r) {
+    int up = 3, dn = 3; uint32_t ob = 0;
+    for (int k = 0; k < 3; k++) {
+        const int c = 3 * f + k, o = t_opp(t, c);
+        r.v[k] = t_vert(t, c); r.o[k] = o;
+        ob |= (uint32_t)table_on_boundary(t, lmc_base, c) << k;
+        if (o >= 0) { const int of = o / 3; if (of == f - 1 && up == 3) up = k; if (of == f + 1 && dn == 3) dn = k; }
+    }
+    r.meta = (uint32_t)up | ((uint32_t)dn << 2) | (ob << 14); r.pad = 0;
+}
+// Tip vertex of the corner through which the walk enters face f from face f - dir (0xffffffff: f does not touch that face).
+UVOL_HD uint32_t face_entry_tip(int f, int F, int dir, const TableView &t) {
+    if (f < 0 || f >= F) return 0xffffffffu;
+    for (int k = 0; k < 3; k++) { const int o = t_opp(t, 3 * f + k); if (o >= 0 && o / 3 == f - dir) return (uint32_t)t_vert(t, 3 * f + k); }
+    return 0xffffffffu;
+}
+#define FREC_UPK(m) ((m) & 3u)
+#define FREC_DNK(m) (((m) >> 2) & 3u)
+#define FREC_DUPU(m) (((m) >> 4) & 31u)
+#define FREC_DUPD(m) (((m) >> 9) & 31u)
+// One lane's view of its face: the corner it stands on (k_first >= 0: the walk's actual corner, lane 0; else the static entry corner
+// for walking direction dir), that corner's tip vertex, right / left corners, boundary flag and duplicate distance.
+struct TravLane { int ci, rc, lc; uint32_t v, pd; bool ob; };
+UVOL_HD TravLane trav_lane(int v0, int v1, int v2, int o0, int o1, int o2, uint32_t meta, int fi, int k_first, int dir, bool inrange) {
+    TravLane L; L.ci = -1; L.rc = L.lc = -1; L.v = 0; L.pd = 0; L.ob = false;
+    if (!inrange) return L;
+    const uint32_t k = k_first >= 0 ? (uint32_t)k_first : (dir > 0 ? FREC_UPK(meta) : FREC_DNK(meta));
+    if (k > 2) return L;
+    L.ci = 3 * fi + (int)k;
+    L.v = (uint32_t)(k == 0 ? v0 : (k == 1 ? v1 : v2));
+    L.rc = k == 0 ? o1 : (k == 1 ? o2 : o0);                           // opposite of next(c)
+    L.lc = k == 0 ? o2 : (k == 1 ? o0 : o1);                           // opposite of prev(c)
+    L.ob = ((meta >> (14 + k)) & 1u) != 0;
+    L.pd = k_first >= 0 ? 0u : (dir > 0 ? FREC_DUPU(meta) : FREC_DUPD(meta));
+    return L;
+}
+// The step rule of the depth-first traverser for one face: act 0 = continue to corner nx, 1 = pop, 2 = push the left corner and
+// continue to the right one.
+UVOL_HD void trav_decide(bool vis, bool ob, bool fr, bool fl, int rc, int lc, int *act, int *nx) {
+    *act = 0; *nx = -1;
+    if (!vis && !ob) *nx = rc;
+    else if (fr) { if (fl) *act = 1; else *nx = lc; }
+    else if (fl) *nx = rc;
+    else { *act = 2; *nx = rc; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Prediction reversal.
 // Parallelogram parents of entry p (element-parallel): par = {opp entry, next entry, prev entry} or {-1,..}.
 UVOL_HD void parallelogram_parents(int p, const TableView &t, const int *d2c, const int *v2d1, int *par4) {
@@ -587,14 +641,17 @@ UVOL_HD void draco_oct_to_unit(int32_t s, int32_t t, int32_t max_v, float *out) 
     out[0] = UVOL_FMUL(x, d); out[1] = UVOL_FMUL(y, d); out[2] = UVOL_FMUL(z, d);
 }
 
-// Per-point expansion of one attribute (GetAttributeDataArrayForAllPoints, DT_FLOAT32).
-UVOL_HD void expand_point(int p, const int *p2c, const int *vert_of_corner, const int *v2d1, const DracoAttr &a, const int32_t *val, float *out) {
-    const int c = p2c[p]; const int e = v2d1[vert_of_corner[c]] - 1; const int nc = a.nc;
-    float *o = out + (size_t)p * nc;
+// Per-point expansion of one attribute value (GetAttributeDataArrayForAllPoints, DT_FLOAT32): entry e of `val` -> out[0..nc).
+UVOL_HD void expand_value(const DracoAttr &a, const int32_t *val, int e, float *o) {
+    const int nc = a.nc;
     if (a.seq == 2) { const float delta = draco_dequant_delta(a.qrange, a.qbits); for (int k = 0; k < nc; k++) o[k] = draco_dequant(val[e * nc + k], delta, a.qmin[k]); }
     else if (a.seq == 3) draco_oct_to_unit(val[e * 2], val[e * 2 + 1], ((1 << a.qbits) - 1) - 1, o);
     else {
         const float tmax = a.dtype == 1 ? 127.f : a.dtype == 2 ? 255.f : a.dtype == 3 ? 32767.f : a.dtype == 4 ? 65535.f : a.dtype == 5 ? 2147483647.f : 4294967295.f;
         for (int k = 0; k < nc; k++) { float v = (float)val[e * nc + k]; if (a.normalized && a.dtype >= 1 && a.dtype <= 6) v = UVOL_FDIV(v, tmax); o[k] = v; }
     }
+}
+UVOL_HD void expand_point(int p, const int *p2c, const int *vert_of_corner, const int *v2d1, const DracoAttr &a, const int32_t *val, float *out) {
+    const int c = p2c[p]; const int e = v2d1[vert_of_corner[c]] - 1;
+    expand_value(a, val, e, out + (size_t)p * a.nc);
 }

@@ -3,9 +3,10 @@
 // Replaces DRACOLoader.decodeGeometry -> DRACOWorker 'decode' (src/lib/DRACOLoader.js:104-187,
 // 433-457, 470-590) for a whole batch of .drc files.  Stage order (DESIGN.md "Geometry pipeline"):
 //   phase 1  rans_ctx -> rabs_seams -> edgebreaker -> seams -> attr_fan(count|scan|assign) -> point_fan(count|scan)
-//   (one 4-byte-per-field count readback per frame; exact-size phase-2 buffers are planned from it)
-//   phase 2  point_fan(assign) -> traverse -> rans_attr + rabs_aux -> parents -> predict_wrap ->
-//            uv_prepare -> predict_uv | normals -> expand
+//   plan2    the count-sized arrays (points, attribute vertices) are laid out ON THE DEVICE from the counts phase 1 produced
+//            (k_plan2; no host round trip: the host reads the counts once, after the last kernel)
+//   phase 2  point_fan(assign) -> face_records -> traverse -> rans_attr + rabs_aux -> parents -> predict_wrap ->
+//            normals | uv_prepare -> predict_uv -> expand
 // Serial units (entropy runs, connectivity walk, traversal, prediction chains) get one warp each and
 // rely on the batch for parallelism; everything else is element-parallel over corners / vertices /
 // entries / points of all frames.  No tensor-core work exists on this path (HBM / latency bound).
@@ -85,7 +86,7 @@ __device__ __forceinline__ uint32_t rans_walk(RansRun r, uint32_t count, void *o
 
 #define RANS_LUT_BITS 10          // 8 KB index + 2 KB ranks + 16 B per used symbol: every run of a 300-frame batch is resident at once
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
-                                             uint8_t *scratch, uint8_t *scratch2, const Job *jobs, int njobs, int smem_words_per_warp, int early) {
+                                             uint8_t *scratch, const Job *jobs, int njobs, int smem_words_per_warp, int early) {
     extern __shared__ uint32_t smem_all[];
     const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if (ji >= njobs) return;
@@ -102,10 +103,12 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *fr
         const int j = jb.what - 16; const DracoAttr &a = f.attr[j];
         s = a.sym;
         mode = (a.pred != -2 && (a.xform == 2 || a.xform == 3)) ? 2 : 1;
-        if (early) { out = scratch + f.o_corr_early[j]; count = f.corr_early_cap[j]; if (lane == 0) counts[jb.frame].rans_early[j] = 0xffffffffu; }
+        out = scratch + f.o_corr[j];
+        if (early) { count = f.corr_cap[j]; if (lane == 0) counts[jb.frame].rans_early[j] = 0xffffffffu; }
         else {
-            out = scratch2 + f.o_corr[j]; count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
-            if (counts[jb.frame].rans_early[j] == count) return;               // the early run produced exactly these symbols (k_corr_settle copies them)
+            count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
+            if (counts[jb.frame].rans_early[j] == count) return;               // the early run already produced exactly these symbols, in place
+            if (count > f.corr_cap[j]) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_FRAME_CAPACITY); return; }
         }
     }
     // Tables in shared memory (built by the whole warp): cs[k] = {first slot, frequency, symbol} of the k-th symbol with a
@@ -171,24 +174,11 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *fr
     else { if (mode == 0) rans_walk<0, true, false>(r, count, out); else if (mode == 1) rans_walk<1, true, false>(r, count, out); else rans_walk<2, true, false>(r, count, out); }
 }
 
-// Moves the symbols of the early attribute runs that came out with exactly the expected count into their phase-2 place
-// (runs that did not are decoded again, by count, by the regular k_rans launch that follows).  grid = (ceil(max/1024), jobs)
-__global__ void __launch_bounds__(256) k_corr_settle(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, uint8_t *S2, const Job *jobs) {
-    const Job jb = jobs[blockIdx.y];
-    if (frame_dead(frames, counts, jb.frame)) return;
-    const DracoFrame &f = frames[jb.frame]; const int j = jb.what - 16; const DracoAttr &a = f.attr[j];
-    const uint32_t count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
-    if (counts[jb.frame].rans_early[j] != count) return;
-    const uint4 *src = (const uint4 *)(S + f.o_corr_early[j]); uint4 *dst = (uint4 *)(S2 + f.o_corr[j]);
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i * 4 < count) dst[i] = src[i];
-}
-
 // rABS bit runs: one warp per run (lane 0 walks).  what: 0..3 = seam bits of attribute data i
 // (upper bound 3F/2+1 bits); 16+j = attribute j aux bits (TEX_COORDS orientations incl. the
 // toggle decoding, or GEOMETRIC_NORMAL flip bits).
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rabs(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob,
-                                             uint8_t *scratch, uint8_t *scratch2, const Job *jobs, int njobs) {
+                                             uint8_t *scratch, const Job *jobs, int njobs) {
     const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if (ji >= njobs || (threadIdx.x & 31) != 0) return;
     const Job jb = jobs[ji];
@@ -203,8 +193,9 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rabs(const DracoFrame *fr
     } else {
         const DracoAttr &a = f.attr[jb.what - 16];
         if (!rabs_init(r, file, a.aux_bits)) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
-        uint8_t *o = scratch2 + f.o_auxbits[jb.what - 16];
+        uint8_t *o = scratch + f.o_auxbits[jb.what - 16];
         const uint32_t n = counts[jb.frame].expected[a.table + 1];
+        if (n > f.table_cap[a.table + 1]) { frame_fail(counts, jb.frame, UVOL_ERR_FRAME_CAPACITY); return; }
         if (a.pred == 5) {
             if ((uint32_t)a.num_orient > n) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
             int last = 1;
@@ -608,127 +599,130 @@ __device__ __forceinline__ TableView make_view(const DracoFrame &f, int t, const
     return tv;
 }
 
-// Corner records of one corner table (element-parallel): everything the serial traversal needs about
-// a corner in 16 bytes -- {vertex id | on-boundary << 31, right corner, left corner, 0} -- so that its
-// hot loop is one shared-memory load plus bitmap tests, with no division, no table indirection.
-// Corner ids follow the edgebreaker strip order and the depth-first traversal mostly walks the same
-// strips (94-99 % of its moves go to an adjacent face id), hence a small sliding window suffices.
-// grid = (ceil(3*maxF/128), traversal jobs)
-__global__ void __launch_bounds__(128) k_corner_records(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, const uint8_t *Z, uint8_t *S2,
-                                                        const Job *jobs) {
-    const Job jb = jobs[blockIdx.y];
-    if (frame_dead(frames, counts, jb.frame)) return;
-    const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
-    if (f.o_d2c[t] == UVOL_NONE) return;
-    const int C = 3 * (int)f.nf, c = blockIdx.x * 128 + threadIdx.x;
-    if (c >= C) return;
-    const TableView tv = make_view(f, t, S, Z);
-    const int *lmc = (const int *)(S + f.o_lmc);
-    int ob;
-    if (tv.ac2v) ob = tv.vos[tv.c2v_base[c]]; else ob = b_swl(tv.opp, lmc[tv.c2v_base[c]]) == DINV;
-    const uint32_t v = (uint32_t)t_vert(tv, c) | ((uint32_t)ob << 31);
-    ((uint4 *)(S2 + f.o_frec[t]))[c] = make_uint4(v, (uint32_t)t_opp(tv, cnext(c)), (uint32_t)t_opp(tv, cprev(c)), 0u);
-}
-
-// Per-face entry records (element-parallel): the corner record of the corner through which the
-// traversal ENTERS face f when it arrives from face f-1 ("up") or from face f+1 ("down"), i.e. the corner
-// of f whose opposite corner lies in that neighbour; w = the corner id, -1 when f does not touch it.
-// grid = (ceil(maxF/128), traversal jobs)
-__global__ void __launch_bounds__(128) k_face_entries(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S2, const Job *jobs) {
-    const Job jb = jobs[blockIdx.y];
-    if (frame_dead(frames, counts, jb.frame)) return;
-    const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
-    if (f.o_d2c[t] == UVOL_NONE) return;
-    const int F = (int)f.nf, fi = blockIdx.x * 128 + threadIdx.x;
-    if (fi >= F) return;
-    const uint4 *rec = (const uint4 *)(S2 + f.o_frec[t]);
-    uint4 *up = (uint4 *)(S2 + f.o_frec[t]) + 3 * (size_t)F + 4, *dn = up + F + 4;
-    uint4 u = make_uint4(0, 0xffffffffu, 0xffffffffu, 0xffffffffu), d = u;
-    // corner k of face fi is entered across the edge opposite k; its opposite corner is the "right" link of prev(k)
+// Device planner: lays out the count-sized arrays of every frame (point -> corner map, entry maps, per-point output arrays) from
+// the counts the connectivity kernels have just produced, with the same function the host runs on the final counts
+// (draco_plan2_frame): per-frame sizes, block-wide exclusive scan over the frames, offsets written into the device descriptors.
+// A frame whose attribute tables outgrew their optimistic capacity is failed with UVOL_ERR_FRAME_CAPACITY, a batch that outgrew the
+// reserved arenas fails every frame with UVOL_ERR_BATCH_CAPACITY (the launcher re-plans and runs the batch again).  One block.
+__global__ void __launch_bounds__(1024) k_plan2(DracoFrame *frames, DracoCounts *counts, DracoBatchPlan *bp, int n, uint64_t out_index_bytes,
+                                                uint64_t cap_s2, uint64_t cap_z2, uint64_t cap_out) {
+    __shared__ unsigned long long wsum[3][32]; __shared__ unsigned long long carry[3]; __shared__ int over;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) { carry[0] = 0; carry[1] = 0; carry[2] = out_index_bytes; over = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        Plan2Cursor sz{0, 0, 0};
+        if (i < n && !frame_dead(frames, counts, i)) {
+            for (uint32_t t = 1; t <= frames[i].nad; t++) if (counts[i].attr_vertices[t - 1] > frames[i].table_cap[t]) counts[i].status = UVOL_ERR_FRAME_CAPACITY;
+            draco_plan2_frame(frames[i], counts[i], sz, false);
+        }
+        unsigned long long x[3] = {sz.s, sz.z, sz.o}, inc[3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int c = 3 * fi + k, kp = k == 0 ? 2 : k - 1;
-        const int o = (int)rec[3 * fi + kp].y;                    // t_opp(cnext(prev(c))) = t_opp(c)
-        if (o < 0) continue;
-        const int of = (int)(__umulhi((unsigned)o, 0xAAAAAAABu) >> 1);
-        uint4 r = rec[c]; r.w = (uint32_t)c;
-        if (of == fi - 1 && (int)u.w < 0) u = r;
-        if (of == fi + 1 && (int)d.w < 0) d = r;
+        for (int k = 0; k < 3; k++) {
+            unsigned long long v = x[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+            inc[k] = v;
+            if (lane == 31) wsum[k][w] = v;
+        }
+        __syncthreads();
+        Plan2Cursor cur;
+        {
+            unsigned long long pre[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { pre[k] = carry[k]; for (int j = 0; j < w; j++) pre[k] += wsum[k][j]; pre[k] += inc[k] - x[k]; }
+            cur.s = pre[0]; cur.z = pre[1]; cur.o = pre[2];
+        }
+        if (i < n && !frame_dead(frames, counts, i)) draco_plan2_frame(frames[i], counts[i], cur, true);
+        __syncthreads();
+        if (tid == 1023) { carry[0] = cur.s; carry[1] = cur.z; carry[2] = cur.o; }          // the last thread's cursors have advanced past its own frame
+        __syncthreads();
     }
-    up[fi] = u; dn[fi] = d;
-}
-
-// Duplicate distances (element-parallel): for the up entry of face f the smallest k in 1..31 such that the up entry of
-// face f-k has the same tip vertex (0: none), for the down entry the same towards f+k; stored in bits 26..30 of x.
-// The traversal uses it to know, without any exchange between lanes, that a tip was already reached by an earlier
-// face of the same 32-face run.   grid = (ceil(maxF/256), traversal jobs)
-#define TIP_MASK 0x03ffffffu          // x = tip vertex | duplicate distance << 26 | on-boundary << 31
-__global__ void __launch_bounds__(256) k_face_dups(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S2, const Job *jobs) {
-    __shared__ uint32_t tipU[256 + 32], tipD[256 + 32];
-    const Job jb = jobs[blockIdx.y];
-    if (frame_dead(frames, counts, jb.frame)) return;
-    const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
-    if (f.o_d2c[t] == UVOL_NONE) return;
-    const int F = (int)f.nf, base = blockIdx.x * 256;
-    if (base >= F) return;
-    uint4 *up = (uint4 *)(S2 + f.o_frec[t]) + 3 * (size_t)F + 4, *dn = up + F + 4;
-    for (int i = threadIdx.x; i < 256 + 31; i += 256) {
-        const int gu = base - 31 + i, gd = base + i;
-        uint32_t a = 0xffffffffu, b = 0xffffffffu;
-        if (gu >= 0 && gu < F) { const uint4 r = up[gu]; if ((int)r.w >= 0) a = r.x & TIP_MASK; }
-        if (gd < F) { const uint4 r = dn[gd]; if ((int)r.w >= 0) b = r.x & TIP_MASK; }
-        tipU[i] = a; tipD[i] = b;
+    if (tid == 0) {
+        bp->s2_need = carry[0]; bp->z2_need = carry[1]; bp->out_need = carry[2];
+        over = carry[0] > cap_s2 || carry[1] > cap_z2 || carry[2] > cap_out;
+        bp->overflow = (uint32_t)over;
     }
     __syncthreads();
-    const int fi = base + threadIdx.x;
-    if (fi >= F) return;
-    const uint32_t mu = tipU[threadIdx.x + 31], md = tipD[threadIdx.x];
-    uint32_t du = 0, dd = 0;
-    if (mu != 0xffffffffu) { for (int k = 1; k < 32; k++) if (tipU[threadIdx.x + 31 - k] == mu) { du = (uint32_t)k; break; } }
-    if (md != 0xffffffffu) { for (int k = 1; k < 32; k++) if (tipD[threadIdx.x + k] == md) { dd = (uint32_t)k; break; } }
-    if (du) ((uint32_t *)(up + fi))[0] |= du << 26;
-    if (dd) ((uint32_t *)(dn + fi))[0] |= dd << 26;
+    if (over) for (int i = tid; i < n; i += 1024) if (!frames[i].status && !counts[i].status) counts[i].status = UVOL_ERR_BATCH_CAPACITY;
 }
 
-// Depth-first traversal (A.3): one warp per (frame, table), 32 faces per step.
-// Face ids follow the edgebreaker strip order and the traversal walks along the same strips (94-99 % of its
-// moves go to face id +-1), so lane i SPECULATES that the walk reaches face f0 + i*dir through that face's
-// static entry corner (k_face_entries).  Every lane evaluates the exact step rule for its face against the
-// visited bitmaps plus the effects of the lanes before it (warp match / ballot), the longest prefix whose
-// transitions really lead to the next lane's corner is committed at once, and the first lane that deviates
-// (pop, push, turn) hands its exact outcome to the next step.  Output order is identical to the serial walk.
+// Traversal records of one corner table (element-parallel, one thread per face): the three vertex ids, the three opposite corners
+// (cut at seams), boundary flags, the corners through which a walk along the face-id order enters the face (from f-1 / from f+1) and
+// -- for those two entry corners -- the distance to the nearest earlier face of the run whose entry corner has the same tip vertex
+// (so the traversal knows, without any exchange between lanes, that a tip was already reached inside the same 32-face step).
+// 32 bytes per face; everything the serial traversal needs about a face is one load.   grid = (ceil(maxF/256), traversal jobs)
+__global__ void __launch_bounds__(256) k_face_records(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S, const uint8_t *Z, const Job *jobs) {
+    __shared__ uint32_t tipU[256 + 31], tipD[256 + 31];
+    const Job jb = jobs[blockIdx.y];
+    if (frame_dead(frames, counts, jb.frame)) return;
+    const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
+    if (f.o_frec[t] == UVOL_NONE) return;
+    const int F = (int)f.nf, base = blockIdx.x * 256, tid = threadIdx.x;
+    if (base >= F) return;
+    const TableView tv = make_view(f, t, S, Z);
+    const int *lmc = (const int *)(S + f.o_lmc);
+    const int fi = base + tid;
+    FaceRec r; r.meta = 0xfu; uint32_t mu = 0xffffffffu, md = 0xffffffffu;
+    if (fi < F) {
+        face_record(fi, tv, lmc, r);
+        const uint32_t ku = FREC_UPK(r.meta), kd = FREC_DNK(r.meta);
+        if (ku < 3) mu = (uint32_t)(ku == 0 ? r.v[0] : (ku == 1 ? r.v[1] : r.v[2]));
+        if (kd < 3) md = (uint32_t)(kd == 0 ? r.v[0] : (kd == 1 ? r.v[1] : r.v[2]));
+    }
+    tipU[tid + 31] = mu; tipD[tid] = md;
+    if (tid < 31) { tipU[tid] = face_entry_tip(base - 31 + tid, F, 1, tv); tipD[256 + tid] = face_entry_tip(base + 256 + tid, F, -1, tv); }
+    __syncthreads();
+    if (fi >= F) return;
+    uint32_t du = 0, dd = 0;
+    if (mu != 0xffffffffu) { for (int k = 1; k < 32; k++) if (tipU[tid + 31 - k] == mu) { du = (uint32_t)k; break; } }
+    if (md != 0xffffffffu) { for (int k = 1; k < 32; k++) if (tipD[tid + k] == md) { dd = (uint32_t)k; break; } }
+    r.meta |= (du << 4) | (dd << 9);
+    uint4 *dst = (uint4 *)(S + f.o_frec[t]) + 2 * (size_t)fi;
+    dst[0] = make_uint4((uint32_t)r.v[0], (uint32_t)r.v[1], (uint32_t)r.v[2], (uint32_t)r.o[0]);
+    dst[1] = make_uint4((uint32_t)r.o[1], (uint32_t)r.o[2], r.meta, 0u);
+}
+
+// Depth-first traversal (A.3): one warp per (frame, table), up to 32 faces per step.
+// Face ids follow the edgebreaker strip order and the traversal walks along the same strips, so lane i SPECULATES that the walk
+// reaches face f0 + i*dir through that face's static entry corner (dir = the direction of the last move; lane 0 stands on the
+// walk's actual corner).  One 32-byte record load per lane (k_face_records), then every lane evaluates the exact step rule for its
+// face against the visited maps plus the effects of the lanes before it (static duplicate distances, ballots); the longest
+// prefix whose transitions really lead to the next lane's corner is committed at once, and the first lane that deviates (pop,
+// push, turn, direction change) hands its exact outcome to the next step.  Output order is identical to the serial walk
+// (tests/tools/draco_emu.cpp runs this very scheme lane by lane on the host against traverse_table).
 #define TRAV_STACK 512
-#define TRAV_WARPS 1          // one walk per block: 21 KB of bitmaps each, so the blocks pack around whatever else is resident (entropy runs, texture slices)
 __device__ __forceinline__ unsigned face_of(int c) { return __umulhi((unsigned)c, 0xAAAAAAABu) >> 1; }
-// GMAP = false: visited-face / visited-vertex bitmaps in shared memory (F/8 + V/8 bytes per walk: fastest while all walks of
-// the batch are co-resident).  GMAP = true: a byte per face in global memory plus the vertex -> entry map itself as the
-// visited-vertex test -- 2 KB of shared memory per walk, so large meshes (C3: 77 KB of bitmaps per walk) no longer cap the
-// SM at two walks.  Only this warp touches those bytes, so plain (L1-cached) loads / stores ordered by warp barriers suffice.
-// GMAP = 2: faces in a shared-memory bitmap, vertices through the global vertex -> entry map (two thirds of the footprint).
+// GMAP = 0: visited-face / visited-vertex bitmaps in shared memory (F/8 + V/8 bytes per walk: fastest while all walks of the
+// batch are co-resident).  GMAP = 1: a byte per face in global memory plus the vertex -> entry map itself as the visited-vertex
+// test -- 2 KB of shared memory per walk, so large meshes (C3: 77 KB of bitmaps per walk) no longer cap the SM at two walks.
+// Only this warp touches those bytes, so plain (L1-cached) loads / stores ordered by warp barriers suffice.
 template <int GMAP>
-__global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, uint8_t *Z2,
+__global__ void __launch_bounds__(32) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S, uint8_t *Z, uint8_t *S2, uint8_t *Z2,
                                                  const Job *jobs, int njobs, int fwords_max, int vwords_max) {
-    extern __shared__ uint32_t sm_all[];
-    const int ji = blockIdx.x * TRAV_WARPS + (threadIdx.x >> 5);
+    extern __shared__ uint32_t sm[];
+    const int ji = blockIdx.x;
     if (ji >= njobs) return;
-    constexpr bool FG = GMAP == 1, VG = GMAP != 0;          // faces / vertices tested through global memory
-    const int bitwords = (FG ? 0 : fwords_max) + (VG ? 0 : vwords_max);
-    uint32_t *sm = sm_all + (size_t)(threadIdx.x >> 5) * (bitwords + TRAV_STACK);
+    constexpr bool G = GMAP != 0;
+    const int bitwords = G ? 0 : fwords_max + vwords_max;
     const Job jb = jobs[ji];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
-    if (f.o_d2c[t] == UVOL_NONE) return;
+    if (f.o_frec[t] == UVOL_NONE || f.o_d2c[t] == UVOL_NONE) return;
     const int F = (int)f.nf, C = 3 * F, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    uint32_t *fbits = sm, *vbits = sm + (FG ? 0 : fwords_max); int *stk = (int *)(sm + bitwords);
+    uint32_t *fbits = sm, *vbits = sm + (G ? 0 : fwords_max); int *stk = (int *)(sm + bitwords);
     for (int i = lane; i < bitwords; i += 32) sm[i] = 0;
-    const uint4 *grec = (const uint4 *)(S2 + f.o_frec[t]), *gup = grec + 3 * (size_t)F + 4, *gdn = gup + F + 4;
-    int *d2c = (int *)(S2 + f.o_d2c[t]), *v2d1 = (int *)(Z2 + f.o_v2d[t]), *gst = (int *)(S2 + f.o_tstack[t]);
-    uint8_t *fvis = Z2 + f.o_fvis[t];                        // GMAP only (zero-initialised with the arena)
+    const uint4 *grec = (const uint4 *)(S + f.o_frec[t]);
+    int *d2c = (int *)(S2 + f.o_d2c[t]), *v2d1 = (int *)(Z2 + f.o_v2d[t]), *gst = (int *)(S + f.o_tstack[t]);
+    uint8_t *fvis = Z + f.o_fvis[t];                         // GMAP only (zero-initialised with the arena)
+    const int max_entries = (int)(t == 0 ? counts[jb.frame].num_vertex_slots : counts[jb.frame].attr_vertices[t - 1]);
+    if (!G && (F > fwords_max * 32 || max_entries > vwords_max * 32)) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
     __syncwarp();
     int n = 0, sp = 0, c = -1, fscan = 0, status = 0, pdir = 1;
-#define FBIT(x) (FG ? (uint32_t)fvis[(x)] : ((fbits[(x) >> 5] >> ((x) & 31)) & 1u))
-#define VBIT(x) (VG ? (uint32_t)(v2d1[(x)] != 0) : ((vbits[(x) >> 5] >> ((x) & 31)) & 1u))
+#define FBIT(x) (G ? (uint32_t)fvis[(x)] : ((fbits[(x) >> 5] >> ((x) & 31)) & 1u))
+#define VBIT(x) (G ? (uint32_t)(v2d1[(x)] != 0) : ((vbits[(x) >> 5] >> ((x) & 31)) & 1u))
     for (;;) {
         if (c < 0) {
             // ---- pick the next corner: stack top (lane 0), else the next unvisited face starts a component
@@ -737,15 +731,15 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
                 for (;;) {
                     if (sp == 0) { scan = 1; break; }
                     c = sp <= TRAV_STACK ? stk[sp - 1] : gst[sp - 1];
-                    if (c < 0 || FBIT(face_of(c))) { sp--; c = -1; continue; }
+                    if (c < 0 || c >= C || FBIT(face_of(c))) { sp--; c = -1; continue; }
                     break;
                 }
             }
             scan = __shfl_sync(0xffffffffu, scan, 0);
             if (scan) {
                 int nf = F;
-                if (FG) {            // all lanes: 128 faces per round, four visited-bytes per lane
-                    fscan = __shfl_sync(0xffffffffu, fscan, 0);
+                fscan = __shfl_sync(0xffffffffu, fscan, 0);
+                if (G) {             // all lanes: 128 faces per round, four visited-bytes per lane
                     for (int base = fscan & ~127; base < F && nf == F; base += 128) {
                         const int i0 = base + lane * 4;
                         const uint32_t w = i0 < F ? *(const uint32_t *)(fvis + i0) : 0x01010101u;
@@ -764,9 +758,10 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
                     if (nf >= F) done = 1;
                     else {
                         fscan = nf; c = 3 * nf; stk[0] = c; sp = 1;
-                        const unsigned vn = grec[c + 1].x & TIP_MASK, vp = grec[c + 2].x & TIP_MASK;     // next / previous vertices first
-                        if (!VBIT(vn)) { if (!VG) vbits[vn >> 5] |= 1u << (vn & 31); v2d1[vn] = ++n; d2c[n - 1] = c + 1; }
-                        if (!VBIT(vp)) { if (!VG) vbits[vp >> 5] |= 1u << (vp & 31); v2d1[vp] = ++n; d2c[n - 1] = c + 2; }
+                        const uint4 A = grec[2 * (size_t)nf];
+                        const int vn = (int)A.y, vp = (int)A.z;                                   // next / previous vertices first
+                        if (!VBIT(vn) && n < max_entries) { if (!G) vbits[vn >> 5] |= 1u << (vn & 31); v2d1[vn] = ++n; d2c[n - 1] = c + 1; }
+                        if (!VBIT(vp) && n < max_entries) { if (!G) vbits[vp >> 5] |= 1u << (vp & 31); v2d1[vp] = ++n; d2c[n - 1] = c + 2; }
                     }
                 }
             }
@@ -777,47 +772,26 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
         }
         if (c >= C) { status = UVOL_ERR_CORRUPT; break; }
         // ---- one speculative step over up to 32 faces
-        const int f0 = (int)face_of(c);
-        const uint4 R0 = grec[c];
-        const int fu = f0 + lane, fd = f0 - lane;
-        uint4 U = make_uint4(0, 0, 0, 0xffffffffu), D = U;
-        if (lane > 0 && fu < F) U = gup[fu];
-        if (lane > 0 && fd >= 0) D = gdn[fd];
-        // lane 0's exact decision (computed by every lane) fixes the direction
-        int dir;
-        {
-            const unsigned v = R0.x & TIP_MASK; const int rc = (int)R0.y, lc = (int)R0.z; int nx = -1;
-            if (!VBIT(v) && (int)R0.x >= 0) nx = rc;
-            else {
-                const bool fr = rc < 0 || FBIT(face_of(rc)) || face_of(rc) == (unsigned)f0, fl = lc < 0 || FBIT(face_of(lc)) || face_of(lc) == (unsigned)f0;
-                if (fr && !fl) nx = lc; else if (!fr) nx = rc;
-            }
-            const int nf = nx >= 0 ? (int)face_of(nx) : -9;
-            dir = nf == f0 + 1 ? 1 : (nf == f0 - 1 ? -1 : 0);
-        }
-        if (dir != 0) pdir = dir;
-        uint4 R = lane == 0 ? R0 : (dir > 0 ? U : D);
-        if (lane == 0) R.w = (uint32_t)c;
-        if (lane > 0 && dir == 0) R.w = 0xffffffffu;
-        const int ci = (int)R.w;                                   // my corner (-1: no such entry)
-        const int fi = f0 + lane * dir;
-        const unsigned v = R.x & TIP_MASK, pd = lane == 0 ? 0u : (R.x >> 26) & 31u; const bool ob = (int)R.x < 0; const int rc = (int)R.y, lc = (int)R.z;
+        const int f0 = (int)face_of(c), k0 = c - 3 * f0;
+        const int fi = f0 + lane * pdir;
+        const bool inr = fi >= 0 && fi < F;
+        uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0xfu, 0);
+        if (inr) { A = grec[2 * (size_t)fi]; B = grec[2 * (size_t)fi + 1]; }
+        const TravLane L = trav_lane((int)A.x, (int)A.y, (int)A.z, (int)A.w, (int)B.x, (int)B.y, B.z, fi, lane == 0 ? k0 : -1, pdir, inr);
+        const int ci = L.ci, rc = L.rc, lc = L.lc; const unsigned v = L.v;
         const bool selfopen = ci >= 0 && !FBIT(fi);
-        // vertex visited before my step: bitmap, or the tip of an earlier lane
+        // vertex visited before my step: the map, or the tip of an earlier lane (lane 0's actual tip / the static distance to an earlier face of the run)
         const unsigned v_first = __shfl_sync(0xffffffffu, v, 0);
-        const bool dup = lane > 0 && (v == v_first || (pd != 0 && (int)pd < lane));      // lane 0's actual tip, or the static distance to an earlier face of the run
+        const bool dup = lane > 0 && (v == v_first || (L.pd != 0 && (int)L.pd < lane));
         const bool vis = ci >= 0 && (VBIT(v) || dup);
         // neighbour faces visited before / during this step (faces of the lanes up to and including me)
         bool fr = true, fl = true;
         if (ci >= 0) {
-            if (rc >= 0) { const int rf = (int)face_of(rc), k = (rf - f0) * dir; fr = FBIT(rf) || (dir != 0 ? (k >= 0 && k <= lane) : rf == f0); }
-            if (lc >= 0) { const int lf = (int)face_of(lc), k = (lf - f0) * dir; fl = FBIT(lf) || (dir != 0 ? (k >= 0 && k <= lane) : lf == f0); }
+            if (rc >= 0) { const int rf = (int)face_of(rc), k = (rf - f0) * pdir; fr = FBIT(rf) || (k >= 0 && k <= lane); }
+            if (lc >= 0) { const int lf = (int)face_of(lc), k = (lf - f0) * pdir; fl = FBIT(lf) || (k >= 0 && k <= lane); }
         }
-        int act = 0 /*0 continue to nx, 1 pop, 2 push*/, nx = -1;
-        if (!vis && !ob) nx = rc;
-        else if (fr) { if (fl) act = 1; else nx = lc; }
-        else if (fl) nx = rc;
-        else { act = 2; nx = rc; }
+        int act, nx;
+        trav_decide(vis, L.ob, fr, fl, rc, lc, &act, &nx);
         // does my transition lead exactly to the next lane's corner?
         const int cnext_lane = __shfl_down_sync(0xffffffffu, ci, 1);
         const bool open_next = __shfl_down_sync(0xffffffffu, (int)selfopen, 1) != 0;
@@ -827,11 +801,14 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
         const bool exec = lane <= m;
         if (lane == 0 && !selfopen) status = UVOL_ERR_CORRUPT;        // the walk only ever moves to unvisited faces
         const unsigned newv = __ballot_sync(0xffffffffu, exec && !vis);
+        if (n + __popc(newv) > max_entries) status = UVOL_ERR_CORRUPT;
+        status = __shfl_sync(0xffffffffu, status, 0);
+        if (status) break;
         if (exec) {
-            if (FG) fvis[fi] = 1; else atomicOr(&fbits[fi >> 5], 1u << (fi & 31));
+            if (G) fvis[fi] = 1; else atomicOr(&fbits[fi >> 5], 1u << (fi & 31));
             if (!vis) {
                 const int idx = n + __popc(newv & lt);
-                if (!VG) atomicOr(&vbits[v >> 5], 1u << (v & 31));
+                if (!G) atomicOr(&vbits[v >> 5], 1u << (v & 31));
                 v2d1[v] = idx + 1; d2c[idx] = ci;
             }
         }
@@ -839,10 +816,10 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
         // outcome of the last executed lane
         const int act_m = __shfl_sync(0xffffffffu, act, m), nx_m = __shfl_sync(0xffffffffu, nx, m), lc_m = __shfl_sync(0xffffffffu, lc, m);
         __syncwarp();
-        if (status) break;
         if (act_m == 0) { c = nx_m; if (c < 0) { status = UVOL_ERR_CORRUPT; break; } }
         else if (act_m == 1) { sp--; c = -1; }
         else {      // both neighbours open: the left face waits on the stack, the right one is walked next
+            if (sp >= F + 4) { status = UVOL_ERR_CORRUPT; break; }
             if (lane == 0) {
                 if (sp <= TRAV_STACK) stk[sp - 1] = lc_m; else gst[sp - 1] = lc_m;
                 if (sp < TRAV_STACK) stk[sp] = nx_m; else gst[sp] = nx_m;
@@ -850,6 +827,7 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
             sp++; c = nx_m;
             __syncwarp();
         }
+        if (c >= 0) { const int nf = (int)face_of(c), fm = f0 + m * pdir; if (nf == fm + 1) pdir = 1; else if (nf == fm - 1) pdir = -1; }
     }
 #undef FBIT
 #undef VBIT
@@ -864,25 +842,24 @@ __global__ void __launch_bounds__(32 * TRAV_WARPS) k_traverse(const DracoFrame *
 // par4 = {opp entry, next entry, prev entry, kind}.  kind 1 ("scan-able"): the prediction is
 // x[p-1] + (x[far1] - x[far2]) with both far parents at least 32 entries back -- then a run of such
 // entries is a prefix sum (see k_predict_wrap); par4 is rewritten as {far1, far2, -, 1} (far = -1: term absent).
-__global__ void __launch_bounds__(128) k_parents(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, const uint8_t *Z, uint8_t *S2, const uint8_t *Z2) {
+__global__ void __launch_bounds__(128) k_parents(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S, const uint8_t *Z, const uint8_t *S2, const uint8_t *Z2) {
     const uint32_t fi = blockIdx.y, j = blockIdx.z;
     if (frame_dead(frames, counts, fi)) return;
     const DracoFrame &f = frames[fi];
-    if ((int)j >= f.nattr || f.o_corr[j] == UVOL_NONE || (f.attr[j].pred != 1 && f.attr[j].pred != 0)) return;
-    const int t = f.attr[j].table + 1, n = (int)counts[fi].entries[t], p = blockIdx.x * 128 + threadIdx.x;
-    if (p >= n) return;
-    int par[4] = {-1, -1, -1, 0};
-    if (f.attr[j].pred == 1) {
-        const TableView tv = make_view(f, t, S, Z);
-        parallelogram_parents(p, tv, (const int *)(S2 + f.o_d2c[t]), (const int *)(Z2 + f.o_v2d[t]), par);
+    if ((int)j >= f.nattr || f.o_par[j] == UVOL_NONE || (f.attr[j].pred != 1 && f.attr[j].pred != 0)) return;
+    const int t = f.attr[j].table + 1, n = (int)counts[fi].entries[t];
+    const TableView tv = make_view(f, t, S, Z);
+    for (int p = blockIdx.x * 128 + threadIdx.x; p < n; p += gridDim.x * 128) {
+        int par[4] = {-1, -1, -1, 0};
+        if (f.attr[j].pred == 1) parallelogram_parents(p, tv, (const int *)(S2 + f.o_d2c[t]), (const int *)(Z2 + f.o_v2d[t]), par);
+        int4 out = make_int4(par[0], par[1], par[2], 0);
+        if (p > 0) {
+            if (par[0] < 0) out = make_int4(-1, -1, -1, 1);                                              // delta coding: x[p-1] + corr
+            else if (par[2] == p - 1 && par[0] <= p - 32 && par[1] <= p - 32) out = make_int4(par[1], par[0], -1, 1);   // + next - opp
+            else if (par[1] == p - 1 && par[0] <= p - 32 && par[2] <= p - 32) out = make_int4(par[2], par[0], -1, 1);   // + prev - opp
+        }
+        ((int4 *)(S + f.o_par[j]))[p] = out;
     }
-    int4 out = make_int4(par[0], par[1], par[2], 0);
-    if (p > 0) {
-        if (par[0] < 0) out = make_int4(-1, -1, -1, 1);                                              // delta coding: x[p-1] + corr
-        else if (par[2] == p - 1 && par[0] <= p - 32 && par[1] <= p - 32) out = make_int4(par[1], par[0], -1, 1);   // + next - opp
-        else if (par[1] == p - 1 && par[0] <= p - 32 && par[2] <= p - 32) out = make_int4(par[2], par[0], -1, 1);   // + prev - opp
-    }
-    ((int4 *)(S2 + f.o_par[j]))[p] = out;
 }
 
 // DIFFERENCE / PARALLELOGRAM + WRAP reversal (also the pass-through for "no prediction"): one warp per
@@ -892,7 +869,7 @@ __global__ void __launch_bounds__(128) k_parents(const DracoFrame *frames, const
 // Values of the last PW_RING entries are mirrored in a shared-memory ring (the far parents sit about one
 // strip back).  what = attribute index.
 #define PW_RING 512
-__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_wrap(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S2, const Job *jobs, int njobs) {
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_wrap(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S, const Job *jobs, int njobs) {
     __shared__ int ring_all[SERIAL_WARPS][PW_RING * 4];
     const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if (ji >= njobs) return;
@@ -901,10 +878,11 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_wrap(const DracoF
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int j = jb.what; const DracoAttr &a = f.attr[j];
     const int n = (int)counts[jb.frame].entries[a.table + 1], lane = threadIdx.x & 31, nc = a.vnc;
-    const int32_t *corr = (const int32_t *)(S2 + f.o_corr[j]); int32_t *val = (int32_t *)(S2 + f.o_val_attr[j]);
-    if (a.pred == -2) { for (int i = lane; i < n * nc; i += 32) val[i] = corr[i]; return; }
-    if (n <= 0) return;
-    const int4 *par = (const int4 *)(S2 + f.o_par[j]);
+    // values are reconstructed IN PLACE over the corrections: every entry's correction is read (by the lane that owns the entry)
+    // before its value is stored, and only values of earlier entries are ever looked up
+    const int32_t *corr = (const int32_t *)(S + f.o_corr[j]); int32_t *val = (int32_t *)(S + f.o_corr[j]);
+    if (a.pred == -2 || n <= 0) return;                     // no prediction: the corrections are the values
+    const int4 *par = (const int4 *)(S + f.o_par[j]);
     const int32_t mn = a.wmin, mx = a.wmax;
     // x(e, k): value of entry e, from the ring when recent enough
 #define PW_GET(e, k, pcur) (((e) > (pcur) - PW_RING + 32) ? ring[((e) & (PW_RING - 1)) * 4 + (k)] : val[(e) * nc + (k)])
@@ -965,25 +943,26 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_wrap(const DracoF
 }
 
 // TEX_COORDS_PORTABLE position-only terms, element-parallel.  grid = (ceil(maxN/128), frames, attrs)
-__global__ void __launch_bounds__(128) k_uv_prepare(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, const uint8_t *Z, uint8_t *S2, const uint8_t *Z2) {
+__global__ void __launch_bounds__(128) k_uv_prepare(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S, const uint8_t *Z, const uint8_t *S2, const uint8_t *Z2) {
     const uint32_t fi = blockIdx.y, j = blockIdx.z;
     if (frame_dead(frames, counts, fi)) return;
     const DracoFrame &f = frames[fi];
-    if ((int)j >= f.nattr || f.o_corr[j] == UVOL_NONE || f.attr[j].pred != 5) return;
-    const int t = f.attr[j].table + 1, n = (int)counts[fi].entries[t], p = blockIdx.x * 128 + threadIdx.x;
-    if (p >= n) return;
+    if ((int)j >= f.nattr || f.o_par[j] == UVOL_NONE || f.attr[j].pred != 5) return;
+    const int t = f.attr[j].table + 1, n = (int)counts[fi].entries[t];
     const TableView tv = make_view(f, t, S, Z);
-    UvPrep q;
-    uv_prepare(p, tv, (const int *)(S2 + f.o_d2c[t]), (const int *)(Z2 + f.o_v2d[t]), (const int *)(Z2 + f.o_v2d[0]),
-               (const int32_t *)(S2 + f.o_val_attr[f.pos_attr]), q);
-    UvPrepD o; o.nd = q.nd; o.pd = q.pd; o.pn2 = o.dot = o.ns = o.rcp = 0.0;
-    if (q.pn2 != 0) {
-        const double vmax = fmax(fabs((double)f.attr[j].wmin), fabs((double)f.attr[j].wmax)) + 1.0, lim = 2251799813685248.0 /* 2^51 */;
-        const double dpn2 = (double)q.pn2, ddot = (double)q.dot, dns = (double)q.ns;
-        if ((fabs(ddot) + dns) * 2.0 * vmax < lim && dpn2 * vmax < lim && dpn2 < lim) { o.pn2 = dpn2; o.dot = ddot; o.ns = dns; o.rcp = 1.0 / dpn2; }
-        else { o.pn2 = __longlong_as_double(q.pn2); o.dot = __longlong_as_double(q.dot); o.ns = __longlong_as_double(q.ns); o.rcp = -1.0; }
+    const double vmax = fmax(fabs((double)f.attr[j].wmin), fabs((double)f.attr[j].wmax)) + 1.0, lim = 2251799813685248.0 /* 2^51 */;
+    for (int p = blockIdx.x * 128 + threadIdx.x; p < n; p += gridDim.x * 128) {
+        UvPrep q;
+        uv_prepare(p, tv, (const int *)(S2 + f.o_d2c[t]), (const int *)(Z2 + f.o_v2d[t]), (const int *)(Z2 + f.o_v2d[0]),
+                   (const int32_t *)(S + f.o_corr[f.pos_attr]), q);
+        UvPrepD o; o.nd = q.nd; o.pd = q.pd; o.pn2 = o.dot = o.ns = o.rcp = 0.0;
+        if (q.pn2 != 0) {
+            const double dpn2 = (double)q.pn2, ddot = (double)q.dot, dns = (double)q.ns;
+            if ((fabs(ddot) + dns) * 2.0 * vmax < lim && dpn2 * vmax < lim && dpn2 < lim) { o.pn2 = dpn2; o.dot = ddot; o.ns = dns; o.rcp = 1.0 / dpn2; }
+            else { o.pn2 = __longlong_as_double(q.pn2); o.dot = __longlong_as_double(q.dot); o.ns = __longlong_as_double(q.ns); o.rcp = -1.0; }
+        }
+        ((UvPrepD *)(S + f.o_par[j]))[p] = o;
     }
-    ((UvPrepD *)(S2 + f.o_par[j]))[p] = o;
 }
 
 // TEX_COORDS_PORTABLE chain: one warp per (frame, attribute).  The recurrence is non-linear (integer
@@ -1004,7 +983,7 @@ __device__ __forceinline__ int32_t uv_div_fast(int32_t n, double y, double pn2, 
     return (int32_t)((uint32_t)(unsigned long long)(long long)qd + (uint32_t)n + (uint32_t)adj);
 }
 struct UvTile { UvPrepD prep[32]; int32_t corr[64]; uint8_t orient[32]; int pad[8]; };
-__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_uv(const DracoFrame *frames, DracoCounts *counts, uint8_t *S2, const Job *jobs, int njobs) {
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_uv(const DracoFrame *frames, DracoCounts *counts, uint8_t *S, const Job *jobs, int njobs) {
     __shared__ __align__(16) int ring_all[SERIAL_WARPS][UV_RING * 2];
     __shared__ UvTile tile_all[SERIAL_WARPS];
     const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
@@ -1014,8 +993,8 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_uv(const DracoFra
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int j = jb.what; const DracoAttr &a = f.attr[j];
     const int n = (int)counts[jb.frame].entries[a.table + 1], lane = threadIdx.x & 31;
-    const UvPrepD *prep = (const UvPrepD *)(S2 + f.o_par[j]); const int32_t *corr = (const int32_t *)(S2 + f.o_corr[j]);
-    int32_t *uv = (int32_t *)(S2 + f.o_val_attr[j]); const uint8_t *orient = S2 + f.o_auxbits[j];
+    const UvPrepD *prep = (const UvPrepD *)(S + f.o_par[j]); const int32_t *corr = (const int32_t *)(S + f.o_corr[j]);
+    int32_t *uv = (int32_t *)(S + f.o_corr[j]); const uint8_t *orient = S + f.o_auxbits[j];          // in place: a tile's corrections are staged before its values are stored
     const int32_t mn = a.wmin, mx = a.wmax;
     int nor = a.num_orient, status = 0;
     for (int base = 0; base < n; base += 32) {
@@ -1070,30 +1049,61 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_predict_uv(const DracoFra
     if (status && lane == 0) frame_fail(counts, jb.frame, status);
 }
 
-// GEOMETRIC_NORMAL, element-parallel (each entry depends only on finished positions).
-__global__ void __launch_bounds__(128) k_normals(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, const uint8_t *Z, uint8_t *S2, const uint8_t *Z2) {
+// GEOMETRIC_NORMAL, element-parallel (each entry depends only on finished positions); values in place over the corrections.
+__global__ void __launch_bounds__(128) k_normals(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S, const uint8_t *Z, const uint8_t *S2, const uint8_t *Z2) {
     const uint32_t fi = blockIdx.y, j = blockIdx.z;
     if (frame_dead(frames, counts, fi)) return;
     const DracoFrame &f = frames[fi];
     if ((int)j >= f.nattr || f.o_corr[j] == UVOL_NONE || f.attr[j].pred != 6) return;
-    const int t = f.attr[j].table + 1, n = (int)counts[fi].entries[t], p = blockIdx.x * 128 + threadIdx.x;
-    if (p >= n) return;
+    const int t = f.attr[j].table + 1, n = (int)counts[fi].entries[t];
     const TableView tv = make_view(f, t, S, Z);
-    normal_entry(p, tv, (const int *)(S2 + f.o_d2c[t]), (const int *)(Z2 + f.o_v2d[0]), (const int32_t *)(S2 + f.o_val_attr[f.pos_attr]),
-                 (const int32_t *)(S2 + f.o_corr[j]), S2 + f.o_auxbits[j], f.attr[j].wmin, (int32_t *)(S2 + f.o_val_attr[j]));
+    for (int p = blockIdx.x * 128 + threadIdx.x; p < n; p += gridDim.x * 128)
+        normal_entry(p, tv, (const int *)(S2 + f.o_d2c[t]), (const int *)(Z2 + f.o_v2d[0]), (const int32_t *)(S + f.o_corr[f.pos_attr]),
+                     (const int32_t *)(S + f.o_corr[j]), S + f.o_auxbits[j], f.attr[j].wmin, (int32_t *)(S + f.o_corr[j]));
 }
 
-// Per-point expansion + dequantisation into the output arrays.  grid = (ceil(maxP/256), frames, attrs)
+// Per-point expansion + dequantisation into the output arrays (a5): one thread per point walks point -> corner once and then, per
+// exported attribute, corner -> (attribute) vertex -> entry -> value -> fp32.  Output rows are written with streaming stores
+// (nothing on the device reads them again).   grid = (ceil(capP/256), frames); the per-frame attribute constants sit in shared memory.
+struct ExpandAttr { const int *voc, *v2d; const int32_t *val; float *out; int seq, nc, qbits, normalized, dtype; float qmin[4], qrange; };
 __global__ void __launch_bounds__(256) k_expand(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, const uint8_t *S2, const uint8_t *Z2, uint8_t *O) {
-    const uint32_t fi = blockIdx.y, j = blockIdx.z;
+    __shared__ ExpandAttr A[UVOL_MAX_ATTRS]; __shared__ int na;
+    const uint32_t fi = blockIdx.y;
     if (frame_dead(frames, counts, fi)) return;
     const DracoFrame &f = frames[fi];
-    if ((int)j >= f.nattr || f.attr[j].out_slot < 0) return;
-    const int P = (int)counts[fi].num_points, p = blockIdx.x * 256 + threadIdx.x;
-    if (p >= P) return;
-    const DracoAttr &a = f.attr[j]; const int t = a.table + 1;
-    const int *voc = t == 0 ? (const int *)(S + f.o_c2v) : (const int *)(S + f.o_ac2v[t - 1]);
-    expand_point(p, (const int *)(S2 + f.o_p2c), voc, (const int *)(Z2 + f.o_v2d[t]), a, (const int32_t *)(S2 + f.o_val_attr[j]), (float *)(O + f.out_attr[a.out_slot]));
+    const int P = (int)counts[fi].num_points;
+    if ((int)(blockIdx.x * 256) >= P) return;
+    if (threadIdx.x == 0) {
+        int k = 0;
+        for (int j = 0; j < f.nattr; j++) {
+            const DracoAttr &a = f.attr[j]; if (a.out_slot < 0) continue;
+            const int t = a.table + 1; ExpandAttr &e = A[k++];
+            e.voc = t == 0 ? (const int *)(S + f.o_c2v) : (const int *)(S + f.o_ac2v[t - 1]); e.v2d = (const int *)(Z2 + f.o_v2d[t]);
+            e.val = (const int32_t *)(S + f.o_corr[j]); e.out = (float *)(O + f.out_attr[a.out_slot]);
+            e.seq = a.seq; e.nc = a.nc; e.qbits = a.qbits; e.normalized = a.normalized; e.dtype = a.dtype; e.qrange = a.qrange;
+            for (int c = 0; c < 4; c++) e.qmin[c] = a.qmin[c];
+        }
+        na = k;
+    }
+    __syncthreads();
+    const int *p2c = (const int *)(S2 + f.o_p2c);
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < P; p += gridDim.x * 256) {
+        const int c = p2c[p];
+        for (int k = 0; k < na; k++) {
+            const ExpandAttr &e = A[k];
+            const int en = e.v2d[e.voc[c]] - 1; float *o = e.out + (size_t)p * e.nc;
+            if (e.seq == 2) {
+                const float delta = draco_dequant_delta(e.qrange, e.qbits);
+                for (int q = 0; q < e.nc; q++) __stcs(o + q, draco_dequant(e.val[en * e.nc + q], delta, e.qmin[q]));
+            } else if (e.seq == 3) {
+                float r[3]; draco_oct_to_unit(e.val[en * 2], e.val[en * 2 + 1], ((1 << e.qbits) - 1) - 1, r);
+                __stcs(o, r[0]); __stcs(o + 1, r[1]); __stcs(o + 2, r[2]);
+            } else {
+                const float tmax = e.dtype == 1 ? 127.f : e.dtype == 2 ? 255.f : e.dtype == 3 ? 32767.f : e.dtype == 4 ? 65535.f : e.dtype == 5 ? 2147483647.f : 4294967295.f;
+                for (int q = 0; q < e.nc; q++) { float v = (float)e.val[en * e.nc + q]; if (e.normalized && e.dtype >= 1 && e.dtype <= 6) v = UVOL_FDIV(v, tmax); __stcs(o + q, v); }
+            }
+        }
+    }
 }
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -1110,15 +1120,36 @@ struct GeoBatch {
     int n = 0, j_ransA = 0, j_rabsA = 0, j_trav = 0, j_ransB = 0, j_rabsB = 0, j_wrap = 0, j_uv = 0, j_end = 0;
     uint32_t max_alpha_ctx = 1, max_alpha_attr = 1, maxnad = 0, maxV = 0, maxF = 0; int maxattr = 0;
     uint64_t blob_bytes = 0, bytes_in = 0; DracoPlan pl; double parse_ms = 0; bool any_valence = false, any_standard = false;
+    uint64_t cap_s2 = 0, cap_z2 = 0, cap_out = 0;        // what this batch may use of the count-sized arenas (estimates, or the exact needs after a re-plan)
+    uint32_t replans = 0;
 };
 void uvol_geo_batch_free(GeoBatch *b) { delete b; }
+
+// Test hooks (read per batch): shrink the optimistic per-frame attribute-table capacity / the estimates of the count-sized arenas so
+// that ordinary meshes exercise the re-plan paths.
+static uint32_t cap_permille() { const char *e = getenv("UVOL_CAP_PERMILLE"); const int x = e ? atoi(e) : 1000; return (uint32_t)(x < 1 ? 1 : x); }
+static uint64_t est_scale(uint64_t v) { const char *e = getenv("UVOL_EST_PERMILLE"); const int x = e ? atoi(e) : 1000; return v * (uint64_t)(x < 1 ? 1 : x) / 1000; }
+
+// Sizes every arena of the batch from the planner's numbers (grow-only reservations).
+static int draco_reserve(uvol_ctx *ctx, int memory) {
+    GeoBatch &B = *ctx->geo; const DracoPlan &pl = B.pl; const size_t n = (size_t)B.n;
+    UVOL_CUDA(ctx, ctx->d_scratch.reserve(pl.scratch + 256));
+    UVOL_CUDA(ctx, ctx->d_zscratch.reserve(pl.zscratch + 256));
+    UVOL_CUDA(ctx, ctx->d_scratch2.reserve(B.cap_s2 + 256));
+    UVOL_CUDA(ctx, ctx->d_zscratch2.reserve(B.cap_z2 + 256));
+    UVOL_CUDA(ctx, ctx->d_out_geo.reserve(B.cap_out + 256));
+    UVOL_CUDA(ctx, ctx->d_counts.reserve(align_up(sizeof(DracoCounts) * n, 16) + sizeof(DracoBatchPlan) + 256));
+    UVOL_CUDA(ctx, ctx->h_counts.reserve(align_up(sizeof(DracoCounts) * n, 16) + sizeof(DracoBatchPlan) + 512 + sizeof(DracoFrame) * n));
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, ctx->ph_out->reserve(B.cap_out + 256));
+    return UVOL_OK;
+}
 
 static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n) {
     const double t_begin = now_ms();
     if (!ctx->geo) ctx->geo = new GeoBatch();
     GeoBatch &B = *ctx->geo;
     B.n = n; B.frames.assign((size_t)n, DracoFrame()); B.aux.clear(); B.aux.reserve((size_t)n * 2048); B.jobs.clear();
-    B.max_alpha_ctx = B.max_alpha_attr = 1; B.maxnad = B.maxV = B.maxF = 0; B.maxattr = 0; B.bytes_in = 0; B.any_valence = B.any_standard = false;
+    B.max_alpha_ctx = B.max_alpha_attr = 1; B.maxnad = B.maxV = B.maxF = 0; B.maxattr = 0; B.bytes_in = 0; B.any_valence = B.any_standard = false; B.replans = 0;
     std::vector<DracoFrame> &frames = B.frames; std::vector<uint32_t> &aux = B.aux;
     uint64_t blob_bytes = 0;
     for (int i = 0; i < n; i++) {
@@ -1126,6 +1157,9 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
         f.file_off = blob_bytes; f.file_len = (uint32_t)size[i]; B.bytes_in += size[i];
         blob_bytes = align_up(blob_bytes + size[i] + 8, 16);
         f.status = (data[i] && size[i] < (1ull << 31)) ? uvol_draco_parse(data[i], size[i], f, aux) : UVOL_ERR_ARG;
+        // resource limits (per item, before anything is reserved): a header may not ask for more faces than the configured cap, nor
+        // for absurdly more faces than the file has bytes (the densest real streams stay below one face per byte)
+        if (!f.status && ((uint64_t)f.nf > ctx->cfg.max_faces_per_frame || (uint64_t)f.nf > 4096 + 64ull * size[i])) f.status = UVOL_ERR_UNSUPPORTED;
         if (f.status) continue;
         if (f.trav == 2) B.any_valence = true; else B.any_standard = true;
         for (int k = 0; k < 6; k++) if (f.ctx[k].count && f.ctx[k].nnz > B.max_alpha_ctx) B.max_alpha_ctx = f.ctx[k].nnz;      // (table sizes follow the used symbols)
@@ -1147,7 +1181,8 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
             for (auto &t : pool) t.join();
         }
     }
-    draco_plan_phase1(frames, B.pl);
+    draco_plan_phase1(frames, B.pl, cap_permille());
+    B.cap_s2 = est_scale(B.pl.s2_est); B.cap_z2 = est_scale(B.pl.z2_est); B.cap_out = B.pl.out_index + est_scale(B.pl.out_est - B.pl.out_index);
     std::vector<Job> &jobs = B.jobs; jobs.reserve((size_t)n * 24);
     auto mark = [&]() { return (int)jobs.size(); };
     B.j_ransA = mark();
@@ -1157,8 +1192,7 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
     B.j_trav = mark();
     for (int i = 0; i < n; i++) {
         const DracoFrame &f = frames[i]; if (f.status) continue;
-        bool need[UVOL_MAX_ATTR_DATA + 1] = {true, false, false, false, false};
-        for (int j = 0; j < f.nattr; j++) if (f.attr[j].out_slot >= 0 || j == f.pos_attr) need[f.attr[j].table + 1] = true;
+        bool need[UVOL_MAX_ATTR_DATA + 1]; draco_tables_needed(f, need);
         for (uint32_t t = 0; t <= f.nad; t++) if (need[t]) jobs.push_back({(uint32_t)i, (int)t});
         if (f.nad > B.maxnad) B.maxnad = f.nad;
         if (f.nv_enc + f.nsplit > B.maxV) B.maxV = f.nv_enc + f.nsplit;
@@ -1166,11 +1200,11 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
         if (f.nattr > B.maxattr) B.maxattr = f.nattr;
     }
     B.j_ransB = mark();
-    for (int i = 0; i < n; i++) if (!frames[i].status) for (int j = 0; j < frames[i].nattr; j++) if (frames[i].attr[j].out_slot >= 0 || j == frames[i].pos_attr) jobs.push_back({(uint32_t)i, 16 + j});
+    for (int i = 0; i < n; i++) if (!frames[i].status) for (int j = 0; j < frames[i].nattr; j++) if (draco_attr_needed(frames[i], j)) jobs.push_back({(uint32_t)i, 16 + j});
     B.j_rabsB = mark();
     for (int i = 0; i < n; i++) if (!frames[i].status) for (int j = 0; j < frames[i].nattr; j++) if ((frames[i].attr[j].out_slot >= 0) && (frames[i].attr[j].pred == 5 || frames[i].attr[j].pred == 6)) jobs.push_back({(uint32_t)i, 16 + j});
     B.j_wrap = mark();
-    for (int i = 0; i < n; i++) if (!frames[i].status) for (int j = 0; j < frames[i].nattr; j++) { const DracoAttr &a = frames[i].attr[j]; if ((a.out_slot >= 0 || j == frames[i].pos_attr) && (a.pred == -2 || a.pred == 0 || a.pred == 1)) jobs.push_back({(uint32_t)i, j}); }
+    for (int i = 0; i < n; i++) if (!frames[i].status) for (int j = 0; j < frames[i].nattr; j++) { const DracoAttr &a = frames[i].attr[j]; if (draco_attr_needed(frames[i], j) && (a.pred == 0 || a.pred == 1)) jobs.push_back({(uint32_t)i, j}); }
     B.j_uv = mark();
     for (int i = 0; i < n; i++) if (!frames[i].status) for (int j = 0; j < frames[i].nattr; j++) if (frames[i].attr[j].out_slot >= 0 && frames[i].attr[j].pred == 5) jobs.push_back({(uint32_t)i, j});
     B.j_end = mark();
@@ -1179,11 +1213,7 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
     UVOL_CUDA(ctx, ctx->d_blob.reserve(blob_bytes + 64));
     UVOL_CUDA(ctx, ctx->d_desc.reserve(sizeof(DracoFrame) * (size_t)n));
     UVOL_CUDA(ctx, ctx->d_aux.reserve(aux.size() * 4));
-    UVOL_CUDA(ctx, ctx->d_counts.reserve(sizeof(DracoCounts) * (size_t)n));
-    UVOL_CUDA(ctx, ctx->h_counts.reserve(sizeof(DracoCounts) * (size_t)n));
     UVOL_CUDA(ctx, ctx->d_jobs.reserve(sizeof(Job) * (jobs.size() + 1)));
-    UVOL_CUDA(ctx, ctx->d_scratch.reserve(B.pl.scratch + 256));
-    UVOL_CUDA(ctx, ctx->d_zscratch.reserve(B.pl.zscratch + 256));
     UVOL_CUDA(ctx, ctx->h_desc.reserve(sizeof(DracoFrame) * (size_t)n + aux.size() * 4 + sizeof(Job) * (jobs.size() + 1)));
     B.parse_ms = now_ms() - t_begin;
     if (ctx->profile) cudaEventRecord(ctx->ev[0], st);
@@ -1196,23 +1226,26 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
     return UVOL_OK;
 }
 
-static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_upload) {
+// Enqueues the whole device pipeline of the resident batch on the ctx's streams: no host synchronisation inside.  Ends with the
+// small device -> host copy of the per-frame counts, the batch plan and the descriptors (with the offsets the device planner wrote).
+static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_upload, int *ev_out, int *i_seams_out, int *i_rans_out, int *i_rabs_out, uint32_t *launches_out) {
     GeoBatch &B = *ctx->geo; const int n = B.n;
     std::vector<DracoFrame> &frames = B.frames; DracoPlan &pl = B.pl;
     cudaStream_t st = ctx->s0;
     int ev = 1, i_seams = -1, i_rans = -1, i_rabs = -1;
     auto stamp = [&](const char *name) { if (ev < 32) g_geo_stage_names[ev - 1] = name; if (ctx->profile && ev < 32) cudaEventRecord(ctx->ev[ev], st); ev++; };
-    if (!fresh_upload && ctx->profile) cudaEventRecord(ctx->ev[0], st);
+    if (!first_attempt_of_fresh_upload && ctx->profile) cudaEventRecord(ctx->ev[0], st);
     uint8_t *hd = (uint8_t *)ctx->h_desc.p;
-    draco_plan_phase1(frames, pl);      // restores the phase-1 view of the descriptors (idempotent)
     memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
-    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(DracoCounts) * (size_t)n, st));
+    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, align_up(sizeof(DracoCounts) * (size_t)n, 16) + sizeof(DracoBatchPlan), st));
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_zscratch.p, 0, pl.zscratch + 256, st));
+    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_zscratch2.p, 0, B.cap_z2 + 256, st));
     stamp("h2d");
-    const DracoFrame *dF = (const DracoFrame *)ctx->d_desc.p; DracoCounts *dC = (DracoCounts *)ctx->d_counts.p;
+    DracoFrame *dF = (DracoFrame *)ctx->d_desc.p; DracoCounts *dC = (DracoCounts *)ctx->d_counts.p; DracoBatchPlan *dBP = (DracoBatchPlan *)((uint8_t *)dC + align_up(sizeof(DracoCounts) * (size_t)n, 16));      // (DracoCounts is 108 bytes: the plan's 64-bit fields need their own alignment)
     const uint8_t *dBlob = (const uint8_t *)ctx->d_blob.p; const uint32_t *dAux = (const uint32_t *)ctx->d_aux.p;
     uint8_t *dS = (uint8_t *)ctx->d_scratch.p, *dZ = (uint8_t *)ctx->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
+    uint8_t *dS2 = (uint8_t *)ctx->d_scratch2.p, *dZ2 = (uint8_t *)ctx->d_zscratch2.p, *dO = (uint8_t *)ctx->d_out_geo.p;
     uint32_t launches = 0;
     auto rans_words = [](uint32_t nnz) { return (int)(((size_t)(nnz + 1) * 16 + (10u << RANS_LUT_BITS) + 16 + 15) / 16 * 4); };
     auto rans_smem = [&](uint32_t alphabet) { return (size_t)rans_words(alphabet) * 4 * SERIAL_WARPS; };
@@ -1229,17 +1262,18 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     cudaStream_t sx = getenv("UVOL_NO_OVERLAP") ? ctx->s0 : ctx->s1;
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[0], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->sync_ev[0], 0));
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[0], sx);
-    if (B.j_trav - B.j_rabsA > 0) { k_rabs<<<nblk(B.j_trav - B.j_rabsA), 32 * SERIAL_WARPS, 0, sx>>>(dF, dC, dBlob, dS, nullptr, dJ + B.j_rabsA, B.j_trav - B.j_rabsA); launches++; }
+    if (B.j_trav - B.j_rabsA > 0) { k_rabs<<<nblk(B.j_trav - B.j_rabsA), 32 * SERIAL_WARPS, 0, sx>>>(dF, dC, dBlob, dS, dJ + B.j_rabsA, B.j_trav - B.j_rabsA); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[1], sx);
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[1], sx));
-    // The attribute symbol runs do not wait for the connectivity: they run to the coder's terminal state (k_rans, early
-    // mode) next to the connectivity walk; k_corr_settle adopts every run that came out with exactly the expected count.
+    // The attribute symbol runs do not wait for the connectivity: they run to the coder's terminal state (k_rans, early mode)
+    // next to the connectivity walk, straight into the attribute's correction array; a run that did not come out with exactly
+    // the expected count is decoded again, by count, once the count is known.
     static const bool no_early = getenv("UVOL_NO_EARLY_RANS") != nullptr;
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[2], sx);
-    if (!no_early && B.j_rabsB - B.j_ransB > 0) { k_rans<<<nblk(B.j_rabsB - B.j_ransB), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_attr), sx>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + B.j_ransB, B.j_rabsB - B.j_ransB, rans_words(B.max_alpha_attr), 1); launches++; }
+    if (!no_early && B.j_rabsB - B.j_ransB > 0) { k_rans<<<nblk(B.j_rabsB - B.j_ransB), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_attr), sx>>>(dF, dC, dBlob, dAux, dS, dJ + B.j_ransB, B.j_rabsB - B.j_ransB, rans_words(B.max_alpha_attr), 1); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[3], sx);
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[4], sx));
-    if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<nblk(B.j_rabsA - B.j_ransA), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, nullptr, dJ + B.j_ransA, B.j_rabsA - B.j_ransA, rans_words(B.max_alpha_ctx), 0); launches++; }
+    if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<nblk(B.j_rabsA - B.j_ransA), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, dJ + B.j_ransA, B.j_rabsA - B.j_ransA, rans_words(B.max_alpha_ctx), 0); launches++; }
     stamp("rans_ctx");
     stamp("rabs_seams(s1)"); i_seams = ev - 2;                                     // (stage slot of rabs_seams: timed on s1, filled in below)
     if (B.any_valence) {
@@ -1264,34 +1298,13 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     k_point_fan<0><<<dim3(gv, n), 128, 0, st>>>(dF, dC, dS, dZ, nullptr, nullptr); launches++;
     k_scan<<<dim3(n, 1), 1024, 0, st>>>(dF, dC, dS, 4); launches++;
     stamp("point_count");
-    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    UVOL_CUDA(ctx, cudaStreamSynchronize(st));
-    const DracoCounts *hC = (const DracoCounts *)ctx->h_counts.p;
-    draco_plan_phase2(frames, hC, pl);
-    UVOL_CUDA(ctx, ctx->d_out_geo.reserve(pl.out + 256));
-    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, ctx->ph_out->reserve(pl.out + 256));
-    UVOL_CUDA(ctx, ctx->d_scratch2.reserve(pl.scratch2 + 256));
-    UVOL_CUDA(ctx, ctx->d_zscratch2.reserve(pl.zscratch2 + 256));
-    // The traversal-record arena may be shared with the contexts of other windows (uvol_share_arenas): it is ours from here
-    // until our traversal kernel has finished; the prediction stages that follow and the result copy do not touch it.
-    std::unique_lock<std::mutex> p2_lock(ctx->p2->mu);
-    UVOL_CUDA(ctx, ctx->p2->d_frec.reserve(pl.tscratch + 256));
-    draco_plan_rebase_traversal(frames, (uint64_t)(uintptr_t)ctx->p2->d_frec.p - (uint64_t)(uintptr_t)ctx->d_scratch2.p);
-    memcpy(hd, frames.data(), sizeof(DracoFrame) * (size_t)n);
-    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc.p, hd, sizeof(DracoFrame) * (size_t)n, cudaMemcpyHostToDevice, st));
-    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_zscratch2.p, 0, pl.zscratch2 + 256, st));
-    stamp("counts_readback");
-    uint8_t *dS2 = (uint8_t *)ctx->d_scratch2.p, *dZ2 = (uint8_t *)ctx->d_zscratch2.p, *dO = (uint8_t *)ctx->d_out_geo.p;
-    uint32_t maxP = 1, maxN = 1;
-    for (int i = 0; i < n; i++) if (!frames[i].status && !hC[i].status) {
-        if (hC[i].num_points > maxP) maxP = hC[i].num_points;
-        if (hC[i].num_vertex_slots > maxN) maxN = hC[i].num_vertex_slots;
-        for (uint32_t k = 0; k < frames[i].nad; k++) if (hC[i].attr_vertices[k] > maxN) maxN = hC[i].attr_vertices[k];
-    }
-    // ---- phase 2.  Attribute entropy runs (sized from counts.expected) go to s1 and overlap the traversals.
+    // ---- the count-sized arrays are laid out on the device; everything below is enqueued without waiting for it
+    k_plan2<<<1, 1024, 0, st>>>(dF, dC, dBP, n, pl.out_index, B.cap_s2, B.cap_z2, B.cap_out); launches++;
+    stamp("plan2");
+    // ---- phase 2.  The aux bit runs (sized from counts.expected) go to s1 and overlap the traversals.
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[2], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->sync_ev[2], 0));
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[5], sx);
-    if (B.j_wrap - B.j_rabsB > 0) { k_rabs<<<nblk(B.j_wrap - B.j_rabsB), 32 * SERIAL_WARPS, 0, sx>>>(dF, dC, dBlob, dS, dS2, dJ + B.j_rabsB, B.j_wrap - B.j_rabsB); launches++; }
+    if (B.j_wrap - B.j_rabsB > 0) { k_rabs<<<nblk(B.j_wrap - B.j_rabsB), 32 * SERIAL_WARPS, 0, sx>>>(dF, dC, dBlob, dS, dJ + B.j_rabsB, B.j_wrap - B.j_rabsB); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[4], sx);
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[3], sx));
     k_point_fan<1><<<dim3(gv, n), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dO); launches++;
@@ -1302,86 +1315,106 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     }
     if (B.j_ransB - B.j_trav > 0) {
         const int ntj = B.j_ransB - B.j_trav;
-        k_corner_records<<<dim3((3 * B.maxF + 127) / 128, ntj), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dJ + B.j_trav); launches++;
-        k_face_entries<<<dim3((B.maxF + 127) / 128, ntj), 128, 0, st>>>(dF, dC, dS2, dJ + B.j_trav); launches++;
-        k_face_dups<<<dim3((B.maxF + 255) / 256, ntj), 256, 0, st>>>(dF, dC, dS2, dJ + B.j_trav); launches++;
-        stamp("corner_records");
-        const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((maxN + 31) / 32 + 4) & ~3u);
-        const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_STACK * 4) * TRAV_WARPS;
-        if (maxN >= (1u << 26)) { ctx->set_error("mesh too large for the traversal records"); return UVOL_ERR_UNSUPPORTED; }
+        k_face_records<<<dim3((B.maxF + 255) / 256, ntj), 256, 0, st>>>(dF, dC, dS, dZ, dJ + B.j_trav); launches++;
+        stamp("face_records");
+        uint32_t capN = B.maxV + 4;
+        for (int i = 0; i < n; i++) if (!frames[i].status) for (uint32_t t = 1; t <= frames[i].nad; t++) if (frames[i].table_cap[t] > capN) capN = frames[i].table_cap[t];
+        const int fwords = (int)(((B.maxF + 31) / 32 + 4) & ~3u), vwords = (int)(((capN + 31) / 32 + 4) & ~3u);
+        const size_t smem = ((size_t)(fwords + vwords) * 4 + TRAV_STACK * 4);
         // mode 0: both bitmaps in shared memory -- fastest while the walks of the batch need at most ~3 waves of the SMs' shared memory;
-        // mode 1: byte map + vertex -> entry map in global memory, every walk resident at once (measured at C3: 504 frames = 1512 walks of
-        // 77 KB: 211 ms in mode 0, 146 ms in mode 1; 252 frames: 130 vs 140 ms); mode 2 (faces in shared memory only) never wins, kept for experiments.
+        // mode 1: byte map + vertex -> entry map in global memory, every walk resident at once (large meshes / large batches)
         static const int force = getenv("UVOL_TRAV_GMAP") ? atoi(getenv("UVOL_TRAV_GMAP")) : -1;
         const size_t per_sm = (size_t)((ntj + ctx->num_sms - 1) / ctx->num_sms), fit = smem <= 200 * 1024 ? (200 * 1024) / smem : 0;
-        const size_t smem2 = ((size_t)fwords * 4 + TRAV_STACK * 4) * TRAV_WARPS;
-        int mode = force >= 0 ? force : (fit > 0 && per_sm <= 3 * fit ? 0 : 1);
-        if (mode == 2 && smem2 > 200 * 1024) mode = 1;
+        int mode = force >= 0 ? (force != 0) : (fit > 0 && per_sm <= 3 * fit ? 0 : 1);
         if (mode == 0 && fit == 0) mode = 1;
-        const unsigned tgrid = (ntj + TRAV_WARPS - 1) / TRAV_WARPS;
-        if (mode == 1) k_traverse<1><<<tgrid, 32 * TRAV_WARPS, TRAV_STACK * 4 * TRAV_WARPS, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
-        else if (mode == 2) {
-            if (smem2 > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            k_traverse<2><<<tgrid, 32 * TRAV_WARPS, smem2, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
-        } else {
+        if (mode == 1) k_traverse<1><<<ntj, 32, TRAV_STACK * 4, st>>>(dF, dC, dS, dZ, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
+        else {
             if (smem > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_traverse<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_traverse<0><<<tgrid, 32 * TRAV_WARPS, smem, st>>>(dF, dC, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
+            k_traverse<0><<<ntj, 32, smem, st>>>(dF, dC, dS, dZ, dS2, dZ2, dJ + B.j_trav, ntj, fwords, vwords);
         }
         launches++;
-    }
+    } else stamp("face_records");
     stamp("traverse");
-    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[7], st));          // the traversal records are dead from here on
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[4], 0));
-    if (B.j_rabsB - B.j_ransB > 0) {
+    if (B.j_rabsB - B.j_ransB > 0) {      // attribute runs whose early decode did not end on the expected count (normally none): again, by count
         const int nrj = B.j_rabsB - B.j_ransB;
-        k_corr_settle<<<dim3((4 * maxN + 1023) / 1024 + 1, nrj), 256, 0, st>>>(dF, dC, dS, dS2, dJ + B.j_ransB); launches++;
-        k_rans<<<nblk(nrj), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_attr), st>>>(dF, dC, dBlob, dAux, dS, dS2, dJ + B.j_ransB, nrj, rans_words(B.max_alpha_attr), 0); launches++;
+        k_rans<<<nblk(nrj), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_attr), st>>>(dF, dC, dBlob, dAux, dS, dJ + B.j_ransB, nrj, rans_words(B.max_alpha_attr), 0); launches++;
     }
-    stamp("corr_settle");
+    stamp("rans_recheck");
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[3], 0));
     stamp("rans_attr(s1)"); i_rans = ev - 2;                                     // (stage slots of rans_attr / rabs_aux: timed on s1)
     stamp("rabs_aux(s1)"); i_rabs = ev - 2;
-    const unsigned gn = (maxN + 127) / 128;
+    const unsigned gn = (pl.cap_entries + 127) / 128;
     k_parents<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
     stamp("parents");
-    if (B.j_uv - B.j_wrap > 0) { k_predict_wrap<<<nblk(B.j_uv - B.j_wrap), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dS2, dJ + B.j_wrap, B.j_uv - B.j_wrap); launches++; }
+    if (B.j_uv - B.j_wrap > 0) { k_predict_wrap<<<nblk(B.j_uv - B.j_wrap), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dS, dJ + B.j_wrap, B.j_uv - B.j_wrap); launches++; }
     stamp("predict_wrap");
-    k_uv_prepare<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
-    stamp("uv_prepare");
-    if (B.j_end - B.j_uv > 0) { k_predict_uv<<<nblk(B.j_end - B.j_uv), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dS2, dJ + B.j_uv, B.j_end - B.j_uv); launches++; }
-    stamp("predict_uv");
     k_normals<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
     stamp("normals");
-    k_expand<<<dim3((maxP + 255) / 256, n, B.maxattr), 256, 0, st>>>(dF, dC, dS, dS2, dZ2, dO); launches++;
+    k_uv_prepare<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
+    stamp("uv_prepare");
+    if (B.j_end - B.j_uv > 0) { k_predict_uv<<<nblk(B.j_end - B.j_uv), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dS, dJ + B.j_uv, B.j_end - B.j_uv); launches++; }
+    stamp("predict_uv");
+    k_expand<<<dim3((pl.cap_points + 255) / 256, n), 256, 0, st>>>(dF, dC, dS, dS2, dZ2, dO); launches++;
     stamp("expand");
     ctx->span_geo_end = ev - 1 < 32 ? ev - 1 : 31;
-    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts.p, dC, sizeof(DracoCounts) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->ph_out->p + pl.out_index, dO + pl.out_index, pl.out - pl.out_index, cudaMemcpyDeviceToHost, st));
-    stamp("d2h");
-    UVOL_CUDA(ctx, cudaEventSynchronize(ctx->sync_ev[7]));
-    p2_lock.unlock();
+    uint8_t *hC = (uint8_t *)ctx->h_counts.p; const size_t cbytes = align_up(sizeof(DracoCounts) * (size_t)n, 16) + sizeof(DracoBatchPlan);
+    UVOL_CUDA(ctx, cudaMemcpyAsync(hC, dC, cbytes, cudaMemcpyDeviceToHost, st));
+    UVOL_CUDA(ctx, cudaMemcpyAsync(hC + align_up(cbytes, 256), dF, sizeof(DracoFrame) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    *ev_out = ev; *i_seams_out = i_seams; *i_rans_out = i_rans; *i_rabs_out = i_rabs; *launches_out = launches;
+    return UVOL_OK;
+}
+
+static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_upload) {
+    GeoBatch &B = *ctx->geo; const int n = B.n;
+    std::vector<DracoFrame> &frames = B.frames; DracoPlan &pl = B.pl;
+    cudaStream_t st = ctx->s0;
+    int ev = 1, i_seams = -1, i_rans = -1, i_rabs = -1; uint32_t launches = 0, launches_total = 0;
+    const size_t cbytes = align_up(sizeof(DracoCounts) * (size_t)n, 16) + sizeof(DracoBatchPlan);
+    const DracoCounts *hC = nullptr; const DracoBatchPlan *hBP = nullptr; const DracoFrame *hF = nullptr;
+    for (int attempt = 0;; attempt++) {
+        draco_plan_phase1(frames, pl, cap_permille());      // (re)establishes the header-sized layout (idempotent; honours full_cap)
+        int rc = draco_reserve(ctx, memory); if (rc) return rc;
+        rc = draco_enqueue(ctx, memory, fresh_upload && attempt == 0, &ev, &i_seams, &i_rans, &i_rabs, &launches); if (rc) return rc;
+        launches_total += launches;
+        UVOL_CUDA(ctx, cudaStreamSynchronize(st));
+        hC = (const DracoCounts *)ctx->h_counts.p; hBP = (const DracoBatchPlan *)((const uint8_t *)ctx->h_counts.p + align_up(sizeof(DracoCounts) * (size_t)n, 16)); hF = (const DracoFrame *)((const uint8_t *)ctx->h_counts.p + align_up(cbytes, 256));
+        // Re-plan and run again when the optimistic sizing did not hold (at most twice: the second plan is exact / uses the full bounds).
+        bool again = false;
+        if (hBP->overflow) { B.cap_s2 = std::max(B.cap_s2, hBP->s2_need); B.cap_z2 = std::max(B.cap_z2, hBP->z2_need); B.cap_out = std::max(B.cap_out, hBP->out_need); again = true; }
+        for (int i = 0; i < n; i++) if (!frames[i].status && hC[i].status == UVOL_ERR_FRAME_CAPACITY && !frames[i].full_cap) { frames[i].full_cap = 1; again = true; }
+        if (!again || attempt >= 2) break;
+        B.replans++;
+        if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s3));
+    }
+    pl.scratch2 = hBP->s2_need; pl.zscratch2 = hBP->z2_need; pl.out = hBP->out_need;
+    uint8_t *dO = (uint8_t *)ctx->d_out_geo.p;
+    if (memory == UVOL_MEM_HOST && !hBP->overflow && pl.out > pl.out_index)
+        UVOL_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->ph_out->p + pl.out_index, dO + pl.out_index, pl.out - pl.out_index, cudaMemcpyDeviceToHost, st));
+    { if (ev < 32) g_geo_stage_names[ev - 1] = "d2h"; if (ctx->profile && ev < 32) cudaEventRecord(ctx->ev[ev], st); ev++; }
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));
     if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s3));
     UVOL_CUDA(ctx, cudaGetLastError());
-    // ---- results
+    // ---- results (offsets of the count-sized arrays: as written by the device planner)
     uint8_t *base = memory == UVOL_MEM_HOST ? (uint8_t *)ctx->ph_out->p : dO;
     uint64_t bytes_out = 0;
     for (int i = 0; i < n; i++) {
-        const DracoFrame &f = frames[i]; uvol_geometry &g = out[i];
+        const DracoFrame &f = frames[i], &df = hF[i]; uvol_geometry &g = out[i];
         memset(&g, 0, sizeof g);
         g.status = f.status ? f.status : hC[i].status;
+        if (g.status <= UVOL_ERR_FRAME_CAPACITY) g.status = UVOL_ERR_UNSUPPORTED;      // internal codes never leave the library
         if (g.status) continue;
         g.num_points = hC[i].num_points; g.num_faces = f.nf;
         g.index = (uint32_t *)(base + f.out_index); bytes_out += (uint64_t)f.nf * 12;
         for (int j = 0; j < f.nattr; j++) {
             const DracoAttr &a = f.attr[j]; if (a.out_slot < 0) continue;
-            float *p = (float *)(base + f.out_attr[a.out_slot]); bytes_out += (uint64_t)g.num_points * a.nc * 4;
+            float *p = (float *)(base + df.out_attr[a.out_slot]); bytes_out += (uint64_t)g.num_points * a.nc * 4;
             if (a.out_slot == 0) g.position = p; else if (a.out_slot == 1) g.normal = p; else if (a.out_slot == 2) g.uv = p; else { g.color = p; g.color_components = (uint32_t)a.nc; }
         }
     }
     uvol_stats &s = ctx->stats;
-    s.kernel_launches = launches; s.bytes_in = B.bytes_in; s.bytes_out = bytes_out;
-    s.scratch_bytes = pl.scratch + pl.zscratch + pl.scratch2 + pl.zscratch2 + pl.tscratch;
+    s.kernel_launches = launches_total; s.bytes_in = B.bytes_in; s.bytes_out = bytes_out;
+    s.scratch_bytes = pl.scratch + pl.zscratch + pl.scratch2 + pl.zscratch2;
     if (ctx->profile) {
         s.num_stages = (uint32_t)(ev - 1);
         for (int k = 0; k + 1 < ev && k < 24; k++) cudaEventElapsedTime(&s.stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);

@@ -1,19 +1,48 @@
 // uvol_api.cu -- context management and the small C-ABI utilities of libuvol_b200.so.
 #include <string.h>
+#include <stdlib.h>
 #include "uvol_ctx.h"
 
 extern "C" const char *uvol_geo_stage_name(int i);
 extern "C" const char *uvol_tex_stage_name(int i);
 extern "C" const char *uvol_corto_stage_name(int i);
 
-extern "C" int uvol_create(int device, uvol_ctx **out) {
+// Defaults of every tunable, then the environment overrides (SURVEY 5 "config / flags": the reference takes constructor arguments
+// only -- bufferDuration / intervalDuration, src/Player.ts:50-51 -- and picks the texture target from the GPU, KTX2Loader.js:591-689).
+extern "C" void uvol_config_default(uvol_config *cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = (uint32_t)sizeof *cfg;
+    cfg->texture_target = UVOL_TEX_RGBA32; cfg->corto_index_u16 = 0; cfg->staging_threads = 0;
+    cfg->max_faces_per_frame = 1ull << 24; cfg->max_texture_bytes = 1ull << 31;
+    cfg->buffer_duration_s = 4.0; cfg->interval_duration_s = 2.0;
+    auto env_u64 = [](const char *name, uint64_t &v) { const char *e = getenv(name); if (e && *e) { char *end = nullptr; const unsigned long long x = strtoull(e, &end, 0); if (end && *end == 0) v = x; } };
+    auto env_f64 = [](const char *name, double &v) { const char *e = getenv(name); if (e && *e) { char *end = nullptr; const double x = strtod(e, &end); if (end && *end == 0 && x > 0) v = x; } };
+    uint64_t t = cfg->texture_target, u16 = 0, thr = 0;
+    if (const char *e = getenv("UVOL_TEXTURE_TARGET")) {
+        if (!strcmp(e, "rgba32")) t = UVOL_TEX_RGBA32; else if (!strcmp(e, "etc1")) t = UVOL_TEX_ETC1; else if (!strcmp(e, "bc7")) t = UVOL_TEX_BC7; else env_u64("UVOL_TEXTURE_TARGET", t);
+    }
+    env_u64("UVOL_CORTO_INDEX_U16", u16); env_u64("UVOL_STAGING_THREADS", thr);
+    cfg->texture_target = (uint32_t)t; cfg->corto_index_u16 = (uint32_t)(u16 != 0); cfg->staging_threads = (uint32_t)thr;
+    env_u64("UVOL_MAX_FACES", cfg->max_faces_per_frame); env_u64("UVOL_MAX_TEXTURE_BYTES", cfg->max_texture_bytes);
+    env_f64("UVOL_BUFFER_DURATION", cfg->buffer_duration_s); env_f64("UVOL_INTERVAL_DURATION", cfg->interval_duration_s);
+}
+
+extern "C" int uvol_create(int device, uvol_ctx **out) { return uvol_create_with_config(device, nullptr, out); }
+
+extern "C" int uvol_get_config(const uvol_ctx *c, uvol_config *out) { if (!c || !out) return UVOL_ERR_ARG; *out = c->cfg; return UVOL_OK; }
+
+extern "C" int uvol_create_with_config(int device, const uvol_config *cfg, uvol_ctx **out) {
     if (!out) return UVOL_ERR_ARG;
+    if (cfg && cfg->struct_size != sizeof(uvol_config)) return UVOL_ERR_ARG;
+    if (cfg && cfg->texture_target > UVOL_TEX_BC7) return UVOL_ERR_ARG;
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return UVOL_ERR_CUDA;   // no CPU fallback
     if (cudaSetDevice(device) != cudaSuccess) return UVOL_ERR_CUDA;
     uvol_ctx *c = new uvol_ctx();
     c->device = device;
+    if (cfg) c->cfg = *cfg; else uvol_config_default(&c->cfg);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
     // s0 carries the geometry critical path and gets the highest priority: the block scheduler serves pending grids in
@@ -35,7 +64,7 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *db[] = {&c->d_blob, &c->d_desc, &c->d_aux, &c->d_counts, &c->d_scratch, &c->d_zscratch, &c->d_scratch2, &c->d_zscratch2, &c->own_p2.d_frec, &c->d_jobs, &c->d_out_geo,
+    DevBuf *db[] = {&c->d_blob, &c->d_desc, &c->d_aux, &c->d_counts, &c->d_scratch, &c->d_zscratch, &c->d_scratch2, &c->d_zscratch2, &c->d_jobs, &c->d_out_geo,
                     &c->d_tblob, &c->d_tdesc, &c->d_tslices, &c->d_tscratch, &c->d_out_tex,
                     &c->d_cblob, &c->d_cdesc, &c->d_cscratch, &c->d_czscratch, &c->d_out_corto, &c->d_ccounts, &c->d_caux};
     for (auto *b : db) b->release();
@@ -56,12 +85,10 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     delete c;
 }
 
-// Lets `ctx` use the phase-2 geometry scratch of `owner` (same device) instead of its own: one ctx per window of a sequence,
-// the largest arena exists once.  Calls on the sharing contexts may run concurrently (one host thread per ctx): the arena is
-// handed over under a mutex, so one window's phase 1 and result copies overlap another window's phase 2.
+// Kept for ABI compatibility: since the traversal records shrank to 32 bytes per face and alias the connectivity temporaries, a
+// sequence's scratch fits one context and windows no longer need a shared arena.  No effect.
 extern "C" int uvol_share_arenas(uvol_ctx *ctx, uvol_ctx *owner) {
     if (!ctx || !owner || ctx->device != owner->device) return UVOL_ERR_ARG;
-    ctx->p2 = owner->p2;
     return UVOL_OK;
 }
 

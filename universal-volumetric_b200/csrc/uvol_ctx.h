@@ -40,13 +40,6 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-// The traversal-record arena of the geometry path (16 B per corner + 32 B per face per corner table: more than half of a
-// batch's scratch, dead as soon as the traversal has finished).  A ctx normally owns one; contexts created for consecutive
-// WINDOWS of one sequence share one (uvol_share_arenas), under a mutex held from a window's corner-record kernels to the end
-// of its traversal.  Everything else (other scratch, outputs, inputs) stays per ctx, so the other window's connectivity
-// stages, prediction stages and result copies run concurrently.
-struct Phase2Arena { DevBuf d_frec; std::mutex mu; };
-
 struct GeoBatch; struct TexBatch; struct CortoBatch;
 void uvol_geo_batch_free(GeoBatch *); void uvol_tex_batch_free(TexBatch *); void uvol_corto_batch_free(CortoBatch *);
 
@@ -59,8 +52,8 @@ struct uvol_ctx {
     cudaStream_t s3 = nullptr;                    // early result copies (index buffers) next to the geometry kernels
     std::string err; std::mutex err_mu;           // the texture side of uvol_decode_v2_batch runs on a helper thread: error text is set under err_mu
     void set_error(const char *msg) { std::lock_guard<std::mutex> g(err_mu); err = msg; }
+    uvol_config cfg = {};                          // defaults + environment overrides (uvol_config_default), or the caller's (uvol_create_with_config)
     // geometry path
-    Phase2Arena own_p2; Phase2Arena *p2 = &own_p2;
     PinBuf h_blob, h_desc, h_aux, h_counts, h_out;
     DevBuf d_blob, d_desc, d_aux, d_counts, d_scratch, d_zscratch, d_scratch2, d_zscratch2, d_jobs;
     DevBuf d_out_geo;             // library-owned geometry outputs (valid until the next geometry batch on this ctx)

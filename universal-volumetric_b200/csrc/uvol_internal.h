@@ -14,7 +14,10 @@
 #define UVOL_MAX_ATTRS 6          // attributes per mesh (all decoders flattened)
 
 enum { UVOL_OK = 0, UVOL_ERR_TRUNCATED = -1, UVOL_ERR_CORRUPT = -2, UVOL_ERR_UNSUPPORTED = -3, UVOL_ERR_CUDA = -4,
-       UVOL_ERR_ARG = -5, UVOL_ERR_IO = -6 };
+       UVOL_ERR_ARG = -5, UVOL_ERR_IO = -6,
+       // internal (never returned to the caller): a frame outgrew its optimistic capacity / the batch outgrew the count-sized arenas.
+       // The launcher re-plans (full bounds for that frame / exact arena sizes) and runs the batch again.
+       UVOL_ERR_FRAME_CAPACITY = -100, UVOL_ERR_BATCH_CAPACITY = -101 };
 
 // ---- Draco ---------------------------------------------------------------------------------
 struct RansStream {          // one RAW rANS symbol run (SURVEY A.2 DecodeSymbols)
@@ -50,22 +53,36 @@ struct DracoFrame {
     RansStream ctx[6];
     int32_t nattr; DracoAttr attr[UVOL_MAX_ATTRS];
     int32_t pos_attr;                          // index of the POSITION attribute (parent of uv/normal predictors)
-    // ---- scratch arena byte offsets (filled by the host planner)
+    uint32_t full_cap, pad0;                   // 1: size the attribute-table arrays for the full bound (one attribute vertex per corner)
+    // ---- header-sized arenas S (uninitialised) and Z (zeroed per run): byte offsets filled by the host planner (draco_plan.h).
+    // S = [long-lived arrays][union region: connectivity temporaries | traversal records | prediction parents]
     uint64_t o_opp, o_c2v, o_lmc, o_hole, o_val, o_stack, o_ctxsym[6], o_invalid;
     uint64_t o_seambits[UVOL_MAX_ATTR_DATA], o_eos[UVOL_MAX_ATTR_DATA], o_vos[UVOL_MAX_ATTR_DATA], o_ac2v[UVOL_MAX_ATTR_DATA],
              o_afirst[UVOL_MAX_ATTR_DATA], o_acnt[UVOL_MAX_ATTR_DATA];
     uint64_t o_seamcnt;                    // per chunk of corners: how many carry a seam bit (k_seam_count)
-    uint64_t o_pcnt, o_pfirst, o_p2c;      // per-vertex point counts/offsets, dedup start corner, point -> corner
-    uint64_t o_d2c[UVOL_MAX_ATTR_DATA + 1], o_v2d[UVOL_MAX_ATTR_DATA + 1], o_frec[UVOL_MAX_ATTR_DATA + 1], o_tstack[UVOL_MAX_ATTR_DATA + 1], o_fvis[UVOL_MAX_ATTR_DATA + 1];
-    uint64_t o_corr[UVOL_MAX_ATTRS], o_val_attr[UVOL_MAX_ATTRS], o_par[UVOL_MAX_ATTRS], o_auxbits[UVOL_MAX_ATTRS];
-    uint64_t o_corr_early[UVOL_MAX_ATTRS]; uint32_t corr_early_cap[UVOL_MAX_ATTRS];   // phase-1 arena: symbols decoded before the entry counts are known (and the capacity in symbols)
-    // ---- outputs (device pointers as byte offsets into the output arena; filled after counts are known)
+    uint64_t o_pcnt, o_pfirst;             // per-vertex point counts/offsets, dedup start corner
+    uint64_t o_frec[UVOL_MAX_ATTR_DATA + 1], o_tstack[UVOL_MAX_ATTR_DATA + 1], o_fvis[UVOL_MAX_ATTR_DATA + 1];   // S, S, Z
+    uint64_t o_corr[UVOL_MAX_ATTRS], o_par[UVOL_MAX_ATTRS], o_auxbits[UVOL_MAX_ATTRS];      // S.  Values are reconstructed IN PLACE over the corrections.
+    uint32_t corr_cap[UVOL_MAX_ATTRS];     // capacity of o_corr[j] in symbols
+    uint32_t table_cap[UVOL_MAX_ATTR_DATA + 1];   // capacity in entries of table t (attribute vertices); [0] = encoded vertices + splits (exact bound)
+    // ---- count-sized arenas S2 / Z2 (zeroed) and the attribute part of the output arena: byte offsets filled ON THE DEVICE by
+    // k_plan2 once the connectivity kernels have produced the counts (and recomputed by the host from the final counts)
+    uint64_t o_p2c;                                                     // S2: point -> corner
+    uint64_t o_d2c[UVOL_MAX_ATTR_DATA + 1], o_v2d[UVOL_MAX_ATTR_DATA + 1];   // S2, Z2
+    // ---- outputs (byte offsets into the output arena): out_index header-sized (host), out_attr count-sized (device)
     uint64_t out_index, out_attr[4];
 };
 
-// Per-face record of one corner table (base or attribute), built element-parallel and consumed by
-// the serial traversal through a shared-memory window: 32 bytes per face.
-struct FaceRec { int32_t v[3]; int32_t o[3]; int32_t flags; int32_t pad; };   // vertex ids, opposite corners (-1: boundary/seam), bit k: vertex k on boundary
+// Per-face traversal record of one corner table (base or attribute): built element-parallel (k_face_records, k_face_dups),
+// consumed by the speculative depth-first traversal as one 32-byte load per lane.
+//   v[k]  vertex id of corner 3f+k in this table          o[k]  opposite corner of 3f+k (-1: boundary / seam)
+//   meta  bits 0-1  corner through which the walk enters f from face f-1 (3: none)      bits 2-3  same from face f+1
+//         bits 4-8  duplicate distance of the f-1 entry's tip vertex (k_face_dups)       bits 9-13 same for the f+1 entry
+//         bits 14-16 vertex of corner k lies on the table's boundary
+struct FaceRec { int32_t v[3]; int32_t o[3]; uint32_t meta; uint32_t pad; };
+
+// batch-level result of the device planner (lives behind the DracoCounts array)
+struct DracoBatchPlan { uint64_t s2_need, z2_need, out_need; uint32_t overflow, pad; };
 
 // per-frame state written by the kernels (counts the host reads back once per batch)
 struct DracoCounts {

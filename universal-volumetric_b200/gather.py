@@ -133,3 +133,110 @@ def frame_views(tables, arenas, rank, i):
             count *= s
         out[name] = a[off: off + 4 * count].view(dt).view(*shape)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Whole-shard gather (BASELINE configs[3]: one sequence frame-sharded across G GPUs, then gathered): geometry AND textures.
+# A rank's decoded shard is two contiguous spans of library-owned memory (the geometry output arena: every index buffer, then
+# the per-point arrays; the texture output arena: the segments back to back), so nothing is packed or staged: after one
+# all_gather of the small per-item tables, rank r's spans travel as two broadcasts straight out of the library's buffers into
+# every other rank's slot of one receive arena (an all-gather with per-rank sizes; NVLink / NVSwitch carries the payload).
+GCOLS = 8       # geometry rows: status, num_points, num_faces, off_index, off_position, off_normal, off_uv, span_bytes
+TCOLS = 8       # texture rows:  status, width, height, layers, format, has_alpha, off_data, bytes
+
+
+def _span(ptrs_and_sizes):
+    lo, hi = None, 0
+    for a, nb in ptrs_and_sizes:
+        if a and nb:
+            lo = a if lo is None else min(lo, a); hi = max(hi, a + nb)
+    return (lo or 0), (hi - lo if lo else 0)
+
+
+def shard_tables(geo, n_geo, tex, n_tex):
+    """Tables + spans of one rank's decoded shard.  Offsets in the tables are relative to the start of the rank's geometry span /
+    texture span.  -> (gtab int64[n_geo, GCOLS], ttab int64[n_tex, TCOLS], (geo_addr, geo_bytes), (tex_addr, tex_bytes))"""
+    gt = np.full((max(n_geo, 0), GCOLS), -1, np.int64); tt = np.full((max(n_tex, 0), TCOLS), -1, np.int64)
+    arrs = []
+    for i in range(n_geo):
+        g = geo[i]; gt[i, 0] = g.status
+        if g.status == 0:
+            arrs += [(_addr(g.index), g.num_faces * 12), (_addr(g.position), g.num_points * 12), (_addr(g.normal), g.num_points * 12), (_addr(g.uv), g.num_points * 8)]
+    gbase, gbytes = _span(arrs)
+    for i in range(n_geo):
+        g = geo[i]
+        if g.status == 0:
+            gt[i, 1], gt[i, 2] = g.num_points, g.num_faces
+            for col, p in enumerate((g.index, g.position, g.normal, g.uv), start=3):
+                a = _addr(p); gt[i, col] = a - gbase if a else -1
+    gt[:, 7] = gbytes
+    tbase, tbytes = _span([(_addr(t.data), int(t.bytes)) for t in tex[:n_tex] if t.status == 0])
+    for i in range(n_tex):
+        t = tex[i]; tt[i, 0] = t.status
+        if t.status == 0:
+            tt[i, 1:6] = (t.width, t.height, t.layers, t.format, t.has_alpha); tt[i, 6] = _addr(t.data) - tbase; tt[i, 7] = int(t.bytes)
+    return gt, tt, (gbase, gbytes), (tbase, tbytes)
+
+
+def all_gather_shard(geo, n_geo, tex, n_tex, device, group=None, arena=None):
+    """Gathers every rank's decoded shard on every rank.  Returns dict(gtabs=[world][n, GCOLS], ttabs=[world][n, TCOLS], arena=uint8 tensor
+    on `device`, geo_off=[world], tex_off=[world], bytes=[world]): rank r's geometry span starts at arena[geo_off[r]], its texture span at
+    arena[tex_off[r]].  `arena` (optional) is a caller-owned receive buffer that is reused when large enough."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cuda = torch.device(device).type == "cuda"
+    gt, tt, (gb, gn), (tb, tn) = shard_tables(geo, n_geo, tex, n_tex)
+    meta = torch.tensor([n_geo, n_tex, gn, tn], dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    metas = [[int(x) for x in m.cpu()] for m in metas]
+    mg, mt = max(m[0] for m in metas), max(m[1] for m in metas)
+    pad = torch.full((mg * GCOLS + mt * TCOLS,), -1, dtype=torch.int64, device=device)
+    pad[:n_geo * GCOLS] = torch.from_numpy(gt.reshape(-1)).to(device); pad[mg * GCOLS: mg * GCOLS + n_tex * TCOLS] = torch.from_numpy(tt.reshape(-1)).to(device)
+    tabs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(tabs, pad, group=group)
+    tabs = [t.cpu().numpy() for t in tabs]
+    gtabs = [tabs[r][: metas[r][0] * GCOLS].reshape(-1, GCOLS) for r in range(world)]
+    ttabs = [tabs[r][mg * GCOLS: mg * GCOLS + metas[r][1] * TCOLS].reshape(-1, TCOLS) for r in range(world)]
+    al = lambda v: (v + 255) // 256 * 256
+    geo_off, tex_off, cur = [], [], 0
+    for m in metas:
+        geo_off.append(cur); cur += al(m[2]); tex_off.append(cur); cur += al(m[3])
+    if arena is None or arena.numel() < cur:
+        arena = torch.empty(cur, dtype=torch.uint8, device=device)
+    for r in range(world):          # all-gather with per-rank sizes: the owner sends straight from the library's buffers
+        for off, nb, base in ((geo_off[r], metas[r][2], gb), (tex_off[r], metas[r][3], tb)):
+            if nb == 0:
+                continue
+            slot = arena[off: off + nb]
+            if r == rank:
+                src = arena_tensor(base, nb, device)
+                dist.broadcast(src, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+                slot.copy_(src)
+            else:
+                dist.broadcast(slot, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    return {"gtabs": gtabs, "ttabs": ttabs, "arena": arena, "geo_off": geo_off, "tex_off": tex_off, "bytes": [m[2] + m[3] for m in metas], "cuda": cuda}
+
+
+def shard_frame_views(G, rank, i):
+    """Typed views of geometry frame i of `rank` in a gathered arena (dict(index, position, normal, uv)), or None if it failed."""
+    import torch
+    row = G["gtabs"][rank][i]
+    if int(row[0]) != 0:
+        return None
+    P, F = int(row[1]), int(row[2]); a = G["arena"][G["geo_off"][rank]:]
+    out = {}
+    for name, col, dt, cnt in (("index", 3, torch.int32, F * 3), ("position", 4, torch.float32, P * 3), ("normal", 5, torch.float32, P * 3), ("uv", 6, torch.float32, P * 2)):
+        off = int(row[col])
+        out[name] = None if off < 0 else a[off: off + 4 * cnt].view(dt)
+    return out
+
+
+def shard_texture_view(G, rank, i):
+    """uint8 view of texture segment i of `rank` in a gathered arena (all layers back to back), or None if it failed."""
+    row = G["ttabs"][rank][i]
+    if int(row[0]) != 0:
+        return None
+    o = G["tex_off"][rank] + int(row[6])
+    return G["arena"][o: o + int(row[7])]

@@ -24,10 +24,21 @@ from . import _native as N
 class Context:
     """One context per GPU (mirrors one decoder instance per worker, DRACOLoader.js:439)."""
 
-    def __init__(self, device=0, profiling=False):
+    def __init__(self, device=0, profiling=False, texture_target=None, corto_index_u16=None, **limits):
+        """texture_target / corto_index_u16 / max_faces_per_frame / max_texture_bytes / buffer_duration_s / interval_duration_s override
+        the defaults (which already include the UVOL_* environment overrides, uvol_config_default)."""
         L = N.lib()
         h = ctypes.c_void_p()
-        rc = L.uvol_create(int(device), ctypes.byref(h))
+        cfg = N.Config(); L.uvol_config_default(ctypes.byref(cfg))
+        if texture_target is not None:
+            cfg.texture_target = int(texture_target)
+        if corto_index_u16 is not None:
+            cfg.corto_index_u16 = int(bool(corto_index_u16))
+        for k, v in limits.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown uvol_config field {k}")
+            setattr(cfg, k, v)
+        rc = L.uvol_create_with_config(int(device), ctypes.byref(cfg), ctypes.byref(h))
         if rc != 0 or not h:
             raise N.UvolError(f"uvol_create(device={device}) failed with status {rc}: a CUDA device is required "
                               "(there is no CPU fallback)")
@@ -57,6 +68,10 @@ class Context:
         if self._L.uvol_share_host_outputs(self._h, owner._h) != 0:
             raise N.UvolError("uvol_share_host_outputs failed")
         self._owner_host = owner
+
+    def config(self):
+        cfg = N.Config(); self._L.uvol_get_config(self._h, ctypes.byref(cfg))
+        return {k: getattr(cfg, k) for k, _ in N.Config._fields_}
 
     def flush_l2(self):
         self._L.uvol_flush_l2(self._h)
