@@ -35,7 +35,11 @@ enum uvol_memory { UVOL_MEM_DEVICE = 0, UVOL_MEM_HOST = 1 };
 /* Target texture format (the reference picks it from the GPU's capabilities, getTranscoderFormat / FORMAT_OPTIONS,
  * src/lib/KTX2Loader.js:591-689).  RGBA32 is the parity target and the reference's own fallback (:682-687).  ETC1 is the
  * `etc1Supported` / opaque `etc2Supported` choice (:619-636; an RGB ETC2 texture of ETC1S content is its ETC1 blocks): 8 bytes per
- * 4x4 block in block raster order, layers back to back; opaque ETC1S sources only (others report UVOL_STATUS_UNSUPPORTED per item). */
+ * 4x4 block in block raster order, layers back to back; opaque ETC1S sources only (others report UVOL_STATUS_UNSUPPORTED per item).
+ * BC7 is what those options select for ETC1S *and* UASTC sources on a desktop GPU with EXT_texture_compression_bptc (BC7_M5 /
+ * RGBA_BPTC_Format, :602-604): 16 bytes per 4x4 block in block raster order, layers back to back; ETC1S (with or without alpha) ->
+ * BC7 mode 5, UASTC -> the BC7 mode with the same subset shapes and weight grid (csrc/bc7_core.h).  Not bit-identical to the
+ * reference's transcoder (whose tables are not in its tree): validated by an independent BC7 decoder, bounds in tests/test_bc7.py. */
 enum uvol_texture_format { UVOL_TEX_RGBA32 = 0, UVOL_TEX_ETC1 = 1, UVOL_TEX_BC7 = 2 };
 
 /* Result of one geometry frame.  Replaces the Draco worker reply
@@ -62,7 +66,7 @@ typedef struct uvol_texture {
     uint32_t width, height, layers;
     uint32_t format;       /* uvol_texture_format */
     uint32_t has_alpha, dfd_transfer, dfd_flags;
-    uint8_t *data;         /* RGBA32: u8[layers * width * height * 4]; ETC1: u8[layers * ceil(w/4) * ceil(h/4) * 8] */
+    uint8_t *data;         /* RGBA32: u8[layers * width * height * 4]; ETC1: u8[layers * ceil(w/4) * ceil(h/4) * 8]; BC7: ... * 16 */
     uint64_t bytes;
 } uvol_texture;
 

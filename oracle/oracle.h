@@ -61,6 +61,10 @@ typedef struct {
 int uvo_ktx2_decode(const uint8_t *data, size_t len, uvo_ktx2_image *out);
 void uvo_ktx2_free(uvo_ktx2_image *m);
 
+/* ---- BC7 (BPTC) decoder, all eight modes: the independent check of the product's UVOL_TEX_BC7 target (bc7_decode.c). */
+int uvo_bc7_decode_block(const uint8_t *block16, uint8_t *rgba64);
+int uvo_bc7_decode_image(const uint8_t *blocks, uint32_t w, uint32_t h, uint8_t *rgba);
+
 /* ---- thread-pooled batch drivers for the CPU baseline (frames / segments are independent,
  * mirroring the <=4-worker design of DRACOLoader.js:24,312-364 and WorkerPool.js:7).
  * Return the number of items that decoded OK; checksum (optional) gets an FNV over outputs. */

@@ -99,3 +99,12 @@ def oracle_ktx2(blob, keep_debug=False):
         out["selector_idx"] = np.ctypeslib.as_array(m.selector_idx, (m.layers, nb)).copy()
     L.uvo_ktx2_free(ctypes.byref(m))
     return out
+
+
+def oracle_bc7_image(blocks, width, height):
+    """Decodes BC7 blocks (block-raster order, u8[nblocks, 16]) with the oracle's independent BC7 decoder -> (u8[h, w, 4], bad blocks)."""
+    L = lib()
+    L.uvo_bc7_decode_image.argtypes = [ctypes.c_char_p, c_u32, c_u32, ctypes.c_void_p]; L.uvo_bc7_decode_image.restype = c_int
+    out = np.zeros((height, width, 4), np.uint8)
+    bad = L.uvo_bc7_decode_image(np.ascontiguousarray(blocks, dtype=np.uint8).tobytes(), width, height, out.ctypes.data)
+    return out, bad

@@ -6,6 +6,7 @@
 #include "../../universal-volumetric_b200/csrc/uvol_internal.h"
 #include "../../universal-volumetric_b200/csrc/basis_core.h"
 #include "../../universal-volumetric_b200/csrc/uastc_core.h"
+#include "../../universal-volumetric_b200/csrc/bc7_core.h"
 
 extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
 
@@ -15,12 +16,14 @@ static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba
 extern "C" int basis_emu_decode(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, rgba, w, h, layers, 0); }
 // target ETC1: *rgba receives layers * blocks * 8 bytes (opaque ETC1S files only)
 extern "C" int basis_emu_decode_etc1(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 1); }
+// target BC7: *blocks receives layers * blocks * 16 bytes (ETC1S with or without alpha, UASTC)
+extern "C" int basis_emu_decode_bc7(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 2); }
 static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers, int etc1) {
     std::vector<uint8_t> padded(len + 64, 0); memcpy(padded.data(), data, len);   // the launcher pads the blob the same way
     const uint8_t *file = padded.data();
     Ktx2File f; memset(&f, 0, sizeof f); std::vector<Ktx2Slice> slices;
     int rc = uvol_ktx2_parse(file, len, 0, f, slices); if (rc) return rc;
-    if (f.is_uastc && etc1) return UVOL_ERR_UNSUPPORTED;
+    if (f.is_uastc && etc1 == 1) return UVOL_ERR_UNSUPPORTED;
     if (f.is_uastc) {          // the kernel's per-block function (uastc_core.h) over every block, Zstd levels inflated by the product's decoder
         const uint32_t nblk = f.bx * f.by;
         std::vector<uint8_t> inflated; const uint8_t *level = file + f.level_off;
@@ -31,6 +34,17 @@ static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba
             level = inflated.data();
         }
         UastcShared T; uastc_fill_tables(T);
+        if (etc1 == 2) {          // the BC7 kernel's per-block function (bc7_core.h)
+            Bc7Shared B7; bc7_fill_tables(B7);
+            uint8_t *out = (uint8_t *)malloc((size_t)f.layers * nblk * 16 + 16);
+            for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
+                uint32_t w[4], o[4]; memcpy(w, level + ((size_t)L * nblk + bi) * 16, 16);
+                if (!uastc_to_bc7(T, B7, w[0], w[1], w[2], w[3], o)) { free(out); return UVOL_ERR_CORRUPT; }
+                memcpy(out + ((size_t)L * nblk + bi) * 16, o, 16);
+            }
+            *rgba = out; *w = f.width; *h = f.height; *layers = f.layers;
+            return UVOL_OK;
+        }
         uint8_t *out = (uint8_t *)malloc((size_t)f.layers * f.width * f.height * 4 + 16);
         for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
             uint32_t w[4]; memcpy(w, level + ((size_t)L * nblk + bi) * 16, 16);
@@ -72,6 +86,17 @@ static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba
         }
     }
     *w = f.width; *h = f.height; *layers = f.layers;
+    if (etc1 == 2) {            // the BC7 kernel's per-block function (bc7_core.h etc1s_to_bc7)
+        Bc7Shared B7; bc7_fill_tables(B7);
+        *rgba = (uint8_t *)malloc((size_t)f.layers * nblk * 16 + 16);
+        for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
+            uint32_t o[4];
+            if (f.has_alpha) etc1s_to_bc7(B7, eps[ep[L][bi]], sels[sel[L][bi]], true, eps[ep[f.layers + L][bi]], sels[sel[f.layers + L][bi]], o);
+            else etc1s_to_bc7(B7, eps[ep[L][bi]], sels[sel[L][bi]], false, 0, 0, o);
+            memcpy(*rgba + ((size_t)L * nblk + bi) * 16, o, 16);
+        }
+        return 0;
+    }
     if (etc1) {                 // the kernel's repack function (basis_core.h etc1s_to_etc1) over every block
         if (f.has_alpha) return UVOL_ERR_UNSUPPORTED;
         *rgba = (uint8_t *)malloc((size_t)f.layers * nblk * 8 + 8);

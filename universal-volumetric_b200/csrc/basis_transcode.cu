@@ -14,11 +14,14 @@
 #include <thread>
 #include "uvol_ctx.h"
 #include "basis_core.h"
+#include "bc7_core.h"
 
 int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
 extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
 int uvol_uastc_launch(int device, const Ktx2File *dF, int32_t *status2, const uint8_t *dBlob, uint8_t *dOut, const uint32_t *dLayerList, int nlayers,
-                      uint32_t max_blocks, cudaStream_t st);
+                      uint32_t max_blocks, int target, cudaStream_t st);
+int uvol_texture_tables_ready(int device);
+const uint32_t *uvol_bc7_tables_device();
 
 namespace {
 
@@ -203,6 +206,32 @@ __global__ void __launch_bounds__(256) k_etc1s_blocks_etc1(const Ktx2File *files
     ((uint2 *)(O + f.o_rgba + (size_t)L * nblk * 8))[bi] = make_uint2(w.x, w.y);
 }
 
+// Block -> BC7 mode 5 (target format BC7, src/lib/KTX2Loader.js:602-604): 4 B (8 B with an alpha slice) of indices in, one 16-byte block
+// out per thread; a warp writes 512 contiguous bytes.  grid = (ceil(nblk / 256), layer list); per-block logic in bc7_core.h.
+__global__ void __launch_bounds__(256) k_etc1s_blocks_bc7(const Ktx2File *files, const TexState *state, const Ktx2Slice *slices, const uint32_t *layer_list,
+                                                          const uint8_t *S, uint8_t *O, const uint32_t *bc7_tables) {
+    __shared__ Bc7Shared B7;
+    for (uint32_t i = threadIdx.x; i < sizeof(Bc7Shared) / 4; i += 256) ((uint32_t *)&B7)[i] = bc7_tables[i];
+    __syncthreads();
+    const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
+    const Ktx2File &f = files[fi];
+    if (f.status || state[fi].status || f.is_uastc) return;
+    const uint32_t nblk = f.bx * f.by, bi = blockIdx.x * 256 + threadIdx.x;
+    if (bi >= nblk) return;
+    const Ktx2Slice &sl = slices[f.first_slice + L];
+    const uint32_t *eps = (const uint32_t *)(S + f.o_endpoints), *sels = (const uint32_t *)(S + f.o_selectors);
+    const uint32_t ecm = f.endpoint_count - 1, scm = f.selector_count - 1;
+    const uint32_t ei = min((uint32_t)((const uint16_t *)(S + sl.o_ep))[bi], ecm), si = min((uint32_t)((const uint16_t *)(S + sl.o_sel))[bi], scm);
+    uint32_t aep = 0, asel = 0;
+    if (f.has_alpha) {
+        const Ktx2Slice &al = slices[f.first_slice + f.layers + L];
+        aep = eps[min((uint32_t)((const uint16_t *)(S + al.o_ep))[bi], ecm)]; asel = sels[min((uint32_t)((const uint16_t *)(S + al.o_sel))[bi], scm)];
+    }
+    uint32_t o[4];
+    etc1s_to_bc7(B7, eps[ei], sels[si], f.has_alpha != 0, aep, asel, o);
+    __stcs((uint4 *)(O + f.o_rgba + (size_t)L * nblk * 16) + bi, make_uint4(o[0], o[1], o[2], o[3]));
+}
+
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 uint64_t take(uint64_t &cur, uint64_t bytes) { uint64_t o = cur; cur = (cur + bytes + 127) / 128 * 128; return o; }
 
@@ -241,7 +270,9 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
         const uint64_t nblk = (uint64_t)f.bx * f.by;
         if (nblk > B.max_blocks) B.max_blocks = (uint32_t)nblk;
         if (target == UVOL_TEX_ETC1 && (f.is_uastc || f.has_alpha)) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }   // ETC1 target: opaque ETC1S sources only
-        f.o_rgba = take(o, target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * nblk * 8 : (uint64_t)f.layers * f.width * f.height * 4);
+        const uint64_t out_bytes = target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * nblk * 8 : (target == UVOL_TEX_BC7 ? (uint64_t)f.layers * nblk * 16 : (uint64_t)f.layers * f.width * f.height * 4);
+        if (out_bytes > ctx->cfg.max_texture_bytes) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }      // resource limit, per item
+        f.o_rgba = take(o, out_bytes);
         if (f.is_uastc) { for (uint32_t L = 0; L < f.layers; L++) B.uastc_layers.push_back(((uint32_t)i << 12) | L); continue; }   // no entropy stage, no scratch
         B.any_alpha |= f.has_alpha != 0;
         if (f.endpoint_count + f.selector_count > B.max_codebook) B.max_codebook = f.endpoint_count + f.selector_count;
@@ -322,7 +353,10 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
     stamp();
     if (nsl) { k_etc1s_resolve<<<dim3(nb4, B.any_alpha ? 2 : 1), 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dSl, dS, n); launches++; }
     stamp();
-    if (nll && B.target == UVOL_TEX_ETC1) { k_etc1s_blocks_etc1<<<dim3((B.max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO); launches++; }
+    if (nll && B.target == UVOL_TEX_BC7) {
+        UVOL_CUDA(ctx, (cudaError_t)uvol_texture_tables_ready(ctx->device));
+        k_etc1s_blocks_bc7<<<dim3((B.max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO, uvol_bc7_tables_device()); launches++;
+    } else if (nll && B.target == UVOL_TEX_ETC1) { k_etc1s_blocks_etc1<<<dim3((B.max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO); launches++; }
     else if (nll) {
         const dim3 grid((B.max_blocks + 256 * ETC1S_CHUNKS - 1) / (256 * ETC1S_CHUNKS), (unsigned)nll);
         const size_t cb = (size_t)B.max_codebook * 4;
@@ -332,7 +366,7 @@ static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_
         } else k_etc1s_blocks<false><<<grid, 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO);
         launches++;
     }
-    if (nul) { UVOL_CUDA(ctx, (cudaError_t)uvol_uastc_launch(ctx->device, dF, (int32_t *)dSt, dBlob, dO, dUL, (int)nul, B.max_blocks, st)); launches++; }
+    if (nul) { UVOL_CUDA(ctx, (cudaError_t)uvol_uastc_launch(ctx->device, dF, (int32_t *)dSt, dBlob, dO, dUL, (int)nul, B.max_blocks, B.target, st)); launches++; }
     stamp();
     ctx->span_tex_end = ev - 1;
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
@@ -359,7 +393,8 @@ static int ktx2_finish(uvol_ctx *ctx, int memory, uvol_texture *out, uvol_stats 
         if (t.status) continue;
         t.width = f.width; t.height = f.height; t.layers = f.layers; t.format = (uint32_t)B.target; t.has_alpha = f.has_alpha;
         t.dfd_transfer = f.dfd_transfer; t.dfd_flags = f.dfd_flags;
-        t.bytes = B.target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * f.bx * f.by * 8 : (uint64_t)f.layers * f.width * f.height * 4; t.data = base + f.o_rgba; bytes_out += t.bytes;
+        t.bytes = B.target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * f.bx * f.by * 8 : (B.target == UVOL_TEX_BC7 ? (uint64_t)f.layers * f.bx * f.by * 16 : (uint64_t)f.layers * f.width * f.height * 4);
+        t.data = base + f.o_rgba; bytes_out += t.bytes;
     }
     sx.kernel_launches = B.launches; sx.bytes_in = B.bytes_in; sx.bytes_out = bytes_out; sx.scratch_bytes = B.scratch;
     if (ctx->profile) {
@@ -380,7 +415,7 @@ static int ktx2_run(uvol_ctx *ctx, int memory, uvol_texture *out, bool fresh_upl
 
 extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target_format, int memory, uvol_texture *out) {
     if (!ctx || !out || n < 0 || (n > 0 && (!data || !size)) || n >= (1 << 19)) return UVOL_ERR_ARG;
-    if (target_format != UVOL_TEX_RGBA32 && target_format != UVOL_TEX_ETC1) { ctx->set_error("target formats: UVOL_TEX_RGBA32, UVOL_TEX_ETC1"); return UVOL_ERR_UNSUPPORTED; }
+    if (target_format != UVOL_TEX_RGBA32 && target_format != UVOL_TEX_ETC1 && target_format != UVOL_TEX_BC7) { ctx->set_error("target formats: UVOL_TEX_RGBA32, UVOL_TEX_ETC1, UVOL_TEX_BC7"); return UVOL_ERR_UNSUPPORTED; }
     UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->stats, 0, sizeof ctx->stats);
     if (n == 0) { if (ctx->tex) ctx->tex->n = 0; return UVOL_OK; }

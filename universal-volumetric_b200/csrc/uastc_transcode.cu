@@ -13,6 +13,7 @@
 #include <mutex>
 #include "uvol_ctx.h"
 #include "uastc_core.h"
+#include "bc7_core.h"
 
 namespace {
 
@@ -60,20 +61,67 @@ __global__ void __launch_bounds__(256) k_uastc_blocks(const Ktx2File *files, int
     }
 }
 
+// UASTC -> BC7 (UVOL_TEX_BC7): same traversal of the blocks, 16 bytes out per block in block raster order (a warp stores 512
+// contiguous bytes); per-block logic in bc7_core.h.
+__device__ uint32_t g_bc7_tables[sizeof(Bc7Shared) / 4];
+__global__ void __launch_bounds__(256) k_uastc_blocks_bc7(const Ktx2File *files, int32_t *status2, const uint8_t *blob, uint8_t *O, const uint32_t *layer_list) {
+    __shared__ UastcShared T; __shared__ Bc7Shared B7;
+    for (uint32_t i = threadIdx.x; i < sizeof(UastcShared) / 4; i += 256) ((uint32_t *)&T)[i] = g_tables[i];
+    for (uint32_t i = threadIdx.x; i < sizeof(Bc7Shared) / 4; i += 256) ((uint32_t *)&B7)[i] = g_bc7_tables[i];
+    __shared__ struct { const uint8_t *src0; uint8_t *dst; uint32_t nblk, fi, skip; } K;
+    if (threadIdx.x == 0) {
+        const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
+        const Ktx2File &f = files[fi];
+        K.skip = f.status || !f.is_uastc; K.fi = fi; K.nblk = f.bx * f.by;
+        K.src0 = blob + f.file_off + f.level_off + (size_t)L * K.nblk * 16;
+        K.dst = O + f.o_rgba + (size_t)L * K.nblk * 16;
+    }
+    __syncthreads();
+    if (K.skip) return;
+    const uint32_t nblk = K.nblk, fi = K.fi;
+    const uint8_t *src0 = K.src0; uint8_t *dst = K.dst;
+    const bool aligned = (((uintptr_t)src0) & 15) == 0;
+#pragma unroll 1
+    for (uint32_t k = 0; k < UASTC_CHUNKS; k++) {
+        const uint32_t bi = (blockIdx.x * UASTC_CHUNKS + k) * 256 + threadIdx.x;
+        if (bi >= nblk) return;
+        const uint8_t *src = src0 + (size_t)bi * 16;
+        uint4 blk;
+        if (aligned) blk = __ldcs((const uint4 *)src);
+        else { uint32_t w[4]; for (int q = 0; q < 4; q++) w[q] = src[4 * q] | (src[4 * q + 1] << 8) | (src[4 * q + 2] << 16) | ((uint32_t)src[4 * q + 3] << 24); blk = make_uint4(w[0], w[1], w[2], w[3]); }
+        uint32_t o[4];
+        if (!uastc_to_bc7(T, B7, blk.x, blk.y, blk.z, blk.w, o)) { status2[2 * fi] = UVOL_ERR_CORRUPT; continue; }
+        __stcs((uint4 *)(dst + (size_t)bi * 16), make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+
 bool g_tables_ready[16] = {};
 }  // namespace
 
+__device__ uint32_t g_bc7_tables_etc1s[sizeof(Bc7Shared) / 4];      // second image for the ETC1S kernel in basis_transcode.cu (separate translation unit)
+const uint32_t *uvol_bc7_tables_device() { uint32_t *p = nullptr; cudaGetSymbolAddress((void **)&p, g_bc7_tables_etc1s); return p; }
+
 // status2: the launcher's per-file {status, aux} pairs.  layer list entries: file << 12 | layer.
-int uvol_uastc_launch(int device, const Ktx2File *dF, int32_t *status2, const uint8_t *dBlob, uint8_t *dOut, const uint32_t *dLayerList, int nlayers,
-                      uint32_t max_blocks, cudaStream_t st) {
+// Uploads the table images once per device (synchronous).
+int uvol_texture_tables_ready(int device) {
     static std::mutex table_mu;
     std::lock_guard<std::mutex> table_lock(table_mu);
-    if (device < 0 || device >= 16 || !g_tables_ready[device]) {      // once per device, synchronous
-        UastcShared h; uastc_fill_tables(h);
-        const cudaError_t e = cudaMemcpyToSymbol(g_tables, &h, sizeof h);
-        if (e != cudaSuccess) return (int)e;
-        if (device >= 0 && device < 16) g_tables_ready[device] = true;
-    }
+    if (device >= 0 && device < 16 && g_tables_ready[device]) return 0;
+    UastcShared h; uastc_fill_tables(h);
+    cudaError_t e = cudaMemcpyToSymbol(g_tables, &h, sizeof h);
+    if (e != cudaSuccess) return (int)e;
+    Bc7Shared b; bc7_fill_tables(b);
+    e = cudaMemcpyToSymbol(g_bc7_tables, &b, sizeof b); if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(g_bc7_tables_etc1s, &b, sizeof b); if (e != cudaSuccess) return (int)e;
+    if (device >= 0 && device < 16) g_tables_ready[device] = true;
+    return 0;
+}
+
+int uvol_uastc_launch(int device, const Ktx2File *dF, int32_t *status2, const uint8_t *dBlob, uint8_t *dOut, const uint32_t *dLayerList, int nlayers,
+                      uint32_t max_blocks, int target, cudaStream_t st) {
+    const int rc = uvol_texture_tables_ready(device); if (rc) return rc;
+    const dim3 grid((max_blocks + 256 * UASTC_CHUNKS - 1) / (256 * UASTC_CHUNKS), (unsigned)nlayers);
+    if (target == UVOL_TEX_BC7) { k_uastc_blocks_bc7<<<grid, 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList); return 0; }
     k_uastc_blocks<<<dim3((max_blocks + 256 * UASTC_CHUNKS - 1) / (256 * UASTC_CHUNKS), (unsigned)nlayers), 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList);
     return 0;
 }
