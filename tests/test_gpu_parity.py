@@ -249,6 +249,20 @@ def test_windows_share_the_traversal_arena(uv):
     c1.close(); c0.close()
 
 
+@pytest.mark.parametrize("fmt", ["uastc", "etc1s"])
+def test_sharded_decode_and_gather_equal_single_gpu(uv, fmt):
+    """BASELINE configs[3] / SURVEY 8e: one sequence frame-sharded over 2 GPUs + NCCL gather of the whole decoded shards == the same
+    sequence decoded by one GPU, byte for byte (tests/tools/gather_check.py under torchrun).  Needs 2 GPUs."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    port = 29000 + os.getpid() % 2000
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(ROOT, "tests", "tools", "gather_check.py"), "35", "3000", fmt], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("GATHER_IDENTICAL") == 2, (r.stdout[-800:], r.stderr[-800:])
+
+
 def test_playback_from_manifest(uv, ctx, tmp_path):
     """a V2 manifest on disk played through V2Playback (leaky-bucket look-ahead -> batched decode -> per-tick frame /
     segment / layer selection); what the renderer would show is the oracle's decode of the right file and layer."""

@@ -168,6 +168,68 @@ def test_two_rank_final_gather_gloo():
     assert all(ok for _, ok, _ in got) and all(shape == (2, 5, 8) for _, _, shape in got)
 
 
+class _T:        # stands in for uvol_texture
+    pass
+
+
+def _fake_shard(rank):
+    """(geometry results, texture results, truth) of a rank: region-major geometry arena like the library's, textures back to back."""
+    import ctypes
+    import numpy as np
+    res, truth, arena = _fake_results(rank, 2 + rank)
+    rng = np.random.default_rng(500 + rank)
+    tex, ttruth = [], []
+    sizes = [(8 + 4 * i, 12, 2 + rank) for i in range(3 - rank)] + [None]                # one failed segment at the end
+    tarena = np.zeros(sum((w * h * l * 4 + 127) // 128 * 128 for w, h, l in [x for x in sizes if x]) + 128, np.uint8); cur = 0
+    for sz in sizes:
+        t = _T()
+        if sz is None:
+            t.status = -2; t.width = t.height = t.layers = t.format = t.has_alpha = 0; t.bytes = 0; t.data = None; ttruth.append(None)
+        else:
+            w, h, l = sz; n = w * h * l * 4
+            vals = rng.integers(0, 256, n, dtype=np.uint8); tarena[cur:cur + n] = vals
+            t.status = 0; t.width, t.height, t.layers, t.format, t.has_alpha, t.bytes = w, h, l, 0, 0, n
+            t.data = ctypes.c_void_p(tarena.ctypes.data + cur); cur += (n + 127) // 128 * 128; ttruth.append(vals)
+        tex.append(t)
+    return res, tex, truth, ttruth, (arena, tarena)
+
+
+def _shard_gather_worker(rank, world, port, q):
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gather = importlib.import_module("universal-volumetric_b200.gather")
+    res, tex, _, _, keep = _fake_shard(rank)
+    G = gather.all_gather_shard(res, len(res), tex, len(tex), "cpu")
+    ok = True
+    for r in range(world):
+        _, _, tr, ttr, _ = _fake_shard(r)
+        for i, t in enumerate(tr):
+            v = gather.shard_frame_views(G, r, i)
+            ok &= (v is None) if t is None else all(np.array_equal(v[k].numpy().ravel(), t[k]) for k in t)
+        for i, t in enumerate(ttr):
+            v = gather.shard_texture_view(G, r, i)
+            ok &= (v is None) if t is None else np.array_equal(v.numpy(), t)
+    G2 = gather.all_gather_shard(res, len(res), tex, len(tex), "cpu", arena=G["arena"])          # the receive arena is reused
+    ok &= G2["arena"].data_ptr() == G["arena"].data_ptr()
+    q.put((rank, bool(ok), [int(b) for b in G["bytes"]]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_whole_shard_gather_gloo():
+    """BASELINE configs[3]'s gather: geometry AND textures of every rank's shard end up on every rank byte for byte (ragged shards,
+    failed items included); every rank reports the same per-rank byte counts."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn"); q = ctx.Queue(); port = 33000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_shard_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=180) for _ in range(2)]
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert all(ok for _, ok, _ in got) and got[0][2] == got[1][2] and all(b > 0 for b in got[0][2])
+
+
 def test_playback_buffer_follows_the_reference_scheduler():
     """V2Playback vs src/V2/player.ts:272-323,388-470,531-562 with a stub decoder: the look-ahead stays `bufferDuration` seconds
     ahead, every frame / segment is requested exactly once, a failed mesh is skipped, a missing segment shows the mesh untextured,

@@ -606,42 +606,51 @@ __device__ __forceinline__ TableView make_view(const DracoFrame &f, int t, const
 // reserved arenas fails every frame with UVOL_ERR_BATCH_CAPACITY (the launcher re-plans and runs the batch again).  One block.
 __global__ void __launch_bounds__(1024) k_plan2(DracoFrame *frames, DracoCounts *counts, DracoBatchPlan *bp, int n, uint64_t out_index_bytes,
                                                 uint64_t cap_s2, uint64_t cap_z2, uint64_t cap_out) {
-    __shared__ unsigned long long wsum[3][32]; __shared__ unsigned long long carry[3]; __shared__ int over;
+    __shared__ unsigned long long wsum[6][32]; __shared__ unsigned long long carry[6], total[4]; __shared__ int over;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) { carry[0] = 0; carry[1] = 0; carry[2] = out_index_bytes; over = 0; }
-    __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + tid;
-        Plan2Cursor sz{0, 0, 0};
-        if (i < n && !frame_dead(frames, counts, i)) {
-            for (uint32_t t = 1; t <= frames[i].nad; t++) if (counts[i].attr_vertices[t - 1] > frames[i].table_cap[t]) counts[i].status = UVOL_ERR_FRAME_CAPACITY;
-            draco_plan2_frame(frames[i], counts[i], sz, false);
-        }
-        unsigned long long x[3] = {sz.s, sz.z, sz.o}, inc[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            unsigned long long v = x[k];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
-            inc[k] = v;
-            if (lane == 31) wsum[k][w] = v;
+    // pass 0 totals the per-slot output sizes (the region bases need them), pass 1 assigns
+    for (int pass = 0; pass < 2; pass++) {
+        if (tid == 0) {
+            carry[0] = carry[1] = 0;
+            if (pass == 0) { for (int k = 0; k < 4; k++) carry[2 + k] = 0; }
+            else { uint64_t base[4], need; const uint64_t t4[4] = {total[0], total[1], total[2], total[3]}; draco_plan2_regions(out_index_bytes, t4, base, &need);
+                   for (int k = 0; k < 4; k++) { carry[2 + k] = base[k]; bp->slot_base[k] = base[k]; bp->slot_bytes[k] = total[k]; } bp->out_need = need; }
         }
         __syncthreads();
-        Plan2Cursor cur;
-        {
-            unsigned long long pre[3];
+        for (int base = 0; base < n; base += 1024) {
+            const int i = base + tid;
+            Plan2Cursor sz{0, 0, {0, 0, 0, 0}};
+            if (i < n && !frame_dead(frames, counts, i)) {
+                if (pass == 0) for (uint32_t t = 1; t <= frames[i].nad; t++) if (counts[i].attr_vertices[t - 1] > frames[i].table_cap[t]) counts[i].status = UVOL_ERR_FRAME_CAPACITY;
+                draco_plan2_frame(frames[i], counts[i], sz, false);
+            }
+            unsigned long long x[6] = {sz.s, sz.z, sz.o[0], sz.o[1], sz.o[2], sz.o[3]}, inc[6];
 #pragma unroll
-            for (int k = 0; k < 3; k++) { pre[k] = carry[k]; for (int j = 0; j < w; j++) pre[k] += wsum[k][j]; pre[k] += inc[k] - x[k]; }
-            cur.s = pre[0]; cur.z = pre[1]; cur.o = pre[2];
+            for (int k = 0; k < 6; k++) {
+                unsigned long long v = x[k];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+                inc[k] = v;
+                if (lane == 31) wsum[k][w] = v;
+            }
+            __syncthreads();
+            unsigned long long pre[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) { pre[k] = carry[k]; for (int j = 0; j < w; j++) pre[k] += wsum[k][j]; pre[k] += inc[k] - x[k]; }
+            if (pass == 1 && i < n && !frame_dead(frames, counts, i)) {
+                Plan2Cursor cur{pre[0], pre[1], {pre[2], pre[3], pre[4], pre[5]}};
+                draco_plan2_frame(frames[i], counts[i], cur, true);
+            }
+            __syncthreads();
+            if (tid == 1023) for (int k = 0; k < 6; k++) carry[k] = pre[k] + x[k];
+            __syncthreads();
         }
-        if (i < n && !frame_dead(frames, counts, i)) draco_plan2_frame(frames[i], counts[i], cur, true);
-        __syncthreads();
-        if (tid == 1023) { carry[0] = cur.s; carry[1] = cur.z; carry[2] = cur.o; }          // the last thread's cursors have advanced past its own frame
+        if (tid == 0 && pass == 0) for (int k = 0; k < 4; k++) total[k] = carry[2 + k];
         __syncthreads();
     }
     if (tid == 0) {
-        bp->s2_need = carry[0]; bp->z2_need = carry[1]; bp->out_need = carry[2];
-        over = carry[0] > cap_s2 || carry[1] > cap_z2 || carry[2] > cap_out;
+        bp->s2_need = carry[0]; bp->z2_need = carry[1];
+        over = carry[0] > cap_s2 || carry[1] > cap_z2 || bp->out_need > cap_out;
         bp->overflow = (uint32_t)over;
     }
     __syncthreads();
@@ -1066,7 +1075,7 @@ __global__ void __launch_bounds__(128) k_normals(const DracoFrame *frames, const
 // exported attribute, corner -> (attribute) vertex -> entry -> value -> fp32.  Output rows are written with streaming stores
 // (nothing on the device reads them again).   grid = (ceil(capP/256), frames); the per-frame attribute constants sit in shared memory.
 struct ExpandAttr { const int *voc, *v2d; const int32_t *val; float *out; int seq, nc, qbits, normalized, dtype; float qmin[4], qrange; };
-__global__ void __launch_bounds__(256) k_expand(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, const uint8_t *S2, const uint8_t *Z2, uint8_t *O) {
+__global__ void __launch_bounds__(256) k_expand(const DracoFrame *frames, const DracoCounts *counts, const uint8_t *S, const uint8_t *S2, const uint8_t *Z2, uint8_t *O, uint32_t slot_mask) {
     __shared__ ExpandAttr A[UVOL_MAX_ATTRS]; __shared__ int na;
     const uint32_t fi = blockIdx.y;
     if (frame_dead(frames, counts, fi)) return;
@@ -1076,7 +1085,7 @@ __global__ void __launch_bounds__(256) k_expand(const DracoFrame *frames, const 
     if (threadIdx.x == 0) {
         int k = 0;
         for (int j = 0; j < f.nattr; j++) {
-            const DracoAttr &a = f.attr[j]; if (a.out_slot < 0) continue;
+            const DracoAttr &a = f.attr[j]; if (a.out_slot < 0 || !((slot_mask >> a.out_slot) & 1u)) continue;
             const int t = a.table + 1; ExpandAttr &e = A[k++];
             e.voc = t == 0 ? (const int *)(S + f.o_c2v) : (const int *)(S + f.o_ac2v[t - 1]); e.v2d = (const int *)(Z2 + f.o_v2d[t]);
             e.val = (const int32_t *)(S + f.o_corr[j]); e.out = (float *)(O + f.out_attr[a.out_slot]);
@@ -1228,7 +1237,8 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
 
 // Enqueues the whole device pipeline of the resident batch on the ctx's streams: no host synchronisation inside.  Ends with the
 // small device -> host copy of the per-frame counts, the batch plan and the descriptors (with the offsets the device planner wrote).
-static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_upload, int *ev_out, int *i_seams_out, int *i_rans_out, int *i_rabs_out, uint32_t *launches_out) {
+static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_upload, int *ev_out, int *i_seams_out, int *i_rans_out, int *i_rabs_out, uint32_t *launches_out, bool *attrs_copied) {
+    *attrs_copied = false;
     GeoBatch &B = *ctx->geo; const int n = B.n;
     std::vector<DracoFrame> &frames = B.frames; DracoPlan &pl = B.pl;
     cudaStream_t st = ctx->s0;
@@ -1301,6 +1311,11 @@ static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_
     // ---- the count-sized arrays are laid out on the device; everything below is enqueued without waiting for it
     k_plan2<<<1, 1024, 0, st>>>(dF, dC, dBP, n, pl.out_index, B.cap_s2, B.cap_z2, B.cap_out); launches++;
     stamp("plan2");
+    if (memory == UVOL_MEM_HOST) {      // the batch plan (region bases of the output arena) travels to the host now: it is read below, once everything is enqueued
+        UVOL_CUDA(ctx, ctx->h_aux.reserve(256));
+        UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_aux.p, dBP, sizeof(DracoBatchPlan), cudaMemcpyDeviceToHost, st));
+        UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[5], st));
+    }
     // ---- phase 2.  The aux bit runs (sized from counts.expected) go to s1 and overlap the traversals.
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[2], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->sync_ev[2], 0));
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[5], sx);
@@ -1351,17 +1366,39 @@ static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_
     stamp("predict_wrap");
     k_normals<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
     stamp("normals");
+    // positions, normals and colours are final: expand them now so that their spans of the output arena can travel to the host
+    // while the UV chain still runs
+    const dim3 gexp((pl.cap_points + 255) / 256, n);
+    k_expand<<<gexp, 256, 0, st>>>(dF, dC, dS, dS2, dZ2, dO, 0xbu); launches++;
+    stamp("expand_pnc");
+    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[7], st));
     k_uv_prepare<<<dim3(gn, n, B.maxattr), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dZ2); launches++;
     stamp("uv_prepare");
     if (B.j_end - B.j_uv > 0) { k_predict_uv<<<nblk(B.j_end - B.j_uv), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dS, dJ + B.j_uv, B.j_end - B.j_uv); launches++; }
     stamp("predict_uv");
-    k_expand<<<dim3((pl.cap_points + 255) / 256, n), 256, 0, st>>>(dF, dC, dS, dS2, dZ2, dO); launches++;
+    k_expand<<<gexp, 256, 0, st>>>(dF, dC, dS, dS2, dZ2, dO, 0x4u); launches++;
     stamp("expand");
+    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[8], st));
     ctx->span_geo_end = ev - 1 < 32 ? ev - 1 : 31;
     uint8_t *hC = (uint8_t *)ctx->h_counts.p; const size_t cbytes = align_up(sizeof(DracoCounts) * (size_t)n, 16) + sizeof(DracoBatchPlan);
     UVOL_CUDA(ctx, cudaMemcpyAsync(hC, dC, cbytes, cudaMemcpyDeviceToHost, st));
     UVOL_CUDA(ctx, cudaMemcpyAsync(hC + align_up(cbytes, 256), dF, sizeof(DracoFrame) * (size_t)n, cudaMemcpyDeviceToHost, st));
     *ev_out = ev; *i_seams_out = i_seams; *i_rans_out = i_rans; *i_rabs_out = i_rabs; *launches_out = launches;
+    if (memory == UVOL_MEM_HOST) {
+        // Everything is enqueued; the stream keeps running while this thread waits for the plan (ready once the connectivity stages
+        // are done) and then queues the result copies on s3 behind the kernels that finish each span.
+        UVOL_CUDA(ctx, cudaEventSynchronize(ctx->sync_ev[5]));
+        const DracoBatchPlan plan = *(const DracoBatchPlan *)ctx->h_aux.p;
+        if (!plan.overflow && plan.out_need <= B.cap_out && plan.out_need > pl.out_index) {
+            uint8_t *hO = (uint8_t *)ctx->ph_out->p;
+            const uint64_t first = plan.slot_base[0], mid = plan.slot_base[2], end = plan.out_need;       // [position | normal | colour] then [uv]
+            UVOL_CUDA(ctx, cudaStreamWaitEvent(ctx->s3, ctx->sync_ev[7], 0));
+            if (mid > first) UVOL_CUDA(ctx, cudaMemcpyAsync(hO + first, dO + first, mid - first, cudaMemcpyDeviceToHost, ctx->s3));
+            UVOL_CUDA(ctx, cudaStreamWaitEvent(ctx->s3, ctx->sync_ev[8], 0));
+            if (end > mid) UVOL_CUDA(ctx, cudaMemcpyAsync(hO + mid, dO + mid, end - mid, cudaMemcpyDeviceToHost, ctx->s3));
+            *attrs_copied = true;
+        }
+    }
     return UVOL_OK;
 }
 
@@ -1369,13 +1406,13 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     GeoBatch &B = *ctx->geo; const int n = B.n;
     std::vector<DracoFrame> &frames = B.frames; DracoPlan &pl = B.pl;
     cudaStream_t st = ctx->s0;
-    int ev = 1, i_seams = -1, i_rans = -1, i_rabs = -1; uint32_t launches = 0, launches_total = 0;
+    int ev = 1, i_seams = -1, i_rans = -1, i_rabs = -1; uint32_t launches = 0, launches_total = 0; bool attrs_copied = false;
     const size_t cbytes = align_up(sizeof(DracoCounts) * (size_t)n, 16) + sizeof(DracoBatchPlan);
     const DracoCounts *hC = nullptr; const DracoBatchPlan *hBP = nullptr; const DracoFrame *hF = nullptr;
     for (int attempt = 0;; attempt++) {
         draco_plan_phase1(frames, pl, cap_permille());      // (re)establishes the header-sized layout (idempotent; honours full_cap)
         int rc = draco_reserve(ctx, memory); if (rc) return rc;
-        rc = draco_enqueue(ctx, memory, fresh_upload && attempt == 0, &ev, &i_seams, &i_rans, &i_rabs, &launches); if (rc) return rc;
+        rc = draco_enqueue(ctx, memory, fresh_upload && attempt == 0, &ev, &i_seams, &i_rans, &i_rabs, &launches, &attrs_copied); if (rc) return rc;
         launches_total += launches;
         UVOL_CUDA(ctx, cudaStreamSynchronize(st));
         hC = (const DracoCounts *)ctx->h_counts.p; hBP = (const DracoBatchPlan *)((const uint8_t *)ctx->h_counts.p + align_up(sizeof(DracoCounts) * (size_t)n, 16)); hF = (const DracoFrame *)((const uint8_t *)ctx->h_counts.p + align_up(cbytes, 256));
@@ -1389,7 +1426,7 @@ static int draco_run(uvol_ctx *ctx, int memory, uvol_geometry *out, bool fresh_u
     }
     pl.scratch2 = hBP->s2_need; pl.zscratch2 = hBP->z2_need; pl.out = hBP->out_need;
     uint8_t *dO = (uint8_t *)ctx->d_out_geo.p;
-    if (memory == UVOL_MEM_HOST && !hBP->overflow && pl.out > pl.out_index)
+    if (memory == UVOL_MEM_HOST && !hBP->overflow && pl.out > pl.out_index && !attrs_copied)
         UVOL_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->ph_out->p + pl.out_index, dO + pl.out_index, pl.out - pl.out_index, cudaMemcpyDeviceToHost, st));
     { if (ev < 32) g_geo_stage_names[ev - 1] = "d2h"; if (ctx->profile && ev < 32) cudaEventRecord(ctx->ev[ev], st); ev++; }
     UVOL_CUDA(ctx, cudaStreamSynchronize(st));

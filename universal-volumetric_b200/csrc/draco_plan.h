@@ -114,9 +114,11 @@ static inline void draco_plan_phase1(std::vector<DracoFrame> &frames, DracoPlan 
     pl.scratch = s; pl.zscratch = z; pl.s2_est = s2; pl.z2_est = z2; pl.out_est = o + oa;
 }
 
-// The count-sized arrays of one frame, laid out from the three cursors (S2, Z2, output arena).  assign = false only advances
-// the cursors (sizes are independent of the start because every array is padded to 128 bytes).
-struct Plan2Cursor { uint64_t s, z, o; };
+// The count-sized arrays of one frame, laid out from the cursors (S2, Z2, and one per output slot: the output arena is region-major,
+// see DracoBatchPlan).  assign = false only advances the cursors (sizes are independent of the start because every array is padded
+// to 128 bytes).
+struct Plan2Cursor { uint64_t s, z, o[4]; };
+#define UVOL_SLOT_ORDER {0, 1, 3, 2}          // regions in the arena: position, normal, colour, uv (uv is finished last)
 UVOL_HD void draco_plan2_frame(DracoFrame &f, const DracoCounts &c, Plan2Cursor &cur, bool assign) {
     if (f.status || c.status) return;
     const uint64_t P = c.num_points;
@@ -131,14 +133,24 @@ UVOL_HD void draco_plan2_frame(DracoFrame &f, const DracoCounts &c, Plan2Cursor 
     }
     if (assign) for (int k = 0; k < 4; k++) f.out_attr[k] = UVOL_NONE;
     for (int j = 0; j < f.nattr; j++) if (f.attr[j].out_slot >= 0) {
-        off = plan_take(cur.o, P * (uint64_t)f.attr[j].nc * 4);
-        if (assign) f.out_attr[f.attr[j].out_slot] = off;
+        const int k = f.attr[j].out_slot;
+        off = plan_take(cur.o[k], P * (uint64_t)f.attr[j].nc * 4);
+        if (assign) f.out_attr[k] = off;
     }
+}
+// Region bases from the per-slot totals (both on the device and on the host).
+UVOL_HD void draco_plan2_regions(uint64_t out_index_bytes, const uint64_t total[4], uint64_t base[4], uint64_t *out_need) {
+    const int order[4] = UVOL_SLOT_ORDER; uint64_t cur = out_index_bytes;
+    for (int i = 0; i < 4; i++) { base[order[i]] = cur; cur += total[order[i]]; }
+    *out_need = cur;
 }
 
 // Host: the exact layout from the final counts (identical to what k_plan2 wrote into the device descriptors).
 static inline void draco_plan_phase2(std::vector<DracoFrame> &frames, const DracoCounts *counts, DracoPlan &pl) {
-    Plan2Cursor cur{0, 0, pl.out_index};
+    Plan2Cursor tot{0, 0, {0, 0, 0, 0}};
+    for (size_t i = 0; i < frames.size(); i++) draco_plan2_frame(frames[i], counts[i], tot, false);
+    Plan2Cursor cur{0, 0, {0, 0, 0, 0}};
+    draco_plan2_regions(pl.out_index, tot.o, cur.o, &pl.out);
     for (size_t i = 0; i < frames.size(); i++) draco_plan2_frame(frames[i], counts[i], cur, true);
-    pl.scratch2 = cur.s; pl.zscratch2 = cur.z; pl.out = cur.o;
+    pl.scratch2 = cur.s; pl.zscratch2 = cur.z;
 }

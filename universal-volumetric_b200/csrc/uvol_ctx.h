@@ -47,7 +47,7 @@ struct uvol_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t s0 = nullptr, s1 = nullptr;
-    cudaEvent_t ev[32] = {}, aux_ev[8] = {}, tex_ev[8] = {}, sync_ev[8] = {};
+    cudaEvent_t ev[32] = {}, aux_ev[8] = {}, tex_ev[8] = {}, sync_ev[12] = {};
     cudaStream_t s2 = nullptr;
     cudaStream_t s3 = nullptr;                    // early result copies (index buffers) next to the geometry kernels
     std::string err; std::mutex err_mu;           // the texture side of uvol_decode_v2_batch runs on a helper thread: error text is set under err_mu

@@ -82,7 +82,9 @@ struct DracoFrame {
 struct FaceRec { int32_t v[3]; int32_t o[3]; uint32_t meta; uint32_t pad; };
 
 // batch-level result of the device planner (lives behind the DracoCounts array)
-struct DracoBatchPlan { uint64_t s2_need, z2_need, out_need; uint32_t overflow, pad; };
+// The output arena is region-major: [index buffers of all frames][positions of all frames][normals][colours][uvs], so a finished
+// attribute of the whole batch is one contiguous span that can start its way to the host while later stages still run.
+struct DracoBatchPlan { uint64_t s2_need, z2_need, out_need; uint64_t slot_base[4], slot_bytes[4]; uint32_t overflow, pad; };
 
 // per-frame state written by the kernels (counts the host reads back once per batch)
 struct DracoCounts {
