@@ -570,6 +570,8 @@ def main():
             d2, e2 = maxr(M2["dev_ms"], M2["e2e_s"]); k2 = max(2, min(args.steps, 3))
             o2 = sumr(M2["sg2"]["bytes_out"] + M2["st2"]["bytes_out"])[0]
             extra["bc7_target"] = {"value": frames * k2 / (d2 / 1e3), "e2e": frames * k2 / e2, "unit": "frames/s", "steps": k2, "d2h_bytes_per_step": o2,
+                                   "tex_stage_ms_rank0": {k: round(v / k2, 3) for k, v in M2["stage_acc"].items() if k.startswith("tex_") and v / k2 >= 0.02},
+                                   "geo_kernels_ms_rank0": M2["sg"]["device_ms"], "e2e_breakdown_rank0": {"geo_call_total": M2["sg2"]["total_ms"], "geo_d2h": M2["sg2"]["d2h_ms"], "tex_kernels": M2["st2"]["device_ms"], "tex_d2h": M2["st2"]["d2h_ms"]},
                                    "note": "same sequence, UVOL_TEX_BC7 output (decode only, no gather); BC7 blocks are validated by an independent BC7 decoder, not bit-matched to basisu (DESIGN.md)"}
             r2.close(); del r2
         except Exception as ex:                                       # never lose the headline to a side figure

@@ -1,4 +1,4 @@
-"""UASTC block kernel: CUDA-event time and algorithmic bandwidth (80 B per block) for different mode mixes."""
+"""UASTC block kernels: CUDA-event time and algorithmic bandwidth for different mode mixes, RGBA32 (80 B per block) and BC7 (32 B per block)."""
 import importlib, os, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, root)
 uv = importlib.import_module("universal-volumetric_b200")
@@ -8,8 +8,9 @@ img = synth.texture_layers(2048, 0, 7, 5)
 for name, mask in (("modes 0-8,18 hashed per block", synth.UASTC_OPAQUE_MODES), ("mode 0 only", 1 | 256), ("all 19 modes hashed per block", synth.UASTC_ALL_MODES)):
     seg = synth.encode_uastc(img, mode_mask=mask, seed=3)
     ktx = [seg] * 32
-    for _ in range(3):
-        out = kl.transcode_batch_raw(ktx, uv.MEM_DEVICE)
-    st = ctx.stats(1)
     nb = 32 * 7 * 512 * 512
-    print(name, "blocks %.3f ms -> %.0f GB/s (80 B/block)" % (st["stages"]["blocks"], nb * 80 / st["stages"]["blocks"] / 1e6), flush=True)
+    for tname, target, per in (("rgba32", uv.TEX_RGBA32, 80), ("bc7", uv.TEX_BC7, 32)):
+        for _ in range(3):
+            out = kl.transcode_batch_raw(ktx, uv.MEM_DEVICE, target)
+        st = ctx.stats(1)
+        print(name, tname, "blocks %.3f ms -> %.0f GB/s (%d B/block), %.2f Gblocks/s" % (st["stages"]["blocks"], nb * per / st["stages"]["blocks"] / 1e6, per, nb / st["stages"]["blocks"] / 1e6), flush=True)

@@ -30,8 +30,8 @@ struct TexState { int32_t status; uint32_t hist_size; };
 #ifndef SERIAL_WARPS
 #define SERIAL_WARPS 1        // one unit per warp, one warp per block (small blocks pack around the geometry stream's blocks)
 #endif
-__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_basis_globals(const Ktx2File *files, TexState *state, const uint8_t *blob, uint8_t *S, int nfiles) {
-    const uint32_t fi = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_basis_globals(const Ktx2File *files, TexState *state, const uint8_t *blob, uint8_t *S, int file0, int nfiles) {
+    const uint32_t fi = (uint32_t)file0 + blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if ((int)fi >= nfiles || (threadIdx.x & 31) != 0) return;
     const Ktx2File &f = files[fi];
     if (f.status) { state[fi].status = f.status; return; }
@@ -47,11 +47,11 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_basis_globals(const Ktx2F
 }
 
 #define SLICE_SMEM_BYTES (4 * sizeof(HuffTable) + 4096 + 2048)
-__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_etc1s_slices(const Ktx2File *files, TexState *state, const Ktx2Slice *slices, const uint8_t *blob, uint8_t *S, int nslices) {
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_etc1s_slices(const Ktx2File *files, TexState *state, const Ktx2Slice *slices, const uint8_t *blob, uint8_t *S, int slice0, int nslices) {
     extern __shared__ uint4 slice_smem[];
     uint8_t *my = (uint8_t *)slice_smem + (size_t)(threadIdx.x >> 5) * SLICE_SMEM_BYTES;
     HuffTable *tabs = (HuffTable *)my; uint8_t *rowp = my + 4 * sizeof(HuffTable); uint16_t *hist = (uint16_t *)(rowp + 4096);
-    const uint32_t si = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+    const uint32_t si = (uint32_t)slice0 + blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
     if ((int)si >= nslices) return;
     const Ktx2Slice &sl = slices[si]; const Ktx2File &f = files[sl.file];
     if (f.status || state[sl.file].status) return;
@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_etc1s_slices(const Ktx2Fi
 }
 
 // Endpoint prediction reversal.  One warp per (file, plane); layers and rows in order, 32 blocks per step.
-__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_etc1s_resolve(const Ktx2File *files, TexState *state, const Ktx2Slice *slices, uint8_t *S, int nfiles) {
-    const uint32_t fi = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5), plane = blockIdx.y, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_etc1s_resolve(const Ktx2File *files, TexState *state, const Ktx2Slice *slices, uint8_t *S, int file0, int nfiles) {
+    const uint32_t fi = (uint32_t)file0 + blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5), plane = blockIdx.y, lane = threadIdx.x & 31;
     if ((int)fi >= nfiles) return;
     const Ktx2File &f = files[fi];
     if (f.status || state[fi].status || f.is_uastc) return;
@@ -244,20 +244,23 @@ struct TexBatch {
     std::vector<Ktx2File> files; std::vector<Ktx2Slice> slices; std::vector<uint32_t> layer_list, uastc_layers;
     int n = 0; uint64_t blob_bytes = 0, scratch = 0, out = 0, bytes_in = 0; uint32_t max_blocks = 1, max_codebook = 0; bool any_alpha = false, any_zstd = false; int target = UVOL_TEX_RGBA32;
     size_t desc_bytes = 0, off_sl = 0, off_ll = 0, off_ul = 0; double parse_ms = 0; uint32_t launches = 0; int nev = 0;
+    std::vector<uint32_t> ll_start, ul_start, sl_start;      // per file (+1): first entry in layer_list / uastc_layers / slices
 };
 void uvol_tex_batch_free(TexBatch *b) { delete b; }
 
+// Container parse of every file, memory plan, descriptor upload.  The payload bytes are NOT staged here (see ktx2_stage_range).
 static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target = UVOL_TEX_RGBA32) {
-    const double t_begin = now_ms();
     if (!ctx->tex) ctx->tex = new TexBatch();
     TexBatch &B = *ctx->tex;
     B.n = n; B.files.assign((size_t)n, Ktx2File()); B.slices.clear(); B.layer_list.clear(); B.uastc_layers.clear();
+    B.ll_start.assign((size_t)n + 1, 0); B.ul_start.assign((size_t)n + 1, 0); B.sl_start.assign((size_t)n + 1, 0);
     B.max_blocks = 1; B.max_codebook = 0; B.any_alpha = false; B.any_zstd = false; B.bytes_in = 0; B.target = target;
     std::vector<Ktx2File> &files = B.files; std::vector<Ktx2Slice> &slices = B.slices;
     uint64_t blob_bytes = 0, s = 0, o = 0;
     for (int i = 0; i < n; i++) {
         Ktx2File &f = files[i]; memset(&f, 0, sizeof f);
         f.file_len = (uint32_t)size[i]; B.bytes_in += size[i];
+        B.ll_start[i] = (uint32_t)B.layer_list.size(); B.ul_start[i] = (uint32_t)B.uastc_layers.size(); B.sl_start[i] = (uint32_t)slices.size();
         const size_t slices_before = slices.size();
         f.status = (data[i] && size[i] < (1ull << 31)) ? uvol_ktx2_parse(data[i], size[i], (uint32_t)i, f, slices) : UVOL_ERR_ARG;
         f.file_off = blob_bytes;                                      // the file itself, or (Zstd levels) the inflated level
@@ -268,10 +271,10 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
         if (f.status) { slices.resize(slices_before); continue; }
         if (f.layers > 4095 || f.bx > 4096) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }
         const uint64_t nblk = (uint64_t)f.bx * f.by;
-        if (nblk > B.max_blocks) B.max_blocks = (uint32_t)nblk;
         if (target == UVOL_TEX_ETC1 && (f.is_uastc || f.has_alpha)) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }   // ETC1 target: opaque ETC1S sources only
         const uint64_t out_bytes = target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * nblk * 8 : (target == UVOL_TEX_BC7 ? (uint64_t)f.layers * nblk * 16 : (uint64_t)f.layers * f.width * f.height * 4);
         if (out_bytes > ctx->cfg.max_texture_bytes) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }      // resource limit, per item
+        if (nblk > B.max_blocks) B.max_blocks = (uint32_t)nblk;
         f.o_rgba = take(o, out_bytes);
         if (f.is_uastc) { for (uint32_t L = 0; L < f.layers; L++) B.uastc_layers.push_back(((uint32_t)i << 12) | L); continue; }   // no entropy stage, no scratch
         B.any_alpha |= f.has_alpha != 0;
@@ -285,98 +288,157 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
         }
         for (uint32_t L = 0; L < f.layers; L++) B.layer_list.push_back(((uint32_t)i << 12) | L);
     }
+    B.ll_start[n] = (uint32_t)B.layer_list.size(); B.ul_start[n] = (uint32_t)B.uastc_layers.size(); B.sl_start[n] = (uint32_t)slices.size();
     B.blob_bytes = blob_bytes; B.scratch = s; B.out = o;
     const size_t nsl = slices.size(), nll = B.layer_list.size(), nul = B.uastc_layers.size();
-    UVOL_CUDA(ctx, ctx->h_tblob.reserve(blob_bytes + 64));
-    {   // staging into the pinned blob by a few host threads: a copy of the file, or the inflated level of a Zstd-supercompressed file
-        std::atomic<int> next{0};
-        auto work = [&]() {
-            for (int i; (i = next.fetch_add(1)) < n;) {
-                if (!data[i] || size[i] >= (1ull << 31)) continue;
-                uint8_t *dst = (uint8_t *)ctx->h_tblob.p + files[i].file_off;
-                if (!files[i].status && files[i].zstd) {
-                    size_t got = 0;
-                    const int rc = uvol_zstd_inflate(data[i] + files[i].z_src_off, files[i].z_src_len, dst, files[i].z_len, &got);
-                    if (rc || got != files[i].z_len) files[i].status = rc ? rc : UVOL_ERR_CORRUPT;
-                } else memcpy(dst, data[i], size[i]);
-            }
-        };
-        int nthreads = B.bytes_in > (64ull << 20) || B.any_zstd ? uvol_staging_threads() : 1;
-        if (B.any_zstd && !getenv("UVOL_STAGING_THREADS")) nthreads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));   // inflating is ~20x slower than copying
-        if (nthreads > n) nthreads = n;
-        if (nthreads <= 1) work();
-        else { std::vector<std::thread> pool; for (int t = 0; t < nthreads; t++) pool.emplace_back(work); for (auto &t : pool) t.join(); }
-    }
     B.off_sl = sizeof(Ktx2File) * (size_t)n; B.off_ll = B.off_sl + sizeof(Ktx2Slice) * (nsl + 1); B.off_ul = B.off_ll + 4 * (nll + 1);
     B.desc_bytes = B.off_ul + 4 * (nul + 1);
+    UVOL_CUDA(ctx, ctx->h_tblob.reserve(blob_bytes + 64));
     UVOL_CUDA(ctx, ctx->h_tdesc.reserve(B.desc_bytes));
     UVOL_CUDA(ctx, ctx->d_tdesc.reserve(B.desc_bytes));
     UVOL_CUDA(ctx, ctx->d_tblob.reserve(blob_bytes + 64));
     UVOL_CUDA(ctx, ctx->d_tslices.reserve(sizeof(TexState) * (size_t)n));
     UVOL_CUDA(ctx, ctx->d_tscratch.reserve(s + 256));
     UVOL_CUDA(ctx, ctx->d_out_tex.reserve(o + 256));
-    uint8_t *hd = (uint8_t *)ctx->h_tdesc.p;
-    memcpy(hd, files.data(), sizeof(Ktx2File) * (size_t)n);
-    if (nsl) memcpy(hd + B.off_sl, slices.data(), sizeof(Ktx2Slice) * nsl);
-    if (nll) memcpy(hd + B.off_ll, B.layer_list.data(), 4 * nll);
-    if (nul) memcpy(hd + B.off_ul, B.uastc_layers.data(), 4 * nul);
-    B.parse_ms = now_ms() - t_begin;
-    cudaStream_t st = ctx->s2;
-    if (ctx->profile) cudaEventRecord(ctx->tex_ev[0], st);
-    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_tblob.p, ctx->h_tblob.p, blob_bytes, cudaMemcpyHostToDevice, st));
-    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc.p, hd, B.desc_bytes, cudaMemcpyHostToDevice, st));
     return UVOL_OK;
 }
 
-// Enqueues the whole texture pipeline (kernels + result copies) on stream `st`; no host sync.
-static int ktx2_launch(uvol_ctx *ctx, int memory, bool fresh_upload, cudaStream_t st) {
+// Stages the payload of files [i0, i1) into the pinned blob with a few host threads: a copy of the file, or the inflated level of a
+// Zstd-supercompressed file.  (A file whose inflate fails is marked; its descriptor must be uploaded after this.)
+static void ktx2_stage_range(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int i0, int i1) {
+    TexBatch &B = *ctx->tex; std::vector<Ktx2File> &files = B.files;
+    std::atomic<int> next{i0}; uint64_t bytes = 0;
+    for (int i = i0; i < i1; i++) bytes += size[i];
+    auto work = [&]() {
+        for (int i; (i = next.fetch_add(1)) < i1;) {
+            if (!data[i] || size[i] >= (1ull << 31)) continue;
+            uint8_t *dst = (uint8_t *)ctx->h_tblob.p + files[i].file_off;
+            if (!files[i].status && files[i].zstd) {
+                size_t got = 0;
+                const int rc = uvol_zstd_inflate(data[i] + files[i].z_src_off, files[i].z_src_len, dst, files[i].z_len, &got);
+                if (rc || got != files[i].z_len) files[i].status = rc ? rc : UVOL_ERR_CORRUPT;
+            } else memcpy(dst, data[i], size[i]);
+        }
+    };
+    int nthreads = bytes > (64ull << 20) || B.any_zstd ? (ctx->cfg.staging_threads ? (int)ctx->cfg.staging_threads : uvol_staging_threads()) : 1;
+    if (B.any_zstd && !ctx->cfg.staging_threads && !getenv("UVOL_STAGING_THREADS")) nthreads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));   // inflating is ~20x slower than copying
+    if (nthreads > i1 - i0) nthreads = i1 - i0;
+    if (nthreads <= 1) work();
+    else { std::vector<std::thread> pool; for (int t = 0; t < nthreads; t++) pool.emplace_back(work); for (auto &t : pool) t.join(); }
+}
+
+// Enqueues the kernels of files [i0, i1) on `st` (no host sync).  Every stage works on per-file / per-slice / per-layer lists, so a
+// range of files is a range of each list.
+static int ktx2_launch_range(uvol_ctx *ctx, int i0, int i1, cudaStream_t st, bool stamps, int *ev) {
     TexBatch &B = *ctx->tex; const int n = B.n;
-    int ev = 1;
-    auto stamp = [&]() { if (ctx->profile && ev < 8) cudaEventRecord(ctx->tex_ev[ev++], st); };
-    if (!fresh_upload && ctx->profile) cudaEventRecord(ctx->tex_ev[0], st);
-    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_tslices.p, 0, sizeof(TexState) * (size_t)n, st));
-    stamp();
-    const size_t nsl = B.slices.size(), nll = B.layer_list.size(), nul = B.uastc_layers.size();
+    auto stamp = [&]() { if (stamps && ctx->profile && *ev < 8) cudaEventRecord(ctx->tex_ev[*ev], st); if (stamps) ++*ev; };
     const uint8_t *dD = (const uint8_t *)ctx->d_tdesc.p;
     const Ktx2File *dF = (const Ktx2File *)dD; const Ktx2Slice *dSl = (const Ktx2Slice *)(dD + B.off_sl);
     const uint32_t *dLL = (const uint32_t *)(dD + B.off_ll), *dUL = (const uint32_t *)(dD + B.off_ul);
     TexState *dSt = (TexState *)ctx->d_tslices.p; const uint8_t *dBlob = (const uint8_t *)ctx->d_tblob.p;
     uint8_t *dS = (uint8_t *)ctx->d_tscratch.p, *dO = (uint8_t *)ctx->d_out_tex.p;
-    uint32_t launches = 0;
-    const unsigned nb4 = (unsigned)((n + SERIAL_WARPS - 1) / SERIAL_WARPS);
-    k_basis_globals<<<nb4, 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dBlob, dS, n); launches++;
+    const uint32_t sl0 = B.sl_start[i0], sl1 = B.sl_start[i1], ll0 = B.ll_start[i0], ll1 = B.ll_start[i1], ul0 = B.ul_start[i0], ul1 = B.ul_start[i1];
+    const unsigned nbf = (unsigned)((i1 - i0 + SERIAL_WARPS - 1) / SERIAL_WARPS);
+    (void)n;
+    k_basis_globals<<<nbf, 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dBlob, dS, i0, i1); B.launches++;
     stamp();
-    if (nsl) {
+    if (sl1 > sl0) {
         cudaFuncSetAttribute(k_etc1s_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SLICE_SMEM_BYTES * SERIAL_WARPS));
-        k_etc1s_slices<<<(unsigned)((nsl + SERIAL_WARPS - 1) / SERIAL_WARPS), 32 * SERIAL_WARPS, SLICE_SMEM_BYTES * SERIAL_WARPS, st>>>(dF, dSt, dSl, dBlob, dS, (int)nsl); launches++;
+        k_etc1s_slices<<<(unsigned)((sl1 - sl0 + SERIAL_WARPS - 1) / SERIAL_WARPS), 32 * SERIAL_WARPS, SLICE_SMEM_BYTES * SERIAL_WARPS, st>>>(dF, dSt, dSl, dBlob, dS, (int)sl0, (int)sl1); B.launches++;
     }
     stamp();
-    if (nsl) { k_etc1s_resolve<<<dim3(nb4, B.any_alpha ? 2 : 1), 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dSl, dS, n); launches++; }
+    if (sl1 > sl0) { k_etc1s_resolve<<<dim3(nbf, B.any_alpha ? 2 : 1), 32 * SERIAL_WARPS, 0, st>>>(dF, dSt, dSl, dS, i0, i1); B.launches++; }
     stamp();
+    const unsigned nll = ll1 - ll0, nul = ul1 - ul0;
     if (nll && B.target == UVOL_TEX_BC7) {
         UVOL_CUDA(ctx, (cudaError_t)uvol_texture_tables_ready(ctx->device));
-        k_etc1s_blocks_bc7<<<dim3((B.max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO, uvol_bc7_tables_device()); launches++;
-    } else if (nll && B.target == UVOL_TEX_ETC1) { k_etc1s_blocks_etc1<<<dim3((B.max_blocks + 255) / 256, (unsigned)nll), 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO); launches++; }
+        k_etc1s_blocks_bc7<<<dim3((B.max_blocks + 255) / 256, nll), 256, 0, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO, uvol_bc7_tables_device()); B.launches++;
+    } else if (nll && B.target == UVOL_TEX_ETC1) { k_etc1s_blocks_etc1<<<dim3((B.max_blocks + 255) / 256, nll), 256, 0, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO); B.launches++; }
     else if (nll) {
-        const dim3 grid((B.max_blocks + 256 * ETC1S_CHUNKS - 1) / (256 * ETC1S_CHUNKS), (unsigned)nll);
+        const dim3 grid((B.max_blocks + 256 * ETC1S_CHUNKS - 1) / (256 * ETC1S_CHUNKS), nll);
         const size_t cb = (size_t)B.max_codebook * 4;
         if (cb <= 160 * 1024) {
             if (cb > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_etc1s_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
-            k_etc1s_blocks<true><<<grid, 256, cb, st>>>(dF, dSt, dSl, dLL, dS, dO);
-        } else k_etc1s_blocks<false><<<grid, 256, 0, st>>>(dF, dSt, dSl, dLL, dS, dO);
-        launches++;
+            k_etc1s_blocks<true><<<grid, 256, cb, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO);
+        } else k_etc1s_blocks<false><<<grid, 256, 0, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO);
+        B.launches++;
     }
-    if (nul) { UVOL_CUDA(ctx, (cudaError_t)uvol_uastc_launch(ctx->device, dF, (int32_t *)dSt, dBlob, dO, dUL, (int)nul, B.max_blocks, B.target, st)); launches++; }
+    if (nul) { UVOL_CUDA(ctx, (cudaError_t)uvol_uastc_launch(ctx->device, dF, (int32_t *)dSt, dBlob, dO, dUL + ul0, (int)nul, B.max_blocks, B.target, st)); B.launches++; }
     stamp();
-    ctx->span_tex_end = ev - 1;
+    return UVOL_OK;
+}
+
+// Fresh batch, host buffers in: staging copy, upload, kernels and result copy are PIPELINED over chunks of whole files -- chunk k's
+// kernels and result copy run while chunk k+1 is being staged and uploaded -- so the device -> host link starts carrying results a
+// few tens of milliseconds into the call instead of after the whole batch has been staged, uploaded and transcoded.
+static int ktx2_fresh(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target, int memory, cudaStream_t st) {
+    const double t_begin = now_ms();
+    int rc = ktx2_prepare(ctx, data, size, n, target); if (rc) return rc;
+    TexBatch &B = *ctx->tex; B.launches = 0;
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
     UVOL_CUDA(ctx, ctx->h_tstate.reserve(st_bytes));                       // per-ctx even when the bulk result buffer is shared
     if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, ctx->ph_tout->reserve(B.out + 256));
-    TexState *hSt = (TexState *)ctx->h_tstate.p; uint8_t *hO = (uint8_t *)ctx->ph_tout->p;
-    UVOL_CUDA(ctx, cudaMemcpyAsync(hSt, dSt, sizeof(TexState) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(hO, dO, B.out, cudaMemcpyDeviceToHost, st));
-    stamp();
-    B.launches = launches; B.nev = ev;
+    // chunks of about 1/8 of the input (at least 64 MB) -- a small first chunk gets the pipeline going
+    const uint64_t per = std::max<uint64_t>(64ull << 20, B.bytes_in / 8 + 1);
+    int ev = 0; bool first = true;
+    if (ctx->profile) cudaEventRecord(ctx->tex_ev[0], st);
+    ev = 1;
+    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_tslices.p, 0, sizeof(TexState) * (size_t)n, st));
+    uint8_t *hd = (uint8_t *)ctx->h_tdesc.p;
+    const size_t nsl = B.slices.size(), nll = B.layer_list.size(), nul = B.uastc_layers.size();
+    if (nsl) memcpy(hd + B.off_sl, B.slices.data(), sizeof(Ktx2Slice) * nsl);
+    if (nll) memcpy(hd + B.off_ll, B.layer_list.data(), 4 * nll);
+    if (nul) memcpy(hd + B.off_ul, B.uastc_layers.data(), 4 * nul);
+    UVOL_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_tdesc.p + B.off_sl, hd + B.off_sl, B.desc_bytes - B.off_sl, cudaMemcpyHostToDevice, st));
+    uint8_t *hO = memory == UVOL_MEM_HOST ? (uint8_t *)ctx->ph_tout->p : nullptr, *dO = (uint8_t *)ctx->d_out_tex.p;
+    for (int i0 = 0; i0 < n;) {
+        int i1 = i0; uint64_t acc = 0;
+        const uint64_t want = first ? std::min<uint64_t>(per, 96ull << 20) : per;
+        while (i1 < n && (i1 == i0 || acc + size[i1] <= want)) acc += size[i1++];
+        ktx2_stage_range(ctx, data, size, i0, i1);
+        // descriptors of this chunk (a failed inflate has just been marked), then its bytes
+        memcpy(hd + sizeof(Ktx2File) * (size_t)i0, B.files.data() + i0, sizeof(Ktx2File) * (size_t)(i1 - i0));
+        UVOL_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_tdesc.p + sizeof(Ktx2File) * (size_t)i0, hd + sizeof(Ktx2File) * (size_t)i0, sizeof(Ktx2File) * (size_t)(i1 - i0), cudaMemcpyHostToDevice, st));
+        const uint64_t b0 = B.files[i0].file_off, b1 = i1 < n ? B.files[i1].file_off : B.blob_bytes;
+        UVOL_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_tblob.p + b0, (uint8_t *)ctx->h_tblob.p + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+        if (first) { if (ctx->profile && ev < 8) cudaEventRecord(ctx->tex_ev[ev], st); ev++; B.parse_ms = now_ms() - t_begin; }
+        const bool last = i1 == n;
+        rc = ktx2_launch_range(ctx, i0, i1, st, last, &ev); if (rc) return rc;      // (stage stamps on the last chunk: "blocks" then spans the pipelined middle)
+        if (hO) {
+            uint64_t o0 = ~0ull, o1 = 0;
+            for (int i = i0; i < i1; i++) if (!B.files[i].status) { const uint64_t a = B.files[i].o_rgba; if (a < o0) o0 = a; }
+            o1 = B.out; for (int i = i1; i < n; i++) if (!B.files[i].status) { o1 = B.files[i].o_rgba; break; }
+            if (o0 != ~0ull && o1 > o0) UVOL_CUDA(ctx, cudaMemcpyAsync(hO + o0, dO + o0, o1 - o0, cudaMemcpyDeviceToHost, st));
+        }
+        first = false; i0 = i1;
+    }
+    ctx->span_tex_end = ev - 1;
+    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_tstate.p, ctx->d_tslices.p, sizeof(TexState) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (ctx->profile && ev < 8) cudaEventRecord(ctx->tex_ev[ev], st);
+    ev++;
+    B.nev = ev;
+    return UVOL_OK;
+}
+
+// Replay: the whole resident batch in one go (kernels + result copies), no host sync.
+static int ktx2_launch(uvol_ctx *ctx, int memory, cudaStream_t st) {
+    TexBatch &B = *ctx->tex; const int n = B.n;
+    int ev = 1;
+    if (ctx->profile) cudaEventRecord(ctx->tex_ev[0], st);
+    UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_tslices.p, 0, sizeof(TexState) * (size_t)n, st));
+    if (ctx->profile && ev < 8) cudaEventRecord(ctx->tex_ev[ev], st);
+    ev++;
+    B.launches = 0;
+    int rc = ktx2_launch_range(ctx, 0, n, st, true, &ev); if (rc) return rc;
+    ctx->span_tex_end = ev - 1;
+    const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
+    UVOL_CUDA(ctx, ctx->h_tstate.reserve(st_bytes));
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, ctx->ph_tout->reserve(B.out + 256));
+    UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_tstate.p, ctx->d_tslices.p, sizeof(TexState) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->ph_tout->p, ctx->d_out_tex.p, B.out, cudaMemcpyDeviceToHost, st));
+    if (ctx->profile && ev < 8) cudaEventRecord(ctx->tex_ev[ev], st);
+    ev++;
+    B.nev = ev;
     return UVOL_OK;
 }
 
@@ -407,8 +469,8 @@ static int ktx2_finish(uvol_ctx *ctx, int memory, uvol_texture *out, uvol_stats 
     return UVOL_OK;
 }
 
-static int ktx2_run(uvol_ctx *ctx, int memory, uvol_texture *out, bool fresh_upload) {
-    int rc = ktx2_launch(ctx, memory, fresh_upload, ctx->s2); if (rc) return rc;
+static int ktx2_run_replay(uvol_ctx *ctx, int memory, uvol_texture *out) {
+    int rc = ktx2_launch(ctx, memory, ctx->s2); if (rc) return rc;
     UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s2));
     return ktx2_finish(ctx, memory, out, ctx->stats);
 }
@@ -420,8 +482,9 @@ extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *da
     memset(&ctx->stats, 0, sizeof ctx->stats);
     if (n == 0) { if (ctx->tex) ctx->tex->n = 0; return UVOL_OK; }
     const double t0 = now_ms();
-    int rc = ktx2_prepare(ctx, data, size, n, target_format); if (rc) return rc;
-    rc = ktx2_run(ctx, memory, out, true); if (rc) return rc;
+    int rc = ktx2_fresh(ctx, data, size, n, target_format, memory, ctx->s2); if (rc) return rc;
+    UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s2));
+    rc = ktx2_finish(ctx, memory, out, ctx->stats); if (rc) return rc;
     ctx->stats.host_parse_ms = ctx->tex->parse_ms; ctx->stats.total_ms = now_ms() - t0;
     return UVOL_OK;
 }
@@ -431,7 +494,7 @@ extern "C" int uvol_replay_ktx2_batch(uvol_ctx *ctx, int memory, uvol_texture *o
     UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->stats, 0, sizeof ctx->stats);
     const double t0 = now_ms();
-    const int rc = ktx2_run(ctx, memory, out, false); if (rc) return rc;
+    const int rc = ktx2_run_replay(ctx, memory, out); if (rc) return rc;
     ctx->stats.total_ms = now_ms() - t0;
     return UVOL_OK;
 }
@@ -453,8 +516,7 @@ extern "C" int uvol_decode_v2_batch(uvol_ctx *ctx, const uint8_t *const *drc, co
     std::thread tex_thread;
     if (n_ktx2) tex_thread = std::thread([&]() {
         if (cudaSetDevice(ctx->device) != cudaSuccess) { rc_tex = UVOL_ERR_CUDA; return; }
-        rc_tex = ktx2_prepare(ctx, ktx2, ktx2_size, n_ktx2, (int)ctx->cfg.texture_target);
-        if (!rc_tex) rc_tex = ktx2_launch(ctx, memory, true, ctx->s2);
+        rc_tex = ktx2_fresh(ctx, ktx2, ktx2_size, n_ktx2, (int)ctx->cfg.texture_target, memory, ctx->s2);
     });
     if (n_drc) rc = uvol_geo_prepare_and_run(ctx, drc, drc_size, n_drc, memory, out_geo, false);
     if (n_ktx2) tex_thread.join();
@@ -472,7 +534,7 @@ extern "C" int uvol_replay_v2_batch(uvol_ctx *ctx, int memory, uvol_geometry *ou
     memset(&ctx->stats, 0, sizeof ctx->stats); memset(&ctx->stats_tex, 0, sizeof ctx->stats_tex);
     const double t0 = now_ms();
     int rc;
-    if (n_ktx2) { rc = ktx2_launch(ctx, memory, false, ctx->s2); if (rc) return rc; }
+    if (n_ktx2) { rc = ktx2_launch(ctx, memory, ctx->s2); if (rc) return rc; }
     if (n_drc) { rc = uvol_geo_prepare_and_run(ctx, nullptr, nullptr, n_drc, memory, out_geo, true); if (rc) return rc; }
     if (n_ktx2) { UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s2)); rc = ktx2_finish(ctx, memory, out_tex, ctx->stats_tex); if (rc) return rc; }
     ctx->stats.total_ms = ctx->stats_tex.total_ms = now_ms() - t0;

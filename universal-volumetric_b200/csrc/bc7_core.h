@@ -22,12 +22,30 @@
 #include "uastc_core.h"
 #include "basis_core.h"
 
-struct Bc7Shared { uint32_t info[60]; uint32_t pat3[20]; uint8_t wmap[3][6][32]; uint8_t solid5[256][2]; };
+// Endpoint quantisation is table driven (one shared-memory byte per value): q5 / q7 = nearest 5- / 7-bit code under MSB replication;
+// q7p[p] / q6p[p] = nearest 6- / 5-bit code whose value with the p-bit p appended (7 / 6 bits in all) is nearest, bit 7 of the p = 0
+// row = the parity of the unconstrained nearest code (the vote for the shared p-bit).  7 bits + p is the value itself.
+struct Bc7Shared { uint32_t info[60]; uint32_t pat3[20]; uint8_t wmap[3][6][32]; uint8_t solid5[256][2]; uint8_t q5[256], q7[256], q7p[2][256], q6p[2][256]; };
 static_assert(sizeof(Bc7Shared) % 4 == 0, "copied word by word");
+static inline uint32_t bc7_expand_host(uint32_t x, uint32_t bits) { x <<= (8u - bits); return (x | (x >> bits)) & 255u; }
+static inline uint32_t bc7_nearest_host(uint32_t e, uint32_t bits, int parity) {
+    uint32_t best = 0, beste = 0xffffu;
+    for (uint32_t x = 0; x < (1u << bits); x++) {
+        if (parity >= 0 && (int)(x & 1u) != parity) continue;
+        const uint32_t ex = bc7_expand_host(x, bits), er = ex > e ? ex - e : e - ex;
+        if (er < beste) { beste = er; best = x; }
+    }
+    return best;
+}
 static inline void bc7_fill_tables(Bc7Shared &h) {
     memset(&h, 0, sizeof h);
     memcpy(h.info, UASTC_BC7_INFO_INIT, sizeof UASTC_BC7_INFO_INIT); memcpy(h.pat3, UASTC_BC7_PAT3_INIT, sizeof UASTC_BC7_PAT3_INIT);
     memcpy(h.wmap, UASTC_BC7_WMAP_INIT, sizeof h.wmap); memcpy(h.solid5, BC7_SOLID5_INIT, sizeof h.solid5);
+    for (uint32_t e = 0; e < 256; e++) {
+        h.q5[e] = (uint8_t)bc7_nearest_host(e, 5, -1); h.q7[e] = (uint8_t)bc7_nearest_host(e, 7, -1);
+        for (int p = 0; p < 2; p++) { h.q7p[p][e] = (uint8_t)(bc7_nearest_host(e, 7, p) >> 1); h.q6p[p][e] = (uint8_t)(bc7_nearest_host(e, 6, p) >> 1); }
+        h.q7p[0][e] |= (uint8_t)((bc7_nearest_host(e, 7, -1) & 1u) << 7); h.q6p[0][e] |= (uint8_t)((bc7_nearest_host(e, 6, -1) & 1u) << 7);
+    }
 }
 
 // ---- 128-bit LSB-first writer held in two 64-bit registers
@@ -39,21 +57,6 @@ UASTC_HD void b7_put(Bc7Bits &b, uint32_t v, uint32_t n) {          // n in 1..1
 }
 UASTC_HD uint32_t b7_expand(uint32_t x, uint32_t bits) { x <<= (8u - bits); return (x | (x >> bits)) & 255u; }
 UASTC_HD uint32_t b7_absdiff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
-// nearest `bits`-bit code of the 8-bit value e (under MSB replication); parity < 2 restricts the code's low bit (a p-bit)
-UASTC_HD uint32_t b7_quant(uint32_t e, uint32_t bits, uint32_t parity, uint32_t *err) {
-    const uint32_t maxx = (1u << bits) - 1u, x0 = (e * maxx + 127u) / 255u;
-    uint32_t best = 0, beste = 0xffffu;
-#pragma unroll
-    for (int d = -1; d <= 1; d++) {
-        const int x = (int)x0 + d;
-        if (x < 0 || x > (int)maxx || (parity < 2u && ((uint32_t)x & 1u) != parity)) continue;
-        const uint32_t er = b7_absdiff(b7_expand((uint32_t)x, bits), e);
-        if (er < beste) { beste = er; best = (uint32_t)x; }
-    }
-    if (beste == 0xffffu) { best = parity < 2u ? ((x0 & ~1u) | parity) : x0; if (best > maxx) best = maxx - 1u + parity; beste = b7_absdiff(b7_expand(best, bits), e); }
-    *err += beste * beste;
-    return best;
-}
 UASTC_HD uint32_t b7_interp(uint32_t a, uint32_t b, uint32_t w) { return ((64u - w) * a + w * b + 32u) >> 6; }
 
 // ---- the logical content of a UASTC block
@@ -141,77 +144,66 @@ UASTC_HD void bc7_pack_mode5(uint32_t rot, uint32_t c0, uint32_t c1, uint32_t a0
 }
 
 // ---- the partitioned / single-subset modes 1, 2, 3, 6, 7
-// e0[s] / e1[s]: 8-bit RGBA endpoints of BC7 subset s; sub: BC7 subset per texel (2 bits each); idx[i]: BC7 index per texel
-UASTC_HD void bc7_pack_general(uint32_t m, uint32_t part, uint32_t anc1, uint32_t anc2, const uint32_t e0[3], const uint32_t e1[3], uint32_t sub,
-                               uint8_t idx[16], bool opaque, uint32_t out[4]) {
+// e0[s] / e1[s]: 8-bit RGBA endpoints of BC7 subset s (unused subsets: anything); sub: BC7 subset per texel (2 bits each);
+// idx: BC7 index per texel, 4 bits each
+UASTC_HD void bc7_pack_general(const Bc7Shared &B, uint32_t m, uint32_t part, uint32_t anc1, uint32_t anc2, const uint32_t e0[3], const uint32_t e1[3], uint32_t sub,
+                               unsigned long long idx, bool opaque, uint32_t out[4]) {
     const uint32_t ns = m == 6u ? 1u : (m == 2u ? 3u : 2u), cb = m == 1u ? 6u : (m == 2u ? 5u : (m == 7u ? 5u : 7u)), ab = m == 6u ? 7u : (m == 7u ? 5u : 0u),
                    ib = m == 1u ? 3u : (m == 6u ? 4u : 2u), ptype = m == 2u ? 0u : (m == 1u ? 2u : 1u);      // p-bits: none / per endpoint / shared per subset
-    uint32_t q[3][2][4], pb[3][2];
+    const uint8_t *tp0 = m == 1u ? B.q7p[0] : B.q6p[0], *tp1 = m == 1u ? B.q7p[1] : B.q6p[1];
+    const uint32_t nch = ab ? 4u : 3u;
+    uint32_t q[3][2], pb[3][2];                                    // quantised endpoints, one channel per byte
 #pragma unroll
     for (uint32_t s = 0; s < 3; s++) {
-        if (s >= ns) continue;
         const uint32_t E[2] = {e0[s], e1[s]};
-        if (ptype == 0u) {
+        uint32_t votes[2];
 #pragma unroll
-            for (uint32_t e = 0; e < 2; e++) { uint32_t er = 0; for (uint32_t c = 0; c < 3; c++) q[s][e][c] = b7_quant((E[e] >> (8u * c)) & 255u, cb, 2u, &er); q[s][e][3] = 0; pb[s][e] = 0; }
-        } else if (ptype == 1u) {
+        for (uint32_t e = 0; e < 2; e++) {                         // the parity most channels' nearest codes have
+            if (cb == 7u) votes[e] = (uint32_t)__builtin_popcount(E[e] & (ab ? 0x01010101u : 0x00010101u));
+            else { votes[e] = 0; for (uint32_t c = 0; c < 4; c++) if (c < nch) votes[e] += tp0[(E[e] >> (8u * c)) & 255u] >> 7; }
+        }
 #pragma unroll
-            for (uint32_t e = 0; e < 2; e++) {
-                uint32_t bestp = 1, beste = 0xffffffffu;
-                for (uint32_t p = 0; p < 2; p++) {
-                    if (ab && p == 0u && (opaque || (E[e] >> 24) == 255u)) continue;      // an alpha of 255 must stay 255: only the all-ones code reaches it
-                    uint32_t er = 0;
-                    for (uint32_t c = 0; c < 3; c++) b7_quant((E[e] >> (8u * c)) & 255u, cb + 1u, p, &er);
-                    if (ab) b7_quant((E[e] >> 24) & 255u, ab + 1u, p, &er);
-                    if (er < beste) { beste = er; bestp = p; }
-                }
-                uint32_t er = 0;
-                for (uint32_t c = 0; c < 3; c++) q[s][e][c] = b7_quant((E[e] >> (8u * c)) & 255u, cb + 1u, bestp, &er) >> 1;
-                q[s][e][3] = ab ? b7_quant((E[e] >> 24) & 255u, ab + 1u, bestp, &er) >> 1 : 0u;
-                pb[s][e] = bestp;
+        for (uint32_t e = 0; e < 2; e++) {
+            uint32_t p = 0;
+            if (ptype == 1u) { p = votes[e] * 2u >= nch ? 1u : 0u; if (ab && (opaque || (E[e] >> 24) == 255u)) p = 1u; }      // an alpha of 255 must stay 255: only the all-ones code reaches it
+            else if (ptype == 2u) p = votes[0] + votes[1] >= 3u ? 1u : 0u;
+            uint32_t r = 0;
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint32_t v = (E[e] >> (8u * c)) & 255u; uint32_t qq;
+                if (ptype == 0u) qq = B.q5[v];
+                else if (cb == 7u) { uint32_t x = v; if ((x & 1u) != p) x = v == 255u ? 254u : v + 1u; qq = x >> 1; }      // 7 bits + p: the value itself, moved by one when the low bit disagrees
+                else qq = (p ? tp1[v] : tp0[v]) & 127u;
+                r |= qq << (8u * c);
             }
-        } else {
-            uint32_t bestp = 0, beste = 0xffffffffu;
-            for (uint32_t p = 0; p < 2; p++) {
-                uint32_t er = 0;
-                for (uint32_t e = 0; e < 2; e++) for (uint32_t c = 0; c < 3; c++) b7_quant((E[e] >> (8u * c)) & 255u, cb + 1u, p, &er);
-                if (er < beste) { beste = er; bestp = p; }
-            }
-#pragma unroll
-            for (uint32_t e = 0; e < 2; e++) { uint32_t er = 0; for (uint32_t c = 0; c < 3; c++) q[s][e][c] = b7_quant((E[e] >> (8u * c)) & 255u, cb + 1u, bestp, &er) >> 1; q[s][e][3] = 0; pb[s][e] = bestp; }
+            q[s][e] = r; pb[s][e] = p;
         }
     }
     // anchors: the index of each subset's anchor texel is stored without its high bit; a subset whose anchor has it set is flipped
-    const uint32_t anchor[3] = {0u, anc1, anc2}, msb = 1u << (ib - 1u), maxi = (1u << ib) - 1u;
+    // (endpoints swapped, indices complemented)
+    const uint32_t msb = 1u << (ib - 1u), maxi = (1u << ib) - 1u;
+    const uint32_t f0 = (uint32_t)(idx & 15u) & msb, f1 = (uint32_t)((idx >> (4u * anc1)) & 15u) & msb, f2 = (uint32_t)((idx >> (4u * anc2)) & 15u) & msb;
+    const bool flip[3] = {f0 != 0u, ns > 1u && f1 != 0u, ns > 2u && f2 != 0u};
 #pragma unroll
-    for (uint32_t s = 0; s < 3; s++) {
-        if (s >= ns) continue;
-        uint32_t av = 0;
+    for (uint32_t s = 0; s < 3; s++) if (flip[s]) { const uint32_t t = q[s][0]; q[s][0] = q[s][1]; q[s][1] = t; const uint32_t u = pb[s][0]; pb[s][0] = pb[s][1]; pb[s][1] = u; }
 #pragma unroll
-        for (int i = 0; i < 16; i++) if ((uint32_t)i == anchor[s]) av = idx[i];
-        if (av & msb) {
-#pragma unroll
-            for (uint32_t c = 0; c < 4; c++) { const uint32_t t = q[s][0][c]; q[s][0][c] = q[s][1][c]; q[s][1][c] = t; }
-            const uint32_t t = pb[s][0]; pb[s][0] = pb[s][1]; pb[s][1] = t;
-#pragma unroll
-            for (int i = 0; i < 16; i++) if (((sub >> (2 * i)) & 3u) == s) idx[i] = (uint8_t)(maxi - idx[i]);
-        }
-    }
+    for (int i = 0; i < 16; i++) { const uint32_t sb = (sub >> (2 * i)) & 3u; if (sb == 0u ? flip[0] : (sb == 1u ? flip[1] : flip[2])) idx ^= (unsigned long long)maxi << (4 * i); }
     Bc7Bits b{0, 0, 0};
     b7_put(b, 1u << m, m + 1u);
     if (ns > 1u) b7_put(b, part, 6);
 #pragma unroll
     for (uint32_t c = 0; c < 4; c++) {
         if (c == 3u && !ab) continue;
+        const uint32_t nbits = c == 3u ? ab : cb;
 #pragma unroll
-        for (uint32_t s = 0; s < 3; s++) if (s < ns) { b7_put(b, q[s][0][c], c == 3u ? ab : cb); b7_put(b, q[s][1][c], c == 3u ? ab : cb); }
+        for (uint32_t s = 0; s < 3; s++) if (s < ns) { b7_put(b, (q[s][0] >> (8u * c)) & 255u, nbits); b7_put(b, (q[s][1] >> (8u * c)) & 255u, nbits); }
     }
     if (ptype == 1u) { for (uint32_t s = 0; s < 3; s++) if (s < ns) { b7_put(b, pb[s][0], 1); b7_put(b, pb[s][1], 1); } }
     else if (ptype == 2u) { for (uint32_t s = 0; s < 3; s++) if (s < ns) b7_put(b, pb[s][0], 1); }
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const bool is_anchor = (uint32_t)i == 0u || (ns > 1u && (uint32_t)i == anc1) || (ns > 2u && (uint32_t)i == anc2);
-        b7_put(b, idx[i], is_anchor ? ib - 1u : ib);
+        b7_put(b, (uint32_t)(idx >> (4 * i)) & maxi, is_anchor ? ib - 1u : ib);
     }
     out[0] = (uint32_t)b.lo; out[1] = (uint32_t)(b.lo >> 32); out[2] = (uint32_t)b.hi; out[3] = (uint32_t)(b.hi >> 32);
 }
@@ -234,9 +226,9 @@ UASTC_HD bool uastc_to_bc7(const UastcShared &T, const Bc7Shared &B, uint32_t q0
         if (rot) {                 // the alpha endpoints move into the colour slot of the rotated channel
             l = (l & ~(255u << (8u * ccs))) | ((l >> 24) << (8u * ccs)); h = (h & ~(255u << (8u * ccs))) | ((h >> 24) << (8u * ccs));
         }
-        uint32_t c0 = 0, c1 = 0, er = 0;
+        uint32_t c0 = 0, c1 = 0;
 #pragma unroll
-        for (uint32_t k = 0; k < 3; k++) { c0 |= b7_quant((l >> (8u * k)) & 255u, 7, 2, &er) << (8u * k); c1 |= b7_quant((h >> (8u * k)) & 255u, 7, 2, &er) << (8u * k); }
+        for (uint32_t k = 0; k < 3; k++) { c0 |= (uint32_t)B.q7[(l >> (8u * k)) & 255u] << (8u * k); c1 |= (uint32_t)B.q7[(h >> (8u * k)) & 255u] << (8u * k); }
         uint32_t ci = 0, ai = 0;
 #pragma unroll
         for (int i = 0; i < 16; i++) { ci |= (uint32_t)B.wmap[0][L.wbits][L.w0[i]] << (2 * i); ai |= (uint32_t)B.wmap[0][L.wbits][L.w1[i]] << (2 * i); }
@@ -262,10 +254,10 @@ UASTC_HD bool uastc_to_bc7(const UastcShared &T, const Bc7Shared &B, uint32_t q0
         }
     }
     const uint32_t ib = m == 1u ? 3u : (m == 6u ? 4u : 2u);
-    uint8_t idx[16];
+    unsigned long long idx = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) idx[i] = B.wmap[ib - 2u][L.wbits][L.w0[i]];
-    bc7_pack_general(m, part, anc1, anc2, e0, e1, sub, idx, opaque, out);
+    for (int i = 0; i < 16; i++) idx |= (unsigned long long)B.wmap[ib - 2u][L.wbits][L.w0[i]] << (4 * i);
+    bc7_pack_general(B, m, part, anc1, anc2, e0, e1, sub, idx, opaque, out);
     return true;
 }
 
@@ -286,10 +278,10 @@ UASTC_HD void etc1s_to_bc7(const Bc7Shared &B, uint32_t ep, uint32_t sel, bool h
         for (uint32_t k = 0; k < 3; k++) { const uint32_t v = (c >> (8u * k)) & 255u; c0 |= (uint32_t)B.solid5[v][0] << (8u * k); c1 |= (uint32_t)B.solid5[v][1] << (8u * k); }
         map = 0x55u;          // every selector -> index 1
     } else {
-        const uint32_t lc = col[smin], hc = col[smax]; uint32_t er = 0, L8 = 0, H8 = 0;
+        const uint32_t lc = col[smin], hc = col[smax]; uint32_t L8 = 0, H8 = 0;
 #pragma unroll
         for (uint32_t k = 0; k < 3; k++) {
-            const uint32_t ql = b7_quant((lc >> (8u * k)) & 255u, 7, 2, &er), qh = b7_quant((hc >> (8u * k)) & 255u, 7, 2, &er);
+            const uint32_t ql = B.q7[(lc >> (8u * k)) & 255u], qh = B.q7[(hc >> (8u * k)) & 255u];
             c0 |= ql << (8u * k); c1 |= qh << (8u * k); L8 |= b7_expand(ql, 7) << (8u * k); H8 |= b7_expand(qh, 7) << (8u * k);
         }
 #pragma unroll

@@ -603,10 +603,13 @@ __device__ __forceinline__ TableView make_view(const DracoFrame &f, int t, const
 // the counts the connectivity kernels have just produced, with the same function the host runs on the final counts
 // (draco_plan2_frame): per-frame sizes, block-wide exclusive scan over the frames, offsets written into the device descriptors.
 // A frame whose attribute tables outgrew their optimistic capacity is failed with UVOL_ERR_FRAME_CAPACITY, a batch that outgrew the
-// reserved arenas fails every frame with UVOL_ERR_BATCH_CAPACITY (the launcher re-plans and runs the batch again).  One block.
-__global__ void __launch_bounds__(1024) k_plan2(DracoFrame *frames, DracoCounts *counts, DracoBatchPlan *bp, int n, uint64_t out_index_bytes,
+// reserved arenas fails every frame with UVOL_ERR_BATCH_CAPACITY (the launcher re-plans and runs the batch again).  One block of 256
+// threads: small enough to start at once next to the resident entropy / connectivity blocks of the side streams (a 1024-thread
+// block waited 14 ms for an SM to drain).
+#define PLAN_T 256
+__global__ void __launch_bounds__(PLAN_T) k_plan2(DracoFrame *frames, DracoCounts *counts, DracoBatchPlan *bp, int n, uint64_t out_index_bytes,
                                                 uint64_t cap_s2, uint64_t cap_z2, uint64_t cap_out) {
-    __shared__ unsigned long long wsum[6][32]; __shared__ unsigned long long carry[6], total[4]; __shared__ int over;
+    __shared__ unsigned long long wsum[6][PLAN_T / 32]; __shared__ unsigned long long carry[6], total[4]; __shared__ int over;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     // pass 0 totals the per-slot output sizes (the region bases need them), pass 1 assigns
     for (int pass = 0; pass < 2; pass++) {
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(1024) k_plan2(DracoFrame *frames, DracoCounts 
                    for (int k = 0; k < 4; k++) { carry[2 + k] = base[k]; bp->slot_base[k] = base[k]; bp->slot_bytes[k] = total[k]; } bp->out_need = need; }
         }
         __syncthreads();
-        for (int base = 0; base < n; base += 1024) {
+        for (int base = 0; base < n; base += PLAN_T) {
             const int i = base + tid;
             Plan2Cursor sz{0, 0, {0, 0, 0, 0}};
             if (i < n && !frame_dead(frames, counts, i)) {
@@ -642,7 +645,7 @@ __global__ void __launch_bounds__(1024) k_plan2(DracoFrame *frames, DracoCounts 
                 draco_plan2_frame(frames[i], counts[i], cur, true);
             }
             __syncthreads();
-            if (tid == 1023) for (int k = 0; k < 6; k++) carry[k] = pre[k] + x[k];
+            if (tid == PLAN_T - 1) for (int k = 0; k < 6; k++) carry[k] = pre[k] + x[k];
             __syncthreads();
         }
         if (tid == 0 && pass == 0) for (int k = 0; k < 4; k++) total[k] = carry[2 + k];
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(1024) k_plan2(DracoFrame *frames, DracoCounts 
         bp->overflow = (uint32_t)over;
     }
     __syncthreads();
-    if (over) for (int i = tid; i < n; i += 1024) if (!frames[i].status && !counts[i].status) counts[i].status = UVOL_ERR_BATCH_CAPACITY;
+    if (over) for (int i = tid; i < n; i += PLAN_T) if (!frames[i].status && !counts[i].status) counts[i].status = UVOL_ERR_BATCH_CAPACITY;
 }
 
 // Traversal records of one corner table (element-parallel, one thread per face): the three vertex ids, the three opposite corners
@@ -1309,7 +1312,7 @@ static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_
     k_scan<<<dim3(n, 1), 1024, 0, st>>>(dF, dC, dS, 4); launches++;
     stamp("point_count");
     // ---- the count-sized arrays are laid out on the device; everything below is enqueued without waiting for it
-    k_plan2<<<1, 1024, 0, st>>>(dF, dC, dBP, n, pl.out_index, B.cap_s2, B.cap_z2, B.cap_out); launches++;
+    k_plan2<<<1, PLAN_T, 0, st>>>(dF, dC, dBP, n, pl.out_index, B.cap_s2, B.cap_z2, B.cap_out); launches++;
     stamp("plan2");
     if (memory == UVOL_MEM_HOST) {      // the batch plan (region bases of the output arena) travels to the host now: it is read below, once everything is enqueued
         UVOL_CUDA(ctx, ctx->h_aux.reserve(256));

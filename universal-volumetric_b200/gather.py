@@ -139,8 +139,8 @@ def frame_views(tables, arenas, rank, i):
 # Whole-shard gather (BASELINE configs[3]: one sequence frame-sharded across G GPUs, then gathered): geometry AND textures.
 # A rank's decoded shard is two contiguous spans of library-owned memory (the geometry output arena: every index buffer, then
 # the per-point arrays; the texture output arena: the segments back to back), so nothing is packed or staged: after one
-# all_gather of the small per-item tables, rank r's spans travel as two broadcasts straight out of the library's buffers into
-# every other rank's slot of one receive arena (an all-gather with per-rank sizes; NVLink / NVSwitch carries the payload).
+# all_gather of the small per-item tables, rank r copies its spans into its own slot of one receive arena and broadcasts the
+# slot to every other rank (an all-gather with per-rank sizes; NVLink / NVSwitch carries the payload).
 GCOLS = 8       # geometry rows: status, num_points, num_faces, off_index, off_position, off_normal, off_uv, span_bytes
 TCOLS = 8       # texture rows:  status, width, height, layers, format, has_alpha, off_data, bytes
 
@@ -211,11 +211,8 @@ def all_gather_shard(geo, n_geo, tex, n_tex, device, group=None, arena=None):
                 continue
             slot = arena[off: off + nb]
             if r == rank:
-                src = arena_tensor(base, nb, device)
-                dist.broadcast(src, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
-                slot.copy_(src)
-            else:
-                dist.broadcast(slot, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+                slot.copy_(arena_tensor(base, nb, device))          # own span: one device copy out of the library's buffer into its slot (the collective then
+            dist.broadcast(slot, src=dist.get_global_rank(group, r) if group is not None else r, group=group)      # runs on torch-owned memory only)
     return {"gtabs": gtabs, "ttabs": ttabs, "arena": arena, "geo_off": geo_off, "tex_off": tex_off, "bytes": [m[2] + m[3] for m in metas], "cuda": cuda}
 
 
