@@ -387,6 +387,8 @@ def main():
     import torch
     import torch.distributed as dist
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"                      # keep NCCL's version banner off stdout: the line printed there is the JSON result
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     uv = importlib.import_module("universal-volumetric_b200")

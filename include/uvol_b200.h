@@ -40,7 +40,8 @@ enum uvol_memory { UVOL_MEM_DEVICE = 0, UVOL_MEM_HOST = 1 };
  * RGBA_BPTC_Format, :602-604): 16 bytes per 4x4 block in block raster order, layers back to back; ETC1S (with or without alpha) ->
  * BC7 mode 5, UASTC -> the BC7 mode with the same subset shapes and weight grid (csrc/bc7_core.h).  Not bit-identical to the
  * reference's transcoder (whose tables are not in its tree): validated by an independent BC7 decoder, bounds in tests/test_bc7.py. */
-enum uvol_texture_format { UVOL_TEX_RGBA32 = 0, UVOL_TEX_ETC1 = 1, UVOL_TEX_BC7 = 2 };
+enum uvol_texture_format { UVOL_TEX_RGBA32 = 0, UVOL_TEX_ETC1 = 1, UVOL_TEX_BC7 = 2,
+                           UVOL_TEX_ETC2_RGB = 3 /* only as the format of uvol_upload_etc2_batch results: raw blocks passed through */ };
 
 /* Result of one geometry frame.  Replaces the Draco worker reply
  *   {type:'decode', geometry:{index:{array:Uint32Array(F*3)}, attributes:[{name, array:Float32Array(P*itemSize), itemSize}]}}
@@ -137,16 +138,63 @@ int uvol_get_stats_kind(const uvol_ctx *ctx, int kind /*0 geometry, 1 texture*/,
 /* ---- V1 geometry: replaces the worker's per-frame `new CortoDecoder(slice).decode()` loop (src/V1/worker.ts:48-68;
  * src/lib/corto.ts:73-140 == crt::Decoder::decode, deprecated/encoder/dev/src/decoder.cpp:122-173) for n frames sliced
  * out of a .drcs by the manifest's startBytePosition / meshLength (src/Interfaces.ts:1-8).  Result = the
- * bufferGeometry of src/V1/player.ts:289-297: index (u32 here; the JS path narrows to u16 when nface < 65536,
- * corto.ts:675-680), position f32[V*3], uv f32[V*2].  The single-frame C ABI of the reference is in corto_codec.h. */
+ * bufferGeometry of src/V1/player.ts:289-297: index (u32; with uvol_config.corto_index_u16 also narrowed to u16 when
+ * nface < 65536 like the JS path, corto.ts:675-680), position f32[V*3], uv f32[V*2], plus normals / colours when the file
+ * carries them.  The single-frame C ABI of the reference is in corto_codec.h. */
 typedef struct uvol_corto_mesh {
     int32_t status;
-    uint32_t num_vertices, num_faces, pad;
+    uint32_t num_vertices, num_faces;
+    uint32_t index_type;   /* 0: only `index` (u32); 1: `index16` is filled as well (uvol_config.corto_index_u16 and num_faces < 65536) */
     uint32_t *index;       /* u32[num_faces*3] */
     float *position;       /* f32[num_vertices*3] */
     float *uv;             /* f32[num_vertices*2] or NULL */
+    float *normal;         /* f32[num_vertices*3] or NULL: "normal" attribute, codec 2 (src/lib/corto.ts:470-671) */
+    uint8_t *color;        /* u8[num_vertices*4] RGBA or NULL: "color" attribute, codec 3 (src/lib/corto.ts:439-466) */
+    uint16_t *index16;     /* u16[num_faces*3] or NULL: the web player's index layout (src/V1/player.ts:292) */
 } uvol_corto_mesh;
 int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int memory, uvol_corto_mesh *out);
+
+/* ---- a clip on local storage, opened by its manifest (csrc/uvol_sequence.cpp).  Mirrors the decode side of the reference's
+ * players: V1 / V2 dispatch on version == "v2" (src/Player.ts:127-132); the V2 schema in both dialects (src/Interfaces.ts:75-132;
+ * scripts/Encoder.py:311-328), target choice and path templates (src/V2/player.ts:141-174,199-221; src/utils.ts:10-45);
+ * decodeDraco(url, frameNo) / decodeKTX2(url, segmentNo) keyed by frame / segment number (:325-366); V1: .manifest -> .drcs, one
+ * range read, per-frame slices (src/V1/player.ts:337; src/V1/worker.ts:37-68).  Results are library-owned like those of the batch
+ * calls (valid until the next decode on the same ctx, or uvol_release). */
+typedef struct uvol_sequence uvol_sequence;
+typedef struct uvol_sequence_info {
+    int32_t version;                 /* 1 or 2 */
+    uint32_t geometry_frame_count;   /* V2: geometry target frameCount; V1: frameData entries */
+    double geometry_frame_rate, texture_frame_rate;
+    uint32_t sequence_size, sequence_count;      /* V2: layers per KTX2 segment, number of segments */
+    uint32_t max_vertices, max_triangles;        /* V1 */
+} uvol_sequence_info;
+int uvol_open(uvol_ctx *ctx, const char *manifest_path, uvol_sequence **out);
+void uvol_close(uvol_sequence *seq);
+int uvol_sequence_get_info(const uvol_sequence *seq, uvol_sequence_info *out);
+/* the file a geometry frame (kind 0) / texture segment (kind 1) number maps to; returns its length or a negative status */
+int uvol_sequence_url(const uvol_sequence *seq, int kind, int number, char *buf, size_t cap);
+/* time -> geometry frame, texture segment, layer inside the segment (src/V2/player.ts:43-45,418-420,446) */
+int uvol_sequence_frames_at(const uvol_sequence *seq, double t, uint32_t *geometry_frame, uint32_t *segment, uint32_t *layer);
+/* V2: frames [first_frame, +n_frames) and segments [first_segment, +n_segments) in one uvol_decode_v2_batch call (texture target =
+ * uvol_config.texture_target); a missing file is a per-item UVOL_STATUS_IO */
+int uvol_decode_range(uvol_sequence *seq, int first_frame, int n_frames, int first_segment, int n_segments, int memory,
+                      uvol_geometry *out_geo, uvol_texture *out_tex);
+/* V1: frameData[first .. first + n) in one uvol_decode_corto_batch call; keyframe_numbers (optional) = the keys of the player's meshBuffer */
+int uvol_decode_v1_range(uvol_sequence *seq, int first, int n, int memory, uvol_corto_mesh *out, uint32_t *keyframe_numbers);
+/* Frees the result buffers of `ctx` (device and pinned host) -- the explicit end of the ownership the library holds over returned
+ * arrays (the reference's workers hand ownership over with transferables); every pointer returned before becomes invalid. */
+int uvol_release(uvol_ctx *ctx);
+
+/* ---- the texture-side pieces outside the KTX2 path (csrc/v1_texture.cu)
+ * V1: frame number of n decoded RGBA8 video frames from the 16-cell binary counter in their bottom-left corner
+ * (drawVideoAndGetCurrentFrameNumber, src/V1/player.ts:305-334; window_size = encoderWindowSize 8, byte_length = encoderByteLength 16,
+ * src/Player.ts:47-48).  frames: device memory when frames_on_device != 0 (e.g. NVDEC output), else host memory. */
+int uvol_v1_frame_numbers(uvol_ctx *ctx, const uint8_t *frames, int frames_on_device, int n, int width, int height,
+                          int window_size, int byte_length, int32_t *out);
+/* V2 'etc2' texture target (src/V2/player.ts:338-356,454-470): raw RGB-ETC2 block files, one per frame, handed to the GPU as they are.
+ * Each file must hold exactly ceil(w/4) * ceil(h/4) * 8 bytes (else a per-item status); out[i].format = UVOL_TEX_ETC2_RGB. */
+int uvol_upload_etc2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int width, int height,
+                           int memory, uvol_texture *out);
 
 /* Makes `ctx` use the phase-2 geometry scratch of `owner` (same device) instead of allocating its own.  For sequences
  * decoded in WINDOWS (the prefetch window of src/V2/player.ts:272-323, `fps x bufferDuration` frames): one ctx per window

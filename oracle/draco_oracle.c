@@ -643,6 +643,27 @@ void uvo_draco_free(uvo_draco_mesh *m) {
     memset(m, 0, sizeof *m);
 }
 
+/* Metadata section (header flag 0x8000; written by draco::MetadataEncoder::EncodeGeometryMetadata): decoded past, never used --
+ * DRACOLoader reads no metadata (src/lib/DRACOLoader.js:470-554).  Layout: varint number of attribute metadata, each {varint attribute
+ * unique id, metadata}; then the geometry's own metadata.  metadata = varint entries, each {u8 name length, name, varint value size,
+ * value}; varint sub-metadata count, each {u8 name length, name, metadata}. */
+static int skip_metadata(rd_t *r, int depth) {
+    if (depth > 32) return -1;
+    uint64_t ne = rd_varint(r);
+    if (r->err || ne > r->n) return -1;
+    for (uint64_t i = 0; i < ne; i++) {
+        uint8_t nl = rd_u8(r); if (r->err || nl > r->n - r->p) return -1; r->p += nl;
+        uint64_t vs = rd_varint(r); if (r->err || vs > r->n - r->p) return -1; r->p += vs;
+    }
+    uint64_t ns = rd_varint(r);
+    if (r->err || ns > r->n) return -1;
+    for (uint64_t i = 0; i < ns; i++) {
+        uint8_t nl = rd_u8(r); if (r->err || nl > r->n - r->p) return -1; r->p += nl;
+        if (skip_metadata(r, depth + 1)) return -1;
+    }
+    return 0;
+}
+
 int uvo_draco_decode(const uint8_t *data, size_t len, uvo_draco_mesh *out) {
     memset(out, 0, sizeof *out);
     conn_t cn; memset(&cn, 0, sizeof cn);
@@ -656,7 +677,13 @@ int uvo_draco_decode(const uint8_t *data, size_t len, uvo_draco_mesh *out) {
     r->p = 5;
     int maj = rd_u8(r), mino = rd_u8(r), etype = rd_u8(r), meth = rd_u8(r); int flags = rd_u16(r);
     if (maj != 2 || mino != 2) FAIL(UVO_ERR_UNSUPPORTED);
-    if (etype != 1 || meth != 1 || (flags & 0x8000)) FAIL(UVO_ERR_UNSUPPORTED);
+    if (etype != 1 || meth != 1) FAIL(UVO_ERR_UNSUPPORTED);
+    if (flags & 0x8000) {
+        uint64_t na = rd_varint(r);
+        if (r->err || na > len) FAIL(UVO_ERR_CORRUPT);
+        for (uint64_t i = 0; i < na; i++) { (void)rd_varint(r); if (skip_metadata(r, 0)) FAIL(UVO_ERR_CORRUPT); }
+        if (skip_metadata(r, 0)) FAIL(UVO_ERR_CORRUPT);
+    }
     if ((rc = decode_connectivity(&cn))) goto done;
     if ((rc = decode_attribute_connectivity(&cn, at))) goto done;
     const ctab_t *t = &cn.t; const int F = t->F, nad = cn.nad;

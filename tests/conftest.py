@@ -60,3 +60,28 @@ def fixture_ktx2(limit=None):
 def read(path):
     with open(path, "rb") as fh:
         return fh.read()
+
+
+def with_draco_metadata(blob):
+    """The same .drc with the metadata flag set and a metadata section spliced in behind the header (one attribute metadata, a
+    geometry metadata with two entries and a nested sub-metadata), as draco::MetadataEncoder writes it."""
+    def varint(v):
+        o = b""
+        while True:
+            c = v & 0x7F; v >>= 7
+            if v:
+                o += bytes([c | 0x80])
+            else:
+                return o + bytes([c])
+
+    def md(entries, subs=()):
+        o = varint(len(entries))
+        for k, v in entries:
+            o += bytes([len(k)]) + k + varint(len(v)) + v
+        o += varint(len(subs))
+        for k, m in subs:
+            o += bytes([len(k)]) + k + m
+        return o
+    meta = varint(1) + varint(0) + md([(b"name", b"position")]) + md([(b"clip", b"liam"), (b"fps", b"\x1e\0\0\0")], [(b"sub", md([(b"k", b"v" * 300)]))])
+    hdr = bytearray(blob[:11]); hdr[10] |= 0x80
+    return bytes(hdr) + meta + blob[11:]

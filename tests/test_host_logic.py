@@ -52,6 +52,18 @@ def test_draco_core_logic_matches_oracle(built, name):
         assert np.array_equal(e[k].view(np.uint32), o[k].view(np.uint32)), k
 
 
+def test_draco_metadata_is_skipped(built):
+    """A file with the metadata flag (header bit 15) decodes to the same mesh: the section is walked past by the parser and by the
+    oracle (the reference's loader reads no metadata, DRACOLoader.js:470-554); a truncated metadata section is an error."""
+    from conftest import with_draco_metadata
+    blob = read(os.path.join(GOLDEN, "liam", "00000.drc")); mb = with_draco_metadata(blob)
+    e, o, o0 = emu_draco(mb), oracle_draco(mb), oracle_draco(blob)
+    assert e["status"] == 0 and o["status"] == 0 and np.array_equal(o["index"], o0["index"]) and np.array_equal(e["index"], o0["index"])
+    for k in ("position", "normal", "uv"):
+        assert np.array_equal(e[k].view(np.uint32), o0[k].view(np.uint32)), k
+    assert emu_draco(mb[:40])["status"] < 0 and oracle_draco(mb[:40])["status"] < 0
+
+
 def test_basis_core_logic_matches_oracle(built):
     blob = read(os.path.join(GOLDEN, "liam", "00000.ktx2"))
     e, o = emu_ktx2(blob), oracle_ktx2(blob)

@@ -308,3 +308,47 @@ def test_v1_sequence_slices_and_keys(tmp_path):
     assert seen == [[b"B" * 140, b"C" * 90, b"D" * 60]] and sorted(out) == [1, 3]                    # frame 2 failed to decode -> absent
     assert out[3]["frameNumber"] == 3 and out[3]["bufferGeometry"]["index"] == 60 and out[1]["bufferGeometry"]["position"] == b"B"
     assert sq.decode(4, 9) == {} and sq.man.mesh_file.endswith("clip.drcs")
+
+
+def test_native_sequence_open_matches_python_manifest(tmp_path):
+    """The C++ host layer (csrc/uvol_sequence.cpp: uvol_open / uvol_sequence_get_info / uvol_sequence_url / uvol_sequence_frames_at) reads
+    both V2 dialects and V1 manifests exactly like manifest.py (= src/Interfaces.ts, src/V2/player.ts:141-174,418-446, src/utils.ts:10-45)."""
+    import ctypes
+    uvp = importlib.import_module("universal-volumetric_b200")
+    L = uvp._native.lib()
+
+    def open_seq(path):
+        h = ctypes.c_void_p()
+        assert L.uvol_open(None, str(path).encode(), ctypes.byref(h)) == 0 and h
+        return h
+
+    def url(h, kind, n):
+        buf = ctypes.create_string_buffer(1024)
+        assert L.uvol_sequence_url(h, kind, n, buf, 1024) > 0
+        return buf.value.decode()
+    for dialect in ("player", "encoder"):
+        m = man.emit_v2("geometry_[target]/[#####][ext]" if dialect == "player" else "DRACO/frame_[#####].drc", 30, 250,
+                        "texture_[target]_[type]_[tag]/[#####][ext]" if dialect == "player" else "KTX2/texture_[#######].ktx2", 30, 5, 50, dialect=dialect)
+        p = tmp_path / f"{dialect}.uvol.json"; p.write_text(json.dumps(m))
+        py = man.V2Manifest.load(str(p)); h = open_seq(p)
+        info = uvp._native.SequenceInfo(); assert L.uvol_sequence_get_info(h, ctypes.byref(info)) == 0
+        assert (info.version, info.geometry_frame_count, info.sequence_size, info.sequence_count, info.geometry_frame_rate) == (2, 250, 5, 50, 30.0)
+        for n in (0, 7, 249):
+            assert url(h, 0, n) == py.geometry_url(n)
+        for n in (0, 49):
+            assert url(h, 1, n) == py.texture_url(n)
+        for t in (0.0, 0.016, 0.05, 1.0, 3.99, 8.3):
+            g = ctypes.c_uint32(); s = ctypes.c_uint32(); l = ctypes.c_uint32()
+            assert L.uvol_sequence_frames_at(h, t, ctypes.byref(g), ctypes.byref(s), ctypes.byref(l)) == 0
+            w = py.frames_at(t)
+            assert (g.value, s.value, l.value) == (w["geometry_frame"], w["segment"], w["layer"])
+        L.uvol_close(h)
+    v1 = man.emit_v1(30, [(100, 196, 1500), (101, 198, 1520), (99, 194, 1480)])
+    p = tmp_path / "clip.manifest"; p.write_text(json.dumps(v1))
+    h = open_seq(p); info = uvp._native.SequenceInfo(); L.uvol_sequence_get_info(h, ctypes.byref(info))
+    assert (info.version, info.geometry_frame_count, info.max_vertices, info.max_triangles) == (1, 3, 101, 198)
+    L.uvol_close(h)
+    bad = tmp_path / "bad.json"; bad.write_text('{"version": "v2", "geometry": [1, 2')
+    h = ctypes.c_void_p()
+    assert L.uvol_open(None, str(bad).encode(), ctypes.byref(h)) < 0 and not h
+    assert L.uvol_open(None, str(tmp_path / "missing.json").encode(), ctypes.byref(h)) == -6

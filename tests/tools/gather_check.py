@@ -31,12 +31,13 @@ def main():
     g, t = uv.V2Player(ctx).decode_step_raw(drc[f0:f1], ktx[s0:s1], uv.MEM_DEVICE)
     G = uv.gather.all_gather_shard(g, f1 - f0, t, s1 - s0, f"cuda:{local}")
     h = hashlib.sha256(); nbytes = 0
-    for r in range(world):                         # rank order == frame order (contiguous shards)
+    for r in range(world):                         # rank order == frame order (contiguous shards): every geometry frame of the sequence ...
         for i in range(len(G["gtabs"][r])):
             v = uv.gather.shard_frame_views(G, r, i)
             assert v is not None, (r, i)
             for k in ("index", "position", "normal", "uv"):
                 b = v[k].cpu().numpy().tobytes(); h.update(b); nbytes += len(b)
+    for r in range(world):                         # ... then every texture segment, like the single-GPU walk below
         for i in range(len(G["ttabs"][r])):
             b = uv.gather.shard_texture_view(G, r, i).cpu().numpy().tobytes(); h.update(b); nbytes += len(b)
     mine = h.hexdigest()

@@ -13,6 +13,7 @@ MEM_DEVICE, MEM_HOST = 0, 1
 TEX_RGBA32 = 0
 TEX_ETC1 = 1
 TEX_BC7 = 2
+TEX_ETC2_RGB = 3
 
 
 class UvolError(RuntimeError):
@@ -34,14 +35,20 @@ class Texture(ctypes.Structure):
 
 
 class CortoMesh(ctypes.Structure):
-    _fields_ = [("status", ctypes.c_int32), ("num_vertices", ctypes.c_uint32), ("num_faces", ctypes.c_uint32), ("pad", ctypes.c_uint32),
-                ("index", ctypes.POINTER(ctypes.c_uint32)), ("position", ctypes.POINTER(ctypes.c_float)), ("uv", ctypes.POINTER(ctypes.c_float))]
+    _fields_ = [("status", ctypes.c_int32), ("num_vertices", ctypes.c_uint32), ("num_faces", ctypes.c_uint32), ("index_type", ctypes.c_uint32),
+                ("index", ctypes.POINTER(ctypes.c_uint32)), ("position", ctypes.POINTER(ctypes.c_float)), ("uv", ctypes.POINTER(ctypes.c_float)),
+                ("normal", ctypes.POINTER(ctypes.c_float)), ("color", ctypes.POINTER(ctypes.c_uint8)), ("index16", ctypes.POINTER(ctypes.c_uint16))]
 
 
 class Config(ctypes.Structure):
     """uvol_config (include/uvol_b200.h)."""
     _fields_ = [("struct_size", ctypes.c_uint32), ("texture_target", ctypes.c_uint32), ("corto_index_u16", ctypes.c_uint32), ("staging_threads", ctypes.c_uint32),
                 ("max_faces_per_frame", ctypes.c_uint64), ("max_texture_bytes", ctypes.c_uint64), ("buffer_duration_s", ctypes.c_double), ("interval_duration_s", ctypes.c_double)]
+
+
+class SequenceInfo(ctypes.Structure):
+    _fields_ = [("version", ctypes.c_int32), ("geometry_frame_count", ctypes.c_uint32), ("geometry_frame_rate", ctypes.c_double), ("texture_frame_rate", ctypes.c_double),
+                ("sequence_size", ctypes.c_uint32), ("sequence_count", ctypes.c_uint32), ("max_vertices", ctypes.c_uint32), ("max_triangles", ctypes.c_uint32)]
 
 
 class Vector2(ctypes.Structure):
@@ -94,6 +101,16 @@ def lib():
     L.uvol_replay_v2_batch.argtypes = [vp, i, ctypes.POINTER(Geometry), i, ctypes.POINTER(Texture), i]; L.uvol_replay_v2_batch.restype = i
     L.uvol_get_stats_kind.argtypes = [vp, i, ctypes.POINTER(Stats)]; L.uvol_get_stats_kind.restype = i
     L.uvol_decode_corto_batch.argtypes = [vp, pv, ps, i, i, ctypes.POINTER(CortoMesh)]; L.uvol_decode_corto_batch.restype = i
+    L.uvol_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]; L.uvol_open.restype = i
+    L.uvol_close.argtypes = [vp]; L.uvol_close.restype = None
+    L.uvol_sequence_get_info.argtypes = [vp, ctypes.POINTER(SequenceInfo)]; L.uvol_sequence_get_info.restype = i
+    L.uvol_sequence_url.argtypes = [vp, i, i, ctypes.c_char_p, sz]; L.uvol_sequence_url.restype = i
+    L.uvol_sequence_frames_at.argtypes = [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]; L.uvol_sequence_frames_at.restype = i
+    L.uvol_decode_range.argtypes = [vp, i, i, i, i, i, ctypes.POINTER(Geometry), ctypes.POINTER(Texture)]; L.uvol_decode_range.restype = i
+    L.uvol_decode_v1_range.argtypes = [vp, i, i, i, ctypes.POINTER(CortoMesh), ctypes.POINTER(ctypes.c_uint32)]; L.uvol_decode_v1_range.restype = i
+    L.uvol_release.argtypes = [vp]; L.uvol_release.restype = i
+    L.uvol_v1_frame_numbers.argtypes = [vp, vp, i, i, i, i, i, i, ctypes.POINTER(ctypes.c_int32)]; L.uvol_v1_frame_numbers.restype = i
+    L.uvol_upload_etc2_batch.argtypes = [vp, pv, ps, i, i, i, i, ctypes.POINTER(Texture)]; L.uvol_upload_etc2_batch.restype = i
     L.CreateDecoder.argtypes = [i, ctypes.c_char_p, ctypes.POINTER(Vector2)]; L.CreateDecoder.restype = vp
     L.DestroyDecoder.argtypes = [vp]; L.DestroyDecoder.restype = None
     L.DecodeMesh.argtypes = [vp, vp, vp, vp, vp, vp]; L.DecodeMesh.restype = i
@@ -103,4 +120,6 @@ def lib():
 
 EXPORTED_SYMBOLS = ["uvol_create", "uvol_create_with_config", "uvol_config_default", "uvol_get_config", "uvol_destroy", "uvol_last_error", "uvol_get_stats", "uvol_stage_name", "uvol_set_profiling",
                     "uvol_decode_draco_batch", "uvol_transcode_ktx2_batch", "uvol_replay_draco_batch", "uvol_replay_ktx2_batch", "uvol_flush_l2", "uvol_decode_v2_batch", "uvol_replay_v2_batch", "uvol_get_stats_kind", "uvol_decode_corto_batch",
+                    "uvol_open", "uvol_close", "uvol_sequence_get_info", "uvol_sequence_url", "uvol_sequence_frames_at", "uvol_decode_range", "uvol_decode_v1_range", "uvol_release", "uvol_v1_frame_numbers", "uvol_upload_etc2_batch",
+                    "uvol_share_arenas", "uvol_share_host_outputs", "uvol_span_ms", "uvol_zstd_inflate", "uvol_zstd_feature_counts",
                     "CreateDecoder", "DestroyDecoder", "DecodeMesh"]

@@ -378,8 +378,10 @@ static int ktx2_fresh(uvol_ctx *ctx, const uint8_t *const *data, const size_t *s
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
     UVOL_CUDA(ctx, ctx->h_tstate.reserve(st_bytes));                       // per-ctx even when the bulk result buffer is shared
     if (memory == UVOL_MEM_HOST) UVOL_CUDA(ctx, ctx->ph_tout->reserve(B.out + 256));
-    // chunks of about 1/8 of the input (at least 64 MB) -- a small first chunk gets the pipeline going
+    // chunks of about 1/8 of the input (at least 64 MB) -- a small first chunk gets the pipeline going.  Uploads and kernels run on
+    // `st`, the result copies on s4 behind a per-chunk event, so chunk k's copy overlaps chunk k+1's upload and kernels.
     const uint64_t per = std::max<uint64_t>(64ull << 20, B.bytes_in / 8 + 1);
+    int chunk = 0;
     int ev = 0; bool first = true;
     if (ctx->profile) cudaEventRecord(ctx->tex_ev[0], st);
     ev = 1;
@@ -408,10 +410,15 @@ static int ktx2_fresh(uvol_ctx *ctx, const uint8_t *const *data, const size_t *s
             uint64_t o0 = ~0ull, o1 = 0;
             for (int i = i0; i < i1; i++) if (!B.files[i].status) { const uint64_t a = B.files[i].o_rgba; if (a < o0) o0 = a; }
             o1 = B.out; for (int i = i1; i < n; i++) if (!B.files[i].status) { o1 = B.files[i].o_rgba; break; }
-            if (o0 != ~0ull && o1 > o0) UVOL_CUDA(ctx, cudaMemcpyAsync(hO + o0, dO + o0, o1 - o0, cudaMemcpyDeviceToHost, st));
+            if (o0 != ~0ull && o1 > o0) {
+                cudaEvent_t e = ctx->tex_chunk_ev[chunk % 16];
+                UVOL_CUDA(ctx, cudaEventRecord(e, st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(ctx->s4, e, 0));
+                UVOL_CUDA(ctx, cudaMemcpyAsync(hO + o0, dO + o0, o1 - o0, cudaMemcpyDeviceToHost, ctx->s4));
+            }
         }
-        first = false; i0 = i1;
+        first = false; i0 = i1; chunk++;
     }
+    if (hO) { UVOL_CUDA(ctx, cudaEventRecord(ctx->tex_chunk_ev[15], ctx->s4)); UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->tex_chunk_ev[15], 0)); }      // `st` ends after the last result copy
     ctx->span_tex_end = ev - 1;
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_tstate.p, ctx->d_tslices.p, sizeof(TexState) * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (ctx->profile && ev < 8) cudaEventRecord(ctx->tex_ev[ev], st);

@@ -6,34 +6,44 @@
 // (src/V1/worker.ts:48-68).  Layout: SURVEY.md Appendix C.  Stages:
 //   tunstall   one warp per Tunstall block: lane 0 rebuilds the 256-word dictionary (tunstall.cpp:125-256),
 //              then the warp expands the code bytes with a prefix sum over word lengths (:430-452)
-//   faces      one warp per frame: the front-growing connectivity walk (decoder.cpp:181-333), serial
+//   faces      one warp per frame: the front-growing connectivity walk (corto_core.h; decoder.cpp:181-333)
 //   values     one CTA per (frame, attribute): prefix sum of the per-value bit widths -> every value's bit
 //              offset -> parallel bit extraction (cstream.h:296-362; bitstream.cpp:103-121, MSB-first words)
-//   delta      one warp per (frame, attribute): parallelogram / delta reversal (vertex_attribute.h:155-177)
-//   dequant    element-parallel: (float)value * q (vertex_attribute.h:179-224)
-// Supported: generic attributes "position" (3 x f32) and "uv" (2 x f32), both strategies, Tunstall or no
-// entropy coding; normal / colour codecs are rejected with UNSUPPORTED (UVOL V1 carries position + uv only,
-// src/V1/player.ts:292-294).
+//   delta      one warp per (frame, attribute): parallelogram / delta reversal (vertex_attribute.h:155-177; normals with DIFF
+//              prediction: normal_attribute.cpp:182-204)
+//   estimate   (normals with ESTIMATED / BORDER prediction, normal_attribute.cpp:24-59,206-303): vertex -> incident corners lists
+//              (count, scan, fill), then per vertex the face normals are summed IN FACE ORDER (the reference accumulates floats
+//              face by face, so the order is part of the result) and the boundary mark is XOR-ed together
+//   dequant    element-parallel: (float)value * q (vertex_attribute.h:179-224); octahedral -> unit normals
+//              (normal_attribute.h:104-112); YCC -> RGB colours times the per-channel step (color_attribute.cpp:69-90, point.h:214)
+// Attributes: "position" (3 x f32), "uv" (2 x f32), "normal" (codec 2, all three predictions, 3 x f32), "color" (codec 3, RGBA8);
+// other generic attributes are skipped over (they are self-delimiting).  Tunstall or no entropy coding.
 #include <chrono>
 #include <string.h>
 #include <string>
 #include <vector>
 #include "uvol_ctx.h"
+#include "corto_core.h"
 #include "../../include/corto_codec.h"
 
 namespace {
 
-enum { CL_VERTEX = 0, CL_LEFT = 1, CL_RIGHT = 2, CL_END = 3, CL_BOUNDARY = 4, CL_DELAY = 5, CL_SPLIT = 6 };
-
 struct TunBlock { uint32_t probs_off, nsym, size, csize, data_off; uint64_t o_out; };      // offsets inside the file; o_out in scratch
 struct BitBlock { uint32_t nwords, data_off; };
-struct CortoAttr { int32_t kind /*0 position 1 uv*/, N, strategy, nlogs; float q; BitBlock bits; TunBlock logs[4]; uint64_t o_val, out; };
+enum { CK_POSITION = 0, CK_UV = 1, CK_NORMAL = 2, CK_COLOR = 3 };
+struct CortoAttr {
+    int32_t kind, N /*header components*/, vN /*values per vertex in the stream*/, strategy, nlogs, pred /*normal prediction: 0 DIFF 1 ESTIMATED 2 BORDER*/;
+    float q; uint32_t qc[4]; uint32_t count /*values in the stream*/;
+    BitBlock bits; TunBlock logs[4]; uint64_t o_val, out;
+};
+#define CORTO_MAX_ATTRS 4
 struct CortoFrame {
     uint64_t file_off; uint32_t file_len; int32_t status;
     uint32_t nvert, nface, ngroups, groups_off /*aux u32: end face per group*/, max_front, entropy;
     TunBlock clers; BitBlock ibits;
-    int32_t nattr; CortoAttr attr[2];
-    uint64_t o_front, o_order, o_delayed, o_pred, out_index;
+    int32_t nattr, pos_attr, nrm_attr, index16; CortoAttr attr[CORTO_MAX_ATTRS];
+    uint64_t o_front, o_third, o_queue, o_delayed, o_pred, out_index, out_index16;
+    uint64_t o_voff, o_vfill, o_vlist, o_est, o_bflag;          // normal estimation: corner lists per vertex, summed face normals, boundary marks / their scan
 };
 struct CJob { uint32_t frame; int32_t what; };
 
@@ -43,14 +53,18 @@ struct Rd {
     uint16_t u16() { uint16_t a = u8(), c = u8(); return (uint16_t)(a | (c << 8)); }
     uint32_t u32() { if (p + 4 > n) { err = true; p = n; return 0; } uint32_t v; memcpy(&v, b + p, 4); p += 4; return v; }
     float f32() { uint32_t v = u32(); float f; memcpy(&f, &v, 4); return f; }
-    std::string str() { uint16_t l = u16(); if (err || p + l > n) { err = true; return ""; } std::string s((const char *)b + p, l ? l - 1 : 0); p += l; return s; }
+    std::string str() { uint16_t l = u16(); if (err || l > n - p) { err = true; return ""; } std::string s((const char *)b + p, l ? l - 1 : 0); p += l; return s; }
 };
 bool read_tunstall(Rd &r, uint32_t entropy, TunBlock &t) {
     memset(&t, 0, sizeof t);
-    if (entropy == 0) { t.nsym = 0xffffffffu; t.size = r.u32(); t.csize = t.size; t.data_off = (uint32_t)r.p; if (r.err || r.p + t.size > r.n) return false; r.p += t.size; return true; }
-    t.nsym = r.u8(); t.probs_off = (uint32_t)r.p; r.p += 2 * (size_t)t.nsym;
+    if (entropy == 0) { t.nsym = 0xffffffffu; t.size = r.u32(); t.csize = t.size; t.data_off = (uint32_t)r.p; if (r.err || t.size > r.n - r.p) return false; r.p += t.size; return true; }
+    t.nsym = r.u8(); t.probs_off = (uint32_t)r.p;
+    if (r.err || 2 * (size_t)t.nsym > r.n - r.p) return false;
+    r.p += 2 * (size_t)t.nsym;
     t.size = r.u32(); t.csize = r.u32(); t.data_off = (uint32_t)r.p;
-    if (r.err || r.p + t.csize > r.n || t.size > (1u << 28)) return false;
+    // a code byte expands to at most one dictionary word; the decoded size a header may claim is bounded by what its bytes can
+    // encode (words of up to 2 KiB) and by 2^28 -- checked before anything is reserved
+    if (r.err || t.csize > r.n - r.p || t.size > (1u << 28) || (uint64_t)t.size > 2048ull * t.csize + 64) return false;
     r.p += t.csize;
     return true;
 }
@@ -58,13 +72,13 @@ bool read_bits(Rd &r, BitBlock &b) {
     b.nwords = r.u32();
     const size_t pad = r.p & 3; if (pad) r.p += 4 - pad;
     b.data_off = (uint32_t)r.p;
-    if (r.err || r.p + 4ull * b.nwords > r.n) return false;
+    if (r.err || r.p > r.n || 4ull * b.nwords > r.n - r.p) return false;
     r.p += 4ull * b.nwords;
     return true;
 }
 
 // Header + section walk (decoder.cpp:41-85, index_attribute.h:83-98, cstream.h:285-362).
-int corto_parse(const uint8_t *data, size_t len, CortoFrame &f, std::vector<uint32_t> &aux) {
+int corto_parse(const uint8_t *data, size_t len, CortoFrame &f, std::vector<uint32_t> &aux, uint64_t max_faces) {
     Rd r{data, len, 0, false};
     if (len < 24 || r.u32() != 0x787A6300u) return UVOL_ERR_CORRUPT;
     (void)r.u32();
@@ -81,6 +95,7 @@ int corto_parse(const uint8_t *data, size_t len, CortoFrame &f, std::vector<uint
     f.nvert = r.u32(); f.nface = r.u32();
     if (r.err || f.nvert == 0 || f.nvert > (1u << 26) || f.nface > (1u << 27)) return UVOL_ERR_CORRUPT;
     if (f.nface == 0) return UVOL_ERR_UNSUPPORTED;                 // point clouds: DecodeMesh returns -1 (corto_codec.cpp:27-30)
+    if ((uint64_t)f.nface > max_faces) return UVOL_ERR_UNSUPPORTED; // resource limit (uvol_config.max_faces_per_frame)
     f.ngroups = r.u32(); f.groups_off = (uint32_t)aux.size();
     if (r.err || f.ngroups > 65536) return UVOL_ERR_CORRUPT;
     for (uint32_t g = 0; g < f.ngroups; g++) {
@@ -91,22 +106,45 @@ int corto_parse(const uint8_t *data, size_t len, CortoFrame &f, std::vector<uint
     }
     f.max_front = r.u32();
     if (!read_tunstall(r, f.entropy, f.clers) || !read_bits(r, f.ibits)) return UVOL_ERR_TRUNCATED;
+    // every face and every vertex costs at least one connectivity symbol: counts a header claims beyond that are rejected here,
+    // per item, before any arena is planned from them
+    if ((uint64_t)f.nface > (uint64_t)f.clers.size + 1 || (uint64_t)f.nvert > 3ull * f.clers.size + 3) return UVOL_ERR_CORRUPT;
     // attributes follow in std::map (alphabetical) order of their names (decoder.cpp:146-147)
     std::vector<int> order(nattr); for (uint32_t i = 0; i < nattr; i++) order[i] = (int)i;
     for (uint32_t i = 0; i < nattr; i++) for (uint32_t j = i + 1; j < nattr; j++) if (hdr[order[j]].name < hdr[order[i]].name) std::swap(order[i], order[j]);
-    f.nattr = 0;
+    f.nattr = 0; f.pos_attr = f.nrm_attr = -1;
     for (uint32_t i = 0; i < nattr; i++) {
         const Hdr &h = hdr[order[i]];
-        if (h.codec != 1 || h.N < 1 || h.N > 4) return UVOL_ERR_UNSUPPORTED;
+        if (h.N < 1 || h.N > 4) return UVOL_ERR_UNSUPPORTED;
         CortoAttr a; memset(&a, 0, sizeof a);
-        a.kind = h.name == "position" ? 0 : (h.name == "uv" ? 1 : -1); a.N = h.N; a.strategy = h.strategy; a.q = h.q;
+        a.N = h.N; a.strategy = h.strategy; a.q = h.q; a.kind = -1;
+        if (h.codec == 2) {                                   // NormalAttr::decode (normal_attribute.cpp:168-175): prediction byte, then a correlated array of 2
+            a.kind = h.name == "normal" ? CK_NORMAL : -1; a.vN = 2; a.nlogs = 1;
+            a.pred = r.u8();
+            if (r.err || a.pred > 2) return UVOL_ERR_CORRUPT;
+        } else if (h.codec == 3) {                            // ColorAttr::decode (color_attribute.h:55-59): one step byte per component, then per-component values
+            a.kind = h.name == "color" ? CK_COLOR : -1; a.vN = h.N; a.nlogs = h.N;
+            for (int k = 0; k < 4; k++) a.qc[k] = k < 3 ? 4 : 8;
+            for (int k = 0; k < h.N; k++) a.qc[k] = r.u8();
+        } else {
+            a.kind = h.name == "position" ? CK_POSITION : (h.name == "uv" ? CK_UV : -1); a.vN = h.N; a.nlogs = (h.strategy & 2) ? 1 : h.N;
+            if ((a.kind == CK_POSITION && a.N != 3) || (a.kind == CK_UV && a.N != 2)) return UVOL_ERR_UNSUPPORTED;
+        }
         if (!read_bits(r, a.bits)) return UVOL_ERR_TRUNCATED;
-        a.nlogs = (h.strategy & 2) ? 1 : h.N;
-        for (int k = 0; k < a.nlogs; k++) { if (!read_tunstall(r, f.entropy, a.logs[k])) return UVOL_ERR_TRUNCATED; if (a.logs[k].size != f.nvert) return UVOL_ERR_CORRUPT; }
-        if (a.kind < 0 || (a.kind == 0 && a.N != 3) || (a.kind == 1 && a.N != 2) || f.nattr >= 2) return UVOL_ERR_UNSUPPORTED;
+        for (int k = 0; k < a.nlogs; k++) {
+            if (!read_tunstall(r, f.entropy, a.logs[k])) return UVOL_ERR_TRUNCATED;
+            if (a.kind == CK_NORMAL ? a.logs[k].size > f.nvert : a.logs[k].size != f.nvert) return UVOL_ERR_CORRUPT;
+        }
+        a.count = a.logs[0].size;
+        if (a.kind == CK_NORMAL && a.pred != 2 && a.count != f.nvert) return UVOL_ERR_CORRUPT;
+        if (a.kind < 0) continue;                             // not exported: parsed past
+        for (int k = 0; k < f.nattr; k++) if (f.attr[k].kind == a.kind) return UVOL_ERR_CORRUPT;
+        if (f.nattr >= CORTO_MAX_ATTRS) return UVOL_ERR_UNSUPPORTED;
+        if (a.kind == CK_POSITION) f.pos_attr = f.nattr;
+        if (a.kind == CK_NORMAL) f.nrm_attr = f.nattr;
         f.attr[f.nattr++] = a;
     }
-    if (f.nattr < 1 || f.attr[0].kind != 0) return UVOL_ERR_UNSUPPORTED;
+    if (f.pos_attr < 0) return UVOL_ERR_UNSUPPORTED;
     return UVOL_OK;
 }
 
@@ -205,102 +243,24 @@ __global__ void __launch_bounds__(32 * CW) k_tunstall(const CortoFrame *frames, 
     }
 }
 
-// MSB-first bit reader over 32-bit little-endian words (bitstream.cpp:103-121)
-struct BitsMsb { const uint32_t *w; uint64_t pos; };
-__device__ __forceinline__ uint32_t bits_read(BitsMsb &b, int n) {
-    if (n == 0) return 0;
-    const uint64_t wi = b.pos >> 5; const int sh = (int)(b.pos & 31);
-    const uint64_t two = ((uint64_t)b.w[wi] << 32) | b.w[wi + 1];
-    b.pos += (uint64_t)n;
-    return (uint32_t)((two << sh) >> (64 - n));
-}
 __device__ __forceinline__ int ilog2_u(uint32_t p) { int k = 0; while (p >>= 1) ++k; return k; }
 
-struct FrontEdge { int v0, v1, v2, prev, next, deleted, pad0, pad1; };
-
-// Connectivity: front-growing walk (decoder.cpp:181-333), one warp per frame, lane 0 walks.
+// Connectivity: the front-growing walk (corto_core.h), one warp per frame, lane 0 walks (the batch supplies the parallelism).
 __global__ void __launch_bounds__(32 * CW) k_corto_faces(const CortoFrame *frames, int32_t *status, const uint8_t *blob, const uint32_t *aux, uint8_t *S, uint8_t *O, int nframes) {
     const int fi = blockIdx.x * CW + (threadIdx.x >> 5);
     if (fi >= nframes || (threadIdx.x & 31) != 0) return;
     if (frames[fi].status) { status[fi] = frames[fi].status; return; }
     if (status[fi]) return;
     const CortoFrame &f = frames[fi];
-    const uint8_t *clers = S + f.clers.o_out; const uint32_t nclers = f.clers.size;
-    BitsMsb bits{(const uint32_t *)(blob + f.file_off + f.ibits.data_off), 0};
-    const uint64_t maxbits = (uint64_t)f.ibits.nwords * 32;
-    FrontEdge *front = (FrontEdge *)(S + f.o_front); int *faceorder = (int *)(S + f.o_order), *delayed = (int *)(S + f.o_delayed);
-    int4 *pred = (int4 *)(S + f.o_pred); uint32_t *faces = (uint32_t *)(O + f.out_index);
-    const int nvert = (int)f.nvert, splitbits = ilog2_u(f.nvert) + 1;
-    const int front_cap = 3 * (int)f.nface + 8, order_cap = 2 * (int)f.nface + 8;
-    int vertex_count = 0, st = 0; uint32_t cler = 0, start = 0;
-#define CFAIL(code) do { st = (code); goto done; } while (0)
-#define PUSH_EDGE(a, b, c, p, n) do { if (nfront >= front_cap) CFAIL(UVOL_ERR_CORRUPT); FrontEdge e_ = {(a), (b), (c), (p), (n), 0, 0, 0}; front[nfront++] = e_; } while (0)
-    for (uint32_t g = 0; g < f.ngroups; g++) {
-        const uint32_t end = aux[f.groups_off + g] * 3;
-        int nfront = 0, norder = 0, order = 0, ndelayed = 0, new_edge = -1;
-        while (start < end) {
-            if (new_edge == -1 && order >= norder && ndelayed == 0) {
-                int last_index = vertex_count - 1, vindex[3], split = 0;
-                if (cler >= nclers) CFAIL(UVOL_ERR_TRUNCATED);
-                const int c = clers[cler++];
-                if (c == CL_SPLIT) { if (bits.pos + 3 > maxbits) CFAIL(UVOL_ERR_TRUNCATED); split = (int)bits_read(bits, 3); }
-                else if (c != CL_VERTEX) CFAIL(UVOL_ERR_CORRUPT);
-                for (int k = 0; k < 3; k++) {
-                    int v;
-                    if (split & (1 << k)) { if (bits.pos + splitbits > maxbits) CFAIL(UVOL_ERR_TRUNCATED); v = (int)bits_read(bits, splitbits); if (v >= nvert) CFAIL(UVOL_ERR_CORRUPT); }
-                    else { if (vertex_count >= nvert) CFAIL(UVOL_ERR_CORRUPT); pred[vertex_count] = make_int4(last_index, last_index, last_index, 0); last_index = v = vertex_count++; }
-                    vindex[k] = v; faces[start++] = (uint32_t)v;
-                }
-                const int cur = nfront;
-                if (norder + 3 > order_cap) CFAIL(UVOL_ERR_CORRUPT);
-                faceorder[norder++] = nfront; PUSH_EDGE(vindex[1], vindex[2], vindex[0], cur + 2, cur + 1);
-                faceorder[norder++] = nfront; PUSH_EDGE(vindex[2], vindex[0], vindex[1], cur + 0, cur + 2);
-                faceorder[norder++] = nfront; PUSH_EDGE(vindex[0], vindex[1], vindex[2], cur + 1, cur + 0);
-                continue;
-            }
-            int fe;
-            if (new_edge != -1) { fe = new_edge; new_edge = -1; }
-            else if (order < norder) fe = faceorder[order++];
-            else if (ndelayed) fe = delayed[--ndelayed];
-            else CFAIL(UVOL_ERR_CORRUPT);
-            const FrontEdge e = front[fe];
-            if (e.deleted) continue;
-            if (cler >= nclers) CFAIL(UVOL_ERR_TRUNCATED);
-            const int c = clers[cler++];
-            if (c == CL_BOUNDARY) continue;
-            const int v0 = e.v0, v1 = e.v1;
-            const FrontEdge pe = front[e.prev], ne = front[e.next];
-            new_edge = nfront; int opposite = -1;
-            if (c == CL_VERTEX || c == CL_SPLIT) {
-                if (c == CL_SPLIT) { if (bits.pos + splitbits > maxbits) CFAIL(UVOL_ERR_TRUNCATED); opposite = (int)bits_read(bits, splitbits); }
-                else { if (vertex_count >= nvert) CFAIL(UVOL_ERR_CORRUPT); pred[vertex_count] = make_int4(v1, v0, e.v2, 0); opposite = vertex_count++; }
-                if (opposite >= nvert) CFAIL(UVOL_ERR_CORRUPT);
-                front[e.prev].next = new_edge; front[e.next].prev = new_edge + 1;
-                PUSH_EDGE(v0, opposite, v1, e.prev, new_edge + 1);
-                if (norder >= order_cap) CFAIL(UVOL_ERR_CORRUPT);
-                faceorder[norder++] = nfront;
-                PUSH_EDGE(opposite, v1, v0, new_edge, e.next);
-            } else if (c == CL_LEFT) {
-                front[e.prev].deleted = 1; front[pe.prev].next = new_edge; front[e.next].prev = new_edge; opposite = pe.v0;
-                PUSH_EDGE(opposite, v1, v0, pe.prev, e.next);
-            } else if (c == CL_RIGHT) {
-                front[e.next].deleted = 1; front[ne.next].prev = new_edge; front[e.prev].next = new_edge; opposite = ne.v1;
-                PUSH_EDGE(v0, opposite, v1, e.prev, ne.next);
-            } else if (c == CL_DELAY) {
-                if (ndelayed >= order_cap) CFAIL(UVOL_ERR_CORRUPT);
-                delayed[ndelayed++] = fe; new_edge = -1; continue;
-            } else if (c == CL_END) {
-                front[e.prev].deleted = 1; front[e.next].deleted = 1; front[pe.prev].next = ne.next; front[ne.next].prev = pe.prev; opposite = pe.v0; new_edge = -1;
-            } else CFAIL(UVOL_ERR_CORRUPT);
-            if (start + 3 > end) CFAIL(UVOL_ERR_CORRUPT);
-            faces[start++] = (uint32_t)v1; faces[start++] = (uint32_t)v0; faces[start++] = (uint32_t)opposite;
-        }
-    }
-    if (vertex_count != nvert) st = UVOL_ERR_CORRUPT;
-done:
-    if (st) status[fi] = st;
-#undef CFAIL
-#undef PUSH_EDGE
+    CortoWalkMem m;
+    m.clers = S + f.clers.o_out; m.nclers = f.clers.size;
+    m.bits = CortoBits{(const uint32_t *)(blob + f.file_off + f.ibits.data_off), 0, (uint64_t)f.ibits.nwords * 32};
+    m.group_end = aux + f.groups_off; m.ngroups = f.ngroups;
+    m.front = (CortoEdge *)(S + f.o_front); m.third = (uint32_t *)(S + f.o_third); m.front_cap = 3 * (int)f.nface + 8;
+    m.queue = (int *)(S + f.o_queue); m.delayed = (int *)(S + f.o_delayed); m.order_cap = 3 * (int)f.nface + 8;
+    m.faces = (uint32_t *)(O + f.out_index); m.pred = (int *)(S + f.o_pred); m.nvert = (int)f.nvert; m.nface = (int)f.nface;
+    const int rc = corto_walk(m);
+    if (rc) status[fi] = rc == CORTO_TRUNCATED ? UVOL_ERR_TRUNCATED : UVOL_ERR_CORRUPT;
 }
 
 // Per-value bit widths -> bit offsets -> values (cstream.h:296-362).  grid = (frames, attrs), 256 threads.
@@ -311,10 +271,11 @@ __global__ void __launch_bounds__(256) k_corto_values(const CortoFrame *frames, 
     const CortoFrame &f = frames[fi];
     if ((int)ai >= f.nattr) return;
     const CortoAttr &a = f.attr[ai];
+    // normals always travel as one correlated array of two (normal_attribute.cpp:161-175), colours per component
     const uint32_t *words = (const uint32_t *)(blob + f.file_off + a.bits.data_off);
     int32_t *val = (int32_t *)(S + a.o_val);
-    const int n = (int)f.nvert, N = a.N, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const bool corr = (a.strategy & 2) != 0;
+    const int n = (int)a.count, N = a.vN, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool corr = a.kind == CK_NORMAL ? true : (a.kind == CK_COLOR ? false : (a.strategy & 2) != 0);
     if (tid == 0) carry_s = 0;
     __syncthreads();
     for (int c = 0; c < (corr ? 1 : N); c++) {
@@ -353,36 +314,176 @@ __global__ void __launch_bounds__(256) k_corto_values(const CortoFrame *frames, 
 }
 
 // Prediction reversal (vertex_attribute.h:155-177): values[i] += values[a] + values[b] - values[c] (PARALLEL)
-// or += values[a].  One warp per (frame, attribute), lane k owns component k.
+// or += values[a]; normals with DIFF prediction always use the single parent (normal_attribute.cpp:182-204).  One warp per
+// (frame, attribute), lane k owns component k.  Unsigned arithmetic: colours are decoded modulo 256 (their C++ type is uchar), and
+// sums modulo 2^32 reduce to the same residues.
 __global__ void __launch_bounds__(32 * CW) k_corto_delta(const CortoFrame *frames, const int32_t *status, uint8_t *S, const CJob *jobs, int njobs) {
     const int ji = blockIdx.x * CW + (threadIdx.x >> 5), k = threadIdx.x & 31;
     if (ji >= njobs) return;
     const CJob jb = jobs[ji];
     if (frames[jb.frame].status || status[jb.frame]) return;
     const CortoFrame &f = frames[jb.frame]; const CortoAttr &a = f.attr[jb.what];
-    if (k >= a.N) return;
-    int32_t *val = (int32_t *)(S + a.o_val); const int4 *pred = (const int4 *)(S + f.o_pred);
-    const int n = (int)f.nvert, N = a.N; const bool par = (a.strategy & 1) != 0;
+    if (k >= a.vN) return;
+    uint32_t *val = (uint32_t *)(S + a.o_val); const int4 *pred = (const int4 *)(S + f.o_pred);
+    const int n = (int)f.nvert, N = a.vN; const bool par = a.kind != CK_NORMAL && (a.strategy & 1) != 0;
     int4 p = n > 1 ? pred[1] : make_int4(0, 0, 0, 0);
     for (int i = 1; i < n; i++) {
         const int4 nx = i + 1 < n ? pred[i + 1] : p;       // prefetch the next context
-        int v = val[i * N + k];
+        uint32_t v = val[i * N + k];
         if (par) v += val[p.x * N + k] + val[p.y * N + k] - val[p.z * N + k]; else v += val[p.x * N + k];
         val[i * N + k] = v;
         p = nx;
     }
 }
 
-// Dequantisation: (float)value * q, one rounding (vertex_attribute.h:186-187).  grid = (ceil(max/256), frames, attrs)
+// ---- normal estimation (ESTIMATED / BORDER prediction)
+// corners per vertex.  grid = (ceil(3 * maxF / 256), frames)
+__global__ void __launch_bounds__(256) k_corto_vcount(const CortoFrame *frames, const int32_t *status, uint8_t *S, const uint8_t *O) {
+    const uint32_t fi = blockIdx.y;
+    if (frames[fi].status || status[fi]) return;
+    const CortoFrame &f = frames[fi];
+    if (f.nrm_attr < 0 || f.attr[f.nrm_attr].pred == 0) return;
+    const uint32_t c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= 3 * f.nface) return;
+    const uint32_t v = ((const uint32_t *)(O + f.out_index))[c];
+    if (v < f.nvert) atomicAdd((int *)(S + f.o_voff) + v, 1);
+}
+// In-place exclusive scan of an int array of nvert (+1 total slot) entries.  which: 0 = corner counts, 1 = boundary flags.  grid = frames, 1024 threads
+__global__ void __launch_bounds__(1024) k_corto_scan(const CortoFrame *frames, const int32_t *status, uint8_t *S, int which) {
+    __shared__ int wsum[32]; __shared__ int carry_s;
+    const uint32_t fi = blockIdx.x;
+    if (frames[fi].status || status[fi]) return;
+    const CortoFrame &f = frames[fi];
+    if (f.nrm_attr < 0 || f.attr[f.nrm_attr].pred == 0 || (which == 1 && f.attr[f.nrm_attr].pred != 2)) return;
+    int *a = (int *)(S + (which ? f.o_bflag : f.o_voff));
+    const int V = (int)f.nvert, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < V; base += 4096) {
+        const int i0 = base + tid * 4; int x[4], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { x[k] = (i0 + k < V) ? a[i0 + k] : 0; sum += x[k]; }
+        int inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        int pre = carry_s;
+        for (int k = 0; k < w; k++) pre += wsum[k];
+        int run = pre + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { if (i0 + k < V) a[i0 + k] = run; run += x[k]; }
+        __syncthreads();
+        if (tid == 1023) carry_s = pre + inc;
+        __syncthreads();
+    }
+    if (tid == 0) a[V] = carry_s;
+}
+__global__ void __launch_bounds__(256) k_corto_vfill(const CortoFrame *frames, const int32_t *status, uint8_t *S, const uint8_t *O) {
+    const uint32_t fi = blockIdx.y;
+    if (frames[fi].status || status[fi]) return;
+    const CortoFrame &f = frames[fi];
+    if (f.nrm_attr < 0 || f.attr[f.nrm_attr].pred == 0) return;
+    const uint32_t c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= 3 * f.nface) return;
+    const uint32_t v = ((const uint32_t *)(O + f.out_index))[c];
+    if (v >= f.nvert) return;
+    const int slot = atomicAdd((int *)(S + f.o_vfill) + v, 1);
+    ((uint32_t *)(S + f.o_vlist))[((const int *)(S + f.o_voff))[v] + slot] = c;
+}
+// Per vertex: incident corners sorted by corner id (= face order), face normals of the INTEGER positions summed in that order
+// (estimateNormals, normal_attribute.cpp:40-59: float cross products accumulated face by face), boundary mark = XOR of the other
+// two vertex ids of every incident corner (markBoundary, :24-37).  grid = (ceil(maxV / 128), frames)
+__global__ void __launch_bounds__(128) k_corto_estimate(const CortoFrame *frames, const int32_t *status, uint8_t *S, const uint8_t *O) {
+    const uint32_t fi = blockIdx.y;
+    if (frames[fi].status || status[fi]) return;
+    const CortoFrame &f = frames[fi];
+    if (f.nrm_attr < 0 || f.attr[f.nrm_attr].pred == 0) return;
+    const uint32_t v = blockIdx.x * 128 + threadIdx.x;
+    if (v >= f.nvert) return;
+    const int *off = (const int *)(S + f.o_voff); uint32_t *list = (uint32_t *)(S + f.o_vlist) + off[v]; const int n = off[v + 1] - off[v];
+    for (int i = 1; i < n; i++) { const uint32_t x = list[i]; int j = i - 1; while (j >= 0 && list[j] > x) { list[j + 1] = list[j]; j--; } list[j + 1] = x; }
+    const uint32_t *faces = (const uint32_t *)(O + f.out_index); const int32_t *pos = (const int32_t *)(S + f.attr[f.pos_attr].o_val);
+    float ex = 0.f, ey = 0.f, ez = 0.f; int bmark = 0;
+    for (int i = 0; i < n; i++) {
+        const uint32_t c = list[i], fb = c - c % 3u, k = c - fb;
+        const uint32_t i0 = faces[fb], i1 = faces[fb + 1], i2 = faces[fb + 2];
+        if (i0 >= f.nvert || i1 >= f.nvert || i2 >= f.nvert) continue;
+        const float p0x = (float)pos[3 * i0], p0y = (float)pos[3 * i0 + 1], p0z = (float)pos[3 * i0 + 2];
+        const float ax = __fsub_rn((float)pos[3 * i1], p0x), ay = __fsub_rn((float)pos[3 * i1 + 1], p0y), az = __fsub_rn((float)pos[3 * i1 + 2], p0z);
+        const float bx = __fsub_rn((float)pos[3 * i2], p0x), by = __fsub_rn((float)pos[3 * i2 + 1], p0y), bz = __fsub_rn((float)pos[3 * i2 + 2], p0z);
+        ex = __fadd_rn(ex, __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by)));
+        ey = __fadd_rn(ey, __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz)));
+        ez = __fadd_rn(ez, __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx)));
+        bmark ^= k == 0 ? (int)(i1 ^ i2) : (k == 1 ? (int)(i2 ^ i0) : (int)(i0 ^ i1));
+    }
+    float *est = (float *)(S + f.o_est) + 3 * (size_t)v; est[0] = ex; est[1] = ey; est[2] = ez;
+    ((int *)(S + f.o_bflag))[v] = bmark != 0;
+}
+
+// Octahedral mapping of the reference (normal_attribute.h:75-112), every float operation rounded on its own like the reference build
+__device__ __forceinline__ void corto_to_octa(float x, float y, float z, int unit, int *ox, int *oy) {
+    const float len = __fadd_rn(__fadd_rn(fabsf(x), fabsf(y)), fabsf(z));
+    float px = __fdiv_rn(x, len), py = __fdiv_rn(y, len);
+    if (z < 0.f) { const float qx = __fsub_rn(1.0f, fabsf(py)), qy = __fsub_rn(1.0f, fabsf(px)); px = x < 0.f ? -qx : qx; py = y < 0.f ? -qy : qy; }
+    *ox = (int)__fmul_rn(px, (float)unit); *oy = (int)__fmul_rn(py, (float)unit);
+}
+__device__ __forceinline__ void corto_to_sphere(int vx, int vy, int unit, float *o) {
+    float nx = (float)vx, ny = (float)vy, nz = (float)(unit - abs(vx) - abs(vy));
+    if (nz < 0.f) { nx = (float)((vx > 0 ? 1 : -1) * (unit - abs(vy))); ny = (float)((vy > 0 ? 1 : -1) * (unit - abs(vx))); }
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz));
+    const float len = (float)__dsqrt_rn((double)s);
+    o[0] = __fdiv_rn(nx, len); o[1] = __fdiv_rn(ny, len); o[2] = __fdiv_rn(nz, len);
+}
+
+// Dequantisation of every attribute.  grid = (ceil(maxV / 256), frames, attrs)
+//   position / uv : (float)value * q, one rounding (vertex_attribute.h:186-187)
+//   normal DIFF   : toSphere(value) (normal_attribute.cpp:228-232); ESTIMATED / BORDER : computeNormals (:278-303)
+//   colour        : YCC -> RGB, times the per-channel step, RGBA8 (color_attribute.cpp:69-90, point.h:214)
 __global__ void __launch_bounds__(256) k_corto_dequant(const CortoFrame *frames, const int32_t *status, const uint8_t *S, uint8_t *O) {
     const uint32_t fi = blockIdx.y, ai = blockIdx.z;
     if (frames[fi].status || status[fi]) return;
     const CortoFrame &f = frames[fi];
     if ((int)ai >= f.nattr) return;
     const CortoAttr &a = f.attr[ai];
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= f.nvert * (uint32_t)a.N) return;
-    ((float *)(O + a.out))[i] = __fmul_rn((float)((const int32_t *)(S + a.o_val))[i], a.q);
+    const uint32_t v = blockIdx.x * 256 + threadIdx.x;
+    if (v >= f.nvert) return;
+    const int32_t *val = (const int32_t *)(S + a.o_val);
+    if (a.kind == CK_POSITION || a.kind == CK_UV) {
+        float *o = (float *)(O + a.out) + (size_t)v * a.N;
+        for (int k = 0; k < a.N; k++) o[k] = __fmul_rn((float)val[v * a.N + k], a.q);
+    } else if (a.kind == CK_NORMAL) {
+        float *o = (float *)(O + a.out) + 3 * (size_t)v; const int unit = (int)a.q;
+        if (a.pred == 0) { corto_to_sphere(val[2 * v], val[2 * v + 1], unit, o); return; }
+        const float *e = (const float *)(S + f.o_est) + 3 * (size_t)v; const int *bf = (const int *)(S + f.o_bflag);
+        // BORDER: corrections exist only for boundary vertices, in vertex order (bflag has been scanned: bf[v + 1] - bf[v] is the mark)
+        const bool corrected = a.pred == 1 || bf[v + 1] != bf[v];
+        if (corrected) {
+            const uint32_t ci = a.pred == 1 ? v : (uint32_t)bf[v];
+            int qx, qy; corto_to_octa(e[0], e[1], e[2], unit, &qx, &qy);
+            const int dx = ci < a.count ? val[2 * ci] : 0, dy = ci < a.count ? val[2 * ci + 1] : 0;
+            corto_to_sphere(qx + dx, qy + dy, unit, o);
+        } else {
+            const float s = __fadd_rn(__fadd_rn(__fmul_rn(e[0], e[0]), __fmul_rn(e[1], e[1])), __fmul_rn(e[2], e[2]));
+            const float len = (float)__dsqrt_rn((double)s);
+            o[0] = __fdiv_rn(e[0], len); o[1] = __fdiv_rn(e[1], len); o[2] = __fdiv_rn(e[2], len);
+        }
+    } else {
+        uint32_t c[4] = {0, 0, 0, 255};
+        for (int k = 0; k < a.N; k++) c[k] = (uint32_t)val[v * a.N + k] & 255u;
+        const uint32_t rgb[4] = {(c[2] + c[0]) & 255u, c[0], (c[1] + c[0]) & 255u, c[3]};
+        uint8_t *o = O + a.out + 4 * (size_t)v;
+        for (int k = 0; k < 4; k++) o[k] = (uint8_t)(rgb[k] * a.qc[k]);
+    }
+}
+
+// u32 -> u16 index narrowing (the web player's layout: src/V1/player.ts:292, corto.ts:675-680).  grid = (ceil(3 * maxF / 256), frames)
+__global__ void __launch_bounds__(256) k_corto_index16(const CortoFrame *frames, const int32_t *status, uint8_t *O) {
+    const uint32_t fi = blockIdx.y;
+    if (frames[fi].status || status[fi] || !frames[fi].index16) return;
+    const CortoFrame &f = frames[fi];
+    const uint32_t c = blockIdx.x * 256 + threadIdx.x;
+    if (c < 3 * f.nface) ((uint16_t *)(O + f.out_index16))[c] = (uint16_t)((const uint32_t *)(O + f.out_index))[c];
 }
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -392,8 +493,8 @@ uint64_t take(uint64_t &cur, uint64_t bytes) { uint64_t o = cur; cur = (cur + by
 
 struct CortoBatch { std::vector<CortoFrame> frames; };
 void uvol_corto_batch_free(CortoBatch *b) { delete b; }
-static const char *kCortoStages[] = {"h2d", "tunstall", "faces", "values", "delta", "dequant", "d2h"};
-extern "C" const char *uvol_corto_stage_name(int i) { return (i >= 0 && i < 7) ? kCortoStages[i] : ""; }
+static const char *kCortoStages[] = {"h2d", "tunstall", "faces", "values", "delta", "estimate", "dequant", "d2h"};
+extern "C" const char *uvol_corto_stage_name(int i) { return (i >= 0 && i < 8) ? kCortoStages[i] : ""; }
 
 extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int memory, uvol_corto_mesh *out) {
     if (!ctx || !out || n < 0 || (n > 0 && (!data || !size))) return UVOL_ERR_ARG;
@@ -405,34 +506,47 @@ extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data
     if (!ctx->corto) ctx->corto = new CortoBatch();
     std::vector<CortoFrame> &frames = ctx->corto->frames; frames.assign((size_t)n, CortoFrame());
     std::vector<uint32_t> aux; std::vector<CJob> jobs;
-    uint64_t blob_bytes = 0, s = 0, o = 0; uint32_t maxvals = 1; uint64_t bytes_in = 0;
+    uint64_t blob_bytes = 0, s = 0, z = 0, o = 0; uint32_t maxV = 1, maxF = 1; uint64_t bytes_in = 0; bool any_est = false, any16 = false;
     for (int i = 0; i < n; i++) {
         CortoFrame &f = frames[i]; memset(&f, 0, sizeof f);
         f.file_off = blob_bytes; f.file_len = (uint32_t)size[i]; bytes_in += size[i];
         blob_bytes = align_up(blob_bytes + size[i] + 16, 16);      // 4-byte alignment of the bit streams is preserved (decoder.cpp:42-43)
-        f.status = (data[i] && size[i] < (1ull << 31)) ? corto_parse(data[i], size[i], f, aux) : UVOL_ERR_ARG;
+        f.status = (data[i] && size[i] < (1ull << 31)) ? corto_parse(data[i], size[i], f, aux, ctx->cfg.max_faces_per_frame) : UVOL_ERR_ARG;
         if (f.status) continue;
-        f.clers.o_out = take(s, (uint64_t)f.clers.size + 8);
-        f.o_front = take(s, (3ull * f.nface + 8) * sizeof(FrontEdge)); f.o_order = take(s, (2ull * f.nface + 8) * 4); f.o_delayed = take(s, (2ull * f.nface + 8) * 4);
+        f.clers.o_out = take(s, (uint64_t)f.clers.size + 16);
+        const uint64_t cap = 3ull * f.nface + 8;
+        f.o_front = take(s, cap * sizeof(CortoEdge)); f.o_third = take(s, cap * 4); f.o_queue = take(s, cap * 4); f.o_delayed = take(s, cap * 4);
         f.o_pred = take(s, ((uint64_t)f.nvert + 2) * 16);
         f.out_index = take(o, (uint64_t)f.nface * 12);
+        f.index16 = ctx->cfg.corto_index_u16 && f.nface < 65536;
+        if (f.index16) { f.out_index16 = take(o, (uint64_t)f.nface * 6); any16 = true; }
+        if (f.nvert > maxV) maxV = f.nvert;
+        if (f.nface > maxF) maxF = f.nface;
         for (int a = 0; a < f.nattr; a++) {
             CortoAttr &at = f.attr[a];
             for (int k = 0; k < at.nlogs; k++) at.logs[k].o_out = take(s, (uint64_t)at.logs[k].size + 8);
-            at.o_val = take(s, (uint64_t)f.nvert * at.N * 4); at.out = take(o, (uint64_t)f.nvert * at.N * 4);
-            if (f.nvert * (uint32_t)at.N > maxvals) maxvals = f.nvert * (uint32_t)at.N;
+            at.o_val = take(s, ((uint64_t)f.nvert + 1) * at.vN * 4);
+            at.out = take(o, at.kind == CK_COLOR ? (uint64_t)f.nvert * 4 : (uint64_t)f.nvert * (at.kind == CK_NORMAL ? 3 : at.N) * 4);
+        }
+        if (f.nrm_attr >= 0 && f.attr[f.nrm_attr].pred != 0) {      // zero-initialised: corner counts / fill cursors / boundary flags
+            any_est = true;
+            f.o_voff = take(z, ((uint64_t)f.nvert + 2) * 4); f.o_vfill = take(z, ((uint64_t)f.nvert + 2) * 4); f.o_bflag = take(z, ((uint64_t)f.nvert + 2) * 4);
+            f.o_vlist = take(s, 3ull * f.nface * 4 + 16); f.o_est = take(s, (uint64_t)f.nvert * 12 + 16);
         }
     }
+    // the zero-initialised part follows the uninitialised scratch in one arena
+    const uint64_t zbase = align_up(s, 256);
+    for (int i = 0; i < n; i++) if (!frames[i].status && frames[i].nrm_attr >= 0 && frames[i].attr[frames[i].nrm_attr].pred != 0) { frames[i].o_voff += zbase; frames[i].o_vfill += zbase; frames[i].o_bflag += zbase; }
     aux.push_back(0);
     const int j_tun = 0;
     for (int i = 0; i < n; i++) if (!frames[i].status) { jobs.push_back({(uint32_t)i, 0}); for (int a = 0; a < frames[i].nattr; a++) for (int k = 0; k < frames[i].attr[a].nlogs; k++) jobs.push_back({(uint32_t)i, 1 + 4 * a + k}); }
     const int j_delta = (int)jobs.size();
-    for (int i = 0; i < n; i++) if (!frames[i].status) for (int a = 0; a < frames[i].nattr; a++) jobs.push_back({(uint32_t)i, a});
+    for (int i = 0; i < n; i++) if (!frames[i].status) for (int a = 0; a < frames[i].nattr; a++) if (frames[i].attr[a].kind != CK_NORMAL || frames[i].attr[a].pred == 0) jobs.push_back({(uint32_t)i, a});
     const int j_end = (int)jobs.size();
     const size_t desc_bytes = sizeof(CortoFrame) * (size_t)n, aux_bytes = aux.size() * 4, job_bytes = sizeof(CJob) * (jobs.size() + 1);
     UVOL_CUDA(ctx, ctx->h_cblob.reserve(blob_bytes + 64)); UVOL_CUDA(ctx, ctx->d_cblob.reserve(blob_bytes + 64));
     UVOL_CUDA(ctx, ctx->h_cdesc.reserve(desc_bytes + aux_bytes + job_bytes + 64)); UVOL_CUDA(ctx, ctx->d_cdesc.reserve(desc_bytes + aux_bytes + job_bytes + 64));
-    UVOL_CUDA(ctx, ctx->d_cscratch.reserve(s + 256)); UVOL_CUDA(ctx, ctx->d_out_corto.reserve(o + 256));
+    UVOL_CUDA(ctx, ctx->d_cscratch.reserve(zbase + z + 256)); UVOL_CUDA(ctx, ctx->d_out_corto.reserve(o + 256));
     UVOL_CUDA(ctx, ctx->d_ccounts.reserve(4 * (size_t)n)); UVOL_CUDA(ctx, ctx->h_ccounts.reserve(4 * (size_t)n));
     memset(ctx->h_cblob.p, 0, blob_bytes + 64);
     for (int i = 0; i < n; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_cblob.p + frames[i].file_off, data[i], size[i]);
@@ -445,6 +559,7 @@ extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_cblob.p, ctx->h_cblob.p, blob_bytes + 64, cudaMemcpyHostToDevice, st));
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->d_cdesc.p, hd, desc_bytes + aux_bytes + job_bytes, cudaMemcpyHostToDevice, st));
     UVOL_CUDA(ctx, cudaMemsetAsync(ctx->d_ccounts.p, 0, 4 * (size_t)n, st));
+    if (z) UVOL_CUDA(ctx, cudaMemsetAsync((uint8_t *)ctx->d_cscratch.p + zbase, 0, z, st));
     stamp();
     const CortoFrame *dF = (const CortoFrame *)ctx->d_cdesc.p; const uint32_t *dAux = (const uint32_t *)((const uint8_t *)ctx->d_cdesc.p + desc_bytes);
     const CJob *dJ = (const CJob *)((const uint8_t *)ctx->d_cdesc.p + desc_bytes + aux_bytes);
@@ -459,11 +574,18 @@ extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data
     stamp();
     k_corto_faces<<<nb(n), 32 * CW, 0, st>>>(dF, dSt, dBlob, dAux, dS, dO, n); launches++;
     stamp();
-    k_corto_values<<<dim3(n, 2), 256, 0, st>>>(dF, dSt, dBlob, dS); launches++;
+    k_corto_values<<<dim3(n, CORTO_MAX_ATTRS), 256, 0, st>>>(dF, dSt, dBlob, dS); launches++;
     stamp();
     if (j_end - j_delta > 0) { k_corto_delta<<<nb(j_end - j_delta), 32 * CW, 0, st>>>(dF, dSt, dS, dJ + j_delta, j_end - j_delta); launches++; }
     stamp();
-    k_corto_dequant<<<dim3((maxvals + 255) / 256, n, 2), 256, 0, st>>>(dF, dSt, dS, dO); launches++;
+    if (any_est) {
+        const dim3 gc((3 * maxF + 255) / 256, n);
+        k_corto_vcount<<<gc, 256, 0, st>>>(dF, dSt, dS, dO); k_corto_scan<<<n, 1024, 0, st>>>(dF, dSt, dS, 0); k_corto_vfill<<<gc, 256, 0, st>>>(dF, dSt, dS, dO);
+        k_corto_estimate<<<dim3((maxV + 127) / 128, n), 128, 0, st>>>(dF, dSt, dS, dO); k_corto_scan<<<n, 1024, 0, st>>>(dF, dSt, dS, 1); launches += 5;
+    }
+    stamp();
+    k_corto_dequant<<<dim3((maxV + 255) / 256, n, CORTO_MAX_ATTRS), 256, 0, st>>>(dF, dSt, dS, dO); launches++;
+    if (any16) { k_corto_index16<<<dim3((3 * maxF + 255) / 256, n), 256, 0, st>>>(dF, dSt, dO); launches++; }
     stamp();
     UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_ccounts.p, dSt, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     if (memory == UVOL_MEM_HOST) { UVOL_CUDA(ctx, ctx->h_cout.reserve(o + 256)); UVOL_CUDA(ctx, cudaMemcpyAsync(ctx->h_cout.p, dO, o, cudaMemcpyDeviceToHost, st)); }
@@ -476,10 +598,17 @@ extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data
         m.status = f.status ? f.status : hSt[i];
         if (m.status) continue;
         m.num_vertices = f.nvert; m.num_faces = f.nface; m.index = (uint32_t *)(base + f.out_index); bytes_out += (uint64_t)f.nface * 12;
-        for (int a = 0; a < f.nattr; a++) { float *p = (float *)(base + f.attr[a].out); bytes_out += (uint64_t)f.nvert * f.attr[a].N * 4; if (f.attr[a].kind == 0) m.position = p; else m.uv = p; }
+        if (f.index16) { m.index16 = (uint16_t *)(base + f.out_index16); m.index_type = 1; }
+        for (int a = 0; a < f.nattr; a++) {
+            const CortoAttr &at = f.attr[a]; uint8_t *p = base + at.out;
+            if (at.kind == CK_POSITION) { m.position = (float *)p; bytes_out += (uint64_t)f.nvert * 12; }
+            else if (at.kind == CK_UV) { m.uv = (float *)p; bytes_out += (uint64_t)f.nvert * 8; }
+            else if (at.kind == CK_NORMAL) { m.normal = (float *)p; bytes_out += (uint64_t)f.nvert * 12; }
+            else { m.color = p; bytes_out += (uint64_t)f.nvert * 4; }
+        }
     }
     uvol_stats &sx = ctx->stats;
-    sx.host_parse_ms = t_parsed - t0; sx.total_ms = now_ms() - t0; sx.kernel_launches = launches; sx.bytes_in = bytes_in; sx.bytes_out = bytes_out; sx.scratch_bytes = s;
+    sx.host_parse_ms = t_parsed - t0; sx.total_ms = now_ms() - t0; sx.kernel_launches = launches; sx.bytes_in = bytes_in; sx.bytes_out = bytes_out; sx.scratch_bytes = zbase + z;
     if (ctx->profile) {
         sx.num_stages = (uint32_t)(ev - 1);
         for (int k = 0; k + 1 < ev && k < 24; k++) cudaEventElapsedTime(&sx.stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);
@@ -490,21 +619,24 @@ extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data
 
 // ---- the reference's C ABI (corto_codec.h:41-43): one handle = one frame, decoded on device 0 through a
 // process-wide context.  Errors are negative return values (the reference lets C++ exceptions escape).
-struct Decoder { std::vector<uint8_t> bytes; uint32_t nvert = 0, nface = 0; bool has_uv = false; };
+// Normals are written when the file carries them (Decoder::setNormals(float *), corto_codec.cpp:41-44).  Colours: the reference hands
+// its `Color *` to the FLOAT path of ColorAttr::dequantize, which multiplies the *unconverted bytes of the buffer* by the channel step
+// (color_attribute.cpp:93-106 reads c[k], not the RGB it has just computed) -- an upstream defect whose output is meaningless;
+// this entry point returns what that path evidently intends and what the UINT8 path and the TypeScript decoder compute
+// (src/lib/corto.ts:455-466): RGBA = toRGB(YCC) * step, as floats in [0, 1].
+struct Decoder { std::vector<uint8_t> bytes; uint32_t nvert = 0, nface = 0; };
 static uvol_ctx *g_corto_ctx = nullptr;
 
 extern "C" Decoder *CreateDecoder(int length, unsigned char *data, Vector2 *decoderInfo) {
     if (length <= 0 || !data) return nullptr;
     CortoFrame f; memset(&f, 0, sizeof f); std::vector<uint32_t> aux;
-    if (corto_parse(data, (size_t)length, f, aux) != UVOL_OK && !(f.nvert && f.nface == 0)) return nullptr;
+    if (corto_parse(data, (size_t)length, f, aux, 1ull << 27) != UVOL_OK && !(f.nvert && f.nface == 0)) return nullptr;
     Decoder *d = new Decoder(); d->bytes.assign(data, data + length); d->nvert = f.nvert; d->nface = f.nface;
-    for (int a = 0; a < f.nattr; a++) if (f.attr[a].kind == 1) d->has_uv = true;
     if (decoderInfo) { decoderInfo[0].x = (float)f.nface; decoderInfo[0].y = (float)f.nvert; }
     return d;
 }
 extern "C" void DestroyDecoder(Decoder *decoder) { delete decoder; }
 extern "C" int DecodeMesh(Decoder *decoder, Vector3 *vertices, int *indices, Vector3 *normals, Color *colors, Vector2 *texcoord) {
-    (void)normals; (void)colors;
     if (!decoder) return UVOL_ERR_ARG;
     if (decoder->nface == 0) return -1;                         // point clouds (corto_codec.cpp:27-30)
     if (!g_corto_ctx && uvol_create(0, &g_corto_ctx) != UVOL_OK) return UVOL_ERR_CUDA;
@@ -515,5 +647,7 @@ extern "C" int DecodeMesh(Decoder *decoder, Vector3 *vertices, int *indices, Vec
     if (indices) memcpy(indices, m.index, (size_t)m.num_faces * 12);
     if (vertices && m.position) memcpy(vertices, m.position, (size_t)m.num_vertices * 12);
     if (texcoord && m.uv) memcpy(texcoord, m.uv, (size_t)m.num_vertices * 8);
+    if (normals && m.normal) memcpy(normals, m.normal, (size_t)m.num_vertices * 12);
+    if (colors && m.color) for (uint32_t i = 0; i < m.num_vertices; i++) { colors[i].r = m.color[4 * i] / 255.0f; colors[i].g = m.color[4 * i + 1] / 255.0f; colors[i].b = m.color[4 * i + 2] / 255.0f; colors[i].a = m.color[4 * i + 3] / 255.0f; }
     return (int)m.num_faces;
 }

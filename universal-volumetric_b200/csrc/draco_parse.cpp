@@ -28,6 +28,26 @@ bool read_rabs(Rd &r, RabsStream &s) {
     return true;
 }
 
+// Metadata section (header flag 0x8000, draco::MetadataEncoder::EncodeGeometryMetadata): walked past, never used -- the reference's
+// loader reads no metadata (src/lib/DRACOLoader.js:470-554).  metadata = varint entries {u8 name length, name, varint value size, value},
+// varint sub-metadata count {u8 name length, name, metadata}.
+bool skip_metadata(Rd &r, int depth) {
+    if (depth > 32) return false;
+    const uint64_t ne = r.varint();
+    if (r.err || ne > r.n) return false;
+    for (uint64_t i = 0; i < ne; i++) {
+        const uint8_t nl = r.u8(); if (r.err || nl > r.n - r.p) return false; r.p += nl;
+        const uint64_t vs = r.varint(); if (r.err || vs > r.n - r.p) return false; r.p += vs;
+    }
+    const uint64_t ns = r.varint();
+    if (r.err || ns > r.n) return false;
+    for (uint64_t i = 0; i < ns; i++) {
+        const uint8_t nl = r.u8(); if (r.err || nl > r.n - r.p) return false; r.p += nl;
+        if (!skip_metadata(r, depth + 1)) return false;
+    }
+    return true;
+}
+
 // DecodeSymbols header: scheme, [max_bit_length], probability table, byte run.  Only RAW can be
 // located without decoding it; TAGGED needs the decoded tags to find its end -> unsupported here.
 int read_symbols(Rd &r, RansStream &s, std::vector<uint32_t> &aux) {
@@ -63,7 +83,14 @@ int uvol_draco_parse(const uint8_t *data, size_t len, DracoFrame &f, std::vector
     if (len < 11 || memcmp(data, "DRACO", 5)) return UVOL_ERR_CORRUPT;
     r.p = 5;
     int maj = r.u8(), mino = r.u8(), etype = r.u8(), meth = r.u8(); int flags = r.u16();
-    if (maj != 2 || mino != 2 || etype != 1 || meth != 1 || (flags & 0x8000)) return UVOL_ERR_UNSUPPORTED;
+    if (maj != 2 || mino != 2 || etype != 1 || meth != 1) return UVOL_ERR_UNSUPPORTED;
+    if (flags & 0x8000) {          // geometry metadata: {varint attribute count, each: varint unique id + metadata}, then the geometry's own
+        const uint64_t na = r.varint();
+        if (r.err || na > len) return UVOL_ERR_CORRUPT;
+        for (uint64_t i = 0; i < na; i++) { (void)r.varint(); if (!skip_metadata(r, 0)) return UVOL_ERR_CORRUPT; }
+        if (!skip_metadata(r, 0)) return UVOL_ERR_CORRUPT;
+        // every offset recorded below is relative to the start of the file: nothing else changes
+    }
     f.trav = r.u8(); f.nv_enc = (uint32_t)r.varint(); f.nf = (uint32_t)r.varint(); f.nad = r.u8();
     f.nsym = (uint32_t)r.varint(); f.nsplit = (uint32_t)r.varint();
     if (r.err) return UVOL_ERR_TRUNCATED;

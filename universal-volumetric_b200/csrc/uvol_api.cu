@@ -52,6 +52,8 @@ extern "C" int uvol_create_with_config(int device, const uvol_config *cfg, uvol_
     if (cudaStreamCreateWithPriority(&c->s0, cudaStreamNonBlocking, prio_hi) != cudaSuccess || cudaStreamCreateWithPriority(&c->s1, cudaStreamNonBlocking, prio_mid) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     if (cudaStreamCreateWithPriority(&c->s2, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     if (cudaStreamCreateWithPriority(&c->s3, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    if (cudaStreamCreateWithPriority(&c->s4, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
+    for (auto &e : c->tex_chunk_ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     for (auto &e : c->aux_ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
     for (auto &e : c->tex_ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return UVOL_ERR_CUDA; }
@@ -80,6 +82,8 @@ extern "C" void uvol_destroy(uvol_ctx *c) {
     for (auto &e : c->sync_ev) if (e) cudaEventDestroy(e);
     if (c->s2) cudaStreamDestroy(c->s2);
     if (c->s3) cudaStreamDestroy(c->s3);
+    if (c->s4) cudaStreamDestroy(c->s4);
+    for (auto &e : c->tex_chunk_ev) if (e) cudaEventDestroy(e);
     if (c->s0) cudaStreamDestroy(c->s0);
     if (c->s1) cudaStreamDestroy(c->s1);
     delete c;
@@ -124,6 +128,15 @@ extern "C" int uvol_span_ms(uvol_ctx *const *ctxs, int n, float *ms) {
     }
     if (!any) return UVOL_ERR_ARG;
     *ms = hi - lo;
+    return UVOL_OK;
+}
+
+extern "C" int uvol_release(uvol_ctx *c) {
+    if (!c) return UVOL_ERR_ARG;
+    UVOL_CUDA(c, cudaSetDevice(c->device));
+    UVOL_CUDA(c, cudaDeviceSynchronize());
+    c->d_out_geo.release(); c->d_out_tex.release(); c->d_out_corto.release();
+    c->h_out.release(); c->h_tout.release(); c->h_cout.release();
     return UVOL_OK;
 }
 

@@ -50,6 +50,8 @@ struct uvol_ctx {
     cudaEvent_t ev[32] = {}, aux_ev[8] = {}, tex_ev[8] = {}, sync_ev[12] = {};
     cudaStream_t s2 = nullptr;
     cudaStream_t s3 = nullptr;                    // early result copies (index buffers) next to the geometry kernels
+    cudaStream_t s4 = nullptr;                    // texture result copies of the pipelined fresh path (chunk k's copy runs next to chunk k+1's upload and kernels)
+    cudaEvent_t tex_chunk_ev[16] = {};
     std::string err; std::mutex err_mu;           // the texture side of uvol_decode_v2_batch runs on a helper thread: error text is set under err_mu
     void set_error(const char *msg) { std::lock_guard<std::mutex> g(err_mu); err = msg; }
     uvol_config cfg = {};                          // defaults + environment overrides (uvol_config_default), or the caller's (uvol_create_with_config)

@@ -233,7 +233,9 @@ class V2Player:
 class CortoDecoder:
     """Batch mirror of the V1 worker loop `new CortoDecoder(slice).decode()` (src/V1/worker.ts:48-68, src/lib/corto.ts:73-140).
     `decode_batch` takes the per-frame .crt slices of a .drcs and returns, per frame, the bufferGeometry of
-    src/V1/player.ts:289-297: {"index", "position", "uv"}."""
+    src/V1/player.ts:289-297: {"index", "position", "uv"} -- plus "normal" (f32[V,3]) / "color" (u8[V,4]) when the file carries them
+    (src/lib/corto.ts:439-671).  With Context(corto_index_u16=True) the index is a uint16 array whenever nface < 65536, the
+    reference's JS layout (corto.ts:675-680, player.ts:292)."""
 
     def __init__(self, ctx=None, device=0):
         self.ctx = ctx or Context(device)
@@ -255,6 +257,9 @@ class CortoDecoder:
                 res.append({"status": int(m.status)})
                 continue
             V, F = m.num_vertices, m.num_faces
-            res.append({"status": 0, "index": np.ctypeslib.as_array(m.index, (F * 3,)).copy(), "position": np.ctypeslib.as_array(m.position, (V, 3)).copy(),
-                        "uv": np.ctypeslib.as_array(m.uv, (V, 2)).copy() if m.uv else None})
+            index = np.ctypeslib.as_array(m.index16, (F * 3,)).copy() if m.index_type == 1 and m.index16 else np.ctypeslib.as_array(m.index, (F * 3,)).copy()
+            res.append({"status": 0, "index": index, "position": np.ctypeslib.as_array(m.position, (V, 3)).copy(),
+                        "uv": np.ctypeslib.as_array(m.uv, (V, 2)).copy() if m.uv else None,
+                        "normal": np.ctypeslib.as_array(m.normal, (V, 3)).copy() if m.normal else None,
+                        "color": np.ctypeslib.as_array(m.color, (V, 4)).copy() if m.color else None})
         return res
