@@ -15,6 +15,7 @@
 #include "uvol_ctx.h"
 #include "basis_core.h"
 #include "bc7_core.h"
+#include "tma_bulk.h"
 
 int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
 extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
@@ -128,10 +129,13 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_etc1s_resolve(const Ktx2F
 // shared memory a random lookup is a few bank-conflict cycles.  A CTA decodes ETC1S_CHUNKS x 256 blocks per staged codebook.
 #define ETC1S_CHUNKS 16
 struct BlockLayerConst { const uint32_t *eps, *sels; const uint16_t *ep_idx, *sel_idx, *aep_idx, *asel_idx; uint8_t *dst; uint32_t nblk, bx, W, H, has_alpha, skip, ec, sc; };
+// The staging itself is two bulk asynchronous copies (cp.async.bulk into shared memory, completion counted on an mbarrier) issued by
+// one thread -- the TMA unit moves the codebooks while the CTA's threads already fetch their blocks' indices; use_tma = 0 keeps the
+// copy loop by all threads for the A/B measurement (UVOL_NO_TMA=1).
 template <bool SMEM_CB>
 __global__ void __launch_bounds__(256) k_etc1s_blocks(const Ktx2File *files, const TexState *state, const Ktx2Slice *slices, const uint32_t *layer_list,
-                                                      const uint8_t *S, uint8_t *O) {
-    __shared__ BlockLayerConst K;
+                                                      const uint8_t *S, uint8_t *O, int use_tma) {
+    __shared__ BlockLayerConst K; __shared__ __align__(8) uint64_t bar;
     if (threadIdx.x == 0) {
         const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
         const Ktx2File &f = files[fi];
@@ -148,14 +152,21 @@ __global__ void __launch_bounds__(256) k_etc1s_blocks(const Ktx2File *files, con
     }
     __syncthreads();
     if (K.skip) return;
-    extern __shared__ uint32_t cb_smem[];
+    extern __shared__ __align__(16) uint32_t cb_smem[];
     const uint32_t *eps = K.eps, *sels = K.sels;
     if (SMEM_CB) {
         if (blockIdx.x * (ETC1S_CHUNKS * 256u) >= K.nblk) return;
-        for (uint32_t i = threadIdx.x; i < K.ec; i += 256) cb_smem[i] = K.eps[i];
-        for (uint32_t i = threadIdx.x; i < K.sc; i += 256) cb_smem[K.ec + i] = K.sels[i];
-        __syncthreads();
-        eps = cb_smem; sels = cb_smem + K.ec;
+        const uint32_t ec4 = (K.ec + 3u) & ~3u, sc4 = (K.sc + 3u) & ~3u;          // 16-byte granules; the arena pads every array to 128 bytes, so the tail is readable
+        if (use_tma) {
+            if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_expect_tx(&bar, (ec4 + sc4) * 4u); bulk_g2s(cb_smem, K.eps, ec4 * 4u, &bar); bulk_g2s(cb_smem + ec4, K.sels, sc4 * 4u, &bar); }
+            __syncthreads();
+            mbar_wait(&bar, 0);
+        } else {
+            for (uint32_t i = threadIdx.x; i < K.ec; i += 256) cb_smem[i] = K.eps[i];
+            for (uint32_t i = threadIdx.x; i < K.sc; i += 256) cb_smem[ec4 + i] = K.sels[i];
+            __syncthreads();
+        }
+        eps = cb_smem; sels = cb_smem + ec4;
     }
     const uint32_t nblk = K.nblk, bxn = K.bx, W = K.W, H = K.H;
     const bool whole = (W & 3) == 0;
@@ -356,11 +367,12 @@ static int ktx2_launch_range(uvol_ctx *ctx, int i0, int i1, cudaStream_t st, boo
     } else if (nll && B.target == UVOL_TEX_ETC1) { k_etc1s_blocks_etc1<<<dim3((B.max_blocks + 255) / 256, nll), 256, 0, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO); B.launches++; }
     else if (nll) {
         const dim3 grid((B.max_blocks + 256 * ETC1S_CHUNKS - 1) / (256 * ETC1S_CHUNKS), nll);
-        const size_t cb = (size_t)B.max_codebook * 4;
+        const size_t cb = (size_t)B.max_codebook * 4 + 32;                    // (+ the 16-byte rounding of both codebooks)
+        static const int use_tma = getenv("UVOL_NO_TMA") ? 0 : 1;
         if (cb <= 160 * 1024) {
             if (cb > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_etc1s_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
-            k_etc1s_blocks<true><<<grid, 256, cb, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO);
-        } else k_etc1s_blocks<false><<<grid, 256, 0, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO);
+            k_etc1s_blocks<true><<<grid, 256, cb, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO, use_tma);
+        } else k_etc1s_blocks<false><<<grid, 256, 0, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO, 0);
         B.launches++;
     }
     if (nul) { UVOL_CUDA(ctx, (cudaError_t)uvol_uastc_launch(ctx->device, dF, (int32_t *)dSt, dBlob, dO, dUL + ul0, (int)nul, B.max_blocks, B.target, st)); B.launches++; }

@@ -26,7 +26,7 @@
 // q7p[p] / q6p[p] = nearest 6- / 5-bit code whose value with the p-bit p appended (7 / 6 bits in all) is nearest, bit 7 of the p = 0
 // row = the parity of the unconstrained nearest code (the vote for the shared p-bit).  7 bits + p is the value itself.
 struct Bc7Shared { uint32_t info[60]; uint32_t pat3[20]; uint8_t wmap[3][6][32]; uint8_t solid5[256][2]; uint8_t q5[256], q7[256], q7p[2][256], q6p[2][256]; };
-static_assert(sizeof(Bc7Shared) % 4 == 0, "copied word by word");
+static_assert(sizeof(Bc7Shared) % 16 == 0, "staged with one bulk copy (16-byte granules)");
 static inline uint32_t bc7_expand_host(uint32_t x, uint32_t bits) { x <<= (8u - bits); return (x | (x >> bits)) & 255u; }
 static inline uint32_t bc7_nearest_host(uint32_t e, uint32_t bits, int parity) {
     uint32_t best = 0, beste = 0xffffu;

@@ -46,9 +46,9 @@ UASTC_HD uint32_t take(Bits &x, uint32_t n) {          // n in 0..31; bits past 
 }
 
 struct UastcShared {
-    uint32_t mode[20]; uint32_t pattern[60]; uint16_t anchor[60]; uint8_t mode_of[128]; uint8_t weight[6 * 32]; uint8_t unquant[8 * 256];
+    uint32_t mode[20]; uint32_t pattern[60]; uint16_t anchor[60]; uint8_t mode_of[128]; uint8_t weight[6 * 32]; uint8_t unquant[8 * 256]; uint8_t pad[8];
 };
-static_assert(sizeof(UastcShared) % 4 == 0, "copied word by word");
+static_assert(sizeof(UastcShared) % 16 == 0, "staged with one bulk copy (16-byte granules)");
 
 // One block -> four pixel rows of packed RGBA.  false: the transcoder rejects the block.
 UASTC_HD bool uastc_block(const UastcShared &T, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t rows[4][4]) {

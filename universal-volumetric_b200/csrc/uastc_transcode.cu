@@ -10,21 +10,30 @@
 // rather than a switch per mode, so blocks of different modes in one warp mostly share instructions.
 // Block format: see oracle/uastc_oracle.c (the CPU restatement this kernel is checked against bit for bit).
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 #include "uvol_ctx.h"
 #include "uastc_core.h"
 #include "bc7_core.h"
+#include "tma_bulk.h"
 
 namespace {
 
-__device__ uint32_t g_tables[sizeof(UastcShared) / 4];      // image of UastcShared, filled once per device by the launcher
+__device__ __align__(16) uint32_t g_tables[sizeof(UastcShared) / 4];      // image of UastcShared, filled once per device by the launcher
 
 // grid = (ceil(max blocks / (256 * UASTC_CHUNKS)), UASTC layer list): a CTA loads the tables once and decodes UASTC_CHUNKS x 256 blocks
 #define UASTC_CHUNKS 8
+// TMA = true: the 2.8 KB table image is staged by ONE bulk asynchronous copy (cp.async.bulk, completion on an mbarrier) issued by
+// thread 0 while the other threads already fetch the per-layer constants; TMA = false: the word-by-word copy by all threads (kept
+// for the A/B measurement, UVOL_NO_TMA=1).
+template <bool TMA>
 __global__ void __launch_bounds__(256) k_uastc_blocks(const Ktx2File *files, int32_t *status2, const uint8_t *blob, uint8_t *O, const uint32_t *layer_list) {
-    __shared__ UastcShared T;
-    for (uint32_t i = threadIdx.x; i < sizeof(UastcShared) / 4; i += 256) ((uint32_t *)&T)[i] = g_tables[i];
-    __syncthreads();
+    __shared__ __align__(16) UastcShared T; __shared__ __align__(8) uint64_t bar;
+    if (TMA) {
+        if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_expect_tx(&bar, (uint32_t)sizeof(UastcShared)); bulk_g2s(&T, g_tables, (uint32_t)sizeof(UastcShared), &bar); }
+    } else {
+        for (uint32_t i = threadIdx.x; i < sizeof(UastcShared) / 4; i += 256) ((uint32_t *)&T)[i] = g_tables[i];
+    }
     __shared__ struct { const uint8_t *src0; uint8_t *dst; uint32_t nblk, W, H, bxn, fi, skip; } K;      // per-layer constants, fetched once per CTA
     if (threadIdx.x == 0) {
         const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
@@ -35,6 +44,7 @@ __global__ void __launch_bounds__(256) k_uastc_blocks(const Ktx2File *files, int
         K.dst = O + f.o_rgba + (size_t)L * f.width * f.height * 4;
     }
     __syncthreads();
+    if (TMA) mbar_wait(&bar, 0);
     if (K.skip) return;
     const uint32_t nblk = K.nblk, W = K.W, H = K.H, bxn = K.bxn, fi = K.fi;
     const uint8_t *src0 = K.src0; uint8_t *dst = K.dst;
@@ -63,11 +73,13 @@ __global__ void __launch_bounds__(256) k_uastc_blocks(const Ktx2File *files, int
 
 // UASTC -> BC7 (UVOL_TEX_BC7): same traversal of the blocks, 16 bytes out per block in block raster order (a warp stores 512
 // contiguous bytes); per-block logic in bc7_core.h.
-__device__ uint32_t g_bc7_tables[sizeof(Bc7Shared) / 4];
+__device__ __align__(16) uint32_t g_bc7_tables[sizeof(Bc7Shared) / 4];
 __global__ void __launch_bounds__(256) k_uastc_blocks_bc7(const Ktx2File *files, int32_t *status2, const uint8_t *blob, uint8_t *O, const uint32_t *layer_list) {
-    __shared__ UastcShared T; __shared__ Bc7Shared B7;
-    for (uint32_t i = threadIdx.x; i < sizeof(UastcShared) / 4; i += 256) ((uint32_t *)&T)[i] = g_tables[i];
-    for (uint32_t i = threadIdx.x; i < sizeof(Bc7Shared) / 4; i += 256) ((uint32_t *)&B7)[i] = g_bc7_tables[i];
+    __shared__ __align__(16) UastcShared T; __shared__ __align__(16) Bc7Shared B7; __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {          // both table images by bulk asynchronous copies, one barrier
+        mbar_init(&bar, 1); mbar_expect_tx(&bar, (uint32_t)(sizeof(UastcShared) + sizeof(Bc7Shared)));
+        bulk_g2s(&T, g_tables, (uint32_t)sizeof(UastcShared), &bar); bulk_g2s(&B7, g_bc7_tables, (uint32_t)sizeof(Bc7Shared), &bar);
+    }
     __shared__ struct { const uint8_t *src0; uint8_t *dst; uint32_t nblk, fi, skip; } K;
     if (threadIdx.x == 0) {
         const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
@@ -77,6 +89,7 @@ __global__ void __launch_bounds__(256) k_uastc_blocks_bc7(const Ktx2File *files,
         K.dst = O + f.o_rgba + (size_t)L * K.nblk * 16;
     }
     __syncthreads();
+    mbar_wait(&bar, 0);
     if (K.skip) return;
     const uint32_t nblk = K.nblk, fi = K.fi;
     const uint8_t *src0 = K.src0; uint8_t *dst = K.dst;
@@ -98,7 +111,7 @@ __global__ void __launch_bounds__(256) k_uastc_blocks_bc7(const Ktx2File *files,
 bool g_tables_ready[16] = {};
 }  // namespace
 
-__device__ uint32_t g_bc7_tables_etc1s[sizeof(Bc7Shared) / 4];      // second image for the ETC1S kernel in basis_transcode.cu (separate translation unit)
+__device__ __align__(16) uint32_t g_bc7_tables_etc1s[sizeof(Bc7Shared) / 4];      // second image for the ETC1S kernel in basis_transcode.cu (separate translation unit)
 const uint32_t *uvol_bc7_tables_device() { uint32_t *p = nullptr; cudaGetSymbolAddress((void **)&p, g_bc7_tables_etc1s); return p; }
 
 // status2: the launcher's per-file {status, aux} pairs.  layer list entries: file << 12 | layer.
@@ -122,6 +135,8 @@ int uvol_uastc_launch(int device, const Ktx2File *dF, int32_t *status2, const ui
     const int rc = uvol_texture_tables_ready(device); if (rc) return rc;
     const dim3 grid((max_blocks + 256 * UASTC_CHUNKS - 1) / (256 * UASTC_CHUNKS), (unsigned)nlayers);
     if (target == UVOL_TEX_BC7) { k_uastc_blocks_bc7<<<grid, 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList); return 0; }
-    k_uastc_blocks<<<dim3((max_blocks + 256 * UASTC_CHUNKS - 1) / (256 * UASTC_CHUNKS), (unsigned)nlayers), 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList);
+    static const bool no_tma = getenv("UVOL_NO_TMA") != nullptr;
+    if (no_tma) { k_uastc_blocks<false><<<grid, 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList); return 0; }
+    k_uastc_blocks<true><<<dim3((max_blocks + 256 * UASTC_CHUNKS - 1) / (256 * UASTC_CHUNKS), (unsigned)nlayers), 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList);
     return 0;
 }
