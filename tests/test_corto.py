@@ -93,6 +93,12 @@ def test_connectivity_walk_host_logic():
         seen += np.bincount(cl, minlength=7)[:7]
         out = np.zeros(nf * 3, np.uint32); p4 = np.zeros((nv, 4), np.int32)
         rc = E.corto_emu_walk(cl.ctypes.data, len(cl), words.ctypes.data, len(words), ge.ctypes.data, len(ge), nv, nf, out.ctypes.data, p4.ctypes.data)
+        full = (out.copy(), p4.copy())
+        for ring in (4, 16, 128):      # tiny rings: the same walk with most records served from the global array
+            E.corto_emu_set_ring(ring); out[:] = 0; p4[:] = 0
+            assert E.corto_emu_walk(cl.ctypes.data, len(cl), words.ctypes.data, len(words), ge.ctypes.data, len(ge), nv, nf, out.ctypes.data, p4.ctypes.data) == rc
+            assert np.array_equal(out, full[0]) and np.array_equal(p4, full[1]), ring
+        E.corto_emu_set_ring(1024)
         assert rc == 0 and np.array_equal(out, idx) and np.array_equal(p4[1:, :3].astype(np.uint32), pred[1:])
         assert E.corto_emu_walk(cl.ctypes.data, len(cl) // 2, words.ctypes.data, len(words), ge.ctypes.data, len(ge), nv, nf, out.ctypes.data, p4.ctypes.data) < 0      # truncated symbols: an error, not a crash
     assert (seen > 0).all()                                                          # VERTEX LEFT RIGHT END BOUNDARY DELAY SPLIT all exercised

@@ -83,6 +83,16 @@ static int traverse_spec_emu(const FaceRec *rec, int F, uint8_t *fvis, int *v2d1
     return UVOL_OK;
 }
 
+
+static void emu_rabs_bits(RabsLane &r, uint8_t *o, uint32_t n, bool toggle) {      // eight bits per store, as k_rabs_lanes
+    uint32_t last = 1;
+    for (uint32_t k = 0; k < n; k += 8) {
+        uint8_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int b = 0; b < 8; b++) if (k + b < n) { uint32_t bit = rabs_lane_bit(r, true); if (toggle) { if (!bit) last ^= 1u; bit = last; } w[b] = (uint8_t)bit; }
+        memcpy(o + k, w, 8);
+    }
+}
+
 extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_points, uint32_t *num_faces,
                                 uint32_t **index, float **position, float **normal, float **uv) {
     std::vector<DracoFrame> frames(1); std::vector<uint32_t> aux;
@@ -108,8 +118,8 @@ extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_p
     }
     // stage: seam bits
     for (int i = 0; i < nad; i++) {
-        Rabs r; if (!rabs_init(r, file, f.seams[i])) return UVOL_ERR_CORRUPT;
-        uint8_t *o = S + f.o_seambits[i]; for (int k = 0; k < 3 * F / 2 + 1; k++) o[k] = (uint8_t)rabs_bit(r);
+        RabsLane r; if (!rabs_lane_init(r, file, f.seams[i])) return UVOL_ERR_CORRUPT;
+        emu_rabs_bits(r, S + f.o_seambits[i], (uint32_t)(3 * F / 2 + 1), false);
     }
     // stage: edgebreaker
     EbMem m; m.opp = (int *)(S + f.o_opp); m.c2v = (int *)(S + f.o_c2v); m.lmc = (int *)(S + f.o_lmc); m.val = (int *)(S + f.o_val);
@@ -171,19 +181,18 @@ extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_p
     for (int j = 0; j < f.nattr; j++) {
         const DracoAttr &a = f.attr[j]; if (f.o_corr[j] == UVOL_NONE) continue;
         const RansStream &s = a.sym; const uint32_t n = cnt.entries[a.table + 1];
+        const int positive = a.pred != -2 && (a.xform == 2 || a.xform == 3);
+        if (n * (uint32_t)a.vnc > f.corr_cap[j]) return UVOL_ERR_FRAME_CAPACITY;
         std::vector<uint32_t> cum(s.alphabet + 1, 0); std::vector<uint16_t> bucket(257);
         for (uint32_t k = 0; k < s.alphabet; k++) cum[k + 1] = cum[k] + aux[s.prob_off + k];
         if (cum[s.alphabet] != (1u << s.pb)) return UVOL_ERR_CORRUPT;
         for (uint32_t b = 0; b < 256; b++) bucket[b] = (uint16_t)rans_bucket_symbol(cum.data(), s.alphabet, b << (s.pb - 8));
         RansTables t{cum.data(), bucket.data(), s.alphabet, s.pb};
-        const int positive = a.pred != -2 && (a.xform == 2 || a.xform == 3);
-        if (n * (uint32_t)a.vnc > f.corr_cap[j]) return UVOL_ERR_FRAME_CAPACITY;
         rc = rans_decode_run(file + s.data_off, s.data_len, t, n * a.vnc, positive ? 2 : 1, S + f.o_corr[j]); if (rc) return rc;
         if (a.pred == 5 || a.pred == 6) {
-            Rabs r; if (!rabs_init(r, file, a.aux_bits)) return UVOL_ERR_CORRUPT;
-            uint8_t *o = S + f.o_auxbits[j];
-            if (a.pred == 5) { if ((uint32_t)a.num_orient > n) return UVOL_ERR_CORRUPT; int last = 1; for (int k = 0; k < a.num_orient; k++) { if (!rabs_bit(r)) last = !last; o[k] = (uint8_t)last; } }
-            else for (uint32_t k = 0; k < n; k++) o[k] = (uint8_t)rabs_bit(r);
+            RabsLane r; if (!rabs_lane_init(r, file, a.aux_bits)) return UVOL_ERR_CORRUPT;
+            if (a.pred == 5) { if ((uint32_t)a.num_orient > n) return UVOL_ERR_CORRUPT; emu_rabs_bits(r, S + f.o_auxbits[j], (uint32_t)a.num_orient, true); }
+            else emu_rabs_bits(r, S + f.o_auxbits[j], n, false);
         }
     }
     // prediction reversal: position-like first, then uv / normal

@@ -10,8 +10,12 @@
 //     depth first -- the edge a symbol creates is the next gate -- so after a VERTEX symbol (half of all symbols) nothing is
 //     loaded at all: the new gate and its right neighbour were just built, the left neighbour is the old one; LEFT / RIGHT
 //     need one neighbour of a neighbour, loaded when (and only if) a later symbol asks for it;
-//   * link updates are write-through (a store plus a patch of whichever register copy holds that edge);
-//   * CLERS symbols are taken eight at a time from an aligned 64-bit word.
+//   * the most recent front records are also kept in a small RING (shared memory in the kernel): the walk is depth first, so the
+//     neighbour records it asks for are almost always among the last few hundred created -- a shared-memory read instead of a trip
+//     to L2 for a line this same lane has just written (ncu, before the ring: 35 % of the walk's time was the wait for front[E.prev]);
+//     the array in global memory stays complete (write-through) and serves the old edges the queue brings back;
+//   * link updates patch the global record, the ring copy if there is one, and whichever register copy holds that edge;
+//   * CLERS symbols are taken eight at a time from an aligned 64-bit word, the next word requested while this one is in use.
 #pragma once
 #include <stdint.h>
 
@@ -45,6 +49,7 @@ struct CortoWalkMem {
     CortoBits bits;                                     // split vertices
     const uint32_t *group_end; uint32_t ngroups;        // end face of every group
     CortoEdge *front; uint32_t *third; int front_cap;   // front records; third vertex of the edge's face, or CORTO_DELETED
+    CortoEdge *ring; int ring_size;                     // copies of the last ring_size front records (record i at i & (ring_size - 1)); power of two
     int *queue, *delayed; int order_cap;                // edges left behind by VERTEX symbols (first in, first out) / the DELAY stack
     uint32_t *faces;                                    // out: 3 * nface vertex ids
     int *pred;                                          // out: {a, b, c, 0} per vertex -- the parallelogram context of deltaDecode
@@ -56,12 +61,19 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
     CortoBits bits = m.bits;
     CortoEdge *front = m.front; uint32_t *third = m.third;
     int vertex_count = 0; uint32_t cler = 0, start = 0;
-    unsigned long long cw = 0;
+    CortoEdge *ring = m.ring; const int rsize = m.ring_size, rmask = m.ring_size - 1;
+    unsigned long long cw = 0, cwn = m.nclers ? *(const unsigned long long *)m.clers : 0ull;
 #define CW_FAIL(code) return (code)
-#define CW_SYMBOL(c) do { if (cler >= m.nclers) CW_FAIL(CORTO_TRUNCATED); if ((cler & 7u) == 0u) cw = *(const unsigned long long *)(m.clers + cler); \
+#define CW_SYMBOL(c) do { if (cler >= m.nclers) CW_FAIL(CORTO_TRUNCATED); \
+                          if ((cler & 7u) == 0u) { cw = cwn; if (cler + 8u < m.nclers) cwn = *(const unsigned long long *)(m.clers + cler + 8u); } \
                           (c) = (int)((cw >> (8u * (cler & 7u))) & 255u); cler++; } while (0)
-#define CW_SET_NEXT(x, y) do { const int x_ = (x); front[x_].next = (y); if (x_ == pi) P.next = (y); if (x_ == ni) N.next = (y); } while (0)
-#define CW_SET_PREV(x, y) do { const int x_ = (x); front[x_].prev = (y); if (x_ == pi) P.prev = (y); if (x_ == ni) N.prev = (y); } while (0)
+// record i lives in the ring as long as fewer than ring_size records were created after it (nfront counts the records created,
+// including the ones whose slots are about to be written)
+#define CW_IN_RING(i) ((i) >= nfront - rsize)
+#define CW_LOAD(dst, i) do { const int i_ = (i); if (CW_IN_RING(i_)) (dst) = ring[i_ & rmask]; else (dst) = front[i_]; } while (0)
+#define CW_NEW(i, e) do { const int i_ = (i); ring[i_ & rmask] = (e); front[i_] = (e); } while (0)
+#define CW_SET_NEXT(x, y) do { const int x_ = (x); front[x_].next = (y); if (CW_IN_RING(x_)) ring[x_ & rmask].next = (y); if (x_ == pi) P.next = (y); if (x_ == ni) N.next = (y); } while (0)
+#define CW_SET_PREV(x, y) do { const int x_ = (x); front[x_].prev = (y); if (CW_IN_RING(x_)) ring[x_ & rmask].prev = (y); if (x_ == pi) P.prev = (y); if (x_ == ni) N.prev = (y); } while (0)
 #define CW_FACE(a, b, c) do { if (start + 3 > end) CW_FAIL(CORTO_CORRUPT); m.faces[start] = (uint32_t)(a); m.faces[start + 1] = (uint32_t)(b); m.faces[start + 2] = (uint32_t)(c); start += 3; } while (0)
     for (uint32_t gi = 0; gi < m.ngroups; gi++) {
         const uint32_t end = m.group_end[gi] * 3u;
@@ -90,16 +102,16 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
                     CW_FACE(v[0], v[1], v[2]);
                     const int cur = nfront;
                     if (nfront + 3 > m.front_cap || norder + 3 > m.order_cap) CW_FAIL(CORTO_CORRUPT);
-                    front[cur] = CortoEdge{v[1], v[2], cur + 2, cur + 1}; third[cur] = (uint32_t)v[0];
-                    front[cur + 1] = CortoEdge{v[2], v[0], cur, cur + 2}; third[cur + 1] = (uint32_t)v[1];
-                    front[cur + 2] = CortoEdge{v[0], v[1], cur + 1, cur}; third[cur + 2] = (uint32_t)v[2];
-                    m.queue[norder++] = cur; m.queue[norder++] = cur + 1; m.queue[norder++] = cur + 2;
                     nfront += 3;
+                    { const CortoEdge e0 = {v[1], v[2], cur + 2, cur + 1}, e1 = {v[2], v[0], cur, cur + 2}, e2 = {v[0], v[1], cur + 1, cur};
+                      CW_NEW(cur, e0); CW_NEW(cur + 1, e1); CW_NEW(cur + 2, e2); }
+                    third[cur] = (uint32_t)v[0]; third[cur + 1] = (uint32_t)v[1]; third[cur + 2] = (uint32_t)v[2];
+                    m.queue[norder++] = cur; m.queue[norder++] = cur + 1; m.queue[norder++] = cur + 2;
                     continue;
                 }
                 gv2 = third[g];
                 if (gv2 & CORTO_DELETED) { g = -1; continue; }
-                E = front[g]; pi = ni = -1;
+                CW_LOAD(E, g); pi = ni = -1;
             }
             int c; CW_SYMBOL(c);
             if (c == CL_VERTEX || c == CL_SPLIT) {
@@ -114,7 +126,7 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
                 const int A = nfront, B = nfront + 1; nfront += 2;
                 CW_SET_NEXT(E.prev, A); CW_SET_PREV(E.next, B);
                 const CortoEdge ea = {E.v0, opp, E.prev, B}, eb = {opp, E.v1, A, E.next};
-                front[A] = ea; third[A] = (uint32_t)E.v1; front[B] = eb; third[B] = (uint32_t)E.v0;
+                CW_NEW(A, ea); third[A] = (uint32_t)E.v1; CW_NEW(B, eb); third[B] = (uint32_t)E.v0;
                 m.queue[norder++] = B;
                 CW_FACE(E.v1, E.v0, opp);
                 // the left edge of the new face is the next gate: its left neighbour is the old one (kept if it was held), its right
@@ -122,35 +134,36 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
                 if (pi != E.prev) pi = -1;
                 gv2 = (uint32_t)E.v1; g = A; N = eb; ni = B; E = ea;
             } else if (c == CL_LEFT) {
-                if (pi != E.prev) { P = front[E.prev]; pi = E.prev; }
+                if (pi != E.prev) { CW_LOAD(P, E.prev); pi = E.prev; }
                 third[E.prev] = CORTO_DELETED;
                 if (nfront + 1 > m.front_cap) CW_FAIL(CORTO_CORRUPT);
                 const int X = nfront++, opp = P.v0, pp = P.prev;
                 CW_SET_NEXT(pp, X); CW_SET_PREV(E.next, X);
                 const CortoEdge ex = {opp, E.v1, pp, E.next};
-                front[X] = ex; third[X] = (uint32_t)E.v0;
+                CW_NEW(X, ex); third[X] = (uint32_t)E.v0;
                 CW_FACE(E.v1, E.v0, opp);
                 if (ni != E.next) ni = -1;
                 if (pp == ni) { P = N; pi = ni; } else pi = -1;
                 gv2 = (uint32_t)E.v0; g = X; E = ex;
             } else if (c == CL_RIGHT) {
-                if (ni != E.next) { N = front[E.next]; ni = E.next; }
+                if (ni != E.next) { CW_LOAD(N, E.next); ni = E.next; }
                 third[E.next] = CORTO_DELETED;
                 if (nfront + 1 > m.front_cap) CW_FAIL(CORTO_CORRUPT);
                 const int X = nfront++, opp = N.v1, nn = N.next;
                 CW_SET_PREV(nn, X); CW_SET_NEXT(E.prev, X);
                 const CortoEdge ex = {E.v0, opp, E.prev, nn};
-                front[X] = ex; third[X] = (uint32_t)E.v1;
+                CW_NEW(X, ex); third[X] = (uint32_t)E.v1;
                 CW_FACE(E.v1, E.v0, opp);
                 if (pi != E.prev) pi = -1;
                 if (nn == pi) { N = P; ni = pi; } else ni = -1;
                 gv2 = (uint32_t)E.v1; g = X; E = ex;
             } else if (c == CL_END) {
-                if (pi != E.prev) { P = front[E.prev]; pi = E.prev; }
-                if (ni != E.next) { N = front[E.next]; ni = E.next; }
+                if (pi != E.prev) { CW_LOAD(P, E.prev); pi = E.prev; }
+                if (ni != E.next) { CW_LOAD(N, E.next); ni = E.next; }
                 third[E.prev] = CORTO_DELETED; third[E.next] = CORTO_DELETED;
                 const int pp = P.prev, nn = N.next, opp = P.v0;
-                front[pp].next = nn; front[nn].prev = pp;
+                pi = ni = -1;
+                CW_SET_NEXT(pp, nn); CW_SET_PREV(nn, pp);
                 CW_FACE(E.v1, E.v0, opp);
                 g = -1;
             } else if (c == CL_BOUNDARY) g = -1;
@@ -160,6 +173,9 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
     }
 #undef CW_FAIL
 #undef CW_SYMBOL
+#undef CW_IN_RING
+#undef CW_LOAD
+#undef CW_NEW
 #undef CW_SET_NEXT
 #undef CW_SET_PREV
 #undef CW_FACE

@@ -246,9 +246,12 @@ __global__ void __launch_bounds__(32 * CW) k_tunstall(const CortoFrame *frames, 
 __device__ __forceinline__ int ilog2_u(uint32_t p) { int k = 0; while (p >>= 1) ++k; return k; }
 
 // Connectivity: the front-growing walk (corto_core.h), one warp per frame, lane 0 walks (the batch supplies the parallelism).
-__global__ void __launch_bounds__(32 * CW) k_corto_faces(const CortoFrame *frames, int32_t *status, const uint8_t *blob, const uint32_t *aux, uint8_t *S, uint8_t *O, int nframes) {
-    const int fi = blockIdx.x * CW + (threadIdx.x >> 5);
-    if (fi >= nframes || (threadIdx.x & 31) != 0) return;
+#define CORTO_RING 1024      // front records kept in shared memory per walk (16 KB: seven walks per SM stay resident)
+// One walk per block: the walks of a batch spread over all SMs instead of sharing a scheduler four at a time.
+__global__ void __launch_bounds__(32) k_corto_faces(const CortoFrame *frames, int32_t *status, const uint8_t *blob, const uint32_t *aux, uint8_t *S, uint8_t *O, int nframes) {
+    extern __shared__ uint4 corto_ring_smem[];
+    const int fi = blockIdx.x;
+    if (fi >= nframes || threadIdx.x != 0) return;
     if (frames[fi].status) { status[fi] = frames[fi].status; return; }
     if (status[fi]) return;
     const CortoFrame &f = frames[fi];
@@ -257,6 +260,7 @@ __global__ void __launch_bounds__(32 * CW) k_corto_faces(const CortoFrame *frame
     m.bits = CortoBits{(const uint32_t *)(blob + f.file_off + f.ibits.data_off), 0, (uint64_t)f.ibits.nwords * 32};
     m.group_end = aux + f.groups_off; m.ngroups = f.ngroups;
     m.front = (CortoEdge *)(S + f.o_front); m.third = (uint32_t *)(S + f.o_third); m.front_cap = 3 * (int)f.nface + 8;
+    m.ring = (CortoEdge *)corto_ring_smem; m.ring_size = CORTO_RING;
     m.queue = (int *)(S + f.o_queue); m.delayed = (int *)(S + f.o_delayed); m.order_cap = 3 * (int)f.nface + 8;
     m.faces = (uint32_t *)(O + f.out_index); m.pred = (int *)(S + f.o_pred); m.nvert = (int)f.nvert; m.nface = (int)f.nface;
     const int rc = corto_walk(m);
@@ -317,23 +321,34 @@ __global__ void __launch_bounds__(256) k_corto_values(const CortoFrame *frames, 
 // or += values[a]; normals with DIFF prediction always use the single parent (normal_attribute.cpp:182-204).  One warp per
 // (frame, attribute), lane k owns component k.  Unsigned arithmetic: colours are decoded modulo 256 (their C++ type is uchar), and
 // sums modulo 2^32 reduce to the same residues.
-__global__ void __launch_bounds__(32 * CW) k_corto_delta(const CortoFrame *frames, const int32_t *status, uint8_t *S, const CJob *jobs, int njobs) {
-    const int ji = blockIdx.x * CW + (threadIdx.x >> 5), k = threadIdx.x & 31;
+// The chain is serial (a vertex's parents are, as a rule, the vertices decoded just before it), so what counts is the latency of the
+// three parent reads: the values of the last CORTO_VRING vertices stay in shared memory (a read of a line this warp has just
+// written would otherwise be a trip to L2 per vertex); older parents -- gates the walk came back to -- are read from the array.
+#define CORTO_VRING 2048
+__global__ void __launch_bounds__(32) k_corto_delta(const CortoFrame *frames, const int32_t *status, uint8_t *S, const CJob *jobs, int njobs) {
+    __shared__ uint32_t ring[CORTO_VRING * 4];
+    const int ji = blockIdx.x, k = threadIdx.x;
     if (ji >= njobs) return;
     const CJob jb = jobs[ji];
     if (frames[jb.frame].status || status[jb.frame]) return;
     const CortoFrame &f = frames[jb.frame]; const CortoAttr &a = f.attr[jb.what];
-    if (k >= a.vN) return;
+    if (k >= a.vN || k >= 4) return;
     uint32_t *val = (uint32_t *)(S + a.o_val); const int4 *pred = (const int4 *)(S + f.o_pred);
     const int n = (int)f.nvert, N = a.vN; const bool par = a.kind != CK_NORMAL && (a.strategy & 1) != 0;
-    int4 p = n > 1 ? pred[1] : make_int4(0, 0, 0, 0);
+    if (n > 0) ring[k] = val[k];
+    int4 p = n > 1 ? pred[1] : make_int4(0, 0, 0, 0), p2 = n > 2 ? pred[2] : p;
+    uint32_t c = n > 1 ? val[N + k] : 0u, c2 = n > 2 ? val[2 * N + k] : 0u;
+#define CORTO_PARENT(j) ((j) >= i - CORTO_VRING ? ring[((j) & (CORTO_VRING - 1)) * 4 + k] : val[(j) * N + k])
     for (int i = 1; i < n; i++) {
-        const int4 nx = i + 1 < n ? pred[i + 1] : p;       // prefetch the next context
-        uint32_t v = val[i * N + k];
-        if (par) v += val[p.x * N + k] + val[p.y * N + k] - val[p.z * N + k]; else v += val[p.x * N + k];
+        const int4 p3 = i + 2 < n ? pred[i + 2] : p2;       // contexts and corrections are requested two vertices ahead
+        const uint32_t c3 = i + 2 < n ? val[(i + 2) * N + k] : 0u;
+        uint32_t v = c;
+        if (par) v += CORTO_PARENT(p.x) + CORTO_PARENT(p.y) - CORTO_PARENT(p.z); else v += CORTO_PARENT(p.x);
+        ring[(i & (CORTO_VRING - 1)) * 4 + k] = v;
         val[i * N + k] = v;
-        p = nx;
+        p = p2; p2 = p3; c = c2; c2 = c3;
     }
+#undef CORTO_PARENT
 }
 
 // ---- normal estimation (ESTIMATED / BORDER prediction)
@@ -572,11 +587,11 @@ extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data
         k_tunstall<<<nb(j_delta - j_tun), 32 * CW, sizeof(TunSmem) * CW, st>>>(dF, dSt, dBlob, dS, dJ + j_tun, j_delta - j_tun); launches++;
     }
     stamp();
-    k_corto_faces<<<nb(n), 32 * CW, 0, st>>>(dF, dSt, dBlob, dAux, dS, dO, n); launches++;
+    k_corto_faces<<<n, 32, (size_t)CORTO_RING * sizeof(CortoEdge), st>>>(dF, dSt, dBlob, dAux, dS, dO, n); launches++;
     stamp();
     k_corto_values<<<dim3(n, CORTO_MAX_ATTRS), 256, 0, st>>>(dF, dSt, dBlob, dS); launches++;
     stamp();
-    if (j_end - j_delta > 0) { k_corto_delta<<<nb(j_end - j_delta), 32 * CW, 0, st>>>(dF, dSt, dS, dJ + j_delta, j_end - j_delta); launches++; }
+    if (j_end - j_delta > 0) { k_corto_delta<<<j_end - j_delta, 32, 0, st>>>(dF, dSt, dS, dJ + j_delta, j_end - j_delta); launches++; }
     stamp();
     if (any_est) {
         const dim3 gc((3 * maxF + 255) / 256, n);

@@ -42,6 +42,77 @@ UVOL_HD int rabs_bit(Rabs &a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// rABS bit runs, one run per LANE.  A bit run is a strictly serial chain of a dozen integer instructions per bit, so a warp that gives
+// a run to lane 0 alone issues almost every cycle while using one lane in 32 -- and a 1000-frame batch has 2000 seam-bit runs of
+// 600 000 bits each: enough such warps to take most issue slots of all 148 SMs away from the connectivity walk that is resident
+// beside them (measured: the walk took 107 ms while they ran next to it, 75 without).  Here 32 runs advance in lockstep, one per
+// lane.  Lockstep only pays if the lanes do not diverge, so a step is straight-line code: the byte count of a renormalisation is
+// computed, not looped over, and inactive lanes run along with a byte count of zero.  (The same arrangement was tried for the rANS
+// symbol runs and lost: their step has two dependent shared-memory reads and a data-dependent scan, 32 runs' tables need most
+// of an SM's shared memory, and a lockstep step cost ~400 cycles against ~200 for a run that has a warp to itself.)
+//
+// Backward byte window: the run's bytes are consumed from its end towards its start.  The next bytes sit in a 64-bit register, the
+// next one to consume in the top byte (an aligned little-endian word read backwards is already in that order); a second register
+// holds the aligned word that will be appended next, requested one refill ahead.  Only aligned words that hold bytes of the run
+// are read.
+struct BackWin { const uint32_t *wp, *lo; unsigned long long win; uint32_t nw; int avail, left; };
+UVOL_HD void bw_refill(BackWin &b) {                              // afterwards 4 <= avail <= 8
+    if (b.avail <= 4) {
+        b.win |= (unsigned long long)b.nw << (32 - 8 * b.avail); b.avail += 4;
+        --b.wp;
+        b.nw = b.wp >= b.lo ? *b.wp : 0u;
+#if defined(__CUDA_ARCH__)
+        if ((((uintptr_t)b.wp) & 127u) == 0 && b.wp - 96 >= b.lo) { asm volatile("prefetch.global.L1 [%0];" :: "l"(b.wp - 32)); asm volatile("prefetch.global.L2 [%0];" :: "l"(b.wp - 96)); }
+#endif
+    }
+}
+// st * 256^n + the next n bytes (n <= 3, n <= left, n <= avail)
+UVOL_HD uint32_t bw_take(BackWin &b, uint32_t st, uint32_t n) {
+    const uint32_t hi = (uint32_t)(b.win >> 32);
+#if defined(__CUDA_ARCH__)
+    st = __funnelshift_l(hi, st, 8u * n);
+#else
+    if (n) st = (st << (8u * n)) | (hi >> (32u - 8u * n));
+#endif
+    b.win <<= 8u * n; b.avail -= (int)n; b.left -= (int)n;
+    return st;
+}
+UVOL_HD void bw_init(BackWin &b, const uint8_t *data, uint32_t nbytes) {      // nbytes >= 1
+    const uint8_t *last = data + nbytes - 1;
+    const uint32_t *A = (const uint32_t *)((uintptr_t)last & ~(uintptr_t)3); const uint32_t bi = (uint32_t)((uintptr_t)last & 3);
+    b.lo = (const uint32_t *)((uintptr_t)data & ~(uintptr_t)3);
+    b.left = (int)nbytes; b.avail = (int)bi + 1; b.win = (unsigned long long)A[0] << (32u + 8u * (3u - bi));
+    b.wp = A - 1; b.nw = b.wp >= b.lo ? *b.wp : 0u;
+    bw_refill(b);
+}
+UVOL_HD void bw_idle(BackWin &b, const void *any) { b.wp = b.lo = (const uint32_t *)any; b.win = 0; b.nw = 0; b.avail = 8; b.left = 0; }
+
+// rABS bit run through the same byte window
+struct RabsLane { BackWin in; uint32_t st, p; };
+UVOL_HD void rabs_lane_idle(RabsLane &a, const void *any) { a.st = 4096u; a.p = 1; bw_idle(a.in, any); }
+UVOL_HD bool rabs_lane_init(RabsLane &a, const uint8_t *file, const RabsStream &s) {
+    const uint8_t *b = file + s.data_off; const uint32_t n = s.data_len;
+    rabs_lane_idle(a, file);
+    a.p = 256u - s.prob_zero;
+    if (n == 0) return false;
+    const unsigned x = b[n - 1] >> 6;
+    if (x > 2 || n < x + 1) return false;
+    bw_init(a.in, b, n);
+    const uint32_t st = bw_take(a.in, 0u, x + 1); bw_refill(a.in);
+    a.st = (st & ((1u << (8 * (x + 1) - 2)) - 1u)) + 4096u;
+    return true;
+}
+UVOL_HD uint32_t rabs_lane_bit(RabsLane &a, bool active) {
+    const uint32_t n = (active && a.st < 4096u && a.in.left > 0) ? 1u : 0u;
+    a.st = bw_take(a.in, a.st, n); bw_refill(a.in);
+    const uint32_t x = a.st, q = x >> 8, rem = x & 255u, xn = q * a.p;
+    const bool one = rem < a.p;
+    const uint32_t nx = one ? xn + rem : x - xn - a.p;
+    a.st = active ? nx : x;
+    return one ? 1u : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
 // rANS symbol run (A.2).  cum[alphabet+1] and bucket[257] are prepared by the caller (shared
 // memory in the kernel): bucket[b] = first symbol whose range ends above b << (pb-8).
 struct RansTables { const uint32_t *cum; const uint16_t *bucket; uint32_t alphabet, pb; };

@@ -84,11 +84,14 @@ __device__ __forceinline__ uint32_t rans_walk(RansRun r, uint32_t count, void *o
     return i;
 }
 
-#define RANS_LUT_BITS 10          // 8 KB index + 2 KB ranks + 16 B per used symbol: every run of a 300-frame batch is resident at once
-__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
-                                             uint8_t *scratch, const Job *jobs, int njobs, int smem_words_per_warp, int early) {
+// lut_bits: size of the slot index (8 B + 2 B per entry) -- 10 for the attribute runs (alphabets of hundreds of symbols), 6 for the
+// connectivity context runs (five symbols): their tables then take under 1 KB, four runs share a block, and all six runs of every
+// frame of a 1000-frame batch are resident at once (with the 10-bit index they needed two waves and sat at the head of the critical path).
+#define RANS_LUT_BITS_MAX 10
+__global__ void __launch_bounds__(128) k_rans(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
+                                             uint8_t *scratch, const Job *jobs, int njobs, int smem_words_per_warp, int early, int lut_bits) {
     extern __shared__ uint32_t smem_all[];
-    const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
+    const int ji = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ji >= njobs) return;
     uint32_t *smem = smem_all + (size_t)(threadIdx.x >> 5) * smem_words_per_warp;
     const Job jb = jobs[ji];
@@ -115,9 +118,9 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *fr
     // non-zero probability (cs[nnz].x = total), lut[b] = {first slot | symbol, frequency} and kidx[b] = rank of the first
     // symbol whose range reaches into bucket b.
     const uint32_t A = s.alphabet, pb = s.pb;
-    const uint32_t lb = pb < RANS_LUT_BITS ? pb : RANS_LUT_BITS;
+    const uint32_t lb = pb < (uint32_t)lut_bits ? pb : (uint32_t)lut_bits;
     if (A > (1u << 18) || pb > 20u) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }      // the RAW scheme allows 18-bit symbols, 20-bit precision
-    uint2 *lut = (uint2 *)smem; uint16_t *kidx = (uint16_t *)(lut + (1u << RANS_LUT_BITS)); uint4 *cs = (uint4 *)(kidx + (1u << RANS_LUT_BITS));
+    uint2 *lut = (uint2 *)smem; uint16_t *kidx = (uint16_t *)(lut + (1u << lut_bits)); uint4 *cs = (uint4 *)(kidx + (1u << lut_bits));
     const uint32_t *prob = aux + s.prob_off;
     uint32_t run = 0, nk = 0;
     for (uint32_t base = 0; base < A; base += 32) {
@@ -174,33 +177,43 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rans(const DracoFrame *fr
     else { if (mode == 0) rans_walk<0, true, false>(r, count, out); else if (mode == 1) rans_walk<1, true, false>(r, count, out); else rans_walk<2, true, false>(r, count, out); }
 }
 
-// rABS bit runs: one warp per run (lane 0 walks).  what: 0..3 = seam bits of attribute data i
-// (upper bound 3F/2+1 bits); 16+j = attribute j aux bits (TEX_COORDS orientations incl. the
-// toggle decoding, or GEOMETRIC_NORMAL flip bits).
-__global__ void __launch_bounds__(32 * SERIAL_WARPS) k_rabs(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob,
-                                             uint8_t *scratch, const Job *jobs, int njobs) {
-    const int ji = blockIdx.x * SERIAL_WARPS + (threadIdx.x >> 5);
-    if (ji >= njobs || (threadIdx.x & 31) != 0) return;
-    const Job jb = jobs[ji];
-    if (frame_dead(frames, counts, jb.frame)) return;
-    const DracoFrame &f = frames[jb.frame];
-    const uint8_t *file = blob + f.file_off;
-    Rabs r;
-    if (jb.what < 16) {
-        if (!rabs_init(r, file, f.seams[jb.what])) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
-        uint8_t *o = scratch + f.o_seambits[jb.what]; const int n = (int)(3 * f.nf / 2 + 1);
-        for (int k = 0; k < n; k++) o[k] = (uint8_t)rabs_bit(r);
-    } else {
-        const DracoAttr &a = f.attr[jb.what - 16];
-        if (!rabs_init(r, file, a.aux_bits)) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
-        uint8_t *o = scratch + f.o_auxbits[jb.what - 16];
-        const uint32_t n = counts[jb.frame].expected[a.table + 1];
-        if (n > f.table_cap[a.table + 1]) { frame_fail(counts, jb.frame, UVOL_ERR_FRAME_CAPACITY); return; }
-        if (a.pred == 5) {
-            if ((uint32_t)a.num_orient > n) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
-            int last = 1;
-            for (int k = 0; k < a.num_orient; k++) { if (!rabs_bit(r)) last = !last; o[k] = (uint8_t)last; }
-        } else for (uint32_t k = 0; k < n; k++) o[k] = (uint8_t)rabs_bit(r);
+// rABS bit runs, one run per lane.  what: 0..3 = seam bits of attribute data i (upper bound 3F/2+1 bits); 16+j = attribute j aux
+// bits (TEX_COORDS orientations incl. the toggle decoding, or GEOMETRIC_NORMAL flip bits).  One byte per bit out, eight at a time.
+__global__ void __launch_bounds__(32) k_rabs_lanes(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob,
+                                                   uint8_t *scratch, const Job *jobs, int njobs) {
+    const unsigned FULL = 0xffffffffu;
+    const int ji = blockIdx.x * 32 + (int)threadIdx.x;
+    bool live = ji < njobs;
+    Job jb = {0u, 0};
+    if (live) { jb = jobs[ji]; live = !frame_dead(frames, counts, jb.frame); }
+    RabsLane r; rabs_lane_idle(r, blob); uint8_t *o = nullptr; uint32_t n = 0; bool toggle = false;
+    if (live) {
+        const DracoFrame &f = frames[jb.frame];
+        const uint8_t *file = blob + f.file_off;
+        bool ok;
+        if (jb.what < 16) { ok = rabs_lane_init(r, file, f.seams[jb.what]); o = scratch + f.o_seambits[jb.what]; n = 3 * f.nf / 2 + 1; }
+        else {
+            const DracoAttr &a = f.attr[jb.what - 16];
+            ok = rabs_lane_init(r, file, a.aux_bits); o = scratch + f.o_auxbits[jb.what - 16];
+            n = counts[jb.frame].expected[a.table + 1];
+            if (n > f.table_cap[a.table + 1]) { frame_fail(counts, jb.frame, UVOL_ERR_FRAME_CAPACITY); live = false; }
+            else if (a.pred == 5) { if ((uint32_t)a.num_orient > n) ok = false; n = (uint32_t)a.num_orient; toggle = true; }
+        }
+        if (live && !ok) { frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); live = false; }
+    }
+    if (!live) n = 0;
+    uint32_t last = 1;
+    for (uint32_t k = 0; __any_sync(FULL, k < n); k += 8) {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const bool on = k + b < n;
+            uint32_t bit = rabs_lane_bit(r, on);
+            last ^= (toggle && on && !bit) ? 1u : 0u;
+            bit = on ? (toggle ? last : bit) : 0u;
+            if (b < 4) lo |= bit << (8 * b); else hi |= bit << (8 * (b - 4));
+        }
+        if (k < n) *(uint2 *)(o + k) = make_uint2(lo, hi);      // (the arrays end on 8 bytes of slack)
     }
 }
 
@@ -665,12 +678,13 @@ __global__ void __launch_bounds__(PLAN_T) k_plan2(DracoFrame *frames, DracoCount
 // -- for those two entry corners -- the distance to the nearest earlier face of the run whose entry corner has the same tip vertex
 // (so the traversal knows, without any exchange between lanes, that a tip was already reached inside the same 32-face step).
 // 32 bytes per face; everything the serial traversal needs about a face is one load.   grid = (ceil(maxF/256), traversal jobs)
-__global__ void __launch_bounds__(256) k_face_records(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S, const uint8_t *Z, const Job *jobs) {
+// which: 0 = base tables only, 1 = attribute tables only, 2 = all
+__global__ void __launch_bounds__(256) k_face_records(const DracoFrame *frames, const DracoCounts *counts, uint8_t *S, const uint8_t *Z, const Job *jobs, int which) {
     __shared__ uint32_t tipU[256 + 31], tipD[256 + 31];
     const Job jb = jobs[blockIdx.y];
     if (frame_dead(frames, counts, jb.frame)) return;
     const DracoFrame &f = frames[jb.frame]; const int t = jb.what;
-    if (f.o_frec[t] == UVOL_NONE) return;
+    if (f.o_frec[t] == UVOL_NONE || (which == 0 && t != 0) || (which == 1 && t == 0)) return;
     const int F = (int)f.nf, base = blockIdx.x * 256, tid = threadIdx.x;
     if (base >= F) return;
     const TableView tv = make_view(f, t, S, Z);
@@ -1260,11 +1274,15 @@ static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_
     uint8_t *dS = (uint8_t *)ctx->d_scratch.p, *dZ = (uint8_t *)ctx->d_zscratch.p; const Job *dJ = (const Job *)ctx->d_jobs.p;
     uint8_t *dS2 = (uint8_t *)ctx->d_scratch2.p, *dZ2 = (uint8_t *)ctx->d_zscratch2.p, *dO = (uint8_t *)ctx->d_out_geo.p;
     uint32_t launches = 0;
-    auto rans_words = [](uint32_t nnz) { return (int)(((size_t)(nnz + 1) * 16 + (10u << RANS_LUT_BITS) + 16 + 15) / 16 * 4); };
-    auto rans_smem = [&](uint32_t alphabet) { return (size_t)rans_words(alphabet) * 4 * SERIAL_WARPS; };
+    // context runs: 6-bit index, 4 per block; attribute runs: 8-bit index (2.5 KB + 16 B per used symbol) so that all runs of a
+    // 1000-frame batch are resident at once
+    const int lbA = B.max_alpha_ctx <= 8 ? 6 : RANS_LUT_BITS_MAX, wpbA = lbA == 6 ? 4 : 1, lbB = B.n > 256 ? 8 : RANS_LUT_BITS_MAX;
+    auto rans_words = [](uint32_t nnz, int bits) { return (int)(((size_t)(nnz + 1) * 16 + (10u << bits) + 16 + 15) / 16 * 4); };
+    auto rans_smem = [&](uint32_t alphabet, int bits, int wpb) { return (size_t)rans_words(alphabet, bits) * 4 * wpb; };
     auto nblk = [](int jobs) { return (unsigned)((jobs + SERIAL_WARPS - 1) / SERIAL_WARPS); };
+    auto nblk32 = [](int jobs) { return (unsigned)((jobs + 31) / 32); };
     {
-        const size_t smA = rans_smem(B.max_alpha_ctx), smB = rans_smem(B.max_alpha_attr);
+        const size_t smA = rans_smem(B.max_alpha_ctx, lbA, wpbA), smB = rans_smem(B.max_alpha_attr, lbB, 1);
         const size_t smMax = smA > smB ? smA : smB;
         if (smMax > 200 * 1024) { ctx->set_error("rANS alphabet too large for the shared-memory tables"); return UVOL_ERR_UNSUPPORTED; }
         if (smMax > 48 * 1024) UVOL_CUDA(ctx, cudaFuncSetAttribute(k_rans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smMax));
@@ -1275,18 +1293,18 @@ static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_
     cudaStream_t sx = getenv("UVOL_NO_OVERLAP") ? ctx->s0 : ctx->s1;
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[0], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->sync_ev[0], 0));
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[0], sx);
-    if (B.j_trav - B.j_rabsA > 0) { k_rabs<<<nblk(B.j_trav - B.j_rabsA), 32 * SERIAL_WARPS, 0, sx>>>(dF, dC, dBlob, dS, dJ + B.j_rabsA, B.j_trav - B.j_rabsA); launches++; }
+    if (B.j_trav - B.j_rabsA > 0) { k_rabs_lanes<<<nblk32(B.j_trav - B.j_rabsA), 32, 0, sx>>>(dF, dC, dBlob, dS, dJ + B.j_rabsA, B.j_trav - B.j_rabsA); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[1], sx);
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[1], sx));
-    // The attribute symbol runs do not wait for the connectivity: they run to the coder's terminal state (k_rans, early mode)
-    // next to the connectivity walk, straight into the attribute's correction array; a run that did not come out with exactly
-    // the expected count is decoded again, by count, once the count is known.
+    // The attribute symbol runs do not wait for the COUNTS the connectivity stages produce either: they run to the coder's terminal
+    // state (k_rans, early mode) straight into the attribute's correction array, on the side stream behind the seam bits; a run
+    // that did not come out with exactly the expected count is decoded again, by count, once the count is known.
     static const bool no_early = getenv("UVOL_NO_EARLY_RANS") != nullptr;
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[2], sx);
-    if (!no_early && B.j_rabsB - B.j_ransB > 0) { k_rans<<<nblk(B.j_rabsB - B.j_ransB), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_attr), sx>>>(dF, dC, dBlob, dAux, dS, dJ + B.j_ransB, B.j_rabsB - B.j_ransB, rans_words(B.max_alpha_attr), 1); launches++; }
+    if (!no_early && B.j_rabsB - B.j_ransB > 0) { k_rans<<<nblk(B.j_rabsB - B.j_ransB), 32, rans_smem(B.max_alpha_attr, lbB, 1), sx>>>(dF, dC, dBlob, dAux, dS, dJ + B.j_ransB, B.j_rabsB - B.j_ransB, rans_words(B.max_alpha_attr, lbB), 1, lbB); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[3], sx);
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[4], sx));
-    if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<nblk(B.j_rabsA - B.j_ransA), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_ctx), st>>>(dF, dC, dBlob, dAux, dS, dJ + B.j_ransA, B.j_rabsA - B.j_ransA, rans_words(B.max_alpha_ctx), 0); launches++; }
+    if (B.j_rabsA - B.j_ransA > 0) { k_rans<<<(unsigned)((B.j_rabsA - B.j_ransA + wpbA - 1) / wpbA), 32 * wpbA, rans_smem(B.max_alpha_ctx, lbA, wpbA), st>>>(dF, dC, dBlob, dAux, dS, dJ + B.j_ransA, B.j_rabsA - B.j_ransA, rans_words(B.max_alpha_ctx, lbA), 0, lbA); launches++; }
     stamp("rans_ctx");
     stamp("rabs_seams(s1)"); i_seams = ev - 2;                                     // (stage slot of rabs_seams: timed on s1, filled in below)
     if (B.any_valence) {
@@ -1295,6 +1313,16 @@ static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_
     }
     if (B.any_standard) { k_edgebreaker<<<nblk(n), 32 * SERIAL_WARPS, 0, st>>>(dF, dC, dBlob, dAux, dS, n); launches++; }
     stamp("edgebreaker");
+    UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[9], st));
+    // The base table's traversal records need the corner table only: they are built on the side stream next to the seam /
+    // attribute-table / point stages (their arena lies clear of those stages' temporaries, draco_plan.h).
+    const int ntj_all = B.j_ransB - B.j_trav;
+    const bool early_base = pl.base_records_early && ntj_all > 0 && !getenv("UVOL_NO_OVERLAP");
+    if (early_base) {
+        UVOL_CUDA(ctx, cudaStreamWaitEvent(ctx->s3, ctx->sync_ev[9], 0));      // (s1 is busy with the attribute symbol runs)
+        k_face_records<<<dim3((B.maxF + 255) / 256, ntj_all), 256, 0, ctx->s3>>>(dF, dC, dS, dZ, dJ + B.j_trav, 0); launches++;
+        UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[10], ctx->s3));
+    }
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[1], 0));
     if (B.maxnad) {
         const dim3 sg((3 * B.maxF + SEAM_CHUNK - 1) / SEAM_CHUNK, (unsigned)n);
@@ -1322,7 +1350,7 @@ static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_
     // ---- phase 2.  The aux bit runs (sized from counts.expected) go to s1 and overlap the traversals.
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[2], st)); UVOL_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->sync_ev[2], 0));
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[5], sx);
-    if (B.j_wrap - B.j_rabsB > 0) { k_rabs<<<nblk(B.j_wrap - B.j_rabsB), 32 * SERIAL_WARPS, 0, sx>>>(dF, dC, dBlob, dS, dJ + B.j_rabsB, B.j_wrap - B.j_rabsB); launches++; }
+    if (B.j_wrap - B.j_rabsB > 0) { k_rabs_lanes<<<nblk32(B.j_wrap - B.j_rabsB), 32, 0, sx>>>(dF, dC, dBlob, dS, dJ + B.j_rabsB, B.j_wrap - B.j_rabsB); launches++; }
     if (ctx->profile) cudaEventRecord(ctx->aux_ev[4], sx);
     UVOL_CUDA(ctx, cudaEventRecord(ctx->sync_ev[3], sx));
     k_point_fan<1><<<dim3(gv, n), 128, 0, st>>>(dF, dC, dS, dZ, dS2, dO); launches++;
@@ -1333,7 +1361,8 @@ static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_
     }
     if (B.j_ransB - B.j_trav > 0) {
         const int ntj = B.j_ransB - B.j_trav;
-        k_face_records<<<dim3((B.maxF + 255) / 256, ntj), 256, 0, st>>>(dF, dC, dS, dZ, dJ + B.j_trav); launches++;
+        k_face_records<<<dim3((B.maxF + 255) / 256, ntj), 256, 0, st>>>(dF, dC, dS, dZ, dJ + B.j_trav, early_base ? 1 : 2); launches++;
+        if (early_base) UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[10], 0));
         stamp("face_records");
         uint32_t capN = B.maxV + 4;
         for (int i = 0; i < n; i++) if (!frames[i].status) for (uint32_t t = 1; t <= frames[i].nad; t++) if (frames[i].table_cap[t] > capN) capN = frames[i].table_cap[t];
@@ -1356,7 +1385,7 @@ static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[4], 0));
     if (B.j_rabsB - B.j_ransB > 0) {      // attribute runs whose early decode did not end on the expected count (normally none): again, by count
         const int nrj = B.j_rabsB - B.j_ransB;
-        k_rans<<<nblk(nrj), 32 * SERIAL_WARPS, rans_smem(B.max_alpha_attr), st>>>(dF, dC, dBlob, dAux, dS, dJ + B.j_ransB, nrj, rans_words(B.max_alpha_attr), 0); launches++;
+        k_rans<<<nblk(nrj), 32, rans_smem(B.max_alpha_attr, lbB, 1), st>>>(dF, dC, dBlob, dAux, dS, dJ + B.j_ransB, nrj, rans_words(B.max_alpha_attr, lbB), 0, lbB); launches++;
     }
     stamp("rans_recheck");
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[3], 0));

@@ -30,6 +30,7 @@ struct DracoPlan {
     uint64_t s2_est = 0, z2_est = 0, out_est = 0;             // count-sized arenas: optimistic estimates (out_est includes the index region)
     uint64_t scratch2 = 0, zscratch2 = 0, out = 0;            // count-sized arenas: exact, known after the run
     uint32_t cap_entries = 1, cap_points = 1;                 // grid sizes of the entry- / point-parallel kernels (they stride, so these are not limits)
+    bool base_records_early = false;                          // every frame's base-table traversal records lie clear of the connectivity temporaries
 };
 
 #define UVOL_NONE (~0ull)
@@ -45,7 +46,7 @@ UVOL_HD void draco_tables_needed(const DracoFrame &f, bool need[UVOL_MAX_ATTR_DA
 // the re-plan path.
 static inline void draco_plan_phase1(std::vector<DracoFrame> &frames, DracoPlan &pl, uint32_t cap_permille = 1000) {
     uint64_t s = 0, z = 0, o = 0, s2 = 0, z2 = 0, oa = 0;
-    pl.cap_entries = pl.cap_points = 1;
+    pl.cap_entries = pl.cap_points = 1; pl.base_records_early = true;
     for (auto &f : frames) if (!f.status) f.out_index = plan_take(o, (uint64_t)f.nf * 12);
     pl.out_index = o;
     for (auto &f : frames) {
@@ -85,11 +86,14 @@ static inline void draco_plan_phase1(std::vector<DracoFrame> &frames, DracoPlan 
         }
         f.o_pcnt = plan_take(a, (maxv + 1) * 4);
         f.o_pfirst = plan_take(a, maxv * 4);                  // dedup start corner per vertex
-        for (uint32_t t = 0; t <= UVOL_MAX_ATTR_DATA; t++) {
-            if (t > f.nad || !need[t]) { f.o_frec[t] = f.o_tstack[t] = f.o_fvis[t] = UVOL_NONE; continue; }
+        // attribute tables first, the base table LAST: its records then start behind tenant A whenever an attribute table exists, so
+        // they can be built as soon as the connectivity is decoded (next to the seam / attribute-table / point stages)
+        for (int t = UVOL_MAX_ATTR_DATA; t >= 0; t--) {
+            if ((uint32_t)t > f.nad || !need[t]) { f.o_frec[t] = f.o_tstack[t] = f.o_fvis[t] = UVOL_NONE; continue; }
             f.o_frec[t] = plan_take(b, (F + 2) * sizeof(FaceRec));
             f.o_tstack[t] = plan_take(b, (F + 8) * 4);
         }
+        if (f.o_frec[0] < a) pl.base_records_early = false;
         for (int j = 0; j < f.nattr; j++) {
             const DracoAttr &at = f.attr[j];
             if (!draco_attr_needed(f, j) || !(at.pred == 0 || at.pred == 1 || at.pred == 5)) continue;
