@@ -308,8 +308,18 @@ def bench_v1(args, W, rank, world, local):
     kst = {k: v for k, v in stages.items() if k not in ("h2d", "d2h")}
     dom = max(kst, key=lambda k: kst[k]["ms"])
     # algorithmic bytes per step: compressed bytes in + index / position / uv out; the dominant stage's share: faces = clers in, index out
-    alg = {"faces": F_total * (1 + 12), "dequant": V_total * 5 * 8, "delta": V_total * 5 * 8, "values": st["bytes_in"] + V_total * 5 * 4, "tunstall": st["bytes_in"]}
+    # (faces = the walk plus the delta reversal that follows it inside the same kernel: clers in, index out, corrections in, values out)
+    alg = {"faces": F_total * (1 + 12) + V_total * 5 * 8, "dequant": V_total * 5 * 8, "values": st["bytes_in"] + V_total * 5 * 4, "tunstall": st["bytes_in"]}
     ach = alg.get(dom, 0) / (kst[dom]["ms"] * 1e-3) / 1e9 if kst[dom]["ms"] > 0 else None
+    traffic, traffic_src = None, None
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02*_traffic*.json"))):       # measured DRAM bytes per launch (ncu --set full), scaled per frame
+        try:
+            tr = json.load(open(path))
+            if tr.get("workload") == "c5" and tr.get(dom) and tr.get("frames"):
+                traffic, traffic_src = tr[dom] * frames / tr["frames"], os.path.basename(path)
+        except Exception:
+            pass
     if rank == 0:
         cpu = None
         if world == 1:
@@ -324,7 +334,7 @@ def bench_v1(args, W, rank, world, local):
                                      "parallelism": f"frames sharded, {world} rank(s), no data-path collective"},
                           "mverts_per_s": V_total * world * args.steps / (dev_ms / 1e3) / 1e6,
                           "roofline": {"bound": "hbm", "kernel": "corto_" + dom, "achieved": ach and round(ach, 2), "peak": peak, "unit": "GB/s", "frac": ach and round(ach / peak, 5),
-                                       "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom), "ms_per_launch": kst[dom]["ms"],
+                                       "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom), "ms_per_launch": kst[dom]["ms"],
                                        "note": "dominant stage is a latency-bound serial walk (one warp per frame)"},
                           "stages": stages, "cpu_baseline": cpu,
                           "e2e": {"value": total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": st["bytes_in"], "d2h_bytes_per_step": st["bytes_out"], "ms_per_step": e2e_s / args.steps * 1e3,
@@ -540,7 +550,7 @@ def main():
         v["share_of_kernel_time"] = round(v["ms"] / ksum, 4)          # comparable with the ncu launch-list shares
     traffic = None
     import glob
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02*_traffic.json"))):        # measured DRAM bytes per launch (ncu --set full), newest last
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02*_traffic*.json"))):        # measured DRAM bytes per launch (ncu --set full), newest last
         try:
             tr = json.load(open(path))
             if tr.get("workload") == args.workload:

@@ -17,7 +17,7 @@ extern "C" int corto_emu_walk(const uint8_t *clers, uint32_t nclers, const uint3
     const int cap = 3 * nface + 8;
     std::vector<CortoEdge> front(cap); std::vector<uint32_t> third(cap); std::vector<int> queue(cap), delayed(cap);
     std::vector<CortoEdge> ring((size_t)g_ring_size);
-    CortoWalkMem m; m.ring = ring.data(); m.ring_size = g_ring_size;
+    CortoWalkMem m; m.ring = ring.data(); m.ring_size = g_ring_size; m.progress = nullptr;
     m.clers = (const uint8_t *)cl.data(); m.nclers = nclers; m.bits = CortoBits{w.data(), 0, (uint64_t)nwords * 32};
     m.group_end = group_end; m.ngroups = ngroups; m.front = front.data(); m.third = third.data(); m.front_cap = cap;
     m.queue = queue.data(); m.delayed = delayed.data(); m.order_cap = cap; m.faces = faces; m.pred = pred4; m.nvert = nvert; m.nface = nface;

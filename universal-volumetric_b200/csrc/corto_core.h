@@ -54,6 +54,7 @@ struct CortoWalkMem {
     uint32_t *faces;                                    // out: 3 * nface vertex ids
     int *pred;                                          // out: {a, b, c, 0} per vertex -- the parallelogram context of deltaDecode
     int nvert, nface;
+    volatile int *progress;                             // optional: number of vertices whose context is final, published every 16 vertices (the kernel's delta warps follow it)
 };
 
 CORTO_HD int corto_walk(const CortoWalkMem &m) {
@@ -63,6 +64,11 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
     int vertex_count = 0; uint32_t cler = 0, start = 0;
     CortoEdge *ring = m.ring; const int rsize = m.ring_size, rmask = m.ring_size - 1;
     unsigned long long cw = 0, cwn = m.nclers ? *(const unsigned long long *)m.clers : 0ull;
+#if defined(__CUDA_ARCH__)
+#define CW_PUBLISH() do { if (m.progress && (vertex_count & 15) == 0) { __threadfence_block(); *m.progress = vertex_count; } } while (0)
+#else
+#define CW_PUBLISH() do { if (m.progress && (vertex_count & 15) == 0) *m.progress = vertex_count; } while (0)
+#endif
 #define CW_FAIL(code) return (code)
 #define CW_SYMBOL(c) do { if (cler >= m.nclers) CW_FAIL(CORTO_TRUNCATED); \
                           if ((cler & 7u) == 0u) { cw = cwn; if (cler + 8u < m.nclers) cwn = *(const unsigned long long *)(m.clers + cler + 8u); } \
@@ -97,6 +103,7 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
                             if (vertex_count >= nvert) CW_FAIL(CORTO_CORRUPT);
                             int *pr = m.pred + 4 * vertex_count; pr[0] = last; pr[1] = last; pr[2] = last; pr[3] = 0;
                             last = v[k] = vertex_count++;
+                            CW_PUBLISH();
                         }
                     }
                     CW_FACE(v[0], v[1], v[2]);
@@ -121,6 +128,7 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
                     if (vertex_count >= nvert) CW_FAIL(CORTO_CORRUPT);
                     int *pr = m.pred + 4 * vertex_count; pr[0] = E.v1; pr[1] = E.v0; pr[2] = (int)gv2; pr[3] = 0;
                     opp = vertex_count++;
+                    CW_PUBLISH();
                 }
                 if (nfront + 2 > m.front_cap || norder >= m.order_cap) CW_FAIL(CORTO_CORRUPT);
                 const int A = nfront, B = nfront + 1; nfront += 2;
@@ -171,6 +179,7 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
             else CW_FAIL(CORTO_CORRUPT);
         }
     }
+#undef CW_PUBLISH
 #undef CW_FAIL
 #undef CW_SYMBOL
 #undef CW_IN_RING

@@ -6,11 +6,11 @@
 // (src/V1/worker.ts:48-68).  Layout: SURVEY.md Appendix C.  Stages:
 //   tunstall   one warp per Tunstall block: lane 0 rebuilds the 256-word dictionary (tunstall.cpp:125-256),
 //              then the warp expands the code bytes with a prefix sum over word lengths (:430-452)
-//   faces      one warp per frame: the front-growing connectivity walk (corto_core.h; decoder.cpp:181-333)
 //   values     one CTA per (frame, attribute): prefix sum of the per-value bit widths -> every value's bit
 //              offset -> parallel bit extraction (cstream.h:296-362; bitstream.cpp:103-121, MSB-first words)
-//   delta      one warp per (frame, attribute): parallelogram / delta reversal (vertex_attribute.h:155-177; normals with DIFF
-//              prediction: normal_attribute.cpp:182-204)
+//   faces      one CTA per frame: warp 0 runs the front-growing connectivity walk (corto_core.h; decoder.cpp:181-333), one more warp
+//              per attribute follows it with the parallelogram / delta reversal (vertex_attribute.h:155-177; normals with DIFF
+//              prediction: normal_attribute.cpp:182-204) of the vertices whose context the walk has published
 //   estimate   (normals with ESTIMATED / BORDER prediction, normal_attribute.cpp:24-59,206-303): vertex -> incident corners lists
 //              (count, scan, fill), then per vertex the face normals are summed IN FACE ORDER (the reference accumulates floats
 //              face by face, so the order is part of the result) and the boundary mark is XOR-ed together
@@ -245,26 +245,81 @@ __global__ void __launch_bounds__(32 * CW) k_tunstall(const CortoFrame *frames, 
 
 __device__ __forceinline__ int ilog2_u(uint32_t p) { int k = 0; while (p >>= 1) ++k; return k; }
 
-// Connectivity: the front-growing walk (corto_core.h), one warp per frame, lane 0 walks (the batch supplies the parallelism).
-#define CORTO_RING 1024      // front records kept in shared memory per walk (16 KB: seven walks per SM stay resident)
-// One walk per block: the walks of a batch spread over all SMs instead of sharing a scheduler four at a time.
-__global__ void __launch_bounds__(32) k_corto_faces(const CortoFrame *frames, int32_t *status, const uint8_t *blob, const uint32_t *aux, uint8_t *S, uint8_t *O, int nframes) {
-    extern __shared__ uint4 corto_ring_smem[];
-    const int fi = blockIdx.x;
-    if (fi >= nframes || threadIdx.x != 0) return;
-    if (frames[fi].status) { status[fi] = frames[fi].status; return; }
+// Connectivity + delta reversal, one block per frame.
+//   warp 0, lane 0: the front-growing walk (corto_core.h).  One walk per block, so the walks of a batch spread over all SMs.
+//   warp 1 + a, lanes 0..N-1: the delta reversal of attribute a (value = correction + prediction from the parallelogram context the
+//     walk recorded for the vertex, deltaDecode, vertex_attribute.h:154-189: with the PARALLEL strategy values[i] += values[a] +
+//     values[b] - values[c], else += values[a]; normals with DIFF prediction always use the single parent, normal_attribute.cpp:
+//     182-204; lane k owns component k; unsigned arithmetic: colours are decoded modulo 256 -- their C++ type is uchar -- and sums
+//     modulo 2^32 reduce to the same residues).  The warps FOLLOW the walk: it publishes how many vertices have their context
+//     (every 16 vertices, behind a block-level fence), they reverse what is published -- the chain costs about half of what the
+//     walk costs per vertex, so it is hidden entirely instead of running as a second serial stage after the walk.
+//   Both chains are latency chains, so what they touch again soon stays in shared memory: the walk's last CORTO_RING front records,
+//   each delta warp's last CORTO_VRING values (a parent is, as a rule, a vertex decoded just before; older ones are read from the array).
+#define CORTO_RING 1024      // front records kept in shared memory per walk (16 KB)
+#define CORTO_VRING 512      // values kept in shared memory per attribute (8 KB)
+#define CORTO_FACES_SMEM ((size_t)(CORTO_RING + CORTO_MAX_ATTRS * CORTO_VRING) * 16)
+__global__ void __launch_bounds__(32 * (1 + CORTO_MAX_ATTRS)) k_corto_faces(const CortoFrame *frames, int32_t *status, const uint8_t *blob, const uint32_t *aux, uint8_t *S, uint8_t *O, int nframes) {
+    extern __shared__ uint4 corto_smem[];
+    __shared__ volatile int progress, walk_done;
+    const int fi = blockIdx.x, warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+    if (fi >= nframes) return;
+    if (frames[fi].status) { if (threadIdx.x == 0) status[fi] = frames[fi].status; return; }
     if (status[fi]) return;
     const CortoFrame &f = frames[fi];
-    CortoWalkMem m;
-    m.clers = S + f.clers.o_out; m.nclers = f.clers.size;
-    m.bits = CortoBits{(const uint32_t *)(blob + f.file_off + f.ibits.data_off), 0, (uint64_t)f.ibits.nwords * 32};
-    m.group_end = aux + f.groups_off; m.ngroups = f.ngroups;
-    m.front = (CortoEdge *)(S + f.o_front); m.third = (uint32_t *)(S + f.o_third); m.front_cap = 3 * (int)f.nface + 8;
-    m.ring = (CortoEdge *)corto_ring_smem; m.ring_size = CORTO_RING;
-    m.queue = (int *)(S + f.o_queue); m.delayed = (int *)(S + f.o_delayed); m.order_cap = 3 * (int)f.nface + 8;
-    m.faces = (uint32_t *)(O + f.out_index); m.pred = (int *)(S + f.o_pred); m.nvert = (int)f.nvert; m.nface = (int)f.nface;
-    const int rc = corto_walk(m);
-    if (rc) status[fi] = rc == CORTO_TRUNCATED ? UVOL_ERR_TRUNCATED : UVOL_ERR_CORRUPT;
+    if (threadIdx.x == 0) { progress = 0; walk_done = 0; }
+    __syncthreads();
+    if (warp == 0) {
+        if (k != 0) return;
+        CortoWalkMem m;
+        m.clers = S + f.clers.o_out; m.nclers = f.clers.size;
+        m.bits = CortoBits{(const uint32_t *)(blob + f.file_off + f.ibits.data_off), 0, (uint64_t)f.ibits.nwords * 32};
+        m.group_end = aux + f.groups_off; m.ngroups = f.ngroups;
+        m.front = (CortoEdge *)(S + f.o_front); m.third = (uint32_t *)(S + f.o_third); m.front_cap = 3 * (int)f.nface + 8;
+        m.ring = (CortoEdge *)corto_smem; m.ring_size = CORTO_RING;
+        m.queue = (int *)(S + f.o_queue); m.delayed = (int *)(S + f.o_delayed); m.order_cap = 3 * (int)f.nface + 8;
+        m.faces = (uint32_t *)(O + f.out_index); m.pred = (int *)(S + f.o_pred); m.nvert = (int)f.nvert; m.nface = (int)f.nface;
+        m.progress = &progress;
+        const int rc = corto_walk(m);
+        if (rc) status[fi] = rc == CORTO_TRUNCATED ? UVOL_ERR_TRUNCATED : UVOL_ERR_CORRUPT;
+        __threadfence_block();
+        if (!rc) progress = (int)f.nvert;
+        __threadfence_block();
+        walk_done = 1;
+        return;
+    }
+    // ---- delta reversal of attribute warp - 1
+    const int ai = warp - 1;
+    if (ai >= f.nattr) return;
+    const CortoAttr &a = f.attr[ai];
+    if ((a.kind == CK_NORMAL && a.pred != 0) || k >= a.vN || k >= 4) return;
+    uint32_t *ring = (uint32_t *)(corto_smem + CORTO_RING + (size_t)ai * CORTO_VRING);
+    uint32_t *val = (uint32_t *)(S + a.o_val); const int4 *pred = (const int4 *)(S + f.o_pred);
+    const int n = (int)f.nvert, N = a.vN; const bool par = a.kind != CK_NORMAL && (a.strategy & 1) != 0;
+    if (n > 0) ring[k] = val[k];
+#define CORTO_PARENT(j) ((j) >= i - CORTO_VRING ? ring[((j) & (CORTO_VRING - 1)) * 4 + k] : val[(j) * N + k])
+    int seen = 0;
+    for (int i = 1; i < n;) {
+        while (seen <= i) {                                   // vertex i has its context once progress > i
+            seen = progress;
+            if (seen > i) break;
+            if (walk_done) { seen = progress; if (seen <= i) return; break; }      // the walk ended short of this vertex: a corrupt stream, its status is set
+            __nanosleep(200);
+        }
+        const int hi = seen < n ? seen : n;
+        int4 p = __ldcg(pred + i), p2 = i + 1 < hi ? __ldcg(pred + i + 1) : p;       // (L2 reads: the walk is writing this array)
+        uint32_t c = val[i * N + k], c2 = i + 1 < hi ? val[(i + 1) * N + k] : 0u;
+        for (; i < hi; i++) {
+            const int4 p3 = i + 2 < hi ? __ldcg(pred + i + 2) : p2;       // contexts and corrections are requested two vertices ahead
+            const uint32_t c3 = i + 2 < hi ? val[(i + 2) * N + k] : 0u;
+            uint32_t v = c;
+            if (par) v += CORTO_PARENT(p.x) + CORTO_PARENT(p.y) - CORTO_PARENT(p.z); else v += CORTO_PARENT(p.x);
+            ring[(i & (CORTO_VRING - 1)) * 4 + k] = v;
+            val[i * N + k] = v;
+            p = p2; p2 = p3; c = c2; c2 = c3;
+        }
+    }
+#undef CORTO_PARENT
 }
 
 // Per-value bit widths -> bit offsets -> values (cstream.h:296-362).  grid = (frames, attrs), 256 threads.
@@ -321,36 +376,6 @@ __global__ void __launch_bounds__(256) k_corto_values(const CortoFrame *frames, 
 // or += values[a]; normals with DIFF prediction always use the single parent (normal_attribute.cpp:182-204).  One warp per
 // (frame, attribute), lane k owns component k.  Unsigned arithmetic: colours are decoded modulo 256 (their C++ type is uchar), and
 // sums modulo 2^32 reduce to the same residues.
-// The chain is serial (a vertex's parents are, as a rule, the vertices decoded just before it), so what counts is the latency of the
-// three parent reads: the values of the last CORTO_VRING vertices stay in shared memory (a read of a line this warp has just
-// written would otherwise be a trip to L2 per vertex); older parents -- gates the walk came back to -- are read from the array.
-#define CORTO_VRING 2048
-__global__ void __launch_bounds__(32) k_corto_delta(const CortoFrame *frames, const int32_t *status, uint8_t *S, const CJob *jobs, int njobs) {
-    __shared__ uint32_t ring[CORTO_VRING * 4];
-    const int ji = blockIdx.x, k = threadIdx.x;
-    if (ji >= njobs) return;
-    const CJob jb = jobs[ji];
-    if (frames[jb.frame].status || status[jb.frame]) return;
-    const CortoFrame &f = frames[jb.frame]; const CortoAttr &a = f.attr[jb.what];
-    if (k >= a.vN || k >= 4) return;
-    uint32_t *val = (uint32_t *)(S + a.o_val); const int4 *pred = (const int4 *)(S + f.o_pred);
-    const int n = (int)f.nvert, N = a.vN; const bool par = a.kind != CK_NORMAL && (a.strategy & 1) != 0;
-    if (n > 0) ring[k] = val[k];
-    int4 p = n > 1 ? pred[1] : make_int4(0, 0, 0, 0), p2 = n > 2 ? pred[2] : p;
-    uint32_t c = n > 1 ? val[N + k] : 0u, c2 = n > 2 ? val[2 * N + k] : 0u;
-#define CORTO_PARENT(j) ((j) >= i - CORTO_VRING ? ring[((j) & (CORTO_VRING - 1)) * 4 + k] : val[(j) * N + k])
-    for (int i = 1; i < n; i++) {
-        const int4 p3 = i + 2 < n ? pred[i + 2] : p2;       // contexts and corrections are requested two vertices ahead
-        const uint32_t c3 = i + 2 < n ? val[(i + 2) * N + k] : 0u;
-        uint32_t v = c;
-        if (par) v += CORTO_PARENT(p.x) + CORTO_PARENT(p.y) - CORTO_PARENT(p.z); else v += CORTO_PARENT(p.x);
-        ring[(i & (CORTO_VRING - 1)) * 4 + k] = v;
-        val[i * N + k] = v;
-        p = p2; p2 = p3; c = c2; c2 = c3;
-    }
-#undef CORTO_PARENT
-}
-
 // ---- normal estimation (ESTIMATED / BORDER prediction)
 // corners per vertex.  grid = (ceil(3 * maxF / 256), frames)
 __global__ void __launch_bounds__(256) k_corto_vcount(const CortoFrame *frames, const int32_t *status, uint8_t *S, const uint8_t *O) {
@@ -508,8 +533,8 @@ uint64_t take(uint64_t &cur, uint64_t bytes) { uint64_t o = cur; cur = (cur + by
 
 struct CortoBatch { std::vector<CortoFrame> frames; };
 void uvol_corto_batch_free(CortoBatch *b) { delete b; }
-static const char *kCortoStages[] = {"h2d", "tunstall", "faces", "values", "delta", "estimate", "dequant", "d2h"};
-extern "C" const char *uvol_corto_stage_name(int i) { return (i >= 0 && i < 8) ? kCortoStages[i] : ""; }
+static const char *kCortoStages[] = {"h2d", "tunstall", "values", "faces", "estimate", "dequant", "d2h"};
+extern "C" const char *uvol_corto_stage_name(int i) { return (i >= 0 && i < 7) ? kCortoStages[i] : ""; }
 
 extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int memory, uvol_corto_mesh *out) {
     if (!ctx || !out || n < 0 || (n > 0 && (!data || !size))) return UVOL_ERR_ARG;
@@ -555,8 +580,6 @@ extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data
     aux.push_back(0);
     const int j_tun = 0;
     for (int i = 0; i < n; i++) if (!frames[i].status) { jobs.push_back({(uint32_t)i, 0}); for (int a = 0; a < frames[i].nattr; a++) for (int k = 0; k < frames[i].attr[a].nlogs; k++) jobs.push_back({(uint32_t)i, 1 + 4 * a + k}); }
-    const int j_delta = (int)jobs.size();
-    for (int i = 0; i < n; i++) if (!frames[i].status) for (int a = 0; a < frames[i].nattr; a++) if (frames[i].attr[a].kind != CK_NORMAL || frames[i].attr[a].pred == 0) jobs.push_back({(uint32_t)i, a});
     const int j_end = (int)jobs.size();
     const size_t desc_bytes = sizeof(CortoFrame) * (size_t)n, aux_bytes = aux.size() * 4, job_bytes = sizeof(CJob) * (jobs.size() + 1);
     UVOL_CUDA(ctx, ctx->h_cblob.reserve(blob_bytes + 64)); UVOL_CUDA(ctx, ctx->d_cblob.reserve(blob_bytes + 64));
@@ -582,16 +605,15 @@ extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data
     uint8_t *dS = (uint8_t *)ctx->d_cscratch.p, *dO = (uint8_t *)ctx->d_out_corto.p;
     uint32_t launches = 0;
     auto nb = [](int j) { return (unsigned)((j + CW - 1) / CW); };
-    if (j_delta - j_tun > 0) {
+    if (j_end - j_tun > 0) {
         UVOL_CUDA(ctx, cudaFuncSetAttribute(k_tunstall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TunSmem) * CW)));
-        k_tunstall<<<nb(j_delta - j_tun), 32 * CW, sizeof(TunSmem) * CW, st>>>(dF, dSt, dBlob, dS, dJ + j_tun, j_delta - j_tun); launches++;
+        k_tunstall<<<nb(j_end - j_tun), 32 * CW, sizeof(TunSmem) * CW, st>>>(dF, dSt, dBlob, dS, dJ + j_tun, j_end - j_tun); launches++;
     }
-    stamp();
-    k_corto_faces<<<n, 32, (size_t)CORTO_RING * sizeof(CortoEdge), st>>>(dF, dSt, dBlob, dAux, dS, dO, n); launches++;
     stamp();
     k_corto_values<<<dim3(n, CORTO_MAX_ATTRS), 256, 0, st>>>(dF, dSt, dBlob, dS); launches++;
     stamp();
-    if (j_end - j_delta > 0) { k_corto_delta<<<j_end - j_delta, 32, 0, st>>>(dF, dSt, dS, dJ + j_delta, j_end - j_delta); launches++; }
+    UVOL_CUDA(ctx, cudaFuncSetAttribute(k_corto_faces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CORTO_FACES_SMEM));
+    k_corto_faces<<<n, 32 * (1 + CORTO_MAX_ATTRS), CORTO_FACES_SMEM, st>>>(dF, dSt, dBlob, dAux, dS, dO, n); launches++;
     stamp();
     if (any_est) {
         const dim3 gc((3 * maxF + 255) / 256, n);
