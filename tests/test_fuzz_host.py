@@ -22,6 +22,8 @@ def test_host_parsers_survive_mutations(built, tmp_path):
     p = tmp_path / "uastc_plain.ktx2"; p.write_bytes(plain); seeds.append(str(p))
     small = synth.make_sequence(1, 500, 32, want_textures=False, seed=5)[0][0]
     p = tmp_path / "small.drc"; p.write_bytes(small); seeds.append(str(p))
+    rings, segs = synth.sphere_dims(500); fp, fu, uvs, _ = synth.sphere_topology(rings, segs); pos = synth.sphere_frame(rings, segs, 0.1, 5)
+    p = tmp_path / "tagged.drc"; p.write_bytes(synth.encode_draco(pos, fp, uvs, fu, synth.vertex_normals(pos, fp), tagged=7)); seeds.append(str(p))      # TAGGED symbol scheme: the parser walks the tag runs
     try:
         from test_zstd import Z, compress, corpus
         if Z is not None:

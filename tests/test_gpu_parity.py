@@ -93,6 +93,31 @@ def test_geometry_synthetic(uv, ctx, nverts):
     check_geometry(uv.DRACOLoader(ctx).decode_batch(drc), drc)
 
 
+def _tagged_frames(nverts, masks, qp=11):
+    rings, segs = synth.sphere_dims(nverts); fp, fu, uvs, _ = synth.sphere_topology(rings, segs)
+    out = []
+    for i, mask in enumerate(masks):
+        pos = synth.sphere_frame(rings, segs, i / 30.0, 20260051)
+        out.append(synth.encode_draco(pos, fp, uvs, fu, synth.vertex_normals(pos, fp), qp=qp, tagged=mask))
+    return out
+
+
+@pytest.mark.parametrize("nverts", [60, 3000, 50000])
+def test_geometry_tagged_symbol_scheme(uv, ctx, nverts):
+    """Draco's TAGGED symbol scheme (a bit-length tag per value tuple + raw bit fields; what draco_encoder picks when it estimates
+    fewer bits, e.g. at high quantisation): every attribute kind tagged on its own, all together, and mixed with RAW frames in
+    one batch; 14-bit positions so that tags above 8 bits occur."""
+    blobs = _tagged_frames(nverts, [0, 1, 2, 4, 7, 0, 7]) + _tagged_frames(nverts, [7, 1], qp=14)
+    check_geometry(uv.DRACOLoader(ctx).decode_batch(blobs), blobs)
+    # damaged tagged files fail per item and leave their neighbours alone
+    t = blobs[4]
+    bad = [t[:len(t) // 2], blobs[0], t[:-7], bytes(t[:len(t) - 40]) + bytes(40)]
+    res = uv.DRACOLoader(ctx).decode_batch(bad)
+    assert res[0]["status"] < 0 and res[2]["status"] < 0 and res[1]["status"] == 0
+    assert res[3]["status"] == oracle_draco(bad[3])["status"] or res[3]["status"] < 0
+    check_geometry([res[1]], [bad[1]])
+
+
 @pytest.mark.parametrize("size,layers", [(8, 1), (64, 3), (1024, 7)])
 def test_texture_synthetic(uv, ctx, size, layers):
     blob = synth.encode_etc1s(synth.texture_layers(size, 0, layers, 4))

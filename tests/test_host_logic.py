@@ -52,6 +52,22 @@ def test_draco_core_logic_matches_oracle(built, name):
         assert np.array_equal(e[k].view(np.uint32), o[k].view(np.uint32)), k
 
 
+def test_draco_tagged_scheme_core_logic(built):
+    """TAGGED symbol scheme: parser (tag run walked to its terminal state to locate the bit fields), tag decode and bit-field
+    extraction as the kernels do them, against the oracle; truncated files are errors."""
+    from tools.synth import synth
+    rings, segs = synth.sphere_dims(2000); fp, fu, uvs, _ = synth.sphere_topology(rings, segs)
+    pos = synth.sphere_frame(rings, segs, 0.2, 11); nrm = synth.vertex_normals(pos, fp)
+    for mask, qp in ((1, 11), (2, 11), (4, 11), (7, 14)):
+        blob = synth.encode_draco(pos, fp, uvs, fu, nrm, qp=qp, tagged=mask)
+        e, o = emu_draco(blob), oracle_draco(blob)
+        assert e["status"] == 0 and o["status"] == 0 and np.array_equal(e["index"], o["index"])
+        for k in ("position", "normal", "uv"):
+            assert np.array_equal(e[k].view(np.uint32), o[k].view(np.uint32)), (mask, k)
+        for cut in (len(blob) // 3, len(blob) // 2, len(blob) - 3):
+            assert emu_draco(blob[:cut])["status"] < 0
+
+
 def test_draco_metadata_is_skipped(built):
     """A file with the metadata flag (header bit 15) decodes to the same mesh: the section is walked past by the parser and by the
     oracle (the reference's loader reads no metadata, DRACOLoader.js:470-554); a truncated metadata section is an error."""

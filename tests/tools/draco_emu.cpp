@@ -188,7 +188,21 @@ extern "C" int draco_emu_decode(const uint8_t *data, size_t len, uint32_t *num_p
         if (cum[s.alphabet] != (1u << s.pb)) return UVOL_ERR_CORRUPT;
         for (uint32_t b = 0; b < 256; b++) bucket[b] = (uint16_t)rans_bucket_symbol(cum.data(), s.alphabet, b << (s.pb - 8));
         RansTables t{cum.data(), bucket.data(), s.alphabet, s.pb};
-        rc = rans_decode_run(file + s.data_off, s.data_len, t, n * a.vnc, positive ? 2 : 1, S + f.o_corr[j]); if (rc) return rc;
+        if (!a.tagged) { rc = rans_decode_run(file + s.data_off, s.data_len, t, n * a.vnc, positive ? 2 : 1, S + f.o_corr[j]); if (rc) return rc; }
+        else {      // TAGGED scheme: tags (k_rans, raw symbols) then the bit fields (k_tagged_values)
+            if (f.o_tags[j] == UVOL_NONE) return -78;
+            uint32_t *tags = (uint32_t *)(S + f.o_tags[j]); int32_t *out = (int32_t *)(S + f.o_corr[j]);
+            rc = rans_decode_run(file + s.data_off, s.data_len, t, n, 2, tags); if (rc) return rc;
+            const uint8_t *bits = file + a.tag_bits_off; uint64_t off = 0; const uint64_t total = 8ull * a.tag_bits_len;
+            for (uint32_t e = 0; e < n; e++) {
+                const uint32_t tg = tags[e]; if (tg > 32 || off + (uint64_t)tg * a.vnc > total) return UVOL_ERR_CORRUPT;
+                for (int c = 0; c < a.vnc; c++, off += tg) {
+                    uint64_t x = 0; for (int k = 0; k < 5 && (off >> 3) + k < (uint64_t)a.tag_bits_len; k++) x |= (uint64_t)bits[(off >> 3) + k] << (8 * k);
+                    const uint32_t v = tg == 0 ? 0u : (uint32_t)(x >> (off & 7)) & (tg == 32 ? 0xffffffffu : ((1u << tg) - 1u));
+                    out[e * a.vnc + c] = positive ? (int32_t)v : ((v & 1u) ? -(int32_t)(v >> 1) - 1 : (int32_t)(v >> 1));
+                }
+            }
+        }
         if (a.pred == 5 || a.pred == 6) {
             RabsLane r; if (!rabs_lane_init(r, file, a.aux_bits)) return UVOL_ERR_CORRUPT;
             if (a.pred == 5) { if ((uint32_t)a.num_orient > n) return UVOL_ERR_CORRUPT; emu_rabs_bits(r, S + f.o_auxbits[j], (uint32_t)a.num_orient, true); }

@@ -58,11 +58,9 @@ void write_rabs(Bytes &out, const std::vector<uint8_t> &bits) {
     put_u8(out, p0); put_varint(out, buf.size()); put_bytes(out, buf);
 }
 
-// ---- RAW rANS symbol run: scheme u8=1, max_bit_length u8, probability table, size varint, data (A.2)
-void write_symbols_raw(Bytes &out, const std::vector<uint32_t> &syms) {
+// ---- rANS symbol run body: probability table (alphabet = max symbol + 1, normalised to 2^pb), size varint, data (A.2)
+void write_rans_run(Bytes &out, const std::vector<uint32_t> &syms, int pb) {
     uint32_t maxs = 0; for (uint32_t s : syms) maxs = std::max(maxs, s);
-    int mbl = 1; while ((1u << mbl) <= maxs) mbl++;
-    int pb = (3 * mbl) / 2; pb = pb < 12 ? 12 : (pb > 20 ? 20 : pb);
     const uint32_t prec = 1u << pb, A = maxs + 1;
     std::vector<uint64_t> freq(A, 0); for (uint32_t s : syms) freq[s]++;
     // normalise to `prec` keeping every used symbol >= 1
@@ -83,7 +81,6 @@ void write_symbols_raw(Bytes &out, const std::vector<uint32_t> &syms) {
         if (!moved) break;
     }
     std::vector<uint32_t> cum(A + 1, 0); for (uint32_t i = 0; i < A; i++) cum[i + 1] = cum[i] + prob[i];
-    put_u8(out, 1); put_u8(out, (uint32_t)mbl);
     put_varint(out, A);
     for (uint32_t i = 0; i < A;) {
         if (prob[i] == 0) { uint32_t run = 0; while (i + run < A && prob[i + run] == 0 && run < 64) run++; put_u8(out, ((run - 1) << 2) | 3); i += run; }
@@ -107,6 +104,40 @@ void write_symbols_raw(Bytes &out, const std::vector<uint32_t> &syms) {
     else if (state < (1u << 22)) { const uint32_t v = (2u << 22) + (uint32_t)state; buf.push_back(v & 255); buf.push_back((v >> 8) & 255); buf.push_back(v >> 16); }
     else { const uint32_t v = (3u << 30) + (uint32_t)state; for (int k = 0; k < 4; k++) buf.push_back((v >> (8 * k)) & 255); }
     put_varint(out, buf.size()); put_bytes(out, buf);
+}
+
+// ---- RAW scheme: scheme u8=1, max_bit_length u8, then the run with precision (3 * max_bit_length) / 2 clamped to [12, 20]
+void write_symbols_raw(Bytes &out, const std::vector<uint32_t> &syms) {
+    uint32_t maxs = 0; for (uint32_t s : syms) maxs = std::max(maxs, s);
+    int mbl = 1; while ((1u << mbl) <= maxs) mbl++;
+    int pb = (3 * mbl) / 2; pb = pb < 12 ? 12 : (pb > 20 ? 20 : pb);
+    put_u8(out, 1); put_u8(out, (uint32_t)mbl);
+    write_rans_run(out, syms, pb);
+}
+
+// ---- TAGGED scheme (draco::EncodeTaggedSymbols): scheme u8=0, a 12-bit-precision run of one TAG per value tuple (the bit length
+// that holds every component of the tuple, at least 1), then the components themselves as raw LSB-first bit fields, byte padded.
+void write_symbols_tagged(Bytes &out, const std::vector<uint32_t> &syms, int nc) {
+    std::vector<uint32_t> tags(syms.size() / (size_t)nc);
+    for (size_t i = 0; i < tags.size(); i++) {
+        uint32_t m = 1; for (int c = 0; c < nc; c++) m = std::max(m, syms[i * nc + c]);
+        int bl = 1; while (bl < 32 && (m >> bl) != 0) bl++;
+        tags[i] = (uint32_t)bl;
+    }
+    put_u8(out, 0);
+    write_rans_run(out, tags, 12);
+    Bytes bits; uint64_t acc = 0; int have = 0;
+    for (size_t i = 0; i < tags.size(); i++) for (int c = 0; c < nc; c++) {
+        acc |= (uint64_t)syms[i * nc + c] << have; have += (int)tags[i];
+        while (have >= 8) { bits.push_back((uint8_t)(acc & 255)); acc >>= 8; have -= 8; }
+    }
+    if (have > 0) bits.push_back((uint8_t)(acc & 255));
+    put_bytes(out, bits);
+}
+// which attributes use the TAGGED scheme (bit 0 position, 1 uv, 2 normal): a generator switch for the parity tests
+int g_tagged_mask = 0;
+void write_symbols(Bytes &out, const std::vector<uint32_t> &syms, int nc, int which) {
+    if (g_tagged_mask & (1 << which)) write_symbols_tagged(out, syms, nc); else write_symbols_raw(out, syms);
 }
 
 uint32_t zigzag_sym(int32_t v) { return v >= 0 ? (uint32_t)v << 1 : (((uint32_t)(-(v + 1))) << 1) | 1u; }
@@ -342,16 +373,16 @@ extern "C" size_t uvsynth_draco_encode(const float *pos, uint32_t nv, const uint
     put_varint(b, 1); put_u8(b, 3); put_u8(b, 9); put_u8(b, 2); put_u8(b, 0); put_varint(b, 1); put_u8(b, 2);   // TEX_COORD f32x2, QUANTIZATION
     put_varint(b, 1); put_u8(b, 1); put_u8(b, 9); put_u8(b, 3); put_u8(b, 0); put_varint(b, 2); put_u8(b, 3);   // NORMAL f32x3, NORMALS
     // decoder 0 portable data + transform data
-    put_u8(b, 1); put_u8(b, 1); put_u8(b, 1); write_symbols_raw(b, possym); put_u32(b, (uint32_t)pwmin); put_u32(b, (uint32_t)pwmax);
+    put_u8(b, 1); put_u8(b, 1); put_u8(b, 1); write_symbols(b, possym, 3, 0); put_u32(b, (uint32_t)pwmin); put_u32(b, (uint32_t)pwmax);
     for (int k = 0; k < 3; k++) put_f32(b, pmin[k]);
     put_f32(b, prange); put_u8(b, (uint32_t)qp);
     // decoder 1
-    put_u8(b, 5); put_u8(b, 1); put_u8(b, 1); write_symbols_raw(b, uvsym);
+    put_u8(b, 5); put_u8(b, 1); put_u8(b, 1); write_symbols(b, uvsym, 2, 1);
     put_u32(b, (uint32_t)orient_bits.size()); write_rabs(b, orient_bits); put_u32(b, (uint32_t)uwmin); put_u32(b, (uint32_t)uwmax);
     for (int k = 0; k < 2; k++) put_f32(b, umin[k]);
     put_f32(b, urange); put_u8(b, (uint32_t)qt);
     // decoder 2
-    put_u8(b, 6); put_u8(b, 3); put_u8(b, 1); write_symbols_raw(b, nrmsym);
+    put_u8(b, 6); put_u8(b, 3); put_u8(b, 1); write_symbols(b, nrmsym, 2, 2);
     put_u32(b, (uint32_t)MAXQ); put_u32(b, (uint32_t)CEN); write_rabs(b, flipbits);
     put_u8(b, (uint32_t)qn);
     *out_buf = (uint8_t *)malloc(b.size() + 16);
@@ -360,3 +391,4 @@ extern "C" size_t uvsynth_draco_encode(const float *pos, uint32_t nv, const uint
 }
 
 extern "C" void uvsynth_free(void *p) { free(p); }
+extern "C" void uvsynth_draco_tagged(int mask) { g_tagged_mask = mask; }

@@ -105,8 +105,10 @@ def vertex_normals(pos, faces):
     return n.astype(np.float32)
 
 
-def encode_draco(pos, faces_pos, uv, faces_uv, nrm, qp=11, qt=10, qn=8):
+def encode_draco(pos, faces_pos, uv, faces_uv, nrm, qp=11, qt=10, qn=8, tagged=0):
+    """tagged: bit mask of the attributes written with Draco's TAGGED symbol scheme (1 position, 2 uv, 4 normal) instead of RAW."""
     L = lib()
+    L.uvsynth_draco_tagged(int(tagged))
     pos = np.ascontiguousarray(pos, np.float32); uv = np.ascontiguousarray(uv, np.float32); nrm = np.ascontiguousarray(nrm, np.float32)
     fp = np.ascontiguousarray(faces_pos, np.uint32); fu = np.ascontiguousarray(faces_uv, np.uint32)
     out = ctypes.POINTER(ctypes.c_uint8)()
@@ -117,6 +119,7 @@ def encode_draco(pos, faces_pos, uv, faces_uv, nrm, qp=11, qt=10, qn=8):
         raise RuntimeError("uvsynth_draco_encode failed (input must be one closed manifold genus-0 component)")
     blob = ctypes.string_at(out, n)
     L.uvsynth_free(out)
+    L.uvsynth_draco_tagged(0)
     return blob
 
 

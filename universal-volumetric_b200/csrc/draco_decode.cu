@@ -105,13 +105,16 @@ __global__ void __launch_bounds__(128) k_rans(const DracoFrame *frames, DracoCou
     else {
         const int j = jb.what - 16; const DracoAttr &a = f.attr[j];
         s = a.sym;
-        mode = (a.pred != -2 && (a.xform == 2 || a.xform == 3)) ? 2 : 1;
-        out = scratch + f.o_corr[j];
-        if (early) { count = f.corr_cap[j]; if (lane == 0) counts[jb.frame].rans_early[j] = 0xffffffffu; }
+        // TAGGED scheme: the run holds one bit-length tag per entry (raw symbols into o_tags; k_tagged_values reads the components)
+        const bool tg = a.tagged != 0;
+        mode = (tg || (a.pred != -2 && (a.xform == 2 || a.xform == 3))) ? 2 : 1;
+        out = scratch + (tg ? f.o_tags[j] : f.o_corr[j]);
+        const uint32_t cap = tg ? f.table_cap[a.table + 1] : f.corr_cap[j];
+        if (early) { count = cap; if (lane == 0) counts[jb.frame].rans_early[j] = 0xffffffffu; }
         else {
-            count = counts[jb.frame].expected[a.table + 1] * (uint32_t)a.vnc;
+            count = counts[jb.frame].expected[a.table + 1] * (tg ? 1u : (uint32_t)a.vnc);
             if (counts[jb.frame].rans_early[j] == count) return;               // the early run already produced exactly these symbols, in place
-            if (count > f.corr_cap[j]) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_FRAME_CAPACITY); return; }
+            if (count > cap) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_FRAME_CAPACITY); return; }
         }
     }
     // Tables in shared memory (built by the whole warp): cs[k] = {first slot, frequency, symbol} of the k-th symbol with a
@@ -175,6 +178,55 @@ __global__ void __launch_bounds__(128) k_rans(const DracoFrame *frames, DracoCou
         counts[jb.frame].rans_early[jb.what - 16] = got;
     } else if (!wide) { if (mode == 0) rans_walk<0, false, false>(r, count, out); else if (mode == 1) rans_walk<1, false, false>(r, count, out); else rans_walk<2, false, false>(r, count, out); }
     else { if (mode == 0) rans_walk<0, true, false>(r, count, out); else if (mode == 1) rans_walk<1, true, false>(r, count, out); else rans_walk<2, true, false>(r, count, out); }
+}
+
+// TAGGED symbol scheme, second half (draco::DecodeTaggedSymbols): the tags k_rans decoded (one bit length per entry) -> exclusive prefix
+// sum -> every entry's bit offset -> its components, read as LSB-first bit fields from the bytes behind the tag run and converted
+// like RAW symbols (zig-zag unless the transform yields positive corrections).  grid = (frames, attributes), 256 threads.
+__global__ void __launch_bounds__(256) k_tagged_values(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, uint8_t *S) {
+    __shared__ unsigned long long wsum[8], carry_s;
+    const uint32_t fi = blockIdx.x, j = blockIdx.y;
+    if (frame_dead(frames, counts, fi)) return;
+    const DracoFrame &f = frames[fi];
+    if ((int)j >= f.nattr || f.o_tags[j] == UVOL_NONE || f.o_corr[j] == UVOL_NONE) return;
+    const DracoAttr &a = f.attr[j];
+    const uint32_t n = counts[fi].expected[a.table + 1], nc = (uint32_t)a.vnc;
+    if (n > f.table_cap[a.table + 1]) { if (threadIdx.x == 0) frame_fail(counts, fi, UVOL_ERR_FRAME_CAPACITY); return; }
+    const uint32_t *tags = (const uint32_t *)(S + f.o_tags[j]); int32_t *out = (int32_t *)(S + f.o_corr[j]);
+    const uint8_t *bits = blob + f.file_off + a.tag_bits_off; const unsigned long long total = 8ull * a.tag_bits_len;
+    const bool positive = a.pred != -2 && (a.xform == 2 || a.xform == 3);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    bool bad = false;
+    for (uint32_t base = 0; base < n; base += 256) {
+        const uint32_t e = base + tid;
+        uint32_t t = e < n ? tags[e] : 0u;
+        if (t > 32u) { bad = true; t = 0; }
+        unsigned long long inc = (unsigned long long)t * nc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        unsigned long long before = carry_s;
+        for (int k = 0; k < w; k++) before += wsum[k];
+        const unsigned long long off = before + inc - (unsigned long long)t * nc;
+        if (e < n) {
+            if (off + (unsigned long long)t * nc > total) bad = true;
+            else for (uint32_t c = 0; c < nc; c++) {
+                const unsigned long long p = off + (unsigned long long)c * t; const uint8_t *b = bits + (p >> 3);
+                unsigned long long x = 0;                                     // (the blob is padded: five bytes are always readable)
+#pragma unroll
+                for (int k = 0; k < 5; k++) x |= (unsigned long long)b[k] << (8 * k);
+                const uint32_t v = t == 0 ? 0u : (uint32_t)(x >> (p & 7)) & (t == 32 ? 0xffffffffu : ((1u << t) - 1u));
+                out[e * nc + c] = positive ? (int32_t)v : ((v & 1u) ? -(int32_t)(v >> 1) - 1 : (int32_t)(v >> 1));
+            }
+        }
+        __syncthreads();
+        if (tid == 255) carry_s = before + inc;
+        __syncthreads();
+    }
+    if (bad) frame_fail(counts, fi, UVOL_ERR_CORRUPT);
 }
 
 // rABS bit runs, one run per lane.  what: 0..3 = seam bits of attribute data i (upper bound 3F/2+1 bits); 16+j = attribute j aux
@@ -1145,7 +1197,7 @@ struct GeoBatch {
     std::vector<DracoFrame> frames; std::vector<uint32_t> aux; std::vector<Job> jobs;
     int n = 0, j_ransA = 0, j_rabsA = 0, j_trav = 0, j_ransB = 0, j_rabsB = 0, j_wrap = 0, j_uv = 0, j_end = 0;
     uint32_t max_alpha_ctx = 1, max_alpha_attr = 1, maxnad = 0, maxV = 0, maxF = 0; int maxattr = 0;
-    uint64_t blob_bytes = 0, bytes_in = 0; DracoPlan pl; double parse_ms = 0; bool any_valence = false, any_standard = false;
+    uint64_t blob_bytes = 0, bytes_in = 0; DracoPlan pl; double parse_ms = 0; bool any_valence = false, any_standard = false, any_tagged = false;
     uint64_t cap_s2 = 0, cap_z2 = 0, cap_out = 0;        // what this batch may use of the count-sized arenas (estimates, or the exact needs after a re-plan)
     uint32_t replans = 0;
 };
@@ -1175,7 +1227,7 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
     if (!ctx->geo) ctx->geo = new GeoBatch();
     GeoBatch &B = *ctx->geo;
     B.n = n; B.frames.assign((size_t)n, DracoFrame()); B.aux.clear(); B.aux.reserve((size_t)n * 2048); B.jobs.clear();
-    B.max_alpha_ctx = B.max_alpha_attr = 1; B.maxnad = B.maxV = B.maxF = 0; B.maxattr = 0; B.bytes_in = 0; B.any_valence = B.any_standard = false; B.replans = 0;
+    B.max_alpha_ctx = B.max_alpha_attr = 1; B.maxnad = B.maxV = B.maxF = 0; B.maxattr = 0; B.bytes_in = 0; B.any_valence = B.any_standard = B.any_tagged = false; B.replans = 0;
     std::vector<DracoFrame> &frames = B.frames; std::vector<uint32_t> &aux = B.aux;
     uint64_t blob_bytes = 0;
     for (int i = 0; i < n; i++) {
@@ -1188,6 +1240,7 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
         if (!f.status && ((uint64_t)f.nf > ctx->cfg.max_faces_per_frame || (uint64_t)f.nf > 4096 + 64ull * size[i])) f.status = UVOL_ERR_UNSUPPORTED;
         if (f.status) continue;
         if (f.trav == 2) B.any_valence = true; else B.any_standard = true;
+        for (int j = 0; j < f.nattr; j++) if (f.attr[j].tagged) B.any_tagged = true;
         for (int k = 0; k < 6; k++) if (f.ctx[k].count && f.ctx[k].nnz > B.max_alpha_ctx) B.max_alpha_ctx = f.ctx[k].nnz;      // (table sizes follow the used symbols)
         for (int j = 0; j < f.nattr; j++) {
             if (f.attr[j].sym.nnz > 8192) { f.status = UVOL_ERR_UNSUPPORTED; break; }
@@ -1387,6 +1440,7 @@ static int draco_enqueue(uvol_ctx *ctx, int memory, bool first_attempt_of_fresh_
         const int nrj = B.j_rabsB - B.j_ransB;
         k_rans<<<nblk(nrj), 32, rans_smem(B.max_alpha_attr, lbB, 1), st>>>(dF, dC, dBlob, dAux, dS, dJ + B.j_ransB, nrj, rans_words(B.max_alpha_attr, lbB), 0, lbB); launches++;
     }
+    if (B.any_tagged) { k_tagged_values<<<dim3((unsigned)n, (unsigned)B.maxattr), 256, 0, st>>>(dF, dC, dBlob, dS); launches++; }
     stamp("rans_recheck");
     UVOL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sync_ev[3], 0));
     stamp("rans_attr(s1)"); i_rans = ev - 2;                                     // (stage slots of rans_attr / rabs_aux: timed on s1)

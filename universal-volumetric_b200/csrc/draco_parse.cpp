@@ -48,13 +48,8 @@ bool skip_metadata(Rd &r, int depth) {
     return true;
 }
 
-// DecodeSymbols header: scheme, [max_bit_length], probability table, byte run.  Only RAW can be
-// located without decoding it; TAGGED needs the decoded tags to find its end -> unsupported here.
-int read_symbols(Rd &r, RansStream &s, std::vector<uint32_t> &aux) {
-    uint8_t scheme = r.u8();
-    if (r.err) return UVOL_ERR_TRUNCATED;
-    if (scheme != 1) return UVOL_ERR_UNSUPPORTED;
-    uint8_t mbl = r.u8();
+// Probability table of a rANS symbol run (alphabet size varint, then one token per symbol or zero run), appended to `aux`.
+int read_prob_table(Rd &r, RansStream &s, std::vector<uint32_t> &aux) {
     uint64_t n = r.varint();
     if (r.err || n == 0 || n > (1u << 20)) return UVOL_ERR_CORRUPT;
     s.alphabet = (uint32_t)n; s.prob_off = (uint32_t)aux.size();
@@ -66,12 +61,58 @@ int read_symbols(Rd &r, RansStream &s, std::vector<uint32_t> &aux) {
         if (tok == 3) { uint32_t run = (d >> 2) + 1; if (i + run > n) return UVOL_ERR_CORRUPT; i += run; }
         else { uint32_t pr = d >> 2; for (unsigned k = 0; k < tok; k++) pr |= (uint32_t)r.u8() << (8 * (k + 1) - 2); prob[i++] = pr; }
     }
-    int pb = (3 * mbl) / 2; if (pb < 12) pb = 12; if (pb > 20) pb = 20;
-    s.pb = (uint32_t)pb;
     s.nnz = 0; for (uint32_t i = 0; i < n; i++) s.nnz += aux[s.prob_off + i] != 0;
+    return UVOL_OK;
+}
+
+// The TAGGED scheme stores no length for its raw bit fields: they end where the tags say.  To find the data that follows (the
+// prediction parameters of this attribute, every later attribute), the parser walks the tag run once -- to the coder's terminal
+// state, the tag count is not in the file either -- and adds up the bit lengths.  This locates bytes; the tags the decode uses are
+// decoded again on the device with everything else.  false: not a valid run (or more tags than the mesh has corners).
+bool sum_tags(const uint8_t *data, uint32_t nbytes, const uint32_t *prob, uint32_t alphabet, uint32_t pb, uint64_t max_tags, uint64_t *ntags, uint64_t *sum) {
+    *ntags = 0; *sum = 0;
+    const uint32_t prec = 1u << pb, lbase = prec * 4u;
+    if (alphabet > 64 || nbytes == 0) return false;                 // a tag is a bit length: 0..32
+    uint32_t cum[65]; cum[0] = 0;
+    for (uint32_t i = 0; i < alphabet; i++) { if (prob[i] > prec) return false; cum[i + 1] = cum[i] + prob[i]; }
+    if (cum[alphabet] != prec) return false;
+    const unsigned k = (data[nbytes - 1] >> 6) + 1u;
+    if (nbytes < k) return false;
+    uint32_t st = 0; for (unsigned i = 0; i < k; i++) st |= (uint32_t)data[nbytes - k + i] << (8 * i);
+    st = (st & ((1u << (8 * k - 2)) - 1u)) + lbase;
+    uint32_t off = nbytes - k;
+    for (;;) {
+        while (st < lbase && off > 0) st = st * 256u + data[--off];
+        if (off == 0 && st == lbase) return true;
+        if (*ntags >= max_tags) return false;
+        const uint32_t q = st >> pb, rem = st & (prec - 1);
+        uint32_t sy = 0; while (cum[sy + 1] <= rem) sy++;
+        st = q * prob[sy] + rem - cum[sy];
+        if (sy > 32) return false;
+        *sum += sy; ++*ntags;
+    }
+}
+
+// DecodeSymbols header: scheme, then RAW (max_bit_length, probability table, byte run) or TAGGED (probability table of the tags, byte
+// run, raw bit fields: located by walking the tags, see above).  nc = components per value tuple; tagged = null: RAW only.
+int read_symbols(Rd &r, RansStream &s, std::vector<uint32_t> &aux, int nc = 1, uint64_t max_tuples = 0, DracoAttr *tagged = nullptr) {
+    uint8_t scheme = r.u8();
+    if (r.err) return UVOL_ERR_TRUNCATED;
+    if (scheme > 1 || (scheme == 0 && !tagged)) return UVOL_ERR_UNSUPPORTED;
+    int pb = 12;
+    if (scheme == 1) { const uint8_t mbl = r.u8(); pb = (3 * mbl) / 2; if (pb < 12) pb = 12; if (pb > 20) pb = 20; }
+    int rc = read_prob_table(r, s, aux); if (rc) return rc;
+    s.pb = (uint32_t)pb;
     uint64_t nb = r.varint();
     if (r.err || nb > r.n - r.p) return UVOL_ERR_TRUNCATED;
     s.data_off = (uint32_t)r.p; s.data_len = (uint32_t)nb; r.p += nb;
+    if (scheme == 0) {
+        uint64_t ntags, sum;
+        if (!sum_tags(r.b + s.data_off, s.data_len, aux.data() + s.prob_off, s.alphabet, s.pb, max_tuples, &ntags, &sum)) return UVOL_ERR_CORRUPT;
+        const uint64_t bytes = (sum * (uint64_t)nc + 7) >> 3;
+        if (bytes > r.n - r.p) return UVOL_ERR_TRUNCATED;
+        tagged->tagged = 1; tagged->tag_bits_off = (uint32_t)r.p; tagged->tag_bits_len = (uint32_t)bytes; r.p += bytes;
+    }
     return UVOL_OK;
 }
 }  // namespace
@@ -169,7 +210,7 @@ int uvol_draco_parse(const uint8_t *data, size_t len, DracoFrame &f, std::vector
             int compressed = r.u8();
             if (r.err) return UVOL_ERR_TRUNCATED;
             if (!compressed) return UVOL_ERR_UNSUPPORTED;     // raw ints need the entry count to be skipped
-            int rc = read_symbols(r, a.sym, aux); if (rc) return rc;
+            int rc = read_symbols(r, a.sym, aux, a.vnc, 3ull * f.nf + 8, &a); if (rc) return rc;
             a.sym.count = 0xFFFFFFFFu;
             if (a.pred == -2) { /* no prediction data */ }
             else if (a.pred == 0 || a.pred == 1) {

@@ -64,13 +64,14 @@ static inline void draco_plan_phase1(std::vector<DracoFrame> &frames, DracoPlan 
         f.o_lmc = plan_take(s, maxv * 4); f.o_hole = plan_take(s, maxv);
         for (uint32_t i = 0; i < f.nad; i++) f.o_ac2v[i] = plan_take(s, C * 4);
         f.o_seamcnt = plan_take(s, (C / 8192 + 2) * 4);      // SEAM_CHUNK corners per count
-        for (int j = 0; j < UVOL_MAX_ATTRS; j++) { f.o_corr[j] = f.o_par[j] = f.o_auxbits[j] = UVOL_NONE; f.corr_cap[j] = 0; }
+        for (int j = 0; j < UVOL_MAX_ATTRS; j++) { f.o_corr[j] = f.o_par[j] = f.o_auxbits[j] = f.o_tags[j] = UVOL_NONE; f.corr_cap[j] = 0; }
         for (int j = 0; j < f.nattr; j++) {
             const DracoAttr &a = f.attr[j];
             if (!draco_attr_needed(f, j)) continue;
             const uint64_t cap = (uint64_t)f.table_cap[a.table + 1] * (uint64_t)a.vnc;
             f.corr_cap[j] = (uint32_t)cap; f.o_corr[j] = plan_take(s, (cap + 4) * 4);
             if (a.pred == 5 || a.pred == 6) f.o_auxbits[j] = plan_take(s, (uint64_t)f.table_cap[a.table + 1] + 8);
+            if (a.tagged) f.o_tags[j] = plan_take(s, ((uint64_t)f.table_cap[a.table + 1] + 4) * 4);
         }
         // ---- union region
         const uint64_t U = s;

@@ -41,6 +41,7 @@ struct DracoAttr {
     int32_t wmin, wmax;                       // WRAP bounds, or (max_q, center) for octahedron
     RabsStream aux_bits;                      // TEX_COORDS orientations / GEOMETRIC_NORMAL flips
     int32_t num_orient;
+    uint32_t tagged, tag_bits_off, tag_bits_len;   // TAGGED symbol scheme: `sym` is the run of per-entry bit-length tags, the raw bit fields follow it in the file
     float qmin[4]; float qrange; int32_t qbits;
     int32_t out_slot;                         // 0 position 1 normal 2 uv 3 color, -1 not exported
 };
@@ -64,6 +65,7 @@ struct DracoFrame {
     uint64_t o_frec[UVOL_MAX_ATTR_DATA + 1], o_tstack[UVOL_MAX_ATTR_DATA + 1], o_fvis[UVOL_MAX_ATTR_DATA + 1];   // S, S, Z
     uint64_t o_corr[UVOL_MAX_ATTRS], o_par[UVOL_MAX_ATTRS], o_auxbits[UVOL_MAX_ATTRS];      // S.  Values are reconstructed IN PLACE over the corrections.
     uint32_t corr_cap[UVOL_MAX_ATTRS];     // capacity of o_corr[j] in symbols
+    uint64_t o_tags[UVOL_MAX_ATTRS];       // S: decoded tags (int32 per entry) of attributes coded with the TAGGED scheme
     uint32_t table_cap[UVOL_MAX_ATTR_DATA + 1];   // capacity in entries of table t (attribute vertices); [0] = encoded vertices + splits (exact bound)
     // ---- count-sized arenas S2 / Z2 (zeroed) and the attribute part of the output arena: byte offsets filled ON THE DEVICE by
     // k_plan2 once the connectivity kernels have produced the counts (and recomputed by the host from the final counts)
