@@ -214,7 +214,8 @@ def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex, fmt, target="
         "predict_wrap": frames * (V * 16 + 2 * V * 12),                       # parents + corrections in, values out
         "predict_uv": frames * P * (32 + 8 + 8),
         "normals": frames * V * (8 + 8 + 7 * 12),
-        "expand": frames * (P * 4 + P * 3 * 8 + P * 28 + P * 32),              # p2c + (corner->vertex, vertex->entry) x 3 + 28 B of int values in, 32 B/point out
+        "expand_pnc": frames * (P * 4 + P * 2 * 8 + P * 20 + P * 24),          # positions + normals: p2c + (corner->vertex, vertex->entry) x 2 + 20 B of int values in, 24 B/point out
+        "expand": frames * (P * 4 + P * 8 + P * 8 + P * 8),                    # uv: p2c + one table walk + 8 B of int values in, 8 B/point out
         "seams": frames * (3 * F * 4 + 2 * 3 * F),
         "attr_tables": frames * 2 * (3 * F * 4 + 3 * F * 4),
         "point_assign": frames * (3 * F * 4 * 3),

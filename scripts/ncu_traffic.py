@@ -30,6 +30,8 @@ def num(r, name, scale_bytes=False):
         v = float(r[i].replace(",", ""))
     except ValueError:
         v = 0.0
+    if v != v:          # "nan": the metric was not collected for this launch
+        v = 0.0
     if scale_bytes:
         u = units[i].lower()
         v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(u, 1.0)
