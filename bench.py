@@ -517,9 +517,9 @@ def main():
     if with_gather:
         G = M["G"]
         # every rank must now hold the same bytes: compare a checksum of the gathered arena across ranks
-        ssum = G["arena"][: G["arena"].numel() // 8 * 8].view(torch.int64).sum().reshape(1)
+        ssum = G["arena"][: G["used"] // 8 * 8].view(torch.int64).sum().reshape(1)
         lo, hi = ssum.clone(), ssum.clone(); dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        gather_info = {"what": "whole decoded shard of every rank (geometry index / position / normal / uv + texture layers), gather.all_gather_shard: per-rank sized broadcasts from the library's device buffers",
+        gather_info = {"what": "whole decoded shard of every rank (geometry index / position / normal / uv + texture layers), gather.all_gather_shard: one in-place NCCL all-gather over equal slots of a torch-owned arena (own spans copied in from the library's device buffers)",
                        "bytes_received_per_gpu": int(sum(G["bytes"]) - G["bytes"][rank]), "bytes_total": int(sum(G["bytes"])), "all_ranks_identical": bool(torch.equal(lo, hi))}
     dev_ms, gat_ms, e2e_s = maxr(M["dev_ms"], M["gat_ms"], M["e2e_s"])
     P_all, F_all, tex_all, bin_g, bin_t, bout_g, bout_t, bout_g2, bout_t2, launches_all = sumr(M["P_total"], M["F_total"], M["texels"], M["sg"]["bytes_in"], M["st"]["bytes_in"], M["sg"]["bytes_out"], M["st"]["bytes_out"],

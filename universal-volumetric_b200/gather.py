@@ -180,8 +180,8 @@ def shard_tables(geo, n_geo, tex, n_tex):
 
 def all_gather_shard(geo, n_geo, tex, n_tex, device, group=None, arena=None):
     """Gathers every rank's decoded shard on every rank.  Returns dict(gtabs=[world][n, GCOLS], ttabs=[world][n, TCOLS], arena=uint8 tensor
-    on `device`, geo_off=[world], tex_off=[world], bytes=[world]): rank r's geometry span starts at arena[geo_off[r]], its texture span at
-    arena[tex_off[r]].  `arena` (optional) is a caller-owned receive buffer that is reused when large enough."""
+    on `device`, used=bytes of the arena in use, geo_off=[world], tex_off=[world], bytes=[world]): rank r's geometry span starts at
+    arena[geo_off[r]], its texture span at arena[tex_off[r]].  `arena` (optional) is a caller-owned receive buffer that is reused when large enough."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -200,20 +200,34 @@ def all_gather_shard(geo, n_geo, tex, n_tex, device, group=None, arena=None):
     gtabs = [tabs[r][: metas[r][0] * GCOLS].reshape(-1, GCOLS) for r in range(world)]
     ttabs = [tabs[r][mg * GCOLS: mg * GCOLS + metas[r][1] * TCOLS].reshape(-1, TCOLS) for r in range(world)]
     al = lambda v: (v + 255) // 256 * 256
-    geo_off, tex_off, cur = [], [], 0
-    for m in metas:
-        geo_off.append(cur); cur += al(m[2]); tex_off.append(cur); cur += al(m[3])
-    if arena is None or arena.numel() < cur:
-        arena = torch.empty(cur, dtype=torch.uint8, device=device)
-    for r in range(world):          # all-gather with per-rank sizes: the owner sends straight from the library's buffers
-        for off, nb, base in ((geo_off[r], metas[r][2], gb), (tex_off[r], metas[r][3], tb)):
-            if nb == 0:
-                continue
-            slot = arena[off: off + nb]
-            if r == rank:
-                slot.copy_(arena_tensor(base, nb, device))          # own span: one device copy out of the library's buffer into its slot (the collective then
-            dist.broadcast(slot, src=dist.get_global_rank(group, r) if group is not None else r, group=group)      # runs on torch-owned memory only)
-    return {"gtabs": gtabs, "ttabs": ttabs, "arena": arena, "geo_off": geo_off, "tex_off": tex_off, "bytes": [m[2] + m[3] for m in metas], "cuda": cuda}
+    if cuda:
+        # NCCL: ONE all-gather over equal slots (a slot = the largest rank's geometry span + texture span; shards of one sequence differ
+        # by at most one segment, so the padding is under 1 %).  Every rank copies its two spans out of the library's buffers into its
+        # own slot of the receive arena -- the collective then runs in place on torch-owned memory, all links busy in both directions.
+        slot = max(al(m[2]) + al(m[3]) for m in metas)
+        geo_off = [r * slot for r in range(world)]; tex_off = [r * slot + al(metas[r][2]) for r in range(world)]; cur = world * slot
+        if arena is None or arena.numel() < cur:
+            arena = torch.empty(cur, dtype=torch.uint8, device=device)
+        for off, nb, base in ((geo_off[rank], gn, gb), (tex_off[rank], tn, tb)):
+            if nb:
+                arena[off: off + nb].copy_(arena_tensor(base, nb, device))
+        if slot:
+            dist.all_gather_into_tensor(arena[:cur], arena[rank * slot: (rank + 1) * slot], group=group)
+    else:
+        geo_off, tex_off, cur = [], [], 0
+        for m in metas:
+            geo_off.append(cur); cur += al(m[2]); tex_off.append(cur); cur += al(m[3])
+        if arena is None or arena.numel() < cur:
+            arena = torch.empty(cur, dtype=torch.uint8, device=device)
+        for r in range(world):          # host backends (gloo, the CPU tests): per-rank sized broadcasts
+            for off, nb, base in ((geo_off[r], metas[r][2], gb), (tex_off[r], metas[r][3], tb)):
+                if nb == 0:
+                    continue
+                slot = arena[off: off + nb]
+                if r == rank:
+                    slot.copy_(arena_tensor(base, nb, device))
+                dist.broadcast(slot, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    return {"gtabs": gtabs, "ttabs": ttabs, "arena": arena, "used": cur, "geo_off": geo_off, "tex_off": tex_off, "bytes": [m[2] + m[3] for m in metas], "cuda": cuda}
 
 
 def shard_frame_views(G, rank, i):
