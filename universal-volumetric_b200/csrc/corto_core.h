@@ -76,10 +76,25 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
 // record i lives in the ring as long as fewer than ring_size records were created after it (nfront counts the records created,
 // including the ones whose slots are about to be written)
 #define CW_IN_RING(i) ((i) >= nfront - rsize)
-#define CW_LOAD(dst, i) do { const int i_ = (i); if (CW_IN_RING(i_)) (dst) = ring[i_ & rmask]; else (dst) = front[i_]; } while (0)
-#define CW_NEW(i, e) do { const int i_ = (i); ring[i_ & rmask] = (e); front[i_] = (e); } while (0)
-#define CW_SET_NEXT(x, y) do { const int x_ = (x); front[x_].next = (y); if (CW_IN_RING(x_)) ring[x_ & rmask].next = (y); if (x_ == pi) P.next = (y); if (x_ == ni) N.next = (y); } while (0)
-#define CW_SET_PREV(x, y) do { const int x_ = (x); front[x_].prev = (y); if (CW_IN_RING(x_)) ring[x_ & rmask].prev = (y); if (x_ == pi) P.prev = (y); if (x_ == ni) N.prev = (y); } while (0)
+// (In the kernel the ring is addressed as shared memory outright: through the generic pointer every access paid for an address-space
+// conversion -- S2R / R2UR / ULEA on the uniform datapath -- on a chain where each instruction's latency counts.)
+#if defined(__CUDA_ARCH__)
+    uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    asm volatile("" : "+r"(ring_s));      // opaque: keeps the address in a register (the compiler would otherwise re-derive it, S2UR + ULEA, at every access)
+#define CW_RING_GET(dst, i_) asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"((dst).v0), "=r"((dst).v1), "=r"((dst).prev), "=r"((dst).next) : "r"(ring_s + 16u * (uint32_t)((i_) & rmask)))
+#define CW_RING_PUT(i_, e) asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" :: "r"(ring_s + 16u * (uint32_t)((i_) & rmask)), "r"((e).v0), "r"((e).v1), "r"((e).prev), "r"((e).next) : "memory")
+#define CW_RING_PUT_NEXT(i_, y) asm volatile("st.shared.s32 [%0], %1;" :: "r"(ring_s + 16u * (uint32_t)((i_) & rmask) + 12u), "r"(y) : "memory")
+#define CW_RING_PUT_PREV(i_, y) asm volatile("st.shared.s32 [%0], %1;" :: "r"(ring_s + 16u * (uint32_t)((i_) & rmask) + 8u), "r"(y) : "memory")
+#else
+#define CW_RING_GET(dst, i_) (dst) = ring[(i_) & rmask]
+#define CW_RING_PUT(i_, e) ring[(i_) & rmask] = (e)
+#define CW_RING_PUT_NEXT(i_, y) ring[(i_) & rmask].next = (y)
+#define CW_RING_PUT_PREV(i_, y) ring[(i_) & rmask].prev = (y)
+#endif
+#define CW_LOAD(dst, i) do { const int i_ = (i); if (CW_IN_RING(i_)) CW_RING_GET(dst, i_); else (dst) = front[i_]; } while (0)
+#define CW_NEW(i, e) do { const int i_ = (i); CW_RING_PUT(i_, e); front[i_] = (e); } while (0)
+#define CW_SET_NEXT(x, y) do { const int x_ = (x); front[x_].next = (y); if (CW_IN_RING(x_)) CW_RING_PUT_NEXT(x_, y); if (x_ == pi) P.next = (y); if (x_ == ni) N.next = (y); } while (0)
+#define CW_SET_PREV(x, y) do { const int x_ = (x); front[x_].prev = (y); if (CW_IN_RING(x_)) CW_RING_PUT_PREV(x_, y); if (x_ == pi) P.prev = (y); if (x_ == ni) N.prev = (y); } while (0)
 #define CW_FACE(a, b, c) do { if (start + 3 > end) CW_FAIL(CORTO_CORRUPT); m.faces[start] = (uint32_t)(a); m.faces[start + 1] = (uint32_t)(b); m.faces[start + 2] = (uint32_t)(c); start += 3; } while (0)
     for (uint32_t gi = 0; gi < m.ngroups; gi++) {
         const uint32_t end = m.group_end[gi] * 3u;
@@ -183,6 +198,10 @@ CORTO_HD int corto_walk(const CortoWalkMem &m) {
 #undef CW_FAIL
 #undef CW_SYMBOL
 #undef CW_IN_RING
+#undef CW_RING_GET
+#undef CW_RING_PUT
+#undef CW_RING_PUT_NEXT
+#undef CW_RING_PUT_PREV
 #undef CW_LOAD
 #undef CW_NEW
 #undef CW_SET_NEXT
