@@ -7,9 +7,10 @@ prints ONE JSON line on rank 0.
 Workload at N=1 (default `--workload c3`): the configuration BASELINE.json's metric is quoted on, configs[2] -- a
 synthetic 1000-frame V2 sequence, 200k verts/frame Draco geometry, 2048^2 UASTC KTX2 textures with sequenceSize 7
 (143 segments), built by tools/synth (deterministic).  `--workload c2` is configs[1] (300 frames, 50k verts, 1024^2
-ETC1S).  One "step" = one pass of the hot path over the whole sequence.  A sequence whose scratch does not fit HBM at
-once is decoded in WINDOWS of whole segments (the prefetch window of src/V2/player.ts:272-323); every window's
-compressed inputs stay resident in HBM (one ctx per window), the scratch / output arenas exist once (uvol_share_arenas).
+ETC1S), `--workload liam` the reference's 250 real frames / 50 real segments cycled to 1000 frames, `--workload c5` configs[4]
+(V1 Corto).  One "step" = one pass of the hot path over the whole sequence; C3 is ONE window of 1000 frames (82.5 MB of scratch
+per frame).  A sequence whose scratch would not fit HBM at once can still be decoded in WINDOWS of whole segments (`window_segments`
+of a workload; the prefetch window of src/V2/player.ts:272-323), one ctx per window.
 N>1 (BASELINE configs[3]): ONE sequence (same seed on every rank) is frame-sharded with manifest.shard_v2 -- rank r decodes only
 its contiguous block of whole KTX2 segments and the geometry frames they cover, no data-path collective -- and the decoded
 shards (geometry AND textures) are then gathered on every rank over NCCL / NVLink (gather.all_gather_shard).  "scaling":
@@ -19,9 +20,9 @@ weak-scaling figure (every rank decodes a whole sequence of its own) is kept und
   value     frames/s with the compressed inputs already resident in HBM (uvol_replay_v2_batch), device
             time from CUDA events on the library's streams (geometry and texture run concurrently, the
             step time is the longer of the two spans), outputs left in HBM.
-  e2e       frames/s through the C ABI with HOST buffers: uvol_decode_draco_batch +
-            uvol_transcode_ktx2_batch with UVOL_MEM_HOST (host parse, H2D of the compressed bytes,
-            kernels, D2H of every decoded buffer into pinned host memory), wall clock around the calls.
+  e2e       frames/s through the C ABI with HOST buffers: uvol_decode_v2_batch with UVOL_MEM_HOST (host parse, H2D of the
+            compressed bytes, kernels, D2H of every decoded buffer into pinned host memory), wall clock around the calls.
+  bc7_target  the same sequence with UVOL_TEX_BC7 output (what the reference picks on desktop GPUs): value and e2e.
   roofline  for the kernel stage with the largest share of the step (ALGORITHMIC bytes of that stage /
             its CUDA-event duration vs the measured HBM peak), plus the same for every stage.
   cpu_baseline  the CPU oracle (oracle/liboracle.so, a restatement: "port") on all host cores over a

@@ -303,6 +303,8 @@ __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker(const DracoFr
 //   * consistency checks accumulate in a sticky flag (all indices stay in range whatever the stream
 //     says) that is examined when the walk ends.
 // S symbols (component merges) flush the staged faces and use the memory path, executed uniformly.
+// (compute-sanitizer racecheck reports the redundant execution as hazards on the ring / stage words: every lane writes the SAME
+// value to the same word and reads back what it -- or a lane in the same state -- wrote; memcheck is clean.)
 #define EB2_RING 1024
 #define EB2_STAGE 32
 __global__ void __launch_bounds__(32 * SERIAL_WARPS) k_edgebreaker_valence2(const DracoFrame *frames, DracoCounts *counts, const uint8_t *blob, const uint32_t *aux,
