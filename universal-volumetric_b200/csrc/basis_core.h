@@ -14,14 +14,16 @@
 // ---------------------------------------------------------------------------------------------
 // LSB-first bit reader over 32-bit aligned words, bounded by the section's byte length: past the last word that holds a
 // section byte it yields zeros (a corrupt stream is then caught by the callers' `consumed` check instead of walking out of the
-// blob).  The batch blob is padded, so the aligned words that straddle the section's ends are always readable.
-struct BitRd { const uint32_t *w; uint32_t wi, lim; uint64_t buf; int nbits; uint64_t consumed; };
+// blob).  The batch blob is padded, so the aligned words that straddle the section's ends are always readable.  The word behind
+// the one in use is requested at the previous refill, so a refill never waits for memory on the symbol chain.
+struct BitRd { const uint32_t *w; uint32_t wi, lim, nxt; uint64_t buf; int nbits; uint64_t consumed; };      // nxt = word wi, requested one refill ahead of its use
 UVOL_HD void br_init(BitRd &b, const uint8_t *p, uint32_t nbytes) {
     const uintptr_t a = (uintptr_t)p; const unsigned mis = (unsigned)(a & 3);
     b.w = (const uint32_t *)(a - mis); b.lim = (mis + nbytes + 3) / 4;
     b.buf = b.lim ? (uint64_t)b.w[0] >> (8 * mis) : 0; b.nbits = 32 - 8 * (int)mis; b.wi = 1; b.consumed = 0;
+    b.nxt = b.lim > 1 ? b.w[1] : 0u;
 }
-UVOL_HD void br_refill(BitRd &b) { if (b.nbits <= 32) { const uint32_t v = b.wi < b.lim ? b.w[b.wi] : 0u; b.wi++; b.buf |= (uint64_t)v << b.nbits; b.nbits += 32; } }
+UVOL_HD void br_refill(BitRd &b) { if (b.nbits <= 32) { b.buf |= (uint64_t)b.nxt << b.nbits; b.nbits += 32; b.wi++; b.nxt = b.wi < b.lim ? b.w[b.wi] : 0u; } }
 UVOL_HD uint32_t br_peek(BitRd &b) { br_refill(b); return (uint32_t)b.buf; }
 UVOL_HD void br_skip(BitRd &b, int n) { b.buf >>= n; b.nbits -= n; b.consumed += (uint64_t)n; }
 UVOL_HD uint32_t br_get(BitRd &b, int n) { if (n == 0) return 0; br_refill(b); uint32_t v = (uint32_t)b.buf & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u)); br_skip(b, n); return v; }
@@ -37,11 +39,23 @@ UVOL_HD int huff_decode(const HuffTable &T, const uint16_t *sorted_pool, BitRd &
     const uint32_t v = br_peek(b);
     const uint32_t e = T.fast[v & ((1u << UVOL_HUFF_FAST_BITS) - 1u)];
     if (e & 0xff) { br_skip(b, (int)(e & 0xff)); return (int)(e >> 8); }
-    uint32_t code = 0;
-    for (uint32_t l = 1; l <= T.maxl; l++) {
-        code = (code << 1) | ((v >> (l - 1)) & 1u);
-        if (T.count[l] && code >= T.first_code[l] && code - T.first_code[l] < T.count[l]) { br_skip(b, (int)l); return sorted_pool[T.sorted_off + T.first_idx[l] + (code - T.first_code[l])]; }
+    // every code of up to UVOL_HUFF_FAST_BITS bits is in the fast table: the search starts behind it, on the bit-reversed window
+    // (canonical codes are MSB-first, the stream is LSB-first), one compare per length
+#if defined(__CUDA_ARCH__)
+    const uint32_t rv = __brev(v);
+#else
+    uint32_t rv = 0; for (int i = 0; i < 32; i++) rv |= ((v >> i) & 1u) << (31 - i);
+#endif
+    // (all six candidate lengths are tested at once -- their table words are independent loads -- and the shortest match is kept:
+    // a loop that stops at the first match would pay one shared-memory round trip per length, in series)
+    uint32_t len = 0, idx = 0;
+    const uint32_t maxl = T.maxl;
+#pragma unroll
+    for (uint32_t l = 16; l > UVOL_HUFF_FAST_BITS; l--) {
+        const uint32_t fc = T.first_code[l], code = rv >> (32u - l), k = code - fc;
+        if (l <= maxl && code >= fc && k < T.count[l]) { len = l; idx = T.first_idx[l] + k; }
     }
+    if (len) { br_skip(b, (int)len); return sorted_pool[T.sorted_off + idx]; }
     br_skip(b, 16);
     return -1;
 }
