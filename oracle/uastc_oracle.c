@@ -71,10 +71,24 @@ static int astc_partition(int seed, int x, int y, int count) {
     return 2;
 }
 
+/* n (<= 32) bits at bit offset *ofs of the 128-bit little-endian block, LSB first; bits past the block read as zero */
 static uint32_t take(const uint8_t *blk, uint32_t *ofs, uint32_t n) {
-    uint32_t v = 0;
-    for (uint32_t i = 0; i < n; i++, (*ofs)++) if (*ofs < 128) v |= (uint32_t)((blk[*ofs >> 3] >> (*ofs & 7)) & 1u) << i;
-    return v;
+    const uint32_t o = *ofs; *ofs = o + n;
+    if (n == 0 || o >= 128) return 0;
+    uint64_t lo, hi; memcpy(&lo, blk, 8); memcpy(&hi, blk + 8, 8);          /* (little-endian host, like every other reader here) */
+    uint64_t w;
+    if (o >= 64) w = hi >> (o - 64);
+    else w = o ? (lo >> o) | (hi << (64 - o)) : lo;
+    return (uint32_t)(n >= 32 ? w : w & ((1ull << n) - 1ull));
+}
+
+/* The partition of every texel for each pattern UASTC can select (30 two-subset, 11 three-subset, 19 mode-7 patterns), evaluated
+ * once from the ASTC partition function above instead of sixteen hashes per block. */
+static uint8_t PART2[30][16], PART3[11][16], PART7[19][16];
+__attribute__((constructor)) static void uastc_oracle_init(void) {
+    for (int p = 0; p < 30; p++) for (int i = 0; i < 16; i++) PART2[p][i] = (uint8_t)astc_partition(SEED2[p], i & 3, i >> 2, 2);
+    for (int p = 0; p < 11; p++) for (int i = 0; i < 16; i++) PART3[p][i] = (uint8_t)astc_partition(SEED3[p], i & 3, i >> 2, 3);
+    for (int p = 0; p < 19; p++) for (int i = 0; i < 16; i++) PART7[p][i] = (uint8_t)astc_partition(SEED7[p], i & 3, i >> 2, 2);
 }
 
 /* ASTC endpoint unquantisation of one BISE value (low bits + trit/quint << bits) */
@@ -130,11 +144,11 @@ int uvo_uastc_block_to_rgba(const uint8_t *blk, uint8_t *rgba) {
     int part[16] = {0};
     if (subsets > 1) {
         const uint32_t pat = take(blk, &ofs, mode == 3 ? 4 : 5);
-        int seed;
-        if (mode == 3) { if (pat >= 11) return -2; seed = SEED3[pat]; }
-        else if (mode == 7) { if (pat >= 19) return -2; seed = SEED7[pat]; }
-        else { if (pat >= 30) return -2; seed = SEED2[pat]; }
-        for (int i = 0; i < 16; i++) part[i] = astc_partition(seed, i & 3, i >> 2, subsets);
+        const uint8_t *pp;
+        if (mode == 3) { if (pat >= 11) return -2; pp = PART3[pat]; }
+        else if (mode == 7) { if (pat >= 19) return -2; pp = PART7[pat]; }
+        else { if (pat >= 30) return -2; pp = PART2[pat]; }
+        for (int i = 0; i < 16; i++) part[i] = pp[i];
     }
     int ccs = -1;
     if (planes == 2) ccs = mode == 17 ? 3 : (int)take(blk, &ofs, 2);
