@@ -68,6 +68,24 @@ def test_draco_tagged_scheme_core_logic(built):
             assert emu_draco(blob[:cut])["status"] < 0
 
 
+def test_speculative_traversal_row_pattern(built):
+    """k_traverse's scheme, emulated lane by lane (tests/tools/draco_emu.cpp), must reproduce the serial depth-first order -- the
+    emulation returns an error otherwise -- and on a UV sphere the seam-cut attribute table, which the walk crosses sideways (two faces
+    per ring, then a jump of one ring), must be served by the row pattern: well above the two faces per step of the plain guess."""
+    import ctypes as _c
+    from emu_bind import TOOLS
+    from tools.synth import synth
+    drc = synth.make_sequence(1, 20000, 32, want_textures=False, seed=20260003)[0][0]
+    e, o = emu_draco(drc), oracle_draco(drc)
+    assert e["status"] == 0 and np.array_equal(e["index"], o["index"])
+    for k in ("position", "normal", "uv"):
+        assert np.array_equal(e[k].view(np.uint32), o[k].view(np.uint32)), k
+    steps = (_c.c_long * 5)(); faces = _c.c_long()
+    _c.CDLL(os.path.join(TOOLS, "libdraco_emu.so")).draco_emu_spec(1, steps, _c.byref(faces))
+    per_step = [faces.value / s for s in list(steps)[:3] if s]
+    assert len(per_step) == 3 and min(per_step) > 8.0, per_step
+
+
 def test_draco_metadata_is_skipped(built):
     """A file with the metadata flag (header bit 15) decodes to the same mesh: the section is walked past by the parser and by the
     oracle (the reference's loader reads no metadata, DRACOLoader.js:470-554); a truncated metadata section is an error."""

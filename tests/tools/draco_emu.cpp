@@ -25,8 +25,14 @@ static void build_face_records(const TableView &tv, const int *lmc, int F, FaceR
         rec[f].meta |= (du << 4) | (dd << 9);
     }
 }
+// The speculative traversal of k_traverse, lane by lane.  Row pattern: the walk often advances in ROWS -- k faces along the face order, then a jump of D
+// faces (a strip crossed sideways: two faces per ring of a UV sphere, D = faces per ring) -- so lane l guesses face
+// f0 + (l / k) * D + (l % k) * dir.  A lane at the start of a row finds its entry corner from its own record (the corner whose opposite
+// lies in the previous lane's face); everything else -- the exact validation of every transition -- is as in traverse_spec_emu.
+// (k, D) is adopted when two consecutive steps ended with the same row length and the same jump, and dropped on the first mismatch.
 static int traverse_spec_emu(const FaceRec *rec, int F, uint8_t *fvis, int *v2d1, int *d2c, int *stk, int max_entries, uint32_t *out_n, long *steps) {
     const int C = 3 * F; int n = 0, sp = 0, c = -1, fscan = 0, pdir = 1; *steps = 0;
+    int pk = 32, pD = 0, lastk = 0, lastD = 0;
     for (;;) {
         if (c < 0) {
             bool scan = false;
@@ -43,46 +49,60 @@ static int traverse_spec_emu(const FaceRec *rec, int F, uint8_t *fvis, int *v2d1
         if (c >= C) return UVOL_ERR_CORRUPT;
         ++*steps;
         const int f0 = c / 3, k0 = c - 3 * f0;
-        TravLane L[32]; bool selfopen[32], vis[32]; int act[32], nx[32];
+        TravLane L[32]; bool selfopen[32], vis[32]; int act[32], nx[32], face[32];
         for (int l = 0; l < 32; l++) {
-            const int fi = f0 + l * pdir; const bool inr = fi >= 0 && fi < F;
+            const int fi = f0 + (l / pk) * pD + (l % pk) * pdir; face[l] = fi;
+            const bool inr = fi >= 0 && fi < F;
             const FaceRec z{}; const FaceRec &r = inr ? rec[fi] : z;
-            L[l] = trav_lane(r.v[0], r.v[1], r.v[2], r.o[0], r.o[1], r.o[2], r.meta, fi, l == 0 ? k0 : -1, pdir, inr);
+            int kf = l == 0 ? k0 : -1;
+            if (l > 0 && (l % pk) == 0) {          // row start: entered from the previous lane's face
+                kf = 3;
+                if (inr) for (int k = 0; k < 3; k++) if (r.o[k] >= 0 && r.o[k] / 3 == face[l - 1]) { kf = k; break; }
+            }
+            L[l] = trav_lane(r.v[0], r.v[1], r.v[2], r.o[0], r.o[1], r.o[2], r.meta, fi, kf, pdir, inr && kf != 3);
             selfopen[l] = L[l].ci >= 0 && !fvis[fi];
         }
         for (int l = 0; l < 32; l++) {
-            const bool dup = l > 0 && (L[l].v == L[0].v || (L[l].pd != 0 && (int)L[l].pd < l));
+            bool dup = false;
+            if (pk == 32) dup = l > 0 && (L[l].v == L[0].v || (L[l].pd != 0 && (int)L[l].pd < l));          // static distances along the face order
+            else for (int e = 0; e < l; e++) if (L[e].ci >= 0 && L[e].v == L[l].v) dup = true;                // row pattern: the lanes compare their tips
             vis[l] = L[l].ci >= 0 && (v2d1[L[l].v] != 0 || dup);
             bool fr = true, fl = true;
             if (L[l].ci >= 0) {
-                if (L[l].rc >= 0) { const int rf = L[l].rc / 3, k = (rf - f0) * pdir; fr = fvis[rf] || (k >= 0 && k <= l); }
-                if (L[l].lc >= 0) { const int lf = L[l].lc / 3, k = (lf - f0) * pdir; fl = fvis[lf] || (k >= 0 && k <= l); }
+                if (L[l].rc >= 0) { const int rf = L[l].rc / 3; fr = fvis[rf] != 0; for (int e = 0; e <= l; e++) if (face[e] == rf) fr = true; }
+                if (L[l].lc >= 0) { const int lf = L[l].lc / 3; fl = fvis[lf] != 0; for (int e = 0; e <= l; e++) if (face[e] == lf) fl = true; }
             }
             trav_decide(vis[l], L[l].ob, fr, fl, L[l].rc, L[l].lc, &act[l], &nx[l]);
         }
         int m = 31;
         for (int l = 0; l < 32; l++) { const bool trans = act[l] == 0 && nx[l] >= 0 && l < 31 && nx[l] == L[l + 1].ci && selfopen[l + 1]; if (!trans) { m = l; break; } }
-        if (getenv("EMU_TRAV_SEQ")) { static long cnt2 = 0; if (cnt2 > 20000 && cnt2 < 20080) fprintf(stderr, "step f0=%d c=%d pdir=%d m=%d act=%d nx=%d(face %d)\n", f0, c, pdir, m, act[m], nx[m], nx[m] / 3); cnt2++; }
-        if (getenv("EMU_TRAV_DEBUG")) {
-            static long hist[8]; static long cnt = 0; int why;
-            if (m == 31) why = 0; else if (act[m] == 1) why = 1; else if (act[m] == 2) why = 2; else if (nx[m] < 0) why = 3;
-            else { const int nf = nx[m] / 3, fm = f0 + m * pdir; if (nf == fm + pdir) why = (nx[m] == L[m + 1].ci) ? 4 /*next not open*/ : 5 /*adjacent face, other corner*/; else if (nf == fm - pdir) why = 6; else why = 7; }
-            hist[why]++; if (++cnt % 5000 == 0) fprintf(stderr, "steps %ld: full %ld pop %ld push %ld bad %ld nextclosed %ld othercorner %ld reverse %ld jump %ld\n", cnt, hist[0], hist[1], hist[2], hist[3], hist[4], hist[5], hist[6], hist[7]);
-        }
         if (!selfopen[0]) return UVOL_ERR_CORRUPT;
         for (int l = 0; l <= m; l++) {
-            fvis[f0 + l * pdir] = 1;
+            fvis[face[l]] = 1;
             if (!vis[l]) { if (n >= max_entries) return UVOL_ERR_CORRUPT; v2d1[L[l].v] = n + 1; d2c[n] = L[l].ci; n++; }
         }
+        const int fm = face[m];
         if (act[m] == 0) { c = nx[m]; if (c < 0) return UVOL_ERR_CORRUPT; }
         else if (act[m] == 1) { sp--; c = -1; }
         else { stk[sp - 1] = L[m].lc; stk[sp] = nx[m]; sp++; c = nx[m]; }
-        if (c >= 0) { const int nf = c / 3, fm = f0 + m * pdir; if (nf == fm + 1) pdir = 1; else if (nf == fm - 1) pdir = -1; }
+        // next step's guess (as in the kernel)
+        int nk = 32, nD = 0;
+        if (c >= 0) {
+            const int nf = c / 3;
+            if (nf == fm + 1) pdir = 1; else if (nf == fm - 1) pdir = -1;
+            else {
+                const int row0 = pk == 32 ? 0 : (m / pk) * pk, rowlen = m - row0 + 1, D = nf - face[row0];
+                const bool usable = rowlen <= 16 && (D > 32 || D < -32);
+                if (usable && ((rowlen == lastk && D == lastD) || (pk < 32 && rowlen == pk && D == pD))) { nk = rowlen; nD = D; }
+                lastk = rowlen; lastD = D;
+            }
+        } else { lastk = 0; lastD = 0; }
+        if (pk < 32 && m == 31) { nk = pk; nD = pD; }          // a full step on the pattern: keep it
+        pk = nk; pD = nD;
     }
     *out_n = (uint32_t)n;
     return UVOL_OK;
 }
-
 
 static void emu_rabs_bits(RabsLane &r, uint8_t *o, uint32_t n, bool toggle) {      // eight bits per store, as k_rabs_lanes
     uint32_t last = 1;

@@ -765,19 +765,34 @@ __global__ void __launch_bounds__(256) k_face_records(const DracoFrame *frames, 
 }
 
 // Depth-first traversal (A.3): one warp per (frame, table), up to 32 faces per step.
-// Face ids follow the edgebreaker strip order and the traversal walks along the same strips, so lane i SPECULATES that the walk
-// reaches face f0 + i*dir through that face's static entry corner (dir = the direction of the last move; lane 0 stands on the
-// walk's actual corner).  One 32-byte record load per lane (k_face_records), then every lane evaluates the exact step rule for its
-// face against the visited maps plus the effects of the lanes before it (static duplicate distances, ballots); the longest
-// prefix whose transitions really lead to the next lane's corner is committed at once, and the first lane that deviates (pop,
-// push, turn, direction change) hands its exact outcome to the next step.  Output order is identical to the serial walk
-// (tests/tools/draco_emu.cpp runs this very scheme lane by lane on the host against traverse_table).
+// Face ids follow the edgebreaker strip order and the traversal mostly walks along the same strips, so lane i SPECULATES which face
+// the walk reaches i moves from now and through which corner:
+//   * default: face f0 + i*dir through that face's static entry corner (dir = the direction of the last move; lane 0 stands on
+//     the walk's actual corner);
+//   * row pattern: when the last steps each ended after k faces with a jump of D faces (a strip crossed sideways: an attribute table
+//     cut by a seam sends the walk across the rings of a UV sphere, two faces per ring), face f0 + (i / k)*D + (i % k)*dir; a lane
+//     at the start of a row takes as entry corner the corner of its own record whose opposite lies in the previous lane's face.
+// One 32-byte record load per lane (k_face_records), then every lane evaluates the exact step rule for its face against the
+// visited maps plus the effects of the lanes before it (tips already reached inside the step: static duplicate distances along the
+// face order, __match_any_sync on a row pattern; faces visited inside the step: index arithmetic on the pattern); the longest prefix whose transitions really lead to the next lane's corner is
+// committed at once, and the first lane that deviates (pop, push, turn, direction change, jump) hands its exact outcome to the next
+// step.  A wrong guess only shortens the step.  Output order is identical to the serial walk (tests/tools/draco_emu.cpp runs this
+// very scheme lane by lane on the host against traverse_table).
 #define TRAV_STACK 512
 __device__ __forceinline__ unsigned face_of(int c) { return __umulhi((unsigned)c, 0xAAAAAAABu) >> 1; }
 // GMAP = 0: visited-face / visited-vertex bitmaps in shared memory (F/8 + V/8 bytes per walk: fastest while all walks of the
 // batch are co-resident).  GMAP = 1: a byte per face in global memory plus the vertex -> entry map itself as the visited-vertex
 // test -- 2 KB of shared memory per walk, so large meshes (C3: 77 KB of bitmaps per walk) no longer cap the SM at two walks.
 // Only this warp touches those bytes, so plain (L1-cached) loads / stores ordered by warp barriers suffice.
+// Is the face at distance d from the step's first face one of the faces of lanes 0..lane?  Default guess: d * dir in [0, lane].
+// Row pattern (k faces per row, rows D apart, |D| > 32 >= k so the decomposition is unique): d = q * D + r * dir with 0 <= r < k.
+__device__ __forceinline__ bool trav_in_step(int d, int lane, int pk, int pD, int pdir) {
+    if (pk == 32) { const int k = d * pdir; return k >= 0 && k <= lane; }
+    const int e = d * pdir, PD = pD * pdir;                      // r = e - q * PD
+    int q = e / PD; if (e - q * PD < 0) q += PD > 0 ? -1 : 1;   // floor-style: the remainder must be non-negative
+    const int r = e - q * PD;
+    return q >= 0 && r >= 0 && r < pk && q * pk + r <= lane;
+}
 template <int GMAP>
 __global__ void __launch_bounds__(32) k_traverse(const DracoFrame *frames, DracoCounts *counts, uint8_t *S, uint8_t *Z, uint8_t *S2, uint8_t *Z2,
                                                  const Job *jobs, int njobs, int fwords_max, int vwords_max) {
@@ -801,6 +816,8 @@ __global__ void __launch_bounds__(32) k_traverse(const DracoFrame *frames, Draco
     if (!G && (F > fwords_max * 32 || max_entries > vwords_max * 32)) { if (lane == 0) frame_fail(counts, jb.frame, UVOL_ERR_CORRUPT); return; }
     __syncwarp();
     int n = 0, sp = 0, c = -1, fscan = 0, status = 0, pdir = 1;
+    int pk = 32, pD = 0, lastk = 0, lastD = 0;      // row pattern in use (pk = 32: none), row length / jump of the step before
+    int prow = 0, pcol = lane;
 #define FBIT(x) (G ? (uint32_t)fvis[(x)] : ((fbits[(x) >> 5] >> ((x) & 31)) & 1u))
 #define VBIT(x) (G ? (uint32_t)(v2d1[(x)] != 0) : ((vbits[(x) >> 5] >> ((x) & 31)) & 1u))
     for (;;) {
@@ -853,22 +870,33 @@ __global__ void __launch_bounds__(32) k_traverse(const DracoFrame *frames, Draco
         if (c >= C) { status = UVOL_ERR_CORRUPT; break; }
         // ---- one speculative step over up to 32 faces
         const int f0 = (int)face_of(c), k0 = c - 3 * f0;
-        const int fi = f0 + lane * pdir;
+        const int fi = f0 + prow * pD + pcol * pdir;      // (prow, pcol: this lane's row / column under the pattern in use; 0, lane by default)
         const bool inr = fi >= 0 && fi < F;
         uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0xfu, 0);
         if (inr) { A = grec[2 * (size_t)fi]; B = grec[2 * (size_t)fi + 1]; }
-        const TravLane L = trav_lane((int)A.x, (int)A.y, (int)A.z, (int)A.w, (int)B.x, (int)B.y, B.z, fi, lane == 0 ? k0 : -1, pdir, inr);
+        int kf = lane == 0 ? k0 : -1;
+        if (pk != 32) {   // the first lane of a later row: entered from the previous lane's face
+            const int pf = __shfl_up_sync(0xffffffffu, fi, 1);
+            if (lane > 0 && pcol == 0) {
+                const int o0 = (int)A.w, o1 = (int)B.x, o2 = (int)B.y;
+                kf = (o0 >= 0 && (int)face_of(o0) == pf) ? 0 : ((o1 >= 0 && (int)face_of(o1) == pf) ? 1 : ((o2 >= 0 && (int)face_of(o2) == pf) ? 2 : 3));
+            }
+        }
+        const TravLane L = trav_lane((int)A.x, (int)A.y, (int)A.z, (int)A.w, (int)B.x, (int)B.y, B.z, fi, kf, pdir, inr && kf != 3);
         const int ci = L.ci, rc = L.rc, lc = L.lc; const unsigned v = L.v;
         const bool selfopen = ci >= 0 && !FBIT(fi);
-        // vertex visited before my step: the map, or the tip of an earlier lane (lane 0's actual tip / the static distance to an earlier face of the run)
-        const unsigned v_first = __shfl_sync(0xffffffffu, v, 0);
-        const bool dup = lane > 0 && (v == v_first || (L.pd != 0 && (int)L.pd < lane));
+        // vertex visited before my step: the map, or the tip of an earlier lane of this step -- along the face order that is lane 0's
+        // actual tip or the static distance to an earlier face of the run with the same entry tip (k_face_records); on a row pattern
+        // the lanes compare their tips (MATCH.ANY costs a round per distinct value, so it is kept off the default path)
+        bool dup;
+        if (pk == 32) { const unsigned v_first = __shfl_sync(0xffffffffu, v, 0); dup = lane > 0 && (v == v_first || (L.pd != 0 && (int)L.pd < lane)); }
+        else dup = (__match_any_sync(0xffffffffu, ci >= 0 ? v : (0x80000000u | (unsigned)lane)) & lt) != 0;
         const bool vis = ci >= 0 && (VBIT(v) || dup);
         // neighbour faces visited before / during this step (faces of the lanes up to and including me)
         bool fr = true, fl = true;
         if (ci >= 0) {
-            if (rc >= 0) { const int rf = (int)face_of(rc), k = (rf - f0) * pdir; fr = FBIT(rf) || (k >= 0 && k <= lane); }
-            if (lc >= 0) { const int lf = (int)face_of(lc), k = (lf - f0) * pdir; fl = FBIT(lf) || (k >= 0 && k <= lane); }
+            if (rc >= 0) { const int rf = (int)face_of(rc); fr = FBIT(rf) || trav_in_step(rf - f0, lane, pk, pD, pdir); }
+            if (lc >= 0) { const int lf = (int)face_of(lc); fl = FBIT(lf) || trav_in_step(lf - f0, lane, pk, pD, pdir); }
         }
         int act, nx;
         trav_decide(vis, L.ob, fr, fl, rc, lc, &act, &nx);
@@ -895,6 +923,8 @@ __global__ void __launch_bounds__(32) k_traverse(const DracoFrame *frames, Draco
         n += __popc(newv);
         // outcome of the last executed lane
         const int act_m = __shfl_sync(0xffffffffu, act, m), nx_m = __shfl_sync(0xffffffffu, nx, m), lc_m = __shfl_sync(0xffffffffu, lc, m);
+        int fm = f0 + m * pdir;
+        if (pk != 32) fm = __shfl_sync(0xffffffffu, fi, m);
         __syncwarp();
         if (act_m == 0) { c = nx_m; if (c < 0) { status = UVOL_ERR_CORRUPT; break; } }
         else if (act_m == 1) { sp--; c = -1; }
@@ -907,7 +937,25 @@ __global__ void __launch_bounds__(32) k_traverse(const DracoFrame *frames, Draco
             sp++; c = nx_m;
             __syncwarp();
         }
-        if (c >= 0) { const int nf = (int)face_of(c), fm = f0 + m * pdir; if (nf == fm + 1) pdir = 1; else if (nf == fm - 1) pdir = -1; }
+        // ---- the next step's guess (uniform): direction after a move to a neighbouring face id; after a jump, the row pattern if the
+        // row that just ended and the distance between row starts repeat what the step before saw
+        {
+            int nk = 32, nD = 0;
+            if (c >= 0) {
+                const int nf = (int)face_of(c);
+                if (nf == fm + 1) pdir = 1; else if (nf == fm - 1) pdir = -1;
+                else {
+                    int rowlen = m + 1, D = nf - f0;
+                    if (pk != 32) { const int row0 = (m / pk) * pk; rowlen = m - row0 + 1; D = nf - __shfl_sync(0xffffffffu, fi, row0); }
+                    const bool usable = rowlen <= 16 && (D > 32 || D < -32);
+                    if (usable && ((rowlen == lastk && D == lastD) || (pk < 32 && rowlen == pk && D == pD))) { nk = rowlen; nD = D; }
+                    lastk = rowlen; lastD = D;
+                }
+            } else { lastk = 0; lastD = 0; }
+            if (pk < 32 && m == 31) { nk = pk; nD = pD; }          // a full step on the pattern: keep it
+            if (nk != pk) { prow = nk == 32 ? 0 : lane / nk; pcol = lane - prow * nk; }
+            pk = nk; pD = nD;
+        }
     }
 #undef FBIT
 #undef VBIT

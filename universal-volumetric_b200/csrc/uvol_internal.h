@@ -75,11 +75,11 @@ struct DracoFrame {
     uint64_t out_index, out_attr[4];
 };
 
-// Per-face traversal record of one corner table (base or attribute): built element-parallel (k_face_records, k_face_dups),
+// Per-face traversal record of one corner table (base or attribute): built element-parallel (k_face_records),
 // consumed by the speculative depth-first traversal as one 32-byte load per lane.
 //   v[k]  vertex id of corner 3f+k in this table          o[k]  opposite corner of 3f+k (-1: boundary / seam)
 //   meta  bits 0-1  corner through which the walk enters f from face f-1 (3: none)      bits 2-3  same from face f+1
-//         bits 4-8  duplicate distance of the f-1 entry's tip vertex (k_face_dups)       bits 9-13 same for the f+1 entry
+//         bits 4-8  duplicate distance of the f-1 entry's tip vertex                      bits 9-13 same for the f+1 entry
 //         bits 14-16 vertex of corner k lies on the table's boundary
 struct FaceRec { int32_t v[3]; int32_t o[3]; uint32_t meta; uint32_t pad; };
 
