@@ -76,6 +76,11 @@ static int traverse_spec_emu(const FaceRec *rec, int F, uint8_t *fvis, int *v2d1
         }
         int m = 31;
         for (int l = 0; l < 32; l++) { const bool trans = act[l] == 0 && nx[l] >= 0 && l < 31 && nx[l] == L[l + 1].ci && selfopen[l + 1]; if (!trans) { m = l; break; } }
+        if (getenv("EMU_TRAV_SEQ")) {          // debug trace of a window of steps (development aid)
+            static long cnt2 = 0; const long w0 = atol(getenv("EMU_TRAV_SEQ"));
+            if (cnt2 >= w0 && cnt2 < w0 + 70) fprintf(stderr, "step f0=%d k0=%d pdir=%d pk=%d pD=%d m=%d act=%d next=(face %d corner %d)\n", f0, k0, pdir, pk, pD, m, act[m], nx[m] >= 0 ? nx[m] / 3 : -1, nx[m] >= 0 ? nx[m] % 3 : -1);
+            cnt2++;
+        }
         if (!selfopen[0]) return UVOL_ERR_CORRUPT;
         for (int l = 0; l <= m; l++) {
             fvis[face[l]] = 1;
