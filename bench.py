@@ -23,6 +23,7 @@ weak-scaling figure (every rank decodes a whole sequence of its own) is kept und
   e2e       frames/s through the C ABI with HOST buffers: uvol_decode_v2_batch with UVOL_MEM_HOST (host parse, H2D of the
             compressed bytes, kernels, D2H of every decoded buffer into pinned host memory), wall clock around the calls.
   bc7_target  the same sequence with UVOL_TEX_BC7 output (what the reference picks on desktop GPUs): value and e2e.
+  astc_target the same sequence with UVOL_TEX_ASTC_4x4 output (UASTC workloads; the reference's choice on GPUs with ASTC): lossless repack.
   roofline  for the kernel stage with the largest share of the step (ALGORITHMIC bytes of that stage /
             its CUDA-event duration vs the measured HBM peak), plus the same for every stage.
   cpu_baseline  the CPU oracle (oracle/liboracle.so, a restatement: "port") on all host cores over a
@@ -199,7 +200,7 @@ def cpu_sample(drc, ktx, seq, nseg):
     return drc[: nseg * seq], ktx[:nseg]
 
 
-TARGETS = {"rgba32": 0, "etc1": 1, "bc7": 2}
+TARGETS = {"rgba32": 0, "etc1": 1, "bc7": 2, "astc": 4}
 
 
 def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex, fmt, target="rgba32"):
@@ -224,7 +225,7 @@ def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex, fmt, target="
     t = {
         "slices": bytes_in_tex + frames * nblk * 5,                            # VLC bits in, {pred u8, delta/selector u16} out
         "resolve": frames * nblk * (1 + 2 + 2 + 2),
-        "blocks": frames * nblk * ((16 if fmt == "uastc" else 4) + {"rgba32": 64, "etc1": 8, "bc7": 16}[target]),   # UASTC: 16 B block in; ETC1S: 2x u16 indices in; 64 B RGBA / 16 B BC7 / 8 B ETC1 out
+        "blocks": frames * nblk * ((16 if fmt == "uastc" else 4) + {"rgba32": 64, "etc1": 8, "bc7": 16, "astc": 16}[target]),   # UASTC: 16 B block in; ETC1S: 2x u16 indices in; 64 B RGBA / 16 B BC7 or ASTC / 8 B ETC1 out
     }
     return g, t
 
@@ -590,6 +591,19 @@ def main():
             r2.close(); del r2
         except Exception as ex:                                       # never lose the headline to a side figure
             extra["bc7_target"] = {"error": str(ex)[:200]}
+    if args.texture_target == "rgba32" and not args.no_extra_targets and W["fmt"] == "uastc":
+        try:       # the reference's first choice for UASTC on GPUs with ASTC support (KTX2Loader.js:592-600): a LOSSLESS repack, same texels, 4x fewer bytes
+            r4 = Runner(drc_all[f0:f1], ktx_all[s0:s1], "astc")
+            k4 = max(2, min(args.steps, 3))
+            M4 = measure(r4, k4, 1, False)
+            d4, e4 = maxr(M4["dev_ms"], M4["e2e_s"])
+            o4 = sumr(M4["sg2"]["bytes_out"] + M4["st2"]["bytes_out"])[0]
+            extra["astc_target"] = {"value": frames * k4 / (d4 / 1e3), "e2e": frames * k4 / e4, "unit": "frames/s", "steps": k4, "d2h_bytes_per_step": o4,
+                                    "tex_stage_ms_rank0": {k: round(v / k4, 3) for k, v in M4["stage_acc"].items() if k.startswith("tex_") and v / k4 >= 0.02},
+                                    "note": "same sequence, UVOL_TEX_ASTC_4x4 output (decode only, no gather); lossless: the blocks decode to exactly the RGBA32 texels (tests/test_astc.py)"}
+            r4.close(); del r4
+        except Exception as ex:
+            extra["astc_target"] = {"error": str(ex)[:200]}
     if world > 1 and not args.no_weak:
         try:       # last round's weak-scaling figure: every rank decodes a whole sequence of its own
             dw, kw, _ = make_workload(args.workload, rank)

@@ -39,9 +39,14 @@ enum uvol_memory { UVOL_MEM_DEVICE = 0, UVOL_MEM_HOST = 1 };
  * BC7 is what those options select for ETC1S *and* UASTC sources on a desktop GPU with EXT_texture_compression_bptc (BC7_M5 /
  * RGBA_BPTC_Format, :602-604): 16 bytes per 4x4 block in block raster order, layers back to back; ETC1S (with or without alpha) ->
  * BC7 mode 5, UASTC -> the BC7 mode with the same subset shapes and weight grid (csrc/bc7_core.h).  Not bit-identical to the
- * reference's transcoder (whose tables are not in its tree): validated by an independent BC7 decoder, bounds in tests/test_bc7.py. */
+ * reference's transcoder (whose tables are not in its tree): validated by an independent BC7 decoder, bounds in tests/test_bc7.py.
+ * ASTC_4x4 is the reference's first choice for UASTC sources on GPUs with WEBGL_compressed_texture_astc (ASTC_4x4 /
+ * RGBA_ASTC_4x4_Format, :592-600; not offered for ETC1S: those items report UVOL_STATUS_UNSUPPORTED): 16 bytes per block, block raster
+ * order, layers back to back.  UASTC is a subset of ASTC, so this repack is LOSSLESS: the blocks decode to exactly the RGBA32 texels
+ * (csrc/astc_core.h; checked bit for bit through an independent ASTC decoder, tests/test_astc.py). */
 enum uvol_texture_format { UVOL_TEX_RGBA32 = 0, UVOL_TEX_ETC1 = 1, UVOL_TEX_BC7 = 2,
-                           UVOL_TEX_ETC2_RGB = 3 /* only as the format of uvol_upload_etc2_batch results: raw blocks passed through */ };
+                           UVOL_TEX_ETC2_RGB = 3 /* only as the format of uvol_upload_etc2_batch results: raw blocks passed through */,
+                           UVOL_TEX_ASTC_4x4 = 4 };
 
 /* Result of one geometry frame.  Replaces the Draco worker reply
  *   {type:'decode', geometry:{index:{array:Uint32Array(F*3)}, attributes:[{name, array:Float32Array(P*itemSize), itemSize}]}}
@@ -67,7 +72,7 @@ typedef struct uvol_texture {
     uint32_t width, height, layers;
     uint32_t format;       /* uvol_texture_format */
     uint32_t has_alpha, dfd_transfer, dfd_flags;
-    uint8_t *data;         /* RGBA32: u8[layers * width * height * 4]; ETC1: u8[layers * ceil(w/4) * ceil(h/4) * 8]; BC7: ... * 16 */
+    uint8_t *data;         /* RGBA32: u8[layers * width * height * 4]; ETC1: u8[layers * ceil(w/4) * ceil(h/4) * 8]; BC7, ASTC_4x4: ... * 16 */
     uint64_t bytes;
 } uvol_texture;
 
@@ -83,7 +88,7 @@ typedef struct uvol_stats {
 /* Tunables of a context (SURVEY 5 "config / flags").  The reference takes constructor arguments only (bufferDuration = 4,
  * intervalDuration = 2, src/Player.ts:50-51) and derives the texture target from the GPU's capabilities
  * (src/lib/KTX2Loader.js:591-689); here they are one struct.  uvol_config_default() fills the defaults and then applies the
- * environment overrides UVOL_TEXTURE_TARGET (rgba32 | etc1 | bc7), UVOL_CORTO_INDEX_U16, UVOL_STAGING_THREADS, UVOL_MAX_FACES,
+ * environment overrides UVOL_TEXTURE_TARGET (rgba32 | etc1 | bc7 | astc), UVOL_CORTO_INDEX_U16, UVOL_STAGING_THREADS, UVOL_MAX_FACES,
  * UVOL_MAX_TEXTURE_BYTES, UVOL_BUFFER_DURATION, UVOL_INTERVAL_DURATION. */
 typedef struct uvol_config {
     uint32_t struct_size;            /* sizeof(uvol_config) */

@@ -65,6 +65,11 @@ void uvo_ktx2_free(uvo_ktx2_image *m);
 int uvo_bc7_decode_block(const uint8_t *block16, uint8_t *rgba64);
 int uvo_bc7_decode_image(const uint8_t *blocks, uint32_t w, uint32_t h, uint8_t *rgba);
 
+/* ---- ASTC LDR 4x4 decoder written from the ASTC specification: the independent check of the product's UVOL_TEX_ASTC_4x4 target
+ * (astc_decode.c).  decode_block: 0 = decoded, 1 = a block outside the decoder's scope; decode_image returns the number of those. */
+int uvo_astc_decode_block(const uint8_t *block16, uint8_t *rgba64);
+int uvo_astc_decode_image(const uint8_t *blocks, uint32_t w, uint32_t h, uint8_t *rgba);
+
 /* ---- thread-pooled batch drivers for the CPU baseline (frames / segments are independent,
  * mirroring the <=4-worker design of DRACOLoader.js:24,312-364 and WorkerPool.js:7).
  * Return the number of items that decoded OK; checksum (optional) gets an FNV over outputs. */

@@ -55,3 +55,14 @@ def emu_ktx2_bc7(blob):
         return {"status": rc}
     nb = ((w.value + 3) // 4) * ((h.value + 3) // 4)
     return {"status": 0, "width": w.value, "height": h.value, "layers": l.value, "blocks": np.ctypeslib.as_array(p, (l.value, nb, 16)).copy()}
+
+
+def emu_ktx2_astc(blob):
+    """Target ASTC 4x4 through the product's per-block function (csrc/astc_core.h) on the host: u8[layers, blocks, 16] (UASTC sources only)."""
+    E = _load("libbasis_emu.so")
+    p = ctypes.POINTER(ctypes.c_uint8)(); w = ctypes.c_uint32(); h = ctypes.c_uint32(); l = ctypes.c_uint32()
+    rc = E.basis_emu_decode_astc(blob, ctypes.c_size_t(len(blob)), ctypes.byref(p), ctypes.byref(w), ctypes.byref(h), ctypes.byref(l))
+    if rc:
+        return {"status": rc}
+    nb = ((w.value + 3) // 4) * ((h.value + 3) // 4)
+    return {"status": 0, "width": w.value, "height": h.value, "layers": l.value, "blocks": np.ctypeslib.as_array(p, (l.value, nb, 16)).copy()}

@@ -108,3 +108,12 @@ def oracle_bc7_image(blocks, width, height):
     out = np.zeros((height, width, 4), np.uint8)
     bad = L.uvo_bc7_decode_image(np.ascontiguousarray(blocks, dtype=np.uint8).tobytes(), width, height, out.ctypes.data)
     return out, bad
+
+
+def oracle_astc_image(blocks, width, height):
+    """Decodes ASTC 4x4 blocks (block-raster order, u8[nblocks, 16]) with the oracle's independent ASTC decoder -> (u8[h, w, 4], bad blocks)."""
+    L = lib()
+    L.uvo_astc_decode_image.argtypes = [ctypes.c_char_p, c_u32, c_u32, ctypes.c_void_p]; L.uvo_astc_decode_image.restype = c_int
+    out = np.zeros((height, width, 4), np.uint8)
+    bad = L.uvo_astc_decode_image(np.ascontiguousarray(blocks, dtype=np.uint8).tobytes(), width, height, out.ctypes.data)
+    return out, bad

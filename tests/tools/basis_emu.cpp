@@ -7,6 +7,7 @@
 #include "../../universal-volumetric_b200/csrc/basis_core.h"
 #include "../../universal-volumetric_b200/csrc/uastc_core.h"
 #include "../../universal-volumetric_b200/csrc/bc7_core.h"
+#include "../../universal-volumetric_b200/csrc/astc_core.h"
 
 extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
 
@@ -18,12 +19,15 @@ extern "C" int basis_emu_decode(const uint8_t *data, size_t len, uint8_t **rgba,
 extern "C" int basis_emu_decode_etc1(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 1); }
 // target BC7: *blocks receives layers * blocks * 16 bytes (ETC1S with or without alpha, UASTC)
 extern "C" int basis_emu_decode_bc7(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 2); }
+// target ASTC 4x4: *blocks receives layers * blocks * 16 bytes (UASTC sources only, like the reference's ASTC option)
+extern "C" int basis_emu_decode_astc(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 3); }
 static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers, int etc1) {
     std::vector<uint8_t> padded(len + 64, 0); memcpy(padded.data(), data, len);   // the launcher pads the blob the same way
     const uint8_t *file = padded.data();
     Ktx2File f; memset(&f, 0, sizeof f); std::vector<Ktx2Slice> slices;
     int rc = uvol_ktx2_parse(file, len, 0, f, slices); if (rc) return rc;
     if (f.is_uastc && etc1 == 1) return UVOL_ERR_UNSUPPORTED;
+    if (!f.is_uastc && etc1 == 3) return UVOL_ERR_UNSUPPORTED;
     if (f.is_uastc) {          // the kernel's per-block function (uastc_core.h) over every block, Zstd levels inflated by the product's decoder
         const uint32_t nblk = f.bx * f.by;
         std::vector<uint8_t> inflated; const uint8_t *level = file + f.level_off;
@@ -40,6 +44,17 @@ static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba
             for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
                 uint32_t w[4], o[4]; memcpy(w, level + ((size_t)L * nblk + bi) * 16, 16);
                 if (!uastc_to_bc7(T, B7, w[0], w[1], w[2], w[3], o)) { free(out); return UVOL_ERR_CORRUPT; }
+                memcpy(out + ((size_t)L * nblk + bi) * 16, o, 16);
+            }
+            *rgba = out; *w = f.width; *h = f.height; *layers = f.layers;
+            return UVOL_OK;
+        }
+        if (etc1 == 3) {          // the ASTC kernel's per-block function (astc_core.h)
+            AstcShared AS; astc_fill_tables(AS);
+            uint8_t *out = (uint8_t *)malloc((size_t)f.layers * nblk * 16 + 16);
+            for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
+                uint32_t w[4], o[4]; memcpy(w, level + ((size_t)L * nblk + bi) * 16, 16);
+                if (!uastc_to_astc(T, AS, w[0], w[1], w[2], w[3], o)) { free(out); return UVOL_ERR_CORRUPT; }
                 memcpy(out + ((size_t)L * nblk + bi) * 16, o, 16);
             }
             *rgba = out; *w = f.width; *h = f.height; *layers = f.layers;

@@ -139,6 +139,54 @@ def check():
     return True
 
 
+def astc_trits(T):
+    """The five trits an 8-bit ASTC trit block T encodes (ASTC spec, integer sequence encoding)."""
+    b = lambda i: (T >> i) & 1
+    if (T >> 2) & 7 == 7:
+        C = ((T >> 5) << 2) | (T & 3); t4 = t3 = 2
+    else:
+        C = T & 31
+        if (T >> 5) & 3 == 3: t4 = 2; t3 = b(7)
+        else: t4 = b(7); t3 = (T >> 5) & 3
+    c = lambda i: (C >> i) & 1
+    if C & 3 == 3: t2 = 2; t1 = c(4); t0 = (c(3) << 1) | (c(2) & ~c(3) & 1)
+    elif (C >> 2) & 3 == 3: t2 = 2; t1 = 2; t0 = C & 3
+    else: t2 = c(4); t1 = (C >> 2) & 3; t0 = (c(1) << 1) | (c(0) & ~c(1) & 1)
+    return (t0, t1, t2, t3, t4)
+
+
+def astc_quints(Q):
+    """The three quints a 7-bit ASTC quint block Q encodes."""
+    b = lambda i: (Q >> i) & 1
+    if (Q >> 1) & 3 == 3 and (Q >> 5) & 3 == 0:
+        q2 = (b(0) << 2) | ((b(4) & ~b(0) & 1) << 1) | (b(3) & ~b(0) & 1); q1 = q0 = 4
+    else:
+        if (Q >> 1) & 3 == 3: q2 = 4; C = (((Q >> 3) & 3) << 3) | ((~(Q >> 5) & 3) << 1) | b(0)
+        else: q2 = (Q >> 5) & 3; C = Q & 31
+        if C & 7 == 5: q1 = 4; q0 = (C >> 3) & 3
+        else: q1 = (C >> 3) & 3; q0 = C & 7
+    return (q0, q1, q2)
+
+
+def bise_encode_tables():
+    """Smallest block value per combination (index = plain base-3 / base-5 number, first value = lowest digit).  Checked: every
+    combination is reachable with all digits in range, and a bundle whose trailing values are absent (digit 0) has zero in the
+    bits a truncated bundle does not store (2 / 4 / 5 / 7 bits for 1..4 trits, 3 / 5 bits for 1 / 2 quints)."""
+    trit, quint = {}, {}
+    for T in range(256):
+        t = astc_trits(T); assert all(0 <= v <= 2 for v in t), (T, t)
+        trit.setdefault(sum(v * 3 ** i for i, v in enumerate(t)), T)
+    for Q in range(128):
+        q = astc_quints(Q); assert all(0 <= v <= 4 for v in q), (Q, q)
+        quint.setdefault(sum(v * 5 ** i for i, v in enumerate(q)), Q)
+    assert sorted(trit) == list(range(243)) and sorted(quint) == list(range(125))
+    for n, bits in ((1, 2), (2, 4), (3, 5), (4, 7)):
+        for v in range(3 ** n): assert trit[v] < (1 << bits), (n, v)
+    for n, bits in ((1, 3), (2, 5)):
+        for v in range(5 ** n): assert quint[v] < (1 << bits), (n, v)
+    return [trit[v] for v in range(243)], [quint[v] for v in range(125)]
+
+
 def unquant_endpoint(val, bits, trits, quints):
     lo, D = val & ((1 << bits) - 1), val >> bits
     if not trits and not quints:
@@ -212,6 +260,18 @@ def main():
     out += ["};", "// BC7 mode 5, solid colours: 7-bit endpoints {lo, hi} that give exactly v at colour index 1 (weight 21), v = 0..255", "static const uint8_t BC7_SOLID5_INIT[256][2] = {"]
     sol = solid_mode5()
     out += ["    " + ", ".join("{%d, %d}" % sol[v] for v in range(i, i + 8)) + "," for i in range(0, 256, 8)]
+    out.append("};")
+    # ---- ASTC target (astc_core.h): the ASTC partition seed of every pattern and the BISE trit / quint block encodings
+    out += ["// ASTC view: 10-bit partition seed of the 60 patterns; smallest 8-bit trit block per base-3 number of five trits (first value =",
+            "// lowest digit) and smallest 7-bit quint block per base-5 number of three quints (ASTC integer sequence encoding, inverted).",
+            "static const uint16_t UASTC_ASTC_SEED_INIT[60] = {"]
+    seeds = [s_ for _, s_, _ in COMMON2] + [s_ for _, s_, _ in COMMON3] + [s_ for _, s_, _ in BC7_3_ASTC2]
+    out += ["    " + ", ".join(str(v) for v in seeds[i:i + 15]) + "," for i in range(0, 60, 15)]
+    tr, qu = bise_encode_tables()
+    out += ["};", "static const uint8_t ASTC_TRIT_ENC_INIT[243] = {"]
+    out += ["    " + ", ".join(str(v) for v in tr[i:i + 27]) + "," for i in range(0, 243, 27)]
+    out += ["};", "static const uint8_t ASTC_QUINT_ENC_INIT[125] = {"]
+    out += ["    " + ", ".join(str(v) for v in qu[i:i + 25]) + "," for i in range(0, 125, 25)]
     out.append("};")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "universal-volumetric_b200", "csrc", "uastc_tables.h")
     with open(path, "w") as f:

@@ -13,6 +13,7 @@ MEM_DEVICE, MEM_HOST = 0, 1
 TEX_RGBA32 = 0
 TEX_ETC1 = 1
 TEX_BC7 = 2
+TEX_ASTC_4x4 = 4
 TEX_ETC2_RGB = 3
 
 

@@ -283,7 +283,8 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
         if (f.layers > 4095 || f.bx > 4096) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }
         const uint64_t nblk = (uint64_t)f.bx * f.by;
         if (target == UVOL_TEX_ETC1 && (f.is_uastc || f.has_alpha)) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }   // ETC1 target: opaque ETC1S sources only
-        const uint64_t out_bytes = target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * nblk * 8 : (target == UVOL_TEX_BC7 ? (uint64_t)f.layers * nblk * 16 : (uint64_t)f.layers * f.width * f.height * 4);
+        if (target == UVOL_TEX_ASTC_4x4 && !f.is_uastc) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }             // ASTC target: UASTC sources only (KTX2Loader.js:592-600)
+        const uint64_t out_bytes = target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * nblk * 8 : (target == UVOL_TEX_BC7 || target == UVOL_TEX_ASTC_4x4 ? (uint64_t)f.layers * nblk * 16 : (uint64_t)f.layers * f.width * f.height * 4);
         if (out_bytes > ctx->cfg.max_texture_bytes) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }      // resource limit, per item
         if (nblk > B.max_blocks) B.max_blocks = (uint32_t)nblk;
         f.o_rgba = take(o, out_bytes);
@@ -474,7 +475,7 @@ static int ktx2_finish(uvol_ctx *ctx, int memory, uvol_texture *out, uvol_stats 
         if (t.status) continue;
         t.width = f.width; t.height = f.height; t.layers = f.layers; t.format = (uint32_t)B.target; t.has_alpha = f.has_alpha;
         t.dfd_transfer = f.dfd_transfer; t.dfd_flags = f.dfd_flags;
-        t.bytes = B.target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * f.bx * f.by * 8 : (B.target == UVOL_TEX_BC7 ? (uint64_t)f.layers * f.bx * f.by * 16 : (uint64_t)f.layers * f.width * f.height * 4);
+        t.bytes = B.target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * f.bx * f.by * 8 : (B.target == UVOL_TEX_BC7 || B.target == UVOL_TEX_ASTC_4x4 ? (uint64_t)f.layers * f.bx * f.by * 16 : (uint64_t)f.layers * f.width * f.height * 4);
         t.data = base + f.o_rgba; bytes_out += t.bytes;
     }
     sx.kernel_launches = B.launches; sx.bytes_in = B.bytes_in; sx.bytes_out = bytes_out; sx.scratch_bytes = B.scratch;
@@ -496,7 +497,7 @@ static int ktx2_run_replay(uvol_ctx *ctx, int memory, uvol_texture *out) {
 
 extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target_format, int memory, uvol_texture *out) {
     if (!ctx || !out || n < 0 || (n > 0 && (!data || !size)) || n >= (1 << 19)) return UVOL_ERR_ARG;
-    if (target_format != UVOL_TEX_RGBA32 && target_format != UVOL_TEX_ETC1 && target_format != UVOL_TEX_BC7) { ctx->set_error("target formats: UVOL_TEX_RGBA32, UVOL_TEX_ETC1, UVOL_TEX_BC7"); return UVOL_ERR_UNSUPPORTED; }
+    if (target_format != UVOL_TEX_RGBA32 && target_format != UVOL_TEX_ETC1 && target_format != UVOL_TEX_BC7 && target_format != UVOL_TEX_ASTC_4x4) { ctx->set_error("target formats: UVOL_TEX_RGBA32, UVOL_TEX_ETC1, UVOL_TEX_BC7, UVOL_TEX_ASTC_4x4"); return UVOL_ERR_UNSUPPORTED; }
     UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->stats, 0, sizeof ctx->stats);
     if (n == 0) { if (ctx->tex) ctx->tex->n = 0; return UVOL_OK; }

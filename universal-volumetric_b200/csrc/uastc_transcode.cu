@@ -15,6 +15,7 @@
 #include "uvol_ctx.h"
 #include "uastc_core.h"
 #include "bc7_core.h"
+#include "astc_core.h"
 #include "tma_bulk.h"
 
 namespace {
@@ -71,14 +72,16 @@ __global__ void __launch_bounds__(256) k_uastc_blocks(const Ktx2File *files, int
     }
 }
 
-// UASTC -> BC7 (UVOL_TEX_BC7): same traversal of the blocks, 16 bytes out per block in block raster order (a warp stores 512
-// contiguous bytes); per-block logic in bc7_core.h.
+// UASTC -> BC7 (UVOL_TEX_BC7) / UASTC -> ASTC 4x4 (UVOL_TEX_ASTC_4x4): same traversal of the blocks, 16 bytes out per block in block
+// raster order (a warp stores 512 contiguous bytes); per-block logic in bc7_core.h / astc_core.h.  X = the target's table image.
 __device__ __align__(16) uint32_t g_bc7_tables[sizeof(Bc7Shared) / 4];
-__global__ void __launch_bounds__(256) k_uastc_blocks_bc7(const Ktx2File *files, int32_t *status2, const uint8_t *blob, uint8_t *O, const uint32_t *layer_list) {
-    __shared__ __align__(16) UastcShared T; __shared__ __align__(16) Bc7Shared B7; __shared__ __align__(8) uint64_t bar;
+__device__ __align__(16) uint32_t g_astc_tables[sizeof(AstcShared) / 4];
+template <typename X>
+__global__ void __launch_bounds__(256) k_uastc_blocks_16(const Ktx2File *files, int32_t *status2, const uint8_t *blob, uint8_t *O, const uint32_t *layer_list, const uint32_t *x_tables) {
+    __shared__ __align__(16) UastcShared T; __shared__ __align__(16) X TX; __shared__ __align__(8) uint64_t bar;
     if (threadIdx.x == 0) {          // both table images by bulk asynchronous copies, one barrier
-        mbar_init(&bar, 1); mbar_expect_tx(&bar, (uint32_t)(sizeof(UastcShared) + sizeof(Bc7Shared)));
-        bulk_g2s(&T, g_tables, (uint32_t)sizeof(UastcShared), &bar); bulk_g2s(&B7, g_bc7_tables, (uint32_t)sizeof(Bc7Shared), &bar);
+        mbar_init(&bar, 1); mbar_expect_tx(&bar, (uint32_t)(sizeof(UastcShared) + sizeof(X)));
+        bulk_g2s(&T, g_tables, (uint32_t)sizeof(UastcShared), &bar); bulk_g2s(&TX, x_tables, (uint32_t)sizeof(X), &bar);
     }
     __shared__ struct { const uint8_t *src0; uint8_t *dst; uint32_t nblk, fi, skip; } K;
     if (threadIdx.x == 0) {
@@ -102,11 +105,14 @@ __global__ void __launch_bounds__(256) k_uastc_blocks_bc7(const Ktx2File *files,
         uint4 blk;
         if (aligned) blk = __ldcs((const uint4 *)src);
         else { uint32_t w[4]; for (int q = 0; q < 4; q++) w[q] = src[4 * q] | (src[4 * q + 1] << 8) | (src[4 * q + 2] << 16) | ((uint32_t)src[4 * q + 3] << 24); blk = make_uint4(w[0], w[1], w[2], w[3]); }
-        uint32_t o[4];
-        if (!uastc_to_bc7(T, B7, blk.x, blk.y, blk.z, blk.w, o)) { status2[2 * fi] = UVOL_ERR_CORRUPT; continue; }
+        uint32_t o[4]; bool ok;
+        if constexpr (sizeof(X) == sizeof(Bc7Shared)) ok = uastc_to_bc7(T, TX, blk.x, blk.y, blk.z, blk.w, o);
+        else ok = uastc_to_astc(T, TX, blk.x, blk.y, blk.z, blk.w, o);
+        if (!ok) { status2[2 * fi] = UVOL_ERR_CORRUPT; continue; }
         __stcs((uint4 *)(dst + (size_t)bi * 16), make_uint4(o[0], o[1], o[2], o[3]));
     }
 }
+static_assert(sizeof(Bc7Shared) != sizeof(AstcShared), "k_uastc_blocks_16 tells its targets apart by the table image");
 
 bool g_tables_ready[16] = {};
 }  // namespace
@@ -126,6 +132,8 @@ int uvol_texture_tables_ready(int device) {
     Bc7Shared b; bc7_fill_tables(b);
     e = cudaMemcpyToSymbol(g_bc7_tables, &b, sizeof b); if (e != cudaSuccess) return (int)e;
     e = cudaMemcpyToSymbol(g_bc7_tables_etc1s, &b, sizeof b); if (e != cudaSuccess) return (int)e;
+    AstcShared a; astc_fill_tables(a);
+    e = cudaMemcpyToSymbol(g_astc_tables, &a, sizeof a); if (e != cudaSuccess) return (int)e;
     if (device >= 0 && device < 16) g_tables_ready[device] = true;
     return 0;
 }
@@ -134,7 +142,12 @@ int uvol_uastc_launch(int device, const Ktx2File *dF, int32_t *status2, const ui
                       uint32_t max_blocks, int target, cudaStream_t st) {
     const int rc = uvol_texture_tables_ready(device); if (rc) return rc;
     const dim3 grid((max_blocks + 256 * UASTC_CHUNKS - 1) / (256 * UASTC_CHUNKS), (unsigned)nlayers);
-    if (target == UVOL_TEX_BC7) { k_uastc_blocks_bc7<<<grid, 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList); return 0; }
+    if (target == UVOL_TEX_BC7 || target == UVOL_TEX_ASTC_4x4) {
+        uint32_t *xt = nullptr;
+        if (target == UVOL_TEX_BC7) { cudaGetSymbolAddress((void **)&xt, g_bc7_tables); k_uastc_blocks_16<Bc7Shared><<<grid, 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList, xt); }
+        else { cudaGetSymbolAddress((void **)&xt, g_astc_tables); k_uastc_blocks_16<AstcShared><<<grid, 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList, xt); }
+        return 0;
+    }
     static const bool no_tma = getenv("UVOL_NO_TMA") != nullptr;
     if (no_tma) { k_uastc_blocks<false><<<grid, 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList); return 0; }
     k_uastc_blocks<true><<<dim3((max_blocks + 256 * UASTC_CHUNKS - 1) / (256 * UASTC_CHUNKS), (unsigned)nlayers), 256, 0, st>>>(dF, status2, dBlob, dOut, dLayerList);

@@ -187,20 +187,21 @@ class KTX2Loader:
     def transcode_batch(self, files, target=N.TEX_RGBA32):
         """target = TEX_RGBA32 (default; data u8[layers, h, w, 4]), TEX_ETC1 (data u8[layers, blocks, 8], the reference's
         RGB_ETC1_Format / opaque RGB_ETC2_Format choice, KTX2Loader.js:619-636) or TEX_BC7 (data u8[layers, blocks, 16], its
-        RGBA_BPTC_Format choice on desktop GPUs, :602-604)."""
+        RGBA_BPTC_Format choice on desktop GPUs, :602-604) or TEX_ASTC_4x4 (u8[layers, blocks, 16], its RGBA_ASTC_4x4_Format choice
+        for UASTC sources, :592-600; lossless)."""
         raw = self.transcode_batch_raw(files, N.MEM_HOST, target)
         res = []
         for t in raw:
             if t.status != 0:
                 res.append({"status": int(t.status), "data": None})
                 continue
-            if target in (N.TEX_ETC1, N.TEX_BC7):
+            if target in (N.TEX_ETC1, N.TEX_BC7, N.TEX_ASTC_4x4):
                 nb = ((t.width + 3) // 4) * ((t.height + 3) // 4)
                 data = np.ctypeslib.as_array(t.data, (t.layers, nb, 8 if target == N.TEX_ETC1 else 16)).copy()
             else:
                 data = np.ctypeslib.as_array(t.data, (t.layers, t.height, t.width, 4)).copy()
             res.append({"status": 0, "width": int(t.width), "height": int(t.height), "layers": int(t.layers), "hasAlpha": bool(t.has_alpha),
-                        "format": {N.TEX_ETC1: "RGB_ETC1_Format", N.TEX_BC7: "RGBA_BPTC_Format"}.get(target, "RGBAFormat"), "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data})
+                        "format": {N.TEX_ETC1: "RGB_ETC1_Format", N.TEX_BC7: "RGBA_BPTC_Format", N.TEX_ASTC_4x4: "RGBA_ASTC_4x4_Format"}.get(target, "RGBAFormat"), "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data})
         return res
 
 
