@@ -302,6 +302,8 @@ def bench_v1(args, W, rank, world, local):
     for _ in range(args.steps):
         ctx.flush_l2(); t1 = time.perf_counter(); dec.decode_batch_raw(blobs, uv.MEM_HOST); e2e_s += time.perf_counter() - t1
         st = ctx.stats(2); launches += st["kernel_launches"]
+        e2e_parts = {"host_parse_and_staging": round(st["host_parse_ms"], 3), "call_total": round(st["total_ms"], 3), "kernels": round(st["device_ms"], 3),
+                     "d2h": round(st["stages"].get("d2h", 0.0), 3), "h2d": round(st["stages"].get("h2d", 0.0), 3)}
     barrier(); clk = clocks.stop()
     if world > 1:
         v = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(v, op=dist.ReduceOp.MAX); dev_ms, e2e_s = float(v[0]), float(v[1])
@@ -341,7 +343,7 @@ def bench_v1(args, W, rank, world, local):
                                        "note": "dominant stage is a latency-bound serial walk (one warp per frame)"},
                           "stages": stages, "cpu_baseline": cpu,
                           "e2e": {"value": total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": st["bytes_in"], "d2h_bytes_per_step": st["bytes_out"], "ms_per_step": e2e_s / args.steps * 1e3,
-                                  "path": "uvol_decode_corto_batch, UVOL_MEM_HOST"},
+                                  "path": "uvol_decode_corto_batch, UVOL_MEM_HOST", "breakdown_ms_last_step_rank0": e2e_parts},
                           "gpu_launches": launches, "clocks": clk, "workload_gen_s": round(gen_s, 2)}))
     ctx.close()
     if world > 1:

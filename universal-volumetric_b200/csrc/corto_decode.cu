@@ -22,6 +22,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <thread>
 #include "uvol_ctx.h"
 #include "corto_core.h"
 #include "../../include/corto_codec.h"
@@ -586,8 +587,25 @@ extern "C" int uvol_decode_corto_batch(uvol_ctx *ctx, const uint8_t *const *data
     UVOL_CUDA(ctx, ctx->h_cdesc.reserve(desc_bytes + aux_bytes + job_bytes + 64)); UVOL_CUDA(ctx, ctx->d_cdesc.reserve(desc_bytes + aux_bytes + job_bytes + 64));
     UVOL_CUDA(ctx, ctx->d_cscratch.reserve(zbase + z + 256)); UVOL_CUDA(ctx, ctx->d_out_corto.reserve(o + 256));
     UVOL_CUDA(ctx, ctx->d_ccounts.reserve(4 * (size_t)n)); UVOL_CUDA(ctx, ctx->h_ccounts.reserve(4 * (size_t)n));
-    memset(ctx->h_cblob.p, 0, blob_bytes + 64);
-    for (int i = 0; i < n; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_cblob.p + frames[i].file_off, data[i], size[i]);
+    {   // staging copy into the pinned blob (it sits in front of the first kernel): only the padding behind each file is zeroed, and a
+        // large batch is copied by a few threads
+        uint8_t *hb = (uint8_t *)ctx->h_cblob.p;
+        auto copy_range = [&](int lo, int hi) {
+            for (int i = lo; i < hi; i++) {
+                const bool have = data[i] && size[i] < (1ull << 31);
+                const uint64_t end = i + 1 < n ? frames[i + 1].file_off : blob_bytes + 64, used = have ? size[i] : 0;
+                if (have) memcpy(hb + frames[i].file_off, data[i], size[i]);
+                memset(hb + frames[i].file_off + used, 0, end - frames[i].file_off - used);
+            }
+        };
+        const int nthreads = bytes_in > (16ull << 20) ? (ctx->cfg.staging_threads ? (int)ctx->cfg.staging_threads : uvol_staging_threads()) : 1;
+        if (nthreads <= 1) copy_range(0, n);
+        else {
+            std::vector<std::thread> pool; const int per = (n + nthreads - 1) / nthreads;
+            for (int lo = 0; lo < n; lo += per) pool.emplace_back(copy_range, lo, std::min(n, lo + per));
+            for (auto &t : pool) t.join();
+        }
+    }
     uint8_t *hd = (uint8_t *)ctx->h_cdesc.p;
     memcpy(hd, frames.data(), desc_bytes); memcpy(hd + desc_bytes, aux.data(), aux_bytes); memcpy(hd + desc_bytes + aux_bytes, jobs.data(), sizeof(CJob) * jobs.size());
     const double t_parsed = now_ms();
