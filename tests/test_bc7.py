@@ -105,3 +105,37 @@ def test_bc7_kernels_match_host_logic(uv, ctx):
         assert np.array_equal(np.ctypeslib.as_array(t[0].data, e["blocks"].shape), e["blocks"])
     finally:
         c2.close()
+
+
+def _dds_bc7(blocks, w, h):
+    """A DDS file (DX10 header, DXGI_FORMAT_BC7_UNORM = 98) around raw BC7 blocks: what Pillow's DdsImagePlugin reads."""
+    import struct
+    hdr = b"DDS " + struct.pack("<7I", 124, 0x1 | 0x2 | 0x4 | 0x1000 | 0x80000, h, w, len(blocks), 0, 1) + struct.pack("<11I", *([0] * 11))
+    pf = struct.pack("<II4sIIIII", 32, 0x4, b"DX10", 0, 0, 0, 0, 0)
+    return hdr + pf + struct.pack("<IIIII", 0x1000, 0, 0, 0, 0) + struct.pack("<IIIII", 98, 3, 0, 1, 0) + blocks
+
+
+def test_bc7_decoder_pinned_to_pillow(built):
+    """THIRD-PARTY pin of the BC7 side: Pillow's BC7 decoder (its own C implementation, DdsImagePlugin / BcnDecoder) must return exactly
+    the texels of oracle/bc7_decode.c -- on the product's blocks (UASTC and ETC1S sources) and on 4096 blocks of random bits per BC7 mode
+    (every mode, partition, rotation and index-selection combination).  So the BC7 bounds above are measured with a decoder that an
+    independent implementation agrees with, not only with our own reading of the BPTC layout."""
+    import io
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(20260006)
+    cases = []
+    for name in ("uastc_all_modes", "etc1s_synth"):
+        e = emu_ktx2_bc7(files()[name])
+        cases.append((name, e["blocks"][0], e["width"], e["height"]))
+    for mode in range(8):
+        rnd = rng.integers(0, 256, (64 * 64, 16), dtype=np.uint8)
+        rnd[:, 0] = (rnd[:, 0] & np.uint8(0xFF & ~((2 << mode) - 1))) | np.uint8(1 << mode)      # the unary mode prefix: `mode` zero bits, then a one
+        cases.append(("random_mode_%d" % mode, rnd, 256, 256))
+    for name, blocks, w, h in cases:
+        try:
+            img = np.array(Image.open(io.BytesIO(_dds_bc7(np.ascontiguousarray(blocks).tobytes(), w, h))).convert("RGBA"))
+        except Exception as ex:          # a Pillow build without the BC7 path
+            pytest.skip("Pillow cannot decode BC7 DDS here: %s" % ex)
+        ours, bad = oracle_bc7_image(blocks, w, h)
+        assert bad == 0, name
+        assert np.array_equal(img, ours), (name, int((img != ours).sum()))
