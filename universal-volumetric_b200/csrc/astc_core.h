@@ -51,6 +51,19 @@ UASTC_HD unsigned long long astc_rev64(unsigned long long v) {
 #endif
 }
 
+UASTC_HD int astc_ctz(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+// inserts a zero bit at position p (0..126) of the 128-bit value {lo, hi}: bits p.. move up by one
+UASTC_HD void astc_ins0(unsigned long long &lo, unsigned long long &hi, uint32_t p) {
+    if (p < 64u) { const unsigned long long m = (1ull << p) - 1ull; hi = (hi << 1) | (lo >> 63); lo = (lo & m) | ((lo & ~m) << 1); }
+    else { const unsigned long long m = (1ull << (p - 64u)) - 1ull; hi = (hi & m) | ((hi & ~m) << 1); }
+}
+
 // One UASTC block -> one ASTC block (four little-endian words).  false: the block is rejected (like uastc_block).
 UASTC_HD bool uastc_to_astc(const UastcShared &T, const AstcShared &A, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, uint32_t out[4]) {
     Bits x{q0, q1, q2, q3};
@@ -146,29 +159,46 @@ UASTC_HD bool uastc_to_astc(const UastcShared &T, const AstcShared &A, uint32_t 
 #pragma unroll
                 for (uint32_t e = 0; e < 2; e++) if (s < subsets && c < comps) {
                     const uint32_t sl = swap[s] ? slot[s][c][e ^ 1u] : slot[s][c][e];
-                    astc_put(b, sl & 255u, epbits);
-                    if (tq) {
+                    uint32_t v = sl & 255u, nbits = epbits;
+                    if (tq) {                       // the piece of the trit / quint block that follows this value goes out with it
                         const uint32_t n = (widths >> (4u * k)) & 15u;
-                        astc_put(b, cur & ((1u << n) - 1u), n); cur >>= n;
+                        v |= (cur & ((1u << n) - 1u)) << epbits; nbits += n; cur >>= n;
                         if (++k == bundle) { k = 0; cur = blocks & 255u; blocks >>= 8; }
                     }
+                    astc_put(b, v, nbits);
                 }
     }
-    // ---- weights, in full, LSB first into a second stream that is mirrored onto the top of the block
-    AstcBits w{0, 0, 0};
-    const uint32_t maxw = (1u << wbits) - 1u;
+    // ---- weights: the stored stream (what is left of the block, right-aligned) is turned into ASTC's as a whole -- a zero bit
+    // inserted above each subset's first weight (which UASTC stores one bit short), the fields of swapped subsets complemented by
+    // one XOR, the second-plane selector appended -- and then mirrored onto the top of the block
+    unsigned long long wl = (unsigned long long)x.a | ((unsigned long long)x.b << 32), wh = (unsigned long long)x.c | ((unsigned long long)x.d << 32);
+    const uint32_t stride = wbits * planes, wtotal = 16u * stride;
+    {
+        uint32_t am = anchors;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const uint32_t s = (pattern >> (2 * i)) & 3u;
-        const bool inv = s == 0 ? swap[0] : (s == 1 ? swap[1] : swap[2]);
-        const uint32_t nb = wbits - ((anchors >> i) & 1u);
-        uint32_t w0 = take(x, nb);
-        if (inv) w0 = maxw - w0;
-        astc_put(w, w0, wbits);
-        if (planes == 2u) { uint32_t w1 = take(x, nb); if (inv) w1 = maxw - w1; astc_put(w, w1, wbits); }
+        for (int t = 0; t < 3; t++) if (am) {
+            const uint32_t i = (uint32_t)astc_ctz(am); am &= am - 1u;
+            astc_ins0(wl, wh, i * stride + wbits - 1u);
+            if (planes == 2u) astc_ins0(wl, wh, i * stride + 2u * wbits - 1u);
+        }
     }
-    if (planes == 2u) astc_put(w, ((ccs & 1u) << 1) | (ccs >> 1), 2);     // the selector sits below the weights in normal bit order
-    const unsigned long long lo = b.lo | astc_rev64(w.hi), hi = b.hi | astc_rev64(w.lo);
+    if (swap[0] | swap[1] | swap[2]) {
+        unsigned long long ml = 0, mh = 0;
+        if (subsets == 1u) { ml = ~0ull; mh = ~0ull; }
+        else {
+            const unsigned long long ones = (1ull << stride) - 1ull;          // stride <= 3 with more than one subset: the whole field lies in the low word
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint32_t sb = (pattern >> (2 * i)) & 3u;
+                if (sb == 0 ? swap[0] : (sb == 1 ? swap[1] : swap[2])) ml |= ones << ((uint32_t)i * stride);
+            }
+        }
+        wl ^= ml; wh ^= mh;
+    }
+    // keep exactly the weight field, then the selector (bit-swapped: the stream is mirrored, the selector is not)
+    if (wtotal < 64u) { wl &= (1ull << wtotal) - 1ull; wh = 0; } else if (wtotal < 128u) wh &= (1ull << (wtotal - 64u)) - 1ull;
+    if (planes == 2u) { const unsigned long long sel = ((ccs & 1u) << 1) | (ccs >> 1); if (wtotal < 64u) wl |= sel << wtotal; else wh |= sel << (wtotal - 64u); }
+    const unsigned long long lo = b.lo | astc_rev64(wh), hi = b.hi | astc_rev64(wl);
     out[0] = (uint32_t)lo; out[1] = (uint32_t)(lo >> 32); out[2] = (uint32_t)hi; out[3] = (uint32_t)(hi >> 32);
     return true;
 }
