@@ -67,13 +67,20 @@ typedef struct uvol_geometry {
 /* Result of one KTX2 segment.  Replaces the Basis worker reply
  *   {type:'transcode', faces:[{mipmaps:[{data, width, height}], ...}], width, height, hasAlpha, format, dfdTransferFn, dfdFlags}
  * (src/lib/KTX2Loader.js:431,565-578): `data` holds all layers back to back (concat, :565). */
+typedef struct uvol_texture_level {   /* one entry of `mipmaps` (KTX2Loader.js:514-573): all layers of that level back to back at data + offset */
+    uint32_t width, height;            /* max(1, base >> level) */
+    uint64_t offset, bytes;
+} uvol_texture_level;
 typedef struct uvol_texture {
     int32_t status;
     uint32_t width, height, layers;
     uint32_t format;       /* uvol_texture_format */
     uint32_t has_alpha, dfd_transfer, dfd_flags;
-    uint8_t *data;         /* RGBA32: u8[layers * width * height * 4]; ETC1: u8[layers * ceil(w/4) * ceil(h/4) * 8]; BC7, ASTC_4x4: ... * 16 */
-    uint64_t bytes;
+    uint8_t *data;         /* level 0.  RGBA32: u8[layers * width * height * 4]; ETC1: u8[layers * ceil(w/4) * ceil(h/4) * 8]; BC7, ASTC_4x4: ... * 16 */
+    uint64_t bytes;        /* level 0 when levels == 1; with a mip chain: up to the end of the last level (levels are 128-byte aligned) */
+    uint32_t levels;       /* levelCount of the file (1 for UVOL content: scripts/Encoder.py writes no mips); cube faces are not supported */
+    uint32_t reserved;
+    const uvol_texture_level *mips;   /* [levels], library-owned like data; mips[0].offset == 0 (NULL for uvol_upload_etc2_batch results) */
 } uvol_texture;
 
 /* Timing / traffic of the last batch call on a ctx (CUDA events on the ctx's stream). */

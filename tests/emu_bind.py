@@ -66,3 +66,13 @@ def emu_ktx2_astc(blob):
         return {"status": rc}
     nb = ((w.value + 3) // 4) * ((h.value + 3) // 4)
     return {"status": 0, "width": w.value, "height": h.value, "layers": l.value, "blocks": np.ctypeslib.as_array(p, (l.value, nb, 16)).copy()}
+
+
+def emu_ktx2_split_levels(blob):
+    """The product's mip-chain splitter (csrc/basis_parse.cpp uvol_ktx2_split_levels): (status or level count, [single-level .ktx2 bytes])."""
+    E = _load("libbasis_emu.so")
+    files = (ctypes.POINTER(ctypes.c_uint8) * 16)(); sizes = (ctypes.c_size_t * 16)()
+    E.basis_emu_split_levels.restype = ctypes.c_int
+    rc = E.basis_emu_split_levels(blob, ctypes.c_size_t(len(blob)), files, sizes, 16)
+    out = [ctypes.string_at(files[k], sizes[k]) for k in range(max(0, min(rc, 16)))]
+    return rc, out

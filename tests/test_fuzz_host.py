@@ -20,6 +20,9 @@ def test_host_parsers_survive_mutations(built, tmp_path):
     seeds = list(golden_drc()[:2]) + list(golden_ktx2())
     plain = synth.encode_uastc(synth.texture_layers(32, 0, 2, 5), seed=3)
     p = tmp_path / "uastc_plain.ktx2"; p.write_bytes(plain); seeds.append(str(p))
+    from test_ktx2_mips import etc1s_chain, uastc_chain          # mip chains: the splitter (uvol_ktx2_split_levels) reads the same untrusted bytes
+    p = tmp_path / "uastc_mips.ktx2"; p.write_bytes(uastc_chain()[0]); seeds.append(str(p))
+    p = tmp_path / "etc1s_mips.ktx2"; p.write_bytes(etc1s_chain()[0]); seeds.append(str(p))
     small = synth.make_sequence(1, 500, 32, want_textures=False, seed=5)[0][0]
     p = tmp_path / "small.drc"; p.write_bytes(small); seeds.append(str(p))
     rings, segs = synth.sphere_dims(500); fp, fu, uvs, _ = synth.sphere_topology(rings, segs); pos = synth.sphere_frame(rings, segs, 0.1, 5)

@@ -12,6 +12,16 @@
 extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
 
 int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
+int uvol_ktx2_split_levels(const uint8_t *b, size_t len, std::vector<std::vector<uint8_t>> &out);
+
+// The product's mip-chain splitter (basis_parse.cpp): returns its result; level k's synthetic single-level file is copied to
+// files[k] (malloc'ed, sizes[k] bytes), at most `cap` of them.
+extern "C" int basis_emu_split_levels(const uint8_t *data, size_t len, uint8_t **files, size_t *sizes, int cap) {
+    std::vector<std::vector<uint8_t>> out;
+    const int rc = uvol_ktx2_split_levels(data, len, out);
+    for (int k = 0; k < rc && k < cap; k++) { files[k] = (uint8_t *)malloc(out[k].size()); memcpy(files[k], out[k].data(), out[k].size()); sizes[k] = out[k].size(); }
+    return rc;
+}
 
 static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers, int etc1);
 extern "C" int basis_emu_decode(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, rgba, w, h, layers, 0); }

@@ -20,6 +20,7 @@
 
 int uvol_draco_parse(const uint8_t *data, size_t len, DracoFrame &f, std::vector<uint32_t> &aux);
 int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
+int uvol_ktx2_split_levels(const uint8_t *b, size_t len, std::vector<std::vector<uint8_t>> &out);
 extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
 
 static uint64_t rng_state;
@@ -50,6 +51,14 @@ static void run_one(const std::string &name, const uint8_t *p, size_t n, long *o
     alarm(20);                                           // a parser that loops on a crafted length is a failure too (SIGALRM kills the run)
     if (name.size() > 4 && name.substr(name.size() - 4) == ".drc") { GuardedObj<DracoFrame> f; std::vector<uint32_t> aux; rc = uvol_draco_parse(buf, n, *f.p, aux); }
     else if (name.size() > 5 && name.substr(name.size() - 5) == ".ktx2") {
+        {   // mip chains are taken apart first (basis_parse.cpp): the splitter sees the same untrusted bytes, and what it emits must be
+            // single-level files whose descriptors stay inside THEM
+            std::vector<std::vector<uint8_t>> lv; const int L = uvol_ktx2_split_levels(buf, n, lv);
+            for (int k = 0; k < L; k++) {
+                Ktx2File g; memset(&g, 0, sizeof g); std::vector<Ktx2Slice> s2;
+                if (uvol_ktx2_parse(lv[k].data(), lv[k].size(), 0, g, s2) == 0) for (const Ktx2Slice &s : s2) if ((uint64_t)s.data_off + s.data_len > lv[k].size()) { fprintf(stderr, "fuzz_host: split level points outside itself\n"); abort(); }
+            }
+        }
         GuardedObj<Ktx2File> f; std::vector<Ktx2Slice> sl; rc = uvol_ktx2_parse(buf, n, 0, *f.p, sl);
         if (rc == 0) {          // what the device kernels will dereference must lie inside the file
             const Ktx2File &k = *f.p;
@@ -116,6 +125,12 @@ int main(int argc, char **argv) {
             for (int i = 0; i < 5; i++) for (int j = 0; j < 10; j++) for (int i2 = -1; i2 < 5; i2++) for (int j2 = 0; j2 < (i2 < 0 ? 1 : 10); j2++) {
                 std::vector<uint8_t> m = seed; memcpy(&m[off64[i]], &v64[j], 8); if (i2 >= 0) memcpy(&m[off64[i2]], &v64[j2], 8);
                 run_one(name, m.data(), m.size(), &ok); total++;
+            }
+            uint32_t nlev; memcpy(&nlev, &seed[40], 4);
+            if (nlev > 1 && nlev < 16 && seed.size() >= 80 + 24ull * nlev) {          // a mip chain: every entry of the level index, and the level / layer counts
+                for (uint32_t e = 0; e < 3 * nlev; e++) for (int j = 0; j < 10; j++) { std::vector<uint8_t> m = seed; memcpy(&m[80 + 8 * e], &v64[j], 8); run_one(name, m.data(), m.size(), &ok); total++; }
+                const uint32_t cnt[6] = {0u, 2u, 15u, 16u, 0x7FFFFFFFu, 0xFFFFFFFFu};
+                for (int f2 = 0; f2 < 2; f2++) for (int j = 0; j < 6; j++) { std::vector<uint8_t> m = seed; memcpy(&m[f2 ? 32 : 40], &cnt[j], 4); run_one(name, m.data(), m.size(), &ok); total++; }
             }
             const uint32_t v32[6] = {0xFFFFFFFFu, 0xFFFFFFFCu, 0x7FFFFFFFu, 0x80000000u, (uint32_t)L, 0u};
             for (int i = 0; i < 4; i++) for (int j = 0; j < 6; j++) { std::vector<uint8_t> m = seed; memcpy(&m[off32[i]], &v32[j], 4); run_one(name, m.data(), m.size(), &ok); total++; }

@@ -29,10 +29,15 @@ class Geometry(ctypes.Structure):
                 ("color", ctypes.POINTER(ctypes.c_float))]
 
 
+class TextureLevel(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("offset", ctypes.c_uint64), ("bytes", ctypes.c_uint64)]
+
+
 class Texture(ctypes.Structure):
     _fields_ = [("status", ctypes.c_int32), ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("layers", ctypes.c_uint32),
                 ("format", ctypes.c_uint32), ("has_alpha", ctypes.c_uint32), ("dfd_transfer", ctypes.c_uint32), ("dfd_flags", ctypes.c_uint32),
-                ("data", ctypes.POINTER(ctypes.c_uint8)), ("bytes", ctypes.c_uint64)]
+                ("data", ctypes.POINTER(ctypes.c_uint8)), ("bytes", ctypes.c_uint64),
+                ("levels", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("mips", ctypes.POINTER(TextureLevel))]
 
 
 class CortoMesh(ctypes.Structure):

@@ -4,6 +4,7 @@
 // header, level index, DFD, key/value block and the BasisLZ image descriptors are touched; the
 // codebooks, Huffman tables and slice payloads are decoded on the GPU.  Layout: SURVEY.md B.1/B.2.
 #include <string.h>
+#include <algorithm>
 #include <vector>
 #include "uvol_internal.h"
 
@@ -81,4 +82,55 @@ int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File 
         }
     }
     return UVOL_OK;
+}
+
+// Mip levels (levelCount > 1; the level / layer / face loop of src/lib/KTX2Loader.js:514-573).  The transcode machinery works on
+// single-level files, so a file with a mip chain is taken apart HERE, on the host, into one synthetic single-level KTX2 per level
+// (level 0 = the largest first): header with that level's dimensions and levelCount 1, a one-entry level index, the DFD and the
+// key/value block as they are, for BasisLZ the global data with the image descriptors of that level only (codebooks and tables
+// copied), then the level's payload (still Zstandard-compressed if the file's levels are).  Image descriptors are ordered level-major
+// (level 0 first), then by layer.  Returns the number of levels written to `out`, 0 when the file has a single level or is not a
+// KTX2 file this function understands (the caller passes it on unchanged and the parser reports on it), or a negative status when
+// the mip chain itself is inconsistent.  Cube faces (faceCount 6) are not taken apart: such files stay UNSUPPORTED.
+int uvol_ktx2_split_levels(const uint8_t *b, size_t len, std::vector<std::vector<uint8_t>> &out) {
+    if (!b || len < 104 || memcmp(b, KTX2_ID, 12)) return 0;
+    const uint32_t w = rd32(b + 20), h = rd32(b + 24), layers = rd32(b + 32), faces = rd32(b + 36), levels = rd32(b + 40), sc = rd32(b + 44);
+    if (levels <= 1 || faces != 1) return 0;
+    if (levels > 15 || w == 0 || h == 0 || w > 16384 || h > 16384 || ((w >> (levels - 1)) == 0 && (h >> (levels - 1)) == 0)) return UVOL_ERR_CORRUPT;
+    auto inside = [len](uint64_t off, uint64_t n) { return off <= len && n <= len - off; };
+    if (len < 80 + 24ull * levels) return UVOL_ERR_TRUNCATED;
+    const uint32_t dfdOff = rd32(b + 48), dfdLen = rd32(b + 52), kvdOff = rd32(b + 56), kvdLen = rd32(b + 60);
+    const uint64_t sgdOff = rd64(b + 64), sgdLen = rd64(b + 72);
+    if (!inside(dfdOff, dfdLen) || !inside(kvdOff, kvdLen) || !inside(sgdOff, sgdLen)) return UVOL_ERR_CORRUPT;
+    const uint32_t nl = layers ? layers : 1;
+    uint64_t cb_bytes = 0;                                   // BasisLZ: codebooks + tables (+ extended data) behind the image descriptors
+    if (sc == 1) {
+        if (sgdLen < 20 + 20ull * nl * levels) return UVOL_ERR_CORRUPT;
+        cb_bytes = sgdLen - 20 - 20ull * nl * levels;
+    }
+    for (uint32_t k = 0; k < levels; k++) {
+        const uint64_t lvOff = rd64(b + 80 + 24ull * k), lvLen = rd64(b + 88 + 24ull * k), lvU = rd64(b + 96 + 24ull * k);
+        if (!inside(lvOff, lvLen) || lvLen >= (1ull << 31)) return UVOL_ERR_TRUNCATED;
+        const uint64_t o_dfd = 104, o_kvd = (o_dfd + dfdLen + 3) & ~3ull, o_sgd = (o_kvd + kvdLen + 7) & ~7ull;
+        const uint64_t sgd2 = sc == 1 ? 20 + 20ull * nl + cb_bytes : 0, o_lv = (o_sgd + sgd2 + 15) & ~15ull;
+        std::vector<uint8_t> f((size_t)(o_lv + lvLen), 0);
+        memcpy(f.data(), b, 80);
+        const uint32_t lw = std::max(1u, w >> k), lh = std::max(1u, h >> k), one = 1;
+        auto w32 = [&](size_t at, uint32_t v) { memcpy(f.data() + at, &v, 4); };
+        auto w64 = [&](size_t at, uint64_t v) { memcpy(f.data() + at, &v, 8); };
+        w32(20, lw); w32(24, lh); w32(40, one);
+        w32(48, (uint32_t)o_dfd); w32(56, kvdLen ? (uint32_t)o_kvd : 0); w64(64, sgd2 ? o_sgd : 0); w64(72, sgd2);
+        w64(80, o_lv); w64(88, lvLen); w64(96, lvU);
+        memcpy(f.data() + o_dfd, b + dfdOff, dfdLen);
+        if (kvdLen) memcpy(f.data() + o_kvd, b + kvdOff, kvdLen);
+        if (sc == 1) {
+            const uint8_t *g = b + sgdOff;
+            memcpy(f.data() + o_sgd, g, 20);
+            memcpy(f.data() + o_sgd + 20, g + 20 + 20ull * nl * k, 20ull * nl);
+            memcpy(f.data() + o_sgd + 20 + 20ull * nl, g + 20 + 20ull * nl * levels, (size_t)cb_bytes);
+        }
+        memcpy(f.data() + o_lv, b + lvOff, (size_t)lvLen);
+        out.push_back(std::move(f));
+    }
+    return (int)levels;
 }

@@ -18,6 +18,7 @@
 #include "tma_bulk.h"
 
 int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
+int uvol_ktx2_split_levels(const uint8_t *b, size_t len, std::vector<std::vector<uint8_t>> &out);
 extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
 int uvol_uastc_launch(int device, const Ktx2File *dF, int32_t *status2, const uint8_t *dBlob, uint8_t *dOut, const uint32_t *dLayerList, int nlayers,
                       uint32_t max_blocks, int target, cudaStream_t st);
@@ -256,6 +257,9 @@ struct TexBatch {
     int n = 0; uint64_t blob_bytes = 0, scratch = 0, out = 0, bytes_in = 0; uint32_t max_blocks = 1, max_codebook = 0; bool any_alpha = false, any_zstd = false; int target = UVOL_TEX_RGBA32;
     size_t desc_bytes = 0, off_sl = 0, off_ll = 0, off_ul = 0; double parse_ms = 0; uint32_t launches = 0; int nev = 0;
     std::vector<uint32_t> ll_start, ul_start, sl_start;      // per file (+1): first entry in layer_list / uastc_layers / slices
+    // mip chains: the caller's files [0, n_user) -> the single-level files [0, n) the machinery works on (uvol_ktx2_split_levels)
+    int n_user = 0; std::vector<uint32_t> first_of, nlev; std::vector<int32_t> split_status; std::vector<std::vector<uint8_t>> synth;
+    std::vector<const uint8_t *> xdata; std::vector<size_t> xsize; std::vector<uvol_texture_level> mips;
 };
 void uvol_tex_batch_free(TexBatch *b) { delete b; }
 
@@ -386,6 +390,25 @@ static int ktx2_launch_range(uvol_ctx *ctx, int i0, int i1, cudaStream_t st, boo
 // few tens of milliseconds into the call instead of after the whole batch has been staged, uploaded and transcoded.
 static int ktx2_fresh(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target, int memory, cudaStream_t st) {
     const double t_begin = now_ms();
+    if (!ctx->tex) ctx->tex = new TexBatch();
+    {   // files with a mip chain are taken apart into one single-level file per level; everything below sees only those
+        TexBatch &X = *ctx->tex; X.n_user = n; X.first_of.assign((size_t)n, 0); X.nlev.assign((size_t)n, 1); X.split_status.assign((size_t)n, 0); X.synth.clear(); X.xdata.clear(); X.xsize.clear();
+        bool any = false;
+        for (int i = 0; i < n && !any; i++) any = data[i] && size[i] >= 44 && size[i] < (1ull << 31) && (data[i][40] | data[i][41] << 8 | data[i][42] << 16 | (uint32_t)data[i][43] << 24) > 1u;
+        if (any) {
+            std::vector<std::pair<int, int>> ref;          // per internal file: (caller's file, index into synth or -1)
+            for (int i = 0; i < n; i++) {
+                X.first_of[i] = (uint32_t)ref.size();
+                const size_t before = X.synth.size();
+                const int L = (data[i] && size[i] < (1ull << 31)) ? uvol_ktx2_split_levels(data[i], size[i], X.synth) : 0;
+                if (L > 0) { X.nlev[i] = (uint32_t)L; for (int k = 0; k < L; k++) ref.push_back({i, (int)(before + k)}); }
+                else { X.synth.resize(before); X.split_status[i] = L; ref.push_back({i, -1}); }
+            }
+            for (auto &r : ref) { if (r.second >= 0) { X.xdata.push_back(X.synth[r.second].data()); X.xsize.push_back(X.synth[r.second].size()); } else { X.xdata.push_back(data[r.first]); X.xsize.push_back(size[r.first]); } }
+            if (X.xdata.size() >= (1u << 19)) { ctx->set_error("too many mip levels in one batch"); return UVOL_ERR_ARG; }
+            data = X.xdata.data(); size = X.xsize.data(); n = (int)X.xdata.size();
+        } else for (int i = 0; i < n; i++) X.first_of[i] = (uint32_t)i;
+    }
     int rc = ktx2_prepare(ctx, data, size, n, target); if (rc) return rc;
     TexBatch &B = *ctx->tex; B.launches = 0;
     const size_t st_bytes = align_up(sizeof(TexState) * (size_t)n, 256);
@@ -468,15 +491,25 @@ static int ktx2_finish(uvol_ctx *ctx, int memory, uvol_texture *out, uvol_stats 
     UVOL_CUDA(ctx, cudaGetLastError());
     TexState *hSt = (TexState *)ctx->h_tstate.p; uint8_t *hO = (uint8_t *)ctx->ph_tout->p;
     uint8_t *base = memory == UVOL_MEM_HOST ? hO : (uint8_t *)ctx->d_out_tex.p; uint64_t bytes_out = 0;
-    for (int i = 0; i < n; i++) {
-        const Ktx2File &f = B.files[i]; uvol_texture &t = out[i];
+    auto out_bytes = [&](const Ktx2File &f) {
+        return B.target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * f.bx * f.by * 8 : (B.target == UVOL_TEX_BC7 || B.target == UVOL_TEX_ASTC_4x4 ? (uint64_t)f.layers * f.bx * f.by * 16 : (uint64_t)f.layers * f.width * f.height * 4);
+    };
+    B.mips.assign((size_t)n, uvol_texture_level());          // one entry per internal (single-level) file; a caller's file owns a run of them
+    for (int u = 0; u < B.n_user; u++) {
+        const uint32_t i0 = B.first_of[u], L = B.nlev[u];
+        const Ktx2File &f = B.files[i0]; uvol_texture &t = out[u];
         memset(&t, 0, sizeof t);
-        t.status = f.status ? f.status : hSt[i].status;
+        t.status = B.split_status[u];                        // an inconsistent mip chain
+        for (uint32_t k = 0; k < L && !t.status; k++) t.status = B.files[i0 + k].status ? B.files[i0 + k].status : hSt[i0 + k].status;      // any failed level fails the texture
         if (t.status) continue;
         t.width = f.width; t.height = f.height; t.layers = f.layers; t.format = (uint32_t)B.target; t.has_alpha = f.has_alpha;
         t.dfd_transfer = f.dfd_transfer; t.dfd_flags = f.dfd_flags;
-        t.bytes = B.target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * f.bx * f.by * 8 : (B.target == UVOL_TEX_BC7 || B.target == UVOL_TEX_ASTC_4x4 ? (uint64_t)f.layers * f.bx * f.by * 16 : (uint64_t)f.layers * f.width * f.height * 4);
-        t.data = base + f.o_rgba; bytes_out += t.bytes;
+        t.data = base + f.o_rgba; t.levels = L; t.mips = &B.mips[i0];
+        for (uint32_t k = 0; k < L; k++) {
+            const Ktx2File &g = B.files[i0 + k]; uvol_texture_level &m = B.mips[i0 + k];
+            m.width = g.width; m.height = g.height; m.offset = g.o_rgba - f.o_rgba; m.bytes = out_bytes(g);
+            t.bytes = m.offset + m.bytes; bytes_out += m.bytes;
+        }
     }
     sx.kernel_launches = B.launches; sx.bytes_in = B.bytes_in; sx.bytes_out = bytes_out; sx.scratch_bytes = B.scratch;
     if (ctx->profile) {
@@ -500,7 +533,7 @@ extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *da
     if (target_format != UVOL_TEX_RGBA32 && target_format != UVOL_TEX_ETC1 && target_format != UVOL_TEX_BC7 && target_format != UVOL_TEX_ASTC_4x4) { ctx->set_error("target formats: UVOL_TEX_RGBA32, UVOL_TEX_ETC1, UVOL_TEX_BC7, UVOL_TEX_ASTC_4x4"); return UVOL_ERR_UNSUPPORTED; }
     UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->stats, 0, sizeof ctx->stats);
-    if (n == 0) { if (ctx->tex) ctx->tex->n = 0; return UVOL_OK; }
+    if (n == 0) { if (ctx->tex) ctx->tex->n = ctx->tex->n_user = 0; return UVOL_OK; }
     const double t0 = now_ms();
     int rc = ktx2_fresh(ctx, data, size, n, target_format, memory, ctx->s2); if (rc) return rc;
     UVOL_CUDA(ctx, cudaStreamSynchronize(ctx->s2));
@@ -510,7 +543,7 @@ extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *da
 }
 
 extern "C" int uvol_replay_ktx2_batch(uvol_ctx *ctx, int memory, uvol_texture *out, int n) {
-    if (!ctx || !out || !ctx->tex || ctx->tex->n != n || n <= 0) return UVOL_ERR_ARG;
+    if (!ctx || !out || !ctx->tex || ctx->tex->n_user != n || n <= 0) return UVOL_ERR_ARG;
     UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->stats, 0, sizeof ctx->stats);
     const double t0 = now_ms();
@@ -549,7 +582,7 @@ extern "C" int uvol_decode_v2_batch(uvol_ctx *ctx, const uint8_t *const *drc, co
 
 // Same, on the batches still resident in HBM (no parse, no input upload).
 extern "C" int uvol_replay_v2_batch(uvol_ctx *ctx, int memory, uvol_geometry *out_geo, int n_drc, uvol_texture *out_tex, int n_ktx2) {
-    if (!ctx || (n_drc && (!ctx->geo || !out_geo)) || (n_ktx2 && (!ctx->tex || ctx->tex->n != n_ktx2 || !out_tex))) return UVOL_ERR_ARG;
+    if (!ctx || (n_drc && (!ctx->geo || !out_geo)) || (n_ktx2 && (!ctx->tex || ctx->tex->n_user != n_ktx2 || !out_tex))) return UVOL_ERR_ARG;
     UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->stats, 0, sizeof ctx->stats); memset(&ctx->stats_tex, 0, sizeof ctx->stats_tex);
     const double t0 = now_ms();

@@ -72,7 +72,7 @@ extern "C" int uvol_upload_etc2_batch(uvol_ctx *ctx, const uint8_t *const *data,
     }
     off = 0;
     for (int i = 0; i < n; i++) if (!out[i].status) {
-        out[i].width = (uint32_t)width; out[i].height = (uint32_t)height; out[i].layers = 1; out[i].format = UVOL_TEX_ETC2_RGB; out[i].data = base + off; out[i].bytes = per;
+        out[i].width = (uint32_t)width; out[i].height = (uint32_t)height; out[i].layers = 1; out[i].levels = 1; out[i].format = UVOL_TEX_ETC2_RGB; out[i].data = base + off; out[i].bytes = per;
         off += align_up(per, 128);
     }
     return UVOL_OK;

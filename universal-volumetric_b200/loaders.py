@@ -195,13 +195,17 @@ class KTX2Loader:
             if t.status != 0:
                 res.append({"status": int(t.status), "data": None})
                 continue
-            if target in (N.TEX_ETC1, N.TEX_BC7, N.TEX_ASTC_4x4):
-                nb = ((t.width + 3) // 4) * ((t.height + 3) // 4)
-                data = np.ctypeslib.as_array(t.data, (t.layers, nb, 8 if target == N.TEX_ETC1 else 16)).copy()
-            else:
-                data = np.ctypeslib.as_array(t.data, (t.layers, t.height, t.width, 4)).copy()
+            def level_array(w, h, offset):
+                p = ctypes.cast(ctypes.addressof(t.data.contents) + offset, ctypes.POINTER(ctypes.c_uint8))
+                if target in (N.TEX_ETC1, N.TEX_BC7, N.TEX_ASTC_4x4):
+                    return np.ctypeslib.as_array(p, (t.layers, ((w + 3) // 4) * ((h + 3) // 4), 8 if target == N.TEX_ETC1 else 16)).copy()
+                return np.ctypeslib.as_array(p, (t.layers, h, w, 4)).copy()
+            data = level_array(t.width, t.height, 0)
             res.append({"status": 0, "width": int(t.width), "height": int(t.height), "layers": int(t.layers), "hasAlpha": bool(t.has_alpha),
-                        "format": {N.TEX_ETC1: "RGB_ETC1_Format", N.TEX_BC7: "RGBA_BPTC_Format", N.TEX_ASTC_4x4: "RGBA_ASTC_4x4_Format"}.get(target, "RGBAFormat"), "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data})
+                        "format": {N.TEX_ETC1: "RGB_ETC1_Format", N.TEX_BC7: "RGBA_BPTC_Format", N.TEX_ASTC_4x4: "RGBA_ASTC_4x4_Format"}.get(target, "RGBAFormat"), "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data,
+                        # the reply's `mipmaps` (KTX2Loader.js:514-573): level 0 is `data`; UVOL content has exactly one level
+                        "mipmaps": [{"width": int(t.mips[k].width), "height": int(t.mips[k].height), "data": data if k == 0 else level_array(t.mips[k].width, t.mips[k].height, t.mips[k].offset)}
+                                    for k in range(int(t.levels))]})
         return res
 
 
