@@ -76,3 +76,14 @@ def emu_ktx2_split_levels(blob):
     rc = E.basis_emu_split_levels(blob, ctypes.c_size_t(len(blob)), files, sizes, 16)
     out = [ctypes.string_at(files[k], sizes[k]) for k in range(max(0, min(rc, 16)))]
     return rc, out
+
+
+def emu_ktx2_etc2a(blob):
+    """Target ETC2 RGBA through the product's per-block functions (csrc/basis_core.h) on the host: u8[layers, blocks, 16] (ETC1S sources only)."""
+    E = _load("libbasis_emu.so")
+    p = ctypes.POINTER(ctypes.c_uint8)(); w = ctypes.c_uint32(); h = ctypes.c_uint32(); l = ctypes.c_uint32()
+    rc = E.basis_emu_decode_etc2a(blob, ctypes.c_size_t(len(blob)), ctypes.byref(p), ctypes.byref(w), ctypes.byref(h), ctypes.byref(l))
+    if rc:
+        return {"status": rc}
+    nb = ((w.value + 3) // 4) * ((h.value + 3) // 4)
+    return {"status": 0, "width": w.value, "height": h.value, "layers": l.value, "blocks": np.ctypeslib.as_array(p, (l.value, nb, 16)).copy()}

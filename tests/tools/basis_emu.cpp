@@ -29,6 +29,8 @@ extern "C" int basis_emu_decode(const uint8_t *data, size_t len, uint8_t **rgba,
 extern "C" int basis_emu_decode_etc1(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 1); }
 // target BC7: *blocks receives layers * blocks * 16 bytes (ETC1S with or without alpha, UASTC)
 extern "C" int basis_emu_decode_bc7(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 2); }
+// target ETC2 RGBA: *blocks receives layers * blocks * 16 bytes (ETC1S files, with or without alpha)
+extern "C" int basis_emu_decode_etc2a(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 4); }
 // target ASTC 4x4: *blocks receives layers * blocks * 16 bytes (UASTC sources only, like the reference's ASTC option)
 extern "C" int basis_emu_decode_astc(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 3); }
 static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba, uint32_t *w, uint32_t *h, uint32_t *layers, int etc1) {
@@ -36,7 +38,7 @@ static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba
     const uint8_t *file = padded.data();
     Ktx2File f; memset(&f, 0, sizeof f); std::vector<Ktx2Slice> slices;
     int rc = uvol_ktx2_parse(file, len, 0, f, slices); if (rc) return rc;
-    if (f.is_uastc && etc1 == 1) return UVOL_ERR_UNSUPPORTED;
+    if (f.is_uastc && (etc1 == 1 || etc1 == 4)) return UVOL_ERR_UNSUPPORTED;
     if (!f.is_uastc && etc1 == 3) return UVOL_ERR_UNSUPPORTED;
     if (f.is_uastc) {          // the kernel's per-block function (uastc_core.h) over every block, Zstd levels inflated by the product's decoder
         const uint32_t nblk = f.bx * f.by;
@@ -122,6 +124,16 @@ static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba
         }
         return 0;
     }
+    if (etc1 == 4) {            // the ETC2 RGBA kernel's per-block functions (basis_core.h etc1s_alpha_to_eac + etc1s_to_etc1)
+        *rgba = (uint8_t *)malloc((size_t)f.layers * nblk * 16 + 16);
+        for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
+            const Etc1Words e = etc1s_to_etc1(eps[ep[L][bi]], sels[sel[L][bi]]);
+            const EacWords a = f.has_alpha ? etc1s_alpha_to_eac(eps[ep[f.layers + L][bi]], sels[sel[f.layers + L][bi]], ETC1S_EAC_MAP_INIT) : eac_opaque();
+            uint8_t *o = *rgba + ((size_t)L * nblk + bi) * 16;
+            memcpy(o, &a.x, 4); memcpy(o + 4, &a.y, 4); memcpy(o + 8, &e.x, 4); memcpy(o + 12, &e.y, 4);
+        }
+        return 0;
+    }
     if (etc1) {                 // the kernel's repack function (basis_core.h etc1s_to_etc1) over every block
         if (f.has_alpha) return UVOL_ERR_UNSUPPORTED;
         *rgba = (uint8_t *)malloc((size_t)f.layers * nblk * 8 + 8);
@@ -134,6 +146,10 @@ static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba
     *rgba = (uint8_t *)malloc((size_t)f.layers * f.width * f.height * 4);
     for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
         uint32_t rows[4][4]; etc1s_block_rows(eps[ep[L][bi]], sels[sel[L][bi]], rows);
+        if (f.has_alpha) {          // as k_etc1s_blocks: alpha = G of the alpha slice's block colour
+            const uint32_t aep = eps[ep[f.layers + L][bi]], ase = sels[sel[f.layers + L][bi]];
+            for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) { const uint32_t q = (ase >> (8 * y + 2 * x)) & 3u; rows[y][x] = (rows[y][x] & 0x00ffffffu) | (((etc1s_color(aep, (int)q) >> 8) & 255u) << 24); }
+        }
         const uint32_t xb = bi % f.bx, yb = bi / f.bx;
         for (uint32_t y = 0; y < 4 && yb * 4 + y < f.height; y++) for (uint32_t x = 0; x < 4 && xb * 4 + x < f.width; x++)
             memcpy(*rgba + ((size_t)L * f.width * f.height + (size_t)(yb * 4 + y) * f.width + xb * 4 + x) * 4, &rows[y][x], 4);

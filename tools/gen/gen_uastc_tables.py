@@ -187,6 +187,43 @@ def bise_encode_tables():
     return [trit[v] for v in range(243)], [quint[v] for v in range(125)]
 
 
+# ---- ETC2 EAC alpha (UVOL_TEX_ETC2_RGBA: the alpha slice of an ETC1S file re-expressed as an EAC block)
+ETC1_INTEN = [(2, 8), (5, 17), (9, 29), (13, 42), (18, 60), (24, 80), (33, 106), (47, 183)]          # (a, b): a block's values are g + {-b, -a, a, b}
+EAC_MOD = [[-3, -6, -9, -15, 2, 5, 8, 14], [-3, -7, -10, -13, 2, 6, 9, 12], [-2, -5, -8, -13, 1, 4, 7, 12], [-2, -4, -6, -13, 1, 3, 5, 12],
+           [-3, -6, -8, -12, 2, 5, 7, 11], [-3, -7, -9, -11, 2, 6, 8, 10], [-4, -7, -8, -11, 3, 6, 7, 10], [-3, -5, -8, -11, 2, 4, 7, 10],
+           [-2, -6, -8, -10, 1, 5, 7, 9], [-2, -5, -8, -10, 1, 4, 7, 9], [-2, -4, -8, -10, 1, 3, 7, 9], [-2, -5, -7, -10, 1, 4, 6, 9],
+           [-3, -4, -7, -10, 2, 3, 6, 9], [-1, -2, -3, -10, 0, 1, 2, 9], [-4, -6, -8, -9, 3, 5, 7, 8], [-3, -5, -7, -9, 2, 4, 6, 8]]
+
+
+def eac_map():
+    """For every ETC1S intensity table t and every non-empty set of used selectors (mask): the EAC {table, multiplier, base offset, index
+    per selector} with the least squared error on the unclamped values g + {-b, -a, a, b}.  Entry: table | mult << 4 | (offset + 128) << 8 |
+    idx0 << 16 | idx1 << 19 | idx2 << 22 | idx3 << 25; rows of EAC_MOD are checked for the format's symmetry (m[4 + k] == -m[k] - 1)."""
+    for row in EAC_MOD:
+        assert all(row[4 + k] == -row[k] - 1 for k in range(4)), row
+    out = []
+    for a, b in ETC1_INTEN:
+        vals = [-b, -a, a, b]
+        for mask in range(16):
+            if mask == 0:
+                out.append(0); continue
+            best = None
+            used = [k for k in range(4) if (mask >> k) & 1]
+            for tab in range(16):
+                for mult in range(1, 16):
+                    for off in range(-16, 17):
+                        err, idx = 0, [0, 0, 0, 0]
+                        for k in used:
+                            e, j = min((abs(vals[k] - (off + mult * m)), j) for j, m in enumerate(EAC_MOD[tab]))
+                            err += e * e; idx[k] = j
+                        key = (err, mult, abs(off), tab)
+                        if best is None or key < best[0]:
+                            best = (key, tab, mult, off, idx)
+            _, tab, mult, off, idx = best
+            out.append(tab | (mult << 4) | ((off + 128) << 8) | (idx[0] << 16) | (idx[1] << 19) | (idx[2] << 22) | (idx[3] << 25))
+    return out
+
+
 def unquant_endpoint(val, bits, trits, quints):
     lo, D = val & ((1 << bits) - 1), val >> bits
     if not trits and not quints:
@@ -272,6 +309,15 @@ def main():
     out += ["    " + ", ".join(str(v) for v in tr[i:i + 27]) + "," for i in range(0, 243, 27)]
     out += ["};", "static const uint8_t ASTC_QUINT_ENC_INIT[125] = {"]
     out += ["    " + ", ".join(str(v) for v in qu[i:i + 25]) + "," for i in range(0, 125, 25)]
+    out.append("};")
+    # ---- ETC2 RGBA target (basis_core.h etc1s_alpha_to_eac)
+    out += ["// EAC alpha: modifier tables of the format, and per ETC1S intensity table (row) and used-selector mask (column) the EAC block",
+            "// parameters that fit the slice's alpha values best: table | mult << 4 | (base offset + 128) << 8 | index of selector k << (16 + 3k).",
+            "static const int8_t EAC_MOD_INIT[16][8] = {"]
+    out += ["    {" + ", ".join(str(v) for v in row) + "}," for row in EAC_MOD]
+    out += ["};", "static const uint32_t ETC1S_EAC_MAP_INIT[8 * 16] = {"]
+    em = eac_map()
+    out += ["    " + ", ".join("0x%08xu" % w for w in em[i:i + 8]) + "," for i in range(0, 128, 8)]
     out.append("};")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "universal-volumetric_b200", "csrc", "uastc_tables.h")
     with open(path, "w") as f:

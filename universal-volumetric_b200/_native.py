@@ -14,6 +14,7 @@ TEX_RGBA32 = 0
 TEX_ETC1 = 1
 TEX_BC7 = 2
 TEX_ASTC_4x4 = 4
+TEX_ETC2_RGBA = 5
 TEX_ETC2_RGB = 3
 
 

@@ -256,6 +256,36 @@ UVOL_HD int basis_build_globals(const Ktx2File &f, const uint8_t *file, BasisGlo
 // sub-blocks share the 5:5:5 base colour and the intensity table), flip bit set, selectors re-ordered to ETC1's pixel indices
 // (column-major, value 0 1 2 3 = +a +b -a -b where the codebook stores 0 1 2 3 = -b -a +a +b).  Returned as the two 32-bit words a
 // little-endian store writes: x = bytes 0-3 (R, G, B, table / diff / flip), y = bytes 4-7 (index MSBs, then LSBs, big-endian).
+// ---- ETC2 RGBA target (UVOL_TEX_ETC2_RGBA): the 8-byte EAC alpha block that goes in front of the colour block.
+// Replaces transcodeImage(..., ETC2, ...) for ETC1S sources with alpha (`etc2Supported`: [ETC1, ETC2] -> RGB_ETC2 / RGBA_ETC2_EAC,
+// src/lib/KTX2Loader.js:619-627, the top-priority option for ETC1S).  The colour half is the ETC1 block as it is (differential mode with a
+// zero delta is the same block in ETC2).  The alpha half: an ETC1S alpha block holds four values g + {-b, -a, a, b}; `map` (generated,
+// tools/gen/gen_uastc_tables.py eac_map) gives per intensity table and set of used selectors the EAC {table, multiplier, base offset,
+// index per selector} that reproduces them best.  Lossy by at most a few levels (bounds in tests/test_etc2.py); the reference's own
+// table-driven conversion lives in the absent basis_transcoder WASM and cannot be bit-matched.
+// EAC layout (big-endian 64 bits): base 8 | multiplier 4 | table 4 | 16 x 3-bit indices, pixel (x, y) at position x * 4 + y, first pixel in
+// the top bits.  Returned as two little-endian words (bytes 0-3, 4-7).
+struct EacWords { uint32_t x, y; };
+UVOL_HD uint32_t eac_bswap(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
+UVOL_HD EacWords eac_pack(uint32_t base, uint32_t mult, uint32_t table, unsigned long long idx48) {
+    const unsigned long long be = ((unsigned long long)base << 56) | ((unsigned long long)mult << 52) | ((unsigned long long)table << 48) | idx48;
+    EacWords o; o.x = eac_bswap((uint32_t)(be >> 32)); o.y = eac_bswap((uint32_t)be);
+    return o;
+}
+UVOL_HD EacWords eac_opaque() { return eac_pack(255u, 1u, 13u, 0x924924924924ull); }      // table 13, index 4 (modifier 0) everywhere: 255
+UVOL_HD EacWords etc1s_alpha_to_eac(uint32_t aep, uint32_t asel, const uint32_t *map) {
+    uint32_t used = 0;
+    for (int i = 0; i < 16; i++) used |= 1u << ((asel >> (2 * i)) & 3u);
+    const uint32_t g5 = (aep >> 8) & 31u, g = (g5 << 3) | (g5 >> 2), e = map[((aep >> 24) & 7u) * 16u + used];
+    int base = (int)g + (int)((e >> 8) & 255u) - 128; base = base < 0 ? 0 : (base > 255 ? 255 : base);
+    unsigned long long idx = 0;
+    for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) {
+        const uint32_t q = (asel >> (8 * y + 2 * x)) & 3u, j = (e >> (16u + 3u * q)) & 7u;
+        idx |= (unsigned long long)j << (45 - 3 * (x * 4 + y));
+    }
+    return eac_pack((uint32_t)base, (e >> 4) & 15u, e & 15u, idx);
+}
+
 struct Etc1Words { uint32_t x, y; };
 UVOL_HD Etc1Words etc1s_to_etc1(uint32_t ep, uint32_t sel) {
     const uint32_t r5 = ep & 31u, g5 = (ep >> 8) & 31u, b5 = (ep >> 16) & 31u, inten = (ep >> 24) & 7u;

@@ -119,6 +119,8 @@ bool g_tables_ready[16] = {};
 
 __device__ __align__(16) uint32_t g_bc7_tables_etc1s[sizeof(Bc7Shared) / 4];      // second image for the ETC1S kernel in basis_transcode.cu (separate translation unit)
 const uint32_t *uvol_bc7_tables_device() { uint32_t *p = nullptr; cudaGetSymbolAddress((void **)&p, g_bc7_tables_etc1s); return p; }
+__device__ __align__(16) uint32_t g_eac_map[128];                                  // ETC1S alpha -> EAC parameters (basis_core.h etc1s_alpha_to_eac)
+const uint32_t *uvol_eac_map_device() { uint32_t *p = nullptr; cudaGetSymbolAddress((void **)&p, g_eac_map); return p; }
 
 // status2: the launcher's per-file {status, aux} pairs.  layer list entries: file << 12 | layer.
 // Uploads the table images once per device (synchronous).
@@ -132,6 +134,7 @@ int uvol_texture_tables_ready(int device) {
     Bc7Shared b; bc7_fill_tables(b);
     e = cudaMemcpyToSymbol(g_bc7_tables, &b, sizeof b); if (e != cudaSuccess) return (int)e;
     e = cudaMemcpyToSymbol(g_bc7_tables_etc1s, &b, sizeof b); if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(g_eac_map, ETC1S_EAC_MAP_INIT, sizeof ETC1S_EAC_MAP_INIT); if (e != cudaSuccess) return (int)e;
     AstcShared a; astc_fill_tables(a);
     e = cudaMemcpyToSymbol(g_astc_tables, &a, sizeof a); if (e != cudaSuccess) return (int)e;
     if (device >= 0 && device < 16) g_tables_ready[device] = true;

@@ -188,7 +188,8 @@ class KTX2Loader:
         """target = TEX_RGBA32 (default; data u8[layers, h, w, 4]), TEX_ETC1 (data u8[layers, blocks, 8], the reference's
         RGB_ETC1_Format / opaque RGB_ETC2_Format choice, KTX2Loader.js:619-636) or TEX_BC7 (data u8[layers, blocks, 16], its
         RGBA_BPTC_Format choice on desktop GPUs, :602-604) or TEX_ASTC_4x4 (u8[layers, blocks, 16], its RGBA_ASTC_4x4_Format choice
-        for UASTC sources, :592-600; lossless)."""
+        for UASTC sources, :592-600; lossless) or TEX_ETC2_RGBA (u8[layers, blocks, 16]: EAC alpha block + ETC1 colour block, its
+        RGBA_ETC2_EAC_Format choice for ETC1S sources, :619-627)."""
         raw = self.transcode_batch_raw(files, N.MEM_HOST, target)
         res = []
         for t in raw:
@@ -197,12 +198,12 @@ class KTX2Loader:
                 continue
             def level_array(w, h, offset):
                 p = ctypes.cast(ctypes.addressof(t.data.contents) + offset, ctypes.POINTER(ctypes.c_uint8))
-                if target in (N.TEX_ETC1, N.TEX_BC7, N.TEX_ASTC_4x4):
+                if target in (N.TEX_ETC1, N.TEX_BC7, N.TEX_ASTC_4x4, N.TEX_ETC2_RGBA):
                     return np.ctypeslib.as_array(p, (t.layers, ((w + 3) // 4) * ((h + 3) // 4), 8 if target == N.TEX_ETC1 else 16)).copy()
                 return np.ctypeslib.as_array(p, (t.layers, h, w, 4)).copy()
             data = level_array(t.width, t.height, 0)
             res.append({"status": 0, "width": int(t.width), "height": int(t.height), "layers": int(t.layers), "hasAlpha": bool(t.has_alpha),
-                        "format": {N.TEX_ETC1: "RGB_ETC1_Format", N.TEX_BC7: "RGBA_BPTC_Format", N.TEX_ASTC_4x4: "RGBA_ASTC_4x4_Format"}.get(target, "RGBAFormat"), "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data,
+                        "format": {N.TEX_ETC1: "RGB_ETC1_Format", N.TEX_BC7: "RGBA_BPTC_Format", N.TEX_ASTC_4x4: "RGBA_ASTC_4x4_Format", N.TEX_ETC2_RGBA: "RGBA_ETC2_EAC_Format"}.get(target, "RGBAFormat"), "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data,
                         # the reply's `mipmaps` (KTX2Loader.js:514-573): level 0 is `data`; UVOL content has exactly one level
                         "mipmaps": [{"width": int(t.mips[k].width), "height": int(t.mips[k].height), "data": data if k == 0 else level_array(t.mips[k].width, t.mips[k].height, t.mips[k].offset)}
                                     for k in range(int(t.levels))]})
