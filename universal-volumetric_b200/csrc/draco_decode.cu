@@ -1280,11 +1280,47 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
     B.max_alpha_ctx = B.max_alpha_attr = 1; B.maxnad = B.maxV = B.maxF = 0; B.maxattr = 0; B.bytes_in = 0; B.any_valence = B.any_standard = B.any_tagged = false; B.replans = 0;
     std::vector<DracoFrame> &frames = B.frames; std::vector<uint32_t> &aux = B.aux;
     uint64_t blob_bytes = 0;
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < n; i++) {          // where every file goes in the blob follows from the sizes alone
         DracoFrame &f = frames[i]; memset(&f, 0, sizeof f);
         f.file_off = blob_bytes; f.file_len = (uint32_t)size[i]; B.bytes_in += size[i];
         blob_bytes = align_up(blob_bytes + size[i] + 8, 16);
-        f.status = (data[i] && size[i] < (1ull << 31)) ? uvol_draco_parse(data[i], size[i], f, aux) : UVOL_ERR_ARG;
+    }
+    B.blob_bytes = blob_bytes;
+    UVOL_CUDA(ctx, ctx->h_blob.reserve(blob_bytes + 64));
+    {   // Structural parse + staging copy into the pinned blob, both in front of the first kernel: a large batch is split over a few
+        // threads, each parsing its frames into its own table area (spliced into `aux` afterwards, offsets rebased) and copying them.
+        const int nthreads = std::max(1, std::min(n, (B.bytes_in > (4ull << 20) && n >= 16) ? (ctx->cfg.staging_threads ? (int)ctx->cfg.staging_threads : uvol_staging_threads()) : 1));
+        const int per = (n + nthreads - 1) / nthreads;
+        std::vector<std::vector<uint32_t>> laux((size_t)nthreads);
+        auto work = [&](int t) {          // (uvol_draco_parse leaves file_off / file_len of the descriptor alone)
+            std::vector<uint32_t> &la = nthreads == 1 ? aux : laux[(size_t)t];
+            const int lo = t * per, hi = std::min(n, lo + per);
+            if (nthreads > 1) la.reserve((size_t)std::max(0, hi - lo) * 2048);
+            for (int i = lo; i < hi; i++) {
+                const bool have = data[i] && size[i] < (1ull << 31);
+                frames[i].status = have ? uvol_draco_parse(data[i], size[i], frames[i], la) : UVOL_ERR_ARG;
+                if (have) memcpy((uint8_t *)ctx->h_blob.p + frames[i].file_off, data[i], size[i]);
+            }
+        };
+        if (nthreads == 1) work(0);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthreads; t++) pool.emplace_back(work, t);
+            for (auto &t : pool) t.join();
+            for (int t = 0; t < nthreads; t++) {          // splice the table areas, rebasing what points into them
+                const uint32_t base = (uint32_t)aux.size();
+                aux.insert(aux.end(), laux[(size_t)t].begin(), laux[(size_t)t].end());
+                for (int i = t * per; i < std::min(n, (t + 1) * per); i++) {
+                    DracoFrame &f = frames[i];
+                    f.ts_off += base;
+                    for (int k = 0; k < 6; k++) f.ctx[k].prob_off += base;
+                    for (int j = 0; j < UVOL_MAX_ATTRS; j++) f.attr[j].sym.prob_off += base;
+                }
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        DracoFrame &f = frames[i];
         // resource limits (per item, before anything is reserved): a header may not ask for more faces than the configured cap, nor
         // for absurdly more faces than the file has bytes (the densest real streams stay below one face per byte)
         if (!f.status && ((uint64_t)f.nf > ctx->cfg.max_faces_per_frame || (uint64_t)f.nf > 4096 + 64ull * size[i])) f.status = UVOL_ERR_UNSUPPORTED;
@@ -1298,18 +1334,6 @@ static int draco_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t
         }
     }
     aux.push_back(0);
-    B.blob_bytes = blob_bytes;
-    UVOL_CUDA(ctx, ctx->h_blob.reserve(blob_bytes + 64));
-    {   // staging copy into the pinned blob, by a few threads when the batch is large (it sits in front of the first kernel)
-        auto copy_range = [&](int lo, int hi) { for (int i = lo; i < hi; i++) if (data[i] && size[i] < (1ull << 31)) memcpy((uint8_t *)ctx->h_blob.p + frames[i].file_off, data[i], size[i]); };
-        const int nthreads = B.bytes_in > (32ull << 20) ? uvol_staging_threads() : 1;
-        if (nthreads <= 1) copy_range(0, n);
-        else {
-            std::vector<std::thread> pool; const int per = (n + nthreads - 1) / nthreads;
-            for (int lo = 0; lo < n; lo += per) pool.emplace_back(copy_range, lo, std::min(n, lo + per));
-            for (auto &t : pool) t.join();
-        }
-    }
     draco_plan_phase1(frames, B.pl, cap_permille());
     B.cap_s2 = est_scale(B.pl.s2_est); B.cap_z2 = est_scale(B.pl.z2_est); B.cap_out = B.pl.out_index + est_scale(B.pl.out_est - B.pl.out_index);
     std::vector<Job> &jobs = B.jobs; jobs.reserve((size_t)n * 24);
