@@ -200,7 +200,7 @@ def cpu_sample(drc, ktx, seq, nseg):
     return drc[: nseg * seq], ktx[:nseg]
 
 
-TARGETS = {"rgba32": 0, "etc1": 1, "bc7": 2, "astc": 4}
+TARGETS = {"rgba32": 0, "etc1": 1, "bc7": 2, "astc": 4, "etc2": 5}
 
 
 def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex, fmt, target="rgba32"):
@@ -225,7 +225,7 @@ def stage_bytes(info, P_total, frames, bytes_in_geo, bytes_in_tex, fmt, target="
     t = {
         "slices": bytes_in_tex + frames * nblk * 5,                            # VLC bits in, {pred u8, delta/selector u16} out
         "resolve": frames * nblk * (1 + 2 + 2 + 2),
-        "blocks": frames * nblk * ((16 if fmt == "uastc" else 4) + {"rgba32": 64, "etc1": 8, "bc7": 16, "astc": 16}[target]),   # UASTC: 16 B block in; ETC1S: 2x u16 indices in; 64 B RGBA / 16 B BC7 or ASTC / 8 B ETC1 out
+        "blocks": frames * nblk * ((16 if fmt == "uastc" else 4) + {"rgba32": 64, "etc1": 8, "bc7": 16, "astc": 16, "etc2": 16}[target]),   # UASTC: 16 B block in; ETC1S: 2x u16 indices in; 64 B RGBA / 16 B BC7 or ASTC / 8 B ETC1 out
     }
     return g, t
 
@@ -373,6 +373,9 @@ def main():
     ncores = os.cpu_count() or 1
     if W["fmt"] == "corto":
         return bench_v1(args, W, rank, world, local)
+    # targets follow the reference's FORMAT_OPTIONS: ASTC is offered for UASTC sources only, ETC1 / ETC2 for ETC1S sources only
+    if (args.texture_target == "astc" and W["fmt"] != "uastc") or (args.texture_target in ("etc1", "etc2") and W["fmt"] != "etc1s"):
+        ap.error(f"--texture-target {args.texture_target} does not apply to the {W['fmt']} textures of workload {args.workload}")
 
     # ------------------------------------------------------------------ reference arm (CPU oracle)
     if args.impl == "reference":
