@@ -49,7 +49,10 @@ enum uvol_texture_format { UVOL_TEX_RGBA32 = 0, UVOL_TEX_ETC1 = 1, UVOL_TEX_BC7 
                            UVOL_TEX_ASTC_4x4 = 4,
                            UVOL_TEX_ETC2_RGBA = 5 /* `etc2Supported` with alpha (ETC2 / RGBA_ETC2_EAC_Format, :619-627, the top-priority option for ETC1S
                              sources): 16 bytes per block = EAC alpha block + the ETC1 colour block (exact); ETC1S sources only, opaque ones get a
-                             constant-255 alpha block; the alpha fit is lossy (<= 12 / 255 per texel, >= 42 dB; csrc/basis_core.h, tests/test_etc2.py) */ };
+                             constant-255 alpha block; the alpha fit is lossy (<= 12 / 255 per texel, >= 42 dB; csrc/basis_core.h, tests/test_etc2.py) */,
+                           UVOL_TEX_BC1 = 6, UVOL_TEX_BC3 = 7 /* `dxtSupported` (BC1 / BC3, RGB_S3TC_DXT1 / RGBA_S3TC_DXT5, :610-618), the fallback on desktop GPUs
+                             without BPTC: 8 bytes per block (BC1) or the BC4 alpha block + the BC1 block (BC3); ETC1S sources only; lossy (RGB565
+                             endpoints), decoded by Pillow's DXT decoder in tests/test_dxt.py */ };
 
 /* Result of one geometry frame.  Replaces the Draco worker reply
  *   {type:'decode', geometry:{index:{array:Uint32Array(F*3)}, attributes:[{name, array:Float32Array(P*itemSize), itemSize}]}}
@@ -79,7 +82,7 @@ typedef struct uvol_texture {
     uint32_t width, height, layers;
     uint32_t format;       /* uvol_texture_format */
     uint32_t has_alpha, dfd_transfer, dfd_flags;
-    uint8_t *data;         /* level 0.  RGBA32: u8[layers * width * height * 4]; ETC1: u8[layers * ceil(w/4) * ceil(h/4) * 8]; BC7, ASTC_4x4, ETC2_RGBA: ... * 16 */
+    uint8_t *data;         /* level 0.  RGBA32: u8[layers * width * height * 4]; ETC1: u8[layers * ceil(w/4) * ceil(h/4) * 8]; BC1: same * 8; BC7, ASTC_4x4, ETC2_RGBA, BC3: ... * 16 */
     uint64_t bytes;        /* level 0 when levels == 1; with a mip chain: up to the end of the last level (levels are 128-byte aligned) */
     uint32_t levels;       /* levelCount of the file (1 for UVOL content: scripts/Encoder.py writes no mips); cube faces are not supported */
     uint32_t reserved;
@@ -98,7 +101,7 @@ typedef struct uvol_stats {
 /* Tunables of a context (SURVEY 5 "config / flags").  The reference takes constructor arguments only (bufferDuration = 4,
  * intervalDuration = 2, src/Player.ts:50-51) and derives the texture target from the GPU's capabilities
  * (src/lib/KTX2Loader.js:591-689); here they are one struct.  uvol_config_default() fills the defaults and then applies the
- * environment overrides UVOL_TEXTURE_TARGET (rgba32 | etc1 | bc7 | astc | etc2), UVOL_CORTO_INDEX_U16, UVOL_STAGING_THREADS, UVOL_MAX_FACES,
+ * environment overrides UVOL_TEXTURE_TARGET (rgba32 | etc1 | bc7 | astc | etc2 | bc1 | bc3), UVOL_CORTO_INDEX_U16, UVOL_STAGING_THREADS, UVOL_MAX_FACES,
  * UVOL_MAX_TEXTURE_BYTES, UVOL_BUFFER_DURATION, UVOL_INTERVAL_DURATION. */
 typedef struct uvol_config {
     uint32_t struct_size;            /* sizeof(uvol_config) */

@@ -87,3 +87,15 @@ def emu_ktx2_etc2a(blob):
         return {"status": rc}
     nb = ((w.value + 3) // 4) * ((h.value + 3) // 4)
     return {"status": 0, "width": w.value, "height": h.value, "layers": l.value, "blocks": np.ctypeslib.as_array(p, (l.value, nb, 16)).copy()}
+
+
+def emu_ktx2_dxt(blob, bc3):
+    """Targets BC1 (bc3 = False: u8[layers, blocks, 8]) / BC3 (u8[layers, blocks, 16]) through the product's per-block functions on the host."""
+    E = _load("libbasis_emu.so")
+    p = ctypes.POINTER(ctypes.c_uint8)(); w = ctypes.c_uint32(); h = ctypes.c_uint32(); l = ctypes.c_uint32()
+    fn = E.basis_emu_decode_bc3 if bc3 else E.basis_emu_decode_bc1
+    rc = fn(blob, ctypes.c_size_t(len(blob)), ctypes.byref(p), ctypes.byref(w), ctypes.byref(h), ctypes.byref(l))
+    if rc:
+        return {"status": rc}
+    nb = ((w.value + 3) // 4) * ((h.value + 3) // 4)
+    return {"status": 0, "width": w.value, "height": h.value, "layers": l.value, "blocks": np.ctypeslib.as_array(p, (l.value, nb, 16 if bc3 else 8)).copy()}

@@ -29,6 +29,9 @@ extern "C" int basis_emu_decode(const uint8_t *data, size_t len, uint8_t **rgba,
 extern "C" int basis_emu_decode_etc1(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 1); }
 // target BC7: *blocks receives layers * blocks * 16 bytes (ETC1S with or without alpha, UASTC)
 extern "C" int basis_emu_decode_bc7(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 2); }
+// targets BC1 / BC3: *blocks receives layers * blocks * 8 / 16 bytes (ETC1S files)
+extern "C" int basis_emu_decode_bc1(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 5); }
+extern "C" int basis_emu_decode_bc3(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 6); }
 // target ETC2 RGBA: *blocks receives layers * blocks * 16 bytes (ETC1S files, with or without alpha)
 extern "C" int basis_emu_decode_etc2a(const uint8_t *data, size_t len, uint8_t **blocks, uint32_t *w, uint32_t *h, uint32_t *layers) { return basis_emu_decode_impl(data, len, blocks, w, h, layers, 4); }
 // target ASTC 4x4: *blocks receives layers * blocks * 16 bytes (UASTC sources only, like the reference's ASTC option)
@@ -38,7 +41,7 @@ static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba
     const uint8_t *file = padded.data();
     Ktx2File f; memset(&f, 0, sizeof f); std::vector<Ktx2Slice> slices;
     int rc = uvol_ktx2_parse(file, len, 0, f, slices); if (rc) return rc;
-    if (f.is_uastc && (etc1 == 1 || etc1 == 4)) return UVOL_ERR_UNSUPPORTED;
+    if (f.is_uastc && (etc1 == 1 || etc1 == 4 || etc1 == 5 || etc1 == 6)) return UVOL_ERR_UNSUPPORTED;
     if (!f.is_uastc && etc1 == 3) return UVOL_ERR_UNSUPPORTED;
     if (f.is_uastc) {          // the kernel's per-block function (uastc_core.h) over every block, Zstd levels inflated by the product's decoder
         const uint32_t nblk = f.bx * f.by;
@@ -121,6 +124,20 @@ static int basis_emu_decode_impl(const uint8_t *data, size_t len, uint8_t **rgba
             if (f.has_alpha) etc1s_to_bc7(B7, eps[ep[L][bi]], sels[sel[L][bi]], true, eps[ep[f.layers + L][bi]], sels[sel[f.layers + L][bi]], o);
             else etc1s_to_bc7(B7, eps[ep[L][bi]], sels[sel[L][bi]], false, 0, 0, o);
             memcpy(*rgba + ((size_t)L * nblk + bi) * 16, o, 16);
+        }
+        return 0;
+    }
+    if (etc1 == 5 || etc1 == 6) {          // the BC1 / BC3 kernel's per-block functions (basis_core.h etc1s_to_bc1 + etc1s_alpha_to_bc4)
+        const size_t bs = etc1 == 5 ? 8 : 16;
+        *rgba = (uint8_t *)malloc((size_t)f.layers * nblk * bs + 16);
+        for (uint32_t L = 0; L < f.layers; L++) for (uint32_t bi = 0; bi < nblk; bi++) {
+            const Bc1Words c = etc1s_to_bc1(eps[ep[L][bi]], sels[sel[L][bi]]);
+            uint8_t *o = *rgba + ((size_t)L * nblk + bi) * bs;
+            if (etc1 == 6) {
+                const Bc1Words a = f.has_alpha ? etc1s_alpha_to_bc4(eps[ep[f.layers + L][bi]], sels[sel[f.layers + L][bi]]) : bc4_opaque();
+                memcpy(o, &a.x, 4); memcpy(o + 4, &a.y, 4); o += 8;
+            }
+            memcpy(o, &c.x, 4); memcpy(o + 4, &c.y, 4);
         }
         return 0;
     }

@@ -15,6 +15,8 @@ TEX_ETC1 = 1
 TEX_BC7 = 2
 TEX_ASTC_4x4 = 4
 TEX_ETC2_RGBA = 5
+TEX_BC1 = 6
+TEX_BC3 = 7
 TEX_ETC2_RGB = 3
 
 

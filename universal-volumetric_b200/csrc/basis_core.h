@@ -286,6 +286,82 @@ UVOL_HD EacWords etc1s_alpha_to_eac(uint32_t aep, uint32_t asel, const uint32_t 
     return eac_pack((uint32_t)base, (e >> 4) & 15u, e & 15u, idx);
 }
 
+// ---- BC1 / BC3 targets (UVOL_TEX_BC1 / UVOL_TEX_BC3): `dxtSupported`, transcoderFormat [BC1, BC3] -> RGB_S3TC_DXT1 / RGBA_S3TC_DXT5
+// (src/lib/KTX2Loader.js:610-618), the reference's fallback on desktop GPUs without BPTC.  ETC1S sources: the block's darkest and
+// brightest SELECTED colours become the two RGB565 endpoints, every selector takes the nearest of the four BC1 colours; the BC3 alpha
+// block (BC4: two 8-bit endpoints, eight interpolants, 3-bit indices) is built the same way from the alpha slice.  Lossy (565
+// endpoints, thirds instead of ETC1S's intensity steps); decoded by Pillow's DXT1 / DXT5 decoder in tests/test_dxt.py, PSNR bounds
+// there.  Index layouts coincide with ETC1S's selector layout (pixel (x, y) at field 4y + x).
+UVOL_HD uint32_t bc1_q(uint32_t v, uint32_t bits) {                 // nearest code under MSB replication
+    const uint32_t maxq = (1u << bits) - 1u; uint32_t q = (v * maxq + 127u) / 255u, best = q, beste = 0xffffu;
+    for (uint32_t c = q ? q - 1u : 0u; c <= (q < maxq ? q + 1u : maxq); c++) {
+        const uint32_t e8 = bits == 5u ? ((c << 3) | (c >> 2)) : ((c << 2) | (c >> 4)), e = e8 > v ? e8 - v : v - e8;
+        if (e < beste) { beste = e; best = c; }
+    }
+    return best;
+}
+UVOL_HD uint32_t bc1_565(uint32_t rgb) { return (bc1_q(rgb & 255u, 5) << 11) | (bc1_q((rgb >> 8) & 255u, 6) << 5) | bc1_q((rgb >> 16) & 255u, 5); }
+UVOL_HD uint32_t bc1_rgb(uint32_t c) {                              // RGB565 -> packed RGB8
+    const uint32_t r = c >> 11, g = (c >> 5) & 63u, b = c & 31u;
+    return ((r << 3) | (r >> 2)) | (((g << 2) | (g >> 4)) << 8) | (((b << 3) | (b >> 2)) << 16);
+}
+UVOL_HD uint32_t bc1_dist(uint32_t a, uint32_t b) {
+    uint32_t d = 0;
+    for (int c = 0; c < 3; c++) { const uint32_t x = (a >> (8 * c)) & 255u, y = (b >> (8 * c)) & 255u; d += x > y ? x - y : y - x; }
+    return d;
+}
+UVOL_HD uint32_t bc1_mix(uint32_t a, uint32_t b) {                  // (2a + b) / 3 per channel
+    uint32_t o = 0;
+    for (int c = 0; c < 3; c++) o |= ((2u * ((a >> (8 * c)) & 255u) + ((b >> (8 * c)) & 255u)) / 3u) << (8 * c);
+    return o;
+}
+struct Bc1Words { uint32_t x, y; };
+UVOL_HD Bc1Words etc1s_to_bc1(uint32_t ep, uint32_t sel) {
+    uint32_t col[4], used = 0;
+    for (int k = 0; k < 4; k++) col[k] = etc1s_color(ep, k);
+    for (int i = 0; i < 16; i++) used |= 1u << ((sel >> (2 * i)) & 3u);
+    const uint32_t smin = used & 1u ? 0u : (used & 2u ? 1u : (used & 4u ? 2u : 3u)), smax = used & 8u ? 3u : (used & 4u ? 2u : (used & 2u ? 1u : 0u));
+    const uint32_t ca = bc1_565(col[smin]), cb = bc1_565(col[smax]);
+    Bc1Words o;
+    if (ca == cb) { o.x = ca | (cb << 16); o.y = 0; return o; }     // c0 == c1: index 0 everywhere is that colour
+    const uint32_t c0 = ca > cb ? ca : cb, c1 = ca > cb ? cb : ca;   // c0 > c1: the four-colour mode
+    uint32_t P[4]; P[0] = bc1_rgb(c0); P[1] = bc1_rgb(c1); P[2] = bc1_mix(P[0], P[1]); P[3] = bc1_mix(P[1], P[0]);
+    uint32_t map = 0;
+    for (uint32_t s = 0; s < 4; s++) {
+        uint32_t bestj = 0, beste = 0xffffffffu;
+        for (uint32_t j = 0; j < 4; j++) { const uint32_t e = bc1_dist(P[j], col[s]); if (e < beste) { beste = e; bestj = j; } }
+        map |= bestj << (2u * s);
+    }
+    uint32_t idx = 0;
+    for (int i = 0; i < 16; i++) idx |= ((map >> (2u * ((sel >> (2 * i)) & 3u))) & 3u) << (2 * i);
+    o.x = c0 | (c1 << 16); o.y = idx;
+    return o;
+}
+// BC4 alpha block of BC3 from an ETC1S alpha-slice block (alpha = G of its four colours); bc4_opaque: 255 everywhere
+UVOL_HD Bc1Words bc4_opaque() { Bc1Words o; o.x = 0xffffu; o.y = 0; return o; }
+UVOL_HD Bc1Words etc1s_alpha_to_bc4(uint32_t aep, uint32_t asel) {
+    uint32_t av[4], used = 0;
+    for (int k = 0; k < 4; k++) av[k] = (etc1s_color(aep, k) >> 8) & 255u;
+    for (int i = 0; i < 16; i++) used |= 1u << ((asel >> (2 * i)) & 3u);
+    const uint32_t smin = used & 1u ? 0u : (used & 2u ? 1u : (used & 4u ? 2u : 3u)), smax = used & 8u ? 3u : (used & 4u ? 2u : (used & 2u ? 1u : 0u));
+    const uint32_t a0 = av[smax], a1 = av[smin];
+    Bc1Words o;
+    if (a0 <= a1) { o.x = a0 | (a0 << 8); o.y = 0; return o; }      // one value (a0 == a1 selects the six-value mode: index 0 is a0)
+    uint32_t map = 0;
+    for (uint32_t s = 0; s < 4; s++) {
+        uint32_t bestj = 0, beste = 0xffffffffu;
+        for (uint32_t j = 0; j < 8; j++) {
+            const uint32_t v = j == 0 ? a0 : (j == 1 ? a1 : ((8u - j) * a0 + (j - 1u) * a1) / 7u), e = v > av[s] ? v - av[s] : av[s] - v;
+            if (e < beste) { beste = e; bestj = j; }
+        }
+        map |= bestj << (3u * s);
+    }
+    unsigned long long idx = 0;
+    for (int i = 0; i < 16; i++) idx |= (unsigned long long)((map >> (3u * ((asel >> (2 * i)) & 3u))) & 7u) << (3 * i);
+    o.x = a0 | (a1 << 8) | ((uint32_t)(idx & 0xffffu) << 16); o.y = (uint32_t)(idx >> 16);
+    return o;
+}
+
 struct Etc1Words { uint32_t x, y; };
 UVOL_HD Etc1Words etc1s_to_etc1(uint32_t ep, uint32_t sel) {
     const uint32_t r5 = ep & 31u, g5 = (ep >> 8) & 31u, b5 = (ep >> 16) & 31u, inten = (ep >> 24) & 7u;

@@ -245,6 +245,29 @@ __global__ void __launch_bounds__(256) k_etc1s_blocks_etc2a(const Ktx2File *file
     __stcs((uint4 *)(O + f.o_rgba + (size_t)L * nblk * 16) + bi, make_uint4(a.x, a.y, w.x, w.y));
 }
 
+// Block -> BC1 / BC3 (`dxtSupported`, src/lib/KTX2Loader.js:610-618): one 8-byte BC1 block, or the BC4 alpha block + the BC1 block, per thread
+// (basis_core.h etc1s_to_bc1 / etc1s_alpha_to_bc4).  grid = (ceil(nblk / 256), layer list).
+__global__ void __launch_bounds__(256) k_etc1s_blocks_dxt(const Ktx2File *files, const TexState *state, const Ktx2Slice *slices, const uint32_t *layer_list,
+                                                          const uint8_t *S, uint8_t *O, int bc3) {
+    const uint32_t ll = layer_list[blockIdx.y], fi = ll >> 12, L = ll & 4095;
+    const Ktx2File &f = files[fi];
+    if (f.status || state[fi].status || f.is_uastc) return;
+    const uint32_t nblk = f.bx * f.by, bi = blockIdx.x * 256 + threadIdx.x;
+    if (bi >= nblk) return;
+    const Ktx2Slice &sl = slices[f.first_slice + L];
+    const uint32_t *eps = (const uint32_t *)(S + f.o_endpoints), *sels = (const uint32_t *)(S + f.o_selectors);
+    const uint32_t ecm = f.endpoint_count - 1, scm = f.selector_count - 1;
+    const uint32_t ei = min((uint32_t)((const uint16_t *)(S + sl.o_ep))[bi], ecm), si = min((uint32_t)((const uint16_t *)(S + sl.o_sel))[bi], scm);
+    const Bc1Words w = etc1s_to_bc1(eps[ei], sels[si]);
+    if (!bc3) { ((uint2 *)(O + f.o_rgba + (size_t)L * nblk * 8))[bi] = make_uint2(w.x, w.y); return; }
+    Bc1Words a = bc4_opaque();
+    if (f.has_alpha) {
+        const Ktx2Slice &al = slices[f.first_slice + f.layers + L];
+        a = etc1s_alpha_to_bc4(eps[min((uint32_t)((const uint16_t *)(S + al.o_ep))[bi], ecm)], sels[min((uint32_t)((const uint16_t *)(S + al.o_sel))[bi], scm)]);
+    }
+    __stcs((uint4 *)(O + f.o_rgba + (size_t)L * nblk * 16) + bi, make_uint4(a.x, a.y, w.x, w.y));
+}
+
 // Block -> BC7 mode 5 (target format BC7, src/lib/KTX2Loader.js:602-604): 4 B (8 B with an alpha slice) of indices in, one 16-byte block
 // out per thread; a warp writes 512 contiguous bytes.  grid = (ceil(nblk / 256), layer list); per-block logic in bc7_core.h.
 __global__ void __launch_bounds__(256) k_etc1s_blocks_bc7(const Ktx2File *files, const TexState *state, const Ktx2Slice *slices, const uint32_t *layer_list,
@@ -314,9 +337,10 @@ static int ktx2_prepare(uvol_ctx *ctx, const uint8_t *const *data, const size_t 
         if (f.layers > 4095 || f.bx > 4096) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }
         const uint64_t nblk = (uint64_t)f.bx * f.by;
         if (target == UVOL_TEX_ETC1 && (f.is_uastc || f.has_alpha)) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }   // ETC1 target: opaque ETC1S sources only
+        if ((target == UVOL_TEX_BC1 || target == UVOL_TEX_BC3) && f.is_uastc) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }   // BC1 / BC3 targets: ETC1S sources only
         if (target == UVOL_TEX_ETC2_RGBA && f.is_uastc) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }            // ETC2 RGBA target: ETC1S sources only (UASTC would need an ETC1 encoder)
         if (target == UVOL_TEX_ASTC_4x4 && !f.is_uastc) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }             // ASTC target: UASTC sources only (KTX2Loader.js:592-600)
-        const uint64_t out_bytes = target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * nblk * 8 : (target == UVOL_TEX_BC7 || target == UVOL_TEX_ASTC_4x4 || target == UVOL_TEX_ETC2_RGBA ? (uint64_t)f.layers * nblk * 16 : (uint64_t)f.layers * f.width * f.height * 4);
+        const uint64_t out_bytes = target == UVOL_TEX_ETC1 || target == UVOL_TEX_BC1 ? (uint64_t)f.layers * nblk * 8 : (target == UVOL_TEX_BC7 || target == UVOL_TEX_ASTC_4x4 || target == UVOL_TEX_ETC2_RGBA || target == UVOL_TEX_BC3 ? (uint64_t)f.layers * nblk * 16 : (uint64_t)f.layers * f.width * f.height * 4);
         if (out_bytes > ctx->cfg.max_texture_bytes) { f.status = UVOL_ERR_UNSUPPORTED; slices.resize(slices_before); continue; }      // resource limit, per item
         if (nblk > B.max_blocks) B.max_blocks = (uint32_t)nblk;
         f.o_rgba = take(o, out_bytes);
@@ -397,6 +421,8 @@ static int ktx2_launch_range(uvol_ctx *ctx, int i0, int i1, cudaStream_t st, boo
     if (nll && B.target == UVOL_TEX_BC7) {
         UVOL_CUDA(ctx, (cudaError_t)uvol_texture_tables_ready(ctx->device));
         k_etc1s_blocks_bc7<<<dim3((B.max_blocks + 255) / 256, nll), 256, 0, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO, uvol_bc7_tables_device()); B.launches++;
+    } else if (nll && (B.target == UVOL_TEX_BC1 || B.target == UVOL_TEX_BC3)) {
+        k_etc1s_blocks_dxt<<<dim3((B.max_blocks + 255) / 256, nll), 256, 0, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO, B.target == UVOL_TEX_BC3 ? 1 : 0); B.launches++;
     } else if (nll && B.target == UVOL_TEX_ETC2_RGBA) {
         UVOL_CUDA(ctx, (cudaError_t)uvol_texture_tables_ready(ctx->device));
         k_etc1s_blocks_etc2a<<<dim3((B.max_blocks + 255) / 256, nll), 256, 0, st>>>(dF, dSt, dSl, dLL + ll0, dS, dO, uvol_eac_map_device()); B.launches++;
@@ -523,7 +549,7 @@ static int ktx2_finish(uvol_ctx *ctx, int memory, uvol_texture *out, uvol_stats 
     TexState *hSt = (TexState *)ctx->h_tstate.p; uint8_t *hO = (uint8_t *)ctx->ph_tout->p;
     uint8_t *base = memory == UVOL_MEM_HOST ? hO : (uint8_t *)ctx->d_out_tex.p; uint64_t bytes_out = 0;
     auto out_bytes = [&](const Ktx2File &f) {
-        return B.target == UVOL_TEX_ETC1 ? (uint64_t)f.layers * f.bx * f.by * 8 : (B.target == UVOL_TEX_BC7 || B.target == UVOL_TEX_ASTC_4x4 || B.target == UVOL_TEX_ETC2_RGBA ? (uint64_t)f.layers * f.bx * f.by * 16 : (uint64_t)f.layers * f.width * f.height * 4);
+        return B.target == UVOL_TEX_ETC1 || B.target == UVOL_TEX_BC1 ? (uint64_t)f.layers * f.bx * f.by * 8 : (B.target == UVOL_TEX_BC7 || B.target == UVOL_TEX_ASTC_4x4 || B.target == UVOL_TEX_ETC2_RGBA || B.target == UVOL_TEX_BC3 ? (uint64_t)f.layers * f.bx * f.by * 16 : (uint64_t)f.layers * f.width * f.height * 4);
     };
     B.mips.assign((size_t)n, uvol_texture_level());          // one entry per internal (single-level) file; a caller's file owns a run of them
     for (int u = 0; u < B.n_user; u++) {
@@ -561,7 +587,7 @@ static int ktx2_run_replay(uvol_ctx *ctx, int memory, uvol_texture *out) {
 
 extern "C" int uvol_transcode_ktx2_batch(uvol_ctx *ctx, const uint8_t *const *data, const size_t *size, int n, int target_format, int memory, uvol_texture *out) {
     if (!ctx || !out || n < 0 || (n > 0 && (!data || !size)) || n >= (1 << 19)) return UVOL_ERR_ARG;
-    if (target_format != UVOL_TEX_RGBA32 && target_format != UVOL_TEX_ETC1 && target_format != UVOL_TEX_BC7 && target_format != UVOL_TEX_ASTC_4x4 && target_format != UVOL_TEX_ETC2_RGBA) { ctx->set_error("target formats: UVOL_TEX_RGBA32, UVOL_TEX_ETC1, UVOL_TEX_BC7, UVOL_TEX_ASTC_4x4, UVOL_TEX_ETC2_RGBA"); return UVOL_ERR_UNSUPPORTED; }
+    if (target_format != UVOL_TEX_RGBA32 && target_format != UVOL_TEX_ETC1 && target_format != UVOL_TEX_BC7 && target_format != UVOL_TEX_ASTC_4x4 && target_format != UVOL_TEX_ETC2_RGBA && target_format != UVOL_TEX_BC1 && target_format != UVOL_TEX_BC3) { ctx->set_error("target formats: UVOL_TEX_RGBA32, UVOL_TEX_ETC1, UVOL_TEX_BC7, UVOL_TEX_ASTC_4x4, UVOL_TEX_ETC2_RGBA, UVOL_TEX_BC1, UVOL_TEX_BC3"); return UVOL_ERR_UNSUPPORTED; }
     UVOL_CUDA(ctx, cudaSetDevice(ctx->device));
     memset(&ctx->stats, 0, sizeof ctx->stats);
     if (n == 0) { if (ctx->tex) ctx->tex->n = ctx->tex->n_user = 0; return UVOL_OK; }

@@ -20,7 +20,7 @@ extern "C" void uvol_config_default(uvol_config *cfg) {
     auto env_f64 = [](const char *name, double &v) { const char *e = getenv(name); if (e && *e) { char *end = nullptr; const double x = strtod(e, &end); if (end && *end == 0 && x > 0) v = x; } };
     uint64_t t = cfg->texture_target, u16 = 0, thr = 0;
     if (const char *e = getenv("UVOL_TEXTURE_TARGET")) {
-        if (!strcmp(e, "rgba32")) t = UVOL_TEX_RGBA32; else if (!strcmp(e, "etc1")) t = UVOL_TEX_ETC1; else if (!strcmp(e, "bc7")) t = UVOL_TEX_BC7; else if (!strcmp(e, "astc")) t = UVOL_TEX_ASTC_4x4; else if (!strcmp(e, "etc2")) t = UVOL_TEX_ETC2_RGBA; else env_u64("UVOL_TEXTURE_TARGET", t);
+        if (!strcmp(e, "rgba32")) t = UVOL_TEX_RGBA32; else if (!strcmp(e, "etc1")) t = UVOL_TEX_ETC1; else if (!strcmp(e, "bc7")) t = UVOL_TEX_BC7; else if (!strcmp(e, "astc")) t = UVOL_TEX_ASTC_4x4; else if (!strcmp(e, "etc2")) t = UVOL_TEX_ETC2_RGBA; else if (!strcmp(e, "bc1")) t = UVOL_TEX_BC1; else if (!strcmp(e, "bc3")) t = UVOL_TEX_BC3; else env_u64("UVOL_TEXTURE_TARGET", t);
     }
     env_u64("UVOL_CORTO_INDEX_U16", u16); env_u64("UVOL_STAGING_THREADS", thr);
     cfg->texture_target = (uint32_t)t; cfg->corto_index_u16 = (uint32_t)(u16 != 0); cfg->staging_threads = (uint32_t)thr;
@@ -35,7 +35,7 @@ extern "C" int uvol_get_config(const uvol_ctx *c, uvol_config *out) { if (!c || 
 extern "C" int uvol_create_with_config(int device, const uvol_config *cfg, uvol_ctx **out) {
     if (!out) return UVOL_ERR_ARG;
     if (cfg && cfg->struct_size != sizeof(uvol_config)) return UVOL_ERR_ARG;
-    if (cfg && (cfg->texture_target > UVOL_TEX_ETC2_RGBA || cfg->texture_target == UVOL_TEX_ETC2_RGB)) return UVOL_ERR_ARG;
+    if (cfg && (cfg->texture_target > UVOL_TEX_BC3 || cfg->texture_target == UVOL_TEX_ETC2_RGB)) return UVOL_ERR_ARG;
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return UVOL_ERR_CUDA;   // no CPU fallback

@@ -189,7 +189,8 @@ class KTX2Loader:
         RGB_ETC1_Format / opaque RGB_ETC2_Format choice, KTX2Loader.js:619-636) or TEX_BC7 (data u8[layers, blocks, 16], its
         RGBA_BPTC_Format choice on desktop GPUs, :602-604) or TEX_ASTC_4x4 (u8[layers, blocks, 16], its RGBA_ASTC_4x4_Format choice
         for UASTC sources, :592-600; lossless) or TEX_ETC2_RGBA (u8[layers, blocks, 16]: EAC alpha block + ETC1 colour block, its
-        RGBA_ETC2_EAC_Format choice for ETC1S sources, :619-627)."""
+        RGBA_ETC2_EAC_Format choice for ETC1S sources, :619-627) or TEX_BC1 / TEX_BC3 (u8[layers, blocks, 8 / 16], its RGB_S3TC_DXT1 /
+        RGBA_S3TC_DXT5 fallback, :610-618; ETC1S sources)."""
         raw = self.transcode_batch_raw(files, N.MEM_HOST, target)
         res = []
         for t in raw:
@@ -198,12 +199,12 @@ class KTX2Loader:
                 continue
             def level_array(w, h, offset):
                 p = ctypes.cast(ctypes.addressof(t.data.contents) + offset, ctypes.POINTER(ctypes.c_uint8))
-                if target in (N.TEX_ETC1, N.TEX_BC7, N.TEX_ASTC_4x4, N.TEX_ETC2_RGBA):
-                    return np.ctypeslib.as_array(p, (t.layers, ((w + 3) // 4) * ((h + 3) // 4), 8 if target == N.TEX_ETC1 else 16)).copy()
+                if target in (N.TEX_ETC1, N.TEX_BC7, N.TEX_ASTC_4x4, N.TEX_ETC2_RGBA, N.TEX_BC1, N.TEX_BC3):
+                    return np.ctypeslib.as_array(p, (t.layers, ((w + 3) // 4) * ((h + 3) // 4), 8 if target in (N.TEX_ETC1, N.TEX_BC1) else 16)).copy()
                 return np.ctypeslib.as_array(p, (t.layers, h, w, 4)).copy()
             data = level_array(t.width, t.height, 0)
             res.append({"status": 0, "width": int(t.width), "height": int(t.height), "layers": int(t.layers), "hasAlpha": bool(t.has_alpha),
-                        "format": {N.TEX_ETC1: "RGB_ETC1_Format", N.TEX_BC7: "RGBA_BPTC_Format", N.TEX_ASTC_4x4: "RGBA_ASTC_4x4_Format", N.TEX_ETC2_RGBA: "RGBA_ETC2_EAC_Format"}.get(target, "RGBAFormat"), "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data,
+                        "format": {N.TEX_ETC1: "RGB_ETC1_Format", N.TEX_BC7: "RGBA_BPTC_Format", N.TEX_ASTC_4x4: "RGBA_ASTC_4x4_Format", N.TEX_ETC2_RGBA: "RGBA_ETC2_EAC_Format", N.TEX_BC1: "RGB_S3TC_DXT1_Format", N.TEX_BC3: "RGBA_S3TC_DXT5_Format"}.get(target, "RGBAFormat"), "dfdTransferFn": int(t.dfd_transfer), "dfdFlags": int(t.dfd_flags), "data": data,
                         # the reply's `mipmaps` (KTX2Loader.js:514-573): level 0 is `data`; UVOL content has exactly one level
                         "mipmaps": [{"width": int(t.mips[k].width), "height": int(t.mips[k].height), "data": data if k == 0 else level_array(t.mips[k].width, t.mips[k].height, t.mips[k].offset)}
                                     for k in range(int(t.levels))]})
