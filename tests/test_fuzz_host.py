@@ -23,6 +23,8 @@ def test_host_parsers_survive_mutations(built, tmp_path):
     from test_ktx2_mips import etc1s_chain, uastc_chain          # mip chains: the splitter (uvol_ktx2_split_levels) reads the same untrusted bytes
     p = tmp_path / "uastc_mips.ktx2"; p.write_bytes(uastc_chain()[0]); seeds.append(str(p))
     p = tmp_path / "etc1s_mips.ktx2"; p.write_bytes(etc1s_chain()[0]); seeds.append(str(p))
+    import glob
+    seeds += sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corto", "*.crt")))[:3]      # V1 Corto frames (made by the reference's encoder)
     small = synth.make_sequence(1, 500, 32, want_textures=False, seed=5)[0][0]
     p = tmp_path / "small.drc"; p.write_bytes(small); seeds.append(str(p))
     rings, segs = synth.sphere_dims(500); fp, fu, uvs, _ = synth.sphere_topology(rings, segs); pos = synth.sphere_frame(rings, segs, 0.1, 5)

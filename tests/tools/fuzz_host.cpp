@@ -21,6 +21,7 @@
 int uvol_draco_parse(const uint8_t *data, size_t len, DracoFrame &f, std::vector<uint32_t> &aux);
 int uvol_ktx2_parse(const uint8_t *b, size_t len, uint32_t file_index, Ktx2File &f, std::vector<Ktx2Slice> &slices);
 int uvol_ktx2_split_levels(const uint8_t *b, size_t len, std::vector<std::vector<uint8_t>> &out);
+#include "../../universal-volumetric_b200/csrc/corto_parse.h"
 extern "C" int uvol_zstd_inflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
 
 static uint64_t rng_state;
@@ -68,6 +69,18 @@ static void run_one(const std::string &name, const uint8_t *p, size_t n, long *o
             else if (!k.zstd) in = in && (uint64_t)k.level_off + (uint64_t)k.layers * k.bx * k.by * 16 <= n;
             else in = in && (uint64_t)k.z_src_off + k.z_src_len <= n;
             if (!in) { fprintf(stderr, "fuzz_host: accepted KTX2 descriptor points outside the file\n"); abort(); }
+        }
+    }
+    else if (name.size() > 4 && name.substr(name.size() - 4) == ".crt") {          // V1 Corto frame: header + section walk (corto_parse.h)
+        GuardedObj<CortoFrame> f; std::vector<uint32_t> aux; rc = corto_parse(buf, n, *f.p, aux, 1ull << 24);
+        if (rc == 0) {          // every section the kernels will read lies inside the file, and the counts are what the sections can hold
+            const CortoFrame &c = *f.p; bool in = true;
+            auto tun = [&](const TunBlock &t) { return (uint64_t)t.data_off + t.csize <= n && (t.nsym == 0xffffffffu || (uint64_t)t.probs_off + 2ull * t.nsym <= n); };
+            auto bits = [&](const BitBlock &b) { return (uint64_t)b.data_off + 4ull * b.nwords <= n; };
+            in = in && tun(c.clers) && bits(c.ibits) && c.nattr >= 1 && c.nattr <= CORTO_MAX_ATTRS && c.pos_attr >= 0 && c.pos_attr < c.nattr;
+            for (int a = 0; a < c.nattr && in; a++) { in = in && bits(c.attr[a].bits) && c.attr[a].nlogs >= 1 && c.attr[a].nlogs <= 4; for (int k = 0; k < c.attr[a].nlogs && in; k++) in = in && tun(c.attr[a].logs[k]); }
+            in = in && (uint64_t)c.nface <= (uint64_t)c.clers.size + 1 && c.groups_off + (uint64_t)c.ngroups <= aux.size();
+            if (!in) { fprintf(stderr, "fuzz_host: accepted Corto descriptor points outside the file\n"); abort(); }
         }
     }
     else { const size_t cap = g_zcap; Guarded out = guarded(cap, false); size_t got = 0; rc = uvol_zstd_inflate(buf, n, out.p, cap, &got); munmap(out.base, out.map); }
@@ -136,6 +149,11 @@ int main(int argc, char **argv) {
             for (int i = 0; i < 4; i++) for (int j = 0; j < 6; j++) { std::vector<uint8_t> m = seed; memcpy(&m[off32[i]], &v32[j], 4); run_one(name, m.data(), m.size(), &ok); total++; }
             uint32_t kvd; memcpy(&kvd, &seed[56], 4);
             if ((uint64_t)kvd + 4 <= L) for (int j = 0; j < 6; j++) { std::vector<uint8_t> m = seed; memcpy(&m[kvd], &v32[j], 4); run_one(name, m.data(), m.size(), &ok); total++; }   // keyAndValueByteLength
+        }
+        if (name.size() > 4 && name.substr(name.size() - 4) == ".crt") {          // every 32-bit field of the header / section heads with extreme values
+            const uint32_t v32[7] = {0xFFFFFFFFu, 0x7FFFFFFFu, 0x80000000u, (uint32_t)seed.size(), 1u << 27, 1u << 26, 0u};
+            const size_t lim = seed.size() < 4096 ? seed.size() : 4096;
+            for (size_t at = 0; at + 4 <= lim; at++) for (int j = 0; j < 7; j++) { std::vector<uint8_t> m = seed; memcpy(&m[at], &v32[j], 4); run_one(name, m.data(), m.size(), &ok); total++; }
         }
         if (name.size() > 4 && name.substr(name.size() - 4) == ".drc") {
             static const uint8_t vi[3][5] = {{0xFF, 0xFF, 0xFF, 0xFF, 0x07}, {0xFF, 0xFF, 0xFF, 0xFF, 0x0F}, {0xFE, 0xFF, 0xFF, 0xFF, 0x07}};
