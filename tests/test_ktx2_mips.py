@@ -96,6 +96,14 @@ def test_split_levels_host_logic(built):
             if zl is None:          # (the oracle reads no Zstandard levels; the product's inflater is pinned to libzstd in test_zstd.py)
                 o = oracle_ktx2(f)
                 assert o["status"] == 0 and np.array_equal(o["rgba"], expect[k])
+    # a full chain of a ragged texture: 52x38 -> 26x19 -> 13x9 -> 6x4 -> 3x2 -> 1x1 (every level max(1, base >> k), partial blocks at every size)
+    dims = [(max(1, 52 >> k), max(1, 38 >> k)) for k in range(6)]
+    singles = [synth.encode_uastc(synth.texture_layers(64, 0, 1, 50 + k)[:, :h, :w], mode_mask=synth.UASTC_ALL_MODES, seed=50 + k) for k, (w, h) in enumerate(dims)]
+    rc, files = emu_ktx2_split_levels(merge_uastc_levels(singles))
+    assert rc == 6
+    for k, f in enumerate(files):
+        e, o = emu_ktx2(f), oracle_ktx2(singles[k])
+        assert e["status"] == 0 and e["rgba"].shape[1:3] == (dims[k][1], dims[k][0]) and np.array_equal(e["rgba"], o["rgba"]), k
     blob, expect = etc1s_chain()
     rc, files = emu_ktx2_split_levels(blob)
     assert rc == 3
