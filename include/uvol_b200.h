@@ -193,6 +193,15 @@ int uvol_sequence_get_info(const uvol_sequence *seq, uvol_sequence_info *out);
 int uvol_sequence_url(const uvol_sequence *seq, int kind, int number, char *buf, size_t cap);
 /* time -> geometry frame, texture segment, layer inside the segment (src/V2/player.ts:43-45,418-420,446) */
 int uvol_sequence_frames_at(const uvol_sequence *seq, double t, uint32_t *geometry_frame, uint32_t *segment, uint32_t *layer);
+/* Playback planning, the decode side of V2Player.fetchBuffers' leaky bucket (src/V2/player.ts:272-323): given the clock t and the last
+ * frame / segment already requested (*last_geometry / *last_segment, -1 at the start; updated), the contiguous ranges that bring the
+ * buffer up to `buffer_duration_s` whole seconds ahead -- to be handed to uvol_decode_range as ONE batch instead of one worker request per
+ * file.  Either count may come back 0.  uvol_sequence_keep_from: what removePlayedBuffer keeps at time t (:531-562: frames / segments
+ * older than ceil(120 / fps) behind the clock may be dropped by the caller's mesh / texture maps). */
+typedef struct uvol_fetch_plan { int32_t first_frame, n_frames, first_segment, n_segments; } uvol_fetch_plan;
+int uvol_sequence_fetch_window(const uvol_sequence *seq, double t, int32_t *last_geometry, int32_t *last_segment, double buffer_duration_s,
+                               uvol_fetch_plan *plan);
+int uvol_sequence_keep_from(const uvol_sequence *seq, double t, int32_t *first_frame_to_keep, int32_t *first_segment_to_keep);
 /* V2: frames [first_frame, +n_frames) and segments [first_segment, +n_segments) in one uvol_decode_v2_batch call (texture target =
  * uvol_config.texture_target); a missing file is a per-item UVOL_STATUS_IO */
 int uvol_decode_range(uvol_sequence *seq, int first_frame, int n_frames, int first_segment, int n_segments, int memory,

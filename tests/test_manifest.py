@@ -2,6 +2,7 @@
 (src/utils.ts, src/V2/player.ts); frame sharding covers every frame exactly once (also across 2 gloo ranks)."""
 import importlib
 import json
+import math
 import os
 import sys
 
@@ -342,6 +343,23 @@ def test_native_sequence_open_matches_python_manifest(tmp_path):
             assert L.uvol_sequence_frames_at(h, t, ctypes.byref(g), ctypes.byref(s), ctypes.byref(l)) == 0
             w = py.frames_at(t)
             assert (g.value, s.value, l.value) == (w["geometry_frame"], w["segment"], w["layer"])
+        # playback planning: the native fetch window / eviction thresholds follow manifest.py (= fetchBuffers / removePlayedBuffer) along a whole clip
+        class Plan(ctypes.Structure):
+            _fields_ = [("first_frame", ctypes.c_int32), ("n_frames", ctypes.c_int32), ("first_segment", ctypes.c_int32), ("n_segments", ctypes.c_int32)]
+        L.uvol_sequence_fetch_window.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), ctypes.c_double, ctypes.POINTER(Plan)]
+        L.uvol_sequence_keep_from.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
+        lg = ctypes.c_int32(-1); ls = ctypes.c_int32(-1); plg, pls = -1, -1
+        pb = man.V2Playback(py, lambda g, s_: ({}, {}), buffer_duration=4)
+        for step in range(0, 120):
+            t = step * 0.1
+            geo, tex, plg, pls = py.fetch_window(t, plg, pls, 4)
+            plan = Plan(); assert L.uvol_sequence_fetch_window(h, t, ctypes.byref(lg), ctypes.byref(ls), 4.0, ctypes.byref(plan)) == 0
+            assert (lg.value, ls.value) == (plg, pls)
+            assert list(range(plan.first_frame, plan.first_frame + plan.n_frames)) == geo and list(range(plan.first_segment, plan.first_segment + plan.n_segments)) == tex
+            kf = ctypes.c_int32(); ks = ctypes.c_int32(); assert L.uvol_sequence_keep_from(h, t, ctypes.byref(kf), ctypes.byref(ks)) == 0
+            at = py.frames_at(t)
+            assert kf.value == at["geometry_frame"] - math.ceil(120 / 30) and ks.value == at["segment"] - math.ceil(120 / (30 * 5))
+        assert lg.value == 249 and ls.value == 49                  # the whole clip was requested exactly once
         L.uvol_close(h)
     v1 = man.emit_v1(30, [(100, 196, 1500), (101, 198, 1520), (99, 194, 1480)])
     p = tmp_path / "clip.manifest"; p.write_text(json.dumps(v1))

@@ -11,6 +11,7 @@
 #include <string.h>
 #include <math.h>
 #include <memory>
+#include <algorithm>
 #include <string>
 #include <utility>
 #include <vector>
@@ -219,6 +220,32 @@ extern "C" int uvol_sequence_frames_at(const uvol_sequence *s, double t, uint32_
     if (geometry_frame) *geometry_frame = (uint32_t)gf;
     if (segment) *segment = (uint32_t)(tf / s->seq_size);
     if (layer) *layer = (uint32_t)(tf % s->seq_size);
+    return UVOL_OK;
+}
+
+// fetchBuffers' leaky bucket (src/V2/player.ts:272-323), as manifest.py V2Manifest.fetch_window: for every whole second i of the look-ahead the
+// request grows to min(current + (i + 1) * per-second, last index); what is new since the last request is one contiguous range.
+extern "C" int uvol_sequence_fetch_window(const uvol_sequence *s, double t, int32_t *last_geometry, int32_t *last_segment, double buffer_duration_s, uvol_fetch_plan *plan) {
+    if (!s || s->version != 2 || !s->seq_size || !last_geometry || !last_segment || !plan || buffer_duration_s < 0) return UVOL_ERR_ARG;
+    const long gsize = (long)s->geo_fps, cur_g = (long)floor(s->geo_fps * t + 0.5);
+    const long tsize = (long)ceil(s->tex_fps / (double)s->seq_size), cur_s = (long)floor(s->tex_fps * t + 0.5) / (long)s->seq_size;
+    const long g_last = (long)s->geo_frames - 1, s_last = (long)s->seq_count - 1;
+    long lg = *last_geometry, ls = *last_segment;
+    plan->first_frame = (int32_t)(lg + 1); plan->first_segment = (int32_t)(ls + 1);
+    for (long i = 0; i < (long)buffer_duration_s; i++) {
+        const long g_end = std::min(cur_g + (i + 1) * gsize, g_last), s_end = std::min(cur_s + (i + 1) * tsize, s_last);
+        if (lg != g_last && lg < g_end) lg = g_end;
+        if (ls != s_last && ls < s_end) ls = s_end;
+    }
+    plan->n_frames = (int32_t)(lg - *last_geometry); plan->n_segments = (int32_t)(ls - *last_segment);
+    *last_geometry = (int32_t)lg; *last_segment = (int32_t)ls;
+    return UVOL_OK;
+}
+extern "C" int uvol_sequence_keep_from(const uvol_sequence *s, double t, int32_t *first_frame_to_keep, int32_t *first_segment_to_keep) {
+    if (!s || s->version != 2 || !s->seq_size || s->geo_fps <= 0 || s->tex_fps <= 0) return UVOL_ERR_ARG;
+    const long gf = (long)floor(s->geo_fps * t + 0.5), seg = (long)floor(s->tex_fps * t + 0.5) / (long)s->seq_size;
+    if (first_frame_to_keep) *first_frame_to_keep = (int32_t)(gf - (long)ceil(120.0 / s->geo_fps));                                  // screens up to 120 Hz (:544-546)
+    if (first_segment_to_keep) *first_segment_to_keep = (int32_t)(seg - (long)ceil(120.0 / (s->tex_fps * (double)s->seq_size)));
     return UVOL_OK;
 }
 
