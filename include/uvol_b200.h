@@ -54,6 +54,14 @@ enum uvol_texture_format { UVOL_TEX_RGBA32 = 0, UVOL_TEX_ETC1 = 1, UVOL_TEX_BC7 
                              without BPTC: 8 bytes per block (BC1) or the BC4 alpha block + the BC1 block (BC3); ETC1S sources only; lossy (RGB565
                              endpoints), decoded by Pillow's DXT decoder in tests/test_dxt.py */ };
 
+/* getTranscoderFormat (src/lib/KTX2Loader.js:659-689): the target a context with the given capabilities gets for a source.  The options are
+ * tried in the order the reference effectively uses for BOTH source kinds (its two option lists alias one array sorted in place twice,
+ * :648-657, so the UASTC priorities win): ASTC (UASTC sources only) -> BC7 -> ETC2 pair [ETC1, ETC2 RGBA] -> ETC1 (opaque only) -> DXT pair
+ * [BC1, BC3] -> PVRTC, else RGBA32 (:682-687).  An option this library cannot produce for that source (PVRTC; ETC / DXT from UASTC) is passed
+ * over like an unsupported capability, so the result is always a format uvol_transcode_ktx2_batch accepts for the file. */
+enum uvol_gpu_caps { UVOL_CAP_ASTC = 1, UVOL_CAP_BPTC = 2, UVOL_CAP_DXT = 4, UVOL_CAP_ETC2 = 8, UVOL_CAP_ETC1 = 16, UVOL_CAP_PVRTC = 32 };
+int uvol_pick_texture_format(int source_is_uastc, int has_alpha, uint32_t caps);
+
 /* Result of one geometry frame.  Replaces the Draco worker reply
  *   {type:'decode', geometry:{index:{array:Uint32Array(F*3)}, attributes:[{name, array:Float32Array(P*itemSize), itemSize}]}}
  * (src/lib/DRACOLoader.js:449,502,567,584-588); attribute presence follows the semantic lookup at

@@ -370,3 +370,18 @@ def test_native_sequence_open_matches_python_manifest(tmp_path):
     h = ctypes.c_void_p()
     assert L.uvol_open(None, str(bad).encode(), ctypes.byref(h)) < 0 and not h
     assert L.uvol_open(None, str(tmp_path / "missing.json").encode(), ctypes.byref(h)) == -6
+
+
+def test_pick_texture_format_follows_format_options():
+    """uvol_pick_texture_format = getTranscoderFormat (src/lib/KTX2Loader.js:591-689) in the order the reference effectively applies, restricted to
+    what the library produces for the source."""
+    uvp = importlib.import_module("universal-volumetric_b200")
+    L = uvp._native.lib(); N = uvp._native
+    ASTC, BPTC, DXT, ETC2, ETC1, PVRTC = 1, 2, 4, 8, 16, 32
+    pick = lambda uastc, alpha, caps: L.uvol_pick_texture_format(int(uastc), int(alpha), caps)
+    assert pick(True, False, ASTC | BPTC | DXT) == N.TEX_ASTC_4x4 and pick(False, False, ASTC | BPTC | DXT) == N.TEX_BC7          # ASTC is UASTC-only
+    assert pick(True, True, BPTC | DXT) == N.TEX_BC7 and pick(False, True, BPTC | ETC2) == N.TEX_BC7                              # desktop NVIDIA: BC7 for both
+    assert pick(False, False, ETC2 | ETC1 | DXT) == N.TEX_ETC1 and pick(False, True, ETC2 | ETC1 | DXT) == N.TEX_ETC2_RGBA         # mobile: the ETC2 pair
+    assert pick(False, True, ETC1 | DXT) == N.TEX_BC3 and pick(False, False, ETC1 | DXT) == N.TEX_ETC1                            # ETC1 has no alpha form
+    assert pick(False, False, DXT) == N.TEX_BC1 and pick(False, True, DXT) == N.TEX_BC3
+    assert pick(True, False, ETC2 | ETC1 | DXT | PVRTC) == N.TEX_RGBA32 and pick(False, False, PVRTC) == N.TEX_RGBA32 and pick(False, True, 0) == N.TEX_RGBA32

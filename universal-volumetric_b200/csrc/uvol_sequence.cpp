@@ -223,6 +223,16 @@ extern "C" int uvol_sequence_frames_at(const uvol_sequence *s, double t, uint32_
     return UVOL_OK;
 }
 
+// getTranscoderFormat (src/lib/KTX2Loader.js:659-689) over FORMAT_OPTIONS in the order the reference effectively applies (UASTC priorities).
+extern "C" int uvol_pick_texture_format(int source_is_uastc, int has_alpha, uint32_t caps) {
+    if ((caps & UVOL_CAP_ASTC) && source_is_uastc) return UVOL_TEX_ASTC_4x4;                       // basisFormat: [UASTC_4x4] only
+    if (caps & UVOL_CAP_BPTC) return UVOL_TEX_BC7;                                                  // [BC7_M5, BC7_M5]
+    if ((caps & UVOL_CAP_ETC2) && !source_is_uastc) return has_alpha ? UVOL_TEX_ETC2_RGBA : UVOL_TEX_ETC1;      // [ETC1, ETC2]; from UASTC: not produced here
+    if ((caps & UVOL_CAP_ETC1) && !source_is_uastc && !has_alpha) return UVOL_TEX_ETC1;            // [ETC1]: one entry, skipped for alpha (:672)
+    if ((caps & UVOL_CAP_DXT) && !source_is_uastc) return has_alpha ? UVOL_TEX_BC3 : UVOL_TEX_BC1; // [BC1, BC3]
+    return UVOL_TEX_RGBA32;                                                                         // PVRTC is not produced; the reference's own last resort
+}
+
 // fetchBuffers' leaky bucket (src/V2/player.ts:272-323), as manifest.py V2Manifest.fetch_window: for every whole second i of the look-ahead the
 // request grows to min(current + (i + 1) * per-second, last index); what is new since the last request is one contiguous range.
 extern "C" int uvol_sequence_fetch_window(const uvol_sequence *s, double t, int32_t *last_geometry, int32_t *last_segment, double buffer_duration_s, uvol_fetch_plan *plan) {
