@@ -59,6 +59,11 @@ enum uvol_texture_format { UVOL_TEX_RGBA32 = 0, UVOL_TEX_ETC1 = 1, UVOL_TEX_BC7 
  * :648-657, so the UASTC priorities win): ASTC (UASTC sources only) -> BC7 -> ETC2 pair [ETC1, ETC2 RGBA] -> ETC1 (opaque only) -> DXT pair
  * [BC1, BC3] -> PVRTC, else RGBA32 (:682-687).  An option this library cannot produce for that source (PVRTC; ETC / DXT from UASTC) is passed
  * over like an unsupported capability, so the result is always a format uvol_transcode_ktx2_batch accepts for the file. */
+/* The KTX2File getters the reference reads before it picks a target (getWidth / getHeight / getLayers / getLevels / getFaces / getHasAlpha /
+ * isUASTC / isVideo, src/lib/KTX2Loader.js:471-495): container header only, host code, nothing is decoded.  Returns 0 or the status the
+ * transcode call would report for the file. */
+typedef struct uvol_ktx2_info { uint32_t width, height, layers, levels, faces, is_uastc, has_alpha, is_video, supercompression, dfd_transfer, dfd_flags; } uvol_ktx2_info;
+int uvol_ktx2_probe(const uint8_t *data, size_t size, uvol_ktx2_info *out);
 enum uvol_gpu_caps { UVOL_CAP_ASTC = 1, UVOL_CAP_BPTC = 2, UVOL_CAP_DXT = 4, UVOL_CAP_ETC2 = 8, UVOL_CAP_ETC1 = 16, UVOL_CAP_PVRTC = 32 };
 int uvol_pick_texture_format(int source_is_uastc, int has_alpha, uint32_t caps);
 

@@ -148,3 +148,30 @@ def test_mip_chains_on_the_gpu(uv, ctx):
         for L in range(2):
             img, bad = oracle_astc_image(m["data"][L], m["width"], m["height"])
             assert bad == 0 and np.array_equal(img, ue[k][L])
+
+
+def test_ktx2_probe_reports_what_the_transcode_would_see(built):
+    """uvol_ktx2_probe = the KTX2File getters the reference reads before choosing a target (src/lib/KTX2Loader.js:471-495)."""
+    import ctypes
+    import importlib
+    from conftest import golden_ktx2, read
+    from test_etc2 import etc1s_with_alpha
+    uvp = importlib.import_module("universal-volumetric_b200"); L = uvp._native.lib()
+
+    class Info(ctypes.Structure):
+        _fields_ = [(k, ctypes.c_uint32) for k in ("width", "height", "layers", "levels", "faces", "is_uastc", "has_alpha", "is_video", "supercompression", "dfd_transfer", "dfd_flags")]
+
+    def probe(blob):
+        i = Info(); rc = L.uvol_ktx2_probe(blob, ctypes.c_size_t(len(blob)), ctypes.byref(i))
+        return rc, i
+    rc, i = probe(read(golden_ktx2()[0])); o = oracle_ktx2(read(golden_ktx2()[0]))
+    assert rc == 0 and (i.width, i.height, i.layers, i.levels, i.is_uastc, i.has_alpha, i.is_video, i.supercompression) == (o["width"], o["height"], o["layers"], 1, 0, 0, 1, 1)
+    rc, i = probe(uastc_chain()[0])
+    assert rc == 0 and (i.width, i.height, i.layers, i.levels, i.is_uastc) == (64, 64, 2, 3, 1)
+    rc, i = probe(etc1s_with_alpha()[0])
+    assert rc == 0 and (i.layers, i.has_alpha, i.is_uastc) == (2, 1, 0)
+    rc, i = probe(synth.encode_uastc(synth.texture_layers(52, 0, 1, 9)[:, :38, :], mode_mask=synth.UASTC_ALL_MODES, seed=11, has_alpha=True))
+    assert rc == 0 and (i.width, i.height, i.has_alpha, i.is_uastc, i.supercompression) == (52, 38, 1, 1, 0)
+    assert probe(b"x" * 300)[0] == -2 and probe(read(golden_ktx2()[0])[:90])[0] < 0
+    # the chooser on the probe's answer: desktop NVIDIA (bptc + s3tc) -> BC7; a context with ASTC -> lossless ASTC for the UASTC chain
+    assert L.uvol_pick_texture_format(0, 0, 2 | 4) == uvp._native.TEX_BC7 and L.uvol_pick_texture_format(1, 0, 1 | 2) == uvp._native.TEX_ASTC_4x4

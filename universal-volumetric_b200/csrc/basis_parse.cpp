@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <vector>
 #include "uvol_internal.h"
+#include "../../include/uvol_b200.h"
 
 namespace {
 uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
@@ -133,4 +134,24 @@ int uvol_ktx2_split_levels(const uint8_t *b, size_t len, std::vector<std::vector
         out.push_back(std::move(f));
     }
     return (int)levels;
+}
+
+// KTX2File's header getters (src/lib/KTX2Loader.js:471-495) for a caller that picks the target format before transcoding.
+extern "C" int uvol_ktx2_probe(const uint8_t *data, size_t size, uvol_ktx2_info *out) {
+    if (!data || !out) return UVOL_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (size < 104 || memcmp(data, KTX2_ID, 12)) return UVOL_ERR_CORRUPT;
+    out->levels = std::max(1u, rd32(data + 40)); out->faces = rd32(data + 36); out->supercompression = rd32(data + 44);
+    std::vector<std::vector<uint8_t>> lv; std::vector<Ktx2Slice> slices; Ktx2File f; memset(&f, 0, sizeof f);
+    const uint8_t *b = data; size_t n = size;
+    if (out->levels > 1) {          // a mip chain is described by its base level
+        const int L = uvol_ktx2_split_levels(data, size, lv);
+        if (L < 0) return L;
+        if (L > 0) { b = lv[0].data(); n = lv[0].size(); }
+    }
+    const int rc = uvol_ktx2_parse(b, n, 0, f, slices);
+    if (rc) return rc;
+    out->width = f.width; out->height = f.height; out->layers = f.layers; out->is_uastc = f.is_uastc; out->has_alpha = f.has_alpha; out->is_video = f.is_video;
+    out->dfd_transfer = f.dfd_transfer; out->dfd_flags = f.dfd_flags;
+    return UVOL_OK;
 }
