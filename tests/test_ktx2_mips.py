@@ -173,5 +173,8 @@ def test_ktx2_probe_reports_what_the_transcode_would_see(built):
     rc, i = probe(synth.encode_uastc(synth.texture_layers(52, 0, 1, 9)[:, :38, :], mode_mask=synth.UASTC_ALL_MODES, seed=11, has_alpha=True))
     assert rc == 0 and (i.width, i.height, i.has_alpha, i.is_uastc, i.supercompression) == (52, 38, 1, 1, 0)
     assert probe(b"x" * 300)[0] == -2 and probe(read(golden_ktx2()[0])[:90])[0] < 0
+    rc, d = uvp.ktx2_probe(uastc_chain()[0])          # the Python mirror of both calls
+    assert rc == 0 and d["levels"] == 3 and uvp.pick_texture_format(d["is_uastc"], d["has_alpha"], astcSupported=True, bptcSupported=True) == uvp.TEX_ASTC_4x4
+    assert uvp.pick_texture_format(False, True, etc2Supported=True, dxtSupported=True) == uvp.TEX_ETC2_RGBA and uvp.ktx2_probe(b"nope")[0] < 0
     # the chooser on the probe's answer: desktop NVIDIA (bptc + s3tc) -> BC7; a context with ASTC -> lossless ASTC for the UASTC chain
     assert L.uvol_pick_texture_format(0, 0, 2 | 4) == uvp._native.TEX_BC7 and L.uvol_pick_texture_format(1, 0, 1 | 2) == uvp._native.TEX_ASTC_4x4

@@ -36,6 +36,13 @@ class TextureLevel(ctypes.Structure):
     _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("offset", ctypes.c_uint64), ("bytes", ctypes.c_uint64)]
 
 
+class Ktx2Info(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_uint32) for k in ("width", "height", "layers", "levels", "faces", "is_uastc", "has_alpha", "is_video", "supercompression", "dfd_transfer", "dfd_flags")]
+
+
+CAPS = {"astcSupported": 1, "bptcSupported": 2, "dxtSupported": 4, "etc2Supported": 8, "etc1Supported": 16, "pvrtcSupported": 32}      # workerConfig keys (KTX2Loader.js:113-149)
+
+
 class Texture(ctypes.Structure):
     _fields_ = [("status", ctypes.c_int32), ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("layers", ctypes.c_uint32),
                 ("format", ctypes.c_uint32), ("has_alpha", ctypes.c_uint32), ("dfd_transfer", ctypes.c_uint32), ("dfd_flags", ctypes.c_uint32),

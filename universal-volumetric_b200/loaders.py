@@ -162,6 +162,22 @@ class DRACOLoader:
         return res
 
 
+def ktx2_probe(blob):
+    """The KTX2File getters (src/lib/KTX2Loader.js:471-495) of one .ktx2, from its header alone (host code, no GPU): dict, or None with a status."""
+    i = N.Ktx2Info(); b = bytes(blob)
+    rc = N.lib().uvol_ktx2_probe(b, ctypes.c_size_t(len(b)), ctypes.byref(i))
+    return (rc, None) if rc else (0, {k: int(getattr(i, k)) for k, _ in N.Ktx2Info._fields_})
+
+
+def pick_texture_format(is_uastc, has_alpha, **config):
+    """getTranscoderFormat (src/lib/KTX2Loader.js:659-689) for a context described by the reference's own workerConfig keys, e.g.
+    pick_texture_format(True, False, astcSupported=True, bptcSupported=True) -> TEX_ASTC_4x4."""
+    caps = 0
+    for k, v in config.items():
+        caps |= N.CAPS[k] if v else 0
+    return int(N.lib().uvol_pick_texture_format(int(bool(is_uastc)), int(bool(has_alpha)), caps))
+
+
 class KTX2Loader:
     """Batch replacement of the reference's Basis worker pool (<=4 workers FIFO, WorkerPool.js:5-102)."""
 
